@@ -1,0 +1,163 @@
+/* pcm_b200 — C ABI of the B200-native hot path of the Physics-Based-Climate-Model emulator.
+ *
+ * The reference (/root/reference) is pure Python on stock torch.nn modules and defines NO native
+ * interface; these entry points are what its modules' forward/backward bodies
+ * bind instead of the ATen calls they make today.  Each declaration cites the reference lines it
+ * replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer unless named host_*; `stream` is a cudaStream_t;
+ *   - activations are NHWC ("channels last") with the channel count padded to a multiple of 8,
+ *     stored as `dtype` (PCM_F32 or PCM_BF16); statistics, gate maps, cell state, weight
+ *     gradients and optimizer state are always fp32;
+ *   - an activation view is (ptr, nstride, pstride): element (n, h, w, c) lives at
+ *     ptr[n*nstride + (h*W + w)*pstride + c]  (lets kernels read/write slices of concat buffers
+ *     and time-strided image sequences without copies);
+ *   - functions return PCM_OK or an error code and never abort; pcm_last_error() gives the text;
+ *   - nothing allocates or synchronises: every call is CUDA-Graph capturable.
+ *   - "accumulates" means += into a buffer the caller zeroed (weight-gradient buffers).
+ */
+#ifndef PCM_B200_H_
+#define PCM_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCM_OK 0
+#define PCM_ERR_INVALID 1
+#define PCM_ERR_CUDA 2
+#define PCM_F32 0
+#define PCM_BF16 1
+
+typedef void* pcm_stream_t; /* cudaStream_t */
+
+#if defined(PCM_BUILDING)
+#define PCM_API __attribute__((visibility("default")))
+#else
+#define PCM_API
+#endif
+
+PCM_API const char* pcm_last_error(void);
+PCM_API int pcm_version(void);
+
+/* ---- layout staging ------------------------------------------------------------------------
+ * Module boundary tensors are NCHW fp32 (reference: every nn.Module in src/*.py). */
+PCM_API int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp, int dtype, pcm_stream_t s);
+PCM_API int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, int W, int Cp, int dtype, pcm_stream_t s);
+/* main_final.py:186-216 (seasonal channels): x5 (N,5,H,W) + month index (N) -> NHWC with
+ * ch5 = sin(2 pi m/12), ch6 = cos(2 pi m/12), ch7.. = 0. */
+PCM_API int pcm_season_embed_stage(const float* x5, const int* month, void* y, int N, int H, int W, int Cp, int dtype,
+                           pcm_stream_t s);
+
+/* ---- weight packing: out[t][o][i] = (o<O && i<I) ? w[o*so + i*si + t*st] : 0, stored as dtype */
+PCM_API int pcm_pack_weight(const float* w, long long so, long long si, long long st, int O, int I, int taps, int Op,
+                    int Ip, void* out, int dtype, pcm_stream_t s);
+
+/* ---- convolution family (nn.Conv2d / nn.ConvTranspose2d call sites: src/convlstm.py:9,13;
+ * src/unet.py:36,38,63; src/cnn_transformer.py:10,12,36,38; src/models.py:47,50,57,90,108).
+ * "gather" form: dst(n,hd,wd,dc) = sum_taps sum_sc src(n,hs,ws,sc) * wk[tap][dc][sc] (+bias)(relu)
+ *   mode 0 (conv forward / convT data-grad): hs = hd*stride - pad + kh
+ *   mode 1 (conv data-grad / convT forward): hs = (hd + pad - kh)/stride when divisible
+ * wk is packed [KH*KW][Dc][Sc] in `dtype`; dst is `dtype`, or fp32 when dst_f32. */
+PCM_API int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int Hs, int Ws, int Sc,
+                    void* dst, long long dst_ns, int dst_ps, int Hd, int Wd, int Dc,
+                    const void* wk, const float* bias, int N, int KH, int KW, int stride, int pad, int mode,
+                    int dst_f32, int accumulate, int relu, int dtype, pcm_stream_t s);
+/* weight gradient: dw[ac*sa + bc*sb + tap*st] += sum_{n,ha,wa} A(n,ha,wa,ac) * B(n,hb,wb,bc),
+ * hb = ha*stride - pad + kh; only ac < Ca_real, bc < Cb_real are written.  fp32, accumulates. */
+PCM_API int pcm_conv_wgrad(const void* A, long long a_ns, int a_ps, int Ha, int Wa, int Ca, int Ca_real,
+                   const void* B, long long b_ns, int b_ps, int Hb, int Wb, int Cb, int Cb_real,
+                   float* dw, long long sa, long long sb, long long st, int N, int KH, int KW, int stride, int pad,
+                   int dtype, pcm_stream_t s);
+/* per-channel sum over pixels: out[c] += sum_{n,p} x(n,p,c) (bias gradients), or, when per_image,
+ * out[n][c] += sum_p x(n,p,c) (SE squeeze); c < C_real */
+PCM_API int pcm_channel_sum(const void* x, long long ns, int ps, int N, int P, int C, int C_real, float* out,
+                            int per_image, int dtype, pcm_stream_t s);
+
+/* ---- ConvBlock tail: GroupNorm(8)+SiLU, SE, SpatialGate (src/unet.py:6-29, 35-49) ------------ */
+/* stats[n][g][2] += (sum, sum of squares) of x over group g of image n (caller zeroes stats) */
+PCM_API int pcm_gn_stats(const void* x, float* stats, int N, int P, int C, int G, int dtype, pcm_stream_t s);
+/* y = silu(gamma*(x-mu)*rstd+beta); pool[n][c] += sum_p y (nullable) */
+PCM_API int pcm_gn_silu_fwd(const void* x, const float* stats, const float* gamma, const float* beta, void* y, float* pool,
+                    int N, int P, int C, int G, float eps, int dtype, pcm_stream_t s);
+/* SE excitation + channel statistics of u = a*se: se[n][c] = sigmoid(W2 relu(W1 pool/P));
+ * cmap[n][p] = (mean_c u, max_c u).  w1 == NULL means "no excitation" (se = 1). */
+PCM_API int pcm_se_chanstat_fwd(const void* a, const float* pool, const float* w1, const float* w2, float* se, float* hid,
+                        float* cmap, int N, int P, int C, int Cr, int dtype, pcm_stream_t s);
+/* out = x*scale[n][c] + add[n][c] (scale/add nullable) — stand-alone SEBlock (src/unet.py:16-17) */
+PCM_API int pcm_scale_channels(const void* x, const float* scale, const float* add, void* out, int N, int P, int C,
+                               int dtype, pcm_stream_t s);
+/* gate[n][p] = sigmoid(conv7x7(cmap)); out = a*se*gate */
+PCM_API int pcm_spatial_gate_fwd(const void* a, const float* se, const float* cmap, const float* wsp, float* gate, void* out,
+                         int N, int H, int W, int C, int dtype, pcm_stream_t s);
+/* backward of out = a*se*gate:  dq[n][p] = (sum_c dout*a*se) * gate*(1-gate) */
+PCM_API int pcm_spatial_gate_bwd_dq(const void* dout, const void* a, const float* se, const float* gate, float* dq, int N,
+                            int P, int C, int dtype, pcm_stream_t s);
+/* dwsp[k][dy][dx] += sum dq[p]*cmap_k[p+off]  (98 values) */
+PCM_API int pcm_spatial_gate_bwd_dw(const float* dq, const float* cmap, float* dwsp, int N, int H, int W, pcm_stream_t s);
+/* da = (dout*gate + dmean/C + dmax*tie)*se ; dse[n][c] += sum_p du*a */
+PCM_API int pcm_spatial_gate_bwd_da(const void* dout, const void* a, const float* se, const float* gate, const float* cmap,
+                            const float* dq, const float* wsp, void* da, float* dse, int N, int H, int W, int C,
+                            int dtype, pcm_stream_t s);
+/* SE backward: dpool[n][c] (already divided by P) ; dw1, dw2 accumulate */
+PCM_API int pcm_se_bwd(const float* dse, const float* se, const float* hid, const float* pool, const float* w1,
+               const float* w2, float* dpool, float* dw1, float* dw2, int N, int P, int C, int Cr, pcm_stream_t s);
+/* GroupNorm+SiLU backward, pass 1: with da_total = da + dpool[n][c] (dpool nullable):
+ * gsum[n][g][2] += (sum dxhat, sum dxhat*xhat); dgamma[c] += sum dz*xhat; dbeta[c] += sum dz */
+PCM_API int pcm_gn_silu_bwd_reduce(const void* da, const float* dpool, const void* x, const float* stats,
+                           const float* gamma, const float* beta, float* gsum, float* dgamma, float* dbeta, int N,
+                           int P, int C, int G, float eps, int dtype, pcm_stream_t s);
+/* pass 2: dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) */
+PCM_API int pcm_gn_silu_bwd_apply(const void* da, const float* dpool, const void* x, const float* stats,
+                          const float* gamma, const float* beta, const float* gsum, void* dx, int N, int P, int C,
+                          int G, float eps, int dtype, pcm_stream_t s);
+
+/* ---- pooling / skips (src/unet.py:54,57; src/unet_convlstm_attention.py:21,24,91-93) ----------- */
+PCM_API int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, pcm_stream_t s);
+/* dx(n,h,w,c) = [first max of its 2x2 window] * dy(n,h/2,w/2,c) + dskip(n/T, h, w, c)/T
+ * (dy nullable; dskip nullable, an activation view with channel offset applied by the caller) */
+PCM_API int pcm_maxpool2_bwd_skip(const void* x, const void* dy, const void* dskip, long long dskip_ns, int dskip_ps,
+                          void* dx, int N, int H, int W, int C, int T, int dtype, pcm_stream_t s);
+/* dst(b,p,c) = mean_t src(b*T+t, p, c)  (dst is a view into the decoder's concat buffer) */
+PCM_API int pcm_time_mean(const void* src, void* dst, long long dst_ns, int dst_ps, int B, int T, int P, int C, int dtype,
+                  pcm_stream_t s);
+
+/* ---- ConvLSTM cell (src/convlstm.py:11-19) ----------------------------------------------------
+ * gates: fp32 [M][4*Ch] pre-activations in order i,f,o,g (bias already added); c_prev nullable (=0).
+ * acts: activated gates (dtype) saved for backward; c: fp32 [M][Ch]; h: dtype [M][Ch]. */
+PCM_API int pcm_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c, void* h, int M, int Ch,
+                      int dtype, pcm_stream_t s);
+/* dh = dh_a + dh_b (either nullable); dc_in nullable.  dgates: dtype [M][4*Ch]; dc_prev fp32 */
+PCM_API int pcm_lstm_cell_bwd(const void* dh_a, const void* dh_b, const float* dc_in, const void* acts, const float* c_prev,
+                      const float* c, void* dgates, float* dc_prev, int M, int Ch, int dtype, pcm_stream_t s);
+
+/* ---- head (1x1 conv, src/unet_convlstm_attention.py:56,104) and loss (main_final.py:544,559) ---- */
+PCM_API int pcm_head_fwd(const void* x, const float* w, const float* b, float* out_nchw, int N, int P, int C, int K,
+                 int dtype, pcm_stream_t s);
+PCM_API int pcm_head_bwd(const float* dout_nchw, const void* x, const float* w, void* dx, float* dw, float* db, int N, int P,
+                 int C, int K, int dtype, pcm_stream_t s);
+/* loss[0] += mean((a-b)^2) (caller zeroes) */
+PCM_API int pcm_mse_fwd(const float* a, const float* b, float* loss, long long n, pcm_stream_t s);
+/* da = 2*(a-b)/n * gscale[0] */
+PCM_API int pcm_mse_bwd(const float* a, const float* b, const float* gscale, float* da, long long n, pcm_stream_t s);
+
+/* ---- optimizer (torch.optim.Adam as configured at main_final.py:737-747) ------------------------
+ * state[0] = step count (float), updated on device so a captured graph advances it. */
+PCM_API int pcm_adam_step(float* p, const float* g, float* m, float* v, float* state, long long n, float lr, float b1,
+                  float b2, float eps, float wd, float grad_scale, pcm_stream_t s);
+
+/* ---- cos(lat)-weighted metric (src/utils_final.py:282-302, main_final.py:616-631) ----------------
+ * pred/truth: fp32 [T][V][Y][X]; w_lat: fp64 [Y]; partial: fp64 workspace [V][Y][X][5] (zeroed by
+ * the call); out: fp64 [V][3] = monthly_rmse, time_mean_rmse, time_std_mae.
+ * pcm_metric_partial accumulates the per-pixel time sums (shardable over T: partials add);
+ * pcm_metric_finalize reduces them with the latitude weights. */
+PCM_API int pcm_metric_partial(const float* pred, const float* truth, double* partial, int T, int V, int Y, int X,
+                       int zero_first, pcm_stream_t s);
+PCM_API int pcm_metric_finalize(const double* partial, const double* w_lat, double* out, long long T_total, int V, int Y,
+                        int X, pcm_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCM_B200_H_ */

@@ -1,0 +1,95 @@
+// Shared device/host helpers for the pcm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pcm_b200.h"
+
+namespace pcm {
+
+// ---- error plumbing: the C ABI never aborts; it returns a status and keeps a message ---------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define PCM_REQUIRE(cond, ...)                  \
+  do {                                          \
+    if (!(cond)) {                              \
+      pcm::set_error(__VA_ARGS__);              \
+      return PCM_ERR_INVALID;                   \
+    }                                           \
+  } while (0)
+
+// dtype dispatch for activation storage: 0 = f32, 1 = bf16
+#define PCM_DISPATCH_DTYPE(dtype, T, ...)                          \
+  do {                                                             \
+    if ((dtype) == PCM_F32) { using T = float; __VA_ARGS__; }      \
+    else if ((dtype) == PCM_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { pcm::set_error("bad dtype %d", (int)(dtype)); return PCM_ERR_INVALID; } \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- 8-channel vector access (all channel counts are padded to a multiple of 8) --------------
+__device__ __forceinline__ void load8(const float* __restrict__ p, float v[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ p, float v[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float v[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float v[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+// value as the storage type would round it (so saved/recomputed quantities agree bit-for-bit)
+template <typename T> __device__ __forceinline__ float round_to(float x) { return to_f(from_f<T>(x)); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ---- reductions ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum; result valid in thread 0 (smem: >= 32 entries of T)
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem[threadIdx.x] : T(0);
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+
+}  // namespace pcm

@@ -1,0 +1,305 @@
+// SIMT convolution family (gather form), weight gradient and weight packing.
+// These are the general-shape kernels (any K, stride, channel count multiple of 8); the
+// tensor-core implicit-GEMM path for the 3x3/stride-1 layers lives in conv_tc.cu.
+#include "common.cuh"
+
+namespace pcm {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: out[t][o][i] = w[o*so + i*si + t*st] (zero padded)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, long long so, long long si, long long st, int O, int I,
+                                   int taps, int Op, int Ip, T* __restrict__ out) {
+  const long long total = (long long)taps * Op * Ip;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % Ip);
+    const int o = (int)((idx / Ip) % Op);
+    const int t = (int)(idx / ((long long)Ip * Op));
+    float v = 0.f;
+    if (o < O && i < I) v = __ldg(w + o * so + i * si + t * st);
+    out[idx] = from_f<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather convolution: one thread = one destination pixel x 8 destination channels
+// ------------------------------------------------------------------------------------------------
+struct GatherGeom {
+  long long src_ns, dst_ns;
+  int src_ps, dst_ps;
+  int Hs, Ws, Sc, Hd, Wd, Dc;
+  int N, KH, KW, stride, pad, mode;
+};
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(128)
+conv_gather_kernel(const T* __restrict__ src, TO* __restrict__ dst, const T* __restrict__ wk,
+                   const float* __restrict__ bias, GatherGeom g, int accumulate, int relu) {
+  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long npix = (long long)g.N * g.Hd * g.Wd;
+  if (pix >= npix) return;
+  const int dc0 = blockIdx.y * 8;
+  const int wd = (int)(pix % g.Wd);
+  const int hd = (int)((pix / g.Wd) % g.Hd);
+  const int n = (int)(pix / ((long long)g.Wd * g.Hd));
+
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+
+  const T* src_n = src + n * g.src_ns;
+  for (int kh = 0; kh < g.KH; ++kh) {
+    int hs;
+    if (g.mode == 0) {
+      hs = hd * g.stride - g.pad + kh;
+    } else {
+      const int t = hd + g.pad - kh;
+      if (t < 0 || (t % g.stride) != 0) continue;
+      hs = t / g.stride;
+    }
+    if (hs < 0 || hs >= g.Hs) continue;
+    for (int kw = 0; kw < g.KW; ++kw) {
+      int ws;
+      if (g.mode == 0) {
+        ws = wd * g.stride - g.pad + kw;
+      } else {
+        const int t = wd + g.pad - kw;
+        if (t < 0 || (t % g.stride) != 0) continue;
+        ws = t / g.stride;
+      }
+      if (ws < 0 || ws >= g.Ws) continue;
+      const T* sp = src_n + ((long long)hs * g.Ws + ws) * g.src_ps;
+      const T* wp = wk + ((long long)(kh * g.KW + kw) * g.Dc + dc0) * g.Sc;
+      for (int sc = 0; sc < g.Sc; sc += 8) {
+        float xv[8];
+        load8(sp + sc, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float wv[8];
+          load8(wp + (long long)j * g.Sc + sc, wv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[j] = fmaf(xv[k], wv[k], acc[j]);
+        }
+      }
+    }
+  }
+  if (bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(bias + dc0 + j);
+  }
+  TO* dp = dst + n * g.dst_ns + ((long long)hd * g.Wd + wd) * g.dst_ps + dc0;
+  if (accumulate) {
+    float old[8];
+    load8(dp, old);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += old[j];
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+  }
+  store8(dp, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient.  Thread = (8 A-channels x 8 B-channels) tile for one tap, looping over the
+// A-grid pixels of its chunk; `lanes` threads share a tile and are reduced in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct WgradGeom {
+  long long a_ns, b_ns, sa, sb, st;
+  int a_ps, b_ps;
+  int Ha, Wa, Ca, Ca_real, Hb, Wb, Cb, Cb_real;
+  int N, KH, KW, stride, pad;
+  int tiles_a, tiles_b, tiles, lanes, tiles_per_block;
+  long long chunk;   // A-pixels per block
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ dw, WgradGeom g) {
+  extern __shared__ float red[];   // [tiles_per_block][64] when lanes > 1
+  const int tap = blockIdx.z;
+  const int kh = tap / g.KW, kw = tap % g.KW;
+  const int tile_local = threadIdx.x % g.tiles_per_block;
+  const int lane = threadIdx.x / g.tiles_per_block;
+  const int tile = blockIdx.y * g.tiles_per_block + tile_local;
+  const bool active = (tile < g.tiles) && (lane < g.lanes);
+  const int ta = tile / g.tiles_b, tb = tile % g.tiles_b;
+
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+
+  if (g.lanes > 1) {
+    for (int i = threadIdx.x; i < g.tiles_per_block * 64; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+  }
+
+  if (active) {
+    const long long npix = (long long)g.N * g.Ha * g.Wa;
+    const long long p0 = blockIdx.x * g.chunk;
+    const long long p1 = min(npix, p0 + g.chunk);
+    for (long long p = p0 + lane; p < p1; p += g.lanes) {
+      const int wa = (int)(p % g.Wa);
+      const int ha = (int)((p / g.Wa) % g.Ha);
+      const int n = (int)(p / ((long long)g.Wa * g.Ha));
+      const int hb = ha * g.stride - g.pad + kh;
+      const int wb = wa * g.stride - g.pad + kw;
+      if (hb < 0 || hb >= g.Hb || wb < 0 || wb >= g.Wb) continue;
+      float av[8], bv[8];
+      load8(A + n * g.a_ns + ((long long)ha * g.Wa + wa) * g.a_ps + ta * 8, av);
+      load8(B + n * g.b_ns + ((long long)hb * g.Wb + wb) * g.b_ps + tb * 8, bv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fmaf(av[i], bv[j], acc[i * 8 + j]);
+    }
+  }
+  if (g.lanes > 1) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) atomicAdd(&red[tile_local * 64 + i], acc[i]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < g.tiles_per_block * 64; idx += blockDim.x) {
+      const int tl = idx / 64, e = idx % 64;
+      const int t2 = blockIdx.y * g.tiles_per_block + tl;
+      if (t2 >= g.tiles) continue;
+      const int ac = (t2 / g.tiles_b) * 8 + e / 8, bc = (t2 % g.tiles_b) * 8 + e % 8;
+      if (ac < g.Ca_real && bc < g.Cb_real) atomicAdd(dw + ac * g.sa + bc * g.sb + tap * g.st, red[idx]);
+    }
+  } else if (active) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const int ac = ta * 8 + i / 8, bc = tb * 8 + i % 8;
+      if (ac < g.Ca_real && bc < g.Cb_real) atomicAdd(dw + ac * g.sa + bc * g.sb + tap * g.st, acc[i]);
+    }
+  }
+}
+
+// per-channel sum over pixels
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const T* __restrict__ x, long long ns, int ps, int N, int P, int C, int C_real,
+                   float* __restrict__ out, int per_image) {
+  extern __shared__ float sacc[];   // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cv = C / 8;
+  // per_image: blockIdx.y = image, the x-grid covers that image's pixels only
+  const int n_fixed = per_image ? blockIdx.y : -1;
+  const long long total = per_image ? (long long)P * cv : (long long)N * P * cv;
+  if (per_image) out += (long long)n_fixed * C_real;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  int my_cb = -1;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(v % cv);
+    const long long pix = v / cv;
+    const int n = per_image ? n_fixed : (int)(pix / P);
+    const int p = (int)(pix % P);
+    if (cb != my_cb) {
+      if (my_cb >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[my_cb * 8 + j], acc[j]); acc[j] = 0.f; }
+      }
+      my_cb = cb;
+    }
+    float xv[8];
+    load8(x + n * ns + (long long)p * ps + cb * 8, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += xv[j];
+  }
+  if (my_cb >= 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sacc[my_cb * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C_real; i += blockDim.x) atomicAdd(out + i, sacc[i]);
+}
+
+}  // namespace pcm
+
+using namespace pcm;
+
+extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long long st, int O, int I, int taps,
+                               int Op, int Ip, void* out, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(O <= Op && I <= Ip && taps > 0, "pack_weight: bad sizes");
+  const long long total = (long long)taps * Op * Ip;
+  const int blocks = (int)min((long long)1184, (total + 255) / 256);
+  PCM_DISPATCH_DTYPE(dtype, T, (pack_weight_kernel<T><<<blocks, 256, 0, (cudaStream_t)s>>>(
+                                   w, so, si, st, O, I, taps, Op, Ip, (T*)out)));
+  return check_launch("pack_weight");
+}
+
+extern "C" int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int Hs, int Ws, int Sc, void* dst,
+                               long long dst_ns, int dst_ps, int Hd, int Wd, int Dc, const void* wk,
+                               const float* bias, int N, int KH, int KW, int stride, int pad, int mode, int dst_f32,
+                               int accumulate, int relu, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(Sc % 8 == 0 && Dc % 8 == 0, "conv_gather: channels must be multiples of 8 (Sc=%d Dc=%d)", Sc, Dc);
+  PCM_REQUIRE(src_ps % 8 == 0 && dst_ps % 8 == 0, "conv_gather: pixel strides must be multiples of 8");
+  PCM_REQUIRE(mode == 0 || mode == 1, "conv_gather: bad mode");
+  if (N == 0) return PCM_OK;
+  GatherGeom g{src_ns, dst_ns, src_ps, dst_ps, Hs, Ws, Sc, Hd, Wd, Dc, N, KH, KW, stride, pad, mode};
+  const long long npix = (long long)N * Hd * Wd;
+  dim3 grid(ceil_div(npix, 128), Dc / 8);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dst_f32) {
+    PCM_DISPATCH_DTYPE(dtype, T, (conv_gather_kernel<T, float><<<grid, 128, 0, st>>>(
+                                     (const T*)src, (float*)dst, (const T*)wk, bias, g, accumulate, relu)));
+  } else {
+    PCM_DISPATCH_DTYPE(dtype, T, (conv_gather_kernel<T, T><<<grid, 128, 0, st>>>(
+                                     (const T*)src, (T*)dst, (const T*)wk, bias, g, accumulate, relu)));
+  }
+  return check_launch("conv_gather");
+}
+
+extern "C" int pcm_conv_wgrad(const void* A, long long a_ns, int a_ps, int Ha, int Wa, int Ca, int Ca_real,
+                              const void* B, long long b_ns, int b_ps, int Hb, int Wb, int Cb, int Cb_real,
+                              float* dw, long long sa, long long sb, long long st, int N, int KH, int KW, int stride,
+                              int pad, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "conv_wgrad: channels must be multiples of 8");
+  if (N == 0) return PCM_OK;
+  WgradGeom g;
+  g.a_ns = a_ns; g.b_ns = b_ns; g.sa = sa; g.sb = sb; g.st = st; g.a_ps = a_ps; g.b_ps = b_ps;
+  g.Ha = Ha; g.Wa = Wa; g.Ca = Ca; g.Ca_real = Ca_real; g.Hb = Hb; g.Wb = Wb; g.Cb = Cb; g.Cb_real = Cb_real;
+  g.N = N; g.KH = KH; g.KW = KW; g.stride = stride; g.pad = pad;
+  g.tiles_a = Ca / 8; g.tiles_b = Cb / 8; g.tiles = g.tiles_a * g.tiles_b;
+  g.tiles_per_block = g.tiles < 256 ? g.tiles : 256;
+  g.lanes = 256 / g.tiles_per_block;
+  const int grid_y = ceil_div(g.tiles, g.tiles_per_block);
+  const long long npix = (long long)N * Ha * Wa;
+  // aim for ~4 waves of blocks over 148 SMs, but at least 64 pixels per lane
+  long long want_chunks = (4 * 148 + grid_y * KH * KW - 1) / (grid_y * KH * KW);
+  if (want_chunks < 1) want_chunks = 1;
+  long long chunk = (npix + want_chunks - 1) / want_chunks;
+  const long long min_chunk = 64LL * g.lanes;
+  if (chunk < min_chunk) chunk = min_chunk;
+  g.chunk = chunk;
+  dim3 grid(ceil_div(npix, chunk), grid_y, KH * KW);
+  const size_t smem = g.lanes > 1 ? (size_t)g.tiles_per_block * 64 * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    PCM_DISPATCH_DTYPE(dtype, T, cudaFuncSetAttribute(conv_wgrad_kernel<T>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  PCM_DISPATCH_DTYPE(dtype, T, (conv_wgrad_kernel<T><<<grid, 256, smem, (cudaStream_t)s>>>(
+                                   (const T*)A, (const T*)B, dw, g)));
+  return check_launch("conv_wgrad");
+}
+
+extern "C" int pcm_channel_sum(const void* x, long long ns, int ps, int N, int P, int C, int C_real, float* out,
+                               int per_image, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(C % 8 == 0, "channel_sum: C must be a multiple of 8");
+  if (N == 0) return PCM_OK;
+  const long long total = per_image ? (long long)P * (C / 8) : (long long)N * P * (C / 8);
+  int bx = (int)min((long long)592, (total + 255) / 256);
+  if (per_image) bx = (int)min((long long)max(1, 592 / N), (total + 1023) / 1024);
+  dim3 grid(bx, per_image ? N : 1);
+  PCM_DISPATCH_DTYPE(dtype, T, (channel_sum_kernel<T><<<grid, 256, C * sizeof(float), (cudaStream_t)s>>>(
+                                   (const T*)x, ns, ps, N, P, C, C_real, out, per_image)));
+  return check_launch("channel_sum");
+}

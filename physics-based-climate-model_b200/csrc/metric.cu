@@ -1,0 +1,86 @@
+// cos(lat)-area-weighted metric triplet (src/utils_final.py:282-302, main_final.py:616-631):
+// monthly RMSE, time-mean RMSE and time-std MAE per variable, in one pass over pred/truth.
+// Pass 1 (HBM-bound, reads 2*T*V*Y*X*4 bytes once): per pixel time sums of p, p^2, t, t^2, (p-t)^2
+// accumulated in fp64 (tas ~ 273 K: fp32 sums of squares would cancel catastrophically in the
+// variance).  Pass 2: per-pixel terms -> latitude-weighted warp-shuffle reduction.
+#include "common.cuh"
+
+namespace pcm {
+
+// grid: (ceil(V*Y*X / 256), time_chunks)
+__global__ void __launch_bounds__(256)
+metric_partial_kernel(const float* __restrict__ pred, const float* __restrict__ truth, double* __restrict__ partial,
+                      int T, int VYX) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= VYX) return;
+  const int per = (T + gridDim.y - 1) / gridDim.y;
+  const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
+  double sp = 0, spp = 0, st = 0, stt = 0, sd = 0;
+  for (int t = t0; t < t1; ++t) {
+    const double p = (double)__ldg(pred + (long long)t * VYX + pix);
+    const double q = (double)__ldg(truth + (long long)t * VYX + pix);
+    const double d = p - q;
+    sp += p; st += q;
+    spp = fma(p, p, spp);
+    stt = fma(q, q, stt);
+    sd = fma(d, d, sd);
+  }
+  double* o = partial + (long long)pix * 5;
+  atomicAdd(o + 0, sp); atomicAdd(o + 1, spp); atomicAdd(o + 2, st); atomicAdd(o + 3, stt); atomicAdd(o + 4, sd);
+}
+
+// one block per variable; out[v][0..2]
+__global__ void __launch_bounds__(256)
+metric_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ w_lat, double* __restrict__ out,
+                       double Tn, int Y, int X) {
+  __shared__ double red[32];
+  const int v = blockIdx.x;
+  double a0 = 0, a1 = 0, a2 = 0, wsum = 0;
+  for (int i = threadIdx.x; i < Y * X; i += blockDim.x) {
+    const double w = w_lat[i / X];
+    const double* q = partial + ((long long)v * Y * X + i) * 5;
+    const double mp = q[0] / Tn, mt = q[2] / Tn;
+    const double vp = fmax(q[1] / Tn - mp * mp, 0.0), vt = fmax(q[3] / Tn - mt * mt, 0.0);
+    a0 += w * q[4] / Tn;                       // time-mean of (p-t)^2 at this pixel
+    a1 += w * (mp - mt) * (mp - mt);
+    a2 += w * fabs(sqrt(vp) - sqrt(vt));
+    wsum += w;
+  }
+  a0 = block_sum(a0, red);
+  a1 = block_sum(a1, red);
+  a2 = block_sum(a2, red);
+  wsum = block_sum(wsum, red);
+  if (threadIdx.x == 0) {
+    out[v * 3 + 0] = sqrt(a0 / wsum);
+    out[v * 3 + 1] = sqrt(a1 / wsum);
+    out[v * 3 + 2] = a2 / wsum;
+  }
+}
+
+}  // namespace pcm
+
+using namespace pcm;
+
+extern "C" int pcm_metric_partial(const float* pred, const float* truth, double* partial, int T, int V, int Y, int X,
+                                  int zero_first, pcm_stream_t s) {
+  const int VYX = V * Y * X;
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(partial, 0, (size_t)VYX * 5 * sizeof(double), (cudaStream_t)s);
+    if (e != cudaSuccess) { set_error("metric_partial memset: %s", cudaGetErrorString(e)); return PCM_ERR_CUDA; }
+  }
+  if (T == 0) return PCM_OK;
+  const int gx = ceil_div(VYX, 256);
+  int chunks = (4 * 148 + gx - 1) / gx;
+  if (chunks > (T + 15) / 16) chunks = (T + 15) / 16;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(gx, chunks);
+  metric_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(pred, truth, partial, T, VYX);
+  return check_launch("metric_partial");
+}
+
+extern "C" int pcm_metric_finalize(const double* partial, const double* w_lat, double* out, long long T_total, int V,
+                                   int Y, int X, pcm_stream_t s) {
+  PCM_REQUIRE(T_total > 0, "metric_finalize: T_total must be positive");
+  metric_finalize_kernel<<<V, 256, 0, (cudaStream_t)s>>>(partial, w_lat, out, (double)T_total, Y, X);
+  return check_launch("metric_finalize");
+}

@@ -1,0 +1,491 @@
+// Layout staging, pooling / skip aggregation, ConvLSTM cell pointwise, head + loss, Adam.
+// All HBM-bound: 16-byte vector accesses, grids sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace pcm {
+
+constexpr int kGridCap = 148 * 8;
+
+// ---- layout --------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC T (pad channels with 0). One thread = one pixel x 8 output channels; reads
+// are coalesced across pixels (w fastest), writes are 16 B per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int P, int Cp,
+                    const int* __restrict__ month) {
+  const int cv = Cp / 8;
+  const long long total = (long long)N * cv * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % P);
+    const int cb = (int)((idx / P) % cv);
+    const int n = (int)(idx / ((long long)P * cv));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      v[j] = (c < C) ? __ldg(x + ((long long)n * C + c) * P + p) : 0.f;
+    }
+    if (month != nullptr) {   // seasonal channels C, C+1 (main_final.py:188-196)
+      const float ang = 6.283185307179586f * (float)__ldg(month + n) / 12.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cb * 8 + j;
+        if (c == C) v[j] = sinf(ang);
+        if (c == C + 1) v[j] = cosf(ang);
+      }
+    }
+    store8(y + ((long long)n * P + p) * Cp + cb * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int P, int Cp) {
+  const int cv = Cp / 8;
+  const long long total = (long long)N * cv * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % P);
+    const int cb = (int)((idx / P) % cv);
+    const int n = (int)(idx / ((long long)P * cv));
+    float v[8];
+    load8(x + ((long long)n * P + p) * Cp + cb * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      if (c < C) y[((long long)n * C + c) * P + p] = v[j];
+    }
+  }
+}
+
+// ---- pooling / skips -------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, cv = C / 8;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(idx % cv);
+    long long r = idx / cv;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const T* xp = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cb * 8;
+    float a[8], b[8], c[8], d[8];
+    load8(xp, a); load8(xp + C, b); load8(xp + (long long)W * C, c); load8(xp + (long long)W * C + C, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
+    store8(y + idx * 8, a);
+  }
+}
+
+// dx = [x is the FIRST max of its window (scan order)] * dy + dskip/T
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ dskip,
+                         long long dskip_ns, int dskip_ps, T* __restrict__ dx, int N, int H, int W, int C, int Tn) {
+  const int Ho = H / 2, Wo = W / 2, cv = C / 8;
+  const float invT = 1.f / (float)Tn;
+  const long long total = (long long)N * H * W * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(idx % cv);
+    long long r = idx / cv;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = 0.f;
+    const int ho = h >> 1, wo = w >> 1;
+    if (dy != nullptr && ho < Ho && wo < Wo) {
+      const T* xp = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cb * 8;
+      float q[4][8], g[8];
+      load8(xp, q[0]); load8(xp + C, q[1]); load8(xp + (long long)W * C, q[2]); load8(xp + (long long)W * C + C, q[3]);
+      load8(dy + (((long long)n * Ho + ho) * Wo + wo) * C + cb * 8, g);
+      const int me = (h & 1) * 2 + (w & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int arg = 0;
+        float m = q[0][j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (q[k][j] > m) { m = q[k][j]; arg = k; }
+        out[j] = (arg == me) ? g[j] : 0.f;
+      }
+    }
+    if (dskip != nullptr) {
+      float sk[8];
+      load8(dskip + (long long)(n / Tn) * dskip_ns + ((long long)h * W + w) * dskip_ps + cb * 8, sk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] = fmaf(sk[j], invT, out[j]);
+    }
+    store8(dx + idx * 8, out);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+time_mean_kernel(const T* __restrict__ src, T* __restrict__ dst, long long dst_ns, int dst_ps, int B, int Tn, int P,
+                 int C) {
+  const int cv = C / 8;
+  const float invT = 1.f / (float)Tn;
+  const long long total = (long long)B * P * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(idx % cv);
+    const int p = (int)((idx / cv) % P);
+    const int b = (int)(idx / ((long long)cv * P));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int t = 0; t < Tn; ++t) {
+      float v[8];
+      load8(src + (((long long)b * Tn + t) * P + p) * C + cb * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= invT;
+    store8(dst + b * dst_ns + (long long)p * dst_ps + cb * 8, acc);
+  }
+}
+
+// ---- ConvLSTM cell (src/convlstm.py:14-18) ------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+lstm_cell_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, T* __restrict__ acts,
+                     float* __restrict__ c, T* __restrict__ h, int M, int Ch) {
+  const int cv = Ch / 8;
+  const long long total = (long long)M * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(idx % cv);
+    const long long m = idx / cv;
+    const float* gp = gates + m * 4 * Ch + cb * 8;
+    float gi[8], gf[8], go[8], gg[8], cp[8], cn[8], hn[8];
+    load8(gp, gi); load8(gp + Ch, gf); load8(gp + 2 * Ch, go); load8(gp + 3 * Ch, gg);
+    if (c_prev) load8(c_prev + m * Ch + cb * 8, cp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gi[j] = round_to<T>(sigmoidf_(gi[j]));
+      gf[j] = round_to<T>(sigmoidf_(gf[j]));
+      go[j] = round_to<T>(sigmoidf_(go[j]));
+      gg[j] = round_to<T>(tanhf(gg[j]));
+      cn[j] = fmaf(gf[j], c_prev ? cp[j] : 0.f, gi[j] * gg[j]);
+      hn[j] = go[j] * tanhf(cn[j]);
+    }
+    T* ap = acts + m * 4 * Ch + cb * 8;
+    store8(ap, gi); store8(ap + Ch, gf); store8(ap + 2 * Ch, go); store8(ap + 3 * Ch, gg);
+    store8(c + m * Ch + cb * 8, cn);
+    store8(h + m * Ch + cb * 8, hn);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_kernel(const T* __restrict__ dh_a, const T* __restrict__ dh_b, const float* __restrict__ dc_in,
+                     const T* __restrict__ acts, const float* __restrict__ c_prev, const float* __restrict__ c,
+                     T* __restrict__ dgates, float* __restrict__ dc_prev, int M, int Ch) {
+  const int cv = Ch / 8;
+  const long long total = (long long)M * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(idx % cv);
+    const long long m = idx / cv;
+    const long long o1 = m * Ch + cb * 8;
+    float dh[8], t[8], dc[8], gi[8], gf[8], go[8], gg[8], cp[8], cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dh[j] = dc[j] = cp[j] = 0.f;
+    if (dh_a) load8(dh_a + o1, dh);
+    if (dh_b) {
+      load8(dh_b + o1, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dh[j] += t[j];
+    }
+    if (dc_in) load8(dc_in + o1, dc);
+    if (c_prev) load8(c_prev + o1, cp);
+    load8(c + o1, cc);
+    const T* ap = acts + m * 4 * Ch + cb * 8;
+    load8(ap, gi); load8(ap + Ch, gf); load8(ap + 2 * Ch, go); load8(ap + 3 * Ch, gg);
+    float di[8], df[8], dO[8], dg[8], dcp[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float tc = tanhf(cc[j]);
+      const float dct = fmaf(dh[j] * go[j], 1.f - tc * tc, dc[j]);
+      dO[j] = dh[j] * tc * go[j] * (1.f - go[j]);
+      di[j] = dct * gg[j] * gi[j] * (1.f - gi[j]);
+      df[j] = dct * cp[j] * gf[j] * (1.f - gf[j]);
+      dg[j] = dct * gi[j] * (1.f - gg[j] * gg[j]);
+      dcp[j] = dct * gf[j];
+    }
+    T* dp = dgates + m * 4 * Ch + cb * 8;
+    store8(dp, di); store8(dp + Ch, df); store8(dp + 2 * Ch, dO); store8(dp + 3 * Ch, dg);
+    store8(dc_prev + o1, dcp);
+  }
+}
+
+// ---- head 1x1 (+bias) to NCHW fp32 and its backward ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ out, int N, int P, int C, int K) {
+  extern __shared__ float sw[];   // w[K][C] | b[K]
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = __ldg(w + i);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) sw[K * C + i] = __ldg(b + i);
+  __syncthreads();
+  const long long total = (long long)N * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % P);
+    const int n = (int)(idx / P);
+    for (int k = 0; k < K; ++k) {
+      float acc = sw[K * C + k];
+      for (int cb = 0; cb < C; cb += 8) {
+        float v[8];
+        load8(x + idx * C + cb, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(v[j], sw[k * C + cb + j], acc);
+      }
+      out[((long long)n * K + k) * P + p] = acc;
+    }
+  }
+}
+
+// dx[p][c] = sum_k w[k][c]*dout[n][k][p]; dw[k][c] += sum dout*x; db[k] += sum dout   (K <= 8)
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ x, const float* __restrict__ w,
+                T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int N, int P, int C, int K) {
+  extern __shared__ float sm[];   // w[K][C] | accw[K][C] | accb[K]
+  float* sw = sm;
+  float* accw = sm + K * C;
+  float* accb = accw + K * C;
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) { sw[i] = __ldg(w + i); accw[i] = 0.f; }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) accb[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)N * P;
+  const long long iters = (total + (long long)gridDim.x * blockDim.x - 1) / ((long long)gridDim.x * blockDim.x);
+  for (long long it = 0; it < iters; ++it) {
+    const long long idx = (it * gridDim.x + blockIdx.x) * (long long)blockDim.x + threadIdx.x;
+    const bool valid = idx < total;
+    float d[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = 0.f;
+    if (valid) {
+      const int p = (int)(idx % P);
+      const int n = (int)(idx / P);
+      for (int k = 0; k < K; ++k) d[k] = __ldg(dout + ((long long)n * K + k) * P + p);
+    }
+    for (int k = 0; k < K; ++k) {
+      const float s = warp_sum(d[k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&accb[k], s);
+    }
+    for (int cb = 0; cb < C; cb += 8) {
+      float v[8], r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r[j] = 0.f;
+      if (valid) load8(x + idx * C + cb, v);
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          r[j] = fmaf(sw[k * C + cb + j], d[k], r[j]);
+          const float s = warp_sum(d[k] * v[j]);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&accw[k * C + cb + j], s);
+        }
+      }
+      if (valid) store8(dx + idx * C + cb, r);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) atomicAdd(dw + i, accw[i]);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(db + i, accb[i]);
+}
+
+__global__ void __launch_bounds__(256)
+mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ loss, long long n) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    acc = fmaf(d, d, acc);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss, acc / (float)n);
+}
+
+__global__ void __launch_bounds__(256)
+mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gscale,
+               float* __restrict__ da, long long n) {
+  const float k = 2.f / (float)n * (gscale ? __ldg(gscale) : 1.f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    da[i] = k * (__ldg(a + i) - __ldg(b + i));
+}
+
+// ---- Adam (torch.optim.Adam semantics, main_final.py:742-746) -----------------------------------------
+__global__ void adam_tick_kernel(float* state, float b1, float b2) {
+  // state: [0]=step, [1]=1-b1^step, [2]=1-b2^step
+  const float step = state[0] + 1.f;
+  state[0] = step;
+  state[1] = 1.f - powf(b1, step);
+  state[2] = 1.f - powf(b2, step);
+}
+
+__global__ void __launch_bounds__(256)
+adam_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  const float* __restrict__ state, long long n, float lr, float b1, float b2, float eps, float wd,
+                  float grad_scale) {
+  const float bc1 = state[1], bc2s = sqrtf(state[2]);
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * mi / (sqrtf(vi) / bc2s + eps);
+  }
+}
+
+static inline int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > kGridCap) b = kGridCap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace pcm
+
+using namespace pcm;
+
+extern "C" int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp, int dtype,
+                                pcm_stream_t s) {
+  PCM_REQUIRE(Cp % 8 == 0 && Cp >= C, "nchw_to_nhwc: bad channel padding C=%d Cp=%d", C, Cp);
+  if (N == 0) return PCM_OK;
+  const long long total = (long long)N * (Cp / 8) * H * W;
+  PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   x, (T*)y, N, C, H * W, Cp, nullptr)));
+  return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int pcm_season_embed_stage(const float* x5, const int* month, void* y, int N, int H, int W, int Cp,
+                                      int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(Cp % 8 == 0 && Cp >= 7, "season_embed_stage: Cp must be >= 7 and a multiple of 8");
+  if (N == 0) return PCM_OK;
+  const long long total = (long long)N * (Cp / 8) * H * W;
+  PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   x5, (T*)y, N, 5, H * W, Cp, month)));
+  return check_launch("season_embed_stage");
+}
+
+extern "C" int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, int W, int Cp, int dtype,
+                                pcm_stream_t s) {
+  PCM_REQUIRE(Cp % 8 == 0 && Cp >= C, "nhwc_to_nchw: bad channel padding C=%d Cp=%d", C, Cp);
+  if (N == 0) return PCM_OK;
+  const long long total = (long long)N * (Cp / 8) * H * W;
+  PCM_DISPATCH_DTYPE(dtype, T, (nhwc_to_nchw_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   (const T*)x, y, N, C, H * W, Cp)));
+  return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "maxpool2_fwd: bad shape");
+  if (N == 0) return PCM_OK;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  PCM_DISPATCH_DTYPE(dtype, T, (maxpool2_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   (const T*)x, (T*)y, N, H, W, C)));
+  return check_launch("maxpool2_fwd");
+}
+
+extern "C" int pcm_maxpool2_bwd_skip(const void* x, const void* dy, const void* dskip, long long dskip_ns,
+                                     int dskip_ps, void* dx, int N, int H, int W, int C, int T_, int dtype,
+                                     pcm_stream_t s) {
+  PCM_REQUIRE(C % 8 == 0 && T_ >= 1, "maxpool2_bwd_skip: bad shape");
+  if (N == 0) return PCM_OK;
+  const long long total = (long long)N * H * W * (C / 8);
+  PCM_DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_skip_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps, (T*)dx, N, H, W, C,
+                                   T_)));
+  return check_launch("maxpool2_bwd_skip");
+}
+
+extern "C" int pcm_time_mean(const void* src, void* dst, long long dst_ns, int dst_ps, int B, int T_, int P, int C,
+                             int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(C % 8 == 0 && T_ >= 1, "time_mean: bad shape");
+  if (B == 0) return PCM_OK;
+  const long long total = (long long)B * P * (C / 8);
+  PCM_DISPATCH_DTYPE(dtype, T, (time_mean_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   (const T*)src, (T*)dst, dst_ns, dst_ps, B, T_, P, C)));
+  return check_launch("time_mean");
+}
+
+extern "C" int pcm_lstm_cell_fwd(const float* gates, const float* c_prev, void* acts, float* c, void* h, int M,
+                                 int Ch, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(Ch % 8 == 0, "lstm_cell_fwd: Ch must be a multiple of 8");
+  if (M == 0) return PCM_OK;
+  const long long total = (long long)M * (Ch / 8);
+  PCM_DISPATCH_DTYPE(dtype, T, (lstm_cell_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   gates, c_prev, (T*)acts, c, (T*)h, M, Ch)));
+  return check_launch("lstm_cell_fwd");
+}
+
+extern "C" int pcm_lstm_cell_bwd(const void* dh_a, const void* dh_b, const float* dc_in, const void* acts,
+                                 const float* c_prev, const float* c, void* dgates, float* dc_prev, int M, int Ch,
+                                 int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(Ch % 8 == 0, "lstm_cell_bwd: Ch must be a multiple of 8");
+  if (M == 0) return PCM_OK;
+  const long long total = (long long)M * (Ch / 8);
+  PCM_DISPATCH_DTYPE(dtype, T, (lstm_cell_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   (const T*)dh_a, (const T*)dh_b, dc_in, (const T*)acts, c_prev, c, (T*)dgates,
+                                   dc_prev, M, Ch)));
+  return check_launch("lstm_cell_bwd");
+}
+
+extern "C" int pcm_head_fwd(const void* x, const float* w, const float* b, float* out_nchw, int N, int P, int C, int K,
+                            int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(C % 8 == 0 && K >= 1, "head_fwd: bad shape");
+  if (N == 0) return PCM_OK;
+  const size_t smem = (size_t)(K * C + K) * sizeof(float);
+  PCM_DISPATCH_DTYPE(dtype, T, (head_fwd_kernel<T><<<grid_for((long long)N * P), 256, smem, (cudaStream_t)s>>>(
+                                   (const T*)x, w, b, out_nchw, N, P, C, K)));
+  return check_launch("head_fwd");
+}
+
+extern "C" int pcm_head_bwd(const float* dout_nchw, const void* x, const float* w, void* dx, float* dw, float* db,
+                            int N, int P, int C, int K, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(C % 8 == 0 && K >= 1 && K <= 8, "head_bwd: K must be in 1..8");
+  if (N == 0) return PCM_OK;
+  const size_t smem = (size_t)(2 * K * C + K) * sizeof(float);
+  long long blocks = ((long long)N * P + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  PCM_DISPATCH_DTYPE(dtype, T, (head_bwd_kernel<T><<<(int)blocks, 256, smem, (cudaStream_t)s>>>(
+                                   dout_nchw, (const T*)x, w, (T*)dx, dw, db, N, P, C, K)));
+  return check_launch("head_bwd");
+}
+
+extern "C" int pcm_mse_fwd(const float* a, const float* b, float* loss, long long n, pcm_stream_t s) {
+  if (n == 0) return PCM_OK;
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 296) blocks = 296;
+  mse_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(a, b, loss, n);
+  return check_launch("mse_fwd");
+}
+
+extern "C" int pcm_mse_bwd(const float* a, const float* b, const float* gscale, float* da, long long n,
+                           pcm_stream_t s) {
+  if (n == 0) return PCM_OK;
+  mse_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(a, b, gscale, da, n);
+  return check_launch("mse_bwd");
+}
+
+extern "C" int pcm_adam_step(float* p, const float* g, float* m, float* v, float* state, long long n, float lr,
+                             float b1, float b2, float eps, float wd, float grad_scale, pcm_stream_t s) {
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(state, b1, b2);
+  if (n > 0)
+    adam_apply_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(p, g, m, v, state, n, lr, b1, b2, eps, wd, grad_scale);
+  return check_launch("adam_step");
+}

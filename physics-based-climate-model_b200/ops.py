@@ -1,0 +1,643 @@
+"""Host-side operator layer: torch.autograd.Functions whose forward/backward bodies are sequences of
+pcm_b200 C-ABI kernel launches (include/pcm_b200.h) on torch's current CUDA stream.
+
+Activations travel between Functions as contiguous NHWC tensors (N, H, W, C) in the compute dtype
+(torch.bfloat16 by default, torch.float32 for the tight-parity path), C padded to a multiple of 8.
+Parameters stay the module's fp32 nn.Parameters in the reference's shapes;
+weight gradients are accumulated by the kernels in fp32 either into ``param.main_grad`` (a view of
+the trainer's flat, pre-zeroed gradient buffer — no autograd accumulation kernels) or into a fresh
+zeroed tensor returned to autograd.
+
+torch is used for device memory (empty/zeros), streams and autograd bookkeeping only; every
+arithmetic kernel is ours.  There is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import lib
+
+GN_GROUPS = 8
+GN_EPS = 1e-5
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name: str, *args):
+    lib().call(name, *args)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"pcm_b200: {what} must be a CUDA tensor — the pcm_b200 kernels have no CPU fallback")
+
+
+def _grad_buf(p: torch.Tensor):
+    """(buffer the kernels accumulate into, value to hand back to autograd)."""
+    mg = getattr(p, "main_grad", None)
+    if mg is not None:
+        return mg, None
+    g = torch.zeros_like(p, dtype=torch.float32)
+    return g, g
+
+
+# ------------------------------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# ------------------------------------------------------------------------------------------------
+def pack_weight(w: torch.Tensor, so: int, si: int, st: int, O: int, I: int, taps: int, dtype, offset: int = 0):
+    """out[t][o][i] = w.flatten()[offset + o*so + i*si + t*st], zero padded to (taps, pad8(O), pad8(I))."""
+    Op, Ip = pad8(O), pad8(I)
+    out = torch.empty((taps, Op, Ip), device=w.device, dtype=dtype)
+    _call("pcm_pack_weight", w.data_ptr() + 4 * offset, so, si, st, O, I, taps, Op, Ip, out.data_ptr(), _DT[dtype], _s())
+    return out
+
+
+def conv_weight_fwd(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None):
+    """nn.Conv2d weight (Co, Ci_tot, KH, KW) -> [taps][Co][Ci] for mode-0 gather."""
+    Co, Ci_tot, KH, KW = w.shape
+    ci = Ci_tot - ci_off if ci is None else ci
+    K = KH * KW
+    return pack_weight(w, Ci_tot * K, K, 1, Co, ci, K, dtype, offset=ci_off * K)
+
+
+def conv_weight_dgrad(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None):
+    """nn.Conv2d weight -> [taps][Ci][Co] for mode-1 gather (data gradient)."""
+    Co, Ci_tot, KH, KW = w.shape
+    ci = Ci_tot - ci_off if ci is None else ci
+    K = KH * KW
+    return pack_weight(w, K, Ci_tot * K, 1, ci, Co, K, dtype, offset=ci_off * K)
+
+
+def conv_gather(src, wk, N, Hs, Ws, Sc, Hd, Wd, Dc, KH, KW, stride, pad, mode, dst=None, dst_f32=False,
+                bias=None, accumulate=False, relu=False, src_ns=None, src_ps=None, dst_ns=None, dst_ps=None,
+                src_off=0, dst_off=0, dtype=None):
+    dtype = dtype or src.dtype
+    if dst is None:
+        dst = torch.empty((N, Hd, Wd, Dc), device=src.device, dtype=torch.float32 if dst_f32 else dtype)
+    src_ps = Sc if src_ps is None else src_ps
+    dst_ps = Dc if dst_ps is None else dst_ps
+    src_ns = Hs * Ws * src_ps if src_ns is None else src_ns
+    dst_ns = Hd * Wd * dst_ps if dst_ns is None else dst_ns
+    _call("pcm_conv_gather", src.data_ptr() + src_off * src.element_size(), src_ns, src_ps, Hs, Ws, Sc,
+          dst.data_ptr() + dst_off * dst.element_size(), dst_ns, dst_ps, Hd, Wd, Dc, wk.data_ptr(), _p(bias),
+          N, KH, KW, stride, pad, mode, int(dst_f32), int(accumulate), int(relu), _DT[dtype], _s())
+    return dst
+
+
+def conv_wgrad(A, B, dw, sa, sb, st, N, Ha, Wa, Ca, Ca_real, Hb, Wb, Cb, Cb_real, KH, KW, stride, pad,
+               a_ns=None, a_ps=None, b_ns=None, b_ps=None, a_off=0, b_off=0, dw_off=0):
+    a_ps = Ca if a_ps is None else a_ps
+    b_ps = Cb if b_ps is None else b_ps
+    a_ns = Ha * Wa * a_ps if a_ns is None else a_ns
+    b_ns = Hb * Wb * b_ps if b_ns is None else b_ns
+    _call("pcm_conv_wgrad", A.data_ptr() + a_off * A.element_size(), a_ns, a_ps, Ha, Wa, Ca, Ca_real,
+          B.data_ptr() + b_off * B.element_size(), b_ns, b_ps, Hb, Wb, Cb, Cb_real,
+          dw.data_ptr() + 4 * dw_off, sa, sb, st, N, KH, KW, stride, pad, _DT[A.dtype], _s())
+
+
+def channel_sum(x, out, N, P, C, C_real, ns=None, ps=None, off=0, per_image=False):
+    ps = C if ps is None else ps
+    ns = P * ps if ns is None else ns
+    _call("pcm_channel_sum", x.data_ptr() + off * x.element_size(), ns, ps, N, P, C, C_real, out.data_ptr(),
+          int(per_image), _DT[x.dtype], _s())
+
+
+# ------------------------------------------------------------------------------------------------
+# layout staging at the module boundary (NCHW fp32 <-> NHWC compute dtype)
+# ------------------------------------------------------------------------------------------------
+class StageIn(torch.autograd.Function):
+    """(N, C, H, W) fp32 -> (N, H, W, pad8(C)) compute dtype."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        _require_cuda(x, "input")
+        x = x.contiguous().float()
+        N, C, H, W = x.shape
+        Cp = pad8(C)
+        y = torch.empty((N, H, W, Cp), device=x.device, dtype=dtype)
+        _call("pcm_nchw_to_nhwc", x.data_ptr(), y.data_ptr(), N, C, H, W, Cp, _DT[dtype], _s())
+        ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty((N, C, H, W), device=dy.device, dtype=torch.float32)
+        _call("pcm_nhwc_to_nchw", dy.data_ptr(), dx.data_ptr(), N, C, H, W, dy.shape[-1], _DT[dy.dtype], _s())
+        return dx, None
+
+
+class StageOut(torch.autograd.Function):
+    """(N, H, W, Cp) compute dtype -> (N, C, H, W) fp32."""
+
+    @staticmethod
+    def forward(ctx, x, C):
+        x = x.contiguous()
+        N, H, W, Cp = x.shape
+        y = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
+        _call("pcm_nhwc_to_nchw", x.data_ptr(), y.data_ptr(), N, C, H, W, Cp, _DT[x.dtype], _s())
+        ctx.meta = (Cp, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        Cp, dtype = ctx.meta
+        dy = dy.contiguous().float()
+        N, C, H, W = dy.shape
+        dx = torch.empty((N, H, W, Cp), device=dy.device, dtype=dtype)
+        _call("pcm_nchw_to_nhwc", dy.data_ptr(), dx.data_ptr(), N, C, H, W, Cp, _DT[dtype], _s())
+        return dx, None
+
+
+def season_embed_stage(x5: torch.Tensor, month: torch.Tensor, dtype) -> torch.Tensor:
+    """main_final.py:186-216: (N,5,H,W) forcings + month index (N,) -> NHWC 8-channel frames with
+    sin/cos month channels synthesised on the fly (no gradient: inputs are data)."""
+    _require_cuda(x5, "input")
+    N, C, H, W = x5.shape
+    assert C == 5
+    y = torch.empty((N, H, W, 8), device=x5.device, dtype=dtype)
+    _call("pcm_season_embed_stage", x5.contiguous().float().data_ptr(), month.to(torch.int32).contiguous().data_ptr(),
+          y.data_ptr(), N, H, W, 8, _DT[dtype], _s())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvBlock: [conv3x3 -> GN(8) -> SiLU] x2 -> SE -> SpatialGate   (src/unet.py:32-49)
+# ------------------------------------------------------------------------------------------------
+class ConvBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp):
+        _require_cuda(x, "activation")
+        x = x.contiguous()
+        N, H, W, Cip = x.shape
+        Co, Ci = w1.shape[0], w1.shape[1]
+        assert pad8(Ci) == Cip and Co % 8 == 0, (Ci, Cip, Co)
+        Cr = sw1.shape[0]
+        P, G, dt, dev = H * W, GN_GROUPS, x.dtype, x.device
+        d = _DT[dt]
+        st = _s()
+        # one zeroed scratch for every small accumulator of the forward
+        small = torch.zeros(N * G * 2 * 2 + N * Co, device=dev, dtype=torch.float32)
+        stats1 = small[: N * G * 2]
+        stats2 = small[N * G * 2: N * G * 4]
+        pool = small[N * G * 4:]
+        wk1 = conv_weight_fwd(w1, dt)
+        y1 = conv_gather(x, wk1, N, H, W, Cip, H, W, Co, 3, 3, 1, 1, 0)
+        _call("pcm_gn_stats", y1.data_ptr(), stats1.data_ptr(), N, P, Co, G, d, st)
+        a1 = torch.empty_like(y1)
+        _call("pcm_gn_silu_fwd", y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(), b1.data_ptr(), a1.data_ptr(), 0,
+              N, P, Co, G, GN_EPS, d, st)
+        wk2 = conv_weight_fwd(w2, dt)
+        y2 = conv_gather(a1, wk2, N, H, W, Co, H, W, Co, 3, 3, 1, 1, 0)
+        _call("pcm_gn_stats", y2.data_ptr(), stats2.data_ptr(), N, P, Co, G, d, st)
+        a2 = torch.empty_like(y2)
+        _call("pcm_gn_silu_fwd", y2.data_ptr(), stats2.data_ptr(), g2.data_ptr(), b2.data_ptr(), a2.data_ptr(),
+              pool.data_ptr(), N, P, Co, G, GN_EPS, d, st)
+        se = torch.empty(N * Co + N * Cr, device=dev, dtype=torch.float32)
+        hid = se[N * Co:]
+        maps = torch.empty(N * P * 3, device=dev, dtype=torch.float32)
+        cmap, gate = maps[: N * P * 2], maps[N * P * 2:]
+        _call("pcm_se_chanstat_fwd", a2.data_ptr(), pool.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), se.data_ptr(),
+              hid.data_ptr(), cmap.data_ptr(), N, P, Co, Cr, d, st)
+        out = torch.empty_like(a2)
+        _call("pcm_spatial_gate_fwd", a2.data_ptr(), se.data_ptr(), cmap.data_ptr(), wsp.data_ptr(), gate.data_ptr(),
+              out.data_ptr(), N, H, W, Co, d, st)
+        ctx.save_for_backward(x, y1, a1, y2, a2, small, se, maps, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp)
+        ctx.dims = (N, H, W, Cip, Ci, Co, Cr)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y1, a1, y2, a2, small, se, maps, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp = ctx.saved_tensors
+        N, H, W, Cip, Ci, Co, Cr = ctx.dims
+        P, G, dt, dev = H * W, GN_GROUPS, x.dtype, x.device
+        d = _DT[dt]
+        st = _s()
+        dout = dout.contiguous()
+        stats1 = small[: N * G * 2]
+        stats2 = small[N * G * 2: N * G * 4]
+        pool = small[N * G * 4:]
+        hid = se[N * Co:]
+        cmap, gate = maps[: N * P * 2], maps[N * P * 2:]
+        # scratch: dse[N*Co] | gsum2[N*G*2] | gsum1[N*G*2]   (zeroed) ; dq, dpool (written fully)
+        z = torch.zeros(N * Co + N * G * 4, device=dev, dtype=torch.float32)
+        dse, gsum2, gsum1 = z[: N * Co], z[N * Co: N * Co + N * G * 2], z[N * Co + N * G * 2:]
+        e = torch.empty(N * P + N * Co, device=dev, dtype=torch.float32)
+        dq, dpool = e[: N * P], e[N * P:]
+        gw1, rw1 = _grad_buf(w1); gg1, rg1 = _grad_buf(g1); gb1, rb1 = _grad_buf(b1)
+        gw2, rw2 = _grad_buf(w2); gg2, rg2 = _grad_buf(g2); gb2, rb2 = _grad_buf(b2)
+        gs1, rs1 = _grad_buf(sw1); gs2, rs2 = _grad_buf(sw2); gsp, rsp = _grad_buf(wsp)
+
+        _call("pcm_spatial_gate_bwd_dq", dout.data_ptr(), a2.data_ptr(), se.data_ptr(), gate.data_ptr(), dq.data_ptr(),
+              N, P, Co, d, st)
+        _call("pcm_spatial_gate_bwd_dw", dq.data_ptr(), cmap.data_ptr(), gsp.data_ptr(), N, H, W, st)
+        da2 = torch.empty_like(a2)
+        _call("pcm_spatial_gate_bwd_da", dout.data_ptr(), a2.data_ptr(), se.data_ptr(), gate.data_ptr(),
+              cmap.data_ptr(), dq.data_ptr(), wsp.data_ptr(), da2.data_ptr(), dse.data_ptr(), N, H, W, Co, d, st)
+        _call("pcm_se_bwd", dse.data_ptr(), se.data_ptr(), hid.data_ptr(), pool.data_ptr(), sw1.data_ptr(),
+              sw2.data_ptr(), dpool.data_ptr(), gs1.data_ptr(), gs2.data_ptr(), N, P, Co, Cr, st)
+        _call("pcm_gn_silu_bwd_reduce", da2.data_ptr(), dpool.data_ptr(), y2.data_ptr(), stats2.data_ptr(),
+              g2.data_ptr(), b2.data_ptr(), gsum2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(), N, P, Co, G, GN_EPS, d, st)
+        dy2 = torch.empty_like(y2)
+        _call("pcm_gn_silu_bwd_apply", da2.data_ptr(), dpool.data_ptr(), y2.data_ptr(), stats2.data_ptr(),
+              g2.data_ptr(), b2.data_ptr(), gsum2.data_ptr(), dy2.data_ptr(), N, P, Co, G, GN_EPS, d, st)
+        # conv2: weight + data gradients
+        conv_wgrad(dy2, a1, gw2, Co * 9, 9, 1, N, H, W, Co, Co, H, W, Co, Co, 3, 3, 1, 1)
+        wk2t = conv_weight_dgrad(w2, dt)
+        da1 = conv_gather(dy2, wk2t, N, H, W, Co, H, W, Co, 3, 3, 1, 1, 1, dst=da2)     # reuse da2 storage
+        _call("pcm_gn_silu_bwd_reduce", da1.data_ptr(), 0, y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(),
+              b1.data_ptr(), gsum1.data_ptr(), gg1.data_ptr(), gb1.data_ptr(), N, P, Co, G, GN_EPS, d, st)
+        dy1 = dy2                                                                          # reuse dy2 storage
+        _call("pcm_gn_silu_bwd_apply", da1.data_ptr(), 0, y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(),
+              b1.data_ptr(), gsum1.data_ptr(), dy1.data_ptr(), N, P, Co, G, GN_EPS, d, st)
+        conv_wgrad(dy1, x, gw1, Ci * 9, 9, 1, N, H, W, Co, Co, H, W, Cip, Ci, 3, 3, 1, 1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wk1t = conv_weight_dgrad(w1, dt)
+            dx = conv_gather(dy1, wk1t, N, H, W, Co, H, W, Cip, 3, 3, 1, 1, 1)
+        return dx, rw1, rg1, rb1, rw2, rg2, rb2, rs1, rs2, rsp
+
+
+# ------------------------------------------------------------------------------------------------
+# MaxPool2d(2) fused with the time-mean skip (src/unet_convlstm_attention.py:21,24,91-93)
+# ------------------------------------------------------------------------------------------------
+class PoolSkipFn(torch.autograd.Function):
+    """s (B*T, H, W, C) -> pooled (B*T, H/2, W/2, C), skip (B, H, W, C) = mean over the T frames of
+    each sample.  Backward is ONE kernel: max-pool routing (first max wins, like torch) + dskip/T."""
+
+    @staticmethod
+    def forward(ctx, s, T):
+        s = s.contiguous()
+        N, H, W, C = s.shape
+        B = N // T
+        d = _DT[s.dtype]
+        pooled = torch.empty((N, H // 2, W // 2, C), device=s.device, dtype=s.dtype)
+        _call("pcm_maxpool2_fwd", s.data_ptr(), pooled.data_ptr(), N, H, W, C, d, _s())
+        skip = torch.empty((B, H, W, C), device=s.device, dtype=s.dtype)
+        _call("pcm_time_mean", s.data_ptr(), skip.data_ptr(), H * W * C, C, B, T, H * W, C, d, _s())
+        ctx.save_for_backward(s)
+        ctx.T = T
+        return pooled, skip
+
+    @staticmethod
+    def backward(ctx, dpooled, dskip):
+        (s,) = ctx.saved_tensors
+        N, H, W, C = s.shape
+        ds = torch.empty_like(s)
+        dp = dpooled.contiguous() if dpooled is not None else None
+        ns = ps = 0
+        if dskip is not None:
+            # dskip may be a channel-slice view of the decoder's concat gradient: pass its strides
+            assert dskip.stride(3) == 1 and dskip.stride(1) == W * dskip.stride(2)
+            ns, ps = dskip.stride(0), dskip.stride(2)
+        _call("pcm_maxpool2_bwd_skip", s.data_ptr(), _p(dp), _p(dskip), ns, ps, ds.data_ptr(), N, H, W, C, ctx.T,
+              _DT[s.dtype], _s())
+        return ds, None
+
+
+class MaxPoolFn(torch.autograd.Function):
+    """Plain nn.MaxPool2d(2) (src/unet.py:54)."""
+
+    @staticmethod
+    def forward(ctx, s):
+        s = s.contiguous()
+        N, H, W, C = s.shape
+        pooled = torch.empty((N, H // 2, W // 2, C), device=s.device, dtype=s.dtype)
+        _call("pcm_maxpool2_fwd", s.data_ptr(), pooled.data_ptr(), N, H, W, C, _DT[s.dtype], _s())
+        ctx.save_for_backward(s)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        (s,) = ctx.saved_tensors
+        N, H, W, C = s.shape
+        ds = torch.empty_like(s)
+        _call("pcm_maxpool2_bwd_skip", s.data_ptr(), dpooled.contiguous().data_ptr(), 0, 0, 0, ds.data_ptr(), N, H, W,
+              C, 1, _DT[s.dtype], _s())
+        return ds
+
+
+# ------------------------------------------------------------------------------------------------
+# Up: ConvTranspose2d(k2,s2,bias) + cat([up, skip])   (src/unet.py:63,67-68)
+# ------------------------------------------------------------------------------------------------
+class UpCatFn(torch.autograd.Function):
+    """x (B,h,w,Ci), skip (B,2h,2w,Cs) -> cat (B,2h,2w,Co+Cs); the transposed conv writes straight
+    into the first Co channels of the concat buffer."""
+
+    @staticmethod
+    def forward(ctx, x, skip, wt, bt):
+        x = x.contiguous()
+        B, h, w, Ci = x.shape
+        Co, Cs = wt.shape[1], skip.shape[-1]
+        assert wt.shape[0] == Ci and Co % 8 == 0 and Cs % 8 == 0
+        H, W, Cc, dt = 2 * h, 2 * w, Co + Cs, x.dtype
+        cat = torch.empty((B, H, W, Cc), device=x.device, dtype=dt)
+        # convT forward == mode-1 gather with (k=2, s=2, p=0); wk[tap][d][c] = wt[c][d][tap]
+        wk = pack_weight(wt, 4, Co * 4, 1, Co, Ci, 4, dt)
+        conv_gather(x, wk, B, h, w, Ci, H, W, Co, 2, 2, 2, 0, 1, dst=cat, bias=bt, dst_ns=H * W * Cc, dst_ps=Cc)
+        cat[..., Co:].copy_(skip)          # strided D2D copy (plumbing, no arithmetic)
+        ctx.save_for_backward(x, wt, bt)
+        ctx.dims = (B, h, w, Ci, Co, Cs)
+        return cat
+
+    @staticmethod
+    def backward(ctx, dcat):
+        x, wt, bt = ctx.saved_tensors
+        B, h, w, Ci, Co, Cs = ctx.dims
+        H, W, Cc, dt = 2 * h, 2 * w, Co + Cs, x.dtype
+        dcat = dcat.contiguous()
+        gwt, rwt = _grad_buf(wt)
+        gbt, rbt = _grad_buf(bt)
+        # data grad == mode-0 gather (k=2,s=2,p=0) over the first Co channels; wk[tap][c][d] = wt[c][d][tap]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wk = pack_weight(wt, Co * 4, 4, 1, Ci, Co, 4, dt)
+            dx = conv_gather(dcat, wk, B, H, W, Co, h, w, Ci, 2, 2, 2, 0, 0, src_ns=H * W * Cc, src_ps=Cc)
+        # weight grad: A = x (small grid), B = dcat (big grid): dwt[c][d][tap]
+        conv_wgrad(x, dcat, gwt, Co * 4, 4, 1, B, h, w, Ci, Ci, H, W, Co, Co, 2, 2, 2, 0, b_ns=H * W * Cc, b_ps=Cc)
+        channel_sum(dcat, gbt, B, H * W, Co, Co, ns=H * W * Cc, ps=Cc)
+        dskip = dcat[..., Co:] if ctx.needs_input_grad[1] else None     # view; consumer reads it strided
+        return dx, dskip, rwt, rbt
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvLSTM (src/convlstm.py:11-35)
+# ------------------------------------------------------------------------------------------------
+class ConvLSTMFn(torch.autograd.Function):
+    """x: NHWC frames (T*B images); frame (t, b) is image t*st_t + b*st_b.  Returns h for all steps
+    as (T, B, H, W, Ch), or only the last step when last_only (src/unet_convlstm_attention.py:88).
+
+    W.cat(x,h) = Wx.x + Wh.h: the x half is computed for all T up front (it does not
+    depend on the recurrence); each step then adds Wh.h_{t-1} and runs the fused cell update."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, T, B, st_t, st_b, last_only):
+        x = x.contiguous()
+        _, H, W, Cip = x.shape
+        Ch = w.shape[0] // 4
+        Ci = w.shape[1] - Ch
+        K = w.shape[-1]
+        pad = K // 2
+        assert pad8(Ci) == Cip and Ch % 8 == 0
+        P, dt, dev = H * W, x.dtype, x.device
+        d, st = _DT[dt], _s()
+        img = P * Cip
+        wx = conv_weight_fwd(w, dt, 0, Ci)
+        wh = conv_weight_fwd(w, dt, Ci, Ch)
+        gates = torch.empty((T, B, P, 4 * Ch), device=dev, dtype=torch.float32)
+        acts = torch.empty((T, B, P, 4 * Ch), device=dev, dtype=dt)
+        c_all = torch.empty((T, B, P, Ch), device=dev, dtype=torch.float32)
+        h_all = torch.empty((T, B, H, W, Ch), device=dev, dtype=dt)
+        for t in range(T):
+            conv_gather(x, wx, B, H, W, Cip, H, W, 4 * Ch, K, K, 1, pad, 0, dst=gates[t], dst_f32=True, bias=b,
+                        src_ns=st_b * img, src_off=t * st_t * img, dtype=dt)
+        for t in range(T):
+            if t > 0:
+                conv_gather(h_all[t - 1], wh, B, H, W, Ch, H, W, 4 * Ch, K, K, 1, pad, 0, dst=gates[t], dst_f32=True,
+                            accumulate=True, dtype=dt)
+            _call("pcm_lstm_cell_fwd", gates[t].data_ptr(), c_all[t - 1].data_ptr() if t > 0 else 0,
+                  acts[t].data_ptr(), c_all[t].data_ptr(), h_all[t].data_ptr(), B * P, Ch, d, st)
+        ctx.save_for_backward(x, w, b, acts, c_all, h_all)
+        ctx.dims = (T, B, H, W, Cip, Ci, Ch, K, st_t, st_b, last_only)
+        return h_all[T - 1] if last_only else h_all
+
+    @staticmethod
+    def backward(ctx, dh_ext):
+        x, w, b, acts, c_all, h_all = ctx.saved_tensors
+        T, B, H, W, Cip, Ci, Ch, K, st_t, st_b, last_only = ctx.dims
+        pad = K // 2
+        P, dt, dev = H * W, x.dtype, x.device
+        d, st = _DT[dt], _s()
+        img = P * Cip
+        dh_ext = dh_ext.contiguous()
+        gw, rw = _grad_buf(w)
+        gb, rb = _grad_buf(b)
+        dgates = torch.empty((T, B, H, W, 4 * Ch), device=dev, dtype=dt)
+        dc = [torch.empty((B, P, Ch), device=dev, dtype=torch.float32) for _ in range(2)]
+        wht = conv_weight_dgrad(w, dt, Ci, Ch)
+        dh_next = None
+        for t in range(T - 1, -1, -1):
+            if last_only:
+                ext = dh_ext if t == T - 1 else None
+            else:
+                ext = dh_ext[t]
+            _call("pcm_lstm_cell_bwd", _p(ext), _p(dh_next), dc[(t + 1) & 1].data_ptr() if t < T - 1 else 0,
+                  acts[t].data_ptr(), c_all[t - 1].data_ptr() if t > 0 else 0, c_all[t].data_ptr(),
+                  dgates[t].data_ptr(), dc[t & 1].data_ptr(), B * P, Ch, d, st)
+            if t > 0:
+                dh_next = conv_gather(dgates[t], wht, B, H, W, 4 * Ch, H, W, Ch, K, K, 1, pad, 1, dst=dh_next)
+        KK = K * K
+        Ct = Ci + Ch
+        # dW[:, :Ci] — x frames may be time-strided, one launch per step; dW[:, Ci:] — one launch over t>=1
+        for t in range(T):
+            conv_wgrad(dgates[t], x, gw, Ct * KK, KK, 1, B, H, W, 4 * Ch, 4 * Ch, H, W, Cip, Ci, K, K, 1, pad,
+                       b_ns=st_b * img, b_off=t * st_t * img)
+        if T > 1:
+            conv_wgrad(dgates[1:], h_all[:-1], gw, Ct * KK, KK, 1, (T - 1) * B, H, W, 4 * Ch, 4 * Ch, H, W, Ch, Ch,
+                       K, K, 1, pad, dw_off=Ci * KK)
+        channel_sum(dgates, gb, T * B, P, 4 * Ch, 4 * Ch)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wxt = conv_weight_dgrad(w, dt, 0, Ci)
+            dx = torch.empty_like(x)
+            for t in range(T):
+                conv_gather(dgates[t], wxt, B, H, W, 4 * Ch, H, W, Cip, K, K, 1, pad, 1, dst=dx,
+                            dst_ns=st_b * img, dst_off=t * st_t * img)
+        return dx, rw, rb, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# head (1x1 conv + bias -> NCHW fp32) and MSE loss
+# ------------------------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    """nn.Conv2d(base, out_ch, 1) (src/unet_convlstm_attention.py:56,104): NHWC in, NCHW fp32 out."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        K = w.shape[0]
+        out = torch.empty((N, K, H, W), device=x.device, dtype=torch.float32)
+        _call("pcm_head_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), N, H * W, C, K, _DT[x.dtype], _s())
+        ctx.save_for_backward(x, w, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, b = ctx.saved_tensors
+        N, H, W, C = x.shape
+        K = w.shape[0]
+        dout = dout.contiguous().float()
+        gw, rw = _grad_buf(w)
+        gb, rb = _grad_buf(b)
+        dx = torch.empty_like(x)
+        _call("pcm_head_bwd", dout.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), gw.data_ptr(), gb.data_ptr(),
+              N, H * W, C, K, _DT[x.dtype], _s())
+        return dx, rw, rb
+
+
+class MSELossFn(torch.autograd.Function):
+    """nn.MSELoss() (main_final.py:544,559)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        _require_cuda(pred, "prediction")
+        pred = pred.contiguous().float()
+        target = target.contiguous().float()
+        loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+        _call("pcm_mse_fwd", pred.data_ptr(), target.data_ptr(), loss.data_ptr(), pred.numel(), _s())
+        ctx.save_for_backward(pred, target)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        g = g.contiguous().float()
+        dp = torch.empty_like(pred)
+        _call("pcm_mse_bwd", pred.data_ptr(), target.data_ptr(), g.data_ptr(), dp.data_ptr(), pred.numel(), _s())
+        return dp, None
+
+
+def mse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    return MSELossFn.apply(pred, target)
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone attention helpers and single cell step (reference modules usable on their own)
+# ------------------------------------------------------------------------------------------------
+class SEFn(torch.autograd.Function):
+    """SEBlock.forward (src/unet.py:16-17): x * sigmoid(W2 relu(W1 avgpool(x))) on NHWC."""
+
+    @staticmethod
+    def forward(ctx, a, w1, w2):
+        a = a.contiguous()
+        N, H, W, C = a.shape
+        if w1.shape[1] != C:
+            raise RuntimeError("pcm_b200 SEBlock needs a channel count that is a multiple of 8")
+        Cr, P, d, st, dev = w1.shape[0], H * W, _DT[a.dtype], _s(), a.device
+        pool = torch.zeros(N * C, device=dev, dtype=torch.float32)
+        channel_sum(a, pool, N, P, C, C, per_image=True)
+        se = torch.empty(N * C + N * Cr, device=dev, dtype=torch.float32)
+        hid = se[N * C:]
+        cmap = torch.empty(N * P * 2, device=dev, dtype=torch.float32)
+        _call("pcm_se_chanstat_fwd", a.data_ptr(), pool.data_ptr(), w1.data_ptr(), w2.data_ptr(), se.data_ptr(),
+              hid.data_ptr(), cmap.data_ptr(), N, P, C, Cr, d, st)
+        out = torch.empty_like(a)
+        _call("pcm_scale_channels", a.data_ptr(), se.data_ptr(), 0, out.data_ptr(), N, P, C, d, st)
+        ctx.save_for_backward(a, pool, se, w1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, pool, se, w1, w2 = ctx.saved_tensors
+        N, H, W, C = a.shape
+        Cr, P, d, st, dev = w1.shape[0], H * W, _DT[a.dtype], _s(), a.device
+        dout = dout.contiguous()
+        hid = se[N * C:]
+        g1, r1 = _grad_buf(w1)
+        g2, r2 = _grad_buf(w2)
+        # reuse the gate backward with gate = 1, dq = 0: da = dout*se, dse = sum_p dout*a
+        ones = torch.ones(N * P, device=dev, dtype=torch.float32)
+        zer = torch.zeros(N * P * 3 + 98 + N * C, device=dev, dtype=torch.float32)
+        dq, cmap, wsp0, dse = zer[: N * P], zer[N * P: N * P * 3], zer[N * P * 3: N * P * 3 + 98], zer[N * P * 3 + 98:]
+        da = torch.empty_like(a)
+        _call("pcm_spatial_gate_bwd_da", dout.data_ptr(), a.data_ptr(), se.data_ptr(), ones.data_ptr(), cmap.data_ptr(),
+              dq.data_ptr(), wsp0.data_ptr(), da.data_ptr(), dse.data_ptr(), N, H, W, C, d, st)
+        dpool = torch.empty(N * C, device=dev, dtype=torch.float32)
+        _call("pcm_se_bwd", dse.data_ptr(), se.data_ptr(), hid.data_ptr(), pool.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+              dpool.data_ptr(), g1.data_ptr(), g2.data_ptr(), N, P, C, Cr, st)
+        _call("pcm_scale_channels", da.data_ptr(), 0, dpool.data_ptr(), da.data_ptr(), N, P, C, d, st)
+        return da, r1, r2
+
+
+class SpatialGateFn(torch.autograd.Function):
+    """SpatialGate.forward (src/unet.py:25-29) on NHWC: x * sigmoid(conv7x7([mean_C x, amax_C x]))."""
+
+    @staticmethod
+    def forward(ctx, a, wsp):
+        a = a.contiguous()
+        N, H, W, C = a.shape
+        P, d, st, dev = H * W, _DT[a.dtype], _s(), a.device
+        se = torch.ones(N * C + N, device=dev, dtype=torch.float32)      # se = 1 (no excitation); hid dummy
+        maps = torch.empty(N * P * 3, device=dev, dtype=torch.float32)
+        cmap, gate = maps[: N * P * 2], maps[N * P * 2:]
+        _call("pcm_se_chanstat_fwd", a.data_ptr(), 0, 0, 0, se.data_ptr(), se[N * C:].data_ptr(), cmap.data_ptr(),
+              N, P, C, 1, d, st)
+        out = torch.empty_like(a)
+        _call("pcm_spatial_gate_fwd", a.data_ptr(), se.data_ptr(), cmap.data_ptr(), wsp.data_ptr(), gate.data_ptr(),
+              out.data_ptr(), N, H, W, C, d, st)
+        ctx.save_for_backward(a, se, maps, wsp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, se, maps, wsp = ctx.saved_tensors
+        N, H, W, C = a.shape
+        P, d, st, dev = H * W, _DT[a.dtype], _s(), a.device
+        dout = dout.contiguous()
+        cmap, gate = maps[: N * P * 2], maps[N * P * 2:]
+        gsp, rsp = _grad_buf(wsp)
+        dq = torch.empty(N * P, device=dev, dtype=torch.float32)
+        dse = torch.zeros(N * C, device=dev, dtype=torch.float32)
+        _call("pcm_spatial_gate_bwd_dq", dout.data_ptr(), a.data_ptr(), se.data_ptr(), gate.data_ptr(), dq.data_ptr(),
+              N, P, C, d, st)
+        _call("pcm_spatial_gate_bwd_dw", dq.data_ptr(), cmap.data_ptr(), gsp.data_ptr(), N, H, W, st)
+        da = torch.empty_like(a)
+        _call("pcm_spatial_gate_bwd_da", dout.data_ptr(), a.data_ptr(), se.data_ptr(), gate.data_ptr(), cmap.data_ptr(),
+              dq.data_ptr(), wsp.data_ptr(), da.data_ptr(), dse.data_ptr(), N, H, W, C, d, st)
+        return da, rsp
+
+
+class CellStepFn(torch.autograd.Function):
+    """ConvLSTMCell.forward (src/convlstm.py:11-19) for one explicit step: xh = NHWC cat([x, h]),
+    c = NHWC fp32 cell state -> (h_next NHWC, c_next NHWC fp32)."""
+
+    @staticmethod
+    def forward(ctx, xh, c, w, b):
+        xh, c = xh.contiguous(), c.contiguous()
+        B, H, W, Cp = xh.shape
+        Ch, Ct, K = w.shape[0] // 4, w.shape[1], w.shape[-1]
+        assert pad8(Ct) == Cp and Ch % 8 == 0
+        P, dt, dev = H * W, xh.dtype, xh.device
+        wk = conv_weight_fwd(w, dt)
+        gates = conv_gather(xh, wk, B, H, W, Cp, H, W, 4 * Ch, K, K, 1, K // 2, 0, dst_f32=True, bias=b)
+        acts = torch.empty((B, P, 4 * Ch), device=dev, dtype=dt)
+        c2 = torch.empty((B, H, W, Ch), device=dev, dtype=torch.float32)
+        h2 = torch.empty((B, H, W, Ch), device=dev, dtype=dt)
+        _call("pcm_lstm_cell_fwd", gates.data_ptr(), c.data_ptr(), acts.data_ptr(), c2.data_ptr(), h2.data_ptr(),
+              B * P, Ch, _DT[dt], _s())
+        ctx.save_for_backward(xh, c, w, b, acts, c2)
+        return h2, c2
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        xh, c, w, b, acts, c2 = ctx.saved_tensors
+        B, H, W, Cp = xh.shape
+        Ch, Ct, K = w.shape[0] // 4, w.shape[1], w.shape[-1]
+        P, dt, dev = H * W, xh.dtype, xh.device
+        gw, rw = _grad_buf(w)
+        gb, rb = _grad_buf(b)
+        dgates = torch.empty((B, H, W, 4 * Ch), device=dev, dtype=dt)
+        dcp = torch.empty((B, H, W, Ch), device=dev, dtype=torch.float32)
+        _call("pcm_lstm_cell_bwd", _p(dh.contiguous() if dh is not None else None), 0,
+              _p(dc.contiguous().float() if dc is not None else None), acts.data_ptr(), c.data_ptr(), c2.data_ptr(),
+              dgates.data_ptr(), dcp.data_ptr(), B * P, Ch, _DT[dt], _s())
+        conv_wgrad(dgates, xh, gw, Ct * K * K, K * K, 1, B, H, W, 4 * Ch, 4 * Ch, H, W, Cp, Ct, K, K, 1, K // 2)
+        channel_sum(dgates, gb, B, P, 4 * Ch, 4 * Ch)
+        wkt = conv_weight_dgrad(w, dt)
+        dxh = conv_gather(dgates, wkt, B, H, W, 4 * Ch, H, W, Cp, K, K, 1, K // 2, 1)
+        return dxh, dcp, rw, rb

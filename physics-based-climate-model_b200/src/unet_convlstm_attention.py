@@ -1,0 +1,73 @@
+"""B200-native AttUNetConvLSTM — interface of reference src/unet_convlstm_attention.py
+(DownPoolEnc :18-25, AttUNetConvLSTM :27-104).
+
+forward(x_seq[B,T,C,H,W]) -> [B,out_ch,H,W].  B200-first restructuring (results identical):
+  * the per-frame encoder loop (:71-82) is frame independent (GroupNorm is per sample), so the T
+    frames are folded into the batch — every encoder kernel runs once over B*T images;
+  * the time-mean skips (:91-93) are produced by the same Function that max-pools each level, so
+    the T stacked copies of s1..s3 are never materialised twice and their backward is one kernel;
+  * only the last hidden state feeds the decoder (:88): the ConvLSTM Function returns just it;
+  * `post_conv` (:46-49) is constructed for checkpoint compatibility and, as in the reference,
+    never executed (its gradients stay None)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..config import compute_dtype
+from .convlstm import ConvLSTM
+from .unet import ConvBlock, Up
+
+
+class DownPoolEnc(nn.Module):
+    def __init__(self, c_in, c_out):
+        super().__init__()
+        self.pool = nn.MaxPool2d(2)
+        self.conv = ConvBlock(c_in, c_out)
+
+    def forward_nhwc(self, x):
+        return self.conv.forward_nhwc(ops.MaxPoolFn.apply(x))
+
+    def forward(self, x):
+        y = self.forward_nhwc(ops.StageIn.apply(x, compute_dtype()))
+        return ops.StageOut.apply(y, self.conv.c_out)
+
+
+class AttUNetConvLSTM(nn.Module):
+    def __init__(self, in_ch: int = 5, out_ch: int = 2, base: int = 16, seq_len: int = 3):
+        super().__init__()
+        self.seq_len = seq_len
+        self.enc1 = ConvBlock(in_ch, base)
+        self.enc2 = DownPoolEnc(base, base * 2)
+        self.enc3 = DownPoolEnc(base * 2, base * 4)
+        self.enc4 = DownPoolEnc(base * 4, base * 8)
+        self.convlstm = ConvLSTM(c_in=base * 8, c_hid=base * 4, kernel_size=3)
+        self.post_conv = nn.Sequential(
+            nn.Conv2d(base * 4, base * 4, kernel_size=3, padding=1),
+            nn.ReLU(inplace=True)
+        )
+        self.up3 = Up(c_in=base * 4, c_skip=base * 4, c_out=base * 4)
+        self.up2 = Up(c_in=base * 4, c_skip=base * 2, c_out=base * 2)
+        self.up1 = Up(c_in=base * 2, c_skip=base, c_out=base)
+        self.head = nn.Conv2d(base, out_ch, kernel_size=1)
+
+    def forward(self, x_seq):
+        """x_seq : (B, T, C_in, H, W); returns predictions for the last frame (B, C_out, H, W)."""
+        B, T, C, H, W = x_seq.shape
+        x = ops.StageIn.apply(x_seq.reshape(B * T, C, H, W), compute_dtype())   # image n = b*T + t
+        return self.forward_staged(x, B, T)
+
+    def forward_staged(self, x, B, T):
+        """x: NHWC frames (B*T, H, W, pad8(C_in)), image n = b*T + t (e.g. from
+        ops.season_embed_stage, which synthesises the sin/cos month channels on the fly)."""
+        s1 = self.enc1.forward_nhwc(x)
+        p1, k1 = ops.PoolSkipFn.apply(s1, T)
+        s2 = self.enc2.conv.forward_nhwc(p1)
+        p2, k2 = ops.PoolSkipFn.apply(s2, T)
+        s3 = self.enc3.conv.forward_nhwc(p2)
+        p3, k3 = ops.PoolSkipFn.apply(s3, T)
+        s4 = self.enc4.conv.forward_nhwc(p3)
+        bott = self.convlstm.forward_nhwc(s4, T, B, st_t=1, st_b=T, last_only=True)
+        d3 = self.up3.forward_nhwc(bott, k3)
+        d2 = self.up2.forward_nhwc(d3, k2)
+        d1 = self.up1.forward_nhwc(d2, k1)
+        return ops.HeadFn.apply(d1, self.head.weight, self.head.bias)

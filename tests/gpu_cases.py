@@ -1,0 +1,234 @@
+"""GPU parity cases: run a pcm_b200 module / op on cuda:0 and the oracle on the CPU on identical
+seeded inputs, return error metrics.  Used by tests/test_gpu_*.py (asserting) and by
+tests/gpu_diag.py (printing a full table without stopping at the first failure)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+import pcm_b200  # noqa: F401  (registers the package)
+from oracle import metric_oracle as MO
+from oracle import model_oracle as O
+from pcm_b200 import ops
+from pcm_b200.config import set_compute_dtype
+from tests.golden_util import grad_errors, load_golden, rel_l2
+
+DEV = "cuda:0"
+
+
+def _oracle_run(fn, sd, x, y, dtype=torch.float64):
+    sdd = {k: v.clone().to(dtype).requires_grad_(True) for k, v in sd.items()}
+    xx = x.clone().to(dtype).requires_grad_(True)
+    out = fn(xx, sdd)
+    loss = O.mse_loss(out, y.to(dtype))
+    loss.backward()
+    return out.detach(), float(loss.detach()), {k: v.grad for k, v in sdd.items()}, xx.grad
+
+
+def _module_run(mod, sd, x, y, need_dx=True):
+    mod.load_state_dict(sd, strict=True)
+    mod = mod.to(DEV).train()
+    xg = x.to(DEV).requires_grad_(need_dx)
+    out = mod(xg)
+    loss = ops.mse_loss(out, y.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in mod.named_parameters()}
+    return out.detach().cpu(), float(loss.detach().cpu()), grads, (xg.grad.detach().cpu() if need_dx else None)
+
+
+def compare(mod, fn, sd, x, y, dtype, golden=None):
+    """-> dict(out=rel_l2, loss=rel, dx=rel_l2, grads={name: rel_l2}, golden_* likewise)."""
+    set_compute_dtype(dtype)
+    try:
+        out, loss, grads, dx = _module_run(mod, sd, x, y)
+    finally:
+        set_compute_dtype(torch.bfloat16)
+    o_out, o_loss, o_grads, o_dx = _oracle_run(fn, sd, x, y)
+    res = {"out": rel_l2(out.numpy(), o_out.numpy()), "loss": abs(loss - o_loss) / abs(o_loss),
+           "dx": rel_l2(dx.numpy(), o_dx.numpy()), "grads": {}, "gnorm": {}}
+    for k, og in o_grads.items():
+        g = grads.get(k)
+        if og is None:
+            assert g is None or float(g.abs().max()) == 0.0, f"{k}: oracle grad is None"
+            continue
+        assert g is not None, f"{k}: missing gradient"
+        gn = float(og.norm())
+        res["gnorm"][k] = gn
+        res["grads"][k] = rel_l2(g.numpy(), og.numpy()) if gn > 1e-7 else float(g.norm())
+    if golden is not None:
+        z = golden
+        res["golden_out"] = rel_l2(out.numpy(), z["out"])
+        res["golden_loss"] = abs(loss - float(z["loss"])) / abs(float(z["loss"]))
+        ge = grad_errors(grads, z)
+        res["golden_grads"] = {k: v[0] for k, v in ge.items()}
+    return res
+
+
+# ---- cases ---------------------------------------------------------------------------------------
+def case_convblock(dtype):
+    from pcm_b200.src.unet import ConvBlock
+    cfg, z = load_golden("convblock_small")
+    sd = O.synth_state_dict(O._convblock_spec("", cfg["c_in"], cfg["c_out"]), cfg["seed"])
+    x, y = O.synth_frame_batch(cfg["B"], cfg["c_in"], cfg["H"], cfg["W"], cfg["seed"] + 1, out_ch=cfg["c_out"])
+    return compare(ConvBlock(cfg["c_in"], cfg["c_out"]), lambda a, s: O.conv_block(a, s, ""), sd, x, y, dtype, z)
+
+
+def case_convlstm(dtype):
+    from pcm_b200.src.convlstm import ConvLSTM
+    cfg, z = load_golden("convlstm_small")
+    spec = [("cell.conv.weight", (4 * cfg["c_hid"], cfg["c_in"] + cfg["c_hid"], 3, 3)), ("cell.conv.bias", (4 * cfg["c_hid"],))]
+    sd = O.synth_state_dict(spec, cfg["seed"])
+    g = torch.Generator().manual_seed(cfg["seed"] + 1)
+    x = torch.randn(cfg["T"], cfg["B"], cfg["c_in"], cfg["H"], cfg["W"], generator=g)
+    y = torch.randn(cfg["T"], cfg["B"], cfg["c_hid"], cfg["H"], cfg["W"], generator=g)
+    return compare(ConvLSTM(cfg["c_in"], cfg["c_hid"]), lambda a, s: O.convlstm(a, s, ""), sd, x, y, dtype, z)
+
+
+def case_attunet(tag, dtype):
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    cfg, z = load_golden(tag)
+    sd = O.synth_state_dict(O.attunet_spec(cfg["in_ch"], cfg["out_ch"], cfg["base"]), cfg["seed"])
+    x, y, _ = O.synth_attunet_batch(cfg["B"], cfg["T"], cfg["H"], cfg["W"], cfg["seed"] + 1, cfg["in_ch"], cfg["out_ch"])
+    mod = AttUNetConvLSTM(cfg["in_ch"], cfg["out_ch"], cfg["base"], seq_len=cfg["T"])
+    return compare(mod, O.attunet_convlstm, sd, x, y, dtype, z)
+
+
+def case_unet(dtype):
+    from pcm_b200.src.unet import UNet
+    cfg, z = load_golden("unet_small")
+    sd = O.synth_state_dict(O.unet_spec(cfg["in_ch"], cfg["out_ch"], cfg["base"]), cfg["seed"])
+    x, y = O.synth_frame_batch(cfg["B"], cfg["in_ch"], cfg["H"], cfg["W"], cfg["seed"] + 1)
+    return compare(UNet(cfg["in_ch"], cfg["out_ch"], cfg["base"]), O.unet, sd, x, y, dtype, z)
+
+
+def case_se(dtype):
+    from pcm_b200.src.unet import SEBlock
+    sd = O.synth_state_dict([("fc.0.weight", (2, 16, 1, 1)), ("fc.2.weight", (16, 2, 1, 1))], 5)
+    x, y = O.synth_frame_batch(3, 16, 10, 14, 6, out_ch=16)
+    return compare(SEBlock(16), lambda a, s: O.se_block(a, s, ""), sd, x, y, dtype)
+
+
+def case_spatial_gate(dtype):
+    from pcm_b200.src.unet import SpatialGate
+    sd = O.synth_state_dict([("conv.weight", (1, 2, 7, 7))], 7)
+    x, y = O.synth_frame_batch(3, 16, 10, 14, 8, out_ch=16)
+    return compare(SpatialGate(), lambda a, s: O.spatial_gate(a, s, ""), sd, x, y, dtype)
+
+
+def case_down_up(dtype):
+    """Down then Up with the un-pooled input as skip (odd spatial size exercises floor pooling)."""
+    from pcm_b200.src.unet import Down, Up
+
+    class DU(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.down = Down(8, 16)
+            self.up = Up(16, 8, 8)
+
+        def forward(self, x):
+            return self.up(self.down(x), x)
+
+    spec = O._convblock_spec("down.conv.", 8, 16) + [("up.up.weight", (16, 8, 2, 2)), ("up.up.bias", (8,))] \
+        + O._convblock_spec("up.conv.", 16, 8)
+    sd = O.synth_state_dict(spec, 9)
+    x, y = O.synth_frame_batch(2, 8, 12, 20, 10, out_ch=8)
+    fn = lambda a, s: O.up(O.down(a, s, "down."), a, s, "up.")
+    return compare(DU(), fn, sd, x, y, dtype)
+
+
+def case_cell_step(dtype):
+    """ConvLSTMCell with explicit non-zero state."""
+    from pcm_b200.src.convlstm import ConvLSTMCell
+    c_in, c_hid, B, H, W = 8, 8, 2, 6, 9
+    sd = O.synth_state_dict([("conv.weight", (4 * c_hid, c_in + c_hid, 3, 3)), ("conv.bias", (4 * c_hid,))], 11)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(B, c_in, H, W, generator=g)
+    h0 = torch.randn(B, c_hid, H, W, generator=g) * 0.5
+    c0 = torch.randn(B, c_hid, H, W, generator=g)
+    yh = torch.randn(B, c_hid, H, W, generator=g)
+    yc = torch.randn(B, c_hid, H, W, generator=g)
+    set_compute_dtype(dtype)
+    try:
+        cell = ConvLSTMCell(c_in, c_hid)
+        cell.load_state_dict(sd)
+        cell = cell.to(DEV)
+        xs = [t.to(DEV).requires_grad_(True) for t in (x, h0, c0)]
+        h1, c1 = cell(xs[0], (xs[1], xs[2]))
+        loss = ops.mse_loss(h1, yh.to(DEV)) + ops.mse_loss(c1, yc.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        set_compute_dtype(torch.bfloat16)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xo = [t.double().requires_grad_(True) for t in (x, h0, c0)]
+    ho, co = O.convlstm_cell(xo[0], xo[1], xo[2], sdd, "")
+    lo = O.mse_loss(ho, yh.double()) + O.mse_loss(co, yc.double())
+    lo.backward()
+    res = {"out": rel_l2(h1.detach().cpu().numpy(), ho.detach().numpy()),
+           "loss": abs(float(loss) - float(lo)) / float(lo),
+           "dx": rel_l2(xs[0].grad.cpu().numpy(), xo[0].grad.numpy()),
+           "grads": {"c_next": rel_l2(c1.detach().cpu().numpy(), co.detach().numpy()),
+                     "dh0": rel_l2(xs[1].grad.cpu().numpy(), xo[1].grad.numpy()),
+                     "dc0": rel_l2(xs[2].grad.cpu().numpy(), xo[2].grad.numpy())}, "gnorm": {}}
+    for k, p in cell.named_parameters():
+        res["grads"][k] = rel_l2(p.grad.cpu().numpy(), sdd[k].grad.numpy())
+    return res
+
+
+def case_metric(T=1080):
+    from pcm_b200 import metric as M
+    pred, true, lat = MO.synth_metric_arrays(T)
+    w = MO.get_lat_weights(lat)
+    want = {v: MO.metric_triplet(pred[:, i], true[:, i], w) for i, v in enumerate(["tas", "pr"])}
+    got = M.weighted_metric_triplets(torch.from_numpy(pred).to(DEV), torch.from_numpy(true).to(DEV), lat)
+    err = max(abs(got[i][j] - want[v][j]) / abs(want[v][j]) for i, v in enumerate(["tas", "pr"]) for j in range(3))
+    sc = M.combined_score({v: got[i] for i, v in enumerate(["tas", "pr"])})
+    return {"max_rel": err, "score_rel": abs(sc - MO.combined_score(want)) / MO.combined_score(want)}
+
+
+def case_metric_appendix_g():
+    from pcm_b200 import metric as M
+    fx = MO.known_answer_fixture()
+    pred = np.stack([fx["tas_pred"], fx["pr_pred"]], 1).astype(np.float32)
+    true = np.stack([fx["tas_true"], fx["pr_true"]], 1).astype(np.float32)
+    got = M.weighted_metric_triplets(torch.from_numpy(pred).to(DEV), torch.from_numpy(true).to(DEV), fx["lats"])
+    want = {"tas": [1.9653055953, 0.5983730314, 0.5430399866], "pr": [0.9742019753, 0.3126719193, 0.7152702066]}
+    err = max(abs(got[i][j] - want[v][j]) / want[v][j] for i, v in enumerate(["tas", "pr"]) for j in range(3))
+    sc = M.combined_score({v: got[i] for i, v in enumerate(["tas", "pr"])})
+    return {"max_rel": err, "score_rel": abs(sc - 1.1422441747) / 1.1422441747}
+
+
+def case_adam():
+    from pcm_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    ps = [torch.randn(1000, generator=g), torch.randn(37, 5, generator=g)]
+    params = [torch.nn.Parameter(p.clone().to(DEV)) for p in ps]
+    opt = FusedAdam(params, lr=5e-4)
+    ref = [p.clone() for p in ps]
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    for step in range(1, 5):
+        gr = [torch.randn(p.shape, generator=g) for p in ps]
+        for p, gg in zip(params, gr):
+            p.main_grad.copy_(gg.to(DEV))
+        opt.step()
+        for p, gg, m, v in zip(ref, gr, ms, vs):
+            O.adam_step(p, gg, m, v, step)
+    torch.cuda.synchronize()
+    return {"max_rel": max(rel_l2(p.detach().cpu().numpy(), r.numpy()) for p, r in zip(params, ref))}
+
+
+def case_season_stage():
+    g = torch.Generator().manual_seed(4)
+    x5 = torch.randn(6, 5, 8, 12, generator=g)
+    month = torch.randint(0, 12, (6,), generator=g)
+    y = ops.season_embed_stage(x5.to(DEV), month.to(DEV), torch.float32).cpu()
+    ang = 2 * math.pi * month.float() / 12
+    want = torch.zeros(6, 8, 12, 8)
+    want[..., :5] = x5.permute(0, 2, 3, 1)
+    want[..., 5] = torch.sin(ang)[:, None, None]
+    want[..., 6] = torch.cos(ang)[:, None, None]
+    return {"max_abs": float((y - want).abs().max())}
