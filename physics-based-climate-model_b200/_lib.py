@@ -61,7 +61,8 @@ class _Lib:
             fn.restype = ret
             fn.argtypes = [a for a, _ in args]
             self._fn[name] = fn
-        self.launches = 0                           # kernels-launched counter (bench `gpu_launches`)
+        self.launches = 0                           # C-ABI calls issued (bench `gpu_launches`)
+        self.trace = None                           # list -> per-call CUDA-event timing (bench roofline pass)
 
     def last_error(self) -> str:
         return self._fn["pcm_last_error"]().decode()
@@ -70,7 +71,16 @@ class _Lib:
         return int(self._fn["pcm_version"]())
 
     def call(self, name: str, *args):
-        rc = self._fn[name](*args)
+        if self.trace is not None:
+            import torch
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = self._fn[name](*args)
+            e1.record()
+            self.trace.append((name, args, e0, e1))
+        else:
+            rc = self._fn[name](*args)
         if rc != 0:
             raise RuntimeError(f"{name} failed (status {rc}): {self.last_error()}")
         self.launches += 1

@@ -1,0 +1,91 @@
+"""Data-parallel training step for the emulator models (one process per GPU).
+
+Replaces what Lightning's Trainer + DDP + torch.optim.Adam do around the reference's
+`training_step` (main_final.py:556-561, :737-747): forward -> MSE -> backward ->
+gradient all-reduce (mean over ranks, NCCL over NVLink/NVSwitch; skipped at world size 1) -> Adam.
+The whole step is captured once into a CUDA graph and replayed (the reference's step is ~8 000
+ATen launches; ours is a few hundred kernels whose launch cost the graph removes).
+
+Samples are independent (GroupNorm is per sample), so the path shards by batch with ONE exchange:
+the all-reduce of the flat gradient buffer (`post_conv`'s never-used parameters sit at its tail
+and are excluded — SURVEY F5)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import lib
+from .optim import FusedAdam
+
+
+class TrainStep:
+    def __init__(self, model: torch.nn.Module, x_shape, y_shape, lr: float = 5e-4, weight_decay: float = 0.0,
+                 use_graph: bool = True, process_group=None, device: Optional[torch.device] = None):
+        self.model = model
+        self.device = device or next(model.parameters()).device
+        unused = list(model.post_conv.parameters()) if hasattr(model, "post_conv") else []
+        self.opt = FusedAdam(model.parameters(), lr=lr, weight_decay=weight_decay, unused=unused)
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.pg = process_group
+        self.x = torch.zeros(x_shape, device=self.device, dtype=torch.float32)
+        self.y = torch.zeros(y_shape, device=self.device, dtype=torch.float32)
+        self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches_per_step = 0
+
+    # -- one eager step on the static buffers ---------------------------------------------------
+    def _step_impl(self):
+        self.opt.zero_grad()
+        out = self.model(self.x)
+        loss = ops.mse_loss(out, self.y)
+        loss.backward()
+        if self.world > 1:
+            g = self.opt.flat_grad[: self.opt.n_reduced]
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+        self.opt.step(grad_scale=1.0 / self.world)
+        self.loss.copy_(loss.detach())
+
+    def warmup_and_capture(self, warmup: int = 3):
+        """Eager warm-up on a side stream (also sizes the allocator), then capture the graph.
+        NOTE: warm-up steps DO update the weights; callers that need exact step counts should
+        re-load parameters and call `reset_optimizer_state()` afterwards."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for i in range(warmup):
+                n0 = lib().launches
+                self._step_impl()
+                self.launches_per_step = lib().launches - n0
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_impl()
+            torch.cuda.synchronize(self.device)
+
+    def reset_optimizer_state(self):
+        self.opt.exp_avg.zero_()
+        self.opt.exp_avg_sq.zero_()
+        self.opt.state.zero_()
+
+    def load_batch(self, x: torch.Tensor, y: torch.Tensor):
+        """Copy a batch (host pinned or device) into the static input buffers (async)."""
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+
+    def run(self):
+        """One optimisation step on whatever is in the static buffers; returns the device loss."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_impl()
+        return self.loss
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.load_batch(x, y)
+        return self.run()
