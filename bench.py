@@ -132,12 +132,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def kernel_trace(step_fn, n_steps=2):
+def kernel_trace(step_fn, n_steps=2, dump=None):
     """Eager steps with per-C-ABI-call CUDA events on the launching stream -> {name: [ms, calls, flops]}."""
     import torch
     from pcm_b200._lib import lib
     L = lib()
     agg = {}
+    calls = []
     torch.cuda.synchronize()
     for _ in range(n_steps):
         L.trace = []
@@ -156,10 +157,15 @@ def kernel_trace(step_fn, n_steps=2):
             elif name == "pcm_conv_wgrad":
                 Ha, Wa, Ca, Cb, N, KH, KW = a[3], a[4], a[5], a[12], a[18], a[19], a[20]
                 flops = 2.0 * N * Ha * Wa * Ca * Cb * KH * KW
+            calls.append((ms, name, flops, [x for x in a if isinstance(x, int) and abs(x) < (1 << 31)]))
             rec = agg.setdefault(key, [0.0, 0, 0.0])
             rec[0] += ms / n_steps
             rec[1] += 1.0 / n_steps
             rec[2] += flops / n_steps
+    if dump:
+        with open(dump, "w") as f:
+            for ms, name, flops, ints in calls[len(calls) // n_steps * (n_steps - 1):]:
+                f.write(f"{ms:9.4f} ms  {name:28s} {flops / 1e9:9.3f} GF  {flops / max(ms, 1e-6) / 1e9:9.2f} TF/s  {ints}\n")
     return agg
 
 
@@ -268,7 +274,7 @@ def run_ours(args):
 
     # ---- dominant kernel roofline: eager pass with per-call CUDA events on the launching stream -----------
     if rank == 0 and world == 1:
-        agg = kernel_trace(step._step_impl, n_steps=2)
+        agg = kernel_trace(step._step_impl, n_steps=2, dump=args.trace_file)
         tot = sum(v[0] for v in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1][0])
         name, (kms, calls, flops) = top[0]
@@ -304,6 +310,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace-file", default=None, help="write the per-call timing of one eager step here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

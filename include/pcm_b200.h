@@ -64,6 +64,15 @@ PCM_API int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int H
                     void* dst, long long dst_ns, int dst_ps, int Hd, int Wd, int Dc,
                     const void* wk, const float* bias, int N, int KH, int KW, int stride, int pad, int mode,
                     int dst_f32, int accumulate, int relu, int dtype, pcm_stream_t s);
+/* Tensor-core path (tcgen05 implicit GEMM, TMA-staged halo tiles; bf16 in, fp32 accumulate) for the
+ * 3x3 / stride 1 / pad 1 convolutions: dst(n,h,w,co) = sum_{kh,kw,ci} src(n,h+kh-1,w+kw-1,ci)*wk[kh*3+kw][co][ci]
+ * (+bias) (+= dst when accumulate; fp32 dst only).  wk is bf16 [9][Cout][Cin]; Cin in {16,32,64k},
+ * Cout multiple of 16, <= 256.  Data gradients use the same entry with flipped/transposed weights. */
+PCM_API int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                           long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                           int dst_f32, int accumulate, pcm_stream_t s);
+/* number of bounded-wait timeouts recorded by the tensor-core kernels since load (0 when healthy; syncs) */
+PCM_API int pcm_tc_error_count(void);
 /* weight gradient: dw[ac*sa + bc*sb + tap*st] += sum_{n,ha,wa} A(n,ha,wa,ac) * B(n,hb,wb,bc),
  * hb = ha*stride - pad + kh; only ac < Ca_real, bc < Cb_real are written.  fp32, accumulates. */
 PCM_API int pcm_conv_wgrad(const void* A, long long a_ns, int a_ps, int Ha, int Wa, int Ca, int Ca_real,

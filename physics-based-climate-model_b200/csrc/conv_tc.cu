@@ -1,0 +1,334 @@
+// 3x3 / stride-1 / pad-1 convolution as a tcgen05 implicit GEMM (sm_100a), NHWC bf16.
+//
+//   D[128 pixels x Cout] (fp32, TMEM) = sum over 9 taps, Cin chunks:  A_tap[128 x KC] * B_tap[Cout x KC]^T
+//
+// * A tiles are TMA boxes {KC channels, Wb, Hb, Nb} of the activation tensor, fetched at the tap's
+//   (kh-1, kw-1) offset — the hardware zero-fills out-of-bounds coordinates, which IS the conv padding,
+//   so halo tiles need no im2col buffer and no predication.  The box lands in shared memory as
+//   consecutive pixel rows of KC*2 bytes with the 32/64/128-byte swizzle == the canonical K-major UMMA
+//   operand layout.
+// * B tiles are boxes {KC, Cout, 1} of the packed weight [9][Cout][Cin].
+// * Persistent, warp-specialised CTA (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+//   thread), warps 2-5 = epilogue.  smem ring (full/empty mbarriers) between producer and MMA; the fp32
+//   accumulator is double buffered in TMEM (tmem_full/tmem_empty mbarriers) so the epilogue of tile i
+//   overlaps the MMAs of tile i+1.
+// * Epilogue: tcgen05.ld -> registers -> (+bias) (+= previous fp32 contents) -> bf16 / fp32 NHWC store.
+//
+// The same kernel is the data-gradient convolution (weights packed flipped + transposed) and the
+// ConvLSTM gate convolution (fp32 output, accumulate = Wx.x + Wh.h split).
+#include "tc_common.cuh"
+
+namespace pcm {
+
+using namespace tc;
+
+struct ConvTcParams {
+  int N, H, W, Cin, Cout;
+  int Wb, Hb, Nb, tiles_w, tiles_h, num_tiles;
+  int KC, kchunks, stages;
+  long long dst_ns;
+  int dst_ps, dst_f32, accumulate;
+  uint32_t tmem_cols, acc_stride, a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+};
+
+constexpr int kThreads = 192;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
+                  const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_stage_bytes);
+  uint64_t* full = bars;                  // [stages]
+  uint64_t* empty = bars + p.stages;      // [stages]
+  uint64_t* tfull = empty + p.stages;     // [2]
+  uint64_t* tempty = tfull + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kiters = 9 * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int th = (tile / p.tiles_w) % p.tiles_h;
+        const int tn = tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.Wb, h0 = th * p.Hb, n0 = tn * p.Nb;
+        for (int tap = 0; tap < 9 && ok; ++tap) {
+          const int kh = tap / 3, kw = tap % 3;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            ok = mbar_wait(&empty[stage], phase ^ 1, err);
+            if (!ok) break;
+            mbar_expect_tx(&full[stage], p.a_tx_bytes + p.b_tx_bytes);
+            tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + kw - 1, h0 + kh - 1, n0);
+            tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage], kc * p.KC, 0, tap);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
+      const uint32_t row_bytes = p.KC * 2;
+      const uint32_t ltype = layout_type_for_row_bytes(row_bytes);
+      const uint32_t sbo = 8 * row_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ok = mbar_wait(&tempty[acc], acc_phase ^ 1, err);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+        for (int ki = 0; ki < kiters; ++ki) {
+          ok = mbar_wait(&full[stage], phase, err);
+          if (!ok) break;
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)stage * p.a_stage_bytes), 16, sbo, ltype);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * p.b_stage_bytes), 16, sbo, ltype);
+          for (int k = 0; k < p.KC / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int mvalid = p.Wb * p.Hb * p.Nb;
+    int it = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tw = tile % p.tiles_w;
+      const int th = (tile / p.tiles_w) % p.tiles_h;
+      const int tn = tile / (p.tiles_w * p.tiles_h);
+      const int wl = row % p.Wb, hl = (row / p.Wb) % p.Hb, nl = row / (p.Wb * p.Hb);
+      const int w = tw * p.Wb + wl, h = th * p.Hb + hl, n = tn * p.Nb + nl;
+      const bool valid = row < mvalid && w < p.W && h < p.H && n < p.N;
+      const long long off = (long long)n * p.dst_ns + ((long long)h * p.W + w) * p.dst_ps;
+      ok = mbar_wait(&tfull[acc], acc_phase, err);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_addr + c0, v);
+        if (valid) {
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
+          }
+          if (p.dst_f32) {
+            float* dp = reinterpret_cast<float*>(dst) + off + c0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(dp + j);
+                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dst) + off + c0;
+            store8(dp, v);
+            store8(dp + 8, v + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int row_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PCM_ERR_CUDA; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return PCM_ERR_CUDA; }
+  return PCM_OK;
+}
+
+// choose the pixel box {Wb, Hb, Nb} (<= 128 rows) that wastes the fewest MMA rows
+void choose_tile(int N, int H, int W, int* Wb, int* Hb, int* Nb) {
+  double best = -1.0;
+  for (int wb = 1; wb <= W && wb <= 128; ++wb) {
+    if (W % wb != 0 && wb != 128) continue;
+    int hmax = 128 / wb;
+    if (hmax < 1) continue;
+    for (int hb = 1; hb <= hmax && hb <= H; ++hb) {
+      int nb = 1;
+      if (hb == H && wb == W) nb = 128 / (wb * hb);
+      if (nb > N) nb = N;
+      if (nb < 1) nb = 1;
+      const long long tiles = (long long)((W + wb - 1) / wb) * ((H + hb - 1) / hb) * ((N + nb - 1) / nb);
+      const double eff = (double)N * H * W / ((double)tiles * 128.0);
+      if (eff > best + 1e-9) { best = eff; *Wb = wb; *Hb = hb; *Nb = nb; }
+    }
+  }
+}
+
+static int g_num_sms = 0;
+
+unsigned int* tc_error_counter() {
+  static unsigned int* ptr = nullptr;
+  if (ptr == nullptr) {
+    if (cudaMalloc(&ptr, sizeof(unsigned int)) != cudaSuccess) { ptr = nullptr; return nullptr; }
+    cudaMemset(ptr, 0, sizeof(unsigned int));
+  }
+  return ptr;
+}
+
+}  // namespace pcm
+
+using namespace pcm;
+
+extern "C" int pcm_tc_error_count(void) {
+  unsigned int v = 0;
+  unsigned int* p = pcm::tc_error_counter();
+  if (p == nullptr || cudaMemcpy(&v, p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int)v;
+}
+
+extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                              long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                              int dst_f32, int accumulate, pcm_stream_t s) {
+  PCM_REQUIRE(Cin % 16 == 0 && Cin >= 16, "conv3x3_tc: Cin must be a multiple of 16 (got %d)", Cin);
+  PCM_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv3x3_tc: Cin above 64 must be a multiple of 64 (got %d)", Cin);
+  PCM_REQUIRE(Cin == 16 || Cin == 32 || Cin >= 64, "conv3x3_tc: unsupported Cin %d", Cin);
+  PCM_REQUIRE(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "conv3x3_tc: Cout must be a multiple of 16 in [16,256] (got %d)", Cout);
+  PCM_REQUIRE(src_ps % 8 == 0 && src_ns % 8 == 0 && dst_ps % 8 == 0, "conv3x3_tc: strides must be multiples of 8 elements");
+  PCM_REQUIRE(!accumulate || dst_f32, "conv3x3_tc: accumulate needs an fp32 destination");
+  PCM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(wk) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "conv3x3_tc: pointers must be 16-byte aligned");
+  if (N == 0) return PCM_OK;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  ConvTcParams p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  choose_tile(N, H, W, &p.Wb, &p.Hb, &p.Nb);
+  p.tiles_w = (W + p.Wb - 1) / p.Wb;
+  p.tiles_h = (H + p.Hb - 1) / p.Hb;
+  const int tiles_n = (N + p.Nb - 1) / p.Nb;
+  p.num_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  p.KC = Cin < 64 ? Cin : 64;
+  p.kchunks = Cin / p.KC;
+  p.dst_ns = dst_ns; p.dst_ps = dst_ps; p.dst_f32 = dst_f32; p.accumulate = accumulate;
+  p.acc_stride = Cout < 32 ? 32 : Cout;
+  uint32_t cols = 32;
+  while (cols < 2 * p.acc_stride) cols <<= 1;
+  p.tmem_cols = cols;
+  p.a_stage_bytes = 128u * p.KC * 2;
+  p.b_stage_bytes = ((uint32_t)Cout * p.KC * 2 + 1023u) & ~1023u;
+  p.a_tx_bytes = (uint32_t)(p.Wb * p.Hb * p.Nb) * p.KC * 2;
+  p.b_tx_bytes = (uint32_t)Cout * p.KC * 2;
+  const size_t per_stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+  int stages = (int)((200 * 1024) / per_stage);
+  if (stages > 8) stages = 8;
+  if (stages > 9 * p.kchunks) stages = 9 * p.kchunks;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = 1024 + stages * per_stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)src_ps * 2, (uint64_t)W * src_ps * 2, (uint64_t)src_ns * 2};
+    uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    int rc = make_tensor_map(&tmA, src, 4, dims, strides, box, p.KC * 2);
+    if (rc != PCM_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+    uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+    uint32_t box[3] = {(uint32_t)p.KC, (uint32_t)Cout, 1};
+    int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, p.KC * 2);
+    if (rc != PCM_OK) return rc;
+  }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("conv3x3_tc: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
+    smem_set = smem;
+  }
+  unsigned int* err = tc_error_counter();
+  PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  conv3x3_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, p);
+  return check_launch("conv3x3_tc");
+}

@@ -28,6 +28,11 @@ def pad8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
+def padc(c: int) -> int:
+    """Channel padding of staged activations: 16 = one UMMA K step of bf16."""
+    return (c + 15) // 16 * 16
+
+
 def _p(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
@@ -57,28 +62,58 @@ def _grad_buf(p: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # ------------------------------------------------------------------------------------------------
-def pack_weight(w: torch.Tensor, so: int, si: int, st: int, O: int, I: int, taps: int, dtype, offset: int = 0):
-    """out[t][o][i] = w.flatten()[offset + o*so + i*si + t*st], zero padded to (taps, pad8(O), pad8(I))."""
-    Op, Ip = pad8(O), pad8(I)
+def pack_weight(w: torch.Tensor, so: int, si: int, st: int, O: int, I: int, taps: int, dtype, offset: int = 0,
+                Op: Optional[int] = None, Ip: Optional[int] = None):
+    """out[t][o][i] = w.flatten()[offset + o*so + i*si + t*st], zero padded to (taps, Op, Ip)."""
+    Op = pad8(O) if Op is None else Op
+    Ip = pad8(I) if Ip is None else Ip
     out = torch.empty((taps, Op, Ip), device=w.device, dtype=dtype)
     _call("pcm_pack_weight", w.data_ptr() + 4 * offset, so, si, st, O, I, taps, Op, Ip, out.data_ptr(), _DT[dtype], _s())
     return out
 
 
-def conv_weight_fwd(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None):
-    """nn.Conv2d weight (Co, Ci_tot, KH, KW) -> [taps][Co][Ci] for mode-0 gather."""
+def conv_weight_fwd(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None, Ip: Optional[int] = None):
+    """nn.Conv2d weight (Co, Ci_tot, KH, KW) -> [taps][Co][Ci] (forward, gather mode 0)."""
     Co, Ci_tot, KH, KW = w.shape
     ci = Ci_tot - ci_off if ci is None else ci
     K = KH * KW
-    return pack_weight(w, Ci_tot * K, K, 1, Co, ci, K, dtype, offset=ci_off * K)
+    return pack_weight(w, Ci_tot * K, K, 1, Co, ci, K, dtype, offset=ci_off * K, Ip=Ip)
 
 
-def conv_weight_dgrad(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None):
-    """nn.Conv2d weight -> [taps][Ci][Co] for mode-1 gather (data gradient)."""
+def conv_weight_dgrad(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None, Op: Optional[int] = None):
+    """nn.Conv2d weight (stride 1, odd K) -> [taps][Ci][Co] with the taps FLIPPED, so the data gradient
+    is itself a forward (mode 0) convolution of dy: dx = conv(dy, flip(W)^T)."""
     Co, Ci_tot, KH, KW = w.shape
     ci = Ci_tot - ci_off if ci is None else ci
     K = KH * KW
-    return pack_weight(w, K, Ci_tot * K, 1, ci, Co, K, dtype, offset=ci_off * K)
+    return pack_weight(w, K, Ci_tot * K, -1, ci, Co, K, dtype, offset=ci_off * K + K - 1, Op=Op)
+
+
+def tc_supported(dtype, Sc: int, Dc: int, K: int = 3) -> bool:
+    """Shapes the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu) takes; everything else runs on the
+    general-shape SIMT gather kernel."""
+    return (dtype == torch.bfloat16 and K == 3 and (Sc in (16, 32) or (Sc >= 64 and Sc % 64 == 0))
+            and Dc % 16 == 0 and 16 <= Dc <= 256)
+
+
+def conv_s1(src, wk, N, H, W, Sc, Dc, K=3, dst=None, dst_f32=False, bias=None, accumulate=False,
+            src_ns=None, src_ps=None, dst_ns=None, dst_ps=None, src_off=0, dst_off=0):
+    """Stride-1 'same' convolution dst = conv(src, wk) on NHWC views; wk = [K*K][Dc][Sc]."""
+    dtype = src.dtype
+    if not tc_supported(dtype, Sc, Dc, K):
+        return conv_gather(src, wk, N, H, W, Sc, H, W, Dc, K, K, 1, K // 2, 0, dst=dst, dst_f32=dst_f32, bias=bias,
+                           accumulate=accumulate, src_ns=src_ns, src_ps=src_ps, dst_ns=dst_ns, dst_ps=dst_ps,
+                           src_off=src_off, dst_off=dst_off)
+    if dst is None:
+        dst = torch.empty((N, H, W, Dc), device=src.device, dtype=torch.float32 if dst_f32 else dtype)
+    src_ps = Sc if src_ps is None else src_ps
+    dst_ps = Dc if dst_ps is None else dst_ps
+    src_ns = H * W * src_ps if src_ns is None else src_ns
+    dst_ns = H * W * dst_ps if dst_ns is None else dst_ns
+    _call("pcm_conv3x3_tc", src.data_ptr() + src_off * src.element_size(), src_ns, src_ps, H, W, Sc,
+          dst.data_ptr() + dst_off * dst.element_size(), dst_ns, dst_ps, Dc, wk.data_ptr(), _p(bias), N,
+          int(dst_f32), int(accumulate), _s())
+    return dst
 
 
 def conv_gather(src, wk, N, Hs, Ws, Sc, Hd, Wd, Dc, KH, KW, stride, pad, mode, dst=None, dst_f32=False,
@@ -119,14 +154,14 @@ def channel_sum(x, out, N, P, C, C_real, ns=None, ps=None, off=0, per_image=Fals
 # layout staging at the module boundary (NCHW fp32 <-> NHWC compute dtype)
 # ------------------------------------------------------------------------------------------------
 class StageIn(torch.autograd.Function):
-    """(N, C, H, W) fp32 -> (N, H, W, pad8(C)) compute dtype."""
+    """(N, C, H, W) fp32 -> (N, H, W, padc(C)) compute dtype."""
 
     @staticmethod
-    def forward(ctx, x, dtype):
+    def forward(ctx, x, dtype, gran=16):
         _require_cuda(x, "input")
         x = x.contiguous().float()
         N, C, H, W = x.shape
-        Cp = pad8(C)
+        Cp = (C + gran - 1) // gran * gran
         y = torch.empty((N, H, W, Cp), device=x.device, dtype=dtype)
         _call("pcm_nchw_to_nhwc", x.data_ptr(), y.data_ptr(), N, C, H, W, Cp, _DT[dtype], _s())
         ctx.shape = (N, C, H, W)
@@ -138,7 +173,7 @@ class StageIn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty((N, C, H, W), device=dy.device, dtype=torch.float32)
         _call("pcm_nhwc_to_nchw", dy.data_ptr(), dx.data_ptr(), N, C, H, W, dy.shape[-1], _DT[dy.dtype], _s())
-        return dx, None
+        return dx, None, None
 
 
 class StageOut(torch.autograd.Function):
@@ -165,13 +200,13 @@ class StageOut(torch.autograd.Function):
 
 def season_embed_stage(x5: torch.Tensor, month: torch.Tensor, dtype) -> torch.Tensor:
     """main_final.py:186-216: (N,5,H,W) forcings + month index (N,) -> NHWC 8-channel frames with
-    sin/cos month channels synthesised on the fly (no gradient: inputs are data)."""
+    sin/cos month channels (5, 6) synthesised on the fly, padded to 16 channels (no gradient: inputs are data)."""
     _require_cuda(x5, "input")
     N, C, H, W = x5.shape
     assert C == 5
-    y = torch.empty((N, H, W, 8), device=x5.device, dtype=dtype)
+    y = torch.empty((N, H, W, 16), device=x5.device, dtype=dtype)
     _call("pcm_season_embed_stage", x5.contiguous().float().data_ptr(), month.to(torch.int32).contiguous().data_ptr(),
-          y.data_ptr(), N, H, W, 8, _DT[dtype], _s())
+          y.data_ptr(), N, H, W, 16, _DT[dtype], _s())
     return y
 
 
@@ -185,7 +220,7 @@ class ConvBlockFn(torch.autograd.Function):
         x = x.contiguous()
         N, H, W, Cip = x.shape
         Co, Ci = w1.shape[0], w1.shape[1]
-        assert pad8(Ci) == Cip and Co % 8 == 0, (Ci, Cip, Co)
+        assert Ci <= Cip and Cip % 8 == 0 and Co % 8 == 0, (Ci, Cip, Co)
         Cr = sw1.shape[0]
         P, G, dt, dev = H * W, GN_GROUPS, x.dtype, x.device
         d = _DT[dt]
@@ -195,14 +230,14 @@ class ConvBlockFn(torch.autograd.Function):
         stats1 = small[: N * G * 2]
         stats2 = small[N * G * 2: N * G * 4]
         pool = small[N * G * 4:]
-        wk1 = conv_weight_fwd(w1, dt)
-        y1 = conv_gather(x, wk1, N, H, W, Cip, H, W, Co, 3, 3, 1, 1, 0)
+        wk1 = conv_weight_fwd(w1, dt, Ip=Cip)
+        y1 = conv_s1(x, wk1, N, H, W, Cip, Co)
         _call("pcm_gn_stats", y1.data_ptr(), stats1.data_ptr(), N, P, Co, G, d, st)
         a1 = torch.empty_like(y1)
         _call("pcm_gn_silu_fwd", y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(), b1.data_ptr(), a1.data_ptr(), 0,
               N, P, Co, G, GN_EPS, d, st)
         wk2 = conv_weight_fwd(w2, dt)
-        y2 = conv_gather(a1, wk2, N, H, W, Co, H, W, Co, 3, 3, 1, 1, 0)
+        y2 = conv_s1(a1, wk2, N, H, W, Co, Co)
         _call("pcm_gn_stats", y2.data_ptr(), stats2.data_ptr(), N, P, Co, G, d, st)
         a2 = torch.empty_like(y2)
         _call("pcm_gn_silu_fwd", y2.data_ptr(), stats2.data_ptr(), g2.data_ptr(), b2.data_ptr(), a2.data_ptr(),
@@ -258,7 +293,7 @@ class ConvBlockFn(torch.autograd.Function):
         # conv2: weight + data gradients
         conv_wgrad(dy2, a1, gw2, Co * 9, 9, 1, N, H, W, Co, Co, H, W, Co, Co, 3, 3, 1, 1)
         wk2t = conv_weight_dgrad(w2, dt)
-        da1 = conv_gather(dy2, wk2t, N, H, W, Co, H, W, Co, 3, 3, 1, 1, 1, dst=da2)     # reuse da2 storage
+        da1 = conv_s1(dy2, wk2t, N, H, W, Co, Co, dst=da2)                                # reuse da2 storage
         _call("pcm_gn_silu_bwd_reduce", da1.data_ptr(), 0, y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(),
               b1.data_ptr(), gsum1.data_ptr(), gg1.data_ptr(), gb1.data_ptr(), N, P, Co, G, GN_EPS, d, st)
         dy1 = dy2                                                                          # reuse dy2 storage
@@ -267,8 +302,8 @@ class ConvBlockFn(torch.autograd.Function):
         conv_wgrad(dy1, x, gw1, Ci * 9, 9, 1, N, H, W, Co, Co, H, W, Cip, Ci, 3, 3, 1, 1)
         dx = None
         if ctx.needs_input_grad[0]:
-            wk1t = conv_weight_dgrad(w1, dt)
-            dx = conv_gather(dy1, wk1t, N, H, W, Co, H, W, Cip, 3, 3, 1, 1, 1)
+            wk1t = conv_weight_dgrad(w1, dt, Op=Cip)
+            dx = conv_s1(dy1, wk1t, N, H, W, Co, Cip)
         return dx, rw1, rg1, rb1, rw2, rg2, rb2, rs1, rs2, rsp
 
 
@@ -392,23 +427,22 @@ class ConvLSTMFn(torch.autograd.Function):
         Ci = w.shape[1] - Ch
         K = w.shape[-1]
         pad = K // 2
-        assert pad8(Ci) == Cip and Ch % 8 == 0
+        assert Ci <= Cip and Cip % 8 == 0 and Ch % 8 == 0
         P, dt, dev = H * W, x.dtype, x.device
         d, st = _DT[dt], _s()
         img = P * Cip
-        wx = conv_weight_fwd(w, dt, 0, Ci)
+        wx = conv_weight_fwd(w, dt, 0, Ci, Ip=Cip)
         wh = conv_weight_fwd(w, dt, Ci, Ch)
         gates = torch.empty((T, B, P, 4 * Ch), device=dev, dtype=torch.float32)
         acts = torch.empty((T, B, P, 4 * Ch), device=dev, dtype=dt)
         c_all = torch.empty((T, B, P, Ch), device=dev, dtype=torch.float32)
         h_all = torch.empty((T, B, H, W, Ch), device=dev, dtype=dt)
         for t in range(T):
-            conv_gather(x, wx, B, H, W, Cip, H, W, 4 * Ch, K, K, 1, pad, 0, dst=gates[t], dst_f32=True, bias=b,
-                        src_ns=st_b * img, src_off=t * st_t * img, dtype=dt)
+            conv_s1(x, wx, B, H, W, Cip, 4 * Ch, K, dst=gates[t], dst_f32=True, bias=b,
+                    src_ns=st_b * img, src_off=t * st_t * img)
         for t in range(T):
             if t > 0:
-                conv_gather(h_all[t - 1], wh, B, H, W, Ch, H, W, 4 * Ch, K, K, 1, pad, 0, dst=gates[t], dst_f32=True,
-                            accumulate=True, dtype=dt)
+                conv_s1(h_all[t - 1], wh, B, H, W, Ch, 4 * Ch, K, dst=gates[t], dst_f32=True, accumulate=True)
             _call("pcm_lstm_cell_fwd", gates[t].data_ptr(), c_all[t - 1].data_ptr() if t > 0 else 0,
                   acts[t].data_ptr(), c_all[t].data_ptr(), h_all[t].data_ptr(), B * P, Ch, d, st)
         ctx.save_for_backward(x, w, b, acts, c_all, h_all)
@@ -439,7 +473,7 @@ class ConvLSTMFn(torch.autograd.Function):
                   acts[t].data_ptr(), c_all[t - 1].data_ptr() if t > 0 else 0, c_all[t].data_ptr(),
                   dgates[t].data_ptr(), dc[t & 1].data_ptr(), B * P, Ch, d, st)
             if t > 0:
-                dh_next = conv_gather(dgates[t], wht, B, H, W, 4 * Ch, H, W, Ch, K, K, 1, pad, 1, dst=dh_next)
+                dh_next = conv_s1(dgates[t], wht, B, H, W, 4 * Ch, Ch, K, dst=dh_next)
         KK = K * K
         Ct = Ci + Ch
         # dW[:, :Ci] — x frames may be time-strided, one launch per step; dW[:, Ci:] — one launch over t>=1
@@ -452,11 +486,10 @@ class ConvLSTMFn(torch.autograd.Function):
         channel_sum(dgates, gb, T * B, P, 4 * Ch, 4 * Ch)
         dx = None
         if ctx.needs_input_grad[0]:
-            wxt = conv_weight_dgrad(w, dt, 0, Ci)
+            wxt = conv_weight_dgrad(w, dt, 0, Ci, Op=Cip)
             dx = torch.empty_like(x)
             for t in range(T):
-                conv_gather(dgates[t], wxt, B, H, W, 4 * Ch, H, W, Cip, K, K, 1, pad, 1, dst=dx,
-                            dst_ns=st_b * img, dst_off=t * st_t * img)
+                conv_s1(dgates[t], wxt, B, H, W, 4 * Ch, Cip, K, dst=dx, dst_ns=st_b * img, dst_off=t * st_t * img)
         return dx, rw, rb, None, None, None, None, None
 
 
@@ -611,10 +644,10 @@ class CellStepFn(torch.autograd.Function):
         xh, c = xh.contiguous(), c.contiguous()
         B, H, W, Cp = xh.shape
         Ch, Ct, K = w.shape[0] // 4, w.shape[1], w.shape[-1]
-        assert pad8(Ct) == Cp and Ch % 8 == 0
+        assert Ct <= Cp and Ch % 8 == 0
         P, dt, dev = H * W, xh.dtype, xh.device
-        wk = conv_weight_fwd(w, dt)
-        gates = conv_gather(xh, wk, B, H, W, Cp, H, W, 4 * Ch, K, K, 1, K // 2, 0, dst_f32=True, bias=b)
+        wk = conv_weight_fwd(w, dt, Ip=Cp)
+        gates = conv_s1(xh, wk, B, H, W, Cp, 4 * Ch, K, dst_f32=True, bias=b)
         acts = torch.empty((B, P, 4 * Ch), device=dev, dtype=dt)
         c2 = torch.empty((B, H, W, Ch), device=dev, dtype=torch.float32)
         h2 = torch.empty((B, H, W, Ch), device=dev, dtype=dt)
@@ -638,6 +671,6 @@ class CellStepFn(torch.autograd.Function):
               dgates.data_ptr(), dcp.data_ptr(), B * P, Ch, _DT[dt], _s())
         conv_wgrad(dgates, xh, gw, Ct * K * K, K * K, 1, B, H, W, 4 * Ch, 4 * Ch, H, W, Cp, Ct, K, K, 1, K // 2)
         channel_sum(dgates, gb, B, P, 4 * Ch, 4 * Ch)
-        wkt = conv_weight_dgrad(w, dt)
-        dxh = conv_gather(dgates, wkt, B, H, W, 4 * Ch, H, W, Cp, K, K, 1, K // 2, 1)
+        wkt = conv_weight_dgrad(w, dt, Op=Cp)
+        dxh = conv_s1(dgates, wkt, B, H, W, 4 * Ch, Cp, K)
         return dxh, dcp, rw, rb

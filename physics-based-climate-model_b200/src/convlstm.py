@@ -52,6 +52,6 @@ def _cell_step(cell: ConvLSTMCell, x, h, c):
     Ch = conv.out_channels // 4
     dt = compute_dtype()
     xh = ops.StageIn.apply(torch.cat([x, h], dim=1), dt)        # cat is layout plumbing, no arithmetic
-    cs = ops.StageIn.apply(c, torch.float32)
+    cs = ops.StageIn.apply(c, torch.float32, 8)
     h2, c2 = ops.CellStepFn.apply(xh, cs, conv.weight, conv.bias)
     return ops.StageOut.apply(h2, Ch), ops.StageOut.apply(c2, Ch)

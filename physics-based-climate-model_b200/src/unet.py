@@ -25,7 +25,9 @@ class SEBlock(nn.Module):
 
     def forward(self, x):
         N, C, H, W = x.shape
-        a = ops.StageIn.apply(x, compute_dtype())
+        if C % 8 != 0:
+            raise RuntimeError("pcm_b200 SEBlock needs a channel count that is a multiple of 8")
+        a = ops.StageIn.apply(x, compute_dtype(), 8)
         y = ops.SEFn.apply(a, self.fc[0].weight, self.fc[2].weight)
         return ops.StageOut.apply(y, C)
 
@@ -41,7 +43,7 @@ class SpatialGate(nn.Module):
         N, C, H, W = x.shape
         if C % 8 != 0:
             raise RuntimeError("pcm_b200 SpatialGate needs a channel count that is a multiple of 8")
-        a = ops.StageIn.apply(x, compute_dtype())
+        a = ops.StageIn.apply(x, compute_dtype(), 8)
         y = ops.SpatialGateFn.apply(a, self.conv.weight)
         return ops.StageOut.apply(y, C)
 

@@ -227,7 +227,7 @@ def case_season_stage():
     month = torch.randint(0, 12, (6,), generator=g)
     y = ops.season_embed_stage(x5.to(DEV), month.to(DEV), torch.float32).cpu()
     ang = 2 * math.pi * month.float() / 12
-    want = torch.zeros(6, 8, 12, 8)
+    want = torch.zeros(6, 8, 12, 16)
     want[..., :5] = x5.permute(0, 2, 3, 1)
     want[..., 5] = torch.sin(ang)[:, None, None]
     want[..., 6] = torch.cos(ang)[:, None, None]

@@ -1,0 +1,102 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu, called through the C ABI) against the
+general-shape SIMT gather kernel and against torch's CPU conv on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import pcm_b200  # noqa: F401
+    from pcm_b200 import ops
+    return ops
+
+
+def _ref(x, w, bias):
+    """x (N,H,W,Ci) bf16-rounded, w (Co,Ci,3,3) bf16-rounded -> NHWC fp32 via torch CPU (fp64 accumulate)."""
+    y = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), None if bias is None else bias.double(), padding=1)
+    return y.permute(0, 2, 3, 1).float()
+
+
+SHAPES = [  # (N, H, W, Cin, Cout): every 3x3 layer geometry of unet_convlstm_attention (config 3) + ragged cases
+    (5, 48, 72, 16, 16), (3, 24, 36, 16, 32), (3, 24, 36, 32, 32), (4, 12, 18, 32, 64), (4, 12, 18, 64, 64),
+    (7, 6, 9, 64, 128), (7, 6, 9, 128, 128), (6, 6, 9, 128, 256), (5, 6, 9, 64, 256), (3, 6, 9, 256, 128),
+    (3, 6, 9, 256, 64), (2, 12, 18, 128, 64), (2, 24, 36, 64, 32), (2, 48, 72, 32, 16),
+    (3, 23, 45, 64, 64), (1, 7, 200, 32, 48), (2, 5, 5, 16, 16), (1, 130, 3, 16, 32),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv3x3_tc_matches_reference(ops, shape):
+    from pcm_b200._lib import lib
+    N, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(N * 1000 + H * 10 + Ci + Co)
+    x = torch.randn(N, H, W, Ci, generator=g).bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Ci ** 0.5)).bfloat16()
+    bias = torch.randn(Co, generator=g)
+    want = _ref(x, w, bias)
+    xg, wg, bg = x.cuda(), w.float().cuda(), bias.cuda()
+    assert ops.tc_supported(torch.bfloat16, Ci, Co)
+    wk = ops.conv_weight_fwd(wg, torch.bfloat16)
+    got = ops.conv_s1(xg, wk, N, H, W, Ci, Co, dst_f32=True, bias=bg)
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    err = float((got.cpu() - want).norm() / want.norm())
+    assert err < 2e-6, err
+    # SIMT kernel on the same operands (fp32 accumulate in a different order)
+    simt = ops.conv_gather(xg, wk, N, H, W, Ci, H, W, Co, 3, 3, 1, 1, 0, dst_f32=True, bias=bg)
+    assert float((got - simt).norm() / simt.norm()) < 2e-6
+    # bf16 destination
+    got16 = ops.conv_s1(xg, wk, N, H, W, Ci, Co, bias=bg)
+    assert float((got16.float().cpu() - want).norm() / want.norm()) < 4e-3
+
+
+def test_conv3x3_tc_accumulate_and_views(ops):
+    """fp32 accumulate (ConvLSTM Wx.x + Wh.h split), time-strided source images, channel-slice source view."""
+    T, B, H, W, Ci, Co = 3, 4, 6, 9, 64, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, H, W, Ci, generator=g).bfloat16()          # image n = b*T + t
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / 24).bfloat16()
+    base = torch.randn(T, B, H, W, Co, generator=g)
+    xg, wk = x.cuda(), ops.conv_weight_fwd(w.float().cuda(), torch.bfloat16)
+    out = base.clone().cuda()
+    img = H * W * Ci
+    for t in range(T):
+        ops.conv_s1(xg, wk, B, H, W, Ci, Co, dst=out[t], dst_f32=True, accumulate=True, src_ns=T * img, src_off=t * img)
+    torch.cuda.synchronize()
+    for t in range(T):
+        want = base[t] + _ref(x[:, t], w, None)
+        assert float((out[t].cpu() - want).norm() / want.norm()) < 2e-6
+    # source = channels [32, 64) of a 96-channel concat buffer; destination = channels [16, 48) of a 64-channel one
+    cat = torch.randn(2, 12, 18, 96, generator=g).bfloat16()
+    w2 = (torch.randn(32, 32, 3, 3, generator=g) / 17).bfloat16()
+    wk2 = ops.conv_weight_fwd(w2.float().cuda(), torch.bfloat16)
+    dst = torch.zeros(2, 12, 18, 64, dtype=torch.bfloat16).cuda()
+    ops.conv_s1(cat.cuda(), wk2, 2, 12, 18, 32, 32, dst=dst, src_ps=96, src_off=32, dst_ps=64, dst_off=16)
+    torch.cuda.synchronize()
+    want = _ref(cat[..., 32:64], w2, None)
+    got = dst.float().cpu()
+    assert float((got[..., 16:48] - want).norm() / want.norm()) < 4e-3
+    assert float(got[..., :16].abs().max()) == 0.0 and float(got[..., 48:].abs().max()) == 0.0
+
+
+def test_dgrad_weights_flip(ops):
+    """dx = conv(dy, flip(W)^T): the data gradient through the same kernel, vs torch autograd."""
+    N, H, W, Ci, Co = 2, 12, 18, 32, 64
+    g = torch.Generator().manual_seed(9)
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / 17).bfloat16().float()
+    dy = torch.randn(N, H, W, Co, generator=g).bfloat16()
+    x = torch.zeros(N, Ci, H, W, requires_grad=True, dtype=torch.float64)
+    F.conv2d(x, w.double(), padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    want = x.grad.permute(0, 2, 3, 1).float()
+    wkt = ops.conv_weight_dgrad(w.cuda(), torch.bfloat16)
+    for use in ("tc", "simt"):
+        if use == "tc":
+            got = ops.conv_s1(dy.cuda(), wkt, N, H, W, Co, Ci, dst_f32=True)
+        else:
+            got = ops.conv_gather(dy.cuda(), wkt, N, H, W, Co, H, W, Ci, 3, 3, 1, 1, 0, dst_f32=True)
+        assert float((got.cpu() - want).norm() / want.norm()) < 2e-6, use
