@@ -71,6 +71,13 @@ PCM_API int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int H
 PCM_API int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, pcm_stream_t s);
+/* Tensor-core weight gradient of the same convolution (GEMM over the pixel dimension, MN-major operands
+ * straight from NHWC, all taps from ONE halo tile): dw[co*sa + ci*sb + tap*st] += sum_p dy(p,co)*x(p+tap,ci).
+ * dy: Co in {16,32,64,128k}; x: Ci in {16,32,64,128,192,256}; only co < Co_real, ci < Ci_real are written.
+ * fp32, accumulates (atomics). */
+PCM_API int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
+                            long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
+                            long long st, int N, int H, int W, pcm_stream_t s);
 /* number of bounded-wait timeouts recorded by the tensor-core kernels since load (0 when healthy; syncs) */
 PCM_API int pcm_tc_error_count(void);
 /* weight gradient: dw[ac*sa + bc*sb + tap*st] += sum_{n,ha,wa} A(n,ha,wa,ac) * B(n,hb,wb,bc),

@@ -16,6 +16,8 @@
 //
 // The same kernel is the data-gradient convolution (weights packed flipped + transposed) and the
 // ConvLSTM gate convolution (fp32 output, accumulate = Wx.x + Wh.h split).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace pcm {
@@ -33,6 +35,7 @@ struct ConvTcParams {
 
 constexpr int kThreads = 192;
 
+template <int KSTEPS>   // KC / 16: UMMA K-steps per pipeline stage
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
@@ -92,33 +95,39 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
+      // The issuing thread is instruction-bound for small N: keep the loop to a handful of SASS
+      // instructions per MMA (descriptors are start-address increments of two precomputed bases).
       const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
-      const uint32_t row_bytes = p.KC * 2;
+      constexpr uint32_t row_bytes = KSTEPS * 32;
       const uint32_t ltype = layout_type_for_row_bytes(row_bytes);
-      const uint32_t sbo = 8 * row_bytes;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 8 * row_bytes, ltype);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 8 * row_bytes, ltype);
+      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      const int nstages = p.stages, ntiles = p.num_tiles, acc_stride = p.acc_stride;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ok = mbar_wait(&tempty[acc], acc_phase ^ 1, err);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
         for (int ki = 0; ki < kiters; ++ki) {
           ok = mbar_wait(&full[stage], phase, err);
           if (!ok) break;
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)stage * p.a_stage_bytes), 16, sbo, ltype);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * p.b_stage_bytes), 16, sbo, ltype);
-          for (int k = 0; k < p.KC / 16; ++k) {
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * a_step);
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * b_step);
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (ok) umma_commit(&tfull[acc]);
       }
@@ -182,6 +191,200 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thin-layer variant (Cin = 16 or 32, i.e. 32/64-byte pixel rows).  TMA throughput is per box ROW
+// (~4 cycles/row measured), so fetching nine shifted 32-byte-row boxes per tile starves the MMA.
+// Here each tile fetches ONE halo box {Cin, Wb+2, Hb+2, Nb}; the nine taps are nine UMMA descriptors
+// into the same shared-memory image whose start address is advanced by (kh*(Wb+2) + kw) pixel rows
+// (the layout is dense, SBO = 8 rows, so a row shift is a pure start-address offset).  The GEMM M index
+// is the flattened halo position; the two halo columns per row produce don't-care accumulator rows the
+// epilogue skips.  All nine weight taps (<= 64 KB) are loaded once per CTA and stay resident.
+// ------------------------------------------------------------------------------------------------
+struct ConvHaloParams {
+  int N, H, W, Cin, Cout;
+  int Wb, Hb, Nb, Wh, Hh, tiles_w, tiles_h, num_tiles;
+  int stages;
+  long long dst_ns;
+  int dst_ps, dst_f32, accumulate;
+  uint32_t tmem_cols, acc_stride, a_stage_bytes, a_tx_bytes, b_bytes;
+};
+
+template <int KSTEPS>   // Cin / 16
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
+                       const ConvHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t b_region = (p.b_bytes + 1023u) & ~1023u;
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + b_region;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)p.stages * p.a_stage_bytes);
+  uint64_t* full = bars;                  // [stages]
+  uint64_t* empty = bars + p.stages;      // [stages]
+  uint64_t* tfull = empty + p.stages;     // [2]
+  uint64_t* tempty = tfull + 2;           // [2]
+  uint64_t* bfull = tempty + 2;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    mbar_init(bfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t row_bytes = p.Cin * 2;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bfull, p.b_bytes);
+      tma_load_3d(sB, &tmB, bfull, 0, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int th = (tile / p.tiles_w) % p.tiles_h;
+        const int tn = tile / (p.tiles_w * p.tiles_h);
+        if (!mbar_wait(&empty[stage], phase ^ 1, err)) break;
+        mbar_expect_tx(&full[stage], p.a_tx_bytes);
+        tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], 0, tw * p.Wb - 1, th * p.Hb - 1, tn * p.Nb);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // Tight issue loop: per-tap descriptor increments live in registers (fully unrolled), so each
+      // MMA costs a 64-bit add + the UTCHMMA (the single issuing thread is otherwise instruction-bound:
+      // ncu showed ~400 cycles of address arithmetic per MMA in the first version of this loop).
+      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
+      constexpr uint32_t rb = KSTEPS * 32;
+      const uint32_t ltype = layout_type_for_row_bytes(rb);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 8 * rb, ltype);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 8 * rb, ltype);
+      uint32_t a_off[9], b_off[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        a_off[tap] = ((uint32_t)((tap / 3) * p.Wh + (tap % 3)) * rb) >> 4;
+        b_off[tap] = ((uint32_t)tap * p.Cout * rb) >> 4;
+      }
+      const uint32_t a_step = p.a_stage_bytes >> 4;
+      const int nstages = p.stages, ntiles = p.num_tiles, acc_stride = p.acc_stride;
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      bool ok = mbar_wait(bfull, 0, err);
+      for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ok = mbar_wait(&tempty[acc], acc_phase ^ 1, err);
+        if (!ok) break;
+        ok = mbar_wait(&full[stage], phase, err);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        const uint64_t abase = adesc0 + (uint64_t)(stage * a_step);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k)
+            umma_bf16(d_tmem, abase + (uint64_t)(a_off[tap] + 2 * k), bdesc0 + (uint64_t)(b_off[tap] + 2 * k), idesc,
+                      (tap | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[acc]);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int per_img = p.Hh * p.Wh;
+    const int nl = row / per_img, rem = row % per_img;
+    const int hl = rem / p.Wh, wl = rem % p.Wh;
+    const bool row_ok = nl < p.Nb && hl < p.Hb && wl < p.Wb;
+    int it = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tw = tile % p.tiles_w;
+      const int th = (tile / p.tiles_w) % p.tiles_h;
+      const int tn = tile / (p.tiles_w * p.tiles_h);
+      const int w = tw * p.Wb + wl, h = th * p.Hb + hl, n = tn * p.Nb + nl;
+      const bool valid = row_ok && w < p.W && h < p.H && n < p.N;
+      const long long off = (long long)n * p.dst_ns + ((long long)h * p.W + w) * p.dst_ps;
+      ok = mbar_wait(&tfull[acc], acc_phase, err);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_addr + c0, v);
+        if (valid) {
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
+          }
+          if (p.dst_f32) {
+            float* dp = reinterpret_cast<float*>(dst) + off + c0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(dp + j);
+                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dst) + off + c0;
+            store8(dp, v);
+            store8(dp + 8, v + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// halo tile chooser: last valid flattened row (Nb-1)*Hh*Wh + (Hb-1)*Wh + Wb-1 must be <= 127
+void choose_tile_halo(int N, int H, int W, int* Wb, int* Hb, int* Nb) {
+  double best = -1.0;
+  for (int wb = 1; wb <= W && wb <= 126; ++wb) {
+    if (W % wb != 0) continue;
+    const int wh = wb + 2;
+    for (int hb = 1; hb <= H; ++hb) {
+      if ((hb - 1) * wh + wb - 1 > 127) break;
+      int nb = 1;
+      if (hb == H && wb == W) {
+        const int per = (hb + 2) * wh;
+        nb = 1 + (127 - ((hb - 1) * wh + wb - 1)) / per;
+        if (nb > N) nb = N;
+      }
+      const long long tiles = (long long)(W / wb) * ((H + hb - 1) / hb) * ((N + nb - 1) / nb);
+      const double eff = (double)N * H * W / ((double)tiles * 128.0);
+      if (eff > best + 1e-9) { best = eff; *Wb = wb; *Hb = hb; *Nb = nb; }
+    }
   }
 }
 
@@ -279,6 +482,66 @@ extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
+  static int halo_env = -1;
+  if (halo_env < 0) {
+    const char* e = getenv("PCM_TC_HALO");      // PCM_TC_HALO=0: force the nine-box kernel (A/B experiments)
+    halo_env = e ? atoi(e) : 1;
+  }
+  unsigned int* err = tc_error_counter();
+  PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
+  if (halo_env && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
+    ConvHaloParams h;
+    h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout;
+    h.Wb = h.Hb = h.Nb = 1;
+    choose_tile_halo(N, H, W, &h.Wb, &h.Hb, &h.Nb);
+    h.Wh = h.Wb + 2; h.Hh = h.Hb + 2;
+    h.tiles_w = W / h.Wb;
+    h.tiles_h = (H + h.Hb - 1) / h.Hb;
+    h.num_tiles = h.tiles_w * h.tiles_h * ((N + h.Nb - 1) / h.Nb);
+    h.dst_ns = dst_ns; h.dst_ps = dst_ps; h.dst_f32 = dst_f32; h.accumulate = accumulate;
+    h.acc_stride = Cout < 32 ? 32 : Cout;
+    uint32_t cols = 32;
+    while (cols < 2 * h.acc_stride) cols <<= 1;
+    h.tmem_cols = cols;
+    const uint32_t row_bytes = Cin * 2;
+    const int box_rows = h.Nb * h.Hh * h.Wh;
+    int need_rows = 128 + 2 * h.Wh + 2;
+    if (box_rows > need_rows) need_rows = box_rows;
+    h.a_stage_bytes = ((uint32_t)need_rows * row_bytes + 1023u) & ~1023u;
+    h.a_tx_bytes = (uint32_t)box_rows * row_bytes;
+    h.b_bytes = 9u * Cout * row_bytes;
+    const size_t b_region = ((size_t)h.b_bytes + 1023) & ~(size_t)1023;
+    int stages = (int)((160 * 1024 - b_region) / h.a_stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    h.stages = stages;
+    const size_t smem = 1024 + b_region + (size_t)stages * h.a_stage_bytes + (2 * stages + 5) * sizeof(uint64_t) + 16;
+    CUtensorMap tmA, tmB;
+    {
+      uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+      uint64_t strides[3] = {(uint64_t)src_ps * 2, (uint64_t)W * src_ps * 2, (uint64_t)src_ns * 2};
+      uint32_t box[4] = {(uint32_t)Cin, (uint32_t)h.Wh, (uint32_t)h.Hh, (uint32_t)h.Nb};
+      int rc = make_tensor_map(&tmA, src, 4, dims, strides, box, row_bytes);
+      if (rc != PCM_OK) return rc;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+      uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+      uint32_t box[3] = {(uint32_t)Cin, (uint32_t)Cout, 9};
+      int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, row_bytes);
+      if (rc != PCM_OK) return rc;
+    }
+    auto kern = Cin == 16 ? conv3x3_tc_halo_kernel<1> : conv3x3_tc_halo_kernel<2>;
+    static size_t smem_set_h[2] = {0, 0};
+    if (smem > smem_set_h[Cin == 16 ? 0 : 1]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("conv3x3_tc(halo): smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
+      smem_set_h[Cin == 16 ? 0 : 1] = smem;
+    }
+    const int grid = h.num_tiles < g_num_sms ? h.num_tiles : g_num_sms;
+    kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, h);
+    return check_launch("conv3x3_tc(halo)");
+  }
   ConvTcParams p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   choose_tile(N, H, W, &p.Wb, &p.Hb, &p.Nb);
@@ -320,15 +583,15 @@ extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int
     int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, p.KC * 2);
     if (rc != PCM_OK) return rc;
   }
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int ksi = p.KC == 16 ? 0 : p.KC == 32 ? 1 : 2;
+  auto kern = ksi == 0 ? conv3x3_tc_kernel<1> : ksi == 1 ? conv3x3_tc_kernel<2> : conv3x3_tc_kernel<4>;
+  static size_t smem_set[3] = {0, 0, 0};
+  if (smem > smem_set[ksi]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
-    smem_set = smem;
+    smem_set[ksi] = smem;
   }
-  unsigned int* err = tc_error_counter();
-  PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-  conv3x3_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, p);
+  kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, p);
   return check_launch("conv3x3_tc");
 }

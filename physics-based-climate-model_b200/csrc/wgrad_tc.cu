@@ -1,0 +1,265 @@
+// Weight gradient of the 3x3 / stride-1 / pad-1 convolution as a tcgen05 GEMM over the PIXEL dimension:
+//
+//   dW[co][ci][tap] += sum_p dy[p][co] * x[p + shift(tap)][ci]        (K = pixels, M = co, N = ci per tap)
+//
+// Both operands are used exactly as they sit in HBM (NHWC): a TMA box {C-chunk, W+2, rows, images}
+// lands in shared memory as consecutive pixel rows of C*2 bytes == the canonical MN-major UMMA operand
+// layout (channels contiguous, K = pixel rows in 8-row groups).  The x box carries a one-pixel halo, the
+// dy box is fetched (W+2) wide with its two extra columns out of bounds (= zero), so both share the row
+// pitch W+2 and the nine taps are nine start-address offsets (kh*(W+2)+kw rows) into the SAME x tile.
+// All taps of a group accumulate side by side in TMEM (tap-major columns); K is split over CTAs and
+// the fp32 partials are reduced with atomics straight into the parameter-gradient tensor.
+//
+// Roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
+#include "tc_common.cuh"
+
+namespace pcm {
+
+using namespace tc;
+
+struct WgradTcParams {
+  int N, H, W, Wp;
+  int Co_real, Ci_real, Ci;     // Ci = padded N extent per tap (multiple of 16)
+  int Cca, Ccb, na_chunks, nb_chunks;
+  int Hb, Nb, tiles_h, num_ktiles, Kpad;
+  int tpg, ngroups;             // taps per group, groups
+  int stages;
+  long long sa, sb, st;
+  uint32_t a_chunk_bytes, b_chunk_bytes, a_stage_bytes, b_stage_bytes, tx_bytes, tmem_cols, lbo_a, lbo_b;
+};
+
+constexpr int kWgThreads = 192;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   float* __restrict__ dw, unsigned int* __restrict__ err, const WgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* done = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, nsplit = gridDim.x, mtile = blockIdx.y, group = blockIdx.z;
+  const int tap0 = group * p.tpg;
+  const int ntap = min(p.tpg, 9 - tap0);
+
+  // rows TMA never writes (K padding, shifted-view overrun) must read as zero: clear the ring once
+  {
+    const uint32_t total16 = (uint32_t)(((size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes)) >> 4);
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = threadIdx.x; i < total16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (p.num_ktiles - split + nsplit - 1) / nsplit;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = split; kt < p.num_ktiles; kt += nsplit) {
+        const int th = kt % p.tiles_h, tn = kt / p.tiles_h;
+        const int h0 = th * p.Hb, n0 = tn * p.Nb;
+        if (!mbar_wait(&empty[stage], phase ^ 1, err)) break;
+        mbar_expect_tx(&full[stage], p.tx_bytes);
+        uint8_t* a = sA + (size_t)stage * p.a_stage_bytes;
+        uint8_t* b = sB + (size_t)stage * p.b_stage_bytes;
+        for (int c = 0; c < p.na_chunks; ++c)
+          tma_load_4d(a + (size_t)c * p.a_chunk_bytes, &tmA, &full[stage], mtile * 128 + c * p.Cca, 0, h0, n0);
+        for (int c = 0; c < p.nb_chunks; ++c)
+          tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, -1, h0 - 1, n0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.Ci, 1, 1);          // A and B MN-major
+      const uint32_t rba = p.Cca * 2, rbb = p.Ccb * 2;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), p.lbo_a, 8 * rba, layout_type_for_row_bytes(rba));
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), p.lbo_b, 8 * rbb, layout_type_for_row_bytes(rbb));
+      const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+      const uint32_t a_k = rba, b_k = rbb;                                 // 16 pixel rows = 16*rb bytes -> (>>4) = rb
+      const uint32_t b_tap_row = (uint32_t)p.Wp * rbb >> 4, b_px = rbb >> 4;
+      const int ksteps = p.Kpad / 16, nstages = p.stages, ci = p.Ci;
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int t = 0; t < my_tiles && ok; ++t) {
+        ok = mbar_wait(&full[stage], phase, err);
+        if (!ok) break;
+        tc_fence_after();
+        const uint64_t ad = adesc0 + (uint64_t)(stage * a_step);
+        const uint64_t bd = bdesc0 + (uint64_t)(stage * b_step);
+        for (int tl = 0; tl < ntap; ++tl) {
+          const int tap = tap0 + tl;
+          const uint64_t bt = bd + (uint64_t)((tap / 3) * b_tap_row + (tap % 3) * b_px);
+          const uint32_t d = tmem_base + tl * ci;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(d, ad + (uint64_t)(k * a_k), bt + (uint64_t)(k * b_k), idesc, (t | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // epilogue: TMEM lane = output channel, columns = (tap, ci)
+    const int q = warp & 3;
+    const int co = mtile * 128 + q * 32 + lane;
+    bool ok = my_tiles > 0 ? mbar_wait(done, 0, err) : false;
+    ok = __all_sync(0xffffffffu, ok);
+    if (ok) {
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int ncols = ntap * p.Ci;
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_addr + c0, v);
+        if (co < p.Co_real) {
+          const int tap = tap0 + c0 / p.Ci;
+          const int ci0 = c0 % p.Ci;
+          float* base = dw + (long long)co * p.sa + (long long)tap * p.st;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (ci0 + j < p.Ci_real) atomicAdd(base + (long long)(ci0 + j) * p.sb, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static int g_wg_sms = 0;
+
+}  // namespace pcm
+
+using namespace pcm;
+
+extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
+                               long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
+                               long long st, int N, int H, int W, pcm_stream_t s) {
+  PCM_REQUIRE(Co % 16 == 0 && (Co <= 64 ? (Co == 16 || Co == 32 || Co == 64) : Co % 128 == 0),
+              "wgrad3x3_tc: Co must be 16, 32, 64 or a multiple of 128 (got %d)", Co);
+  PCM_REQUIRE(Ci % 16 == 0 && (Ci <= 64 ? (Ci == 16 || Ci == 32 || Ci == 64) : (Ci % 64 == 0 && Ci <= 256)),
+              "wgrad3x3_tc: Ci must be 16, 32, 64, 128, 192 or 256 (got %d)", Ci);
+  PCM_REQUIRE(W + 2 <= 256 && H + 2 <= 256, "wgrad3x3_tc: grid too large for one TMA box (W=%d H=%d)", W, H);
+  PCM_REQUIRE(dy_ps % 8 == 0 && x_ps % 8 == 0 && dy_ns % 8 == 0 && x_ns % 8 == 0, "wgrad3x3_tc: strides must be multiples of 8");
+  if (N == 0) return PCM_OK;
+  if (g_wg_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_wg_sms <= 0) g_wg_sms = 148;
+  }
+  WgradTcParams p;
+  p.N = N; p.H = H; p.W = W; p.Wp = W + 2;
+  p.Co_real = Co_real; p.Ci_real = Ci_real; p.Ci = Ci;
+  p.Cca = Co < 64 ? Co : 64;
+  p.Ccb = Ci < 64 ? Ci : 64;
+  const int m_extent = Co < 128 ? Co : 128;
+  p.na_chunks = m_extent / p.Cca;
+  p.nb_chunks = Ci / p.Ccb;
+  const int mtiles = (Co + 127) / 128;
+  p.sa = sa; p.sb = sb; p.st = st;
+  // K tile: whole images (with their zero rows) when small, else a block of image rows
+  const int rows_full = (H + 2) * p.Wp;
+  int a_box_h, b_box_h;
+  if (rows_full <= 128) {
+    p.Nb = 256 / rows_full;
+    if (p.Nb > N) p.Nb = N;
+    p.Hb = H;
+    a_box_h = H + 2; b_box_h = H + 2;
+    p.tiles_h = 1;
+  } else {
+    p.Nb = 1;
+    int hb = 240 / p.Wp;
+    if (hb < 1) hb = 1;
+    if (hb > H) hb = H;
+    p.tiles_h = (H + hb - 1) / hb;
+    p.Hb = (H + p.tiles_h - 1) / p.tiles_h;
+    a_box_h = p.Hb; b_box_h = p.Hb + 2;
+  }
+  const int tiles_n = (N + p.Nb - 1) / p.Nb;
+  p.num_ktiles = tiles_n * p.tiles_h;
+  const int a_rows = p.Nb * a_box_h * p.Wp;
+  const int b_rows = p.Nb * b_box_h * p.Wp;
+  p.Kpad = (a_rows + 15) / 16 * 16;
+  const uint32_t rba = p.Cca * 2, rbb = p.Ccb * 2;
+  // M blocks beyond the real channels alias the tile shifted by 8 rows per block: needs <= 56 rows of slack
+  const int a_alloc = p.Kpad + (p.na_chunks * p.Cca >= 128 ? 0 : 64);
+  int b_alloc = p.Kpad + 2 * p.Wp + 2;
+  if (b_alloc < b_rows) b_alloc = b_rows;
+  p.a_chunk_bytes = ((uint32_t)a_alloc * rba + 1023u) & ~1023u;
+  p.b_chunk_bytes = ((uint32_t)b_alloc * rbb + 1023u) & ~1023u;
+  p.a_stage_bytes = p.a_chunk_bytes * p.na_chunks;
+  p.b_stage_bytes = p.b_chunk_bytes * p.nb_chunks;
+  p.tx_bytes = (uint32_t)a_rows * rba * p.na_chunks + (uint32_t)b_rows * rbb * p.nb_chunks;
+  // M blocks beyond the real channels alias the tile shifted by 8 rows (results unused, reads stay in bounds)
+  p.lbo_a = (p.na_chunks * p.Cca >= 128) ? p.a_chunk_bytes : 8 * rba;
+  p.lbo_b = p.b_chunk_bytes;
+  p.tpg = 512 / Ci;
+  if (p.tpg > 9) p.tpg = 9;
+  p.ngroups = (9 + p.tpg - 1) / p.tpg;
+  p.tpg = (9 + p.ngroups - 1) / p.ngroups;                      // balance the groups
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.tpg * Ci)) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t per_stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+  int stages = (int)((200 * 1024) / per_stage);
+  if (stages > 4) stages = 4;
+  PCM_REQUIRE(stages >= 1, "wgrad3x3_tc: tile does not fit shared memory (%zu B per stage)", per_stage);
+  if (stages > p.num_ktiles) stages = p.num_ktiles;
+  p.stages = stages;
+  const size_t smem = 1024 + stages * per_stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Co, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)dy_ps * 2, (uint64_t)W * dy_ps * 2, (uint64_t)dy_ns * 2};
+    uint32_t box[4] = {(uint32_t)p.Cca, (uint32_t)p.Wp, (uint32_t)a_box_h, (uint32_t)p.Nb};
+    int rc = make_tensor_map(&tmA, dy, 4, dims, strides, box, rba);
+    if (rc != PCM_OK) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)x_ps * 2, (uint64_t)W * x_ps * 2, (uint64_t)x_ns * 2};
+    uint32_t box[4] = {(uint32_t)p.Ccb, (uint32_t)p.Wp, (uint32_t)b_box_h, (uint32_t)p.Nb};
+    int rc = make_tensor_map(&tmB, x, 4, dims, strides, box, rbb);
+    if (rc != PCM_OK) return rc;
+  }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("wgrad3x3_tc: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
+    smem_set = smem;
+  }
+  unsigned int* err = tc_error_counter();
+  PCM_REQUIRE(err != nullptr, "wgrad3x3_tc: could not allocate the error counter");
+  int nsplit = g_wg_sms / (mtiles * p.ngroups);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > p.num_ktiles) nsplit = p.num_ktiles;
+  dim3 grid(nsplit, mtiles, p.ngroups);
+  wgrad3x3_tc_kernel<<<grid, kWgThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dw, err, p);
+  return check_launch("wgrad3x3_tc");
+}

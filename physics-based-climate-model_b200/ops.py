@@ -143,6 +143,29 @@ def conv_wgrad(A, B, dw, sa, sb, st, N, Ha, Wa, Ca, Ca_real, Hb, Wb, Cb, Cb_real
           dw.data_ptr() + 4 * dw_off, sa, sb, st, N, KH, KW, stride, pad, _DT[A.dtype], _s())
 
 
+def wgrad_tc_supported(dtype, Co: int, Ci: int, H: int, W: int) -> bool:
+    return (dtype == torch.bfloat16 and (Co in (16, 32, 64) or (Co % 128 == 0 and Co > 0))
+            and Ci in (16, 32, 64, 128, 192, 256) and W + 2 <= 256 and H + 2 <= 256)
+
+
+def conv3x3_wgrad(dy, x, dw, N, H, W, Co, Ci, Ci_real, Ci_tot=None, dy_ns=None, dy_ps=None, x_ns=None, x_ps=None,
+                  dy_off=0, x_off=0, dw_off=0):
+    """dw[co][ci_off + ci][tap] += sum_p dy(p, co) * x(p + tap, ci) for the 3x3/s1/p1 convolution.
+    dw is the fp32 master-layout gradient (Co, Ci_tot, 3, 3); dw_off selects a ci slice (ConvLSTM Wx / Wh)."""
+    Ci_tot = Ci_real if Ci_tot is None else Ci_tot
+    dy_ps = Co if dy_ps is None else dy_ps
+    x_ps = Ci if x_ps is None else x_ps
+    dy_ns = H * W * dy_ps if dy_ns is None else dy_ns
+    x_ns = H * W * x_ps if x_ns is None else x_ns
+    if wgrad_tc_supported(dy.dtype, Co, Ci, H, W):
+        _call("pcm_wgrad3x3_tc", dy.data_ptr() + dy_off * dy.element_size(), dy_ns, dy_ps, Co, Co,
+              x.data_ptr() + x_off * x.element_size(), x_ns, x_ps, Ci, Ci_real, dw.data_ptr() + 4 * dw_off,
+              Ci_tot * 9, 9, 1, N, H, W, _s())
+    else:
+        conv_wgrad(dy, x, dw, Ci_tot * 9, 9, 1, N, H, W, Co, Co, H, W, Ci, Ci_real, 3, 3, 1, 1, a_ns=dy_ns, a_ps=dy_ps,
+                   b_ns=x_ns, b_ps=x_ps, a_off=dy_off, b_off=x_off, dw_off=dw_off)
+
+
 def channel_sum(x, out, N, P, C, C_real, ns=None, ps=None, off=0, per_image=False):
     ps = C if ps is None else ps
     ns = P * ps if ns is None else ns
@@ -291,7 +314,7 @@ class ConvBlockFn(torch.autograd.Function):
         _call("pcm_gn_silu_bwd_apply", da2.data_ptr(), dpool.data_ptr(), y2.data_ptr(), stats2.data_ptr(),
               g2.data_ptr(), b2.data_ptr(), gsum2.data_ptr(), dy2.data_ptr(), N, P, Co, G, GN_EPS, d, st)
         # conv2: weight + data gradients
-        conv_wgrad(dy2, a1, gw2, Co * 9, 9, 1, N, H, W, Co, Co, H, W, Co, Co, 3, 3, 1, 1)
+        conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
         wk2t = conv_weight_dgrad(w2, dt)
         da1 = conv_s1(dy2, wk2t, N, H, W, Co, Co, dst=da2)                                # reuse da2 storage
         _call("pcm_gn_silu_bwd_reduce", da1.data_ptr(), 0, y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(),
@@ -299,7 +322,7 @@ class ConvBlockFn(torch.autograd.Function):
         dy1 = dy2                                                                          # reuse dy2 storage
         _call("pcm_gn_silu_bwd_apply", da1.data_ptr(), 0, y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(),
               b1.data_ptr(), gsum1.data_ptr(), dy1.data_ptr(), N, P, Co, G, GN_EPS, d, st)
-        conv_wgrad(dy1, x, gw1, Ci * 9, 9, 1, N, H, W, Co, Co, H, W, Cip, Ci, 3, 3, 1, 1)
+        conv3x3_wgrad(dy1, x, gw1, N, H, W, Co, Cip, Ci)
         dx = None
         if ctx.needs_input_grad[0]:
             wk1t = conv_weight_dgrad(w1, dt, Op=Cip)
@@ -477,12 +500,18 @@ class ConvLSTMFn(torch.autograd.Function):
         KK = K * K
         Ct = Ci + Ch
         # dW[:, :Ci] — x frames may be time-strided, one launch per step; dW[:, Ci:] — one launch over t>=1
-        for t in range(T):
-            conv_wgrad(dgates[t], x, gw, Ct * KK, KK, 1, B, H, W, 4 * Ch, 4 * Ch, H, W, Cip, Ci, K, K, 1, pad,
-                       b_ns=st_b * img, b_off=t * st_t * img)
-        if T > 1:
-            conv_wgrad(dgates[1:], h_all[:-1], gw, Ct * KK, KK, 1, (T - 1) * B, H, W, 4 * Ch, 4 * Ch, H, W, Ch, Ch,
-                       K, K, 1, pad, dw_off=Ci * KK)
+        if K == 3:
+            for t in range(T):
+                conv3x3_wgrad(dgates[t], x, gw, B, H, W, 4 * Ch, Cip, Ci, Ci_tot=Ct, x_ns=st_b * img, x_off=t * st_t * img)
+            if T > 1:
+                conv3x3_wgrad(dgates[1:], h_all[:-1], gw, (T - 1) * B, H, W, 4 * Ch, Ch, Ch, Ci_tot=Ct, dw_off=Ci * KK)
+        else:
+            for t in range(T):
+                conv_wgrad(dgates[t], x, gw, Ct * KK, KK, 1, B, H, W, 4 * Ch, 4 * Ch, H, W, Cip, Ci, K, K, 1, pad,
+                           b_ns=st_b * img, b_off=t * st_t * img)
+            if T > 1:
+                conv_wgrad(dgates[1:], h_all[:-1], gw, Ct * KK, KK, 1, (T - 1) * B, H, W, 4 * Ch, 4 * Ch, H, W, Ch, Ch,
+                           K, K, 1, pad, dw_off=Ci * KK)
         channel_sum(dgates, gb, T * B, P, 4 * Ch, 4 * Ch)
         dx = None
         if ctx.needs_input_grad[0]:

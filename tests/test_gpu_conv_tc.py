@@ -100,3 +100,64 @@ def test_dgrad_weights_flip(ops):
         else:
             got = ops.conv_gather(dy.cuda(), wkt, N, H, W, Co, H, W, Ci, 3, 3, 1, 1, 0, dst_f32=True)
         assert float((got.cpu() - want).norm() / want.norm()) < 2e-6, use
+
+
+WG_SHAPES = [  # (N, H, W, Cin, Cout)
+    (5, 48, 72, 16, 16), (3, 24, 36, 16, 32), (3, 24, 36, 32, 32), (4, 12, 18, 32, 64), (4, 12, 18, 64, 64),
+    (7, 6, 9, 64, 128), (7, 6, 9, 128, 128), (6, 6, 9, 128, 256), (5, 6, 9, 64, 256), (2, 12, 18, 128, 64),
+    (2, 24, 36, 64, 32), (2, 48, 72, 32, 16), (3, 23, 45, 64, 64), (1, 7, 200, 32, 16), (2, 5, 5, 16, 16),
+    (300, 6, 9, 128, 256), (40, 48, 72, 16, 16),
+]
+
+
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_wgrad3x3_tc_matches_reference(ops, shape):
+    from pcm_b200._lib import lib
+    N, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(N * 7 + H + Ci * 3 + Co)
+    x = torch.randn(N, H, W, Ci, generator=g).bfloat16()
+    dy = (torch.randn(N, H, W, Co, generator=g) / (N * H * W) ** 0.5).bfloat16()
+    w = torch.zeros(Co, Ci, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double().permute(0, 3, 1, 2), w, padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    want = w.grad.float()
+    assert ops.wgrad_tc_supported(torch.bfloat16, Co, Ci, H, W)
+    dw = torch.zeros(Co, Ci, 3, 3, device="cuda")
+    ops.conv3x3_wgrad(dy.cuda(), x.cuda(), dw, N, H, W, Co, Ci, Ci)
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    err = float((dw.cpu() - want).norm() / want.norm())
+    assert err < 1e-5, err
+    # accumulates into what is already there; a second call doubles the result
+    ops.conv3x3_wgrad(dy.cuda(), x.cuda(), dw, N, H, W, Co, Ci, Ci)
+    assert float((dw.cpu() - 2 * want).norm() / want.norm()) < 2e-5
+
+
+def test_wgrad3x3_tc_slices(ops):
+    """ConvLSTM use: dW[:, ci_off:ci_off+Ci] slice of a (Co, Ci_tot, 3, 3) gradient, time-strided x frames,
+    padded input channels (Ci_real < Ci)."""
+    T, B, H, W, Cx, Ch = 3, 4, 6, 9, 128, 64
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, H, W, Cx, generator=g).bfloat16()            # image n = b*T + t
+    dg = (torch.randn(T, B, H, W, 4 * Ch, generator=g) / 30).bfloat16()
+    dw = torch.zeros(4 * Ch, Cx + Ch, 3, 3, device="cuda")
+    img = H * W * Cx
+    for t in range(T):
+        ops.conv3x3_wgrad(dg[t].cuda(), x.cuda(), dw, B, H, W, 4 * Ch, Cx, Cx, Ci_tot=Cx + Ch, x_ns=T * img, x_off=t * img)
+    w = torch.zeros(4 * Ch, Cx, 3, 3, dtype=torch.float64, requires_grad=True)
+    xs = x.double().permute(1, 0, 4, 2, 3).reshape(T * B, Cx, H, W)
+    F.conv2d(xs, w, padding=1).backward(dg.double().reshape(T * B, H, W, 4 * Ch).permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    got = dw.cpu()
+    assert float((got[:, :Cx] - w.grad.float()).norm() / w.grad.norm()) < 1e-5
+    assert float(got[:, Cx:].abs().max()) == 0.0
+    # first layer: 7 real input channels padded to 16
+    x7 = torch.zeros(3, 12, 18, 16)
+    x7[..., :7] = torch.randn(3, 12, 18, 7, generator=g)
+    x7 = x7.bfloat16()
+    dy = (torch.randn(3, 12, 18, 16, generator=g) / 25).bfloat16()
+    dw7 = torch.zeros(16, 7, 3, 3, device="cuda")
+    ops.conv3x3_wgrad(dy.cuda(), x7.cuda(), dw7, 3, 12, 18, 16, 16, 7)
+    w7 = torch.zeros(16, 7, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x7[..., :7].double().permute(0, 3, 1, 2), w7, padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert float((dw7.cpu() - w7.grad.float()).norm() / w7.grad.norm()) < 1e-5

@@ -1,0 +1,96 @@
+"""Micro-benchmarks of individual pcm_b200 kernels at the config-3 shapes (B=64, T=6, 48x72, base 16).
+Timing: CUDA events around `iters` back-to-back launches after warm-up; a 256 MB buffer is rewritten
+between launches (--flush) so operands do not stay L2 resident.
+
+    python tools/microbench.py conv [--flush] [--only NAME]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pcm_b200  # noqa: E402,F401
+from pcm_b200 import ops  # noqa: E402
+
+CONV_SHAPES = [  # name, N, H, W, Cin, Cout
+    ("enc1.body.0", 384, 48, 72, 16, 16), ("enc1.body.3", 384, 48, 72, 16, 16),
+    ("enc2.body.0", 384, 24, 36, 16, 32), ("enc2.body.3", 384, 24, 36, 32, 32),
+    ("enc3.body.0", 384, 12, 18, 32, 64), ("enc3.body.3", 384, 12, 18, 64, 64),
+    ("enc4.body.0", 384, 6, 9, 64, 128), ("enc4.body.3", 384, 6, 9, 128, 128),
+    ("lstm.Wx(all T)", 384, 6, 9, 128, 256), ("lstm.Wh(step)", 64, 6, 9, 64, 256),
+    ("up3.body.0", 64, 12, 18, 128, 64), ("up2.body.0", 64, 24, 36, 64, 32), ("up1.body.0", 64, 48, 72, 32, 16),
+]
+
+
+def timeit(fn, iters, flush):
+    """flush: one launch per measurement with a 256 MB L2 flush in between (includes ~host launch gap);
+    otherwise: `iters` launches captured in ONE CUDA graph and replayed (pure device time, warm L2)."""
+    buf = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda") if flush else None
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    if not flush:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    tot = 0.0
+    for _ in range(iters):
+        if flush:
+            buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def bench_conv(args):
+    for name, N, H, W, Ci, Co in CONV_SHAPES:
+        if args.only and args.only not in name:
+            continue
+        x = torch.randn(N, H, W, Ci, device="cuda").bfloat16()
+        w = torch.randn(Co, Ci, 3, 3, device="cuda") / (3 * Ci ** 0.5)
+        wk = ops.conv_weight_fwd(w, torch.bfloat16)
+        y = torch.empty(N, H, W, Co, device="cuda", dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.conv_s1(x, wk, N, H, W, Ci, Co, dst=y), args.iters, args.flush)
+        flops = 2.0 * N * H * W * Ci * Co * 9
+        byts = 2.0 * N * H * W * (Ci + Co)
+        print(f"conv3x3 {name:16s} N={N:4d} {H:2d}x{W:2d} {Ci:3d}->{Co:3d}: {ms * 1e3:8.1f} us  "
+              f"{flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s (algorithmic)")
+
+
+def bench_wgrad(args):
+    for name, N, H, W, Ci, Co in CONV_SHAPES:
+        if args.only and args.only not in name:
+            continue
+        x = torch.randn(N, H, W, Ci, device="cuda").bfloat16()
+        dy = torch.randn(N, H, W, Co, device="cuda").bfloat16()
+        dw = torch.zeros(Co, Ci, 3, 3, device="cuda")
+        ms = timeit(lambda: ops.conv3x3_wgrad(dy, x, dw, N, H, W, Co, Ci, Ci), args.iters, args.flush)
+        flops = 2.0 * N * H * W * Ci * Co * 9
+        byts = 2.0 * N * H * W * (Ci + Co)
+        print(f"wgrad   {name:16s} N={N:4d} {H:2d}x{W:2d} {Ci:3d}->{Co:3d}: {ms * 1e3:8.1f} us  "
+              f"{flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s (algorithmic)")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["conv", "wgrad"])
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--flush", action="store_true")
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    {"conv": bench_conv, "wgrad": bench_wgrad}[a.what](a)
