@@ -19,6 +19,7 @@ import torch.distributed as dist
 from . import ops
 from ._lib import lib
 from .optim import FusedAdam
+from .parallel import allreduce_flat_grads
 
 
 class TrainStep:
@@ -43,10 +44,8 @@ class TrainStep:
         out = self.model(self.x)
         loss = ops.mse_loss(out, self.y)
         loss.backward()
-        if self.world > 1:
-            g = self.opt.flat_grad[: self.opt.n_reduced]
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
-        self.opt.step(grad_scale=1.0 / self.world)
+        scale = allreduce_flat_grads(self.opt.flat_grad, self.opt.n_reduced, self.pg)
+        self.opt.step(grad_scale=scale)
         self.loss.copy_(loss.detach())
 
     def warmup_and_capture(self, warmup: int = 3):

@@ -1,0 +1,94 @@
+"""CPU (no GPU needed): the C-ABI library builds for sm_100a, loads, exports every symbol that
+include/pcm_b200.h declares, and the product path refuses to run without the GPU / the library."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import pcm_b200
+from pcm_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    return pcm_b200.build()
+
+
+def test_header_symbols_exported(built):
+    dll = ctypes.CDLL(built)
+    with open(os.path.join(ROOT, "include", "pcm_b200.h")) as f:
+        declared = set(re.findall(r"\b(pcm_\w+)\s*\(", f.read()))
+    assert len(declared) >= 30
+    assert declared == set(_lib.PROTOS), declared ^ set(_lib.PROTOS)
+    for name in declared:
+        assert hasattr(dll, name), f"{name} declared in the header but not exported by libpcm_b200.so"
+
+
+def test_version_and_error_string_without_gpu(built):
+    L = _lib.lib()
+    assert L.version() >= 100
+    assert isinstance(L.last_error(), str)
+
+
+def test_library_is_sm100a_only(built):
+    out = os.popen(f"cuobjdump -lelf {built} 2>/dev/null").read()
+    if not out.strip():
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out), out
+
+
+def test_cpu_tensors_are_refused():
+    from pcm_b200 import ops
+    from pcm_b200.src.unet import ConvBlock
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ConvBlock(8, 16)(torch.zeros(1, 8, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        AttUNetConvLSTM(7, 2, 8)(torch.zeros(1, 2, 7, 16, 24))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.mse_loss(torch.zeros(4), torch.zeros(4))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_build, "LIB_PATH", str(tmp_path / "libpcm_b200.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib._Lib()
+
+
+def test_module_surface_matches_reference_appendix_c():
+    """state_dict keys/shapes of the drop-in modules == the oracle's spec (which make_goldens.py loaded into
+    the REAL reference modules with strict=True)."""
+    from oracle import model_oracle as O
+    from pcm_b200.src.models import get_model
+    from pcm_b200.src.unet import UNet
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    for mod, spec in [(AttUNetConvLSTM(7, 2, 16), O.attunet_spec(7, 2, 16)), (UNet(5, 2, 16), O.unet_spec(5, 2, 16))]:
+        sd = mod.state_dict()
+        assert list(sd.keys()) == [k for k, _ in spec]
+        for k, shape in spec:
+            assert tuple(sd[k].shape) == tuple(shape), k
+    cfg = {"model": {"type": "unet_convlstm_attention", "base_channels": 16},
+           "data": {"input_vars": ["CO2", "SO2", "CH4", "BC", "rsdt"], "output_vars": ["tas", "pr"]}}
+    m = get_model(cfg)
+    assert isinstance(m, AttUNetConvLSTM) and m.enc1.body[0].weight.shape[1] == 7      # in_ch=7 hard-coded
+    assert sum(p.numel() for p in m.parameters()) == 953968
+    with pytest.raises(ValueError, match="Unknown model type"):
+        get_model({"model": {"type": "nope"}, "data": cfg["data"]})
+
+
+def test_default_init_matches_reference_under_seed():
+    """Same registration order as the reference ctor => same default init under torch.manual_seed(42)
+    (checksums recorded from the real reference by oracle/make_goldens.py)."""
+    import json
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    with open(os.path.join(ROOT, "tests", "golden", "metric_appendix_g.json")) as f:
+        want = json.load(f)["attunet_default_init_seed42"]
+    torch.manual_seed(42)
+    m = AttUNetConvLSTM(7, 2, 16)
+    for k, v in m.state_dict().items():
+        s, n = float(v.double().sum()), float(v.double().norm())
+        assert abs(s - want[k][0]) <= 1e-9 * max(1.0, abs(want[k][0])) and abs(n - want[k][1]) <= 1e-9 * max(1.0, want[k][1]), k
