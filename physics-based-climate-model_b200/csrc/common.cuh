@@ -65,7 +65,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 // value as the storage type would round it (so saved/recomputed quantities agree bit-for-bit)
 template <typename T> __device__ __forceinline__ float round_to(float x) { return to_f(from_f<T>(x)); }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // ---- reductions ------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

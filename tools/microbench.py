@@ -86,11 +86,46 @@ def bench_wgrad(args):
               f"{flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s (algorithmic)")
 
 
+def bench_pointwise(args):
+    """ConvBlock tail kernels at the enc1 level (N=384, 48x72, C=16) and enc3 level (12x18, C=64)."""
+    from pcm_b200.ops import _call, _s
+    for (N, H, W, C) in [(384, 48, 72, 16), (384, 24, 36, 32), (384, 12, 18, 64), (384, 6, 9, 128)]:
+        P, G, d = H * W, 8, 1
+        Cr = C // 8
+        bf = lambda *sh: torch.randn(*sh, device="cuda").bfloat16()
+        x, da, y, dout = bf(N, P, C), bf(N, P, C), bf(N, P, C), bf(N, P, C)
+        f32 = lambda *sh: torch.randn(*sh, device="cuda")
+        stats = torch.zeros(N * G * 2, device="cuda")
+        gamma, beta = f32(C), f32(C)
+        pool, se, hid = torch.zeros(N * C, device="cuda"), torch.rand(N * C, device="cuda"), torch.rand(N * Cr, device="cuda")
+        w1, w2, wsp = f32(Cr * C), f32(C * Cr), f32(98)
+        cmap, gate, dq = f32(N * P * 2), torch.rand(N * P, device="cuda"), f32(N * P)
+        gsum, dg, db, dse, dwsp = (torch.zeros(n, device="cuda") for n in (N * G * 2, C, C, N * C, 98))
+        _call("pcm_gn_stats", x.data_ptr(), stats.data_ptr(), N, P, C, G, d, _s())
+        cases = [
+            ("gn_stats", 1, lambda: _call("pcm_gn_stats", x.data_ptr(), stats.data_ptr(), N, P, C, G, d, _s())),
+            ("gn_silu_fwd(+pool)", 2, lambda: _call("pcm_gn_silu_fwd", x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), pool.data_ptr(), N, P, C, G, 1e-5, d, _s())),
+            ("se_chanstat_fwd", 1, lambda: _call("pcm_se_chanstat_fwd", y.data_ptr(), pool.data_ptr(), w1.data_ptr(), w2.data_ptr(), se.data_ptr(), hid.data_ptr(), cmap.data_ptr(), N, P, C, Cr, d, _s())),
+            ("spatial_gate_fwd", 2, lambda: _call("pcm_spatial_gate_fwd", y.data_ptr(), se.data_ptr(), cmap.data_ptr(), wsp.data_ptr(), gate.data_ptr(), x.data_ptr(), N, H, W, C, d, _s())),
+            ("spatial_gate_bwd_dq", 2, lambda: _call("pcm_spatial_gate_bwd_dq", dout.data_ptr(), y.data_ptr(), se.data_ptr(), gate.data_ptr(), dq.data_ptr(), N, P, C, d, _s())),
+            ("spatial_gate_bwd_dw", 0, lambda: _call("pcm_spatial_gate_bwd_dw", dq.data_ptr(), cmap.data_ptr(), dwsp.data_ptr(), N, H, W, _s())),
+            ("spatial_gate_bwd_da", 3, lambda: _call("pcm_spatial_gate_bwd_da", dout.data_ptr(), y.data_ptr(), se.data_ptr(), gate.data_ptr(), cmap.data_ptr(), dq.data_ptr(), wsp.data_ptr(), da.data_ptr(), dse.data_ptr(), N, H, W, C, d, _s())),
+            ("gn_silu_bwd_reduce", 2, lambda: _call("pcm_gn_silu_bwd_reduce", da.data_ptr(), pool.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), gsum.data_ptr(), dg.data_ptr(), db.data_ptr(), N, P, C, G, 1e-5, d, _s())),
+            ("gn_silu_bwd_apply", 3, lambda: _call("pcm_gn_silu_bwd_apply", da.data_ptr(), pool.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), gsum.data_ptr(), y.data_ptr(), N, P, C, G, 1e-5, d, _s())),
+        ]
+        for name, ntens, fn in cases:
+            if args.only and args.only not in name:
+                continue
+            ms = timeit(fn, args.iters, args.flush)
+            byts = ntens * N * P * C * 2.0
+            print(f"{name:22s} N={N} {H}x{W} C={C:3d}: {ms * 1e3:8.1f} us   {byts / ms / 1e6:8.1f} GB/s (algorithmic, {ntens} tensor passes)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["conv", "wgrad"])
+    ap.add_argument("what", choices=["conv", "wgrad", "pointwise"])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--flush", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
-    {"conv": bench_conv, "wgrad": bench_wgrad}[a.what](a)
+    {"conv": bench_conv, "wgrad": bench_wgrad, "pointwise": bench_pointwise}[a.what](a)
