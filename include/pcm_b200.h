@@ -42,13 +42,17 @@ PCM_API const char* pcm_last_error(void);
 PCM_API int pcm_version(void);
 
 /* ---- layout staging ------------------------------------------------------------------------
- * Module boundary tensors are NCHW fp32 (reference: every nn.Module in src/*.py). */
-PCM_API int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp, int dtype, pcm_stream_t s);
-PCM_API int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, int W, int Cp, int dtype, pcm_stream_t s);
+ * Module boundary tensors are NCHW fp32 (reference: every nn.Module in src/*.py).  T > 1 additionally
+ * re-orders a (B, T) window batch: NCHW image b*T + t  <->  NHWC image t*B + b ("t-major", so that every
+ * time step of the ConvLSTM is a contiguous block of B images). */
+PCM_API int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp, int T, int dtype,
+                             pcm_stream_t s);
+PCM_API int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, int W, int Cp, int T, int dtype,
+                             pcm_stream_t s);
 /* main_final.py:186-216 (seasonal channels): x5 (N,5,H,W) + month index (N) -> NHWC with
  * ch5 = sin(2 pi m/12), ch6 = cos(2 pi m/12), ch7.. = 0. */
-PCM_API int pcm_season_embed_stage(const float* x5, const int* month, void* y, int N, int H, int W, int Cp, int dtype,
-                           pcm_stream_t s);
+PCM_API int pcm_season_embed_stage(const float* x5, const int* month, void* y, int N, int H, int W, int Cp, int T,
+                                   int dtype, pcm_stream_t s);
 
 /* ---- weight packing: out[t][o][i] = (o<O && i<I) ? w[o*so + i*si + t*st] : 0, stored as dtype */
 PCM_API int pcm_pack_weight(const float* w, long long so, long long si, long long st, int O, int I, int taps, int Op,
@@ -71,6 +75,12 @@ PCM_API int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int H
 PCM_API int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, pcm_stream_t s);
+/* Fused ConvLSTM step (src/convlstm.py:11-19) for t >= 1: gates = conv3x3(h_prev, Wh) [tcgen05, fp32 in TMEM]
+ * + gx (= Wx.x_t + bias, fp32 [B*P][4Ch], precomputed for all T by one pcm_conv3x3_tc launch); the epilogue
+ * applies sigmoid/tanh, updates c (fp32) and h (bf16) and saves the activated gates for backward — the
+ * gate pre-activations of the recurrent half never reach HBM.  wh: bf16 [9][4Ch][Ch]; Ch in {16,32,64}. */
+PCM_API int pcm_convlstm_step_tc(const void* h_prev, const void* wh, const float* gx, const float* c_prev,
+                                 void* h_out, float* c_out, void* acts, int B, int H, int W, int Ch, pcm_stream_t s);
 /* Tensor-core weight gradient of the same convolution (GEMM over the pixel dimension, MN-major operands
  * straight from NHWC, all taps from ONE halo tile): dw[co*sa + ci*sb + tap*st] += sum_p dy(p,co)*x(p+tap,ci).
  * dy: Co in {16,32,64,128k}; x: Ci in {16,32,64,128,192,256}; only co < Co_real, ci < Ci_real are written.
@@ -131,13 +141,14 @@ PCM_API int pcm_gn_silu_bwd_apply(const void* da, const float* dpool, const void
 
 /* ---- pooling / skips (src/unet.py:54,57; src/unet_convlstm_attention.py:21,24,91-93) ----------- */
 PCM_API int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, pcm_stream_t s);
-/* dx(n,h,w,c) = [first max of its 2x2 window] * dy(n,h/2,w/2,c) + dskip(n/T, h, w, c)/T
+/* dx(n,h,w,c) = [first max of its 2x2 window] * dy(n,h/2,w/2,c) + dskip(b(n), h, w, c)/T, with
+ * b(n) = n % (N/T) for t-major image order, n / T otherwise
  * (dy nullable; dskip nullable, an activation view with channel offset applied by the caller) */
 PCM_API int pcm_maxpool2_bwd_skip(const void* x, const void* dy, const void* dskip, long long dskip_ns, int dskip_ps,
-                          void* dx, int N, int H, int W, int C, int T, int dtype, pcm_stream_t s);
-/* dst(b,p,c) = mean_t src(b*T+t, p, c)  (dst is a view into the decoder's concat buffer) */
-PCM_API int pcm_time_mean(const void* src, void* dst, long long dst_ns, int dst_ps, int B, int T, int P, int C, int dtype,
-                  pcm_stream_t s);
+                                  void* dx, int N, int H, int W, int C, int T, int t_major, int dtype, pcm_stream_t s);
+/* dst(b,p,c) = mean_t src(img(b,t), p, c), img = t*B + b (t-major) or b*T + t */
+PCM_API int pcm_time_mean(const void* src, void* dst, long long dst_ns, int dst_ps, int B, int T, int P, int C,
+                          int t_major, int dtype, pcm_stream_t s);
 
 /* ---- ConvLSTM cell (src/convlstm.py:11-19) ----------------------------------------------------
  * gates: fp32 [M][4*Ch] pre-activations in order i,f,o,g (bias already added); c_prev nullable (=0).

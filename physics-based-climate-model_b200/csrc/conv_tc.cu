@@ -31,11 +31,16 @@ struct ConvTcParams {
   long long dst_ns;
   int dst_ps, dst_f32, accumulate;
   uint32_t tmem_cols, acc_stride, a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+  // fused ConvLSTM cell epilogue (EPI == 1): rows are pixels m = (n*H + h)*W + w of contiguous [B*P] tensors
+  const float* gx;        // [M][4*Ch] fp32: Wx.x + bias for this step (computed for all T by one launch)
+  const float* c_prev;    // [M][Ch] fp32
+  float* c_out;           // [M][Ch] fp32
+  __nv_bfloat16* acts;    // [M][4*Ch] bf16: activated gates i,f,o,g saved for backward
 };
 
 constexpr int kThreads = 192;
 
-template <int KSTEPS>   // KC / 16: UMMA K-steps per pipeline stage
+template <int KSTEPS, int EPI>   // KSTEPS = KC / 16 (UMMA K-steps per stage); EPI 0 = store, 1 = ConvLSTM cell
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
@@ -154,6 +159,54 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (!ok) break;
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
+      if (EPI == 1) {
+        // gates = Wh.h (TMEM) + gx ; i,f,o = sigmoid, g = tanh ; c' = f*c + i*g ; h' = o*tanh(c')
+        // (src/convlstm.py:13-18) — the four gates of a hidden channel sit Ch columns apart in this row.
+        const int Ch = p.Cout >> 2;
+        const long long m = ((long long)n * p.H + h) * p.W + w;
+        for (int c0 = 0; c0 < Ch; c0 += 16) {
+          float gi[16], gf[16], go[16], gg[16];
+          tmem_ld16(t_addr + c0, gi);
+          tmem_ld16(t_addr + Ch + c0, gf);
+          tmem_ld16(t_addr + 2 * Ch + c0, go);
+          tmem_ld16(t_addr + 3 * Ch + c0, gg);
+          if (valid) {
+            const float* gxp = p.gx + m * p.Cout + c0;
+            const float* cp = p.c_prev + m * Ch + c0;
+            float* cq = p.c_out + m * Ch + c0;
+            __nv_bfloat16* ap = p.acts + m * p.Cout + c0;
+            __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(dst) + m * Ch + c0;
+            float cn[16], hn[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 xi = *reinterpret_cast<const float4*>(gxp + j);
+              const float4 xf = *reinterpret_cast<const float4*>(gxp + Ch + j);
+              const float4 xo = *reinterpret_cast<const float4*>(gxp + 2 * Ch + j);
+              const float4 xg = *reinterpret_cast<const float4*>(gxp + 3 * Ch + j);
+              const float4 cc = *reinterpret_cast<const float4*>(cp + j);
+              const float xi_[4] = {xi.x, xi.y, xi.z, xi.w}, xf_[4] = {xf.x, xf.y, xf.z, xf.w};
+              const float xo_[4] = {xo.x, xo.y, xo.z, xo.w}, xg_[4] = {xg.x, xg.y, xg.z, xg.w};
+              const float cc_[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float a_i = round_to<__nv_bfloat16>(sigmoidf_(gi[j + k] + xi_[k]));
+                const float a_f = round_to<__nv_bfloat16>(sigmoidf_(gf[j + k] + xf_[k]));
+                const float a_o = round_to<__nv_bfloat16>(sigmoidf_(go[j + k] + xo_[k]));
+                const float a_g = round_to<__nv_bfloat16>(tanhf(gg[j + k] + xg_[k]));
+                gi[j + k] = a_i; gf[j + k] = a_f; go[j + k] = a_o; gg[j + k] = a_g;
+                cn[j + k] = fmaf(a_f, cc_[k], a_i * a_g);
+                hn[j + k] = a_o * tanhf(cn[j + k]);
+              }
+            }
+            store8(ap, gi); store8(ap + 8, gi + 8);
+            store8(ap + Ch, gf); store8(ap + Ch + 8, gf + 8);
+            store8(ap + 2 * Ch, go); store8(ap + 2 * Ch + 8, go + 8);
+            store8(ap + 3 * Ch, gg); store8(ap + 3 * Ch + 8, gg + 8);
+            store8(cq, cn); store8(cq + 8, cn + 8);
+            store8(hp, hn); store8(hp + 8, hn + 8);
+          }
+        }
+      } else
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         float v[16];
         tmem_ld16(t_addr + c0, v);
@@ -464,9 +517,10 @@ extern "C" int pcm_tc_error_count(void) {
   return (int)v;
 }
 
-extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
-                              long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
-                              int dst_f32, int accumulate, pcm_stream_t s) {
+static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                           long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                           int dst_f32, int accumulate, const float* lstm_gx, const float* lstm_c_prev,
+                           float* lstm_c_out, void* lstm_acts, pcm_stream_t s) {
   PCM_REQUIRE(Cin % 16 == 0 && Cin >= 16, "conv3x3_tc: Cin must be a multiple of 16 (got %d)", Cin);
   PCM_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv3x3_tc: Cin above 64 must be a multiple of 64 (got %d)", Cin);
   PCM_REQUIRE(Cin == 16 || Cin == 32 || Cin >= 64, "conv3x3_tc: unsupported Cin %d", Cin);
@@ -489,7 +543,7 @@ extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int
   }
   unsigned int* err = tc_error_counter();
   PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
-  if (halo_env && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
+  if (halo_env && lstm_gx == nullptr && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
     ConvHaloParams h;
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout;
     h.Wb = h.Hb = h.Nb = 1;
@@ -583,9 +637,11 @@ extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int
     int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, p.KC * 2);
     if (rc != PCM_OK) return rc;
   }
-  const int ksi = p.KC == 16 ? 0 : p.KC == 32 ? 1 : 2;
-  auto kern = ksi == 0 ? conv3x3_tc_kernel<1> : ksi == 1 ? conv3x3_tc_kernel<2> : conv3x3_tc_kernel<4>;
-  static size_t smem_set[3] = {0, 0, 0};
+  p.gx = lstm_gx; p.c_prev = lstm_c_prev; p.c_out = lstm_c_out; p.acts = reinterpret_cast<__nv_bfloat16*>(lstm_acts);
+  const int ksi = (p.KC == 16 ? 0 : p.KC == 32 ? 1 : 2) + (lstm_gx != nullptr ? 3 : 0);
+  auto kern = ksi == 0 ? conv3x3_tc_kernel<1, 0> : ksi == 1 ? conv3x3_tc_kernel<2, 0> : ksi == 2 ? conv3x3_tc_kernel<4, 0>
+            : ksi == 3 ? conv3x3_tc_kernel<1, 1> : ksi == 4 ? conv3x3_tc_kernel<2, 1> : conv3x3_tc_kernel<4, 1>;
+  static size_t smem_set[6] = {0, 0, 0, 0, 0, 0};
   if (smem > smem_set[ksi]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
@@ -594,4 +650,21 @@ extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, p);
   return check_launch("conv3x3_tc");
+}
+
+extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                              long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                              int dst_f32, int accumulate, pcm_stream_t s) {
+  return conv3x3_tc_impl(src, src_ns, src_ps, H, W, Cin, dst, dst_ns, dst_ps, Cout, wk, bias, N, dst_f32, accumulate,
+                         nullptr, nullptr, nullptr, nullptr, s);
+}
+
+extern "C" int pcm_convlstm_step_tc(const void* h_prev, const void* wh, const float* gx, const float* c_prev,
+                                    void* h_out, float* c_out, void* acts, int B, int H, int W, int Ch,
+                                    pcm_stream_t s) {
+  PCM_REQUIRE(gx != nullptr && c_prev != nullptr && c_out != nullptr && acts != nullptr && h_out != nullptr,
+              "convlstm_step_tc: null pointer");
+  PCM_REQUIRE(Ch % 16 == 0 && 4 * Ch <= 256, "convlstm_step_tc: Ch must be a multiple of 16, <= 64 (got %d)", Ch);
+  return conv3x3_tc_impl(h_prev, (long long)H * W * Ch, Ch, H, W, Ch, h_out, (long long)H * W * Ch, Ch, 4 * Ch, wh,
+                         nullptr, B, 0, 0, gx, c_prev, c_out, acts, s);
 }

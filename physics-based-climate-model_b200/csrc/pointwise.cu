@@ -12,22 +12,24 @@ constexpr int kGridCap = 148 * 8;
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int P, int Cp,
-                    const int* __restrict__ month) {
+                    const int* __restrict__ month, int Tp) {
   const int cv = Cp / 8;
+  const int Bn = Tp > 1 ? N / Tp : N;
   const long long total = (long long)N * cv * P;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(idx % P);
     const int cb = (int)((idx / P) % cv);
-    const int n = (int)(idx / ((long long)P * cv));
+    const int n = (int)(idx / ((long long)P * cv));              // NHWC image index (t-major when Tp > 1)
+    const int ni = Tp > 1 ? (n % Bn) * Tp + n / Bn : n;         // NCHW image index b*T + t
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = cb * 8 + j;
-      v[j] = (c < C) ? __ldg(x + ((long long)n * C + c) * P + p) : 0.f;
+      v[j] = (c < C) ? __ldg(x + ((long long)ni * C + c) * P + p) : 0.f;
     }
     if (month != nullptr) {   // seasonal channels C, C+1 (main_final.py:188-196)
-      const float ang = 6.283185307179586f * (float)__ldg(month + n) / 12.f;
+      const float ang = 6.283185307179586f * (float)__ldg(month + ni) / 12.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = cb * 8 + j;
@@ -41,20 +43,22 @@ nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int P, int Cp) {
+nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int P, int Cp, int Tp) {
   const int cv = Cp / 8;
+  const int Bn = Tp > 1 ? N / Tp : N;
   const long long total = (long long)N * cv * P;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(idx % P);
     const int cb = (int)((idx / P) % cv);
     const int n = (int)(idx / ((long long)P * cv));
+    const int no = Tp > 1 ? (n % Bn) * Tp + n / Bn : n;
     float v[8];
     load8(x + ((long long)n * P + p) * Cp + cb * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = cb * 8 + j;
-      if (c < C) y[((long long)n * C + c) * P + p] = v[j];
+      if (c < C) y[((long long)no * C + c) * P + p] = v[j];
     }
   }
 }
@@ -85,7 +89,8 @@ maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, in
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ dskip,
-                         long long dskip_ns, int dskip_ps, T* __restrict__ dx, int N, int H, int W, int C, int Tn) {
+                         long long dskip_ns, int dskip_ps, T* __restrict__ dx, int N, int H, int W, int C, int Tn,
+                         int t_major) {
   const int Ho = H / 2, Wo = W / 2, cv = C / 8;
   const float invT = 1.f / (float)Tn;
   const long long total = (long long)N * H * W * cv;
@@ -118,7 +123,8 @@ maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
     }
     if (dskip != nullptr) {
       float sk[8];
-      load8(dskip + (long long)(n / Tn) * dskip_ns + ((long long)h * W + w) * dskip_ps + cb * 8, sk);
+      const int bi = t_major ? n % (N / Tn) : n / Tn;
+      load8(dskip + (long long)bi * dskip_ns + ((long long)h * W + w) * dskip_ps + cb * 8, sk);
 #pragma unroll
       for (int j = 0; j < 8; ++j) out[j] = fmaf(sk[j], invT, out[j]);
     }
@@ -129,7 +135,7 @@ maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
 template <typename T>
 __global__ void __launch_bounds__(256)
 time_mean_kernel(const T* __restrict__ src, T* __restrict__ dst, long long dst_ns, int dst_ps, int B, int Tn, int P,
-                 int C) {
+                 int C, int t_major) {
   const int cv = C / 8;
   const float invT = 1.f / (float)Tn;
   const long long total = (long long)B * P * cv;
@@ -143,7 +149,8 @@ time_mean_kernel(const T* __restrict__ src, T* __restrict__ dst, long long dst_n
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int t = 0; t < Tn; ++t) {
       float v[8];
-      load8(src + (((long long)b * Tn + t) * P + p) * C + cb * 8, v);
+      const long long img = t_major ? (long long)t * B + b : (long long)b * Tn + t;
+      load8(src + (img * P + p) * C + cb * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
@@ -362,33 +369,36 @@ static inline int grid_for(long long total) {
 
 using namespace pcm;
 
-extern "C" int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp, int dtype,
+extern "C" int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp, int T_, int dtype,
                                 pcm_stream_t s) {
   PCM_REQUIRE(Cp % 8 == 0 && Cp >= C, "nchw_to_nhwc: bad channel padding C=%d Cp=%d", C, Cp);
+  PCM_REQUIRE(T_ >= 1 && N % T_ == 0, "nchw_to_nhwc: N must be a multiple of T");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
   PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   x, (T*)y, N, C, H * W, Cp, nullptr)));
+                                   x, (T*)y, N, C, H * W, Cp, nullptr, T_)));
   return check_launch("nchw_to_nhwc");
 }
 
 extern "C" int pcm_season_embed_stage(const float* x5, const int* month, void* y, int N, int H, int W, int Cp,
-                                      int dtype, pcm_stream_t s) {
+                                      int T_, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(Cp % 8 == 0 && Cp >= 7, "season_embed_stage: Cp must be >= 7 and a multiple of 8");
+  PCM_REQUIRE(T_ >= 1 && N % T_ == 0, "season_embed_stage: N must be a multiple of T");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
   PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   x5, (T*)y, N, 5, H * W, Cp, month)));
+                                   x5, (T*)y, N, 5, H * W, Cp, month, T_)));
   return check_launch("season_embed_stage");
 }
 
-extern "C" int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, int W, int Cp, int dtype,
+extern "C" int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, int W, int Cp, int T_, int dtype,
                                 pcm_stream_t s) {
   PCM_REQUIRE(Cp % 8 == 0 && Cp >= C, "nhwc_to_nchw: bad channel padding C=%d Cp=%d", C, Cp);
+  PCM_REQUIRE(T_ >= 1 && N % T_ == 0, "nhwc_to_nchw: N must be a multiple of T");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
   PCM_DISPATCH_DTYPE(dtype, T, (nhwc_to_nchw_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   (const T*)x, y, N, C, H * W, Cp)));
+                                   (const T*)x, y, N, C, H * W, Cp, T_)));
   return check_launch("nhwc_to_nchw");
 }
 
@@ -402,24 +412,24 @@ extern "C" int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int
 }
 
 extern "C" int pcm_maxpool2_bwd_skip(const void* x, const void* dy, const void* dskip, long long dskip_ns,
-                                     int dskip_ps, void* dx, int N, int H, int W, int C, int T_, int dtype,
-                                     pcm_stream_t s) {
-  PCM_REQUIRE(C % 8 == 0 && T_ >= 1, "maxpool2_bwd_skip: bad shape");
+                                     int dskip_ps, void* dx, int N, int H, int W, int C, int T_, int t_major,
+                                     int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(C % 8 == 0 && T_ >= 1 && N % T_ == 0, "maxpool2_bwd_skip: bad shape");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * H * W * (C / 8);
   PCM_DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_skip_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
                                    (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps, (T*)dx, N, H, W, C,
-                                   T_)));
+                                   T_, t_major)));
   return check_launch("maxpool2_bwd_skip");
 }
 
 extern "C" int pcm_time_mean(const void* src, void* dst, long long dst_ns, int dst_ps, int B, int T_, int P, int C,
-                             int dtype, pcm_stream_t s) {
+                             int t_major, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(C % 8 == 0 && T_ >= 1, "time_mean: bad shape");
   if (B == 0) return PCM_OK;
   const long long total = (long long)B * P * (C / 8);
   PCM_DISPATCH_DTYPE(dtype, T, (time_mean_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   (const T*)src, (T*)dst, dst_ns, dst_ps, B, T_, P, C)));
+                                   (const T*)src, (T*)dst, dst_ns, dst_ps, B, T_, P, C, t_major)));
   return check_launch("time_mean");
 }
 

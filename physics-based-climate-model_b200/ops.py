@@ -180,23 +180,24 @@ class StageIn(torch.autograd.Function):
     """(N, C, H, W) fp32 -> (N, H, W, padc(C)) compute dtype."""
 
     @staticmethod
-    def forward(ctx, x, dtype, gran=16):
+    def forward(ctx, x, dtype, gran=16, T=1):
+        """T > 1: x is a flattened (B, T) window batch (image b*T + t); the staged tensor is t-major."""
         _require_cuda(x, "input")
         x = x.contiguous().float()
         N, C, H, W = x.shape
         Cp = (C + gran - 1) // gran * gran
         y = torch.empty((N, H, W, Cp), device=x.device, dtype=dtype)
-        _call("pcm_nchw_to_nhwc", x.data_ptr(), y.data_ptr(), N, C, H, W, Cp, _DT[dtype], _s())
-        ctx.shape = (N, C, H, W)
+        _call("pcm_nchw_to_nhwc", x.data_ptr(), y.data_ptr(), N, C, H, W, Cp, T, _DT[dtype], _s())
+        ctx.shape = (N, C, H, W, T)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        N, C, H, W = ctx.shape
+        N, C, H, W, T = ctx.shape
         dy = dy.contiguous()
         dx = torch.empty((N, C, H, W), device=dy.device, dtype=torch.float32)
-        _call("pcm_nhwc_to_nchw", dy.data_ptr(), dx.data_ptr(), N, C, H, W, dy.shape[-1], _DT[dy.dtype], _s())
-        return dx, None, None
+        _call("pcm_nhwc_to_nchw", dy.data_ptr(), dx.data_ptr(), N, C, H, W, dy.shape[-1], T, _DT[dy.dtype], _s())
+        return dx, None, None, None
 
 
 class StageOut(torch.autograd.Function):
@@ -207,7 +208,7 @@ class StageOut(torch.autograd.Function):
         x = x.contiguous()
         N, H, W, Cp = x.shape
         y = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
-        _call("pcm_nhwc_to_nchw", x.data_ptr(), y.data_ptr(), N, C, H, W, Cp, _DT[x.dtype], _s())
+        _call("pcm_nhwc_to_nchw", x.data_ptr(), y.data_ptr(), N, C, H, W, Cp, 1, _DT[x.dtype], _s())
         ctx.meta = (Cp, x.dtype)
         return y
 
@@ -217,19 +218,20 @@ class StageOut(torch.autograd.Function):
         dy = dy.contiguous().float()
         N, C, H, W = dy.shape
         dx = torch.empty((N, H, W, Cp), device=dy.device, dtype=dtype)
-        _call("pcm_nchw_to_nhwc", dy.data_ptr(), dx.data_ptr(), N, C, H, W, Cp, _DT[dtype], _s())
+        _call("pcm_nchw_to_nhwc", dy.data_ptr(), dx.data_ptr(), N, C, H, W, Cp, 1, _DT[dtype], _s())
         return dx, None
 
 
-def season_embed_stage(x5: torch.Tensor, month: torch.Tensor, dtype) -> torch.Tensor:
+def season_embed_stage(x5: torch.Tensor, month: torch.Tensor, dtype, T: int = 1) -> torch.Tensor:
     """main_final.py:186-216: (N,5,H,W) forcings + month index (N,) -> NHWC 8-channel frames with
-    sin/cos month channels (5, 6) synthesised on the fly, padded to 16 channels (no gradient: inputs are data)."""
+    sin/cos month channels (5, 6) synthesised on the fly, padded to 16 channels (no gradient: inputs are data).
+    T > 1: the N = B*T frames are given window-major (b*T + t) and staged t-major, as AttUNetConvLSTM wants."""
     _require_cuda(x5, "input")
     N, C, H, W = x5.shape
     assert C == 5
     y = torch.empty((N, H, W, 16), device=x5.device, dtype=dtype)
     _call("pcm_season_embed_stage", x5.contiguous().float().data_ptr(), month.to(torch.int32).contiguous().data_ptr(),
-          y.data_ptr(), N, H, W, 16, _DT[dtype], _s())
+          y.data_ptr(), N, H, W, 16, T, _DT[dtype], _s())
     return y
 
 
@@ -339,6 +341,7 @@ class PoolSkipFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, s, T):
+        """s: t-major frames (image t*B + b)."""
         s = s.contiguous()
         N, H, W, C = s.shape
         B = N // T
@@ -346,7 +349,7 @@ class PoolSkipFn(torch.autograd.Function):
         pooled = torch.empty((N, H // 2, W // 2, C), device=s.device, dtype=s.dtype)
         _call("pcm_maxpool2_fwd", s.data_ptr(), pooled.data_ptr(), N, H, W, C, d, _s())
         skip = torch.empty((B, H, W, C), device=s.device, dtype=s.dtype)
-        _call("pcm_time_mean", s.data_ptr(), skip.data_ptr(), H * W * C, C, B, T, H * W, C, d, _s())
+        _call("pcm_time_mean", s.data_ptr(), skip.data_ptr(), H * W * C, C, B, T, H * W, C, 1, d, _s())
         ctx.save_for_backward(s)
         ctx.T = T
         return pooled, skip
@@ -362,7 +365,7 @@ class PoolSkipFn(torch.autograd.Function):
             # dskip may be a channel-slice view of the decoder's concat gradient: pass its strides
             assert dskip.stride(3) == 1 and dskip.stride(1) == W * dskip.stride(2)
             ns, ps = dskip.stride(0), dskip.stride(2)
-        _call("pcm_maxpool2_bwd_skip", s.data_ptr(), _p(dp), _p(dskip), ns, ps, ds.data_ptr(), N, H, W, C, ctx.T,
+        _call("pcm_maxpool2_bwd_skip", s.data_ptr(), _p(dp), _p(dskip), ns, ps, ds.data_ptr(), N, H, W, C, ctx.T, 1,
               _DT[s.dtype], _s())
         return ds, None
 
@@ -385,7 +388,7 @@ class MaxPoolFn(torch.autograd.Function):
         N, H, W, C = s.shape
         ds = torch.empty_like(s)
         _call("pcm_maxpool2_bwd_skip", s.data_ptr(), dpooled.contiguous().data_ptr(), 0, 0, 0, ds.data_ptr(), N, H, W,
-              C, 1, _DT[s.dtype], _s())
+              C, 1, 0, _DT[s.dtype], _s())
         return ds
 
 
@@ -460,10 +463,21 @@ class ConvLSTMFn(torch.autograd.Function):
         acts = torch.empty((T, B, P, 4 * Ch), device=dev, dtype=dt)
         c_all = torch.empty((T, B, P, Ch), device=dev, dtype=torch.float32)
         h_all = torch.empty((T, B, H, W, Ch), device=dev, dtype=dt)
+        contiguous = (st_t == B and st_b == 1)          # t-major frames: every step is a block of B images
+        if contiguous:
+            conv_s1(x, wx, T * B, H, W, Cip, 4 * Ch, K, dst=gates, dst_f32=True, bias=b)      # Wx.x for ALL steps
+        else:
+            for t in range(T):
+                conv_s1(x, wx, B, H, W, Cip, 4 * Ch, K, dst=gates[t], dst_f32=True, bias=b,
+                        src_ns=st_b * img, src_off=t * st_t * img)
+        fused = dt == torch.bfloat16 and K == 3 and Ch in (16, 32, 64)
         for t in range(T):
-            conv_s1(x, wx, B, H, W, Cip, 4 * Ch, K, dst=gates[t], dst_f32=True, bias=b,
-                    src_ns=st_b * img, src_off=t * st_t * img)
-        for t in range(T):
+            if t > 0 and fused:
+                # tcgen05 conv of h_{t-1} with the sigmoid/tanh cell fused in the epilogue (gates stay in TMEM)
+                _call("pcm_convlstm_step_tc", h_all[t - 1].data_ptr(), wh.data_ptr(), gates[t].data_ptr(),
+                      c_all[t - 1].data_ptr(), h_all[t].data_ptr(), c_all[t].data_ptr(), acts[t].data_ptr(),
+                      B, H, W, Ch, st)
+                continue
             if t > 0:
                 conv_s1(h_all[t - 1], wh, B, H, W, Ch, 4 * Ch, K, dst=gates[t], dst_f32=True, accumulate=True)
             _call("pcm_lstm_cell_fwd", gates[t].data_ptr(), c_all[t - 1].data_ptr() if t > 0 else 0,
@@ -500,9 +514,14 @@ class ConvLSTMFn(torch.autograd.Function):
         KK = K * K
         Ct = Ci + Ch
         # dW[:, :Ci] — x frames may be time-strided, one launch per step; dW[:, Ci:] — one launch over t>=1
+        contiguous = (st_t == B and st_b == 1)
         if K == 3:
-            for t in range(T):
-                conv3x3_wgrad(dgates[t], x, gw, B, H, W, 4 * Ch, Cip, Ci, Ci_tot=Ct, x_ns=st_b * img, x_off=t * st_t * img)
+            if contiguous:
+                conv3x3_wgrad(dgates, x, gw, T * B, H, W, 4 * Ch, Cip, Ci, Ci_tot=Ct)
+            else:
+                for t in range(T):
+                    conv3x3_wgrad(dgates[t], x, gw, B, H, W, 4 * Ch, Cip, Ci, Ci_tot=Ct, x_ns=st_b * img,
+                                  x_off=t * st_t * img)
             if T > 1:
                 conv3x3_wgrad(dgates[1:], h_all[:-1], gw, (T - 1) * B, H, W, 4 * Ch, Ch, Ch, Ci_tot=Ct, dw_off=Ci * KK)
         else:
@@ -517,8 +536,11 @@ class ConvLSTMFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wxt = conv_weight_dgrad(w, dt, 0, Ci, Op=Cip)
             dx = torch.empty_like(x)
-            for t in range(T):
-                conv_s1(dgates[t], wxt, B, H, W, 4 * Ch, Cip, K, dst=dx, dst_ns=st_b * img, dst_off=t * st_t * img)
+            if contiguous:
+                conv_s1(dgates, wxt, T * B, H, W, 4 * Ch, Cip, K, dst=dx)
+            else:
+                for t in range(T):
+                    conv_s1(dgates[t], wxt, B, H, W, 4 * Ch, Cip, K, dst=dx, dst_ns=st_b * img, dst_off=t * st_t * img)
         return dx, rw, rb, None, None, None, None, None
 
 

@@ -53,12 +53,13 @@ class AttUNetConvLSTM(nn.Module):
     def forward(self, x_seq):
         """x_seq : (B, T, C_in, H, W); returns predictions for the last frame (B, C_out, H, W)."""
         B, T, C, H, W = x_seq.shape
-        x = ops.StageIn.apply(x_seq.reshape(B * T, C, H, W), compute_dtype())   # image n = b*T + t
+        # staged t-major (image n = t*B + b): every ConvLSTM step is then a contiguous block of B images
+        x = ops.StageIn.apply(x_seq.reshape(B * T, C, H, W), compute_dtype(), 16, T)
         return self.forward_staged(x, B, T)
 
     def forward_staged(self, x, B, T):
-        """x: NHWC frames (B*T, H, W, pad8(C_in)), image n = b*T + t (e.g. from
-        ops.season_embed_stage, which synthesises the sin/cos month channels on the fly)."""
+        """x: NHWC frames (T*B, H, W, 16), t-major: image n = t*B + b (e.g. from
+        ops.season_embed_stage(..., T=T), which synthesises the sin/cos month channels on the fly)."""
         s1 = self.enc1.forward_nhwc(x)
         p1, k1 = ops.PoolSkipFn.apply(s1, T)
         s2 = self.enc2.conv.forward_nhwc(p1)
@@ -66,7 +67,7 @@ class AttUNetConvLSTM(nn.Module):
         s3 = self.enc3.conv.forward_nhwc(p2)
         p3, k3 = ops.PoolSkipFn.apply(s3, T)
         s4 = self.enc4.conv.forward_nhwc(p3)
-        bott = self.convlstm.forward_nhwc(s4, T, B, st_t=1, st_b=T, last_only=True)
+        bott = self.convlstm.forward_nhwc(s4, T, B, st_t=B, st_b=1, last_only=True)
         d3 = self.up3.forward_nhwc(bott, k3)
         d2 = self.up2.forward_nhwc(d3, k2)
         d1 = self.up1.forward_nhwc(d2, k1)
