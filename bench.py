@@ -186,6 +186,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PCM_NCCL_DEBUG", "WARN")   # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_src = load_peaks()
 
@@ -298,8 +299,17 @@ def run_ours(args):
                                                               f"oracle (torch CPU fp32), {cores} threads"}
     if rank == 0:
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing a NCCL communicator down while a captured graph still references its kernels can hang
+        # (seen on 2 x B200): drop the graph, drain the device, meet at a barrier and leave without the
+        # collective destructor.
+        step.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
