@@ -133,40 +133,65 @@ def run_reference(args):
 
 
 def kernel_trace(step_fn, n_steps=2, dump=None):
-    """Eager steps with per-C-ABI-call CUDA events on the launching stream -> {name: [ms, calls, flops]}."""
+    """Eager steps with per-C-ABI-call CUDA events on the launching stream.  The device is first parked on
+    a ~50 ms spin kernel so the host queues the whole step ahead: the kernels then run back to back and the
+    event pairs measure kernel durations, not the host's launch latency.
+    -> list of (ms, name, args) of the LAST step, and the per-step totals by kernel name."""
     import torch
     from pcm_b200._lib import lib
     L = lib()
-    agg = {}
-    calls = []
     torch.cuda.synchronize()
-    for _ in range(n_steps):
+    last = []
+    agg = {}
+    for it in range(n_steps):
+        torch.cuda._sleep(100_000_000)
         L.trace = []
         step_fn()
         torch.cuda.synchronize()
         tr, L.trace = L.trace, None
-        for name, a, e0, e1 in tr:
-            ms = e0.elapsed_time(e1)
-            flops = 0.0
-            key = name
-            if name == "pcm_conv_gather":
-                # (src,src_ns,src_ps,Hs,Ws,Sc,dst,dst_ns,dst_ps,Hd,Wd,Dc,wk,bias,N,KH,KW,stride,pad,mode,...)
-                Hs, Ws, Sc, Hd, Wd, Dc, N, KH, KW, stride, mode = a[3], a[4], a[5], a[9], a[10], a[11], a[14], a[15], a[16], a[17], a[19]
-                taps = KH * KW if (mode == 0 or stride == 1) else (KH * KW) // (stride * stride)
-                flops = 2.0 * N * Hd * Wd * Dc * Sc * taps
-            elif name == "pcm_conv_wgrad":
-                Ha, Wa, Ca, Cb, N, KH, KW = a[3], a[4], a[5], a[12], a[18], a[19], a[20]
-                flops = 2.0 * N * Ha * Wa * Ca * Cb * KH * KW
-            calls.append((ms, name, flops, [x for x in a if isinstance(x, int) and abs(x) < (1 << 31)]))
-            rec = agg.setdefault(key, [0.0, 0, 0.0])
+        last = [(e0.elapsed_time(e1), name, a) for name, a, e0, e1 in tr]
+        for ms, name, a in last:
+            rec = agg.setdefault(name, [0.0, 0])
             rec[0] += ms / n_steps
             rec[1] += 1.0 / n_steps
-            rec[2] += flops / n_steps
     if dump:
+        from pcm_b200.costmodel import algo_cost, shape_key
         with open(dump, "w") as f:
-            for ms, name, flops, ints in calls[len(calls) // n_steps * (n_steps - 1):]:
-                f.write(f"{ms:9.4f} ms  {name:28s} {flops / 1e9:9.3f} GF  {flops / max(ms, 1e-6) / 1e9:9.2f} TF/s  {ints}\n")
-    return agg
+            for ms, name, a in last:
+                fl, by, _ = algo_cost(name, a)
+                f.write(f"{ms * 1e3:9.2f} us  {fl / max(ms, 1e-6) / 1e9:8.2f} TF/s {by / max(ms, 1e-6) / 1e6:8.1f} GB/s  "
+                        f"{shape_key(name, a)}\n")
+    return last, agg
+
+
+def roofline_groups(calls, peaks):
+    """Group the launches of one step by (kernel, shape); for each group: algorithmic FLOPs and bytes per
+    launch (costmodel.py), mean launch duration, the binding roof (whichever of FLOPs/peak_TF and
+    bytes/peak_BW is the larger time) and the achieved fraction of it."""
+    from pcm_b200.costmodel import algo_cost, shape_key
+    groups = {}
+    for ms, name, a in calls:
+        fl, by, _ = algo_cost(name, a)
+        g = groups.setdefault(shape_key(name, a), {"kernel": name, "launches": 0, "ms": 0.0, "flops": fl, "bytes": by})
+        g["launches"] += 1
+        g["ms"] += ms
+    tf_peak, bw_peak = peaks["bf16_tflops"], peaks["hbm_gbs"]
+    out = []
+    for key, g in groups.items():
+        avg_s = g["ms"] / g["launches"] / 1e3
+        t_tensor = g["flops"] / (tf_peak * 1e12)
+        t_hbm = g["bytes"] / (bw_peak * 1e9)
+        bound = "tensor" if t_tensor > t_hbm else "hbm"
+        if bound == "tensor":
+            ach, peak, unit = g["flops"] / avg_s / 1e12, tf_peak, "TFLOP/s"
+        else:
+            ach, peak, unit = g["bytes"] / avg_s / 1e9, bw_peak, "GB/s"
+        out.append({"launch": key, "kernel": g["kernel"], "launches_per_step": g["launches"],
+                    "ms_per_step": round(g["ms"], 5), "avg_us": round(avg_s * 1e6, 2), "bound": bound,
+                    "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
+                    "algo_flops_per_launch": g["flops"], "algo_bytes_per_launch": g["bytes"]})
+    out.sort(key=lambda r: -r["ms_per_step"])
+    return out
 
 
 def run_ours(args):
@@ -275,21 +300,29 @@ def run_ours(args):
 
     # ---- dominant kernel roofline: eager pass with per-call CUDA events on the launching stream -----------
     if rank == 0 and world == 1:
-        agg = kernel_trace(step._step_impl, n_steps=2, dump=args.trace_file)
+        calls, agg = kernel_trace(step._step_impl, n_steps=2, dump=args.trace_file)
         tot = sum(v[0] for v in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1][0])
-        name, (kms, calls, flops) = top[0]
         line["kernel_breakdown_ms"] = {k: round(v[0], 4) for k, v in top[:12]}
         line["kernel_time_ms_eager_step"] = round(tot, 4)
-        if flops > 0:
-            ach = flops / (kms / 1e3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["bf16_tflops"],
-                                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
-                                "calls_per_step": calls, "ms_per_step": kms, "share_of_step": kms / tot,
-                                "peak_source": peak_src + ", burst figure (kernel timed alone between events)"}
-        else:
-            line["roofline"] = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peaks["hbm_gbs"],
-                                "unit": "GB/s", "frac": None, "traffic": None, "ms_per_step": kms}
+        groups = roofline_groups(calls, peaks)
+        g0 = groups[0]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from `ncu --set full`
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(g0["launch"])
+        line["roofline"] = {"bound": g0["bound"], "kernel": g0["kernel"], "launch": g0["launch"],
+                            "achieved": g0["achieved"], "peak": g0["peak"], "unit": g0["unit"], "frac": g0["frac"],
+                            "traffic": traffic, "avg_launch_us": g0["avg_us"],
+                            "launches_per_step": g0["launches_per_step"], "share_of_step": round(g0["ms_per_step"] / tot, 4),
+                            "algo_bytes_per_launch": g0["algo_bytes_per_launch"],
+                            "algo_flops_per_launch": g0["algo_flops_per_launch"],
+                            "peak_source": peak_src + ", burst figures (kernel timed alone between events)",
+                            "how": "dominant (kernel, shape) group of one eager step; CUDA events around each launch "
+                                   "on the launching stream with the host queued ahead of the device"}
+        line["roofline_top"] = [{k: r[k] for k in ("launch", "launches_per_step", "ms_per_step", "avg_us", "bound",
+                                                   "achieved", "unit", "frac")} for r in groups[:10]]
         # CPU baseline beside it: the oracle port on the host cores, bounded sample
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

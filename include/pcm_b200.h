@@ -88,6 +88,17 @@ PCM_API int pcm_convlstm_step_tc(const void* h_prev, const void* wh, const float
 PCM_API int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                             long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
                             long long st, int N, int H, int W, pcm_stream_t s);
+/* 1x1 convolution / linear layer on the same tcgen05 pipeline (one tap): dst(n,h,w,co) = sum_ci src(n,h,w,ci)*wk[co][ci]
+ * (+bias) (relu) (+= dst, fp32 only).  Call sites: the ResidualBlock skip conv (src/models.py:56), and — with the token
+ * matrix [M][E] presented as an image (N=1, H*W=M) — every nn.Linear of the transformer encoder layer
+ * (src/cnn_transformer.py:25-31: in_proj, out_proj, linear1(+ReLU), linear2).  wk: bf16 [Cout][Cin]. */
+PCM_API int pcm_conv1x1_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                           long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                           int dst_f32, int accumulate, int relu, pcm_stream_t s);
+/* weight gradient of the above: dw[co*sa + ci*sb] += sum_p dy(p,co)*x(p,ci)  (fp32, accumulates) */
+PCM_API int pcm_wgrad1x1_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
+                            long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
+                            int N, int H, int W, pcm_stream_t s);
 /* number of bounded-wait timeouts recorded by the tensor-core kernels since load (0 when healthy; syncs) */
 PCM_API int pcm_tc_error_count(void);
 /* weight gradient: dw[ac*sa + bc*sb + tap*st] += sum_{n,ha,wa} A(n,ha,wa,ac) * B(n,hb,wb,bc),
@@ -138,6 +149,52 @@ PCM_API int pcm_gn_silu_bwd_reduce(const void* da, const float* dpool, const voi
 PCM_API int pcm_gn_silu_bwd_apply(const void* da, const float* dpool, const void* x, const float* stats,
                           const float* gamma, const float* beta, const float* gsum, void* dx, int N, int P, int C,
                           int G, float eps, int dtype, pcm_stream_t s);
+
+/* ---- BatchNorm2d, training mode (src/models.py:48,51,57,91,109; eps 1e-5, momentum 0.1) on NHWC rows
+ * (R = N*H*W rows of C channels; C = 8 * a divisor of 256).  sums[c] = (sum x, sum x^2), zeroed by the caller. */
+PCM_API int pcm_bn_stats(const void* x, float* sums, long long R, int C, int dtype, pcm_stream_t s);
+/* y = [relu]( gamma*(x-mean)*rstd + beta [+ res] )   (res nullable: the residual add of src/models.py:70-71) */
+PCM_API int pcm_bn_apply_fwd(const void* x, const float* sums, const float* gamma, const float* beta, const void* res,
+                             void* y, long long R, int C, float eps, int relu, int dtype, pcm_stream_t s);
+/* running_mean/var <- (1-m)*old + m*(batch mean / unbiased batch var); num_batches_tracked (int64, nullable) += 1 */
+PCM_API int pcm_bn_update_running(const float* sums, float* running_mean, float* running_var,
+                                  long long* num_batches_tracked, long long R, int C, float momentum, pcm_stream_t s);
+/* backward pass 1: with dz = dy * (y > 0) when y != NULL (ReLU mask), else dz = dy:
+ * dsum[c] += (sum dz, sum dz*xhat)   (caller zeroes dsum) */
+PCM_API int pcm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* sums, float* dsum, long long R,
+                              int C, float eps, int dtype, pcm_stream_t s);
+/* pass 2: dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dres = dz (nullable); dgamma/dbeta += dsum */
+PCM_API int pcm_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* sums, const float* gamma,
+                             const float* dsum, void* dx, void* dres, float* dgamma, float* dbeta, long long R, int C,
+                             float eps, int dtype, pcm_stream_t s);
+/* elementwise helpers (n multiple of 8): out = a + b ; y[i] = x[i] + b[i % period] (pos_embedding add,
+ * src/cnn_transformer.py:48) ; dx = dy * (y > 0) (nn.ReLU backward) */
+PCM_API int pcm_add(const void* a, const void* b, void* out, long long n, int dtype, pcm_stream_t s);
+PCM_API int pcm_add_bcast(const void* x, const float* b, void* y, long long n, long long period, int dtype,
+                          pcm_stream_t s);
+/* out[r] += sum_b x[b][r] (x: [B][R]; gradient of a parameter broadcast over the batch, e.g. pos_embedding) */
+PCM_API int pcm_batch_sum(const void* x, float* out, int B, long long R, int dtype, pcm_stream_t s);
+PCM_API int pcm_relu_bwd(const void* dy, const void* y, void* dx, long long n, int dtype, pcm_stream_t s);
+/* nn.Dropout: y = x * keep(seed, i)/(1-p) with a counter-based mask (the same call on dy is the backward);
+ * nn.Dropout2d (src/models.py:103): mask[n*C + c] in {0, 1/(1-p)}, applied with pcm_scale_channels */
+PCM_API int pcm_dropout(const void* x, void* y, long long n, float p, long long seed, int dtype, pcm_stream_t s);
+PCM_API int pcm_dropout_mask(float* mask, long long n, float p, long long seed, pcm_stream_t s);
+
+/* ---- transformer encoder layer (src/cnn_transformer.py:25-31; post-norm, batch_first) ---------------------
+ * y = LayerNorm(a + b)*gamma + beta over the last dim E (eps inside sqrt); sum_out = a + b (nullable) and
+ * stat[m] = (mean, rstd) are saved for backward.  b nullable. */
+PCM_API int pcm_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* sum_out,
+                                  void* y, float* stat, int M, int E, float eps, int dtype, pcm_stream_t s);
+/* ds (gradient of a + b); dgamma, dbeta accumulate */
+PCM_API int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float* stat, const float* gamma, void* ds,
+                              float* dgamma, float* dbeta, int M, int E, int dtype, pcm_stream_t s);
+/* multi-head self-attention core of nn.MultiheadAttention: qkv [B][L][3*nh*D] (q | k | v; head h = columns
+ * h*D..), out [B][L][nh*D] = softmax(scale * q k^T) v per head, lse [B][nh][L] fp32 saved for backward.
+ * drop_p: dropout on the attention probabilities (counter-based mask from `seed`).  D in {8, 16, 32, 64}. */
+PCM_API int pcm_mha_fwd(const void* qkv, void* out, float* lse, int B, int L, int nh, int D, float scale, float drop_p,
+                        long long seed, int dtype, pcm_stream_t s);
+PCM_API int pcm_mha_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int L,
+                        int nh, int D, float scale, float drop_p, long long seed, int dtype, pcm_stream_t s);
 
 /* ---- pooling / skips (src/unet.py:54,57; src/unet_convlstm_attention.py:21,24,91-93) ----------- */
 PCM_API int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, pcm_stream_t s);

@@ -63,6 +63,7 @@ class _Lib:
             self._fn[name] = fn
         self.launches = 0                           # C-ABI calls issued (bench `gpu_launches`)
         self.trace = None                           # list -> per-call CUDA-event timing (bench roofline pass)
+        self.last_call = None                       # name of the most recent C-ABI call (tests: which kernel ran)
 
     def last_error(self) -> str:
         return self._fn["pcm_last_error"]().decode()
@@ -71,6 +72,7 @@ class _Lib:
         return int(self._fn["pcm_version"]())
 
     def call(self, name: str, *args):
+        self.last_call = name
         if self.trace is not None:
             import torch
             e0 = torch.cuda.Event(enable_timing=True)

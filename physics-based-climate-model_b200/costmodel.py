@@ -1,0 +1,112 @@
+"""Algorithmic cost of one C-ABI call: (FLOPs, HBM bytes) from the call's own arguments.
+
+Used by bench.py for the per-kernel roofline (`achieved` = algorithmic work / measured duration) and by
+tools/microbench.py.  "Algorithmic" = what the operation must move/compute at minimum: every input element
+read once, every output written once, MACs x 2 — not what the implementation happens to do.
+Argument names are those of include/pcm_b200.h (the binding parses them from the header)."""
+from __future__ import annotations
+
+from ._lib import PROTOS
+
+
+def _named(name, args):
+    return {an: a for (_, an), a in zip(PROTOS[name][1], args)}
+
+
+def algo_cost(name: str, args):
+    """-> (flops, bytes, bound) with bound in {"tensor", "hbm"}; (0, 0, "hbm") for unknown calls."""
+    a = _named(name, args)
+    es = lambda: 2 if a.get("dtype", 1) == 1 else 4          # activation element size
+    if name == "pcm_conv3x3_tc":
+        px = a["N"] * a["H"] * a["W"]
+        taps = a.get("taps", 9)
+        fl = 2.0 * px * a["Cin"] * a["Cout"] * taps
+        osz = 4 if a["dst_f32"] else 2
+        by = px * (a["Cin"] * 2 + a["Cout"] * osz * (2 if a["accumulate"] else 1)) + taps * a["Cin"] * a["Cout"] * 2
+        return fl, by, "tensor"
+    if name == "pcm_convlstm_step_tc":
+        px = a["B"] * a["H"] * a["W"]
+        Ch = a["Ch"]
+        fl = 2.0 * px * Ch * 4 * Ch * 9
+        # h_prev bf16 + gx fp32 [4Ch] + c_prev fp32 in; h bf16 + c fp32 + acts bf16 [4Ch] out
+        by = px * (Ch * 2 + 4 * Ch * 4 + Ch * 4 + Ch * 2 + Ch * 4 + 4 * Ch * 2) + 9 * Ch * 4 * Ch * 2
+        return fl, by, "tensor"
+    if name == "pcm_wgrad3x3_tc":
+        px = a["N"] * a["H"] * a["W"]
+        taps = a.get("taps", 9)
+        fl = 2.0 * px * a["Co"] * a["Ci"] * taps
+        by = px * (a["Co"] + a["Ci"]) * 2 + taps * a["Co_real"] * a["Ci_real"] * 4
+        return fl, by, "tensor"
+    if name == "pcm_gemm_tc":
+        fl = 2.0 * a["M"] * a["N"] * a["K"]
+        by = a["M"] * a["K"] * 2 + a["N"] * a["K"] * 2 + a["M"] * a["N"] * (4 if a.get("dst_f32") else 2)
+        return fl, by, "tensor"
+    if name == "pcm_conv_gather":
+        taps = a["KH"] * a["KW"]
+        if a["mode"] == 1 or a["stride"] > 1:
+            # strided: every dst pixel sees taps/stride^2 taps (mode 1) or all taps (mode 0)
+            taps_eff = taps if a["mode"] == 0 else max(1, taps // (a["stride"] ** 2))
+        else:
+            taps_eff = taps
+        fl = 2.0 * a["N"] * a["Hd"] * a["Wd"] * a["Dc"] * a["Sc"] * taps_eff
+        by = a["N"] * (a["Hs"] * a["Ws"] * a["Sc"] * es() + a["Hd"] * a["Wd"] * a["Dc"] * (4 if a["dst_f32"] else es()))
+        return fl, by, "tensor"
+    if name == "pcm_conv_wgrad":
+        fl = 2.0 * a["N"] * a["Ha"] * a["Wa"] * a["Ca"] * a["Cb"] * a["KH"] * a["KW"]
+        by = a["N"] * (a["Ha"] * a["Wa"] * a["Ca"] + a["Hb"] * a["Wb"] * a["Cb"]) * es()
+        return fl, by, "tensor"
+    n_el = None
+    if name in ("pcm_gn_stats",):
+        return 0.0, a["N"] * a["P"] * a["C"] * es(), "hbm"
+    if name in ("pcm_gn_silu_fwd", "pcm_scale_channels"):
+        return 0.0, 2 * a["N"] * a["P"] * a["C"] * es(), "hbm"
+    if name == "pcm_gn_silu_bwd_reduce":
+        return 0.0, 2 * a["N"] * a["P"] * a["C"] * es(), "hbm"                 # da, x in
+    if name == "pcm_gn_silu_bwd_apply":
+        return 0.0, 3 * a["N"] * a["P"] * a["C"] * es(), "hbm"                 # da, x in; dx out
+    if name == "pcm_se_chanstat_fwd":
+        return 0.0, a["N"] * a["P"] * (a["C"] * es() + 8), "hbm"               # a in; cmap (2 fp32) out
+    if name == "pcm_spatial_gate_fwd":
+        px = a["N"] * a["H"] * a["W"]
+        return 0.0, px * (2 * a["C"] * es() + 8 + 4), "hbm"                    # a in, out; cmap in, gate out
+    if name == "pcm_spatial_gate_bwd_dq":
+        return 0.0, a["N"] * a["P"] * (2 * a["C"] * es() + 8), "hbm"           # dout, a in; gate in, dq out
+    if name == "pcm_spatial_gate_bwd_dw":
+        return 0.0, a["N"] * a["H"] * a["W"] * 12, "hbm"                       # dq, cmap in
+    if name == "pcm_spatial_gate_bwd_da":
+        px = a["N"] * a["H"] * a["W"]
+        return 0.0, px * (3 * a["C"] * es() + 16), "hbm"                       # dout, a in; da out; gate, cmap, dq
+    if name == "pcm_maxpool2_fwd":
+        return 0.0, a["N"] * a["H"] * a["W"] * a["C"] * es() * 1.25, "hbm"
+    if name == "pcm_maxpool2_bwd_skip":
+        return 0.0, a["N"] * a["H"] * a["W"] * a["C"] * es() * 2.25, "hbm"     # x in, dx out, dy (1/4) in
+    if name == "pcm_time_mean":
+        return 0.0, a["B"] * (a["T"] + 1) * a["P"] * a["C"] * es(), "hbm"
+    if name == "pcm_channel_sum":
+        return 0.0, a["N"] * a["P"] * a["C"] * es(), "hbm"
+    if name in ("pcm_nchw_to_nhwc", "pcm_nhwc_to_nchw"):
+        return 0.0, a["N"] * a["H"] * a["W"] * (a["C"] * 4 + a["Cp"] * es()), "hbm"
+    if name == "pcm_lstm_cell_fwd":
+        return 0.0, a["M"] * a["Ch"] * (16 + 4 + 4 * es() + 4 + es()), "hbm"
+    if name == "pcm_lstm_cell_bwd":
+        return 0.0, a["M"] * a["Ch"] * (2 * es() + 4 + 4 * es() + 8 + 4 * es() + 4), "hbm"
+    if name in ("pcm_head_fwd", "pcm_head_bwd"):
+        k = 2 if name == "pcm_head_bwd" else 1
+        return 2.0 * a["N"] * a["P"] * a["C"] * a["K"] * k, a["N"] * a["P"] * (a["C"] * es() * k + a["K"] * 4), "hbm"
+    if name in ("pcm_mse_fwd", "pcm_mse_bwd"):
+        return 0.0, a["n"] * 4 * (2 if name == "pcm_mse_fwd" else 3), "hbm"
+    if name == "pcm_adam_step":
+        return 0.0, a["n"] * 4 * 7, "hbm"                                      # p,g,m,v in; p,m,v out
+    if name == "pcm_pack_weight":
+        return 0.0, a["taps"] * (a["O"] * a["I"] * 4 + a["Op"] * a["Ip"] * es()), "hbm"
+    if name == "pcm_metric_partial":
+        return 0.0, 2.0 * a["T"] * a["V"] * a["Y"] * a["X"] * 4, "hbm"
+    return 0.0, 0.0, "hbm"
+
+
+def shape_key(name: str, args) -> str:
+    """Short signature of the launch's shape (its integer, non-pointer arguments), for grouping identical launches."""
+    import ctypes
+    ints = [str(x) for (ct, an), x in zip(PROTOS[name][1], args)
+            if ct in (ctypes.c_int, ctypes.c_longlong) and an not in ("dtype",)]
+    return name[4:] + "[" + ",".join(ints) + "]"

@@ -28,6 +28,7 @@ struct ConvTcParams {
   int N, H, W, Cin, Cout;
   int Wb, Hb, Nb, tiles_w, tiles_h, num_tiles;
   int KC, kchunks, stages;
+  int ksz, relu;          // kernel size (1 or 3; pad = ksz/2), ReLU in the store epilogue
   long long dst_ns;
   int dst_ps, dst_f32, accumulate;
   uint32_t tmem_cols, acc_stride, a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
@@ -71,7 +72,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kiters = 9 * p.kchunks;
+  const int ntaps = p.ksz * p.ksz, kpad = p.ksz >> 1;
+  const int kiters = ntaps * p.kchunks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -84,13 +86,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int th = (tile / p.tiles_w) % p.tiles_h;
         const int tn = tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.Wb, h0 = th * p.Hb, n0 = tn * p.Nb;
-        for (int tap = 0; tap < 9 && ok; ++tap) {
-          const int kh = tap / 3, kw = tap % 3;
+        for (int tap = 0; tap < ntaps && ok; ++tap) {
+          const int kh = tap / p.ksz, kw = tap % p.ksz;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             ok = mbar_wait(&empty[stage], phase ^ 1, err);
             if (!ok) break;
             mbar_expect_tx(&full[stage], p.a_tx_bytes + p.b_tx_bytes);
-            tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + kw - 1, h0 + kh - 1, n0);
+            tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + kw - kpad, h0 + kh - kpad, n0);
             tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage], kc * p.KC, 0, tap);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -214,6 +216,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (p.dst_f32) {
             float* dp = reinterpret_cast<float*>(dst) + off + c0;
@@ -520,7 +526,7 @@ extern "C" int pcm_tc_error_count(void) {
 static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, const float* lstm_gx, const float* lstm_c_prev,
-                           float* lstm_c_out, void* lstm_acts, pcm_stream_t s) {
+                           float* lstm_c_out, void* lstm_acts, pcm_stream_t s, int ksz = 3, int relu = 0) {
   PCM_REQUIRE(Cin % 16 == 0 && Cin >= 16, "conv3x3_tc: Cin must be a multiple of 16 (got %d)", Cin);
   PCM_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv3x3_tc: Cin above 64 must be a multiple of 64 (got %d)", Cin);
   PCM_REQUIRE(Cin == 16 || Cin == 32 || Cin >= 64, "conv3x3_tc: unsupported Cin %d", Cin);
@@ -543,7 +549,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   }
   unsigned int* err = tc_error_counter();
   PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
-  if (halo_env && lstm_gx == nullptr && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
+  if (halo_env && ksz == 3 && !relu && lstm_gx == nullptr && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
     ConvHaloParams h;
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout;
     h.Wb = h.Hb = h.Nb = 1;
@@ -605,6 +611,8 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   p.num_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.KC = Cin < 64 ? Cin : 64;
   p.kchunks = Cin / p.KC;
+  p.ksz = ksz; p.relu = relu;
+  const int ntaps = ksz * ksz;
   p.dst_ns = dst_ns; p.dst_ps = dst_ps; p.dst_f32 = dst_f32; p.accumulate = accumulate;
   p.acc_stride = Cout < 32 ? 32 : Cout;
   uint32_t cols = 32;
@@ -617,7 +625,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   const size_t per_stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
   int stages = (int)((200 * 1024) / per_stage);
   if (stages > 8) stages = 8;
-  if (stages > 9 * p.kchunks) stages = 9 * p.kchunks;
+  if (stages > ntaps * p.kchunks) stages = ntaps * p.kchunks;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = 1024 + stages * per_stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
@@ -631,7 +639,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     if (rc != PCM_OK) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
     uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
     uint32_t box[3] = {(uint32_t)p.KC, (uint32_t)Cout, 1};
     int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, p.KC * 2);
@@ -667,4 +675,11 @@ extern "C" int pcm_convlstm_step_tc(const void* h_prev, const void* wh, const fl
   PCM_REQUIRE(Ch % 16 == 0 && 4 * Ch <= 256, "convlstm_step_tc: Ch must be a multiple of 16, <= 64 (got %d)", Ch);
   return conv3x3_tc_impl(h_prev, (long long)H * W * Ch, Ch, H, W, Ch, h_out, (long long)H * W * Ch, Ch, 4 * Ch, wh,
                          nullptr, B, 0, 0, gx, c_prev, c_out, acts, s);
+}
+
+extern "C" int pcm_conv1x1_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                              long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                              int dst_f32, int accumulate, int relu, pcm_stream_t s) {
+  return conv3x3_tc_impl(src, src_ns, src_ps, H, W, Cin, dst, dst_ns, dst_ps, Cout, wk, bias, N, dst_f32, accumulate,
+                         nullptr, nullptr, nullptr, nullptr, s, 1, relu);
 }

@@ -23,6 +23,7 @@ struct WgradTcParams {
   int Cca, Ccb, na_chunks, nb_chunks;
   int Hb, Nb, tiles_h, num_ktiles, Kpad;
   int tpg, ngroups;             // taps per group, groups
+  int ksz, ntaps;               // kernel size (1 or 3), ksz*ksz
   int stages;
   long long sa, sb, st;
   uint32_t a_chunk_bytes, b_chunk_bytes, a_stage_bytes, b_stage_bytes, tx_bytes, tmem_cols, lbo_a, lbo_b;
@@ -46,7 +47,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, nsplit = gridDim.x, mtile = blockIdx.y, group = blockIdx.z;
   const int tap0 = group * p.tpg;
-  const int ntap = min(p.tpg, 9 - tap0);
+  const int ntap = min(p.tpg, p.ntaps - tap0);
 
   // rows TMA never writes (K padding, shifted-view overrun) must read as zero: clear the ring once
   {
@@ -83,7 +84,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c = 0; c < p.na_chunks; ++c)
           tma_load_4d(a + (size_t)c * p.a_chunk_bytes, &tmA, &full[stage], mtile * 128 + c * p.Cca, 0, h0, n0);
         for (int c = 0; c < p.nb_chunks; ++c)
-          tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, -1, h0 - 1, n0);
+          tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, -(p.ksz >> 1), h0 - (p.ksz >> 1), n0);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -108,7 +109,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint64_t bd = bdesc0 + (uint64_t)(stage * b_step);
         for (int tl = 0; tl < ntap; ++tl) {
           const int tap = tap0 + tl;
-          const uint64_t bt = bd + (uint64_t)((tap / 3) * b_tap_row + (tap % 3) * b_px);
+          const uint64_t bt = bd + (uint64_t)((tap / p.ksz) * b_tap_row + (tap % p.ksz) * b_px);
           const uint32_t d = tmem_base + tl * ci;
           for (int k = 0; k < ksteps; ++k)
             umma_bf16(d, ad + (uint64_t)(k * a_k), bt + (uint64_t)(k * b_k), idesc, (t | k) != 0);
@@ -156,14 +157,15 @@ static int g_wg_sms = 0;
 
 using namespace pcm;
 
-extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
-                               long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
-                               long long st, int N, int H, int W, pcm_stream_t s) {
+static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
+                         long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
+                         long long st, int N, int H, int W, int ksz, pcm_stream_t s) {
+  const int pad = ksz >> 1, ntaps = ksz * ksz;
   PCM_REQUIRE(Co % 16 == 0 && (Co <= 64 ? (Co == 16 || Co == 32 || Co == 64) : Co % 128 == 0),
               "wgrad3x3_tc: Co must be 16, 32, 64 or a multiple of 128 (got %d)", Co);
   PCM_REQUIRE(Ci % 16 == 0 && (Ci <= 64 ? (Ci == 16 || Ci == 32 || Ci == 64) : (Ci % 64 == 0 && Ci <= 256)),
               "wgrad3x3_tc: Ci must be 16, 32, 64, 128, 192 or 256 (got %d)", Ci);
-  PCM_REQUIRE(W + 2 <= 256 && H + 2 <= 256, "wgrad3x3_tc: grid too large for one TMA box (W=%d H=%d)", W, H);
+  PCM_REQUIRE(W + 2 * pad <= 256 && H + 2 * pad <= 256, "wgrad3x3_tc: grid too large for one TMA box (W=%d H=%d)", W, H);
   PCM_REQUIRE(dy_ps % 8 == 0 && x_ps % 8 == 0 && dy_ns % 8 == 0 && x_ns % 8 == 0, "wgrad3x3_tc: strides must be multiples of 8");
   if (N == 0) return PCM_OK;
   if (g_wg_sms == 0) {
@@ -173,7 +175,8 @@ extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int C
     if (g_wg_sms <= 0) g_wg_sms = 148;
   }
   WgradTcParams p;
-  p.N = N; p.H = H; p.W = W; p.Wp = W + 2;
+  p.N = N; p.H = H; p.W = W; p.Wp = W + 2 * pad;
+  p.ksz = ksz; p.ntaps = ntaps;
   p.Co_real = Co_real; p.Ci_real = Ci_real; p.Ci = Ci;
   p.Cca = Co < 64 ? Co : 64;
   p.Ccb = Ci < 64 ? Ci : 64;
@@ -182,23 +185,28 @@ extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int C
   p.nb_chunks = Ci / p.Ccb;
   const int mtiles = (Co + 127) / 128;
   p.sa = sa; p.sb = sb; p.st = st;
-  // K tile: whole images (with their zero rows) when small, else a block of image rows
-  const int rows_full = (H + 2) * p.Wp;
+  // K tile: whole images (with their zero rows) when small, else a block of image rows; capped so that one
+  // pipeline stage (A: m_extent channels, B: Ci channels, bf16) stays near 100 KB (two stages fit)
+  const int rows_full = (H + 2 * pad) * p.Wp;
+  int rows_cap = (int)((100 * 1024) / ((size_t)(m_extent + Ci) * 2)) - 2 * pad * p.Wp - 2 * pad;
+  if (rows_cap > 240) rows_cap = 240;
+  if (rows_cap < 16) rows_cap = 16;
   int a_box_h, b_box_h;
-  if (rows_full <= 128) {
-    p.Nb = 256 / rows_full;
+  if (rows_full <= 128 && rows_full <= rows_cap) {
+    p.Nb = (rows_cap + 16) / rows_full;
     if (p.Nb > N) p.Nb = N;
+    if (p.Nb < 1) p.Nb = 1;
     p.Hb = H;
-    a_box_h = H + 2; b_box_h = H + 2;
+    a_box_h = H + 2 * pad; b_box_h = H + 2 * pad;
     p.tiles_h = 1;
   } else {
     p.Nb = 1;
-    int hb = 240 / p.Wp;
+    int hb = rows_cap / p.Wp;
     if (hb < 1) hb = 1;
     if (hb > H) hb = H;
     p.tiles_h = (H + hb - 1) / hb;
     p.Hb = (H + p.tiles_h - 1) / p.tiles_h;
-    a_box_h = p.Hb; b_box_h = p.Hb + 2;
+    a_box_h = p.Hb; b_box_h = p.Hb + 2 * pad;
   }
   const int tiles_n = (N + p.Nb - 1) / p.Nb;
   p.num_ktiles = tiles_n * p.tiles_h;
@@ -208,7 +216,7 @@ extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int C
   const uint32_t rba = p.Cca * 2, rbb = p.Ccb * 2;
   // M blocks beyond the real channels alias the tile shifted by 8 rows per block: needs <= 56 rows of slack
   const int a_alloc = p.Kpad + (p.na_chunks * p.Cca >= 128 ? 0 : 64);
-  int b_alloc = p.Kpad + 2 * p.Wp + 2;
+  int b_alloc = p.Kpad + 2 * pad * p.Wp + 2 * pad;
   if (b_alloc < b_rows) b_alloc = b_rows;
   p.a_chunk_bytes = ((uint32_t)a_alloc * rba + 1023u) & ~1023u;
   p.b_chunk_bytes = ((uint32_t)b_alloc * rbb + 1023u) & ~1023u;
@@ -219,9 +227,9 @@ extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int C
   p.lbo_a = (p.na_chunks * p.Cca >= 128) ? p.a_chunk_bytes : 8 * rba;
   p.lbo_b = p.b_chunk_bytes;
   p.tpg = 512 / Ci;
-  if (p.tpg > 9) p.tpg = 9;
-  p.ngroups = (9 + p.tpg - 1) / p.tpg;
-  p.tpg = (9 + p.ngroups - 1) / p.ngroups;                      // balance the groups
+  if (p.tpg > ntaps) p.tpg = ntaps;
+  p.ngroups = (ntaps + p.tpg - 1) / p.tpg;
+  p.tpg = (ntaps + p.ngroups - 1) / p.ngroups;                  // balance the groups
   uint32_t cols = 32;
   while (cols < (uint32_t)(p.tpg * Ci)) cols <<= 1;
   p.tmem_cols = cols;
@@ -262,4 +270,16 @@ extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int C
   dim3 grid(nsplit, mtiles, p.ngroups);
   wgrad3x3_tc_kernel<<<grid, kWgThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dw, err, p);
   return check_launch("wgrad3x3_tc");
+}
+
+extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
+                               long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
+                               long long st, int N, int H, int W, pcm_stream_t s) {
+  return wgrad_tc_impl(dy, dy_ns, dy_ps, Co, Co_real, x, x_ns, x_ps, Ci, Ci_real, dw, sa, sb, st, N, H, W, 3, s);
+}
+
+extern "C" int pcm_wgrad1x1_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
+                               long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
+                               int N, int H, int W, pcm_stream_t s) {
+  return wgrad_tc_impl(dy, dy_ns, dy_ps, Co, Co_real, x, x_ns, x_ps, Ci, Ci_real, dw, sa, sb, 0, N, H, W, 1, s);
 }

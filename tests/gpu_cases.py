@@ -39,14 +39,16 @@ def _module_run(mod, sd, x, y, need_dx=True):
     return out.detach().cpu(), float(loss.detach().cpu()), grads, (xg.grad.detach().cpu() if need_dx else None)
 
 
-def compare(mod, fn, sd, x, y, dtype, golden=None):
-    """-> dict(out=rel_l2, loss=rel, dx=rel_l2, grads={name: rel_l2}, golden_* likewise)."""
+def compare(mod, fn, sd, x, y, dtype, golden=None, oracle_keys=None):
+    """-> dict(out=rel_l2, loss=rel, dx=rel_l2, grads={name: rel_l2}, golden_* likewise).
+    oracle_keys: the entries of sd the oracle function takes (module buffers are left out)."""
     set_compute_dtype(dtype)
     try:
         out, loss, grads, dx = _module_run(mod, sd, x, y)
     finally:
         set_compute_dtype(torch.bfloat16)
-    o_out, o_loss, o_grads, o_dx = _oracle_run(fn, sd, x, y)
+    osd = sd if oracle_keys is None else {k: sd[k] for k in oracle_keys}
+    o_out, o_loss, o_grads, o_dx = _oracle_run(fn, osd, x, y)
     res = {"out": rel_l2(out.numpy(), o_out.numpy()), "loss": abs(loss - o_loss) / abs(o_loss),
            "dx": rel_l2(dx.numpy(), o_dx.numpy()), "grads": {}, "gnorm": {}}
     for k, og in o_grads.items():
@@ -232,3 +234,75 @@ def case_season_stage():
     want[..., 5] = torch.sin(ang)[:, None, None]
     want[..., 6] = torch.cos(ang)[:, None, None]
     return {"max_abs": float((y - want).abs().max())}
+
+
+def _buffers_state(sd, mod):
+    """oracle state dicts hold parameters only; BN buffers keep the constructor defaults."""
+    full = dict(mod.state_dict())
+    full.update(sd)
+    return full
+
+
+def case_simplecnn(dtype, tag="simplecnn_small"):
+    from pcm_b200.src.models import SimpleCNN
+    cfg, z = load_golden(tag)
+    sd = O.synth_state_dict(O.simplecnn_spec(cfg["n_in"], cfg["n_out"], 3, cfg["init_dim"], cfg["depth"]), cfg["seed"])
+    x, y = O.synth_frame_batch(cfg["B"], cfg["n_in"], cfg["H"], cfg["W"], cfg["seed"] + 1)
+    mod = SimpleCNN(cfg["n_in"], cfg["n_out"], kernel_size=3, init_dim=cfg["init_dim"], depth=cfg["depth"], dropout_rate=0.0)
+    full = _buffers_state(sd, mod)
+    res = compare(mod, lambda a, s: O.simple_cnn(a, s, cfg["depth"]), full, x, y, dtype, z,
+                  oracle_keys=list(sd.keys()))
+    # running statistics after one training step (momentum 0.1, unbiased variance) vs torch's own BatchNorm
+    with torch.no_grad():
+        y0 = torch.nn.functional.conv2d(x.double(), sd["initial.0.weight"].double(), sd["initial.0.bias"].double(), padding=1)
+        rm = 0.1 * y0.mean(dim=(0, 2, 3))
+        rv = 0.9 + 0.1 * y0.var(dim=(0, 2, 3), unbiased=True)
+    res["running_mean"] = rel_l2(mod.initial[1].running_mean.cpu().numpy(), rm.numpy())
+    res["running_var"] = rel_l2(mod.initial[1].running_var.cpu().numpy(), rv.numpy())
+    res["nbt"] = int(mod.initial[1].num_batches_tracked)
+    return res
+
+
+def case_cnn_transformer(dtype, tag="cnn_transformer_small"):
+    from pcm_b200.src.cnn_transformer import CNNTransformer
+    cfg, z = load_golden(tag)
+    sd = O.synth_state_dict(O.cnn_transformer_spec(5, 2, cfg["embed_dim"], cfg["depth"], cfg["n_heads"], cfg["mlp_dim"]),
+                            cfg["seed"])
+    x, y = O.synth_frame_batch(cfg["B"], 5, 48, 72, cfg["seed"] + 1)
+    mod = CNNTransformer(5, 2, cfg["embed_dim"], cfg["depth"], cfg["n_heads"], cfg["mlp_dim"], dropout=0.0)
+    return compare(mod, lambda a, s: O.cnn_transformer(a, s, cfg["depth"], cfg["n_heads"]), sd, x, y, dtype, z)
+
+
+def case_full_size(kind, dtype=torch.bfloat16):
+    """Default-size models (BASELINE configs[0] / configs[1] geometry, reduced batch) on the tensor-core paths
+    against the fp64 oracle."""
+    if kind == "simplecnn":
+        from pcm_b200.src.models import SimpleCNN
+        sd = O.synth_state_dict(O.simplecnn_spec(5, 2, 3, 64, 4), 171)
+        x, y = O.synth_frame_batch(2, 5, 48, 72, 172)
+        mod = SimpleCNN(5, 2, dropout_rate=0.0)
+        return compare(mod, lambda a, s: O.simple_cnn(a, s, 4), _buffers_state(sd, mod), x, y, dtype,
+                       oracle_keys=list(sd.keys()))
+    from pcm_b200.src.cnn_transformer import CNNTransformer
+    sd = O.synth_state_dict(O.cnn_transformer_spec(5, 2, 128, 4, 4, 256), 181)
+    x, y = O.synth_frame_batch(4, 5, 48, 72, 182)
+    mod = CNNTransformer(dropout=0.0)
+    return compare(mod, lambda a, s: O.cnn_transformer(a, s, 4, 4), sd, x, y, dtype)
+
+
+def case_dropout_stats():
+    """Counter-based dropout: keep rate, 1/(1-p) scaling, backward uses the same mask, Dropout2d drops whole channels."""
+    from pcm_b200 import ops_nn
+    p = 0.2
+    x = torch.ones(8, 12, 18, 64, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    y = ops_nn.DropoutFn.apply(x, p, 12345)
+    y.sum().backward()
+    keep = float((y != 0).float().mean())
+    same = bool(((x.grad != 0) == (y != 0)).all())
+    scale = float(y.max())
+    x2 = torch.ones(16, 6, 9, 64, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    y2 = ops_nn.Dropout2dFn.apply(x2, p, 999)
+    per_ch = y2.float().reshape(16, 54, 64)
+    whole = bool(((per_ch == per_ch[:, :1, :]).all()))
+    keep2 = float((per_ch[:, 0, :] != 0).float().mean())
+    return {"keep": keep, "same_mask": same, "scale": scale, "whole_channels": whole, "keep2d": keep2}

@@ -161,3 +161,72 @@ def test_wgrad3x3_tc_slices(ops):
     F.conv2d(x7[..., :7].double().permute(0, 3, 1, 2), w7, padding=1).backward(dy.double().permute(0, 3, 1, 2))
     torch.cuda.synchronize()
     assert float((dw7.cpu() - w7.grad.float()).norm() / w7.grad.norm()) < 1e-5
+
+
+C11_SHAPES = [  # (N, H, W, Cin, Cout): ResidualBlock skip convs, transformer linears (tokens as a 1 x L image)
+    (2, 48, 72, 64, 128), (2, 24, 36, 128, 256), (3, 1, 216, 128, 192), (3, 1, 216, 128, 256), (3, 1, 216, 256, 128),
+    (5, 1, 216, 128, 128), (2, 7, 11, 32, 64), (1, 1, 1000, 64, 16), (2, 12, 18, 16, 32),
+]
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("shape", C11_SHAPES)
+def test_conv1x1_tc_matches_reference(ops, shape, relu):
+    from pcm_b200 import ops_nn
+    from pcm_b200._lib import lib
+    N, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(N * 31 + H + Ci + Co)
+    x = torch.randn(N, H, W, Ci, generator=g).bfloat16()
+    w = (torch.randn(Co, Ci, generator=g) / Ci ** 0.5).bfloat16()
+    bias = torch.randn(Co, generator=g)
+    want = x.double() @ w.double().t() + bias.double()
+    if relu:
+        want = want.clamp_min(0)
+    wk = w.cuda().reshape(1, Co, Ci).contiguous()
+    got = ops_nn.conv_same(x.cuda(), wk, N, H, W, Ci, Co, 1, bias=bias.cuda(), relu=relu)
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    assert lib().last_call == "pcm_conv1x1_tc"
+    err = float((got.double().cpu() - want).norm() / want.norm())
+    assert err < 4e-3, err                                      # bf16 destination rounding
+
+
+@pytest.mark.parametrize("shape", C11_SHAPES + [(2, 48, 72, 512, 128), (4, 1, 216, 128, 384)])
+def test_wgrad1x1_tc_matches_reference(ops, shape):
+    from pcm_b200 import ops_nn
+    from pcm_b200._lib import lib
+    N, H, W, Ci, Co = shape
+    if not (Co in (16, 32, 64) or Co % 128 == 0) or W + 2 > 256:
+        pytest.skip("not a tensor-core weight-gradient shape (falls back to the SIMT kernel)")
+    g = torch.Generator().manual_seed(N * 17 + W + Ci * 3 + Co)
+    x = torch.randn(N, H, W, Ci, generator=g).bfloat16()
+    dy = (torch.randn(N, H, W, Co, generator=g) / (N * H * W) ** 0.5).bfloat16()
+    want = dy.double().reshape(-1, Co).t() @ x.double().reshape(-1, Ci)
+    dw = torch.zeros(Co, Ci, 1, 1, device="cuda")
+    ops_nn.wgrad_same(dy.cuda(), x.cuda(), dw, N, H, W, Co, Ci, Ci, 1)
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    assert lib().last_call == "pcm_wgrad1x1_tc"
+    err = float((dw.cpu().reshape(Co, Ci).double() - want).norm() / want.norm())
+    assert err < 1e-5, err
+
+
+def test_conv3x3_tc_wide_channels(ops):
+    """SimpleCNN widths: Cout 512 (split over two launches), Cin 512 (eight K chunks; weight gradient in 256-wide slices)."""
+    from pcm_b200 import ops_nn
+    N, H, W, Ci, Co = 1, 12, 18, 512, 512
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, H, W, Ci, generator=g).bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Ci ** 0.5)).bfloat16()
+    bias = torch.randn(Co, generator=g)
+    want = _ref(x, w, bias)
+    wk = ops.conv_weight_fwd(w.float().cuda(), torch.bfloat16)
+    got = ops_nn.conv_same(x.cuda(), wk, N, H, W, Ci, Co, 3, bias=bias.cuda())
+    assert float((got.float().cpu() - want).norm() / want.norm()) < 4e-3
+    dy = (torch.randn(N, H, W, Co, generator=g) / (H * W) ** 0.5).bfloat16()
+    wz = torch.zeros(Co, Ci, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double().permute(0, 3, 1, 2), wz, padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    dw = torch.zeros(Co, Ci, 3, 3, device="cuda")
+    ops_nn.wgrad_same(dy.cuda(), x.cuda(), dw, N, H, W, Co, Ci, Ci, 3)
+    torch.cuda.synchronize()
+    assert float((dw.cpu() - wz.grad.float()).norm() / wz.grad.norm()) < 1e-5

@@ -64,6 +64,37 @@ def test_attunet(G, tag, dtype):
     _check(G.case_attunet(tag, dtype), dtype)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_simplecnn_small(G, dtype):
+    """SimpleCNN (src/models.py:76-123), training-mode BatchNorm, against the oracle and the reference-made golden."""
+    r = G.case_simplecnn(dtype)
+    _check(r, dtype)
+    assert r["running_mean"] < (1e-4 if dtype == torch.float32 else 2e-2), r["running_mean"]
+    assert r["running_var"] < (1e-4 if dtype == torch.float32 else 2e-2), r["running_var"]
+    assert r["nbt"] == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cnn_transformer_small(G, dtype):
+    """CNNTransformer (src/cnn_transformer.py), dropout 0, against the oracle and the reference-made golden."""
+    _check(G.case_cnn_transformer(dtype), dtype)
+
+
+@pytest.mark.parametrize("kind", ["simplecnn", "cnn_transformer"])
+def test_full_size_tensor_core_paths(G, kind):
+    """Default widths (init_dim 64 / embed_dim 128, head dim 32): 3x3, 1x1 and linear layers on tcgen05."""
+    from pcm_b200._lib import lib
+    r = G.case_full_size(kind)
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    _check(r, torch.bfloat16)
+
+
+def test_dropout_masks(G):
+    r = G.case_dropout_stats()
+    assert abs(r["keep"] - 0.8) < 0.01 and r["same_mask"] and abs(r["scale"] - 1.25) < 1e-2, r
+    assert r["whole_channels"] and abs(r["keep2d"] - 0.8) < 0.06, r
+
+
 def test_metric_appendix_g(G):
     r = G.case_metric_appendix_g()            # fixture of _test_kaggle_metric.py:33-78, SURVEY Appendix G
     assert r["max_rel"] < 1e-5 and r["score_rel"] < 1e-5, r
