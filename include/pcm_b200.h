@@ -58,6 +58,11 @@ PCM_API int pcm_season_embed_stage(const float* x5, const int* month, void* y, i
 PCM_API int pcm_pack_weight(const float* w, long long so, long long si, long long st, int O, int I, int taps, int Op,
                     int Ip, void* out, int dtype, pcm_stream_t s);
 
+/* every re-pack of a training step in ONE launch.  jobs: device array of njobs records of 8 x int64:
+ * {w ptr, out ptr, so, si, st, O | I<<32, taps | Op<<32, Ip | dtype<<32} (same meaning as pcm_pack_weight);
+ * max_elems = the largest taps*Op*Ip among them (sizes the grid). */
+PCM_API int pcm_pack_weights_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s);
+
 /* ---- convolution family (nn.Conv2d / nn.ConvTranspose2d call sites: src/convlstm.py:9,13;
  * src/unet.py:36,38,63; src/cnn_transformer.py:10,12,36,38; src/models.py:47,50,57,90,108).
  * "gather" form: dst(n,hd,wd,dc) = sum_taps sum_sc src(n,hs,ws,sc) * wk[tap][dc][sc] (+bias)(relu)
@@ -149,6 +154,31 @@ PCM_API int pcm_gn_silu_bwd_reduce(const void* da, const float* dpool, const voi
 PCM_API int pcm_gn_silu_bwd_apply(const void* da, const float* dpool, const void* x, const float* stats,
                           const float* gamma, const float* beta, const float* gsum, void* dx, int N, int P, int C,
                           int G, float eps, int dtype, pcm_stream_t s);
+
+/* ---- per-image fused ConvBlock tails (csrc/convblock_fused.cu): one CTA per image, the image resident in shared
+ * memory.  GroupNorm has 8 groups (nn.GroupNorm(8, c), src/unet.py:37,39); stats[n][8][2] = (sum, sum of squares).
+ * pcm_convblock_fused_supported: 1 when an H x W x C image of `dtype` (plus the gate maps) fits one SM. */
+PCM_API int pcm_convblock_fused_supported(int H, int W, int C, int Cr, int dtype);
+/* tail 1: y = silu(GroupNorm(x))  [statistics + normalise in one pass over shared memory] */
+PCM_API int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const float* beta, float* stats, void* y, int N,
+                                int H, int W, int C, float eps, int dtype, pcm_stream_t s);
+/* tail 2: out = a*se*gate, a = silu(GroupNorm(x)), se = sigmoid(W2 relu(W1 mean_p a)),
+ * gate = sigmoid(conv7x7([mean_c a*se, max_c a*se])).  Saves stats, pool[n][C] (= sum_p a), se[n][C], hid[n][Cr]. */
+PCM_API int pcm_convblock_tail_fwd(const void* x, const float* gamma, const float* beta, const float* w1,
+                                   const float* w2, const float* wsp, float* stats, float* pool, float* se,
+                                   float* hid, void* out, int N, int H, int W, int C, int Cr, float eps, int dtype,
+                                   pcm_stream_t s);
+/* backward of tail 1: da -> dx; dgamma, dbeta accumulate */
+PCM_API int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* stats, const float* gamma,
+                                const float* beta, void* dx, float* dgamma, float* dbeta, int N, int H, int W, int C,
+                                float eps, int dtype, pcm_stream_t s);
+/* backward of tail 2 (recomputes a, the channel maps and the gate from x): dout -> dx; dgamma, dbeta, dw1, dw2,
+ * dwsp accumulate */
+PCM_API int pcm_convblock_tail_bwd(const void* dout, const void* x, const float* stats, const float* gamma,
+                                   const float* beta, const float* w1, const float* w2, const float* wsp,
+                                   const float* pool, const float* se, const float* hid, void* dx, float* dgamma,
+                                   float* dbeta, float* dw1, float* dw2, float* dwsp, int N, int H, int W, int C,
+                                   int Cr, float eps, int dtype, pcm_stream_t s);
 
 /* ---- BatchNorm2d, training mode (src/models.py:48,51,57,91,109; eps 1e-5, momentum 0.1) on NHWC rows
  * (R = N*H*W rows of C channels; C = 8 * a divisor of 256).  sums[c] = (sum x, sum x^2), zeroed by the caller. */

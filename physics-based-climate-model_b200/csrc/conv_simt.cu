@@ -23,6 +23,30 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, long long so, lo
   }
 }
 
+// All weight re-packs of a training step in ONE launch: blockIdx.y = job, the x-grid strides over that job's
+// elements.  Job record (8 x int64, device memory): w ptr, out ptr, so, si, st, (O | I << 32), (taps | Op << 32),
+// (Ip | dtype << 32).
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs) {
+  const long long* j = jobs + (long long)blockIdx.y * 8;
+  const float* w = reinterpret_cast<const float*>(j[0]);
+  void* out = reinterpret_cast<void*>(j[1]);
+  const long long so = j[2], si = j[3], st = j[4];
+  const int O = (int)(j[5] & 0xffffffffll), I = (int)(j[5] >> 32);
+  const int taps = (int)(j[6] & 0xffffffffll), Op = (int)(j[6] >> 32);
+  const int Ip = (int)(j[7] & 0xffffffffll), dtype = (int)(j[7] >> 32);
+  const long long total = (long long)taps * Op * Ip;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % Ip);
+    const int o = (int)((idx / Ip) % Op);
+    const int t = (int)(idx / ((long long)Ip * Op));
+    float v = 0.f;
+    if (o < O && i < I) v = __ldg(w + o * so + i * si + t * st);
+    if (dtype == PCM_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(out)[idx] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // gather convolution: one thread = one destination pixel x 8 destination channels
 // ------------------------------------------------------------------------------------------------
@@ -234,6 +258,15 @@ extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long 
   PCM_DISPATCH_DTYPE(dtype, T, (pack_weight_kernel<T><<<blocks, 256, 0, (cudaStream_t)s>>>(
                                    w, so, si, st, O, I, taps, Op, Ip, (T*)out)));
   return check_launch("pack_weight");
+}
+
+extern "C" int pcm_pack_weights_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
+  PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "pack_weights_batched: bad arguments");
+  if (njobs == 0 || max_elems == 0) return PCM_OK;
+  long long bx = (max_elems + 1023) / 1024;
+  if (bx > 64) bx = 64;
+  pack_weights_batched_kernel<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, (cudaStream_t)s>>>(jobs);
+  return check_launch("pack_weights_batched");
 }
 
 extern "C" int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int Hs, int Ws, int Sc, void* dst,

@@ -11,6 +11,8 @@
 // the fp32 partials are reduced with atomics straight into the parameter-gradient tensor.
 //
 // Roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace pcm {
@@ -24,6 +26,7 @@ struct WgradTcParams {
   int Hb, Nb, tiles_h, num_ktiles, Kpad;
   int tpg, ngroups;             // taps per group, groups
   int ksz, ntaps;               // kernel size (1 or 3), ksz*ksz
+  int wide;                     // 1: one MMA covers the ksz taps of a kernel row (N = ksz*Ci, LBO = one pixel row)
   int stages;
   long long sa, sb, st;
   uint32_t a_chunk_bytes, b_chunk_bytes, a_stage_bytes, b_stage_bytes, tx_bytes, tmem_cols, lbo_a, lbo_b;
@@ -90,14 +93,34 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, p.Ci, 1, 1);          // A and B MN-major
       const uint32_t rba = p.Cca * 2, rbb = p.Ccb * 2;
+      // A (dy) and B (x) are MN-major.  `wide`: the ksz taps of one kernel row are ksz consecutive pixel shifts of
+      // the x tile, i.e. ksz N-chunks one pixel row (LBO) apart -> ONE MMA with N = ksz*Ci per kernel row.  The A
+      // operand (128 rows, re-read from shared memory by every MMA) is then read ksz times less often — for the
+      // thin layers the kernel was bound by exactly that read (ncu: 68 cycles per N=16 MMA, tensor pipe 12 %).
+      const int wide = p.wide;
+      const uint32_t idesc = make_idesc_bf16(128, wide ? p.ksz * p.Ci : p.Ci, 1, 1);
       const uint64_t adesc0 = make_smem_desc(smem_u32(sA), p.lbo_a, 8 * rba, layout_type_for_row_bytes(rba));
-      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), p.lbo_b, 8 * rbb, layout_type_for_row_bytes(rbb));
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), wide ? rbb : p.lbo_b, 8 * rbb, layout_type_for_row_bytes(rbb));
       const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
       const uint32_t a_k = rba, b_k = rbb;                                 // 16 pixel rows = 16*rb bytes -> (>>4) = rb
       const uint32_t b_tap_row = (uint32_t)p.Wp * rbb >> 4, b_px = rbb >> 4;
       const int ksteps = p.Kpad / 16, nstages = p.stages, ci = p.Ci;
+      // per-issue offsets of this group: B start-address offset and TMEM column offset (at most 9)
+      uint32_t b_off[9], d_off[9];
+      int nissue = 0;
+      if (wide) {
+        for (int tl = 0; tl < ntap; tl += p.ksz) {
+          b_off[nissue] = (uint32_t)((tap0 + tl) / p.ksz) * b_tap_row;
+          d_off[nissue++] = (uint32_t)(tl * ci);
+        }
+      } else {
+        for (int tl = 0; tl < ntap; ++tl) {
+          const int tap = tap0 + tl;
+          b_off[nissue] = (uint32_t)(tap / p.ksz) * b_tap_row + (uint32_t)(tap % p.ksz) * b_px;
+          d_off[nissue++] = (uint32_t)(tl * ci);
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
@@ -107,10 +130,9 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         const uint64_t ad = adesc0 + (uint64_t)(stage * a_step);
         const uint64_t bd = bdesc0 + (uint64_t)(stage * b_step);
-        for (int tl = 0; tl < ntap; ++tl) {
-          const int tap = tap0 + tl;
-          const uint64_t bt = bd + (uint64_t)((tap / p.ksz) * b_tap_row + (tap % p.ksz) * b_px);
-          const uint32_t d = tmem_base + tl * ci;
+        for (int i = 0; i < nissue; ++i) {
+          const uint64_t bt = bd + (uint64_t)b_off[i];
+          const uint32_t d = tmem_base + d_off[i];
           for (int k = 0; k < ksteps; ++k)
             umma_bf16(d, ad + (uint64_t)(k * a_k), bt + (uint64_t)(k * b_k), idesc, (t | k) != 0);
         }
@@ -226,10 +248,23 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   // M blocks beyond the real channels alias the tile shifted by 8 rows (results unused, reads stay in bounds)
   p.lbo_a = (p.na_chunks * p.Cca >= 128) ? p.a_chunk_bytes : 8 * rba;
   p.lbo_b = p.b_chunk_bytes;
-  p.tpg = 512 / Ci;
-  if (p.tpg > ntaps) p.tpg = ntaps;
-  p.ngroups = (ntaps + p.tpg - 1) / p.tpg;
-  p.tpg = (ntaps + p.ngroups - 1) / p.ngroups;                  // balance the groups
+  static int wide_env = -1;
+  if (wide_env < 0) {
+    const char* e = getenv("PCM_WGRAD_WIDE");     // PCM_WGRAD_WIDE=0: one MMA per tap (A/B experiments)
+    wide_env = e ? atoi(e) : 1;
+  }
+  p.wide = (wide_env && ksz == 3 && p.nb_chunks == 1 && 3 * Ci <= 256) ? 1 : 0;
+  if (p.wide) {
+    int rows = 512 / (3 * Ci);                                  // whole kernel rows per group (TMEM: 512 columns)
+    if (rows > 3) rows = 3;
+    p.tpg = 3 * rows;
+    p.ngroups = (3 + rows - 1) / rows;
+  } else {
+    p.tpg = 512 / Ci;
+    if (p.tpg > ntaps) p.tpg = ntaps;
+    p.ngroups = (ntaps + p.tpg - 1) / p.tpg;
+    p.tpg = (ntaps + p.ngroups - 1) / p.ngroups;                // balance the groups
+  }
   uint32_t cols = 32;
   while (cols < (uint32_t)(p.tpg * Ci)) cols <<= 1;
   p.tmem_cols = cols;

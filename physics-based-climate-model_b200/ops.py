@@ -62,13 +62,76 @@ def _grad_buf(p: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # ------------------------------------------------------------------------------------------------
+class PackPlan:
+    """Persistent packed-weight buffers for a training loop: every (parameter, layout) pair the step needs is
+    registered the first time it is requested; afterwards `repack()` refreshes ALL of them from the fp32 master
+    parameters in ONE launch (pcm_pack_weights_batched) at the start of each step, and `pack_weight` just hands
+    out the resident buffer.  Without an active plan (plain module use) weights are packed on demand."""
+
+    def __init__(self):
+        self.entries = {}          # key -> (packed tensor, job record)
+        self.table = None
+        self.dirty = False
+        self.max_elems = 0
+
+    def lookup(self, key):
+        e = self.entries.get(key)
+        return None if e is None else e[0]
+
+    def register(self, key, out, job):
+        self.entries[key] = (out, job)
+        self.max_elems = max(self.max_elems, out.numel())
+        self.dirty = True
+
+    def repack(self):
+        if not self.entries:
+            return
+        if self.dirty:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PackPlan: a new packed weight was requested after warm-up; run more eager "
+                                   "warm-up steps before capturing the graph")
+            dev = next(iter(self.entries.values()))[0].device
+            self.table = torch.tensor([j for _, j in self.entries.values()], dtype=torch.int64).to(dev)
+            self.dirty = False
+        _call("pcm_pack_weights_batched", self.table.data_ptr(), len(self.entries), self.max_elems, _s())
+
+
+_PLAN: Optional[PackPlan] = None
+
+
+class use_pack_plan:
+    """Context manager activating a PackPlan for the ops issued inside it (trainer step body)."""
+
+    def __init__(self, plan: Optional[PackPlan]):
+        self.plan = plan
+
+    def __enter__(self):
+        global _PLAN
+        self.prev, _PLAN = _PLAN, self.plan
+        return self.plan
+
+    def __exit__(self, *exc):
+        global _PLAN
+        _PLAN = self.prev
+        return False
+
+
 def pack_weight(w: torch.Tensor, so: int, si: int, st: int, O: int, I: int, taps: int, dtype, offset: int = 0,
                 Op: Optional[int] = None, Ip: Optional[int] = None):
     """out[t][o][i] = w.flatten()[offset + o*so + i*si + t*st], zero padded to (taps, Op, Ip)."""
     Op = pad8(O) if Op is None else Op
     Ip = pad8(I) if Ip is None else Ip
+    src = w.data_ptr() + 4 * offset
+    if _PLAN is not None:
+        key = (src, so, si, st, O, I, taps, Op, Ip, dtype)
+        hit = _PLAN.lookup(key)
+        if hit is not None:
+            return hit
     out = torch.empty((taps, Op, Ip), device=w.device, dtype=dtype)
-    _call("pcm_pack_weight", w.data_ptr() + 4 * offset, so, si, st, O, I, taps, Op, Ip, out.data_ptr(), _DT[dtype], _s())
+    _call("pcm_pack_weight", src, so, si, st, O, I, taps, Op, Ip, out.data_ptr(), _DT[dtype], _s())
+    if _PLAN is not None:
+        _PLAN.register(key, out, [src, out.data_ptr(), so, si, st, O | (I << 32), taps | (Op << 32),
+                                  Ip | (_DT[dtype] << 32)])
     return out
 
 
@@ -238,6 +301,15 @@ def season_embed_stage(x5: torch.Tensor, month: torch.Tensor, dtype, T: int = 1)
 # ------------------------------------------------------------------------------------------------
 # ConvBlock: [conv3x3 -> GN(8) -> SiLU] x2 -> SE -> SpatialGate   (src/unet.py:32-49)
 # ------------------------------------------------------------------------------------------------
+def convblock_fused_ok(H: int, W: int, C: int, Cr: int, dtype) -> bool:
+    """True when one H x W x C image (+ gate maps) fits an SM's shared memory: the per-image fused tails
+    (csrc/convblock_fused.cu) then replace the grid-wide multi-kernel tails.  PCM_FUSED_TAILS=0 disables them."""
+    import os
+    if os.environ.get("PCM_FUSED_TAILS", "1") == "0":
+        return False
+    return bool(lib()._fn["pcm_convblock_fused_supported"](H, W, C, Cr, _DT[dtype]))
+
+
 class ConvBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp):
@@ -250,18 +322,38 @@ class ConvBlockFn(torch.autograd.Function):
         P, G, dt, dev = H * W, GN_GROUPS, x.dtype, x.device
         d = _DT[dt]
         st = _s()
+        fused = convblock_fused_ok(H, W, Co, Cr, dt)
+        ctx.fused = fused
+        ctx.dims = (N, H, W, Cip, Ci, Co, Cr)
+        wk1 = conv_weight_fwd(w1, dt, Ip=Cip)
+        wk2 = conv_weight_fwd(w2, dt)
+        if fused:
+            # per-image tails: conv -> [GN+SiLU] -> conv -> [GN+SiLU+SE+gate]; 4 launches, every tensor read once
+            small = torch.empty(N * G * 2 * 2 + N * Co, device=dev, dtype=torch.float32)     # written fully
+            stats1, stats2, pool = small[: N * G * 2], small[N * G * 2: N * G * 4], small[N * G * 4:]
+            se = torch.empty(N * Co + N * Cr, device=dev, dtype=torch.float32)
+            hid = se[N * Co:]
+            y1 = conv_s1(x, wk1, N, H, W, Cip, Co)
+            a1 = torch.empty_like(y1)
+            _call("pcm_gn_silu_img_fwd", y1.data_ptr(), g1.data_ptr(), b1.data_ptr(), stats1.data_ptr(), a1.data_ptr(),
+                  N, H, W, Co, GN_EPS, d, st)
+            y2 = conv_s1(a1, wk2, N, H, W, Co, Co)
+            out = torch.empty_like(y2)
+            _call("pcm_convblock_tail_fwd", y2.data_ptr(), g2.data_ptr(), b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(),
+                  wsp.data_ptr(), stats2.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), out.data_ptr(),
+                  N, H, W, Co, Cr, GN_EPS, d, st)
+            ctx.save_for_backward(x, y1, a1, y2, small, se, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp)
+            return out
         # one zeroed scratch for every small accumulator of the forward
         small = torch.zeros(N * G * 2 * 2 + N * Co, device=dev, dtype=torch.float32)
         stats1 = small[: N * G * 2]
         stats2 = small[N * G * 2: N * G * 4]
         pool = small[N * G * 4:]
-        wk1 = conv_weight_fwd(w1, dt, Ip=Cip)
         y1 = conv_s1(x, wk1, N, H, W, Cip, Co)
         _call("pcm_gn_stats", y1.data_ptr(), stats1.data_ptr(), N, P, Co, G, d, st)
         a1 = torch.empty_like(y1)
         _call("pcm_gn_silu_fwd", y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(), b1.data_ptr(), a1.data_ptr(), 0,
               N, P, Co, G, GN_EPS, d, st)
-        wk2 = conv_weight_fwd(w2, dt)
         y2 = conv_s1(a1, wk2, N, H, W, Co, Co)
         _call("pcm_gn_stats", y2.data_ptr(), stats2.data_ptr(), N, P, Co, G, d, st)
         a2 = torch.empty_like(y2)
@@ -277,11 +369,12 @@ class ConvBlockFn(torch.autograd.Function):
         _call("pcm_spatial_gate_fwd", a2.data_ptr(), se.data_ptr(), cmap.data_ptr(), wsp.data_ptr(), gate.data_ptr(),
               out.data_ptr(), N, H, W, Co, d, st)
         ctx.save_for_backward(x, y1, a1, y2, a2, small, se, maps, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp)
-        ctx.dims = (N, H, W, Cip, Ci, Co, Cr)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.fused:
+            return ConvBlockFn._backward_fused(ctx, dout)
         x, y1, a1, y2, a2, small, se, maps, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp = ctx.saved_tensors
         N, H, W, Cip, Ci, Co, Cr = ctx.dims
         P, G, dt, dev = H * W, GN_GROUPS, x.dtype, x.device
@@ -324,6 +417,36 @@ class ConvBlockFn(torch.autograd.Function):
         dy1 = dy2                                                                          # reuse dy2 storage
         _call("pcm_gn_silu_bwd_apply", da1.data_ptr(), 0, y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(),
               b1.data_ptr(), gsum1.data_ptr(), dy1.data_ptr(), N, P, Co, G, GN_EPS, d, st)
+        conv3x3_wgrad(dy1, x, gw1, N, H, W, Co, Cip, Ci)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wk1t = conv_weight_dgrad(w1, dt, Op=Cip)
+            dx = conv_s1(dy1, wk1t, N, H, W, Co, Cip)
+        return dx, rw1, rg1, rb1, rw2, rg2, rb2, rs1, rs2, rsp
+
+    @staticmethod
+    def _backward_fused(ctx, dout):
+        x, y1, a1, y2, small, se, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp = ctx.saved_tensors
+        N, H, W, Cip, Ci, Co, Cr = ctx.dims
+        G, dt = GN_GROUPS, x.dtype
+        d, st = _DT[dt], _s()
+        dout = dout.contiguous()
+        stats1, stats2, pool = small[: N * G * 2], small[N * G * 2: N * G * 4], small[N * G * 4:]
+        hid = se[N * Co:]
+        gw1, rw1 = _grad_buf(w1); gg1, rg1 = _grad_buf(g1); gb1, rb1 = _grad_buf(b1)
+        gw2, rw2 = _grad_buf(w2); gg2, rg2 = _grad_buf(g2); gb2, rb2 = _grad_buf(b2)
+        gs1, rs1 = _grad_buf(sw1); gs2, rs2 = _grad_buf(sw2); gsp, rsp = _grad_buf(wsp)
+        dy2 = torch.empty_like(y2)
+        _call("pcm_convblock_tail_bwd", dout.data_ptr(), y2.data_ptr(), stats2.data_ptr(), g2.data_ptr(), b2.data_ptr(),
+              sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(),
+              dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(), gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(),
+              N, H, W, Co, Cr, GN_EPS, d, st)
+        conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
+        wk2t = conv_weight_dgrad(w2, dt)
+        da1 = conv_s1(dy2, wk2t, N, H, W, Co, Co)
+        dy1 = dy2                                                                          # reuse dy2 storage
+        _call("pcm_gn_silu_img_bwd", da1.data_ptr(), y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(), b1.data_ptr(),
+              dy1.data_ptr(), gg1.data_ptr(), gb1.data_ptr(), N, H, W, Co, GN_EPS, d, st)
         conv3x3_wgrad(dy1, x, gw1, N, H, W, Co, Cip, Ci)
         dx = None
         if ctx.needs_input_grad[0]:

@@ -35,15 +35,18 @@ class TrainStep:
         self.y = torch.zeros(y_shape, device=self.device, dtype=torch.float32)
         self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
         self.use_graph = use_graph
+        self.plan = ops.PackPlan()          # resident packed weights, refreshed by one launch per step
         self.graph = None
         self.launches_per_step = 0
 
     # -- one eager step on the static buffers ---------------------------------------------------
     def _step_impl(self):
         self.opt.zero_grad()
-        out = self.model(self.x)
-        loss = ops.mse_loss(out, self.y)
-        loss.backward()
+        with ops.use_pack_plan(self.plan):
+            self.plan.repack()
+            out = self.model(self.x)
+            loss = ops.mse_loss(out, self.y)
+            loss.backward()
         scale = allreduce_flat_grads(self.opt.flat_grad, self.opt.n_reduced, self.pg)
         self.opt.step(grad_scale=scale)
         self.loss.copy_(loss.detach())
