@@ -63,6 +63,12 @@ PCM_API int pcm_pack_weight(const float* w, long long so, long long si, long lon
  * max_elems = the largest taps*Op*Ip among them (sizes the grid). */
 PCM_API int pcm_pack_weights_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s);
 
+/* packed weight gradients -> parameter layout, all layers in ONE launch (and the packed buffers are re-zeroed):
+ * dst[co*sa + ci*sb + tap*st] += packed[(tap*Co + co)*Cpad + ci].  jobs: njobs records of 8 x int64:
+ * {packed ptr, dst ptr, sa, sb, st, Co | Ci_real<<32, Cpad | taps<<32, 0}; max_elems = largest taps*Co*Cpad.
+ * pcm_wgrad3x3_tc reduces into such a buffer with 16-byte vector atomics when called with sb == 1. */
+PCM_API int pcm_unpack_grads_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s);
+
 /* ---- convolution family (nn.Conv2d / nn.ConvTranspose2d call sites: src/convlstm.py:9,13;
  * src/unet.py:36,38,63; src/cnn_transformer.py:10,12,36,38; src/models.py:47,50,57,90,108).
  * "gather" form: dst(n,hd,wd,dc) = sum_taps sum_sc src(n,hs,ws,sc) * wk[tap][dc][sc] (+bias)(relu)

@@ -47,6 +47,29 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
   }
 }
 
+// Packed weight gradients [tap][Co][Cpad] (what the tensor-core weight-gradient kernel reduces into with vector
+// atomics) -> the parameter's own layout: dst[co*sa + ci*sb + tap*st] += packed[(tap*Co + co)*Cpad + ci]; the packed
+// buffer is zeroed on the way (ready for the next step).  blockIdx.y = job.  Job record (8 x int64): packed ptr,
+// dst ptr, sa, sb, st, (Co | Ci_real << 32), (Cpad | taps << 32), unused.
+__global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long long* __restrict__ jobs) {
+  const long long* j = jobs + (long long)blockIdx.y * 8;
+  float* packed = reinterpret_cast<float*>(j[0]);
+  float* dst = reinterpret_cast<float*>(j[1]);
+  const long long sa = j[2], sb = j[3], st = j[4];
+  const int Co = (int)(j[5] & 0xffffffffll), Ci = (int)(j[5] >> 32);
+  const int Cpad = (int)(j[6] & 0xffffffffll), taps = (int)(j[6] >> 32);
+  const long long total = (long long)taps * Co * Cpad;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cpad);
+    const int co = (int)((idx / Cpad) % Co);
+    const int t = (int)(idx / ((long long)Cpad * Co));
+    const float v = packed[idx];
+    packed[idx] = 0.f;
+    if (ci < Ci && v != 0.f) dst[co * sa + ci * sb + t * st] += v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // gather convolution: one thread = one destination pixel x 8 destination channels
 // ------------------------------------------------------------------------------------------------
@@ -267,6 +290,15 @@ extern "C" int pcm_pack_weights_batched(const long long* jobs, int njobs, long l
   if (bx > 64) bx = 64;
   pack_weights_batched_kernel<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, (cudaStream_t)s>>>(jobs);
   return check_launch("pack_weights_batched");
+}
+
+extern "C" int pcm_unpack_grads_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
+  PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "unpack_grads_batched: bad arguments");
+  if (njobs == 0 || max_elems == 0) return PCM_OK;
+  long long bx = (max_elems + 1023) / 1024;
+  if (bx > 64) bx = 64;
+  unpack_grads_batched_kernel<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, (cudaStream_t)s>>>(jobs);
+  return check_launch("unpack_grads_batched");
 }
 
 extern "C" int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int Hs, int Ws, int Sc, void* dst,

@@ -158,9 +158,20 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int tap = tap0 + c0 / p.Ci;
           const int ci0 = c0 % p.Ci;
           float* base = dw + (long long)co * p.sa + (long long)tap * p.st;
+          if (p.sb == 1) {
+            // packed gradient layout [tap][co][ci] (ci contiguous, padded): 16-byte vector reductions — one L2
+            // sector operation per 4 values instead of one per value (the scattered scalar atomics of the
+            // reference layout were the whole cost of the wide layers: 49 splits x 147k values for enc4)
+            float* q = base + ci0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (ci0 + j < p.Ci_real) atomicAdd(base + (long long)(ci0 + j) * p.sb, v[j]);
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + j), "f"(v[j]), "f"(v[j + 1]),
+                           "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ci0 + j < p.Ci_real) atomicAdd(base + (long long)(ci0 + j) * p.sb, v[j]);
+          }
         }
       }
     }
@@ -189,6 +200,8 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
               "wgrad3x3_tc: Ci must be 16, 32, 64, 128, 192 or 256 (got %d)", Ci);
   PCM_REQUIRE(W + 2 * pad <= 256 && H + 2 * pad <= 256, "wgrad3x3_tc: grid too large for one TMA box (W=%d H=%d)", W, H);
   PCM_REQUIRE(dy_ps % 8 == 0 && x_ps % 8 == 0 && dy_ns % 8 == 0 && x_ns % 8 == 0, "wgrad3x3_tc: strides must be multiples of 8");
+  PCM_REQUIRE(sb != 1 || ((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && sa % 4 == 0 && st % 4 == 0),
+              "wgrad3x3_tc: the packed layout (sb == 1) needs a 16-byte aligned dw and sa, st multiples of 4");
   if (N == 0) return PCM_OK;
   if (g_wg_sms == 0) {
     int dev = 0;

@@ -73,6 +73,13 @@ class PackPlan:
         self.table = None
         self.dirty = False
         self.max_elems = 0
+        # packed weight-gradient buffers ([tap][Co][Cpad] fp32, reduced into with vector atomics by the tensor-core
+        # weight-gradient kernel) and the ONE launch that folds them into the parameter-layout gradients
+        self.grad_range = None     # (first byte, one-past-last byte) of the optimizer's flat gradient buffer
+        self.gentries = {}         # (dst ptr, Co, Ci_tot, taps) -> (packed tensor, job record)
+        self.gtable = None
+        self.gdirty = False
+        self.gmax = 0
 
     def lookup(self, key):
         e = self.entries.get(key)
@@ -94,6 +101,37 @@ class PackPlan:
             self.table = torch.tensor([j for _, j in self.entries.values()], dtype=torch.int64).to(dev)
             self.dirty = False
         _call("pcm_pack_weights_batched", self.table.data_ptr(), len(self.entries), self.max_elems, _s())
+
+
+    def grad_pack(self, dw: torch.Tensor, Co: int, Ci_tot: int, taps: int):
+        """Packed accumulation buffer for the parameter gradient `dw` ((Co, Ci_tot, k, k) fp32 inside the flat
+        gradient buffer), or None when dw is not a persistent main_grad view."""
+        if self.grad_range is None or not (self.grad_range[0] <= dw.data_ptr() < self.grad_range[1]):
+            return None
+        key = (dw.data_ptr(), Co, Ci_tot, taps)
+        e = self.gentries.get(key)
+        if e is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PackPlan: a new packed gradient was requested after warm-up")
+            Cpad = (Ci_tot + 15) // 16 * 16
+            packed = torch.zeros((taps, Co, Cpad), device=dw.device, dtype=torch.float32)
+            job = [packed.data_ptr(), dw.data_ptr(), Ci_tot * taps, taps, 1, Co | (Ci_tot << 32), Cpad | (taps << 32), 0]
+            e = (packed, job)
+            self.gentries[key] = e
+            self.gmax = max(self.gmax, packed.numel())
+            self.gdirty = True
+        return e[0]
+
+    def unpack_grads(self):
+        if not self.gentries:
+            return
+        if self.gdirty:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PackPlan: packed-gradient table changed during graph capture")
+            dev = next(iter(self.gentries.values()))[0].device
+            self.gtable = torch.tensor([j for _, j in self.gentries.values()], dtype=torch.int64).to(dev)
+            self.gdirty = False
+        _call("pcm_unpack_grads_batched", self.gtable.data_ptr(), len(self.gentries), self.gmax, _s())
 
 
 _PLAN: Optional[PackPlan] = None
@@ -221,6 +259,15 @@ def conv3x3_wgrad(dy, x, dw, N, H, W, Co, Ci, Ci_real, Ci_tot=None, dy_ns=None, 
     dy_ns = H * W * dy_ps if dy_ns is None else dy_ns
     x_ns = H * W * x_ps if x_ns is None else x_ns
     if wgrad_tc_supported(dy.dtype, Co, Ci, H, W):
+        packed = _PLAN.grad_pack(dw, Co, Ci_tot, 9) if _PLAN is not None else None
+        if packed is not None:
+            # reduce into the packed [tap][Co][Cpad] buffer (16-byte vector atomics); PackPlan.unpack_grads folds
+            # every layer's buffer into the parameter-layout gradient in one launch after backward
+            Cpad = packed.shape[-1]
+            _call("pcm_wgrad3x3_tc", dy.data_ptr() + dy_off * dy.element_size(), dy_ns, dy_ps, Co, Co,
+                  x.data_ptr() + x_off * x.element_size(), x_ns, x_ps, Ci, Ci_real, packed.data_ptr() + 4 * (dw_off // 9),
+                  Cpad, 1, Co * Cpad, N, H, W, _s())
+            return
         _call("pcm_wgrad3x3_tc", dy.data_ptr() + dy_off * dy.element_size(), dy_ns, dy_ps, Co, Co,
               x.data_ptr() + x_off * x.element_size(), x_ns, x_ps, Ci, Ci_real, dw.data_ptr() + 4 * dw_off,
               Ci_tot * 9, 9, 1, N, H, W, _s())

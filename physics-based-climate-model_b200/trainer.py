@@ -36,6 +36,8 @@ class TrainStep:
         self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
         self.use_graph = use_graph
         self.plan = ops.PackPlan()          # resident packed weights, refreshed by one launch per step
+        fg = self.opt.flat_grad
+        self.plan.grad_range = (fg.data_ptr(), fg.data_ptr() + fg.numel() * 4)
         self.graph = None
         self.launches_per_step = 0
 
@@ -47,6 +49,7 @@ class TrainStep:
             out = self.model(self.x)
             loss = ops.mse_loss(out, self.y)
             loss.backward()
+            self.plan.unpack_grads()
         scale = allreduce_flat_grads(self.opt.flat_grad, self.opt.n_reduced, self.pg)
         self.opt.step(grad_scale=scale)
         self.loss.copy_(loss.detach())

@@ -31,8 +31,10 @@ def _check(res, dtype):
     errs = []
     for k, e in res["grads"].items():
         gn = res["gnorm"].get(k, 1.0)
-        if gn <= 1e-7:                      # dead unit in the oracle: ours must be ~0 too
-            assert e < 1e-5, (k, e)
+        if gn <= 1e-7:
+            # exactly-zero gradient in the oracle (dead unit, or a conv bias cancelled by the BatchNorm that follows):
+            # ours must be ~0 too — in bf16 up to the rounding noise of summing bf16-stored values
+            assert e < (1e-5 if dtype == torch.float32 else 1e-3), (k, e)
             continue
         errs.append(e)
         if dtype != torch.float32 and ".se.fc." in k or k.startswith("fc."):

@@ -121,11 +121,39 @@ def bench_pointwise(args):
             print(f"{name:22s} N={N} {H}x{W} C={C:3d}: {ms * 1e3:8.1f} us   {byts / ms / 1e6:8.1f} GB/s (algorithmic, {ntens} tensor passes)")
 
 
+def bench_tails(args):
+    """Per-image fused ConvBlock tails (csrc/convblock_fused.cu) at the four encoder levels and the decoder's top level."""
+    from pcm_b200.ops import _call, _s
+    for (N, H, W, C) in [(384, 48, 72, 16), (384, 24, 36, 32), (384, 12, 18, 64), (384, 6, 9, 128), (64, 48, 72, 16)]:
+        P, d, Cr = H * W, 1, C // 8
+        bf = lambda *sh: torch.randn(*sh, device="cuda").bfloat16()
+        f32 = lambda *sh: torch.randn(*sh, device="cuda")
+        x, y, dout, dx = bf(N, P, C), bf(N, P, C), bf(N, P, C), bf(N, P, C)
+        gamma, beta = f32(C), f32(C)
+        w1, w2, wsp = f32(Cr * C) / C ** 0.5, f32(C * Cr), f32(98) / 7
+        stats, pool, se, hid = torch.zeros(N * 16, device="cuda"), torch.zeros(N * C, device="cuda"), torch.zeros(N * C, device="cuda"), torch.zeros(N * Cr, device="cuda")
+        dg, db, dw1, dw2, dwsp = (torch.zeros(n, device="cuda") for n in (C, C, Cr * C, C * Cr, 98))
+        cases = [
+            ("gn_silu_img_fwd", 2, lambda: _call("pcm_gn_silu_img_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), y.data_ptr(), N, H, W, C, 1e-5, d, _s())),
+            ("convblock_tail_fwd", 2, lambda: _call("pcm_convblock_tail_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), stats.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), y.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())),
+            ("gn_silu_img_bwd", 3, lambda: _call("pcm_gn_silu_img_bwd", dout.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), N, H, W, C, 1e-5, d, _s())),
+            ("convblock_tail_bwd", 3, lambda: _call("pcm_convblock_tail_bwd", dout.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dw1.data_ptr(), dw2.data_ptr(), dwsp.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())),
+        ]
+        cases[1][2]()                      # populate stats / pool / se / hid for the backward kernels
+        for name, ntens, fn in cases:
+            if args.only and args.only not in name:
+                continue
+            ms = timeit(fn, args.iters, args.flush)
+            byts = ntens * N * P * C * 2.0
+            print(f"{name:22s} N={N} {H}x{W} C={C:3d}: {ms * 1e3:8.1f} us   {byts / ms / 1e6:8.1f} GB/s (algorithmic, {ntens} tensor passes)   "
+                  f"{ms * 1e6 / (N * P * C):7.3f} ns/element")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["conv", "wgrad", "pointwise"])
+    ap.add_argument("what", choices=["conv", "wgrad", "pointwise", "tails"])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--flush", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
-    {"conv": bench_conv, "wgrad": bench_wgrad, "pointwise": bench_pointwise}[a.what](a)
+    {"conv": bench_conv, "wgrad": bench_wgrad, "pointwise": bench_pointwise, "tails": bench_tails}[a.what](a)
