@@ -286,8 +286,8 @@ extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long 
 extern "C" int pcm_pack_weights_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
   PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "pack_weights_batched: bad arguments");
   if (njobs == 0 || max_elems == 0) return PCM_OK;
-  long long bx = (max_elems + 1023) / 1024;
-  if (bx > 64) bx = 64;
+  long long bx = (max_elems + 511) / 512;      // the jobs are latency-bound (strided 4-byte accesses): go wide
+  if (bx > 1024) bx = 1024;
   pack_weights_batched_kernel<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, (cudaStream_t)s>>>(jobs);
   return check_launch("pack_weights_batched");
 }
@@ -295,8 +295,8 @@ extern "C" int pcm_pack_weights_batched(const long long* jobs, int njobs, long l
 extern "C" int pcm_unpack_grads_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
   PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "unpack_grads_batched: bad arguments");
   if (njobs == 0 || max_elems == 0) return PCM_OK;
-  long long bx = (max_elems + 1023) / 1024;
-  if (bx > 64) bx = 64;
+  long long bx = (max_elems + 511) / 512;      // the jobs are latency-bound (strided 4-byte accesses): go wide
+  if (bx > 1024) bx = 1024;
   unpack_grads_batched_kernel<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, (cudaStream_t)s>>>(jobs);
   return check_launch("unpack_grads_batched");
 }

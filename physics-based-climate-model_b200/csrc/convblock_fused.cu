@@ -16,7 +16,9 @@
 
 namespace pcm {
 
-constexpr int kFT = 512;       // threads per CTA (one CTA per image)
+constexpr int kFT = 512;       // max threads per CTA (one CTA per image); small images launch 256 / 128 so that
+                               // several CTAs share an SM and their latency-bound phases overlap
+#define NT ((int)blockDim.x)
 constexpr int kGroups = 8;     // nn.GroupNorm(8, c)
 
 template <typename T> __device__ __forceinline__ float sigmoid_t(float z);
@@ -61,29 +63,37 @@ __device__ __forceinline__ void load8_rw(const T* p, float d[8]) {
   }
 }
 
+// Gate maps (channel mean / max, dq) live in zero-padded planes: pixel (h, w) at (h + 3) * Wp + (w + 4), with
+// Wp = roundup8(W) + 8, so that the 16 floats [w0, w0 + 16) a run of 8 pixels needs from one row are four aligned
+// 16-byte shared-memory loads.
+__host__ __device__ inline int plane_wp(int W) { return ((W + 7) / 8) * 8 + 8; }
+
 struct TailSmem {
-  size_t img, cmap, dq, gate, dm, cnt, fl, total;
+  size_t img, cm0, cm1, dq, gate, dm, cnt, fl, total;
 };
 // bwd: 0 = forward tails, 1 = backward tails (needs dq / dm / cnt as well)
 __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int elt, int full, int bwd) {
   TailSmem L;
-  const size_t P = (size_t)H * W, Pp = (size_t)(H + 6) * (W + 6);
+  const size_t P = (size_t)H * W, Pp = (size_t)(H + 6) * plane_wp(W);
   size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
-  L.img = take(P * C * elt);
-  L.cmap = full ? take(Pp * 8) : 0;
-  L.dq = (full && bwd) ? take(Pp * 4) : 0;
-  L.gate = full ? take(P * 4) : 0;
-  L.dm = (full && bwd) ? take(P * 8) : 0;
-  L.cnt = (full && bwd) ? take(P) : 0;
-  // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8] | w[100] dw[100]
-  L.fl = take((size_t)(11 * C + 128 + 32 + 200) * 4);
+#define PCM_TAKE(bytes) ([&]() { size_t o = off; off += ((size_t)(bytes) + 15) & ~(size_t)15; return o; }())
+  L.img = PCM_TAKE(P * C * elt);
+  L.cm0 = full ? PCM_TAKE(Pp * 4) : 0;
+  L.cm1 = full ? PCM_TAKE(Pp * 4) : 0;
+  L.dq = (full && bwd) ? PCM_TAKE(Pp * 4) : 0;
+  L.gate = full ? PCM_TAKE(P * 4) : 0;
+  L.dm = (full && bwd) ? PCM_TAKE(P * 8) : 0;
+  L.cnt = (full && bwd) ? PCM_TAKE(P) : 0;
+  // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
+  //         | wt[2][7][8] | wtf[2][7][8] | dw[100] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
+  L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + (full ? C * C / 4 : 0)) * 4);
+#undef PCM_TAKE
   L.total = off;
   return L;
 }
 
 struct TailPtrs {
-  float *ch0, *ch1, *ch2, *ch3, *ch4, *ca, *cb_, *se, *pool, *dpool, *dpre2, *hid, *dpre1, *mu, *rs, *m1, *m2, *w, *dw;
+  float *ch0, *ch1, *ch2, *ch3, *ch4, *ca, *cb_, *se, *pool, *dpool, *dpre2, *hid, *dpre1, *mu, *rs, *m1, *m2, *wt, *wtf, *dw, *sw1, *sw2;
 };
 __device__ __forceinline__ TailPtrs tail_ptrs(uint8_t* smem, const TailSmem& L, int C) {
   float* f = reinterpret_cast<float*>(smem + L.fl);
@@ -94,19 +104,48 @@ __device__ __forceinline__ TailPtrs tail_ptrs(uint8_t* smem, const TailSmem& L, 
   float* g = f + 11 * C;
   p.hid = g; p.dpre1 = g + 64;
   p.mu = g + 128; p.rs = g + 136; p.m1 = g + 144; p.m2 = g + 152;
-  p.w = g + 160; p.dw = g + 260;
+  p.wt = g + 160; p.wtf = g + 272; p.dw = g + 384;
+  p.sw1 = g + 484; p.sw2 = p.sw1 + C * C / 8;
   return p;
+}
+
+// 7x7 gate weights (2, 7, 7) -> wt[k][dy][8] (dx padded to 8) and the flipped copy wtf[k][dy][dx] = w[k][6-dy][6-dx]
+__device__ __forceinline__ void load_gate_weights(const float* __restrict__ wsp, const TailPtrs& sp) {
+  for (int i = threadIdx.x; i < 112; i += NT) {
+    const int k = i / 56, dy = (i % 56) / 8, dx = i % 8;
+    sp.wt[i] = dx < 7 ? __ldg(wsp + k * 49 + dy * 7 + dx) : 0.f;
+    sp.wtf[i] = dx < 7 ? __ldg(wsp + k * 49 + (6 - dy) * 7 + (6 - dx)) : 0.f;
+  }
+}
+
+// q[i] += sum_{dy,dx} wt[dy][dx] * plane(h + dy - 3, w0 + i + dx - 3) for the 8 pixels (h, w0 .. w0 + 7);
+// row0 = plane + h * Wp + w0 (32-byte aligned).  Per kernel row: 4 + 2 vector loads feed 56 FMAs.
+__device__ __forceinline__ void stencil_run8(const float* row0, int Wp, const float* wt, float (&q)[8]) {
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy) {
+    const float4* r = reinterpret_cast<const float4*>(row0 + dy * Wp);
+    const float4 a = r[0], b = r[1], c = r[2], d = r[3];
+    const float m[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    const float4 wa = reinterpret_cast<const float4*>(wt + dy * 8)[0], wb = reinterpret_cast<const float4*>(wt + dy * 8)[1];
+    const float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(w[dx], m[i + dx + 1], q[i]);
+    }
+  }
 }
 
 // GroupNorm statistics of the image in shared memory -> mu/rs per group (+ raw sums to `stats_out` when non-null)
 template <typename T>
 __device__ __forceinline__ void image_group_stats(const T* s_img, int nvec, int cv, int cg, int P, float eps,
                                                   const TailPtrs& sp, float* stats_out) {
-  const int cb = threadIdx.x % cv;
+  const int cb = threadIdx.x & (cv - 1);
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float x[8];
     load8_rw(s_img + (size_t)v * 8, x);
 #pragma unroll
@@ -140,6 +179,22 @@ __device__ __forceinline__ void group_mu_rs_from_stats(const float* stats_n, int
   }
 }
 
+// Walks the pixels this thread's vectors belong to: vector v = tid + r*NT is (pixel p = v / cv, channel block
+// cb = v % cv); the cv lanes of a pixel are adjacent lanes of one warp.  (h, w) advance without divisions.
+struct PixWalk {
+  int p, h, w, dh, dw, pstep;
+  __device__ __forceinline__ PixWalk(int cvs, int W) {
+    pstep = NT >> cvs;
+    p = (int)threadIdx.x >> cvs;
+    h = p / W; w = p - h * W;
+    dh = pstep / W; dw = pstep - dh * W;
+  }
+  __device__ __forceinline__ void next(int W) {
+    p += pstep; w += dw; h += dh;
+    if (w >= W) { w -= W; ++h; }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // forward tails.  FULL = false: y = silu(GN(x)).  FULL = true: out = a*se*gate with a = silu(GN(x)).
 // ---------------------------------------------------------------------------------------------------------------
@@ -150,24 +205,27 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
                           float* __restrict__ stats, float* __restrict__ pool_g, float* __restrict__ se_g,
                           float* __restrict__ hid_g, T* __restrict__ out, int H, int W, int C, int Cr, float eps) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = W + 6;
+  const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
+  const int cvs = __ffs(cv) - 1;
   const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), FULL ? 1 : 0, 0);
   T* s_img = reinterpret_cast<T*>(smem + L.img);
   const TailPtrs sp = tail_ptrs(smem, L, C);
   const T* xn = x + (size_t)n * P * C;
   T* on = out + (size_t)n * P * C;
-  const int cb = threadIdx.x % cv;
+  const int cb = threadIdx.x & (cv - 1);
 
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+#pragma unroll 4
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8];
     load8(xn + (size_t)v * 8, t);
     store8(s_img + (size_t)v * 8, t);
   }
-  for (int i = threadIdx.x; i < 5 * C; i += kFT) sp.ch0[i] = 0.f;
+  for (int i = threadIdx.x; i < 5 * C; i += NT) sp.ch0[i] = 0.f;
   if (FULL) {
-    float2* s_cmap = reinterpret_cast<float2*>(smem + L.cmap);
-    for (int i = threadIdx.x; i < (H + 6) * Wp; i += kFT) s_cmap[i] = make_float2(0.f, 0.f);
-    for (int i = threadIdx.x; i < 98; i += kFT) sp.w[i] = __ldg(wsp + i);
+    float* cm0 = reinterpret_cast<float*>(smem + L.cm0);       // cm0 and cm1 are contiguous
+    for (int i = threadIdx.x; i < 2 * (H + 6) * Wp; i += NT) cm0[i] = 0.f;
+    load_gate_weights(wsp, sp);
+    for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
   }
   __syncthreads();
   image_group_stats<T>(s_img, nvec, cv, cg, P, eps, sp, stats + (size_t)n * kGroups * 2);
@@ -180,7 +238,8 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
     be[j] = fmaf(-sp.mu[g], ga[j], __ldg(beta + c));
     acc[j] = 0.f;
   }
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8];
     load8_rw(s_img + (size_t)v * 8, t);
 #pragma unroll
@@ -198,65 +257,82 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
   chan_add(acc, sp.ch2, cb, cv);
   __syncthreads();
   const float invP = 1.f / (float)P;
-  for (int c = threadIdx.x; c < C; c += kFT) pool_g[(size_t)n * C + c] = sp.ch2[c];
-  for (int j = threadIdx.x; j < Cr; j += kFT) {
+  for (int c = threadIdx.x; c < C; c += NT) pool_g[(size_t)n * C + c] = sp.ch2[c];
+  // the two 1x1 "fc" matrices were staged in shared memory at kernel start; one warp per hidden unit
+  for (int j = threadIdx.x >> 5; j < Cr; j += NT / 32) {
     float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(__ldg(w1 + (size_t)j * C + c), sp.ch2[c] * invP, a);
-    a = fmaxf(a, 0.f);
-    sp.hid[j] = a;
-    hid_g[(size_t)n * Cr + j] = a;
+    for (int c = threadIdx.x & 31; c < C; c += 32) a = fmaf(sp.sw1[j * C + c], sp.ch2[c], a);
+    a = fmaxf(warp_sum(a) * invP, 0.f);
+    if ((threadIdx.x & 31) == 0) { sp.hid[j] = a; hid_g[(size_t)n * Cr + j] = a; }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kFT) {
+  for (int c = threadIdx.x; c < C; c += NT) {
     float a = 0.f;
-    for (int j = 0; j < Cr; ++j) a = fmaf(__ldg(w2 + (size_t)c * Cr + j), sp.hid[j], a);
+    for (int j = 0; j < Cr; ++j) a = fmaf(sp.sw2[c * Cr + j], sp.hid[j], a);
     a = sigmoidf_(a);
     sp.se[c] = a;
     se_g[(size_t)n * C + c] = a;
   }
   __syncthreads();
 
-  // ---- channel mean / max of u = a*se (SpatialGate.forward, src/unet.py:26-27), zero-padded by 3
-  float2* s_cmap = reinterpret_cast<float2*>(smem + L.cmap);
+  // ---- channel mean / max of u = a*se (SpatialGate.forward, src/unet.py:26-27): each thread reduces its 8
+  // channels, the cv lanes of a pixel finish with a shuffle butterfly
+  float* cm0 = reinterpret_cast<float*>(smem + L.cm0);
+  float* cm1 = reinterpret_cast<float*>(smem + L.cm1);
   float* s_gate = reinterpret_cast<float*>(smem + L.gate);
-  for (int p = threadIdx.x; p < P; p += kFT) {
-    float sum = 0.f, mx = -INFINITY;
-    for (int k = 0; k < cv; ++k) {
-      float t[8];
-      load8_rw(s_img + ((size_t)p * cv + k) * 8, t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = t[j] * sp.se[k * 8 + j];
-        sum += u;
-        mx = fmaxf(mx, u);
-      }
-    }
-    s_cmap[(p / W + 3) * Wp + (p % W) + 3] = make_float2(sum / (float)C, mx);
-  }
-  __syncthreads();
-  // ---- gate = sigmoid(conv7x7([mean, max]))  (:28)
-  for (int p = threadIdx.x; p < P; p += kFT) {
-    const float2* t0 = s_cmap + (p / W) * Wp + (p % W);
-    float q = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 7; ++dy) {
-#pragma unroll
-      for (int dx = 0; dx < 7; ++dx) {
-        const float2 m = t0[dy * Wp + dx];
-        q = fmaf(sp.w[dy * 7 + dx], m.x, q);
-        q = fmaf(sp.w[49 + dy * 7 + dx], m.y, q);
-      }
-    }
-    s_gate[p] = sigmoidf_(q);
-  }
-  __syncthreads();
   float sc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sc[j] = sp.se[cb * 8 + j];
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+  {
+    const int nround = (nvec + NT - 1) / NT;
+    const float invC = 1.f / (float)C;
+    PixWalk pw(cvs, W);
+    for (int r = 0; r < nround; ++r, pw.next(W)) {
+      const bool valid = pw.p < P;
+      float sum = 0.f, mx = -INFINITY;
+      if (valid) {
+        float t[8];
+        load8_rw(s_img + ((size_t)pw.p * cv + cb) * 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float u = t[j] * sc[j];
+          sum += u;
+          mx = fmaxf(mx, u);
+        }
+      }
+      for (int off = 1; off < cv; off <<= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      }
+      if (valid && cb == 0) {
+        const int ip = (pw.h + 3) * Wp + pw.w + 4;
+        cm0[ip] = sum * invC;
+        cm1[ip] = mx;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- gate = sigmoid(conv7x7([mean, max]))  (:28), 8 pixels of a row per work item
+  {
+    const int nrun = (W + 7) / 8;
+    for (int item = threadIdx.x; item < H * nrun; item += NT) {
+      const int h = item / nrun, w0 = (item - h * nrun) * 8;
+      float q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = 0.f;
+      stencil_run8(cm0 + h * Wp + w0, Wp, sp.wt, q);
+      stencil_run8(cm1 + h * Wp + w0, Wp, sp.wt + 56, q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (w0 + i < W) s_gate[h * W + w0 + i] = sigmoidf_(q[i]);
+    }
+  }
+  __syncthreads();
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8];
     load8_rw(s_img + (size_t)v * 8, t);
-    const float gt = s_gate[v / cv];
+    const float gt = s_gate[v >> cvs];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = t[j] * sc[j] * gt;
     store8(on + (size_t)v * 8, t);
@@ -279,35 +355,39 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
   const T* xn = x + (size_t)n * P * C;
   const T* dan = da + (size_t)n * P * C;
   T* dxn = dx + (size_t)n * P * C;
-  const int cb = threadIdx.x % cv;
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+  const int cb = threadIdx.x & (cv - 1);
+#pragma unroll 4
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8];
     load8(xn + (size_t)v * 8, t);
     store8(s_img + (size_t)v * 8, t);
   }
-  for (int i = threadIdx.x; i < 5 * C; i += kFT) sp.ch0[i] = 0.f;
+  for (int i = threadIdx.x; i < 5 * C; i += NT) sp.ch0[i] = 0.f;
   group_mu_rs_from_stats(stats + (size_t)n * kGroups * 2, cg, P, eps, sp);
   __syncthreads();
-  float mu[8], rs[8], ga[8], be[8], r0[8], r1[8], r2[8], r3[8];
+  // xhat = xa*x + xb ; z = za*x + zb
+  float xa[8], xb[8], za[8], zb[8], gm[8], r0[8], r1[8], r2[8], r3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cb * 8 + j, g = c / cg;
-    mu[j] = sp.mu[g]; rs[j] = sp.rs[g];
-    ga[j] = __ldg(gamma + c); be[j] = __ldg(beta + c);
+    gm[j] = __ldg(gamma + c);
+    xa[j] = sp.rs[g]; xb[j] = -sp.mu[g] * sp.rs[g];
+    za[j] = gm[j] * xa[j]; zb[j] = fmaf(gm[j], xb[j], __ldg(beta + c));
     r0[j] = r1[j] = r2[j] = r3[j] = 0.f;
   }
   // pass 1: dxhat (stored to dx as scratch) and the reductions
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8], d[8];
     load8_rw(s_img + (size_t)v * 8, t);
     load8(dan + (size_t)v * 8, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (t[j] - mu[j]) * rs[j];
-      const float z = fmaf(ga[j], xh, be[j]);
+      const float xh = fmaf(xa[j], t[j], xb[j]);
+      const float z = fmaf(za[j], t[j], zb[j]);
       const float sg = sigmoid_t<T>(z);
-      const float dz = d[j] * sg * (1.f + z * (1.f - sg));
-      const float dxh = round_to<T>(dz * ga[j]);
+      const float dz = d[j] * sg * fmaf(z, 1.f - sg, 1.f);
+      const float dxh = round_to<T>(dz * gm[j]);
       r0[j] = fmaf(dz, xh, r0[j]);
       r1[j] += dz;
       r2[j] += dxh;
@@ -329,24 +409,28 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
     sp.m1[g] = a / cnt;
     sp.m2[g] = b / cnt;
   }
-  for (int c = threadIdx.x; c < C; c += kFT) {
+  for (int c = threadIdx.x; c < C; c += NT) {
     atomicAdd(dgamma + c, sp.ch0[c]);
     atomicAdd(dbeta + c, sp.ch1[c]);
   }
   __syncthreads();
-  float m1[8], m2[8];
+  // dx = rs*(dxh - m1 - xh*m2) = rs*dxh - (rs*m1 + rs*m2*xb) - (rs*m2*xa)*x
+  float k0[8], k1[8], k2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { const int g = (cb * 8 + j) / cg; m1[j] = sp.m1[g]; m2[j] = sp.m2[g]; }
+  for (int j = 0; j < 8; ++j) {
+    const int g = (cb * 8 + j) / cg;
+    k0[j] = xa[j];
+    k1[j] = -xa[j] * (sp.m1[g] + sp.m2[g] * xb[j]);
+    k2[j] = -xa[j] * sp.m2[g] * xa[j];
+  }
   // pass 2: every thread re-reads exactly the vectors it wrote in pass 1
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8], d[8];
     load8_rw(s_img + (size_t)v * 8, t);
-    load8_rw(dxn + (size_t)v * 8, d);     // plain loads: written by this same thread in pass 1
+    load8_rw(dxn + (size_t)v * 8, d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (t[j] - mu[j]) * rs[j];
-      d[j] = rs[j] * (d[j] - m1[j] - xh * m2[j]);
-    }
+    for (int j = 0; j < 8; ++j) d[j] = fmaf(k0[j], d[j], fmaf(k2[j], t[j], k1[j]));
     store8(dxn + (size_t)v * 8, d);
   }
 }
@@ -364,10 +448,13 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
                           float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ dw2,
                           float* __restrict__ dwsp, int H, int W, int C, int Cr, float eps) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = W + 6;
+  const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
+  const int cvs = __ffs(cv) - 1;
+  const int nround = (nvec + NT - 1) / NT;
   const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), 1, 1);
   T* s_img = reinterpret_cast<T*>(smem + L.img);
-  float2* s_cmap = reinterpret_cast<float2*>(smem + L.cmap);
+  float* cm0 = reinterpret_cast<float*>(smem + L.cm0);
+  float* cm1 = reinterpret_cast<float*>(smem + L.cm1);
   float* s_dq = reinterpret_cast<float*>(smem + L.dq);
   float* s_gate = reinterpret_cast<float*>(smem + L.gate);
   float2* s_dm = reinterpret_cast<float2*>(smem + L.dm);
@@ -376,158 +463,200 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   const T* xn = x + (size_t)n * P * C;
   const T* don = dout + (size_t)n * P * C;
   T* dxn = dx + (size_t)n * P * C;
-  const int cb = threadIdx.x % cv;
+  const int cb = threadIdx.x & (cv - 1);
   const float invP = 1.f / (float)P;
 
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+#pragma unroll 4
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8];
     load8(xn + (size_t)v * 8, t);
     store8(s_img + (size_t)v * 8, t);
   }
-  for (int i = threadIdx.x; i < 5 * C; i += kFT) sp.ch0[i] = 0.f;
-  for (int i = threadIdx.x; i < (H + 6) * Wp; i += kFT) { s_cmap[i] = make_float2(0.f, 0.f); s_dq[i] = 0.f; }
-  for (int i = threadIdx.x; i < 98; i += kFT) { sp.w[i] = __ldg(wsp + i); sp.dw[i] = 0.f; }
-  for (int c = threadIdx.x; c < C; c += kFT) {
+  for (int i = threadIdx.x; i < 5 * C; i += NT) sp.ch0[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * (H + 6) * Wp; i += NT) cm0[i] = 0.f;     // cm0 | cm1 | dq are contiguous
+  load_gate_weights(wsp, sp);
+  for (int i = threadIdx.x; i < 100; i += NT) sp.dw[i] = 0.f;
+  for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
+  for (int c = threadIdx.x; c < C; c += NT) {
     sp.se[c] = __ldg(se_g + (size_t)n * C + c);
     sp.pool[c] = __ldg(pool_g + (size_t)n * C + c);
   }
-  for (int j = threadIdx.x; j < Cr; j += kFT) sp.hid[j] = __ldg(hid_g + (size_t)n * Cr + j);
+  for (int j = threadIdx.x; j < Cr; j += NT) sp.hid[j] = __ldg(hid_g + (size_t)n * Cr + j);
   group_mu_rs_from_stats(stats + (size_t)n * kGroups * 2, cg, P, eps, sp);
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kFT) {       // z = ca*x + cb_  per channel (for the per-pixel passes)
-    const int g = c / cg;
-    const float a = __ldg(gamma + c) * sp.rs[g];
-    sp.ca[c] = a;
-    sp.cb_[c] = fmaf(-sp.mu[g], a, __ldg(beta + c));
+  // per-thread channel coefficients (fixed channel block): xhat = xa*x + xb ; z = za*x + zb
+  float xa[8], xb[8], za[8], zb[8], gm[8], sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb * 8 + j, g = c / cg;
+    gm[j] = __ldg(gamma + c);
+    xa[j] = sp.rs[g]; xb[j] = -sp.mu[g] * sp.rs[g];
+    za[j] = gm[j] * xa[j]; zb[j] = fmaf(gm[j], xb[j], __ldg(beta + c));
+    sc[j] = sp.se[c];
   }
-  __syncthreads();
 
-  // ---- per pixel: u = a*se -> (mean, max, #ties) ; acc = sum_c dout*a*se   (sigmoid #1)
-  for (int p = threadIdx.x; p < P; p += kFT) {
-    float sum = 0.f, mx = -INFINITY, acc = 0.f;
-    int cnt = 0;
-    for (int k = 0; k < cv; ++k) {
-      float t[8], d[8];
-      load8_rw(s_img + ((size_t)p * cv + k) * 8, t);
-      load8(don + ((size_t)p * cv + k) * 8, d);
+  // ---- pass A (sigmoid #1): u = a*se -> per-pixel (mean, max, #ties) and acc = sum_c dout*u.  The activation a is
+  // recomputed from x (not re-rounded to T: the difference is below the storage resolution and the same u is used
+  // for the max and for the tie test below)
+  {
+    const float invC = 1.f / (float)C;
+    PixWalk pw(cvs, W);
+    for (int r = 0; r < nround; ++r, pw.next(W)) {
+      const bool valid = pw.p < P;
+      float sum = 0.f, mx = -INFINITY, acc = 0.f;
+      int cnt = 0;
+      if (valid) {
+        float t[8], d[8];
+        load8_rw(s_img + ((size_t)pw.p * cv + cb) * 8, t);
+        load8(don + ((size_t)pw.p * cv + cb) * 8, d);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = k * 8 + j;
-        const float z = fmaf(sp.ca[c], t[j], sp.cb_[c]);
-        const float a = round_to<T>(z * sigmoid_t<T>(z));
-        const float u = a * sp.se[c];
-        sum += u;
-        if (u > mx) { mx = u; cnt = 1; } else if (u == mx) { ++cnt; }
-        acc = fmaf(d[j], u, acc);
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(za[j], t[j], zb[j]);
+          const float u = z * sigmoid_t<T>(z) * sc[j];
+          sum += u;
+          if (u > mx) { mx = u; cnt = 1; } else if (u == mx) { ++cnt; }
+          acc = fmaf(d[j], u, acc);
+        }
+      }
+      for (int off = 1; off < cv; off <<= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, off);
+        const int ocnt = __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (omx > mx) { mx = omx; cnt = ocnt; } else if (omx == mx) { cnt += ocnt; }
+      }
+      if (valid && cb == 0) {
+        const int ip = (pw.h + 3) * Wp + pw.w + 4;
+        cm0[ip] = sum * invC;
+        cm1[ip] = mx;
+        s_dq[ip] = acc;
+        s_cnt[pw.p] = (uint8_t)min(cnt, 255);
       }
     }
-    const int ip = (p / W + 3) * Wp + (p % W) + 3;
-    s_cmap[ip] = make_float2(sum / (float)C, mx);
-    s_cnt[p] = (uint8_t)min(cnt, 255);
-    s_dq[ip] = acc;
   }
   __syncthreads();
-  // ---- gate and dq = acc * gate * (1 - gate)
-  for (int p = threadIdx.x; p < P; p += kFT) {
-    const float2* t0 = s_cmap + (p / W) * Wp + (p % W);
-    float q = 0.f;
+  // ---- gate = sigmoid(conv7x7) and dq = acc * gate * (1 - gate)
+  {
+    const int nrun = (W + 7) / 8;
+    for (int item = threadIdx.x; item < H * nrun; item += NT) {
+      const int h = item / nrun, w0 = (item - h * nrun) * 8;
+      float q[8];
 #pragma unroll
-    for (int dy = 0; dy < 7; ++dy) {
+      for (int i = 0; i < 8; ++i) q[i] = 0.f;
+      stencil_run8(cm0 + h * Wp + w0, Wp, sp.wt, q);
+      stencil_run8(cm1 + h * Wp + w0, Wp, sp.wt + 56, q);
 #pragma unroll
-      for (int dxx = 0; dxx < 7; ++dxx) {
-        const float2 m = t0[dy * Wp + dxx];
-        q = fmaf(sp.w[dy * 7 + dxx], m.x, q);
-        q = fmaf(sp.w[49 + dy * 7 + dxx], m.y, q);
+      for (int i = 0; i < 8; ++i) {
+        if (w0 + i < W) {
+          const float gt = sigmoidf_(q[i]);
+          s_gate[h * W + w0 + i] = gt;
+          s_dq[(h + 3) * Wp + w0 + i + 4] *= gt * (1.f - gt);
+        }
       }
     }
-    const float gt = sigmoidf_(q);
-    s_gate[p] = gt;
-    const int ip = (p / W + 3) * Wp + (p % W) + 3;
-    s_dq[ip] *= gt * (1.f - gt);
   }
   __syncthreads();
-  // ---- dwsp[k][dy][dx] += sum_p dq[p] * cmap_k[p + (dy-3, dx-3)] : 98 taps x 5 row partitions
-  if (threadIdx.x < 490) {
-    const int tap = threadIdx.x % 98, part = threadIdx.x / 98;
-    const int k = tap / 49, dy = (tap % 49) / 7, dxx = tap % 7;
-    const float* cm = reinterpret_cast<const float*>(s_cmap) + k;
-    float a0 = 0.f, a1 = 0.f;
-    for (int h = part; h < H; h += 5) {
-      const float* drow = s_dq + (h + 3) * Wp + 3;
-      const float* crow = cm + 2 * ((h + dy) * Wp + dxx);
-      int w = 0;
-      for (; w + 1 < W; w += 2) {
-        a0 = fmaf(drow[w], crow[2 * w], a0);
-        a1 = fmaf(drow[w + 1], crow[2 * w + 2], a1);
+  // ---- dwsp[k][dy][dx] += sum_p dq[p] * cmap_k[p + (dy-3, dx-3)]: thread = (k, dy, row partition), 7 dx sums
+  const int nparts = NT / 14;
+  if ((int)threadIdx.x < 14 * nparts) {
+    const int combo = threadIdx.x % 14, part = threadIdx.x / 14;
+    const int k = combo / 7, dy = combo % 7;
+    const float* pl = k ? cm1 : cm0;
+    float a[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) a[i] = 0.f;
+    const int Wr = (W + 7) / 8 * 8;
+    for (int h = part; h < H; h += nparts) {
+      for (int w0 = 0; w0 < Wr; w0 += 8) {
+        const float4* dr = reinterpret_cast<const float4*>(s_dq + (h + 3) * Wp + w0 + 4);
+        const float4 d0 = dr[0], d1 = dr[1];
+        const float dq8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const float4* cr = reinterpret_cast<const float4*>(pl + (h + dy) * Wp + w0);
+        const float4 c0 = cr[0], c1 = cr[1], c2 = cr[2], c3 = cr[3];
+        const float m[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+#pragma unroll
+        for (int dxx = 0; dxx < 7; ++dxx) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[dxx] = fmaf(dq8[i], m[i + dxx + 1], a[dxx]);
+        }
       }
-      if (w < W) a0 = fmaf(drow[w], crow[2 * w], a0);
     }
-    atomicAdd(&sp.dw[tap], a0 + a1);
+#pragma unroll
+    for (int dxx = 0; dxx < 7; ++dxx) atomicAdd(&sp.dw[k * 49 + dy * 7 + dxx], a[dxx]);
   }
-  // ---- gradient reaching (mean, max) through the transposed stencil
-  for (int p = threadIdx.x; p < P; p += kFT) {
-    const float* t0 = s_dq + (p / W + 6) * Wp + (p % W) + 6;
-    float d0 = 0.f, d1 = 0.f;
+  // ---- gradient reaching (mean, max) through the transposed stencil (flipped weights)
+  {
+    const int nrun = (W + 7) / 8;
+    const float invC = 1.f / (float)C;
+    for (int item = threadIdx.x; item < H * nrun; item += NT) {
+      const int h = item / nrun, w0 = (item - h * nrun) * 8;
+      float q0[8], q1[8];
 #pragma unroll
-    for (int dy = 0; dy < 7; ++dy) {
+      for (int i = 0; i < 8; ++i) q0[i] = q1[i] = 0.f;
+      stencil_run8(s_dq + h * Wp + w0, Wp, sp.wtf, q0);
+      stencil_run8(s_dq + h * Wp + w0, Wp, sp.wtf + 56, q1);
 #pragma unroll
-      for (int dxx = 0; dxx < 7; ++dxx) {
-        const float d = t0[-(dy * Wp + dxx)];
-        d0 = fmaf(sp.w[dy * 7 + dxx], d, d0);
-        d1 = fmaf(sp.w[49 + dy * 7 + dxx], d, d1);
+      for (int i = 0; i < 8; ++i) {
+        if (w0 + i < W) {
+          const int p = h * W + w0 + i;
+          s_dm[p] = make_float2(q0[i] * invC, q1[i] / (float)max((int)s_cnt[p], 1));
+        }
       }
     }
-    s_dm[p] = make_float2(d0 / (float)C, d1 / (float)max((int)s_cnt[p], 1));
   }
   __syncthreads();
   if (threadIdx.x < 98) atomicAdd(dwsp + threadIdx.x, sp.dw[threadIdx.x]);
 
-  // ---- du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ; dse = sum_p du*a  (sigmoid #2)
-  float ga[8], be[8], sc[8], acc[8];
+  // ---- pass B (sigmoid #2): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
+  // dse = sum_p du*a
+  {
+    float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cb * 8 + j;
-    ga[j] = sp.ca[c]; be[j] = sp.cb_[c]; sc[j] = sp.se[c]; acc[j] = 0.f;
-  }
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
-    const int pix = v / cv;
-    float t[8], d[8];
-    load8_rw(s_img + (size_t)v * 8, t);
-    load8(don + (size_t)v * 8, d);
-    const float gt = s_gate[pix];
-    const float2 dm = s_dm[pix];
-    const float mx = s_cmap[(pix / W + 3) * Wp + (pix % W) + 3].y;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    PixWalk pw(cvs, W);
+    for (int r = 0; r < nround; ++r, pw.next(W)) {
+      if (pw.p < P) {
+        const size_t v = (size_t)pw.p * cv + cb;
+        float t[8], d[8];
+        load8_rw(s_img + v * 8, t);
+        load8(don + v * 8, d);
+        const float gt = s_gate[pw.p];
+        const float2 dm = s_dm[pw.p];
+        const float mx = cm1[(pw.h + 3) * Wp + pw.w + 4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(ga[j], t[j], be[j]);
-      const float a = round_to<T>(z * sigmoid_t<T>(z));
-      const float u = a * sc[j];
-      const float du = d[j] * gt + dm.x + ((u == mx) ? dm.y : 0.f);
-      acc[j] = fmaf(du, a, acc[j]);
-      d[j] = du * sc[j];
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(za[j], t[j], zb[j]);
+          const float a = z * sigmoid_t<T>(z);
+          const float u = a * sc[j];
+          const float du = fmaf(d[j], gt, dm.x) + ((u == mx) ? dm.y : 0.f);
+          acc[j] = fmaf(du, a, acc[j]);
+          d[j] = du * sc[j];
+        }
+        store8(dxn + v * 8, d);
+      }
     }
-    store8(dxn + (size_t)v * 8, d);
+    chan_add(acc, sp.ch0, cb, cv);
   }
-  chan_add(acc, sp.ch0, cb, cv);
   __syncthreads();
   // ---- SE backward (tiny): dpool, dw1, dw2
-  for (int c = threadIdx.x; c < C; c += kFT) {
+  for (int c = threadIdx.x; c < C; c += NT) {
     const float s = sp.se[c];
     sp.dpre2[c] = sp.ch0[c] * s * (1.f - s);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < Cr; j += kFT) {
+  for (int j = threadIdx.x >> 5; j < Cr; j += NT / 32) {
     float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(__ldg(w2 + (size_t)c * Cr + j), sp.dpre2[c], a);
-    sp.dpre1[j] = sp.hid[j] > 0.f ? a : 0.f;
+    for (int c = threadIdx.x & 31; c < C; c += 32) a = fmaf(sp.sw2[c * Cr + j], sp.dpre2[c], a);
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) sp.dpre1[j] = sp.hid[j] > 0.f ? a : 0.f;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kFT) {
+  for (int c = threadIdx.x; c < C; c += NT) {
     float a = 0.f;
-    for (int j = 0; j < Cr; ++j) a = fmaf(__ldg(w1 + (size_t)j * C + c), sp.dpre1[j], a);
+    for (int j = 0; j < Cr; ++j) a = fmaf(sp.sw1[j * C + c], sp.dpre1[j], a);
     sp.dpool[c] = a * invP;
   }
-  for (int i = threadIdx.x; i < C * Cr; i += kFT) {
+  for (int i = threadIdx.x; i < C * Cr; i += NT) {
     {
       const int c = i / Cr, j = i % Cr;
       const float v = sp.dpre2[c] * sp.hid[j];
@@ -541,25 +670,20 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   }
   __syncthreads();
   // ---- GroupNorm + SiLU backward, pass 1 (sigmoid #3): dxhat -> scratch, reductions
-  float mu[8], rs[8], gm[8], bt[8], dp[8], r0[8], r1[8], r2[8], r3[8];
+  float dp[8], r0[8], r1[8], r2[8], r3[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cb * 8 + j, g = c / cg;
-    mu[j] = sp.mu[g]; rs[j] = sp.rs[g];
-    gm[j] = __ldg(gamma + c); bt[j] = __ldg(beta + c);
-    dp[j] = sp.dpool[c];
-    r0[j] = r1[j] = r2[j] = r3[j] = 0.f;
-  }
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+  for (int j = 0; j < 8; ++j) { dp[j] = sp.dpool[cb * 8 + j]; r0[j] = r1[j] = r2[j] = r3[j] = 0.f; }
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8], d[8];
     load8_rw(s_img + (size_t)v * 8, t);
     load8_rw(dxn + (size_t)v * 8, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (t[j] - mu[j]) * rs[j];
-      const float z = fmaf(gm[j], xh, bt[j]);
+      const float xh = fmaf(xa[j], t[j], xb[j]);
+      const float z = fmaf(za[j], t[j], zb[j]);
       const float sg = sigmoid_t<T>(z);
-      const float dz = (d[j] + dp[j]) * sg * (1.f + z * (1.f - sg));
+      const float dz = (d[j] + dp[j]) * sg * fmaf(z, 1.f - sg, 1.f);
       const float dxh = round_to<T>(dz * gm[j]);
       r0[j] = fmaf(dz, xh, r0[j]);
       r1[j] += dz;
@@ -582,30 +706,39 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     sp.m1[g] = a / cnt;
     sp.m2[g] = b / cnt;
   }
-  for (int c = threadIdx.x; c < C; c += kFT) {
+  for (int c = threadIdx.x; c < C; c += NT) {
     atomicAdd(dgamma + c, sp.ch1[c]);
     atomicAdd(dbeta + c, sp.ch2[c]);
   }
   __syncthreads();
-  float m1[8], m2[8];
+  float k1[8], k2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { const int g = (cb * 8 + j) / cg; m1[j] = sp.m1[g]; m2[j] = sp.m2[g]; }
-  for (int v = threadIdx.x; v < nvec; v += kFT) {
+  for (int j = 0; j < 8; ++j) {
+    const int g = (cb * 8 + j) / cg;
+    k1[j] = -xa[j] * (sp.m1[g] + sp.m2[g] * xb[j]);
+    k2[j] = -xa[j] * sp.m2[g] * xa[j];
+  }
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8], d[8];
     load8_rw(s_img + (size_t)v * 8, t);
     load8_rw(dxn + (size_t)v * 8, d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (t[j] - mu[j]) * rs[j];
-      d[j] = rs[j] * (d[j] - m1[j] - xh * m2[j]);
-    }
+    for (int j = 0; j < 8; ++j) d[j] = fmaf(xa[j], d[j], fmaf(k2[j], t[j], k1[j]));
     store8(dxn + (size_t)v * 8, d);
   }
 }
 
+// threads per CTA: enough vectors per thread to amortise the phase barriers, few enough that small images get
+// several CTAs per SM (the kernels are register-limited to 512 threads per SM)
+static int tail_threads(int H, int W, int C) {
+  const int nvec = H * W * (C / 8);
+  return nvec >= 4096 ? 512 : nvec >= 1536 ? 256 : 128;
+}
+
 static bool fused_shape_ok(int H, int W, int C, int Cr) {
   const int cv = C / 8;
-  return C % 8 == 0 && C >= 8 && cv <= 32 && (cv & (cv - 1)) == 0 && Cr >= 1 && Cr <= 64 && H >= 1 && W >= 1;
+  return C % 8 == 0 && C >= 8 && cv <= 32 && (cv & (cv - 1)) == 0 && Cr >= 1 && Cr <= 64 && Cr * 8 <= C && H >= 1 && W >= 1;
 }
 
 template <typename K>
@@ -637,7 +770,7 @@ extern "C" int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const floa
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, false>, smem, "gn_silu_img_fwd");
     if (rc == PCM_OK)
-      convblock_tail_fwd_kernel<T, false><<<N, kFT, smem, (cudaStream_t)s>>>(
+      convblock_tail_fwd_kernel<T, false><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
           (const T*)x, gamma, beta, nullptr, nullptr, nullptr, stats, nullptr, nullptr, nullptr, (T*)y, H, W, C, 1, eps);
   });
   if (rc != PCM_OK) return rc;
@@ -656,7 +789,7 @@ extern "C" int pcm_convblock_tail_fwd(const void* x, const float* gamma, const f
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, true>, smem, "convblock_tail_fwd");
     if (rc == PCM_OK)
-      convblock_tail_fwd_kernel<T, true><<<N, kFT, smem, (cudaStream_t)s>>>(
+      convblock_tail_fwd_kernel<T, true><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
           (const T*)x, gamma, beta, w1, w2, wsp, stats, pool, se, hid, (T*)out, H, W, C, Cr, eps);
   });
   if (rc != PCM_OK) return rc;
@@ -674,7 +807,7 @@ extern "C" int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* s
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(gn_silu_img_bwd_kernel<T>, smem, "gn_silu_img_bwd");
     if (rc == PCM_OK)
-      gn_silu_img_bwd_kernel<T><<<N, kFT, smem, (cudaStream_t)s>>>((const T*)da, (const T*)x, stats, gamma, beta, (T*)dx,
+      gn_silu_img_bwd_kernel<T><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>((const T*)da, (const T*)x, stats, gamma, beta, (T*)dx,
                                                                    dgamma, dbeta, H, W, C, eps);
   });
   if (rc != PCM_OK) return rc;
@@ -694,7 +827,7 @@ extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const flo
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_bwd_kernel<T>, smem, "convblock_tail_bwd");
     if (rc == PCM_OK)
-      convblock_tail_bwd_kernel<T><<<N, kFT, smem, (cudaStream_t)s>>>(
+      convblock_tail_bwd_kernel<T><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
           (const T*)dout, (const T*)x, stats, gamma, beta, w1, w2, wsp, pool, se, hid, (T*)dx, dgamma, dbeta, dw1, dw2,
           dwsp, H, W, C, Cr, eps);
   });

@@ -18,12 +18,18 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# SimpleCNN stacks ten BatchNorm layers, which amplify rounding: the REFERENCE under torch.autocast(bf16) against its
+# own fp32 run gives a gradient median rel-L2 of 0.18 (small case) / 0.20 (default widths), worst tensor 0.34 —
+# measured in the build container on the same seeds (see DESIGN.md parity section); ours must stay within that.
+SIMPLECNN_BF16_MEDIAN = 0.25
 F32 = dict(out=1e-4, loss=1e-5, grad=2e-3)
 BF16 = dict(out=3e-2, loss=2e-3, grad=0.5, median=0.12)
 
 
-def _check(res, dtype):
-    tol = F32 if dtype == torch.float32 else BF16
+def _check(res, dtype, median=None):
+    tol = dict(F32 if dtype == torch.float32 else BF16)
+    if median is not None:
+        tol["median"] = median
     assert res["out"] < tol["out"], res["out"]
     assert res["loss"] < tol["loss"], res["loss"]
     if "golden_out" in res:
@@ -70,7 +76,7 @@ def test_attunet(G, tag, dtype):
 def test_simplecnn_small(G, dtype):
     """SimpleCNN (src/models.py:76-123), training-mode BatchNorm, against the oracle and the reference-made golden."""
     r = G.case_simplecnn(dtype)
-    _check(r, dtype)
+    _check(r, dtype, median=SIMPLECNN_BF16_MEDIAN)
     assert r["running_mean"] < (1e-4 if dtype == torch.float32 else 2e-2), r["running_mean"]
     assert r["running_var"] < (1e-4 if dtype == torch.float32 else 2e-2), r["running_var"]
     assert r["nbt"] == 1
@@ -88,7 +94,7 @@ def test_full_size_tensor_core_paths(G, kind):
     from pcm_b200._lib import lib
     r = G.case_full_size(kind)
     assert lib()._fn["pcm_tc_error_count"]() == 0
-    _check(r, torch.bfloat16)
+    _check(r, torch.bfloat16, median=SIMPLECNN_BF16_MEDIAN if kind == "simplecnn" else None)
 
 
 def test_dropout_masks(G):
