@@ -110,6 +110,20 @@ PCM_API int pcm_conv1x1_tc(const void* src, long long src_ns, int src_ps, int H,
 PCM_API int pcm_wgrad1x1_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                             long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
                             int N, int H, int W, pcm_stream_t s);
+/* nn.ConvTranspose2d(kernel_size=2, stride=2) (src/unet.py:63, src/cnn_transformer.py:36,38) on the tensor cores:
+ *   forward   dst(n, 2h+kh, 2w+kw, co) = sum_ci src(n,h,w,ci) * wk[kh*2+kw][co][ci] + bias[co] (relu): ONE GEMM
+ *             [pixels x Cin] x [Cin x 4*Cout] with a pixel-shuffle epilogue; H, W = input grid; Cout multiple of 16, <= 64
+ *   dgrad     dx(n,h,w,ci) = sum_{kh,kw,co} dy(n, 2h+kh, 2w+kw, co) * wk[kh*2+kw][ci][co]: four stride-2 TMA views of dy
+ *   wgrad     dw[ca*sa + cb*sb + q*st] += sum_{n,h,w} a(n,h,w,ca) * b(n, 2h+kh, 2w+kw, cb), q = kh*2 + kw
+ * dy / b / dst may be channel slices of a wider (concat) buffer: pass its pixel and image strides. */
+PCM_API int pcm_convT2x2_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                            int relu, pcm_stream_t s);
+PCM_API int pcm_convT2x2_dgrad_tc(const void* dy, long long dy_ns, int dy_ps, int H, int W, int Cout, void* dx,
+                                  long long dx_ns, int dx_ps, int Cin, const void* wk, int N, pcm_stream_t s);
+PCM_API int pcm_convT2x2_wgrad_tc(const void* a, long long a_ns, int a_ps, int Ca, int Ca_real, const void* b,
+                                  long long b_ns, int b_ps, int Cb, int Cb_real, float* dw, long long sa,
+                                  long long sb, long long st, int N, int H, int W, pcm_stream_t s);
 /* number of bounded-wait timeouts recorded by the tensor-core kernels since load (0 when healthy; syncs) */
 PCM_API int pcm_tc_error_count(void);
 /* weight gradient: dw[ac*sa + bc*sb + tap*st] += sum_{n,ha,wa} A(n,ha,wa,ac) * B(n,hb,wb,bc),

@@ -29,6 +29,10 @@ struct ConvTcParams {
   int Wb, Hb, Nb, tiles_w, tiles_h, num_tiles;
   int KC, kchunks, stages;
   int ksz, relu;          // kernel size (1 or 3; pad = ksz/2), ReLU in the store epilogue
+  int mode;               // 0: conv taps (shifted boxes) ; 1: ConvTranspose2d(k2,s2) data gradient — 4 taps (kh,kw), tap q
+                          //    gathers dy(2h+kh, 2w+kw) through the 5-D views tmA (kh=0) / tmA2 (kh=1) {C, kw, w, h, n}
+  int ps_co;              // > 0: ConvTranspose2d(k2,s2) forward — GEMM column q*ps_co + co is stored at pixel
+                          //    (2h + q/2, 2w + q%2), channel co of a (2H, 2W) destination (pixel shuffle in the epilogue)
   long long dst_ns;
   int dst_ps, dst_f32, accumulate;
   uint32_t tmem_cols, acc_stride, a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
@@ -43,8 +47,8 @@ constexpr int kThreads = 192;
 
 template <int KSTEPS, int EPI>   // KSTEPS = KC / 16 (UMMA K-steps per stage); EPI 0 = store, 1 = ConvLSTM cell
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
                   const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -61,6 +65,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
@@ -72,7 +77,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int ntaps = p.ksz * p.ksz, kpad = p.ksz >> 1;
+  const int ntaps = p.mode == 1 ? 4 : p.ksz * p.ksz, kpad = p.ksz >> 1;
   const int kiters = ntaps * p.kchunks;
 
   if (warp == 0) {
@@ -92,7 +97,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ok = mbar_wait(&empty[stage], phase ^ 1, err);
             if (!ok) break;
             mbar_expect_tx(&full[stage], p.a_tx_bytes + p.b_tx_bytes);
-            tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + kw - kpad, h0 + kh - kpad, n0);
+            if (p.mode == 1)
+              tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, (tap >> 1) ? &tmA2 : &tmA, &full[stage], kc * p.KC, tap & 1, w0,
+                          h0, n0);
+            else
+              tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + kw - kpad, h0 + kh - kpad, n0);
             tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage], kc * p.KC, 0, tap);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -213,16 +222,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float v[16];
         tmem_ld16(t_addr + c0, v);
         if (valid) {
+          long long offc = off + c0;
+          int cbias = c0;
+          if (p.ps_co > 0) {
+            const int q = c0 / p.ps_co;
+            cbias = c0 - q * p.ps_co;
+            offc = (long long)n * p.dst_ns + ((long long)(2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1)) * p.dst_ps + cbias;
+          }
           if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + cbias + j);
           }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (p.dst_f32) {
-            float* dp = reinterpret_cast<float*>(dst) + off + c0;
+            float* dp = reinterpret_cast<float*>(dst) + offc;
             if (p.accumulate) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
@@ -234,7 +250,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
-            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dst) + off + c0;
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dst) + offc;
             store8(dp, v);
             store8(dp + 8, v + 8);
           }
@@ -526,7 +542,8 @@ extern "C" int pcm_tc_error_count(void) {
 static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, const float* lstm_gx, const float* lstm_c_prev,
-                           float* lstm_c_out, void* lstm_acts, pcm_stream_t s, int ksz = 3, int relu = 0) {
+                           float* lstm_c_out, void* lstm_acts, pcm_stream_t s, int ksz = 3, int relu = 0, int mode = 0,
+                           int ps_co = 0) {
   PCM_REQUIRE(Cin % 16 == 0 && Cin >= 16, "conv3x3_tc: Cin must be a multiple of 16 (got %d)", Cin);
   PCM_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv3x3_tc: Cin above 64 must be a multiple of 64 (got %d)", Cin);
   PCM_REQUIRE(Cin == 16 || Cin == 32 || Cin >= 64, "conv3x3_tc: unsupported Cin %d", Cin);
@@ -549,7 +566,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   }
   unsigned int* err = tc_error_counter();
   PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
-  if (halo_env && ksz == 3 && !relu && lstm_gx == nullptr && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
+  if (halo_env && ksz == 3 && mode == 0 && ps_co == 0 && !relu && lstm_gx == nullptr && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
     ConvHaloParams h;
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout;
     h.Wb = h.Hb = h.Nb = 1;
@@ -611,8 +628,8 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   p.num_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.KC = Cin < 64 ? Cin : 64;
   p.kchunks = Cin / p.KC;
-  p.ksz = ksz; p.relu = relu;
-  const int ntaps = ksz * ksz;
+  p.ksz = ksz; p.relu = relu; p.mode = mode; p.ps_co = ps_co;
+  const int ntaps = mode == 1 ? 4 : ksz * ksz;
   p.dst_ns = dst_ns; p.dst_ps = dst_ps; p.dst_f32 = dst_f32; p.accumulate = accumulate;
   p.acc_stride = Cout < 32 ? 32 : Cout;
   uint32_t cols = 32;
@@ -630,13 +647,24 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   p.stages = stages;
   const size_t smem = 1024 + stages * per_stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
 
-  CUtensorMap tmA, tmB;
-  {
+  CUtensorMap tmA, tmA2, tmB;
+  if (mode == 1) {
+    // src is the (2H, 2W) gradient image; view {C, kw, w, h, n}: pixel (2h + kh, 2w + kw) with kh folded into the base
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(src);
+    uint64_t dims[5] = {(uint64_t)Cin, 2, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[4] = {(uint64_t)src_ps * 2, (uint64_t)2 * src_ps * 2, (uint64_t)4 * W * src_ps * 2, (uint64_t)src_ns * 2};
+    uint32_t box[5] = {(uint32_t)p.KC, 1, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    int rc = make_tensor_map(&tmA, base, 5, dims, strides, box, p.KC * 2);
+    if (rc != PCM_OK) return rc;
+    rc = make_tensor_map(&tmA2, base + (size_t)2 * W * src_ps, 5, dims, strides, box, p.KC * 2);
+    if (rc != PCM_OK) return rc;
+  } else {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)src_ps * 2, (uint64_t)W * src_ps * 2, (uint64_t)src_ns * 2};
     uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
     int rc = make_tensor_map(&tmA, src, 4, dims, strides, box, p.KC * 2);
     if (rc != PCM_OK) return rc;
+    tmA2 = tmA;
   }
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
@@ -656,7 +684,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     smem_set[ksi] = smem;
   }
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-  kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, p);
+  kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmA2, tmB, dst, bias, err, p);
   return check_launch("conv3x3_tc");
 }
 
@@ -682,4 +710,21 @@ extern "C" int pcm_conv1x1_tc(const void* src, long long src_ns, int src_ps, int
                               int dst_f32, int accumulate, int relu, pcm_stream_t s) {
   return conv3x3_tc_impl(src, src_ns, src_ps, H, W, Cin, dst, dst_ns, dst_ps, Cout, wk, bias, N, dst_f32, accumulate,
                          nullptr, nullptr, nullptr, nullptr, s, 1, relu);
+}
+
+// ConvTranspose2d(kernel 2, stride 2) forward: one GEMM [pixels x Cin] x [Cin x 4*Cout] whose epilogue scatters
+// quadrant q = (kh, kw) of every input pixel to output pixel (2h + kh, 2w + kw).
+extern "C" int pcm_convT2x2_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                               long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
+                               int relu, pcm_stream_t s) {
+  PCM_REQUIRE(Cout % 16 == 0 && 4 * Cout <= 256, "convT2x2_tc: Cout must be a multiple of 16, <= 64 (got %d)", Cout);
+  return conv3x3_tc_impl(src, src_ns, src_ps, H, W, Cin, dst, dst_ns, dst_ps, 4 * Cout, wk, bias, N, 0, 0, nullptr, nullptr,
+                         nullptr, nullptr, s, 1, relu, 0, Cout);
+}
+
+// ... and its data gradient: dx(n,h,w,ci) = sum_{kh,kw,co} dy(n, 2h+kh, 2w+kw, co) * wk[kh*2+kw][ci][co]
+extern "C" int pcm_convT2x2_dgrad_tc(const void* dy, long long dy_ns, int dy_ps, int H, int W, int Cout, void* dx,
+                                     long long dx_ns, int dx_ps, int Cin, const void* wk, int N, pcm_stream_t s) {
+  return conv3x3_tc_impl(dy, dy_ns, dy_ps, H, W, Cout, dx, dx_ns, dx_ps, Cin, wk, nullptr, N, 0, 0, nullptr, nullptr, nullptr,
+                         nullptr, s, 1, 0, 1, 0);
 }

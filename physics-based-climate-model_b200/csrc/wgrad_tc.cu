@@ -27,6 +27,9 @@ struct WgradTcParams {
   int tpg, ngroups;             // taps per group, groups
   int ksz, ntaps;               // kernel size (1 or 3), ksz*ksz
   int wide;                     // 1: one MMA covers the ksz taps of a kernel row (N = ksz*Ci, LBO = one pixel row)
+  int convt;                    // 1: ConvTranspose2d(k2,s2) weight gradient — 4 taps (kh,kw); tap q's B tile is its own
+                                //    sub-tile, gathered from pixels (2h+kh, 2w+kw) through the 5-D views tmB / tmB2
+  uint32_t b_sub_bytes;         // convt: bytes of one tap's B sub-tile (all chunks)
   int stages;
   long long sa, sb, st;
   uint32_t a_chunk_bytes, b_chunk_bytes, a_stage_bytes, b_stage_bytes, tx_bytes, tmem_cols, lbo_a, lbo_b;
@@ -36,7 +39,7 @@ constexpr int kWgThreads = 192;
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   float* __restrict__ dw, unsigned int* __restrict__ err, const WgradTcParams p) {
+                   const __grid_constant__ CUtensorMap tmB2, float* __restrict__ dw, unsigned int* __restrict__ err, const WgradTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -86,8 +89,15 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint8_t* b = sB + (size_t)stage * p.b_stage_bytes;
         for (int c = 0; c < p.na_chunks; ++c)
           tma_load_4d(a + (size_t)c * p.a_chunk_bytes, &tmA, &full[stage], mtile * 128 + c * p.Cca, 0, h0, n0);
-        for (int c = 0; c < p.nb_chunks; ++c)
-          tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, -(p.ksz >> 1), h0 - (p.ksz >> 1), n0);
+        if (p.convt) {
+          for (int q = 0; q < 4; ++q)
+            for (int c = 0; c < p.nb_chunks; ++c)
+              tma_load_5d(b + (size_t)q * p.b_sub_bytes + (size_t)c * p.b_chunk_bytes, (q >> 1) ? &tmB2 : &tmB, &full[stage],
+                          c * p.Ccb, q & 1, 0, h0, n0);
+        } else {
+          for (int c = 0; c < p.nb_chunks; ++c)
+            tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, -(p.ksz >> 1), h0 - (p.ksz >> 1), n0);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -117,7 +127,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       } else {
         for (int tl = 0; tl < ntap; ++tl) {
           const int tap = tap0 + tl;
-          b_off[nissue] = (uint32_t)(tap / p.ksz) * b_tap_row + (uint32_t)(tap % p.ksz) * b_px;
+          b_off[nissue] = p.convt ? (uint32_t)tap * (p.b_sub_bytes >> 4)
+                                  : (uint32_t)(tap / p.ksz) * b_tap_row + (uint32_t)(tap % p.ksz) * b_px;
           d_off[nissue++] = (uint32_t)(tl * ci);
         }
       }
@@ -192,8 +203,8 @@ using namespace pcm;
 
 static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                          long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
-                         long long st, int N, int H, int W, int ksz, pcm_stream_t s) {
-  const int pad = ksz >> 1, ntaps = ksz * ksz;
+                         long long st, int N, int H, int W, int ksz, pcm_stream_t s, int convt = 0) {
+  const int pad = ksz >> 1, ntaps = convt ? 4 : ksz * ksz;
   PCM_REQUIRE(Co % 16 == 0 && (Co <= 64 ? (Co == 16 || Co == 32 || Co == 64) : Co % 128 == 0),
               "wgrad3x3_tc: Co must be 16, 32, 64 or a multiple of 128 (got %d)", Co);
   PCM_REQUIRE(Ci % 16 == 0 && (Ci <= 64 ? (Ci == 16 || Ci == 32 || Ci == 64) : (Ci % 64 == 0 && Ci <= 256)),
@@ -211,7 +222,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   }
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.Wp = W + 2 * pad;
-  p.ksz = ksz; p.ntaps = ntaps;
+  p.ksz = ksz; p.ntaps = ntaps; p.convt = convt;
   p.Co_real = Co_real; p.Ci_real = Ci_real; p.Ci = Ci;
   p.Cca = Co < 64 ? Co : 64;
   p.Ccb = Ci < 64 ? Ci : 64;
@@ -223,7 +234,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   // K tile: whole images (with their zero rows) when small, else a block of image rows; capped so that one
   // pipeline stage (A: m_extent channels, B: Ci channels, bf16) stays near 100 KB (two stages fit)
   const int rows_full = (H + 2 * pad) * p.Wp;
-  int rows_cap = (int)((100 * 1024) / ((size_t)(m_extent + Ci) * 2)) - 2 * pad * p.Wp - 2 * pad;
+  int rows_cap = (int)((100 * 1024) / ((size_t)(m_extent + (convt ? 4 : 1) * Ci) * 2)) - 2 * pad * p.Wp - 2 * pad;
   if (rows_cap > 240) rows_cap = 240;
   if (rows_cap < 16) rows_cap = 16;
   int a_box_h, b_box_h;
@@ -256,8 +267,9 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   p.a_chunk_bytes = ((uint32_t)a_alloc * rba + 1023u) & ~1023u;
   p.b_chunk_bytes = ((uint32_t)b_alloc * rbb + 1023u) & ~1023u;
   p.a_stage_bytes = p.a_chunk_bytes * p.na_chunks;
-  p.b_stage_bytes = p.b_chunk_bytes * p.nb_chunks;
-  p.tx_bytes = (uint32_t)a_rows * rba * p.na_chunks + (uint32_t)b_rows * rbb * p.nb_chunks;
+  p.b_sub_bytes = p.b_chunk_bytes * p.nb_chunks;
+  p.b_stage_bytes = p.b_sub_bytes * (convt ? 4 : 1);
+  p.tx_bytes = (uint32_t)a_rows * rba * p.na_chunks + (uint32_t)b_rows * rbb * p.nb_chunks * (convt ? 4 : 1);
   // M blocks beyond the real channels alias the tile shifted by 8 rows (results unused, reads stay in bounds)
   p.lbo_a = (p.na_chunks * p.Cca >= 128) ? p.a_chunk_bytes : 8 * rba;
   p.lbo_b = p.b_chunk_bytes;
@@ -266,7 +278,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
     const char* e = getenv("PCM_WGRAD_WIDE");     // PCM_WGRAD_WIDE=0: one MMA per tap (A/B experiments)
     wide_env = e ? atoi(e) : 1;
   }
-  p.wide = (wide_env && ksz == 3 && p.nb_chunks == 1 && 3 * Ci <= 256) ? 1 : 0;
+  p.wide = (wide_env && !convt && ksz == 3 && p.nb_chunks == 1 && 3 * Ci <= 256) ? 1 : 0;
   if (p.wide) {
     int rows = 512 / (3 * Ci);                                  // whole kernel rows per group (TMEM: 512 columns)
     if (rows > 3) rows = 3;
@@ -289,7 +301,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   p.stages = stages;
   const size_t smem = 1024 + stages * per_stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmB2;
   {
     uint64_t dims[4] = {(uint64_t)Co, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)dy_ps * 2, (uint64_t)W * dy_ps * 2, (uint64_t)dy_ns * 2};
@@ -297,12 +309,23 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
     int rc = make_tensor_map(&tmA, dy, 4, dims, strides, box, rba);
     if (rc != PCM_OK) return rc;
   }
-  {
+  if (convt) {
+    // B is the (2H, 2W) image; view {C, kw, w, h, n}: pixel (2h + kh, 2w + kw), kh folded into the base pointer
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(x);
+    uint64_t dims[5] = {(uint64_t)Ci, 2, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[4] = {(uint64_t)x_ps * 2, (uint64_t)2 * x_ps * 2, (uint64_t)4 * W * x_ps * 2, (uint64_t)x_ns * 2};
+    uint32_t box[5] = {(uint32_t)p.Ccb, 1, (uint32_t)p.Wp, (uint32_t)b_box_h, (uint32_t)p.Nb};
+    int rc = make_tensor_map(&tmB, base, 5, dims, strides, box, rbb);
+    if (rc != PCM_OK) return rc;
+    rc = make_tensor_map(&tmB2, base + (size_t)2 * W * x_ps, 5, dims, strides, box, rbb);
+    if (rc != PCM_OK) return rc;
+  } else {
     uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)x_ps * 2, (uint64_t)W * x_ps * 2, (uint64_t)x_ns * 2};
     uint32_t box[4] = {(uint32_t)p.Ccb, (uint32_t)p.Wp, (uint32_t)b_box_h, (uint32_t)p.Nb};
     int rc = make_tensor_map(&tmB, x, 4, dims, strides, box, rbb);
     if (rc != PCM_OK) return rc;
+    tmB2 = tmB;
   }
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -316,7 +339,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   if (nsplit < 1) nsplit = 1;
   if (nsplit > p.num_ktiles) nsplit = p.num_ktiles;
   dim3 grid(nsplit, mtiles, p.ngroups);
-  wgrad3x3_tc_kernel<<<grid, kWgThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dw, err, p);
+  wgrad3x3_tc_kernel<<<grid, kWgThreads, smem, (cudaStream_t)s>>>(tmA, tmB, tmB2, dw, err, p);
   return check_launch("wgrad3x3_tc");
 }
 
@@ -330,4 +353,12 @@ extern "C" int pcm_wgrad1x1_tc(const void* dy, long long dy_ns, int dy_ps, int C
                                long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
                                int N, int H, int W, pcm_stream_t s) {
   return wgrad_tc_impl(dy, dy_ns, dy_ps, Co, Co_real, x, x_ns, x_ps, Ci, Ci_real, dw, sa, sb, 0, N, H, W, 1, s);
+}
+
+// ConvTranspose2d(k2,s2) weight gradient: dw[ca*sa + cb*sb + q*st] += sum_{n,h,w} a(n,h,w,ca) * b(n, 2h+kh, 2w+kw, cb),
+// q = kh*2 + kw; a is the (H, W) input of the transposed conv, b the (2H, 2W) output gradient.
+extern "C" int pcm_convT2x2_wgrad_tc(const void* a, long long a_ns, int a_ps, int Ca, int Ca_real, const void* b,
+                                     long long b_ns, int b_ps, int Cb, int Cb_real, float* dw, long long sa,
+                                     long long sb, long long st, int N, int H, int W, pcm_stream_t s) {
+  return wgrad_tc_impl(a, a_ns, a_ps, Ca, Ca_real, b, b_ns, b_ps, Cb, Cb_real, dw, sa, sb, st, N, H, W, 1, s, 1);
 }

@@ -276,6 +276,54 @@ def conv3x3_wgrad(dy, x, dw, N, H, W, Co, Ci, Ci_real, Ci_tot=None, dy_ns=None, 
                    b_ns=x_ns, b_ps=x_ps, a_off=dy_off, b_off=x_off, dw_off=dw_off)
 
 
+# ---- ConvTranspose2d(kernel 2, stride 2): tensor-core GEMM forms, SIMT gather kernels otherwise ----------------
+def _tc_k_ok(c: int) -> bool:
+    return c in (16, 32) or (c >= 64 and c % 64 == 0)
+
+
+def convT2x2_fwd(x, wt, bt, B, h, w, Ci, Co, dst, dst_ns, dst_ps, relu=False):
+    """dst(b, 2h+kh, 2w+kw, co) = sum_ci x(b,h,w,ci) * wt[ci][co][kh][kw] + bt[co]; dst may be a channel slice of a
+    wider buffer (dst_ns / dst_ps = its image / pixel strides)."""
+    dt = x.dtype
+    wk = pack_weight(wt, 4, Co * 4, 1, Co, Ci, 4, dt)                 # wk[tap][co][ci] = wt[ci][co][tap]
+    if dt == torch.bfloat16 and _tc_k_ok(Ci) and Co % 16 == 0 and Co <= 64:
+        _call("pcm_convT2x2_tc", x.data_ptr(), h * w * Ci, Ci, h, w, Ci, dst.data_ptr(), dst_ns, dst_ps, Co, wk.data_ptr(),
+              _p(bt), B, int(relu), _s())
+    else:
+        conv_gather(x, wk, B, h, w, Ci, 2 * h, 2 * w, Co, 2, 2, 2, 0, 1, dst=dst, bias=bt, relu=relu, dst_ns=dst_ns,
+                    dst_ps=dst_ps)
+    return dst
+
+
+def convT2x2_dgrad(dy, wt, B, h, w, Ci, Co, dy_ns, dy_ps):
+    """dx(b,h,w,ci) = sum_{kh,kw,co} dy(b, 2h+kh, 2w+kw, co) * wt[ci][co][kh][kw]."""
+    dt = dy.dtype
+    wk = pack_weight(wt, Co * 4, 4, 1, Ci, Co, 4, dt)                 # wk[tap][ci][co] = wt[ci][co][tap]
+    dx = torch.empty((B, h, w, Ci), device=dy.device, dtype=dt)
+    if dt == torch.bfloat16 and _tc_k_ok(Co) and Ci % 16 == 0 and Ci <= 256:
+        _call("pcm_convT2x2_dgrad_tc", dy.data_ptr(), dy_ns, dy_ps, h, w, Co, dx.data_ptr(), h * w * Ci, Ci, Ci,
+              wk.data_ptr(), B, _s())
+    else:
+        conv_gather(dy, wk, B, 2 * h, 2 * w, Co, h, w, Ci, 2, 2, 2, 0, 0, dst=dx, src_ns=dy_ns, src_ps=dy_ps)
+    return dx
+
+
+def convT2x2_wgrad(x, dy, gwt, B, h, w, Ci, Co, dy_ns, dy_ps):
+    """gwt (Ci, Co, 2, 2) fp32 += sum_{b,h,w} x(b,h,w,ci) * dy(b, 2h+kh, 2w+kw, co)."""
+    if (x.dtype == torch.bfloat16 and (Ci in (16, 32, 64) or Ci % 128 == 0) and Co in (16, 32, 64, 128, 192, 256)
+            and w <= 256 and h <= 256):
+        packed = _PLAN.grad_pack(gwt, Ci, Co, 4) if _PLAN is not None else None
+        if packed is not None:
+            Cpad = packed.shape[-1]
+            _call("pcm_convT2x2_wgrad_tc", x.data_ptr(), h * w * Ci, Ci, Ci, Ci, dy.data_ptr(), dy_ns, dy_ps, Co, Co,
+                  packed.data_ptr(), Cpad, 1, Ci * Cpad, B, h, w, _s())
+        else:
+            _call("pcm_convT2x2_wgrad_tc", x.data_ptr(), h * w * Ci, Ci, Ci, Ci, dy.data_ptr(), dy_ns, dy_ps, Co, Co,
+                  gwt.data_ptr(), Co * 4, 4, 1, B, h, w, _s())
+    else:
+        conv_wgrad(x, dy, gwt, Co * 4, 4, 1, B, h, w, Ci, Ci, 2 * h, 2 * w, Co, Co, 2, 2, 2, 0, b_ns=dy_ns, b_ps=dy_ps)
+
+
 def channel_sum(x, out, N, P, C, C_real, ns=None, ps=None, off=0, per_image=False):
     ps = C if ps is None else ps
     ns = P * ps if ns is None else ns
@@ -577,9 +625,8 @@ class UpCatFn(torch.autograd.Function):
         assert wt.shape[0] == Ci and Co % 8 == 0 and Cs % 8 == 0
         H, W, Cc, dt = 2 * h, 2 * w, Co + Cs, x.dtype
         cat = torch.empty((B, H, W, Cc), device=x.device, dtype=dt)
-        # convT forward == mode-1 gather with (k=2, s=2, p=0); wk[tap][d][c] = wt[c][d][tap]
-        wk = pack_weight(wt, 4, Co * 4, 1, Co, Ci, 4, dt)
-        conv_gather(x, wk, B, h, w, Ci, H, W, Co, 2, 2, 2, 0, 1, dst=cat, bias=bt, dst_ns=H * W * Cc, dst_ps=Cc)
+        # transposed conv = one GEMM [pixels x Ci] x [Ci x 4*Co] whose epilogue pixel-shuffles into the concat buffer
+        convT2x2_fwd(x, wt, bt, B, h, w, Ci, Co, cat, H * W * Cc, Cc)
         cat[..., Co:].copy_(skip)          # strided D2D copy (plumbing, no arithmetic)
         ctx.save_for_backward(x, wt, bt)
         ctx.dims = (B, h, w, Ci, Co, Cs)
@@ -593,13 +640,11 @@ class UpCatFn(torch.autograd.Function):
         dcat = dcat.contiguous()
         gwt, rwt = _grad_buf(wt)
         gbt, rbt = _grad_buf(bt)
-        # data grad == mode-0 gather (k=2,s=2,p=0) over the first Co channels; wk[tap][c][d] = wt[c][d][tap]
+        # data / weight gradients read the first Co channels of the concat gradient through stride-2 views
         dx = None
         if ctx.needs_input_grad[0]:
-            wk = pack_weight(wt, Co * 4, 4, 1, Ci, Co, 4, dt)
-            dx = conv_gather(dcat, wk, B, H, W, Co, h, w, Ci, 2, 2, 2, 0, 0, src_ns=H * W * Cc, src_ps=Cc)
-        # weight grad: A = x (small grid), B = dcat (big grid): dwt[c][d][tap]
-        conv_wgrad(x, dcat, gwt, Co * 4, 4, 1, B, h, w, Ci, Ci, H, W, Co, Co, 2, 2, 2, 0, b_ns=H * W * Cc, b_ps=Cc)
+            dx = convT2x2_dgrad(dcat, wt, B, h, w, Ci, Co, H * W * Cc, Cc)
+        convT2x2_wgrad(x, dcat, gwt, B, h, w, Ci, Co, H * W * Cc, Cc)
         channel_sum(dcat, gbt, B, H * W, Co, Co, ns=H * W * Cc, ps=Cc)
         dskip = dcat[..., Co:] if ctx.needs_input_grad[1] else None     # view; consumer reads it strided
         return dx, dskip, rwt, rbt

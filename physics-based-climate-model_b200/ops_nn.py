@@ -152,8 +152,8 @@ class ConvT2x2Fn(torch.autograd.Function):
         Co = wt.shape[1]
         assert wt.shape[0] == Ci and Co % 8 == 0
         dt = x.dtype
-        wk = pack_weight(wt, 4, Co * 4, 1, Co, Ci, 4, dt)                          # wk[tap][d][c] = wt[c][d][tap]
-        y = conv_gather(x, wk, B, h, w, Ci, 2 * h, 2 * w, Co, 2, 2, 2, 0, 1, bias=bt, relu=relu)
+        y = torch.empty((B, 2 * h, 2 * w, Co), device=x.device, dtype=dt)
+        ops.convT2x2_fwd(x, wt, bt, B, h, w, Ci, Co, y, 4 * h * w * Co, Co, relu=relu)
         ctx.save_for_backward(x, wt, bt, y if relu else None)
         ctx.relu = relu
         return y
@@ -173,9 +173,8 @@ class ConvT2x2Fn(torch.autograd.Function):
         gbt, rbt = _grad_buf(bt)
         dx = None
         if ctx.needs_input_grad[0]:
-            wk = pack_weight(wt, Co * 4, 4, 1, Ci, Co, 4, dt)
-            dx = conv_gather(dy, wk, B, 2 * h, 2 * w, Co, h, w, Ci, 2, 2, 2, 0, 0)
-        conv_wgrad(x, dy, gwt, Co * 4, 4, 1, B, h, w, Ci, Ci, 2 * h, 2 * w, Co, Co, 2, 2, 2, 0)
+            dx = ops.convT2x2_dgrad(dy, wt, B, h, w, Ci, Co, 4 * h * w * Co, Co)
+        ops.convT2x2_wgrad(x, dy, gwt, B, h, w, Ci, Co, 4 * h * w * Co, Co)
         channel_sum(dy, gbt, B, 4 * h * w, Co, Co)
         return dx, rwt, rbt, None
 

@@ -230,3 +230,48 @@ def test_conv3x3_tc_wide_channels(ops):
     ops_nn.wgrad_same(dy.cuda(), x.cuda(), dw, N, H, W, Co, Ci, Ci, 3)
     torch.cuda.synchronize()
     assert float((dw.cpu() - wz.grad.float()).norm() / wz.grad.norm()) < 1e-5
+
+
+CT_SHAPES = [  # (B, h, w, Ci, Co, Cs): the three Up blocks of config 3, the transformer decoder, ragged sizes
+    (4, 6, 9, 64, 64, 64), (3, 12, 18, 64, 32, 32), (2, 24, 36, 32, 16, 16), (2, 12, 18, 128, 64, 0), (2, 24, 36, 64, 32, 0),
+    (3, 5, 7, 32, 16, 16), (1, 20, 33, 64, 64, 32),
+]
+
+
+@pytest.mark.parametrize("shape", CT_SHAPES)
+def test_convT2x2_tc_matches_reference(ops, shape):
+    """ConvTranspose2d(k2,s2) forward (pixel-shuffle epilogue into a concat buffer), data gradient and weight
+    gradient (stride-2 TMA views) against torch's CPU conv_transpose2d on the same bf16-rounded operands."""
+    from pcm_b200._lib import lib
+    B, h, w, Ci, Co, Cs = shape
+    g = torch.Generator().manual_seed(B * 13 + h + Ci + Co)
+    x = torch.randn(B, h, w, Ci, generator=g).bfloat16()
+    wt = (torch.randn(Ci, Co, 2, 2, generator=g) / Ci ** 0.5).bfloat16()
+    bias = torch.randn(Co, generator=g)
+    Cc = Co + Cs
+    H, W = 2 * h, 2 * w
+    xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.double().requires_grad_(True)
+    want = F.conv_transpose2d(xr, wr, bias.double(), stride=2)                       # (B, Co, H, W)
+    cat = torch.full((B, H, W, Cc), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.convT2x2_fwd(x.cuda(), wt.float().cuda(), bias.cuda(), B, h, w, Ci, Co, cat, H * W * Cc, Cc)
+    torch.cuda.synchronize()
+    assert lib().last_call == "pcm_convT2x2_tc"
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    got = cat[..., :Co].float().cpu()
+    assert float((got - want.detach().permute(0, 2, 3, 1).float()).norm() / want.norm()) < 4e-3
+    if Cs:
+        assert bool((cat[..., Co:] == 7.0).all())                                    # the skip half is untouched
+    # gradients from a bf16 dcat whose first Co channels are the convT gradient
+    dcat = (torch.randn(B, H, W, Cc, generator=g) / (B * H * W) ** 0.5).bfloat16()
+    want.backward(dcat[..., :Co].double().permute(0, 3, 1, 2))
+    dx = ops.convT2x2_dgrad(dcat.cuda(), wt.float().cuda(), B, h, w, Ci, Co, H * W * Cc, Cc)
+    assert lib().last_call == "pcm_convT2x2_dgrad_tc"
+    gwt = torch.zeros(Ci, Co, 2, 2, device="cuda")
+    ops.convT2x2_wgrad(x.cuda(), dcat.cuda(), gwt, B, h, w, Ci, Co, H * W * Cc, Cc)
+    assert lib().last_call == "pcm_convT2x2_wgrad_tc"
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    wdx = xr.grad.permute(0, 2, 3, 1).float()
+    assert float((dx.float().cpu() - wdx).norm() / wdx.norm()) < 4e-3
+    assert float((gwt.cpu() - wr.grad.float()).norm() / wr.grad.norm()) < 1e-5
