@@ -26,8 +26,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, long long so, lo
 // All weight re-packs of a training step in ONE launch: blockIdx.y = job, the x-grid strides over that job's
 // elements.  Job record (8 x int64, device memory): w ptr, out ptr, so, si, st, (O | I << 32), (taps | Op << 32),
 // (Ip | dtype << 32).
-__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs) {
-  const long long* j = jobs + (long long)blockIdx.y * 8;
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs, int njobs) {
+ // every block sweeps all jobs; the job table is staged in shared memory first (reading each record from global
+ // memory inside the sweep serialises ~1 us of latency per job)
+ extern __shared__ long long sjobs[];
+ for (int i = threadIdx.x; i < njobs * 8; i += blockDim.x) sjobs[i] = jobs[i];
+ __syncthreads();
+ for (int job = 0; job < njobs; ++job) {
+  const long long* j = sjobs + job * 8;
   const float* w = reinterpret_cast<const float*>(j[0]);
   void* out = reinterpret_cast<void*>(j[1]);
   const long long so = j[2], si = j[3], st = j[4];
@@ -45,14 +51,19 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
     if (dtype == PCM_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(out)[idx] = v;
   }
+ }
 }
 
 // Packed weight gradients [tap][Co][Cpad] (what the tensor-core weight-gradient kernel reduces into with vector
 // atomics) -> the parameter's own layout: dst[co*sa + ci*sb + tap*st] += packed[(tap*Co + co)*Cpad + ci]; the packed
 // buffer is zeroed on the way (ready for the next step).  blockIdx.y = job.  Job record (8 x int64): packed ptr,
 // dst ptr, sa, sb, st, (Co | Ci_real << 32), (Cpad | taps << 32), unused.
-__global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long long* __restrict__ jobs) {
-  const long long* j = jobs + (long long)blockIdx.y * 8;
+__global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long long* __restrict__ jobs, int njobs) {
+ extern __shared__ long long sjobs[];
+ for (int i = threadIdx.x; i < njobs * 8; i += blockDim.x) sjobs[i] = jobs[i];
+ __syncthreads();
+ for (int job = 0; job < njobs; ++job) {
+  const long long* j = sjobs + job * 8;
   float* packed = reinterpret_cast<float*>(j[0]);
   float* dst = reinterpret_cast<float*>(j[1]);
   const long long sa = j[2], sb = j[3], st = j[4];
@@ -68,6 +79,7 @@ __global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long lo
     packed[idx] = 0.f;
     if (ci < Ci && v != 0.f) dst[co * sa + ci * sb + t * st] += v;
   }
+ }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +273,21 @@ channel_sum_kernel(const T* __restrict__ x, long long ns, int ps, int N, int P, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += xv[j];
   }
-  if (my_cb >= 0) {
+  // cv a power of two < 32 (and the thread stride a multiple of cv): every thread kept one channel block, equal to
+  // lane % cv — combine the lanes that share it with shuffles so that only cv lanes per warp touch shared memory
+  // (256 threads hammering 16 addresses was the whole cost of the thin-layer bias gradients)
+  const bool uniform = cv < 32 && (cv & (cv - 1)) == 0 && ((long long)gridDim.x * blockDim.x) % cv == 0;
+  if (uniform) {
+    for (int off = cv; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+    const int lane_cb = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % cv);
+    if ((int)(threadIdx.x & 31) < cv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[lane_cb * 8 + j], acc[j]);
+    }
+  } else if (my_cb >= 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(&sacc[my_cb * 8 + j], acc[j]);
   }
@@ -286,18 +312,20 @@ extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long 
 extern "C" int pcm_pack_weights_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
   PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "pack_weights_batched: bad arguments");
   if (njobs == 0 || max_elems == 0) return PCM_OK;
-  long long bx = (max_elems + 511) / 512;      // the jobs are latency-bound (strided 4-byte accesses): go wide
-  if (bx > 1024) bx = 1024;
-  pack_weights_batched_kernel<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, (cudaStream_t)s>>>(jobs);
+  long long bx = (max_elems + 511) / 512;
+  if (bx > 148 * 4) bx = 148 * 4;
+  PCM_REQUIRE(njobs <= 512, "pack_weights_batched: at most 512 jobs per launch");
+  pack_weights_batched_kernel<<<(unsigned)bx, 256, (size_t)njobs * 64, (cudaStream_t)s>>>(jobs, njobs);
   return check_launch("pack_weights_batched");
 }
 
 extern "C" int pcm_unpack_grads_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
   PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "unpack_grads_batched: bad arguments");
   if (njobs == 0 || max_elems == 0) return PCM_OK;
-  long long bx = (max_elems + 511) / 512;      // the jobs are latency-bound (strided 4-byte accesses): go wide
-  if (bx > 1024) bx = 1024;
-  unpack_grads_batched_kernel<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, (cudaStream_t)s>>>(jobs);
+  long long bx = (max_elems + 511) / 512;
+  if (bx > 148 * 4) bx = 148 * 4;
+  PCM_REQUIRE(njobs <= 512, "unpack_grads_batched: at most 512 jobs per launch");
+  unpack_grads_batched_kernel<<<(unsigned)bx, 256, (size_t)njobs * 64, (cudaStream_t)s>>>(jobs, njobs);
   return check_launch("unpack_grads_batched");
 }
 

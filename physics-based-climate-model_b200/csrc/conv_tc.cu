@@ -566,7 +566,8 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   }
   unsigned int* err = tc_error_counter();
   PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
-  if (halo_env && ksz == 3 && mode == 0 && ps_co == 0 && !relu && lstm_gx == nullptr && Cin <= 32 && (size_t)9 * Cout * Cin * 2 <= 64 * 1024) {
+  if (halo_env && ksz == 3 && mode == 0 && ps_co == 0 && !relu && lstm_gx == nullptr && Cin <= 64 &&
+      (size_t)9 * Cout * Cin * 2 <= (size_t)(Cin <= 32 ? 64 : 148) * 1024) {
     ConvHaloParams h;
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout;
     h.Wb = h.Hb = h.Nb = 1;
@@ -588,7 +589,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     h.a_tx_bytes = (uint32_t)box_rows * row_bytes;
     h.b_bytes = 9u * Cout * row_bytes;
     const size_t b_region = ((size_t)h.b_bytes + 1023) & ~(size_t)1023;
-    int stages = (int)((160 * 1024 - b_region) / h.a_stage_bytes);
+    int stages = (int)(((Cin <= 32 ? 160 : 212) * 1024 - b_region) / h.a_stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
     h.stages = stages;
@@ -608,12 +609,13 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
       int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, row_bytes);
       if (rc != PCM_OK) return rc;
     }
-    auto kern = Cin == 16 ? conv3x3_tc_halo_kernel<1> : conv3x3_tc_halo_kernel<2>;
-    static size_t smem_set_h[2] = {0, 0};
-    if (smem > smem_set_h[Cin == 16 ? 0 : 1]) {
+    auto kern = Cin == 16 ? conv3x3_tc_halo_kernel<1> : Cin == 32 ? conv3x3_tc_halo_kernel<2> : conv3x3_tc_halo_kernel<4>;
+    const int hk = Cin == 16 ? 0 : Cin == 32 ? 1 : 2;
+    static size_t smem_set_h[3] = {0, 0, 0};
+    if (smem > smem_set_h[hk]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("conv3x3_tc(halo): smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
-      smem_set_h[Cin == 16 ? 0 : 1] = smem;
+      smem_set_h[hk] = smem;
     }
     const int grid = h.num_tiles < g_num_sms ? h.num_tiles : g_num_sms;
     kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, h);

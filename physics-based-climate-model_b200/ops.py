@@ -135,22 +135,63 @@ class PackPlan:
 
 
 _PLAN: Optional[PackPlan] = None
+_SIDE: Optional[torch.cuda.Stream] = None      # trainer-provided stream for weight-gradient kernels
+
+
+class side_stream:
+    """`with side_stream(t1, t2, ...):` issues the enclosed launches on the trainer's side stream (after everything
+    enqueued so far on the current stream), so that weight-gradient GEMMs — which nothing in the backward chain
+    depends on — overlap the data-gradient / tail kernels of the critical path.  The listed tensors are the ones the
+    side kernels read: they are marked in-use on that stream for the caching allocator.  No-op without a side stream."""
+
+    def __init__(self, *tensors):
+        self.tensors = tensors
+        self.ctx = None
+
+    def __enter__(self):
+        if _SIDE is not None:
+            _SIDE.wait_stream(torch.cuda.current_stream())
+            for t in self.tensors:
+                if t is not None:
+                    t.record_stream(_SIDE)
+            self.ctx = torch.cuda.stream(_SIDE)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def side_active() -> bool:
+    return _SIDE is not None
+
+
+def join_side():
+    """Make the current stream wait for everything issued on the side stream."""
+    if _SIDE is not None:
+        torch.cuda.current_stream().wait_stream(_SIDE)
 
 
 class use_pack_plan:
-    """Context manager activating a PackPlan for the ops issued inside it (trainer step body)."""
+    """Context manager activating a PackPlan (and optionally a side stream for weight-gradient kernels) for the ops
+    issued inside it (trainer step body)."""
 
-    def __init__(self, plan: Optional[PackPlan]):
+    def __init__(self, plan: Optional[PackPlan], side: Optional[torch.cuda.Stream] = None):
         self.plan = plan
+        self.side = side
 
     def __enter__(self):
-        global _PLAN
+        global _PLAN, _SIDE
         self.prev, _PLAN = _PLAN, self.plan
+        self.prev_side, _SIDE = _SIDE, self.side
         return self.plan
 
     def __exit__(self, *exc):
-        global _PLAN
+        global _PLAN, _SIDE
         _PLAN = self.prev
+        _SIDE = self.prev_side
         return False
 
 
@@ -536,13 +577,15 @@ class ConvBlockFn(torch.autograd.Function):
               sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(),
               dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(), gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(),
               N, H, W, Co, Cr, GN_EPS, d, st)
-        conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
+        with side_stream(dy2, a1):
+            conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
         wk2t = conv_weight_dgrad(w2, dt)
         da1 = conv_s1(dy2, wk2t, N, H, W, Co, Co)
-        dy1 = dy2                                                                          # reuse dy2 storage
+        dy1 = torch.empty_like(y1) if side_active() else dy2          # dy2 storage is reused unless a side kernel reads it
         _call("pcm_gn_silu_img_bwd", da1.data_ptr(), y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(), b1.data_ptr(),
               dy1.data_ptr(), gg1.data_ptr(), gb1.data_ptr(), N, H, W, Co, GN_EPS, d, st)
-        conv3x3_wgrad(dy1, x, gw1, N, H, W, Co, Cip, Ci)
+        with side_stream(dy1, x):
+            conv3x3_wgrad(dy1, x, gw1, N, H, W, Co, Cip, Ci)
         dx = None
         if ctx.needs_input_grad[0]:
             wk1t = conv_weight_dgrad(w1, dt, Op=Cip)
@@ -644,8 +687,9 @@ class UpCatFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = convT2x2_dgrad(dcat, wt, B, h, w, Ci, Co, H * W * Cc, Cc)
-        convT2x2_wgrad(x, dcat, gwt, B, h, w, Ci, Co, H * W * Cc, Cc)
-        channel_sum(dcat, gbt, B, H * W, Co, Co, ns=H * W * Cc, ps=Cc)
+        with side_stream(x, dcat):
+            convT2x2_wgrad(x, dcat, gwt, B, h, w, Ci, Co, H * W * Cc, Cc)
+            channel_sum(dcat, gbt, B, H * W, Co, Co, ns=H * W * Cc, ps=Cc)
         dskip = dcat[..., Co:] if ctx.needs_input_grad[1] else None     # view; consumer reads it strided
         return dx, dskip, rwt, rbt
 
@@ -731,6 +775,7 @@ class ConvLSTMFn(torch.autograd.Function):
         # dW[:, :Ci] — x frames may be time-strided, one launch per step; dW[:, Ci:] — one launch over t>=1
         contiguous = (st_t == B and st_b == 1)
         if K == 3:
+          with side_stream(dgates, x, h_all):       # the weight / bias gradients overlap the dx convolution below
             if contiguous:
                 conv3x3_wgrad(dgates, x, gw, T * B, H, W, 4 * Ch, Cip, Ci, Ci_tot=Ct)
             else:
@@ -739,6 +784,7 @@ class ConvLSTMFn(torch.autograd.Function):
                                   x_off=t * st_t * img)
             if T > 1:
                 conv3x3_wgrad(dgates[1:], h_all[:-1], gw, (T - 1) * B, H, W, 4 * Ch, Ch, Ch, Ci_tot=Ct, dw_off=Ci * KK)
+            channel_sum(dgates, gb, T * B, P, 4 * Ch, 4 * Ch)
         else:
             for t in range(T):
                 conv_wgrad(dgates[t], x, gw, Ct * KK, KK, 1, B, H, W, 4 * Ch, 4 * Ch, H, W, Cip, Ci, K, K, 1, pad,
@@ -746,7 +792,7 @@ class ConvLSTMFn(torch.autograd.Function):
             if T > 1:
                 conv_wgrad(dgates[1:], h_all[:-1], gw, Ct * KK, KK, 1, (T - 1) * B, H, W, 4 * Ch, 4 * Ch, H, W, Ch, Ch,
                            K, K, 1, pad, dw_off=Ci * KK)
-        channel_sum(dgates, gb, T * B, P, 4 * Ch, 4 * Ch)
+            channel_sum(dgates, gb, T * B, P, 4 * Ch, 4 * Ch)
         dx = None
         if ctx.needs_input_grad[0]:
             wxt = conv_weight_dgrad(w, dt, 0, Ci, Op=Cip)

@@ -38,17 +38,23 @@ class TrainStep:
         self.plan = ops.PackPlan()          # resident packed weights, refreshed by one launch per step
         fg = self.opt.flat_grad
         self.plan.grad_range = (fg.data_ptr(), fg.data_ptr() + fg.numel() * 4)
+        # optional (PCM_SIDE_STREAM=1): weight-gradient kernels on a second stream, forked / joined inside the step (also
+        # under graph capture).  Measured on B200: no gain — every kernel of the step already fills the SMs' shared
+        # memory, so the branches serialise — hence off by default.
+        import os
+        self.side = torch.cuda.Stream(device=self.device) if os.environ.get("PCM_SIDE_STREAM", "0") == "1" else None
         self.graph = None
         self.launches_per_step = 0
 
     # -- one eager step on the static buffers ---------------------------------------------------
     def _step_impl(self):
         self.opt.zero_grad()
-        with ops.use_pack_plan(self.plan):
+        with ops.use_pack_plan(self.plan, self.side):
             self.plan.repack()
             out = self.model(self.x)
             loss = ops.mse_loss(out, self.y)
             loss.backward()
+            ops.join_side()
             self.plan.unpack_grads()
         scale = allreduce_flat_grads(self.opt.flat_grad, self.opt.n_reduced, self.pg)
         self.opt.step(grad_scale=scale)

@@ -39,8 +39,10 @@ def _check(res, dtype, median=None):
         gn = res["gnorm"].get(k, 1.0)
         if gn <= 1e-7:
             # exactly-zero gradient in the oracle (dead unit, or a conv bias cancelled by the BatchNorm that follows):
-            # ours must be ~0 too — in bf16 up to the rounding noise of summing bf16-stored values
-            assert e < (1e-5 if dtype == torch.float32 else 1e-3), (k, e)
+            # ours must be ~0 too, i.e. no larger than the rounding residue of summing O(10^3..10^5) terms of
+            # magnitude ~1e-3 whose exact sum is zero (fp32 atomics in varying order: up to ~1e-5; bf16-stored
+            # terms: ~1e-4)
+            assert e < (1e-4 if dtype == torch.float32 else 1e-3), (k, e)
             continue
         errs.append(e)
         if dtype != torch.float32 and ".se.fc." in k or k.startswith("fc."):
