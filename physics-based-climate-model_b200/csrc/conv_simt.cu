@@ -40,14 +40,13 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
   const int O = (int)(j[5] & 0xffffffffll), I = (int)(j[5] >> 32);
   const int taps = (int)(j[6] & 0xffffffffll), Op = (int)(j[6] >> 32);
   const int Ip = (int)(j[7] & 0xffffffffll), dtype = (int)(j[7] >> 32);
-  const long long total = (long long)taps * Op * Ip;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx % Ip);
-    const int o = (int)((idx / Ip) % Op);
-    const int t = (int)(idx / ((long long)Ip * Op));
+  // 32-bit index arithmetic (the host checks the sizes): 64-bit div/mod was most of this kernel's time
+  const unsigned total = (unsigned)taps * Op * Ip, plane = (unsigned)Op * Ip;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned t = idx / plane, r = idx - t * plane;
+    const int o = (int)(r / (unsigned)Ip), i = (int)(r - (unsigned)o * Ip);
     float v = 0.f;
-    if (o < O && i < I) v = __ldg(w + o * so + i * si + t * st);
+    if (o < O && i < I) v = __ldg(w + o * so + i * si + (long long)t * st);
     if (dtype == PCM_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(out)[idx] = v;
   }
@@ -69,12 +68,10 @@ __global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long lo
   const long long sa = j[2], sb = j[3], st = j[4];
   const int Co = (int)(j[5] & 0xffffffffll), Ci = (int)(j[5] >> 32);
   const int Cpad = (int)(j[6] & 0xffffffffll), taps = (int)(j[6] >> 32);
-  const long long total = (long long)taps * Co * Cpad;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(idx % Cpad);
-    const int co = (int)((idx / Cpad) % Co);
-    const int t = (int)(idx / ((long long)Cpad * Co));
+  const unsigned total = (unsigned)taps * Co * Cpad, plane = (unsigned)Co * Cpad;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned t = idx / plane, r = idx - t * plane;
+    const int co = (int)(r / (unsigned)Cpad), ci = (int)(r - (unsigned)co * Cpad);
     const float v = packed[idx];
     packed[idx] = 0.f;
     if (ci < Ci && v != 0.f) dst[co * sa + ci * sb + t * st] += v;
@@ -314,7 +311,7 @@ extern "C" int pcm_pack_weights_batched(const long long* jobs, int njobs, long l
   if (njobs == 0 || max_elems == 0) return PCM_OK;
   long long bx = (max_elems + 511) / 512;
   if (bx > 148 * 4) bx = 148 * 4;
-  PCM_REQUIRE(njobs <= 512, "pack_weights_batched: at most 512 jobs per launch");
+  PCM_REQUIRE(njobs <= 512 && max_elems < (1ll << 31), "pack_weights_batched: at most 512 jobs of < 2^31 elements");
   pack_weights_batched_kernel<<<(unsigned)bx, 256, (size_t)njobs * 64, (cudaStream_t)s>>>(jobs, njobs);
   return check_launch("pack_weights_batched");
 }
@@ -324,7 +321,7 @@ extern "C" int pcm_unpack_grads_batched(const long long* jobs, int njobs, long l
   if (njobs == 0 || max_elems == 0) return PCM_OK;
   long long bx = (max_elems + 511) / 512;
   if (bx > 148 * 4) bx = 148 * 4;
-  PCM_REQUIRE(njobs <= 512, "unpack_grads_batched: at most 512 jobs per launch");
+  PCM_REQUIRE(njobs <= 512 && max_elems < (1ll << 31), "unpack_grads_batched: at most 512 jobs of < 2^31 elements");
   unpack_grads_batched_kernel<<<(unsigned)bx, 256, (size_t)njobs * 64, (cudaStream_t)s>>>(jobs, njobs);
   return check_launch("unpack_grads_batched");
 }

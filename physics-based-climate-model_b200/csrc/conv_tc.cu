@@ -41,9 +41,18 @@ struct ConvTcParams {
   const float* c_prev;    // [M][Ch] fp32
   float* c_out;           // [M][Ch] fp32
   __nv_bfloat16* acts;    // [M][4*Ch] bf16: activated gates i,f,o,g saved for backward
+  int ngroups;            // EPI == 1: hidden channels are split into ngroups = Ch/16 groups; a work item is (pixel tile,
+                          // group) and computes the 4 x 16 gate columns of its 16 hidden channels (4x more CTAs on the
+                          // 27-tile recurrent step, 4x less epilogue work each); EPI == 0: 1
 };
 
 constexpr int kThreads = 192;
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
 
 template <int KSTEPS, int EPI>   // KSTEPS = KC / 16 (UMMA K-steps per stage); EPI 0 = store, 1 = ConvLSTM cell
 __global__ void __launch_bounds__(kThreads, 1)
@@ -86,7 +95,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < p.num_tiles * p.ngroups && ok; item += gridDim.x) {
+        const int tile = item / p.ngroups, cgrp = item - tile * p.ngroups;
         const int tw = tile % p.tiles_w;
         const int th = (tile / p.tiles_w) % p.tiles_h;
         const int tn = tile / (p.tiles_w * p.tiles_h);
@@ -102,7 +112,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                           h0, n0);
             else
               tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + kw - kpad, h0 + kh - kpad, n0);
-            tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage], kc * p.KC, 0, tap);
+            if (EPI == 1) {
+              // the 16 rows of each gate (i, f, o, g) that belong to this hidden-channel group: four 16-row boxes
+              // land back to back as one 64-row B tile
+              const int Ch = p.Cout >> 2;
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq)
+                tma_load_3d(sB + (size_t)stage * p.b_stage_bytes + (size_t)gq * 16 * p.KC * 2, &tmB, &full[stage], kc * p.KC,
+                            gq * Ch + cgrp * 16, tap);
+            } else {
+              tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage], kc * p.KC, 0, tap);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -113,13 +133,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (elect_one()) {
       // The issuing thread is instruction-bound for small N: keep the loop to a handful of SASS
       // instructions per MMA (descriptors are start-address increments of two precomputed bases).
-      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(128, EPI == 1 ? 64 : p.Cout, 0, 0);
       constexpr uint32_t row_bytes = KSTEPS * 32;
       const uint32_t ltype = layout_type_for_row_bytes(row_bytes);
       const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 8 * row_bytes, ltype);
       const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 8 * row_bytes, ltype);
       const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
-      const int nstages = p.stages, ntiles = p.num_tiles, acc_stride = p.acc_stride;
+      const int nstages = p.stages, ntiles = p.num_tiles * p.ngroups, acc_stride = p.acc_stride;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -155,7 +175,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int mvalid = p.Wb * p.Hb * p.Nb;
     int it = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < p.num_tiles * p.ngroups && ok; item += gridDim.x, ++it) {
+      const int tile = item / p.ngroups, cgrp = item - tile * p.ngroups;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int tw = tile % p.tiles_w;
@@ -172,50 +193,51 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
       if (EPI == 1) {
         // gates = Wh.h (TMEM) + gx ; i,f,o = sigmoid, g = tanh ; c' = f*c + i*g ; h' = o*tanh(c')
-        // (src/convlstm.py:13-18) — the four gates of a hidden channel sit Ch columns apart in this row.
+        // (src/convlstm.py:13-18).  This work item owns hidden channels [c0, c0 + 16); its accumulator holds their
+        // i | f | o | g pre-activations in four 16-column blocks.  sigmoid / tanh use the one-instruction
+        // tanh.approx (rel. error ~2^-11, below the bf16 resolution the gates are stored in).
         const int Ch = p.Cout >> 2;
+        const int c0 = cgrp * 16;
         const long long m = ((long long)n * p.H + h) * p.W + w;
-        for (int c0 = 0; c0 < Ch; c0 += 16) {
-          float gi[16], gf[16], go[16], gg[16];
-          tmem_ld16(t_addr + c0, gi);
-          tmem_ld16(t_addr + Ch + c0, gf);
-          tmem_ld16(t_addr + 2 * Ch + c0, go);
-          tmem_ld16(t_addr + 3 * Ch + c0, gg);
-          if (valid) {
-            const float* gxp = p.gx + m * p.Cout + c0;
-            const float* cp = p.c_prev + m * Ch + c0;
-            float* cq = p.c_out + m * Ch + c0;
-            __nv_bfloat16* ap = p.acts + m * p.Cout + c0;
-            __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(dst) + m * Ch + c0;
-            float cn[16], hn[16];
+        float gi[16], gf[16], go[16], gg[16];
+        tmem_ld16(t_addr, gi);
+        tmem_ld16(t_addr + 16, gf);
+        tmem_ld16(t_addr + 32, go);
+        tmem_ld16(t_addr + 48, gg);
+        if (valid) {
+          const float* gxp = p.gx + m * p.Cout + c0;
+          const float* cp = p.c_prev + m * Ch + c0;
+          float* cq = p.c_out + m * Ch + c0;
+          __nv_bfloat16* ap = p.acts + m * p.Cout + c0;
+          __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(dst) + m * Ch + c0;
+          float cn[16], hn[16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 xi = *reinterpret_cast<const float4*>(gxp + j);
-              const float4 xf = *reinterpret_cast<const float4*>(gxp + Ch + j);
-              const float4 xo = *reinterpret_cast<const float4*>(gxp + 2 * Ch + j);
-              const float4 xg = *reinterpret_cast<const float4*>(gxp + 3 * Ch + j);
-              const float4 cc = *reinterpret_cast<const float4*>(cp + j);
-              const float xi_[4] = {xi.x, xi.y, xi.z, xi.w}, xf_[4] = {xf.x, xf.y, xf.z, xf.w};
-              const float xo_[4] = {xo.x, xo.y, xo.z, xo.w}, xg_[4] = {xg.x, xg.y, xg.z, xg.w};
-              const float cc_[4] = {cc.x, cc.y, cc.z, cc.w};
+          for (int j = 0; j < 16; j += 4) {
+            const float4 xi = *reinterpret_cast<const float4*>(gxp + j);
+            const float4 xf = *reinterpret_cast<const float4*>(gxp + Ch + j);
+            const float4 xo = *reinterpret_cast<const float4*>(gxp + 2 * Ch + j);
+            const float4 xg = *reinterpret_cast<const float4*>(gxp + 3 * Ch + j);
+            const float4 cc = *reinterpret_cast<const float4*>(cp + j);
+            const float xi_[4] = {xi.x, xi.y, xi.z, xi.w}, xf_[4] = {xf.x, xf.y, xf.z, xf.w};
+            const float xo_[4] = {xo.x, xo.y, xo.z, xo.w}, xg_[4] = {xg.x, xg.y, xg.z, xg.w};
+            const float cc_[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float a_i = round_to<__nv_bfloat16>(sigmoidf_(gi[j + k] + xi_[k]));
-                const float a_f = round_to<__nv_bfloat16>(sigmoidf_(gf[j + k] + xf_[k]));
-                const float a_o = round_to<__nv_bfloat16>(sigmoidf_(go[j + k] + xo_[k]));
-                const float a_g = round_to<__nv_bfloat16>(tanhf(gg[j + k] + xg_[k]));
-                gi[j + k] = a_i; gf[j + k] = a_f; go[j + k] = a_o; gg[j + k] = a_g;
-                cn[j + k] = fmaf(a_f, cc_[k], a_i * a_g);
-                hn[j + k] = a_o * tanhf(cn[j + k]);
-              }
+            for (int k = 0; k < 4; ++k) {
+              const float a_i = round_to<__nv_bfloat16>(fmaf(0.5f, tanh_approx(0.5f * (gi[j + k] + xi_[k])), 0.5f));
+              const float a_f = round_to<__nv_bfloat16>(fmaf(0.5f, tanh_approx(0.5f * (gf[j + k] + xf_[k])), 0.5f));
+              const float a_o = round_to<__nv_bfloat16>(fmaf(0.5f, tanh_approx(0.5f * (go[j + k] + xo_[k])), 0.5f));
+              const float a_g = round_to<__nv_bfloat16>(tanh_approx(gg[j + k] + xg_[k]));
+              gi[j + k] = a_i; gf[j + k] = a_f; go[j + k] = a_o; gg[j + k] = a_g;
+              cn[j + k] = fmaf(a_f, cc_[k], a_i * a_g);
+              hn[j + k] = a_o * tanh_approx(cn[j + k]);
             }
-            store8(ap, gi); store8(ap + 8, gi + 8);
-            store8(ap + Ch, gf); store8(ap + Ch + 8, gf + 8);
-            store8(ap + 2 * Ch, go); store8(ap + 2 * Ch + 8, go + 8);
-            store8(ap + 3 * Ch, gg); store8(ap + 3 * Ch + 8, gg + 8);
-            store8(cq, cn); store8(cq + 8, cn + 8);
-            store8(hp, hn); store8(hp + 8, hn + 8);
           }
+          store8(ap, gi); store8(ap + 8, gi + 8);
+          store8(ap + Ch, gf); store8(ap + Ch + 8, gf + 8);
+          store8(ap + 2 * Ch, go); store8(ap + 2 * Ch + 8, go + 8);
+          store8(ap + 3 * Ch, gg); store8(ap + 3 * Ch + 8, gg + 8);
+          store8(cq, cn); store8(cq + 8, cn + 8);
+          store8(hp, hn); store8(hp + 8, hn + 8);
         }
       } else
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
@@ -633,14 +655,15 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   p.ksz = ksz; p.relu = relu; p.mode = mode; p.ps_co = ps_co;
   const int ntaps = mode == 1 ? 4 : ksz * ksz;
   p.dst_ns = dst_ns; p.dst_ps = dst_ps; p.dst_f32 = dst_f32; p.accumulate = accumulate;
-  p.acc_stride = Cout < 32 ? 32 : Cout;
+  const int ncols = lstm_gx != nullptr ? 64 : Cout;        // accumulator columns per work item (fused ConvLSTM: 4 x 16)
+  p.acc_stride = ncols < 32 ? 32 : ncols;
   uint32_t cols = 32;
   while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   p.a_stage_bytes = 128u * p.KC * 2;
-  p.b_stage_bytes = ((uint32_t)Cout * p.KC * 2 + 1023u) & ~1023u;
+  p.b_stage_bytes = ((uint32_t)ncols * p.KC * 2 + 1023u) & ~1023u;
   p.a_tx_bytes = (uint32_t)(p.Wb * p.Hb * p.Nb) * p.KC * 2;
-  p.b_tx_bytes = (uint32_t)Cout * p.KC * 2;
+  p.b_tx_bytes = (uint32_t)ncols * p.KC * 2;
   const size_t per_stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
   int stages = (int)((200 * 1024) / per_stage);
   if (stages > 8) stages = 8;
@@ -671,10 +694,11 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
     uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-    uint32_t box[3] = {(uint32_t)p.KC, (uint32_t)Cout, 1};
+    uint32_t box[3] = {(uint32_t)p.KC, (uint32_t)(lstm_gx != nullptr ? 16 : Cout), 1};
     int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, p.KC * 2);
     if (rc != PCM_OK) return rc;
   }
+  p.ngroups = lstm_gx != nullptr ? (Cout >> 2) / 16 : 1;
   p.gx = lstm_gx; p.c_prev = lstm_c_prev; p.c_out = lstm_c_out; p.acts = reinterpret_cast<__nv_bfloat16*>(lstm_acts);
   const int ksi = (p.KC == 16 ? 0 : p.KC == 32 ? 1 : 2) + (lstm_gx != nullptr ? 3 : 0);
   auto kern = ksi == 0 ? conv3x3_tc_kernel<1, 0> : ksi == 1 ? conv3x3_tc_kernel<2, 0> : ksi == 2 ? conv3x3_tc_kernel<4, 0>
@@ -685,7 +709,8 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     if (e != cudaSuccess) { set_error("conv3x3_tc: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
     smem_set[ksi] = smem;
   }
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  const int nitems = p.num_tiles * p.ngroups;
+  const int grid = nitems < g_num_sms ? nitems : g_num_sms;
   kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmA2, tmB, dst, bias, err, p);
   return check_launch("conv3x3_tc");
 }
