@@ -211,7 +211,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PCM_NCCL_DEBUG", "WARN")   # keep stdout to the ONE JSON line
+        # keep stdout to the ONE JSON line: any NCCL_DEBUG level (even WARN) makes NCCL print its version banner
+        if "PCM_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["PCM_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_src = load_peaks()
 

@@ -77,7 +77,7 @@ class PackPlan:
         # weight-gradient kernel) and the ONE launch that folds them into the parameter-layout gradients
         self.grad_range = None     # (first byte, one-past-last byte) of the optimizer's flat gradient buffer
         self.gentries = {}         # (dst ptr, Co, Ci_tot, taps) -> (packed tensor, job record)
-        self.gtable = None
+        self.gtables = {}
         self.gdirty = False
         self.gmax = 0
 
@@ -122,16 +122,26 @@ class PackPlan:
             self.gdirty = True
         return e[0]
 
-    def unpack_grads(self):
+    def unpack_grads(self, lo: Optional[int] = None, hi: Optional[int] = None):
+        """Fold the packed buffers into the parameter-layout gradients (one launch).  lo/hi (byte addresses inside
+        the flat gradient buffer) restrict the launch to the parameters of one all-reduce bucket."""
         if not self.gentries:
             return
         if self.gdirty:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("PackPlan: packed-gradient table changed during graph capture")
-            dev = next(iter(self.gentries.values()))[0].device
-            self.gtable = torch.tensor([j for _, j in self.gentries.values()], dtype=torch.int64).to(dev)
+            self.gtables = {}
             self.gdirty = False
-        _call("pcm_unpack_grads_batched", self.gtable.data_ptr(), len(self.gentries), self.gmax, _s())
+        key = (lo, hi)
+        if key not in self.gtables:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PackPlan: packed-gradient bucket requested for the first time during capture")
+            jobs = [j for _, j in self.gentries.values() if (lo is None or j[1] >= lo) and (hi is None or j[1] < hi)]
+            dev = next(iter(self.gentries.values()))[0].device
+            self.gtables[key] = (torch.tensor(jobs, dtype=torch.int64).reshape(-1, 8).to(dev), len(jobs))
+        table, n = self.gtables[key]
+        if n:
+            _call("pcm_unpack_grads_batched", table.data_ptr(), n, self.gmax, _s())
 
 
 _PLAN: Optional[PackPlan] = None
@@ -162,6 +172,31 @@ class side_stream:
         if self.ctx is not None:
             self.ctx.__exit__(*exc)
         return False
+
+
+_GRAD_HOOKS = {}          # name -> callable, fired from backward when the gradient at that point has been computed
+
+
+class GradReadyFn(torch.autograd.Function):
+    """Identity whose backward fires the trainer's hook `name`: placed on the ConvLSTM input, it marks the moment in
+    backward at which every decoder / head / ConvLSTM weight gradient has been enqueued — the trainer then starts
+    the all-reduce of that bucket so that it overlaps the encoder's backward."""
+
+    @staticmethod
+    def forward(ctx, x, name):
+        ctx.name = name
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        fn = _GRAD_HOOKS.get(ctx.name)
+        if fn is not None:
+            fn()
+        return g, None
+
+
+def grad_ready_hook(x, name: str):
+    return GradReadyFn.apply(x, name) if (x.requires_grad and name in _GRAD_HOOKS) else x
 
 
 def side_active() -> bool:

@@ -67,6 +67,7 @@ class AttUNetConvLSTM(nn.Module):
         s3 = self.enc3.conv.forward_nhwc(p2)
         p3, k3 = ops.PoolSkipFn.apply(s3, T)
         s4 = self.enc4.conv.forward_nhwc(p3)
+        s4 = ops.grad_ready_hook(s4, "encoder_boundary")     # data-parallel trainer: first gradient bucket is complete here
         bott = self.convlstm.forward_nhwc(s4, T, B, st_t=B, st_b=1, last_only=True)
         d3 = self.up3.forward_nhwc(bott, k3)
         d2 = self.up2.forward_nhwc(d3, k2)

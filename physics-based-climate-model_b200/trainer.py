@@ -11,6 +11,7 @@ the all-reduce of the flat gradient buffer (`post_conv`'s never-used parameters 
 and are excluded — SURVEY F5)."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -41,22 +42,53 @@ class TrainStep:
         # optional (PCM_SIDE_STREAM=1): weight-gradient kernels on a second stream, forked / joined inside the step (also
         # under graph capture).  Measured on B200: no gain — every kernel of the step already fills the SMs' shared
         # memory, so the branches serialise — hence off by default.
-        import os
         self.side = torch.cuda.Stream(device=self.device) if os.environ.get("PCM_SIDE_STREAM", "0") == "1" else None
+        # two all-reduce buckets (world > 1): [split, n_reduced) = ConvLSTM + decoder + head, complete when backward
+        # reaches the encoder boundary and reduced while the encoder's backward runs; [0, split) = encoder, at the end
+        self.split = 0
+        if self.world > 1 and hasattr(model, "convlstm") and os.environ.get("PCM_OVERLAP_ALLREDUCE", "1") != "0":
+            first = next(model.convlstm.parameters())
+            self.split = (first.main_grad.data_ptr() - fg.data_ptr()) // 4
+        self._early_work = None
         self.graph = None
         self.launches_per_step = 0
 
     # -- one eager step on the static buffers ---------------------------------------------------
+    def _early_bucket(self):
+        """Backward has reached the encoder boundary: fold and all-reduce the ConvLSTM/decoder/head gradients now
+        (asynchronously — the NCCL kernel overlaps the encoder's backward)."""
+        fg = self.opt.flat_grad
+        ops.join_side()
+        self.plan.unpack_grads(fg.data_ptr() + 4 * self.split, fg.data_ptr() + 4 * fg.numel())
+        self._early_work = dist.all_reduce(fg[self.split:self.opt.n_reduced], op=dist.ReduceOp.SUM, group=self.pg,
+                                           async_op=True)
+
     def _step_impl(self):
         self.opt.zero_grad()
-        with ops.use_pack_plan(self.plan, self.side):
-            self.plan.repack()
-            out = self.model(self.x)
-            loss = ops.mse_loss(out, self.y)
-            loss.backward()
-            ops.join_side()
-            self.plan.unpack_grads()
-        scale = allreduce_flat_grads(self.opt.flat_grad, self.opt.n_reduced, self.pg)
+        fg = self.opt.flat_grad
+        overlap = self.split > 0
+        if overlap:
+            ops._GRAD_HOOKS["encoder_boundary"] = self._early_bucket
+        try:
+            with ops.use_pack_plan(self.plan, self.side):
+                self.plan.repack()
+                out = self.model(self.x)
+                loss = ops.mse_loss(out, self.y)
+                loss.backward()
+                ops.join_side()
+                if overlap:
+                    self.plan.unpack_grads(fg.data_ptr(), fg.data_ptr() + 4 * self.split)
+                else:
+                    self.plan.unpack_grads()
+        finally:
+            ops._GRAD_HOOKS.pop("encoder_boundary", None)
+        if overlap:
+            dist.all_reduce(fg[:self.split], op=dist.ReduceOp.SUM, group=self.pg)
+            self._early_work.wait()
+            self._early_work = None
+            scale = 1.0 / self.world
+        else:
+            scale = allreduce_flat_grads(fg, self.opt.n_reduced, self.pg)
         self.opt.step(grad_scale=scale)
         self.loss.copy_(loss.detach())
 
