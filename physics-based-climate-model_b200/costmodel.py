@@ -17,9 +17,9 @@ def algo_cost(name: str, args):
     """-> (flops, bytes, bound) with bound in {"tensor", "hbm"}; (0, 0, "hbm") for unknown calls."""
     a = _named(name, args)
     es = lambda: 2 if a.get("dtype", 1) == 1 else 4          # activation element size
-    if name == "pcm_conv3x3_tc":
+    if name in ("pcm_conv3x3_tc", "pcm_conv1x1_tc"):
         px = a["N"] * a["H"] * a["W"]
-        taps = a.get("taps", 9)
+        taps = 9 if name == "pcm_conv3x3_tc" else 1
         fl = 2.0 * px * a["Cin"] * a["Cout"] * taps
         osz = 4 if a["dst_f32"] else 2
         by = px * (a["Cin"] * 2 + a["Cout"] * osz * (2 if a["accumulate"] else 1)) + taps * a["Cin"] * a["Cout"] * 2
@@ -31,16 +31,48 @@ def algo_cost(name: str, args):
         # h_prev bf16 + gx fp32 [4Ch] + c_prev fp32 in; h bf16 + c fp32 + acts bf16 [4Ch] out
         by = px * (Ch * 2 + 4 * Ch * 4 + Ch * 4 + Ch * 2 + Ch * 4 + 4 * Ch * 2) + 9 * Ch * 4 * Ch * 2
         return fl, by, "tensor"
-    if name == "pcm_wgrad3x3_tc":
+    if name in ("pcm_wgrad3x3_tc", "pcm_wgrad1x1_tc"):
         px = a["N"] * a["H"] * a["W"]
-        taps = a.get("taps", 9)
+        taps = 9 if name == "pcm_wgrad3x3_tc" else 1
         fl = 2.0 * px * a["Co"] * a["Ci"] * taps
         by = px * (a["Co"] + a["Ci"]) * 2 + taps * a["Co_real"] * a["Ci_real"] * 4
         return fl, by, "tensor"
-    if name == "pcm_gemm_tc":
-        fl = 2.0 * a["M"] * a["N"] * a["K"]
-        by = a["M"] * a["K"] * 2 + a["N"] * a["K"] * 2 + a["M"] * a["N"] * (4 if a.get("dst_f32") else 2)
-        return fl, by, "tensor"
+    if name == "pcm_convT2x2_tc":          # H, W = input grid; output has 4x the pixels
+        px = a["N"] * a["H"] * a["W"]
+        return 2.0 * px * a["Cin"] * 4 * a["Cout"], px * (a["Cin"] + 4 * a["Cout"]) * 2 + 4 * a["Cin"] * a["Cout"] * 2, "tensor"
+    if name == "pcm_convT2x2_dgrad_tc":
+        px = a["N"] * a["H"] * a["W"]
+        return 2.0 * px * a["Cin"] * 4 * a["Cout"], px * (a["Cin"] + 4 * a["Cout"]) * 2 + 4 * a["Cin"] * a["Cout"] * 2, "tensor"
+    if name == "pcm_convT2x2_wgrad_tc":
+        px = a["N"] * a["H"] * a["W"]
+        return 2.0 * px * a["Ca"] * 4 * a["Cb"], px * (a["Ca"] + 4 * a["Cb"]) * 2 + 4 * a["Ca_real"] * a["Cb_real"] * 4, "tensor"
+    # per-image fused ConvBlock tails: every tensor once (x in, y out; backward: dout + x in, dx out)
+    if name in ("pcm_gn_silu_img_fwd", "pcm_convblock_tail_fwd"):
+        return 0.0, 2 * a["N"] * a["H"] * a["W"] * a["C"] * es(), "hbm"
+    if name in ("pcm_gn_silu_img_bwd", "pcm_convblock_tail_bwd"):
+        return 0.0, 3 * a["N"] * a["H"] * a["W"] * a["C"] * es(), "hbm"
+    if name in ("pcm_bn_stats",):
+        return 0.0, a["R"] * a["C"] * es(), "hbm"
+    if name in ("pcm_bn_apply_fwd",):
+        return 0.0, (3 if a["res"] else 2) * a["R"] * a["C"] * es(), "hbm"
+    if name == "pcm_bn_bwd_reduce":
+        return 0.0, (3 if a["y"] else 2) * a["R"] * a["C"] * es(), "hbm"
+    if name == "pcm_bn_bwd_apply":
+        return 0.0, (3 + (1 if a["y"] else 0) + (1 if a["dres"] else 0)) * a["R"] * a["C"] * es(), "hbm"
+    if name in ("pcm_add", "pcm_relu_bwd"):
+        return 0.0, 3 * a["n"] * es(), "hbm"
+    if name in ("pcm_dropout", "pcm_add_bcast"):
+        return 0.0, 2 * a["n"] * es(), "hbm"
+    if name == "pcm_add_layernorm_fwd":
+        return 0.0, a["M"] * a["E"] * es() * (2 + (1 if a["b"] else 0) + (1 if a["sum_out"] else 0)), "hbm"
+    if name == "pcm_layernorm_bwd":
+        return 0.0, 3 * a["M"] * a["E"] * es(), "hbm"
+    if name in ("pcm_mha_fwd", "pcm_mha_bwd"):
+        E = a["nh"] * a["D"]
+        k = 1 if name == "pcm_mha_fwd" else 2.5
+        return 4.0 * a["B"] * a["nh"] * a["L"] * a["L"] * a["D"] * k, a["B"] * a["L"] * E * es() * (4 if k == 1 else 8), "tensor"
+    if name in ("pcm_pack_weights_batched", "pcm_unpack_grads_batched"):
+        return 0.0, 0.0, "hbm"             # sizes live in the device-side job table
     if name == "pcm_conv_gather":
         taps = a["KH"] * a["KW"]
         if a["mode"] == 1 or a["stride"] > 1:
