@@ -306,3 +306,59 @@ def case_dropout_stats():
     whole = bool(((per_ch == per_ch[:, :1, :]).all()))
     keep2 = float((per_ch[:, 0, :] != 0).float().mean())
     return {"keep": keep, "same_mask": same, "scale": scale, "whole_channels": whole, "keep2d": keep2}
+
+
+def case_config5_geometry():
+    """BASELINE configs[4] geometry (1-degree grid 180x360 zero-padded to 184x360, base channels x2), tiny batch: the
+    tensor-core convolutions take the large grid (TMA boxes, tile chooser), the ConvBlock tails fall back to the
+    grid-wide kernels (an image no longer fits an SM), the weight gradients of the 360-wide levels to the SIMT kernel.
+    Self-consistency against the fp64 oracle on the same inputs."""
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    B, T, H, W, base = 1, 2, 184, 360, 32
+    sd = O.synth_state_dict(O.attunet_spec(7, 2, base), 191)
+    x, y, _ = O.synth_attunet_batch(B, T, H, W, 192)
+    mod = AttUNetConvLSTM(7, 2, base, seq_len=T)
+    return compare(mod, O.attunet_convlstm, sd, x, y, torch.bfloat16)
+
+
+def case_simplecnn_eval():
+    """model.eval(): BatchNorm uses the running statistics, Dropout2d is the identity (src/models.py:114-123 under
+    Lightning's validation loop) — against torch's functional batch_norm with the same buffers."""
+    import torch.nn.functional as F
+    from pcm_b200.src.models import SimpleCNN
+    sd = O.synth_state_dict(O.simplecnn_spec(5, 2, 3, 16, 3), 201)
+    mod = SimpleCNN(5, 2, kernel_size=3, init_dim=16, depth=3, dropout_rate=0.2)
+    full = _buffers_state(sd, mod)
+    g = torch.Generator().manual_seed(202)
+    for k in list(full.keys()):
+        if k.endswith("running_mean"):
+            full[k] = torch.randn(full[k].shape, generator=g) * 0.3
+        elif k.endswith("running_var"):
+            full[k] = torch.rand(full[k].shape, generator=g) + 0.5
+    mod.load_state_dict(full)
+    mod = mod.to(DEV).eval()
+    x, _ = O.synth_frame_batch(3, 5, 16, 24, 203)
+    set_compute_dtype(torch.float32)
+    try:
+        with torch.no_grad():
+            out = mod(x.to(DEV)).cpu()
+    finally:
+        set_compute_dtype(torch.bfloat16)
+
+    def bn(t, p):
+        return F.batch_norm(t, full[p + "running_mean"].double(), full[p + "running_var"].double(),
+                            full[p + "weight"].double(), full[p + "bias"].double(), False, 0.1, 1e-5)
+
+    def conv(t, p, pad):
+        return F.conv2d(t, full[p + "weight"].double(), full[p + "bias"].double(), padding=pad)
+
+    t = F.relu(bn(conv(x.double(), "initial.0.", 1), "initial.1."))
+    for i in range(3):
+        p = f"res_blocks.{i}."
+        o = F.relu(bn(conv(t, p + "conv1.", 1), p + "bn1."))
+        o = bn(conv(o, p + "conv2.", 1), p + "bn2.")
+        idt = bn(conv(t, p + "skip.0.", 0), p + "skip.1.") if (p + "skip.0.weight") in full else t
+        t = F.relu(o + idt)
+    t = F.relu(bn(conv(t, "final.0.", 1), "final.1."))
+    want = conv(t, "final.3.", 0)
+    return {"out": rel_l2(out.numpy(), want.numpy())}

@@ -99,6 +99,18 @@ def test_full_size_tensor_core_paths(G, kind):
     _check(r, torch.bfloat16, median=SIMPLECNN_BF16_MEDIAN if kind == "simplecnn" else None)
 
 
+def test_config5_geometry(G):
+    """BASELINE configs[4]: 184x360 grid, base 32 — kernels beyond the shared-memory-resident regime."""
+    from pcm_b200._lib import lib
+    r = G.case_config5_geometry()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    _check(r, torch.bfloat16)
+
+
+def test_simplecnn_eval_mode(G):
+    assert G.case_simplecnn_eval()["out"] < 1e-4
+
+
 def test_dropout_masks(G):
     r = G.case_dropout_stats()
     assert abs(r["keep"] - 0.8) < 0.01 and r["same_mask"] and abs(r["scale"] - 1.25) < 1e-2, r
