@@ -58,16 +58,18 @@ PCM_API int pcm_season_embed_stage(const float* x5, const int* month, void* y, i
 PCM_API int pcm_pack_weight(const float* w, long long so, long long si, long long st, int O, int I, int taps, int Op,
                     int Ip, void* out, int dtype, pcm_stream_t s);
 
-/* every re-pack of a training step in ONE launch.  jobs: device array of njobs records of 8 x int64:
+/* every re-pack of a training step in ONE launch.  jobs: device array of records of 8 x int64:
  * {w ptr, out ptr, so, si, st, O | I<<32, taps | Op<<32, Ip | dtype<<32} (same meaning as pcm_pack_weight);
- * max_elems = the largest taps*Op*Ip among them (sizes the grid). */
-PCM_API int pcm_pack_weights_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s);
+ * work: device array of nwork (job, block) int32 pairs — block b of job j covers elements [1024 b, 1024 b + 1024)
+ * of that job's taps*Op*Ip outputs, so that all jobs proceed in parallel. */
+PCM_API int pcm_pack_weights_batched(const long long* jobs, const int* work, int nwork, pcm_stream_t s);
 
 /* packed weight gradients -> parameter layout, all layers in ONE launch (and the packed buffers are re-zeroed):
- * dst[co*sa + ci*sb + tap*st] += packed[(tap*Co + co)*Cpad + ci].  jobs: njobs records of 8 x int64:
- * {packed ptr, dst ptr, sa, sb, st, Co | Ci_real<<32, Cpad | taps<<32, 0}; max_elems = largest taps*Co*Cpad.
+ * dst[co*sa + ci*sb + tap*st] += packed[(tap*Co + co)*Cpad + ci].  jobs: records of 8 x int64:
+ * {packed ptr, dst ptr, sa, sb, st, Co | Ci_real<<32, Cpad | taps<<32, 0}; work: nwork (job, co) int32 pairs — one
+ * CTA per output channel of each job (taps*Cpad <= 4608).
  * pcm_wgrad3x3_tc reduces into such a buffer with 16-byte vector atomics when called with sb == 1. */
-PCM_API int pcm_unpack_grads_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s);
+PCM_API int pcm_unpack_grads_batched(const long long* jobs, const int* work, int nwork, pcm_stream_t s);
 
 /* ---- convolution family (nn.Conv2d / nn.ConvTranspose2d call sites: src/convlstm.py:9,13;
  * src/unet.py:36,38,63; src/cnn_transformer.py:10,12,36,38; src/models.py:47,50,57,90,108).

@@ -26,57 +26,70 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, long long so, lo
 // All weight re-packs of a training step in ONE launch: blockIdx.y = job, the x-grid strides over that job's
 // elements.  Job record (8 x int64, device memory): w ptr, out ptr, so, si, st, (O | I << 32), (taps | Op << 32),
 // (Ip | dtype << 32).
-__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs, int njobs) {
- // every block sweeps all jobs; the job table is staged in shared memory first (reading each record from global
- // memory inside the sweep serialises ~1 us of latency per job)
- extern __shared__ long long sjobs[];
- for (int i = threadIdx.x; i < njobs * 8; i += blockDim.x) sjobs[i] = jobs[i];
- __syncthreads();
- for (int job = 0; job < njobs; ++job) {
-  const long long* j = sjobs + job * 8;
+// Work item = (job, 1024-element block of that job): blockIdx.x indexes the flattened work list the host built, so
+// every job proceeds in parallel (a per-thread sweep over the jobs serialises ~2 us of memory latency per job).
+constexpr int kBatchBlockElems = 1024;
+
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs,
+                                                                    const int* __restrict__ work) {
+  const int job = work[2 * blockIdx.x], blk = work[2 * blockIdx.x + 1];
+  const long long* j = jobs + (long long)job * 8;
   const float* w = reinterpret_cast<const float*>(j[0]);
   void* out = reinterpret_cast<void*>(j[1]);
   const long long so = j[2], si = j[3], st = j[4];
   const int O = (int)(j[5] & 0xffffffffll), I = (int)(j[5] >> 32);
   const int taps = (int)(j[6] & 0xffffffffll), Op = (int)(j[6] >> 32);
   const int Ip = (int)(j[7] & 0xffffffffll), dtype = (int)(j[7] >> 32);
-  // 32-bit index arithmetic (the host checks the sizes): 64-bit div/mod was most of this kernel's time
   const unsigned total = (unsigned)taps * Op * Ip, plane = (unsigned)Op * Ip;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const unsigned t = idx / plane, r = idx - t * plane;
-    const int o = (int)(r / (unsigned)Ip), i = (int)(r - (unsigned)o * Ip);
+#pragma unroll
+  for (int r = 0; r < kBatchBlockElems / 256; ++r) {
+    const unsigned idx = (unsigned)blk * kBatchBlockElems + r * 256 + threadIdx.x;
+    if (idx >= total) break;
+    const unsigned t = idx / plane, rem = idx - t * plane;
+    const int o = (int)(rem / (unsigned)Ip), i = (int)(rem - (unsigned)o * Ip);
     float v = 0.f;
     if (o < O && i < I) v = __ldg(w + o * so + i * si + (long long)t * st);
     if (dtype == PCM_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(out)[idx] = v;
   }
- }
 }
 
 // Packed weight gradients [tap][Co][Cpad] (what the tensor-core weight-gradient kernel reduces into with vector
 // atomics) -> the parameter's own layout: dst[co*sa + ci*sb + tap*st] += packed[(tap*Co + co)*Cpad + ci]; the packed
 // buffer is zeroed on the way (ready for the next step).  blockIdx.y = job.  Job record (8 x int64): packed ptr,
 // dst ptr, sa, sb, st, (Co | Ci_real << 32), (Cpad | taps << 32), unused.
-__global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long long* __restrict__ jobs, int njobs) {
- extern __shared__ long long sjobs[];
- for (int i = threadIdx.x; i < njobs * 8; i += blockDim.x) sjobs[i] = jobs[i];
- __syncthreads();
- for (int job = 0; job < njobs; ++job) {
-  const long long* j = sjobs + job * 8;
+// Work item = (job, co): the [taps][Cpad] slab of one output channel is staged through shared memory so that both
+// the packed reads (rows of Cpad floats) and the parameter-layout read-modify-writes (taps*Ci contiguous floats when
+// sb == taps, st == 1 — every conv / convT weight) are coalesced.
+__global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long long* __restrict__ jobs,
+                                                                    const int* __restrict__ work) {
+  extern __shared__ float slab[];       // [taps][Cpad]
+  const int job = work[2 * blockIdx.x], co = work[2 * blockIdx.x + 1];
+  const long long* j = jobs + (long long)job * 8;
   float* packed = reinterpret_cast<float*>(j[0]);
   float* dst = reinterpret_cast<float*>(j[1]);
   const long long sa = j[2], sb = j[3], st = j[4];
   const int Co = (int)(j[5] & 0xffffffffll), Ci = (int)(j[5] >> 32);
   const int Cpad = (int)(j[6] & 0xffffffffll), taps = (int)(j[6] >> 32);
-  const unsigned total = (unsigned)taps * Co * Cpad, plane = (unsigned)Co * Cpad;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const unsigned t = idx / plane, r = idx - t * plane;
-    const int co = (int)(r / (unsigned)Cpad), ci = (int)(r - (unsigned)co * Cpad);
-    const float v = packed[idx];
-    packed[idx] = 0.f;
-    if (ci < Ci && v != 0.f) dst[co * sa + ci * sb + t * st] += v;
+  for (int i = threadIdx.x; i < taps * Cpad; i += blockDim.x) {
+    const int t = i / Cpad, ci = i - t * Cpad;
+    float* p = packed + ((long long)t * Co + co) * Cpad + ci;
+    slab[i] = *p;
+    *p = 0.f;
   }
- }
+  __syncthreads();
+  float* d = dst + (long long)co * sa;
+  if (sb == taps && st == 1) {
+    for (int i = threadIdx.x; i < Ci * taps; i += blockDim.x) {
+      const int ci = i / taps, t = i - ci * taps;
+      d[i] += slab[t * Cpad + ci];
+    }
+  } else {
+    for (int i = threadIdx.x; i < Ci * taps; i += blockDim.x) {
+      const int ci = i / taps, t = i - ci * taps;
+      d[ci * sb + t * st] += slab[t * Cpad + ci];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -306,23 +319,18 @@ extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long 
   return check_launch("pack_weight");
 }
 
-extern "C" int pcm_pack_weights_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
-  PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "pack_weights_batched: bad arguments");
-  if (njobs == 0 || max_elems == 0) return PCM_OK;
-  long long bx = (max_elems + 511) / 512;
-  if (bx > 148 * 4) bx = 148 * 4;
-  PCM_REQUIRE(njobs <= 512 && max_elems < (1ll << 31), "pack_weights_batched: at most 512 jobs of < 2^31 elements");
-  pack_weights_batched_kernel<<<(unsigned)bx, 256, (size_t)njobs * 64, (cudaStream_t)s>>>(jobs, njobs);
+extern "C" int pcm_pack_weights_batched(const long long* jobs, const int* work, int nwork, pcm_stream_t s) {
+  PCM_REQUIRE(jobs != nullptr && work != nullptr && nwork >= 0, "pack_weights_batched: bad arguments");
+  if (nwork == 0) return PCM_OK;
+  pack_weights_batched_kernel<<<(unsigned)nwork, 256, 0, (cudaStream_t)s>>>(jobs, work);
   return check_launch("pack_weights_batched");
 }
 
-extern "C" int pcm_unpack_grads_batched(const long long* jobs, int njobs, long long max_elems, pcm_stream_t s) {
-  PCM_REQUIRE(jobs != nullptr && njobs >= 0 && max_elems >= 0, "unpack_grads_batched: bad arguments");
-  if (njobs == 0 || max_elems == 0) return PCM_OK;
-  long long bx = (max_elems + 511) / 512;
-  if (bx > 148 * 4) bx = 148 * 4;
-  PCM_REQUIRE(njobs <= 512 && max_elems < (1ll << 31), "unpack_grads_batched: at most 512 jobs of < 2^31 elements");
-  unpack_grads_batched_kernel<<<(unsigned)bx, 256, (size_t)njobs * 64, (cudaStream_t)s>>>(jobs, njobs);
+extern "C" int pcm_unpack_grads_batched(const long long* jobs, const int* work, int nwork, pcm_stream_t s) {
+  PCM_REQUIRE(jobs != nullptr && work != nullptr && nwork >= 0, "unpack_grads_batched: bad arguments");
+  if (nwork == 0) return PCM_OK;
+  // dynamic shared memory: the largest [taps][Cpad] slab the library produces (9 x 512 floats)
+  unpack_grads_batched_kernel<<<(unsigned)nwork, 256, 9 * 512 * sizeof(float), (cudaStream_t)s>>>(jobs, work);
   return check_launch("unpack_grads_batched");
 }
 

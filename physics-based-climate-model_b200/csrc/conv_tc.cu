@@ -304,12 +304,15 @@ struct ConvHaloParams {
   int N, H, W, Cin, Cout;
   int Wb, Hb, Nb, Wh, Hh, tiles_w, tiles_h, num_tiles;
   int stages;
+  int kchunks;          // Cin / KC: channel chunks of one swizzle row (KC = min(Cin, 64) channels) — one halo box each
+  int cslice;           // output channels per CTA: blockIdx.y owns columns [y*cslice, (y+1)*cslice) and keeps the nine
+                        // taps of exactly those rows of the weight resident (wide layers: the slice that fits smem)
   long long dst_ns;
   int dst_ps, dst_f32, accumulate;
-  uint32_t tmem_cols, acc_stride, a_stage_bytes, a_tx_bytes, b_bytes;
+  uint32_t tmem_cols, acc_stride, a_chunk_bytes, a_stage_bytes, a_tx_bytes, b_chunk_bytes, b_bytes;
 };
 
-template <int KSTEPS>   // Cin / 16
+template <int KSTEPS>   // KC / 16
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
@@ -328,6 +331,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * p.cslice;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -341,12 +345,13 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t row_bytes = p.Cin * 2;
+  constexpr uint32_t rb = KSTEPS * 32;     // bytes of one pixel row of one channel chunk
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(bfull, p.b_bytes);
-      tma_load_3d(sB, &tmB, bfull, 0, 0, 0);
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        tma_load_3d(sB + (size_t)kc * p.b_chunk_bytes, &tmB, bfull, kc * (int)(rb / 2), co0, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -355,7 +360,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int tn = tile / (p.tiles_w * p.tiles_h);
         if (!mbar_wait(&empty[stage], phase ^ 1, err)) break;
         mbar_expect_tx(&full[stage], p.a_tx_bytes);
-        tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], 0, tw * p.Wb - 1, th * p.Hb - 1, tn * p.Nb);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_4d(sA + (size_t)stage * p.a_stage_bytes + (size_t)kc * p.a_chunk_bytes, &tmA, &full[stage],
+                      kc * (int)(rb / 2), tw * p.Wb - 1, th * p.Hb - 1, tn * p.Nb);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -364,8 +371,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // Tight issue loop: per-tap descriptor increments live in registers (fully unrolled), so each
       // MMA costs a 64-bit add + the UTCHMMA (the single issuing thread is otherwise instruction-bound:
       // ncu showed ~400 cycles of address arithmetic per MMA in the first version of this loop).
-      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
-      constexpr uint32_t rb = KSTEPS * 32;
+      const uint32_t idesc = make_idesc_bf16(128, p.cslice, 0, 0);
       const uint32_t ltype = layout_type_for_row_bytes(rb);
       const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 8 * rb, ltype);
       const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 8 * rb, ltype);
@@ -373,10 +379,10 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         a_off[tap] = ((uint32_t)((tap / 3) * p.Wh + (tap % 3)) * rb) >> 4;
-        b_off[tap] = ((uint32_t)tap * p.Cout * rb) >> 4;
+        b_off[tap] = ((uint32_t)tap * p.cslice * rb) >> 4;
       }
-      const uint32_t a_step = p.a_stage_bytes >> 4;
-      const int nstages = p.stages, ntiles = p.num_tiles, acc_stride = p.acc_stride;
+      const uint32_t a_step = p.a_stage_bytes >> 4, a_chunk = p.a_chunk_bytes >> 4, b_chunk = p.b_chunk_bytes >> 4;
+      const int nstages = p.stages, ntiles = p.num_tiles, acc_stride = p.acc_stride, kchunks = p.kchunks;
       int stage = 0, it = 0;
       uint32_t phase = 0;
       bool ok = mbar_wait(bfull, 0, err);
@@ -390,12 +396,15 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         const uint64_t abase = adesc0 + (uint64_t)(stage * a_step);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const uint64_t ab = abase + (uint64_t)(kc * a_chunk), bb = bdesc0 + (uint64_t)(kc * b_chunk);
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k)
-            umma_bf16(d_tmem, abase + (uint64_t)(a_off[tap] + 2 * k), bdesc0 + (uint64_t)(b_off[tap] + 2 * k), idesc,
-                      (tap | k) != 0);
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_bf16(d_tmem, ab + (uint64_t)(a_off[tap] + 2 * k), bb + (uint64_t)(b_off[tap] + 2 * k), idesc,
+                        (kc | tap | k) != 0);
+          }
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[acc]);
@@ -419,19 +428,19 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int tn = tile / (p.tiles_w * p.tiles_h);
       const int w = tw * p.Wb + wl, h = th * p.Hb + hl, n = tn * p.Nb + nl;
       const bool valid = row_ok && w < p.W && h < p.H && n < p.N;
-      const long long off = (long long)n * p.dst_ns + ((long long)h * p.W + w) * p.dst_ps;
+      const long long off = (long long)n * p.dst_ns + ((long long)h * p.W + w) * p.dst_ps + co0;
       ok = mbar_wait(&tfull[acc], acc_phase, err);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+      for (int c0 = 0; c0 < p.cslice; c0 += 16) {
         float v[16];
         tmem_ld16(t_addr + c0, v);
         if (valid) {
           if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + co0 + c0 + j);
           }
           if (p.dst_f32) {
             float* dp = reinterpret_cast<float*>(dst) + off + c0;
@@ -588,10 +597,27 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   }
   unsigned int* err = tc_error_counter();
   PCM_REQUIRE(err != nullptr, "conv3x3_tc: could not allocate the error counter");
-  if (halo_env && ksz == 3 && mode == 0 && ps_co == 0 && !relu && lstm_gx == nullptr && Cin <= 64 &&
-      (size_t)9 * Cout * Cin * 2 <= (size_t)(Cin <= 32 ? 64 : 148) * 1024) {
+  // halo kernel: one halo box per (tile, channel chunk), nine shifted descriptors, weights resident.  Wide layers
+  // keep only a slice of the output channels per CTA (blockIdx.y) so that the resident weights stay <= ~100 KB.
+  int cslice = 0;
+  if (halo_env && ksz == 3 && mode == 0 && ps_co == 0 && !relu && lstm_gx == nullptr && Cin <= 128) {
+    const size_t budget = (size_t)(Cin <= 32 ? 64 : Cin <= 64 ? 148 : 100) * 1024;
+    for (int cs = Cout; cs >= 16; cs >>= 1) {
+      if (Cout % cs != 0 || cs % 16 != 0) break;
+      if ((size_t)9 * cs * Cin * 2 <= budget) { cslice = cs; break; }
+    }
+    if (Cin <= 64 && cslice != Cout) cslice = 0;        // thin layers: all-or-nothing (as measured)
+    // measured: slices narrower than half the layer lose — every slice CTA re-reads the whole A tile from shared memory
+    // for N = 32 columns only (128->128 in four slices: 24 us vs 17 us for the nine-box kernel; 128->64 in two: 7.4 vs 9.7)
+    if (cslice > 0 && Cout / cslice > 2) cslice = 0;
+  }
+  if (cslice > 0) {
     ConvHaloParams h;
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout;
+    h.cslice = cslice;
+    const int KC = Cin < 64 ? Cin : 64;
+    h.kchunks = Cin / KC;
+    const int nslices = Cout / cslice;
     h.Wb = h.Hb = h.Nb = 1;
     choose_tile_halo(N, H, W, &h.Wb, &h.Hb, &h.Nb);
     h.Wh = h.Wb + 2; h.Hh = h.Hb + 2;
@@ -599,17 +625,20 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     h.tiles_h = (H + h.Hb - 1) / h.Hb;
     h.num_tiles = h.tiles_w * h.tiles_h * ((N + h.Nb - 1) / h.Nb);
     h.dst_ns = dst_ns; h.dst_ps = dst_ps; h.dst_f32 = dst_f32; h.accumulate = accumulate;
-    h.acc_stride = Cout < 32 ? 32 : Cout;
+    h.acc_stride = cslice < 32 ? 32 : cslice;
     uint32_t cols = 32;
     while (cols < 2 * h.acc_stride) cols <<= 1;
     h.tmem_cols = cols;
-    const uint32_t row_bytes = Cin * 2;
+    const uint32_t row_bytes = KC * 2;
     const int box_rows = h.Nb * h.Hh * h.Wh;
     int need_rows = 128 + 2 * h.Wh + 2;
     if (box_rows > need_rows) need_rows = box_rows;
-    h.a_stage_bytes = ((uint32_t)need_rows * row_bytes + 1023u) & ~1023u;
-    h.a_tx_bytes = (uint32_t)box_rows * row_bytes;
-    h.b_bytes = 9u * Cout * row_bytes;
+    h.a_chunk_bytes = ((uint32_t)need_rows * row_bytes + 1023u) & ~1023u;
+    h.a_stage_bytes = h.a_chunk_bytes * h.kchunks;
+    h.a_tx_bytes = (uint32_t)box_rows * row_bytes * h.kchunks;
+    h.b_chunk_bytes = 9u * cslice * row_bytes;                      // multiple of 1024 for cslice >= 16, KC >= 16? checked below
+    h.b_bytes = h.b_chunk_bytes * h.kchunks;
+    PCM_REQUIRE(h.kchunks == 1 || h.b_chunk_bytes % 1024 == 0, "conv3x3_tc(halo): weight chunk not 1 KB aligned");
     const size_t b_region = ((size_t)h.b_bytes + 1023) & ~(size_t)1023;
     int stages = (int)(((Cin <= 32 ? 160 : 212) * 1024 - b_region) / h.a_stage_bytes);
     if (stages > 6) stages = 6;
@@ -620,27 +649,29 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     {
       uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
       uint64_t strides[3] = {(uint64_t)src_ps * 2, (uint64_t)W * src_ps * 2, (uint64_t)src_ns * 2};
-      uint32_t box[4] = {(uint32_t)Cin, (uint32_t)h.Wh, (uint32_t)h.Hh, (uint32_t)h.Nb};
+      uint32_t box[4] = {(uint32_t)KC, (uint32_t)h.Wh, (uint32_t)h.Hh, (uint32_t)h.Nb};
       int rc = make_tensor_map(&tmA, src, 4, dims, strides, box, row_bytes);
       if (rc != PCM_OK) return rc;
     }
     {
       uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
       uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-      uint32_t box[3] = {(uint32_t)Cin, (uint32_t)Cout, 9};
+      uint32_t box[3] = {(uint32_t)KC, (uint32_t)cslice, 9};
       int rc = make_tensor_map(&tmB, wk, 3, dims, strides, box, row_bytes);
       if (rc != PCM_OK) return rc;
     }
-    auto kern = Cin == 16 ? conv3x3_tc_halo_kernel<1> : Cin == 32 ? conv3x3_tc_halo_kernel<2> : conv3x3_tc_halo_kernel<4>;
-    const int hk = Cin == 16 ? 0 : Cin == 32 ? 1 : 2;
+    auto kern = KC == 16 ? conv3x3_tc_halo_kernel<1> : KC == 32 ? conv3x3_tc_halo_kernel<2> : conv3x3_tc_halo_kernel<4>;
+    const int hk = KC == 16 ? 0 : KC == 32 ? 1 : 2;
     static size_t smem_set_h[3] = {0, 0, 0};
     if (smem > smem_set_h[hk]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("conv3x3_tc(halo): smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
       smem_set_h[hk] = smem;
     }
-    const int grid = h.num_tiles < g_num_sms ? h.num_tiles : g_num_sms;
-    kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, h);
+    int gx = g_num_sms / nslices;
+    if (gx < 1) gx = 1;
+    if (gx > h.num_tiles) gx = h.num_tiles;
+    kern<<<dim3(gx, nslices), kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, h);
     return check_launch("conv3x3_tc(halo)");
   }
   ConvTcParams p;

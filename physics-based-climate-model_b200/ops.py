@@ -62,6 +62,12 @@ def _grad_buf(p: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # ------------------------------------------------------------------------------------------------
+def _work_list(sizes, dev, block: int = 1024) -> torch.Tensor:
+    """(job, block) pairs covering every job's elements in blocks of `block` — the grid of the batched kernels."""
+    pairs = [(j, b) for j, n in enumerate(sizes) for b in range((n + block - 1) // block)]
+    return torch.tensor(pairs, dtype=torch.int32).reshape(-1, 2).to(dev)
+
+
 class PackPlan:
     """Persistent packed-weight buffers for a training loop: every (parameter, layout) pair the step needs is
     registered the first time it is requested; afterwards `repack()` refreshes ALL of them from the fp32 master
@@ -99,8 +105,9 @@ class PackPlan:
                                    "warm-up steps before capturing the graph")
             dev = next(iter(self.entries.values()))[0].device
             self.table = torch.tensor([j for _, j in self.entries.values()], dtype=torch.int64).to(dev)
+            self.work = _work_list([t.numel() for t, _ in self.entries.values()], dev)
             self.dirty = False
-        _call("pcm_pack_weights_batched", self.table.data_ptr(), len(self.entries), self.max_elems, _s())
+        _call("pcm_pack_weights_batched", self.table.data_ptr(), self.work.data_ptr(), self.work.shape[0], _s())
 
 
     def grad_pack(self, dw: torch.Tensor, Co: int, Ci_tot: int, taps: int):
@@ -114,6 +121,8 @@ class PackPlan:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("PackPlan: a new packed gradient was requested after warm-up")
             Cpad = (Ci_tot + 15) // 16 * 16
+            if taps * Cpad > 9 * 512:                # slab limit of pcm_unpack_grads_batched: reduce in place instead
+                return None
             packed = torch.zeros((taps, Co, Cpad), device=dw.device, dtype=torch.float32)
             job = [packed.data_ptr(), dw.data_ptr(), Ci_tot * taps, taps, 1, Co | (Ci_tot << 32), Cpad | (taps << 32), 0]
             e = (packed, job)
@@ -136,12 +145,14 @@ class PackPlan:
         if key not in self.gtables:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("PackPlan: packed-gradient bucket requested for the first time during capture")
-            jobs = [j for _, j in self.gentries.values() if (lo is None or j[1] >= lo) and (hi is None or j[1] < hi)]
+            sel = [(t, j) for t, j in self.gentries.values() if (lo is None or j[1] >= lo) and (hi is None or j[1] < hi)]
             dev = next(iter(self.gentries.values()))[0].device
-            self.gtables[key] = (torch.tensor(jobs, dtype=torch.int64).reshape(-1, 8).to(dev), len(jobs))
-        table, n = self.gtables[key]
-        if n:
-            _call("pcm_unpack_grads_batched", table.data_ptr(), n, self.gmax, _s())
+            pairs = [(k, co) for k, (t, _) in enumerate(sel) for co in range(t.shape[1])]      # one CTA per (job, co)
+            self.gtables[key] = (torch.tensor([j for _, j in sel], dtype=torch.int64).reshape(-1, 8).to(dev),
+                                 torch.tensor(pairs, dtype=torch.int32).reshape(-1, 2).to(dev))
+        table, work = self.gtables[key]
+        if work.shape[0]:
+            _call("pcm_unpack_grads_batched", table.data_ptr(), work.data_ptr(), work.shape[0], _s())
 
 
 _PLAN: Optional[PackPlan] = None
