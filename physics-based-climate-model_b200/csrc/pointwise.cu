@@ -41,6 +41,47 @@ nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C
   }
 }
 
+// Same, four consecutive pixels per thread: one 16-byte load per input channel keeps 4x the bytes in flight (the scalar
+// version ran at 2 TB/s on the 74 MB fp32 input of a training batch).  Requires P % 4 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_x4_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int P, int Cp,
+                       const int* __restrict__ month, int Tp) {
+  const int cv = Cp / 8, P4 = P / 4;
+  const int Bn = Tp > 1 ? N / Tp : N;
+  const long long total = (long long)N * cv * P4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int p4 = (int)(idx % P4);
+    const int cb = (int)((idx / P4) % cv);
+    const int n = (int)(idx / ((long long)P4 * cv));
+    const int ni = Tp > 1 ? (n % Bn) * Tp + n / Bn : n;
+    float v[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) q = __ldg(reinterpret_cast<const float4*>(x + ((long long)ni * C + c) * P) + p4);
+      v[0][j] = q.x; v[1][j] = q.y; v[2][j] = q.z; v[3][j] = q.w;
+    }
+    if (month != nullptr) {
+      const float ang = 6.283185307179586f * (float)__ldg(month + ni) / 12.f;
+      const float sn = sinf(ang), cs = cosf(ang);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cb * 8 + j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (c == C) v[k][j] = sn;
+          if (c == C + 1) v[k][j] = cs;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) store8(y + ((long long)n * P + 4 * p4 + k) * Cp + cb * 8, v[k]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int P, int Cp, int Tp) {
@@ -375,8 +416,13 @@ extern "C" int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, in
   PCM_REQUIRE(T_ >= 1 && N % T_ == 0, "nchw_to_nhwc: N must be a multiple of T");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
-  PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   x, (T*)y, N, C, H * W, Cp, nullptr, T_)));
+  if ((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_x4_kernel<T><<<grid_for(total / 4), 256, 0, (cudaStream_t)s>>>(
+                                     x, (T*)y, N, C, H * W, Cp, nullptr, T_)));
+  } else {
+    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                     x, (T*)y, N, C, H * W, Cp, nullptr, T_)));
+  }
   return check_launch("nchw_to_nhwc");
 }
 
@@ -386,8 +432,13 @@ extern "C" int pcm_season_embed_stage(const float* x5, const int* month, void* y
   PCM_REQUIRE(T_ >= 1 && N % T_ == 0, "season_embed_stage: N must be a multiple of T");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
-  PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   x5, (T*)y, N, 5, H * W, Cp, month, T_)));
+  if ((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(x5) & 15) == 0) {
+    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_x4_kernel<T><<<grid_for(total / 4), 256, 0, (cudaStream_t)s>>>(
+                                     x5, (T*)y, N, 5, H * W, Cp, month, T_)));
+  } else {
+    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                     x5, (T*)y, N, 5, H * W, Cp, month, T_)));
+  }
   return check_launch("season_embed_stage");
 }
 
