@@ -218,3 +218,40 @@ def test_train_step_graph_matches_eager_and_oracle(G):
         assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5      # all parameters together
         assert torch.equal(ps["post_conv.0.weight"], sd["post_conv.0.weight"])     # untouched (zero grad, F5)
     np.testing.assert_allclose(results[0][0], results[1][0], rtol=1e-5)
+
+
+def test_step_prefetch_matches_step(G):
+    """TrainStep.step_prefetch (next batch copied host->device on a second stream while the current step runs) yields
+    the same loss sequence as the serial step() on the same batches, under the captured graph."""
+    import pcm_b200
+    from oracle import model_oracle as O
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    from pcm_b200.trainer import TrainStep
+    B, T, H, W, base = 2, 3, 16, 24, 8
+    sd = O.synth_state_dict(O.attunet_spec(7, 2, base), 81)
+    batches = [tuple(t.pin_memory() for t in O.synth_attunet_batch(B, T, H, W, 82 + i)[:2]) for i in range(4)]
+    pcm_b200.set_compute_dtype(torch.float32)
+    try:
+        losses = []
+        for prefetch in (False, True):
+            model = AttUNetConvLSTM(7, 2, base, seq_len=T)
+            model.load_state_dict(sd)
+            model = model.cuda()
+            step = TrainStep(model, (B, T, 7, H, W), (B, 2, H, W), lr=1e-3)
+            step.load_batch(*batches[0])
+            step.warmup_and_capture(warmup=2)
+            model.load_state_dict(sd)                     # undo the warm-up updates (parameters are re-homed views)
+            step.reset_optimizer_state()
+            out = []
+            if prefetch:
+                step.load_batch(*batches[0])
+                for i in range(4):
+                    out.append(float(step.step_prefetch(*batches[(i + 1) % 4]).item()))
+            else:
+                for i in range(4):
+                    out.append(float(step.step(*batches[i]).item()))
+            losses.append(out)
+    finally:
+        pcm_b200.set_compute_dtype(torch.bfloat16)
+    for a, b in zip(*losses):
+        assert abs(a - b) / abs(a) < 1e-4, losses
