@@ -240,7 +240,9 @@ def test_step_prefetch_matches_step(G):
             step = TrainStep(model, (B, T, 7, H, W), (B, 2, H, W), lr=1e-3)
             step.load_batch(*batches[0])
             step.warmup_and_capture(warmup=2)
-            model.load_state_dict(sd)                     # undo the warm-up updates (parameters are re-homed views)
+            with torch.no_grad():                         # undo the warm-up updates
+                for k, p in model.named_parameters():
+                    p.copy_(sd[k].cuda())
             step.reset_optimizer_state()
             out = []
             if prefetch:
