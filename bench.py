@@ -239,11 +239,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------
-    for i in range(args.warmup):
+    sampler = ClockSampler(local)       # started before the warm-up steps (nvidia-smi needs ~100 ms to deliver its first
+    sampler.start()                     # sample); it keeps sampling through the timed region
+    # W untimed warm-up steps (at least 10 under NCCL: the first replays of a graph holding collectives are slow)
+    for i in range(max(args.warmup, 10) if world > 1 else args.warmup):
         step.step(xs_d[i % N_ROTATE], ys_d[i % N_ROTATE])
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
