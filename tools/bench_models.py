@@ -20,6 +20,7 @@ from pcm_b200.trainer import TrainStep  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--trace", action="store_true", help="per-kernel totals of one eager step (CUDA events per C-ABI call)")
     a = ap.parse_args()
     torch.manual_seed(42)
     cases = [
@@ -47,6 +48,12 @@ def main():
         extra = f"  {B / ms * gflop:8.1f} TFLOP/s algorithmic" if gflop else ""
         print(f"{name}: {ms:8.3f} ms/step  {B / ms * 1e3:9.0f} samples/s  {step.launches_per_step} launches{extra}  "
               f"loss {float(step.loss):.4f}")
+        if a.trace:
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            from bench import kernel_trace
+            _, agg = kernel_trace(step._step_impl, n_steps=2)
+            for k, (ms_k, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
+                print(f"    {ms_k * 1e3:9.1f} us  x{n:5.1f}  {k}")
         del step, model
         torch.cuda.empty_cache()
 
