@@ -245,6 +245,11 @@ PCM_API int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float* s
  * drop_p: dropout on the attention probabilities (counter-based mask from `seed`).  D in {8, 16, 32, 64}. */
 PCM_API int pcm_mha_fwd(const void* qkv, void* out, float* lse, int B, int L, int nh, int D, float scale, float drop_p,
                         long long seed, int dtype, pcm_stream_t s);
+/* the same forward on the tensor cores (tcgen05; bf16, head dim 32, L <= 224): S = Q K^T and O = P V as UMMAs with
+ * the scores in TMEM and the probabilities staged in shared memory as the next MMA's operand; same lse / dropout-mask
+ * convention as pcm_mha_fwd, so either backward kernel pairs with it */
+PCM_API int pcm_mha_fwd_tc(const void* qkv, void* out, float* lse, int B, int L, int nh, float scale, float drop_p,
+                           long long seed, pcm_stream_t s);
 PCM_API int pcm_mha_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int L,
                         int nh, int D, float scale, float drop_p, long long seed, int dtype, pcm_stream_t s);
 

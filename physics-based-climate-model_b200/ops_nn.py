@@ -8,6 +8,7 @@ the tcgen05 kernels (pcm_conv3x3_tc / pcm_conv1x1_tc / pcm_wgrad*_tc), everythin
 strided layers) to the general SIMT gather kernels.  No CPU / eager fallback."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -439,8 +440,11 @@ class MHAFn(torch.autograd.Function):
         out = torch.empty((B, L, E), device=qkv.device, dtype=qkv.dtype)
         lse = torch.empty(B * n_heads * L, device=qkv.device, dtype=torch.float32)
         scale = 1.0 / (D ** 0.5)
-        _call("pcm_mha_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L, n_heads, D, scale, drop_p, seed,
-              _DT[qkv.dtype], _s())
+        if qkv.dtype == torch.bfloat16 and D == 32 and L <= 224 and os.environ.get("PCM_MHA_TC", "1") != "0":
+            _call("pcm_mha_fwd_tc", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L, n_heads, scale, drop_p, seed, _s())
+        else:
+            _call("pcm_mha_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L, n_heads, D, scale, drop_p, seed,
+                  _DT[qkv.dtype], _s())
         ctx.save_for_backward(qkv, out, lse)
         ctx.cfg = (n_heads, D, scale, drop_p, seed)
         return out

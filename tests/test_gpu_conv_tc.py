@@ -275,3 +275,30 @@ def test_convT2x2_tc_matches_reference(ops, shape):
     wdx = xr.grad.permute(0, 2, 3, 1).float()
     assert float((dx.float().cpu() - wdx).norm() / wdx.norm()) < 4e-3
     assert float((gwt.cpu() - wr.grad.float()).norm() / wr.grad.norm()) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(3, 216, 4), (2, 224, 2), (2, 100, 4), (1, 17, 1)])
+def test_mha_fwd_tc_matches_reference(ops, cfg):
+    """tcgen05 attention forward (head dim 32) against fp64 softmax(q k^T / sqrt(d)) v on the same bf16 inputs, and the
+    saved log-sum-exp against the SIMT kernel's."""
+    from pcm_b200._lib import lib
+    from pcm_b200.ops import _call, _s
+    B, L, nh = cfg
+    D, E = 32, 32 * nh
+    g = torch.Generator().manual_seed(B * 100 + L + nh)
+    qkv = torch.randn(B, L, 3 * E, generator=g).bfloat16()
+    q, k, v = [t.double().reshape(B, L, nh, D).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    att = torch.softmax(q @ k.transpose(-1, -2) / D ** 0.5, dim=-1)
+    want = (att @ v).transpose(1, 2).reshape(B, L, E)
+    qg = qkv.cuda()
+    out = torch.empty(B, L, E, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B * nh * L, device="cuda")
+    _call("pcm_mha_fwd_tc", qg.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L, nh, 1.0 / D ** 0.5, 0.0, 0, _s())
+    out2 = torch.empty_like(out)
+    lse2 = torch.empty_like(lse)
+    _call("pcm_mha_fwd", qg.data_ptr(), out2.data_ptr(), lse2.data_ptr(), B, L, nh, D, 1.0 / D ** 0.5, 0.0, 0, 1, _s())
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    err = float((out.double().cpu() - want).norm() / want.norm())
+    assert err < 8e-3, err                                   # bf16 probabilities and bf16 output
+    assert float((lse - lse2).abs().max()) < 2e-3
