@@ -250,6 +250,10 @@ PCM_API int pcm_mha_fwd(const void* qkv, void* out, float* lse, int B, int L, in
  * convention as pcm_mha_fwd, so either backward kernel pairs with it */
 PCM_API int pcm_mha_fwd_tc(const void* qkv, void* out, float* lse, int B, int L, int nh, float scale, float drop_p,
                            long long seed, pcm_stream_t s);
+/* ... and the backward on the tensor cores: per (key tile, query tile) S and dP as UMMAs, P~ / dS' through shared
+ * memory (one image serves as K-major and as MN-major operand), dQ / dK / dV accumulated in TMEM */
+PCM_API int pcm_mha_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int L,
+                           int nh, float scale, float drop_p, long long seed, pcm_stream_t s);
 PCM_API int pcm_mha_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int L,
                         int nh, int D, float scale, float drop_p, long long seed, int dtype, pcm_stream_t s);
 

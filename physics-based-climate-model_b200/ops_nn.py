@@ -456,6 +456,10 @@ class MHAFn(torch.autograd.Function):
         B, L, _ = qkv.shape
         dout = dout.contiguous()
         dqkv = torch.empty_like(qkv)
-        _call("pcm_mha_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, L,
-              n_heads, D, scale, drop_p, seed, _DT[qkv.dtype], _s())
+        if qkv.dtype == torch.bfloat16 and D == 32 and L <= 224 and os.environ.get("PCM_MHA_TC", "1") != "0":
+            _call("pcm_mha_bwd_tc", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, L,
+                  n_heads, scale, drop_p, seed, _s())
+        else:
+            _call("pcm_mha_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, L,
+                  n_heads, D, scale, drop_p, seed, _DT[qkv.dtype], _s())
         return dqkv, None, None, None

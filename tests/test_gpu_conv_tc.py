@@ -302,3 +302,38 @@ def test_mha_fwd_tc_matches_reference(ops, cfg):
     err = float((out.double().cpu() - want).norm() / want.norm())
     assert err < 8e-3, err                                   # bf16 probabilities and bf16 output
     assert float((lse - lse2).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("cfg", [(3, 216, 4, 0.0), (2, 224, 2, 0.0), (2, 100, 4, 0.0), (1, 17, 1, 0.0), (2, 216, 4, 0.1)])
+def test_mha_bwd_tc_matches_reference(ops, cfg):
+    """tcgen05 attention backward against fp64 autograd (p = 0) and against the SIMT backward with the same
+    counter-based dropout mask (p > 0)."""
+    from pcm_b200._lib import lib
+    from pcm_b200.ops import _call, _s
+    B, L, nh, pd = cfg
+    D, E = 32, 32 * nh
+    g = torch.Generator().manual_seed(B * 100 + L + nh)
+    qkv = torch.randn(B, L, 3 * E, generator=g).bfloat16()
+    dout = (torch.randn(B, L, E, generator=g) / 8).bfloat16()
+    qg, dg = qkv.cuda(), dout.cuda()
+    sc, seed = 1.0 / D ** 0.5, 4242
+    out = torch.empty(B, L, E, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B * nh * L, device="cuda")
+    _call("pcm_mha_fwd_tc", qg.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L, nh, sc, pd, seed, _s())
+    dq_tc = torch.full((B, L, 3 * E), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _call("pcm_mha_bwd_tc", qg.data_ptr(), out.data_ptr(), dg.data_ptr(), lse.data_ptr(), dq_tc.data_ptr(), B, L, nh, sc, pd,
+          seed, _s())
+    dq_simt = torch.empty_like(dq_tc)
+    _call("pcm_mha_bwd", qg.data_ptr(), out.data_ptr(), dg.data_ptr(), lse.data_ptr(), dq_simt.data_ptr(), B, L, nh, D, sc, pd,
+          seed, 1, _s())
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    a, b = dq_tc.double().cpu(), dq_simt.double().cpu()
+    assert bool(torch.isfinite(a).all())
+    assert float((a - b).norm() / b.norm()) < 1.5e-2                      # bf16 P~ / dS' operands vs fp32 SIMT math
+    if pd == 0.0:
+        x = qkv.double().requires_grad_(True)
+        q, k, v = [t.reshape(B, L, nh, D).transpose(1, 2) for t in x.split(E, dim=-1)]
+        o = (torch.softmax(q @ k.transpose(-1, -2) * sc, dim=-1) @ v).transpose(1, 2).reshape(B, L, E)
+        o.backward(dout.double())
+        assert float((a - x.grad).norm() / x.grad.norm()) < 1.5e-2
