@@ -54,6 +54,13 @@ PCM_API int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, int W
 PCM_API int pcm_season_embed_stage(const float* x5, const int* month, void* y, int N, int H, int W, int Cp, int T,
                                    int dtype, pcm_stream_t s);
 
+/* Sliding windows from a device-resident series (SequenceDataset.__getitem__, main_final.py:97-154):
+ * NHWC image n <- frame frames[n] of series [Ttot][C][H][W] (fp32 NCHW); frames[n] < 0 = the zero left-pad of windows
+ * that start before the record.  With frames[t*B + b] = idx[b] - T + 1 + t the result is the t-major staged batch the
+ * models' forward_staged takes — a training step then needs B window indices from the host, not B*T frames. */
+PCM_API int pcm_window_stage(const float* series, const int* frames, void* y, int N, int C, int H, int W, int Cp,
+                             int dtype, pcm_stream_t s);
+
 /* ---- weight packing: out[t][o][i] = (o<O && i<I) ? w[o*so + i*si + t*st] : 0, stored as dtype */
 PCM_API int pcm_pack_weight(const float* w, long long so, long long si, long long st, int O, int I, int taps, int Op,
                     int Ip, void* out, int dtype, pcm_stream_t s);

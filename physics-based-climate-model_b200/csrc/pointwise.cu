@@ -82,6 +82,33 @@ nchw_to_nhwc_x4_kernel(const float* __restrict__ x, T* __restrict__ y, int N, in
   }
 }
 
+// Sliding-window staging from a device-resident series (main_final.py:97-154): NHWC image n <- NCHW frame frames[n]
+// of `series` (frames[n] < 0: the zero left-pad of windows that start before the record).  Four pixels per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+window_stage_kernel(const float* __restrict__ series, const int* __restrict__ frames, T* __restrict__ y, int N, int C,
+                    int P, int Cp) {
+  const int cv = Cp / 8, P4 = P / 4;
+  const long long total = (long long)N * cv * P4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int p4 = (int)(idx % P4);
+    const int cb = (int)((idx / P4) % cv);
+    const int n = (int)(idx / ((long long)P4 * cv));
+    const int f = __ldg(frames + n);
+    float v[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C && f >= 0) q = __ldg(reinterpret_cast<const float4*>(series + ((long long)f * C + c) * P) + p4);
+      v[0][j] = q.x; v[1][j] = q.y; v[2][j] = q.z; v[3][j] = q.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) store8(y + ((long long)n * P + 4 * p4 + k) * Cp + cb * 8, v[k]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int P, int Cp, int Tp) {
@@ -424,6 +451,17 @@ extern "C" int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, in
                                      x, (T*)y, N, C, H * W, Cp, nullptr, T_)));
   }
   return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int pcm_window_stage(const float* series, const int* frames, void* y, int N, int C, int H, int W, int Cp,
+                                int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(Cp % 8 == 0 && Cp >= C, "window_stage: bad channel padding C=%d Cp=%d", C, Cp);
+  PCM_REQUIRE((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(series) & 15) == 0, "window_stage: H*W must be a multiple of 4");
+  if (N == 0) return PCM_OK;
+  const long long total = (long long)N * (Cp / 8) * H * W / 4;
+  PCM_DISPATCH_DTYPE(dtype, T, (window_stage_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+                                   series, frames, (T*)y, N, C, H * W, Cp)));
+  return check_launch("window_stage");
 }
 
 extern "C" int pcm_season_embed_stage(const float* x5, const int* month, void* y, int N, int H, int W, int Cp,

@@ -480,6 +480,23 @@ def season_embed_stage(x5: torch.Tensor, month: torch.Tensor, dtype, T: int = 1)
     return y
 
 
+def window_stage(series: torch.Tensor, idx: torch.Tensor, T: int, dtype) -> torch.Tensor:
+    """SequenceDataset.__getitem__ (main_final.py:97-154) for a whole batch, on the device: `series` is the resident
+    input record (Ttot, C, H, W) fp32, `idx` (B,) the target time indices; returns the t-major staged frames
+    (T*B, H, W, 16): frame (t, b) = series[idx[b] - T + 1 + t], zeros where that index is negative (left pad).
+    Inputs are data: no gradient."""
+    _require_cuda(series, "series")
+    Ttot, C, H, W = series.shape
+    B = idx.numel()
+    # frame table: a (T, B) int tensor computed with torch integer ops (index plumbing, no activation arithmetic)
+    frames = (idx.to(torch.int32).reshape(1, B) - (T - 1) + torch.arange(T, device=idx.device, dtype=torch.int32).reshape(T, 1))
+    frames = torch.where(frames < Ttot, frames, torch.full_like(frames, -1)).contiguous()
+    y = torch.empty((T * B, H, W, padc(C)), device=series.device, dtype=dtype)
+    _call("pcm_window_stage", series.contiguous().float().data_ptr(), frames.data_ptr(), y.data_ptr(), T * B, C, H, W, padc(C),
+          _DT[dtype], _s())
+    return y
+
+
 # ------------------------------------------------------------------------------------------------
 # ConvBlock: [conv3x3 -> GN(8) -> SiLU] x2 -> SE -> SpatialGate   (src/unet.py:32-49)
 # ------------------------------------------------------------------------------------------------

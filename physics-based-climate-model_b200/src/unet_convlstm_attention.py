@@ -57,6 +57,14 @@ class AttUNetConvLSTM(nn.Module):
         x = ops.StageIn.apply(x_seq.reshape(B * T, C, H, W), compute_dtype(), 16, T)
         return self.forward_staged(x, B, T)
 
+    def forward_windows(self, series, idx, T=None):
+        """Device-resident data path: `series` (Ttot, C_in, H, W) is the whole normalised input record
+        kept in HBM, `idx` (B,) the target months; windows of T = seq_len frames ending at idx (zero left-padded,
+        main_final.py:97-154) are gathered and staged by one kernel.  Equals forward(x_seq) on the stacked windows."""
+        T = self.seq_len if T is None else T
+        x = ops.window_stage(series, idx, T, compute_dtype())
+        return self.forward_staged(x, idx.numel(), T)
+
     def forward_staged(self, x, B, T):
         """x: NHWC frames (T*B, H, W, 16), t-major: image n = t*B + b (e.g. from
         ops.season_embed_stage(..., T=T), which synthesises the sin/cos month channels on the fly)."""

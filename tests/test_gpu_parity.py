@@ -257,3 +257,31 @@ def test_step_prefetch_matches_step(G):
         pcm_b200.set_compute_dtype(torch.bfloat16)
     for a, b in zip(*losses):
         assert abs(a - b) / abs(a) < 1e-4, losses
+
+
+def test_forward_windows_matches_stacked_windows(G):
+    """Device-resident window gather (SequenceDataset semantics, zero left-pad) == forward on the explicitly stacked
+    windows; includes target indices smaller than seq_len - 1."""
+    import pcm_b200
+    from oracle import model_oracle as O
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    T, H, W, base, Ttot = 4, 16, 24, 8, 12
+    sd = O.synth_state_dict(O.attunet_spec(7, 2, base), 91)
+    g = torch.Generator().manual_seed(92)
+    series = torch.randn(Ttot, 7, H, W, generator=g)
+    idx = torch.tensor([0, 2, 3, 7, 11])
+    pad = torch.zeros(7, H, W)
+    x_seq = torch.stack([torch.stack([series[i - T + 1 + t] if i - T + 1 + t >= 0 else pad for t in range(T)]) for i in idx.tolist()])
+    pcm_b200.set_compute_dtype(torch.float32)
+    try:
+        model = AttUNetConvLSTM(7, 2, base, seq_len=T)
+        model.load_state_dict(sd)
+        model = model.cuda()
+        with torch.no_grad():
+            a = model.forward_windows(series.cuda(), idx.cuda()).cpu()
+            b = model(x_seq.cuda()).cpu()
+    finally:
+        pcm_b200.set_compute_dtype(torch.bfloat16)
+    assert float((a - b).abs().max()) < 1e-5            # same kernels; only the order of fp32 atomic sums differs
+    ref = O.attunet_convlstm(x_seq.double(), {k: v.double() for k, v in sd.items()})
+    assert float((a.double() - ref).norm() / ref.norm()) < 1e-4
