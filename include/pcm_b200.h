@@ -306,6 +306,11 @@ PCM_API int pcm_adam_step(float* p, const float* g, float* m, float* v, float* s
  * pcm_metric_finalize reduces them with the latitude weights. */
 PCM_API int pcm_metric_partial(const float* pred, const float* truth, double* partial, int T, int V, int Y, int X,
                        int zero_first, pcm_stream_t s);
+/* the same accumulation on NORMALISED pred/truth with Normalizer.inverse_transform_output (src/utils_final.py:130-206)
+ * fused in: tr: device fp32 [V][4] = (kind, a, b, c), x_phys = g(x*a + b); kind 0 identity (zscore: a = std, b = mean;
+ * minimax: a = max - min, b = min), 1 expm1 (log1p), 2 square (sqrt), 3 (.)^(1/c) (pow) — SURVEY §8(f)3 */
+PCM_API int pcm_metric_partial_denorm(const float* pred, const float* truth, const float* tr, double* partial, int T,
+                                      int V, int Y, int X, int zero_first, pcm_stream_t s);
 PCM_API int pcm_metric_finalize(const double* partial, const double* w_lat, double* out, long long T_total, int V, int Y,
                         int X, pcm_stream_t s);
 

@@ -29,6 +29,39 @@ metric_partial_kernel(const float* __restrict__ pred, const float* __restrict__ 
   atomicAdd(o + 0, sp); atomicAdd(o + 1, spp); atomicAdd(o + 2, st); atomicAdd(o + 3, stt); atomicAdd(o + 4, sd);
 }
 
+// Validation epilogue (main_final.py:563-574 + src/utils_final.py:130-206): predictions and targets arrive NORMALISED;
+// the inverse transform of Normalizer.inverse_transform_output is applied on the fly in fp64, so the de-normalised
+// tensors are never materialised.  tr[v] = (kind, a, b, c): x_phys = g(x*a + b) with
+//   kind 0 zscore / minimax: identity   1 log1p: expm1   2 sqrt: square   3 pow: (.)^(1/c)
+__device__ __forceinline__ double denorm(double x, int kind, double a, double b, double c) {
+  const double u = fma(x, a, b);
+  return kind == 0 ? u : kind == 1 ? expm1(u) : kind == 2 ? u * u : pow(u, 1.0 / c);
+}
+
+__global__ void __launch_bounds__(256)
+metric_partial_denorm_kernel(const float* __restrict__ pred, const float* __restrict__ truth,
+                             const float* __restrict__ tr, double* __restrict__ partial, int T, int YX, int VYX) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= VYX) return;
+  const int v = pix / YX;
+  const int kind = (int)__ldg(tr + 4 * v);
+  const double a = (double)__ldg(tr + 4 * v + 1), b = (double)__ldg(tr + 4 * v + 2), c = (double)__ldg(tr + 4 * v + 3);
+  const int per = (T + gridDim.y - 1) / gridDim.y;
+  const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
+  double sp = 0, spp = 0, st = 0, stt = 0, sd = 0;
+  for (int t = t0; t < t1; ++t) {
+    const double p = denorm((double)__ldg(pred + (long long)t * VYX + pix), kind, a, b, c);
+    const double q = denorm((double)__ldg(truth + (long long)t * VYX + pix), kind, a, b, c);
+    const double d = p - q;
+    sp += p; st += q;
+    spp = fma(p, p, spp);
+    stt = fma(q, q, stt);
+    sd = fma(d, d, sd);
+  }
+  double* o = partial + (long long)pix * 5;
+  atomicAdd(o + 0, sp); atomicAdd(o + 1, spp); atomicAdd(o + 2, st); atomicAdd(o + 3, stt); atomicAdd(o + 4, sd);
+}
+
 // one block per variable; out[v][0..2]
 __global__ void __launch_bounds__(256)
 metric_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ w_lat, double* __restrict__ out,
@@ -76,6 +109,23 @@ extern "C" int pcm_metric_partial(const float* pred, const float* truth, double*
   dim3 grid(gx, chunks);
   metric_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(pred, truth, partial, T, VYX);
   return check_launch("metric_partial");
+}
+
+extern "C" int pcm_metric_partial_denorm(const float* pred, const float* truth, const float* tr, double* partial, int T,
+                                         int V, int Y, int X, int zero_first, pcm_stream_t s) {
+  PCM_REQUIRE(tr != nullptr, "metric_partial_denorm: transform table is null");
+  const int VYX = V * Y * X;
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(partial, 0, (size_t)VYX * 5 * sizeof(double), (cudaStream_t)s);
+    if (e != cudaSuccess) { set_error("metric_partial_denorm memset: %s", cudaGetErrorString(e)); return PCM_ERR_CUDA; }
+  }
+  if (T == 0) return PCM_OK;
+  const int gx = ceil_div(VYX, 256);
+  int chunks = (4 * 148 + gx - 1) / gx;
+  if (chunks > (T + 15) / 16) chunks = (T + 15) / 16;
+  if (chunks < 1) chunks = 1;
+  metric_partial_denorm_kernel<<<dim3(gx, chunks), 256, 0, (cudaStream_t)s>>>(pred, truth, tr, partial, T, Y * X, VYX);
+  return check_launch("metric_partial_denorm");
 }
 
 extern "C" int pcm_metric_finalize(const double* partial, const double* w_lat, double* out, long long T_total, int V,

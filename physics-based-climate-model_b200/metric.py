@@ -44,6 +44,46 @@ def metric_partial_sums(pred: torch.Tensor, truth: torch.Tensor, partial: torch.
     return partial
 
 
+_KINDS = {"zscore": 0, "minimax": 0, "log1p": 1, "sqrt": 2, "pow": 3}
+
+
+def transform_table(output_stats: dict, n_vars: int, device) -> torch.Tensor:
+    """Normalizer.output_stats ({var_idx: {"method": ..., "params": {...}}}, src/utils_final.py:130-206) -> the
+    device table (V, 4) = (kind, a, b, c) pcm_metric_partial_denorm takes; variables without an entry pass through."""
+    rows = []
+    for v in range(n_vars):
+        cfg = output_stats.get(v)
+        if cfg is None:
+            rows.append([0.0, 1.0, 0.0, 1.0])
+            continue
+        m, pr = cfg["method"], cfg.get("params", {})
+        if m not in _KINDS:
+            raise ValueError(f"Unknown inverse method '{m}' for var {v}.")
+        if m == "minimax":
+            a, b = pr["max_val"] - pr["min_val"], pr["min_val"]
+        else:
+            a, b = pr["std"], pr["mean"]
+        rows.append([float(_KINDS[m]), float(a), float(b), float(pr.get("lambda", 1.0))])
+    return torch.tensor(rows, dtype=torch.float32, device=device)
+
+
+def metric_partial_sums_normalized(pred_norm: torch.Tensor, truth_norm: torch.Tensor, table: torch.Tensor,
+                                   partial: torch.Tensor = None) -> torch.Tensor:
+    """As metric_partial_sums, for NORMALISED predictions/targets: the inverse transform of the reference's Normalizer is
+    applied on the fly (validation epilogue of main_final.py:563-574 without the de-normalised copies or the D2H)."""
+    if not pred_norm.is_cuda:
+        raise RuntimeError("pcm_b200.metric: tensors must live on the GPU (no CPU fallback)")
+    pred_norm = pred_norm.contiguous().float()
+    truth_norm = truth_norm.contiguous().float()
+    T, V, Y, X = pred_norm.shape
+    zero = partial is None
+    if zero:
+        partial = torch.empty((V, Y, X, 5), device=pred_norm.device, dtype=torch.float64)
+    lib().call("pcm_metric_partial_denorm", pred_norm.data_ptr(), truth_norm.data_ptr(), table.data_ptr(), partial.data_ptr(),
+               T, V, Y, X, int(zero), _stream())
+    return partial
+
+
 def metric_finalize(partial: torch.Tensor, lat, T_total: int) -> torch.Tensor:
     """-> fp64 (V, 3): monthly_rmse, time_mean_rmse, time_std_mae per variable."""
     V, Y, X, _ = partial.shape

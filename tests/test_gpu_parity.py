@@ -285,3 +285,35 @@ def test_forward_windows_matches_stacked_windows(G):
     assert float((a - b).abs().max()) < 1e-5            # same kernels; only the order of fp32 atomic sums differs
     ref = O.attunet_convlstm(x_seq.double(), {k: v.double() for k, v in sd.items()})
     assert float((a.double() - ref).norm() / ref.norm()) < 1e-4
+
+
+def test_metric_with_fused_inverse_transform(G):
+    """Normalised pred/truth + Normalizer.inverse_transform_output fused into the accumulation (zscore for tas, log1p for
+    pr — the reference's default output transforms) == the metric oracle on the de-normalised fp64 arrays."""
+    from oracle import metric_oracle as MO
+    from pcm_b200 import metric as M
+    pred, true, lat = MO.synth_metric_arrays(120)                       # physical units, (T, 2, Y, X)
+    stats = {0: {"method": "zscore", "params": {"mean": 280.0, "std": 12.0}},
+             1: {"method": "log1p", "params": {"mean": 0.9, "std": 0.6}}}
+
+    def norm(a):
+        out = np.empty_like(a, dtype=np.float64)
+        out[:, 0] = (a[:, 0].astype(np.float64) - 280.0) / 12.0
+        out[:, 1] = (np.log1p(np.maximum(a[:, 1].astype(np.float64), 0.0)) - 0.9) / 0.6
+        return out.astype(np.float32)
+
+    pn, tn = norm(pred), norm(true)
+    # what the reference de-normalises to (fp64 on the fp32 normalised values)
+    def denorm(a):
+        out = np.empty(a.shape, dtype=np.float64)
+        out[:, 0] = a[:, 0].astype(np.float64) * 12.0 + 280.0
+        out[:, 1] = np.expm1(a[:, 1].astype(np.float64) * 0.6 + 0.9)
+        return out
+    w = MO.get_lat_weights(lat)
+    dp, dt = denorm(pn), denorm(tn)
+    table = M.transform_table(stats, 2, "cuda")
+    part = M.metric_partial_sums_normalized(torch.from_numpy(pn).cuda(), torch.from_numpy(tn).cuda(), table)
+    got = M.metric_finalize(part, lat, 120).cpu().numpy()
+    for i in range(2):
+        want = MO.metric_triplet(dp[:, i], dt[:, i], w)
+        np.testing.assert_allclose(got[i], want, rtol=1e-5)
