@@ -149,11 +149,37 @@ def bench_tails(args):
                   f"{ms * 1e6 / (N * P * C):7.3f} ns/element")
 
 
+def bench_mha(args):
+    """Attention core of CNNTransformer (B=64, L=216, 4 heads of 32): tcgen05 vs SIMT kernels, forward and backward."""
+    from pcm_b200.ops import _call, _s
+    B, L, nh, D = 64, 216, 4, 32
+    E = nh * D
+    qkv = torch.randn(B, L, 3 * E, device="cuda").bfloat16()
+    dout = (torch.randn(B, L, E, device="cuda") / 8).bfloat16()
+    out = torch.empty(B, L, E, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B * nh * L, device="cuda")
+    dqkv = torch.empty_like(qkv)
+    sc = 1.0 / D ** 0.5
+    for pd in (0.0, 0.1):
+        cases = [
+            ("mha_fwd_tc", 1.0, lambda: _call("pcm_mha_fwd_tc", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L, nh, sc, pd, 7, _s())),
+            ("mha_fwd (SIMT)", 1.0, lambda: _call("pcm_mha_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L, nh, D, sc, pd, 7, 1, _s())),
+            ("mha_bwd_tc", 2.5, lambda: _call("pcm_mha_bwd_tc", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, L, nh, sc, pd, 7, _s())),
+            ("mha_bwd (SIMT)", 2.5, lambda: _call("pcm_mha_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, L, nh, D, sc, pd, 7, 1, _s())),
+        ]
+        for name, k, fn in cases:
+            if args.only and args.only not in name:
+                continue
+            ms = timeit(fn, args.iters, args.flush)
+            flops = 4.0 * B * nh * L * L * D * k
+            print(f"{name:18s} dropout {pd}: {ms * 1e3:8.1f} us  {flops / ms / 1e9:8.2f} TFLOP/s")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["conv", "wgrad", "pointwise", "tails"])
+    ap.add_argument("what", choices=["conv", "wgrad", "pointwise", "tails", "mha"])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--flush", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
-    {"conv": bench_conv, "wgrad": bench_wgrad, "pointwise": bench_pointwise, "tails": bench_tails}[a.what](a)
+    {"conv": bench_conv, "wgrad": bench_wgrad, "pointwise": bench_pointwise, "tails": bench_tails, "mha": bench_mha}[a.what](a)
