@@ -19,51 +19,67 @@ def _get(cfg, name):
     return cfg[name] if isinstance(cfg, dict) else getattr(cfg, name)
 
 
+def _build_simple_cnn(model_cfg, n_in, n_out):
+    extra = {k: v for k, v in dict(model_cfg).items() if k != "type"}
+    return SimpleCNN(n_input_channels=n_in, n_output_channels=n_out, **extra)
+
+
+def _build_cnn_transformer(model_cfg, n_in, n_out):
+    keys = ("embed_dim", "depth", "n_heads", "mlp_dim", "dropout")
+    return CNNTransformer(in_channels=n_in, out_channels=n_out, **{k: _get(model_cfg, k) for k in keys})
+
+
+def _build_att_unet(model_cfg, n_in, n_out):
+    # the reference hard-codes 7 input channels here (5 forcings + sin/cos month), whatever cfg.data lists
+    return AttUNetConvLSTM(in_ch=7, out_ch=n_out, base=_get(model_cfg, "base_channels"))
+
+
+def _build_unet(model_cfg, n_in, n_out):
+    return UNet(in_ch=n_in, out_ch=n_out, base=_get(model_cfg, "base_channels"))
+
+
+_BUILDERS = {"SimpleCNN": _build_simple_cnn, "cnn_transformer": _build_cnn_transformer,
+             "unet_convlstm_attention": _build_att_unet, "unet": _build_unet}
+
+
 def get_model(cfg):
+    """cfg.model.type selects the architecture; channel counts come from cfg.data.{input_vars,output_vars}."""
     model_cfg, data_cfg = _get(cfg, "model"), _get(cfg, "data")
-    mtype = _get(model_cfg, "type")
-    n_in, n_out = len(_get(data_cfg, "input_vars")), len(_get(data_cfg, "output_vars"))
-    if mtype == "SimpleCNN":
-        kwargs = {k: v for k, v in dict(model_cfg).items() if k != "type"}
-        return SimpleCNN(n_input_channels=n_in, n_output_channels=n_out, **kwargs)
-    elif mtype == "cnn_transformer":
-        return CNNTransformer(in_channels=n_in, out_channels=n_out, embed_dim=_get(model_cfg, "embed_dim"),
-                              depth=_get(model_cfg, "depth"), n_heads=_get(model_cfg, "n_heads"),
-                              mlp_dim=_get(model_cfg, "mlp_dim"), dropout=_get(model_cfg, "dropout"))
-    elif mtype == "unet_convlstm_attention":
-        return AttUNetConvLSTM(in_ch=7, out_ch=n_out, base=_get(model_cfg, "base_channels"))
-    elif mtype == "unet":
-        return UNet(in_ch=n_in, out_ch=n_out, base=_get(model_cfg, "base_channels"))
-    else:
-        raise ValueError(f"Unknown model type: {mtype}")
+    kind = _get(model_cfg, "type")
+    if kind not in _BUILDERS:
+        raise ValueError(f"Unknown model type: {kind}")
+    return _BUILDERS[kind](model_cfg, len(_get(data_cfg, "input_vars")), len(_get(data_cfg, "output_vars")))
 
 
 def _conv_bn(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool, res=None):
-    stride = conv.stride[0]
-    y = ops_nn.Conv2dFn.apply(x, conv.weight, conv.bias, stride, conv.padding[0], False)
+    y = ops_nn.Conv2dFn.apply(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], False)
     return ops_nn.batch_norm(y, bn, res=res, relu=relu)
 
 
+def _same_conv(c_in, c_out, k, stride=1):
+    return nn.Conv2d(c_in, c_out, k, stride=stride, padding=k // 2)
+
+
 class ResidualBlock(nn.Module):
+    """conv-BN-ReLU-conv-BN + (identity | 1x1 conv-BN) -> ReLU.  Registered children, in order: conv1, bn1, relu,
+    conv2, bn2, skip — the parameter containers of the reference block."""
+
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=1):
         super().__init__()
-        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=kernel_size // 2)
-        self.bn1 = nn.BatchNorm2d(out_channels)
+        k, projected = kernel_size, (stride != 1 or in_channels != out_channels)
+        self.conv1, self.bn1 = _same_conv(in_channels, out_channels, k, stride), nn.BatchNorm2d(out_channels)
         self.relu = nn.ReLU(inplace=True)
-        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size, padding=kernel_size // 2)
-        self.bn2 = nn.BatchNorm2d(out_channels)
-        self.skip = nn.Sequential()
-        if stride != 1 or in_channels != out_channels:
-            self.skip = nn.Sequential(
-                nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=stride), nn.BatchNorm2d(out_channels)
-            )
+        self.conv2, self.bn2 = _same_conv(out_channels, out_channels, k), nn.BatchNorm2d(out_channels)
+        # (built only when needed: constructing it unconditionally would consume RNG draws the reference does not make)
+        self.skip = nn.Sequential(*([nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=stride),
+                                     nn.BatchNorm2d(out_channels)] if projected else []))
         self.out_channels = out_channels
 
     def forward_nhwc(self, x):
         x, xs = ops_nn.fork(x)
         out = _conv_bn(x, self.conv1, self.bn1, relu=True)
         identity = _conv_bn(xs, self.skip[0], self.skip[1], relu=False) if len(self.skip) else xs
-        # bn2 + residual add + ReLU in one pass (:68-71)
+        # bn2 + residual add + ReLU in one pass
         return _conv_bn(out, self.conv2, self.bn2, relu=True, res=identity)
 
     def forward(self, x):
@@ -72,27 +88,19 @@ class ResidualBlock(nn.Module):
 
 
 class SimpleCNN(nn.Module):
+    """Stem (conv-BN-ReLU) -> `depth` residual blocks (width doubles in all but the last) -> Dropout2d -> conv-BN-ReLU
+    -> 1x1 conv.  Children: initial, res_blocks, dropout, final."""
+
     def __init__(self, n_input_channels, n_output_channels, kernel_size=3, init_dim=64, depth=4, dropout_rate=0.2):
         super().__init__()
-        self.initial = nn.Sequential(
-            nn.Conv2d(n_input_channels, init_dim, kernel_size=kernel_size, padding=kernel_size // 2),
-            nn.BatchNorm2d(init_dim),
-            nn.ReLU(inplace=True),
-        )
-        self.res_blocks = nn.ModuleList()
-        current_dim = init_dim
-        for i in range(depth):
-            out_dim = current_dim * 2 if i < depth - 1 else current_dim
-            self.res_blocks.append(ResidualBlock(current_dim, out_dim))
-            if i < depth - 1:
-                current_dim *= 2
+        k = kernel_size
+        self.initial = nn.Sequential(_same_conv(n_input_channels, init_dim, k), nn.BatchNorm2d(init_dim), nn.ReLU(inplace=True))
+        widths = [init_dim * 2 ** min(i, depth - 1) for i in range(depth + 1)]       # 64, 128, 256, 512, 512
+        self.res_blocks = nn.ModuleList(ResidualBlock(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        top = widths[-1] if depth > 0 else init_dim
         self.dropout = nn.Dropout2d(dropout_rate)
-        self.final = nn.Sequential(
-            nn.Conv2d(current_dim, current_dim // 2, kernel_size=kernel_size, padding=kernel_size // 2),
-            nn.BatchNorm2d(current_dim // 2),
-            nn.ReLU(inplace=True),
-            nn.Conv2d(current_dim // 2, n_output_channels, kernel_size=1),
-        )
+        self.final = nn.Sequential(_same_conv(top, top // 2, k), nn.BatchNorm2d(top // 2), nn.ReLU(inplace=True),
+                                   nn.Conv2d(top // 2, n_output_channels, kernel_size=1))
 
     def forward(self, x):
         a = ops.StageIn.apply(x, compute_dtype())

@@ -12,16 +12,19 @@ from .. import ops
 from ..config import compute_dtype
 
 
+def _pointwise(c_in, c_out):
+    return nn.Conv2d(c_in, c_out, 1, bias=False)
+
+
 class SEBlock(nn.Module):
-    """Channel-wise squeeze-and-excitation (ratio = 8)."""
+    """Squeeze-and-excitation with reduction r: children `avg` (global average pool) and `fc`
+    (1x1 conv C -> C/r, ReLU, 1x1 conv C/r -> C, Sigmoid; no biases)."""
 
     def __init__(self, c: int, r: int = 8):
         super().__init__()
+        hidden = c // r
         self.avg = nn.AdaptiveAvgPool2d(1)
-        self.fc = nn.Sequential(
-            nn.Conv2d(c, c // r, 1, bias=False), nn.ReLU(inplace=True),
-            nn.Conv2d(c // r, c, 1, bias=False), nn.Sigmoid()
-        )
+        self.fc = nn.Sequential(_pointwise(c, hidden), nn.ReLU(inplace=True), _pointwise(hidden, c), nn.Sigmoid())
 
     def forward(self, x):
         N, C, H, W = x.shape
@@ -33,7 +36,7 @@ class SEBlock(nn.Module):
 
 
 class SpatialGate(nn.Module):
-    """7x7 conv on concatenated mean- & max-over-channel maps (CBAM style)."""
+    """CBAM-style spatial attention: child `conv` = 7x7, 2 -> 1 channels, no bias, over [mean_C, max_C]."""
 
     def __init__(self):
         super().__init__()
@@ -48,17 +51,17 @@ class SpatialGate(nn.Module):
         return ops.StageOut.apply(y, C)
 
 
+def _conv_gn_silu(c_in, c_out):
+    return [nn.Conv2d(c_in, c_out, 3, padding=1, bias=False), nn.GroupNorm(8, c_out), nn.SiLU(inplace=True)]
+
+
 class ConvBlock(nn.Module):
+    """Children: `body` = Sequential[conv3x3, GroupNorm(8), SiLU, conv3x3, GroupNorm(8), SiLU], `se`, `spat`."""
+
     def __init__(self, c_in: int, c_out: int):
         super().__init__()
-        self.body = nn.Sequential(
-            nn.Conv2d(c_in, c_out, 3, padding=1, bias=False),
-            nn.GroupNorm(8, c_out), nn.SiLU(inplace=True),
-            nn.Conv2d(c_out, c_out, 3, padding=1, bias=False),
-            nn.GroupNorm(8, c_out), nn.SiLU(inplace=True),
-        )
-        self.se = SEBlock(c_out)
-        self.spat = SpatialGate()
+        self.body = nn.Sequential(*_conv_gn_silu(c_in, c_out), *_conv_gn_silu(c_out, c_out))
+        self.se, self.spat = SEBlock(c_out), SpatialGate()
         self.c_out = c_out
 
     def forward_nhwc(self, x):
@@ -72,10 +75,11 @@ class ConvBlock(nn.Module):
 
 
 class Down(nn.Module):
+    """MaxPool2d(2) then ConvBlock (children `pool`, `conv`)."""
+
     def __init__(self, c_in, c_out):
         super().__init__()
-        self.pool = nn.MaxPool2d(2)
-        self.conv = ConvBlock(c_in, c_out)
+        self.pool, self.conv = nn.MaxPool2d(2), ConvBlock(c_in, c_out)
 
     def forward_nhwc(self, x):
         return self.conv.forward_nhwc(ops.MaxPoolFn.apply(x))
@@ -86,6 +90,8 @@ class Down(nn.Module):
 
 
 class Up(nn.Module):
+    """ConvTranspose2d(k2, s2) of x, concatenated in front of the skip, then ConvBlock (children `up`, `conv`)."""
+
     def __init__(self, c_in, c_skip, c_out):
         super().__init__()
         self.up = nn.ConvTranspose2d(c_in, c_out, 2, stride=2)
@@ -93,7 +99,7 @@ class Up(nn.Module):
 
     def forward_nhwc(self, x, skip):
         if skip.shape[1] != 2 * x.shape[1] or skip.shape[2] != 2 * x.shape[2]:
-            # the reference fails at torch.cat (src/unet.py:68) for grids not divisible by 8
+            # the reference fails at torch.cat for grids not divisible by 8
             raise RuntimeError(f"Up: skip {tuple(skip.shape[1:3])} does not match upsampled "
                                f"{(2 * x.shape[1], 2 * x.shape[2])}")
         return self.conv.forward_nhwc(ops.UpCatFn.apply(x, skip, self.up.weight, self.up.bias))
@@ -105,19 +111,19 @@ class Up(nn.Module):
 
 
 class UNet(nn.Module):
-    """Depth-4 UNet with attention (single frame)."""
+    """Single-frame depth-4 U-Net with attention blocks.  Children in registration order: enc1, enc2, enc3, enc4,
+    bott, up3, up2, up1, head (widths base, 2base, 4base, 8base)."""
 
     def __init__(self, in_ch: int = 5, out_ch: int = 2, base: int = 16):
         super().__init__()
-        self.enc1 = ConvBlock(in_ch, base)
-        self.enc2 = Down(base, base * 2)
-        self.enc3 = Down(base * 2, base * 4)
-        self.enc4 = Down(base * 4, base * 8)
-        self.bott = ConvBlock(base * 8, base * 8)
-        self.up3 = Up(base * 8, base * 4, base * 4)
-        self.up2 = Up(base * 4, base * 2, base * 2)
-        self.up1 = Up(base * 2, base, base)
-        self.head = nn.Conv2d(base, out_ch, kernel_size=1)
+        w1, w2, w3, w4 = (base << k for k in range(4))
+        self.enc1 = ConvBlock(in_ch, w1)
+        for name, (a, b) in zip(("enc2", "enc3", "enc4"), ((w1, w2), (w2, w3), (w3, w4))):
+            setattr(self, name, Down(a, b))
+        self.bott = ConvBlock(w4, w4)
+        for name, (a, b) in zip(("up3", "up2", "up1"), ((w4, w3), (w3, w2), (w2, w1))):
+            setattr(self, name, Up(a, b, b))
+        self.head = nn.Conv2d(w1, out_ch, kernel_size=1)
 
     def forward(self, x):
         a = ops.StageIn.apply(x, compute_dtype())

@@ -92,3 +92,36 @@ def test_default_init_matches_reference_under_seed():
     for k, v in m.state_dict().items():
         s, n = float(v.double().sum()), float(v.double().norm())
         assert abs(s - want[k][0]) <= 1e-9 * max(1.0, abs(want[k][0])) and abs(n - want[k][1]) <= 1e-9 * max(1.0, want[k][1]), k
+
+
+def test_parameter_surface_and_default_init_match_reference():
+    """Same seed -> bit-identical state_dict (keys, order, shapes, values incl. BatchNorm buffers) as the reference's own
+    constructors, for every model of the family (only where /root/reference is mounted, i.e. in the build container)."""
+    import pytest
+    import torch
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference sources not mounted")
+    import pcm_b200  # noqa: F401
+    R = ref_loader.load()
+    from pcm_b200.src import models as M, unet as U
+    from pcm_b200.src.cnn_transformer import CNNTransformer
+    from pcm_b200.src.convlstm import ConvLSTM
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    pairs = [
+        (lambda: M.SimpleCNN(5, 2), lambda: R.models.SimpleCNN(5, 2)),
+        (lambda: M.SimpleCNN(5, 2, init_dim=8, depth=2), lambda: R.models.SimpleCNN(5, 2, init_dim=8, depth=2)),
+        (lambda: M.ResidualBlock(8, 8), lambda: R.models.ResidualBlock(8, 8)),
+        (lambda: U.UNet(5, 2, 16), lambda: R.unet.UNet(5, 2, 16)),
+        (lambda: AttUNetConvLSTM(7, 2, 16), lambda: R.unet_convlstm_attention.AttUNetConvLSTM(7, 2, 16)),
+        (lambda: CNNTransformer(), lambda: R.cnn_transformer.CNNTransformer()),
+        (lambda: ConvLSTM(16, 8), lambda: R.convlstm.ConvLSTM(16, 8)),
+    ]
+    for ours, ref in pairs:
+        torch.manual_seed(42)
+        a = ours().state_dict()
+        torch.manual_seed(42)
+        b = ref().state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
