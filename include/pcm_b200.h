@@ -133,6 +133,18 @@ PCM_API int pcm_convT2x2_dgrad_tc(const void* dy, long long dy_ns, int dy_ps, in
 PCM_API int pcm_convT2x2_wgrad_tc(const void* a, long long a_ns, int a_ps, int Ca, int Ca_real, const void* b,
                                   long long b_ns, int b_ps, int Cb, int Cb_real, float* dw, long long sa,
                                   long long sb, long long st, int N, int H, int W, pcm_stream_t s);
+/* nn.Conv2d(kernel 3, stride 2, padding 1) (src/cnn_transformer.py:10,12) on the tensor cores, in "pixel pair" form: the
+ * (2H, 2W) input with Cs dense channels is viewed as {(pw, c), w, ph, h, n}; the GEMM has 6 taps q = kh*2 + (dw+1) of
+ * K = 2*Cs (the (dw = -1, pw = 0) half of the weights is zero).  H, W = OUTPUT grid.
+ *   forward  wk: bf16 [6][Cout][2*Cs], wk[q][co][pw*Cs + c] = w[co][c][kh][2*(dw+1) + pw - 1]
+ *   dgrad    dx(2h+ph, 2w+pw, c) = sum_{oh,ow in {0,1}} sum_co dy(h+oh, w+ow, co) * wk[oh*2+ow][(ph*2+pw)*Cq + c][co]
+ *   wgrad    dw[co*sa + (pw*Cs + c)*sb + q*st] += sum dy(n,h,w,co) * x(n, 2h+kh-1, 2(w+dw)+pw, c) */
+PCM_API int pcm_conv3x3s2_tc(const void* src, long long src_ns, int Cs, int H, int W, void* dst, long long dst_ns,
+                             int dst_ps, int Cout, const void* wk, const float* bias, int N, int relu, pcm_stream_t s);
+PCM_API int pcm_conv3x3s2_dgrad_tc(const void* dy, long long dy_ns, int dy_ps, int H, int W, int Cout, void* dx,
+                                   long long dx_ns, int dx_ps, int Cq, const void* wk, int N, pcm_stream_t s);
+PCM_API int pcm_wgrad3x3s2_tc(const void* dy, long long dy_ns, int dy_ps, int Co, const void* x, long long x_ns, int Cs,
+                              float* dw, long long sa, long long sb, long long st, int N, int H, int W, pcm_stream_t s);
 /* number of bounded-wait timeouts recorded by the tensor-core kernels since load (0 when healthy; syncs) */
 PCM_API int pcm_tc_error_count(void);
 /* weight gradient: dw[ac*sa + bc*sb + tap*st] += sum_{n,ha,wa} A(n,ha,wa,ac) * B(n,hb,wb,bc),

@@ -31,6 +31,9 @@ struct ConvTcParams {
   int ksz, relu;          // kernel size (1 or 3; pad = ksz/2), ReLU in the store epilogue
   int mode;               // 0: conv taps (shifted boxes) ; 1: ConvTranspose2d(k2,s2) data gradient — 4 taps (kh,kw), tap q
                           //    gathers dy(2h+kh, 2w+kw) through the 5-D views tmA (kh=0) / tmA2 (kh=1) {C, kw, w, h, n}
+                          // 2: 3x3 / stride-2 / pad-1 conv — the input is viewed as {2C (pw, c), W/2, ph, H/2, n}; 6 taps
+                          //    (kh, dw): tap row 2h+kh-1 = (ph, h+oh), columns 2(w+dw)+pw with the unused (dw=-1, pw=0) weights zero
+  int pad;                // conv taps: leading zero padding (ksz/2 for 'same', 0 for the stride-2 data-gradient taps)
   int ps_co;              // > 0: ConvTranspose2d(k2,s2) forward — GEMM column q*ps_co + co is stored at pixel
                           //    (2h + q/2, 2w + q%2), channel co of a (2H, 2W) destination (pixel shuffle in the epilogue)
   long long dst_ns;
@@ -86,7 +89,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int ntaps = p.mode == 1 ? 4 : p.ksz * p.ksz, kpad = p.ksz >> 1;
+  const int ntaps = p.mode == 1 ? 4 : p.mode == 2 ? 6 : p.ksz * p.ksz, kpad = p.pad;
   const int kiters = ntaps * p.kchunks;
 
   if (warp == 0) {
@@ -110,6 +113,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.mode == 1)
               tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, (tap >> 1) ? &tmA2 : &tmA, &full[stage], kc * p.KC, tap & 1, w0,
                           h0, n0);
+            else if (p.mode == 2)     // tap = kh*2 + (dw+1): kh 0 -> (ph 1, h-1), 1 -> (ph 0, h), 2 -> (ph 1, h)
+              tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + (tap & 1) - 1,
+                          (tap >> 1) != 1 ? 1 : 0, h0 - ((tap >> 1) == 0 ? 1 : 0), n0);
             else
               tma_load_4d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], kc * p.KC, w0 + kw - kpad, h0 + kh - kpad, n0);
             if (EPI == 1) {
@@ -574,7 +580,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, const float* lstm_gx, const float* lstm_c_prev,
                            float* lstm_c_out, void* lstm_acts, pcm_stream_t s, int ksz = 3, int relu = 0, int mode = 0,
-                           int ps_co = 0) {
+                           int ps_co = 0, int pad = -1) {
   PCM_REQUIRE(Cin % 16 == 0 && Cin >= 16, "conv3x3_tc: Cin must be a multiple of 16 (got %d)", Cin);
   PCM_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv3x3_tc: Cin above 64 must be a multiple of 64 (got %d)", Cin);
   PCM_REQUIRE(Cin == 16 || Cin == 32 || Cin >= 64, "conv3x3_tc: unsupported Cin %d", Cin);
@@ -684,7 +690,8 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   p.KC = Cin < 64 ? Cin : 64;
   p.kchunks = Cin / p.KC;
   p.ksz = ksz; p.relu = relu; p.mode = mode; p.ps_co = ps_co;
-  const int ntaps = mode == 1 ? 4 : ksz * ksz;
+  p.pad = pad >= 0 ? pad : (ksz >> 1);
+  const int ntaps = mode == 1 ? 4 : mode == 2 ? 6 : ksz * ksz;
   p.dst_ns = dst_ns; p.dst_ps = dst_ps; p.dst_f32 = dst_f32; p.accumulate = accumulate;
   const int ncols = lstm_gx != nullptr ? 64 : Cout;        // accumulator columns per work item (fused ConvLSTM: 4 x 16)
   p.acc_stride = ncols < 32 ? 32 : ncols;
@@ -714,6 +721,14 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     if (rc != PCM_OK) return rc;
     rc = make_tensor_map(&tmA2, base + (size_t)2 * W * src_ps, 5, dims, strides, box, p.KC * 2);
     if (rc != PCM_OK) return rc;
+  } else if (mode == 2) {
+    // src is the (2H, 2W) input with dense channels (Cin = 2 * pixel stride): view {(pw, c), w, ph, h, n}
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, 2, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)2 * W * Cin * 2, (uint64_t)src_ns * 2};
+    uint32_t box[5] = {(uint32_t)p.KC, (uint32_t)p.Wb, 1, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    int rc = make_tensor_map(&tmA, src, 5, dims, strides, box, p.KC * 2);
+    if (rc != PCM_OK) return rc;
+    tmA2 = tmA;
   } else {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)src_ps * 2, (uint64_t)W * src_ps * 2, (uint64_t)src_ns * 2};
@@ -785,4 +800,24 @@ extern "C" int pcm_convT2x2_dgrad_tc(const void* dy, long long dy_ns, int dy_ps,
                                      long long dx_ns, int dx_ps, int Cin, const void* wk, int N, pcm_stream_t s) {
   return conv3x3_tc_impl(dy, dy_ns, dy_ps, H, W, Cout, dx, dx_ns, dx_ps, Cin, wk, nullptr, N, 0, 0, nullptr, nullptr, nullptr,
                          nullptr, s, 1, 0, 1, 0);
+}
+
+// 3x3 / stride-2 / pad-1 convolution (src/cnn_transformer.py:10,12) on the tensor cores.  src: (2H, 2W) image with Cs
+// dense channels (pixel stride == Cs); the GEMM sees pixel pairs: K = 2*Cs per tap, 6 taps (kh, dw).
+// wk: bf16 [6][Cout][2*Cs], tap kh*2 + (dw+1), channel pw*Cs + c = w[co][c][kh][2*(dw+1) + pw - 1] (0 where that kw < 0).
+extern "C" int pcm_conv3x3s2_tc(const void* src, long long src_ns, int Cs, int H, int W, void* dst, long long dst_ns,
+                                int dst_ps, int Cout, const void* wk, const float* bias, int N, int relu, pcm_stream_t s) {
+  PCM_REQUIRE(Cs % 8 == 0, "conv3x3s2_tc: source channels must be a multiple of 8 (got %d)", Cs);
+  return conv3x3_tc_impl(src, src_ns, Cs, H, W, 2 * Cs, dst, dst_ns, dst_ps, Cout, wk, bias, N, 0, 0, nullptr, nullptr, nullptr,
+                         nullptr, s, 3, relu, 2, 0);
+}
+
+// ... and its data gradient: dx(2h+ph, 2w+pw, c) = sum_{oh,ow in {0,1}} sum_co dy(h+oh, w+ow, co) * wk[oh*2+ow][(ph*2+pw)*Cq + c][co]
+// (a 2x2-tap convolution of dy without leading padding whose 4*Cq output columns are pixel-shuffled into the (2H, 2W)
+// gradient image).  Cq: channel count (= pixel stride granularity) of dx, multiple of 16, 4*Cq <= 256.
+extern "C" int pcm_conv3x3s2_dgrad_tc(const void* dy, long long dy_ns, int dy_ps, int H, int W, int Cout, void* dx,
+                                      long long dx_ns, int dx_ps, int Cq, const void* wk, int N, pcm_stream_t s) {
+  PCM_REQUIRE(Cq % 16 == 0 && 4 * Cq <= 256, "conv3x3s2_dgrad_tc: Cq must be a multiple of 16, <= 64 (got %d)", Cq);
+  return conv3x3_tc_impl(dy, dy_ns, dy_ps, H, W, Cout, dx, dx_ns, dx_ps, 4 * Cq, wk, nullptr, N, 0, 0, nullptr, nullptr, nullptr,
+                         nullptr, s, 2, 0, 0, Cq, 0);
 }

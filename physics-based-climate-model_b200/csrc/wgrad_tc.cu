@@ -89,11 +89,20 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint8_t* b = sB + (size_t)stage * p.b_stage_bytes;
         for (int c = 0; c < p.na_chunks; ++c)
           tma_load_4d(a + (size_t)c * p.a_chunk_bytes, &tmA, &full[stage], mtile * 128 + c * p.Cca, 0, h0, n0);
-        if (p.convt) {
+        if (p.convt == 1) {
           for (int q = 0; q < 4; ++q)
             for (int c = 0; c < p.nb_chunks; ++c)
               tma_load_5d(b + (size_t)q * p.b_sub_bytes + (size_t)c * p.b_chunk_bytes, (q >> 1) ? &tmB2 : &tmB, &full[stage],
                           c * p.Ccb, q & 1, 0, h0, n0);
+        } else if (p.convt == 2) {
+          // 3x3 / stride-2 conv: tap q = kh*2 + (dw+1) reads rows 2h+kh-1 = (ph, h+oh) and pixel pairs w+dw of the input,
+          // viewed as {(pw, c), w, ph, h, n}
+          for (int q = 0; q < p.ntaps; ++q) {
+            const int kh = q >> 1;
+            for (int c = 0; c < p.nb_chunks; ++c)
+              tma_load_5d(b + (size_t)q * p.b_sub_bytes + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, (q & 1) - 1,
+                          kh != 1 ? 1 : 0, h0 - (kh == 0 ? 1 : 0), n0);
+          }
         } else {
           for (int c = 0; c < p.nb_chunks; ++c)
             tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, -(p.ksz >> 1), h0 - (p.ksz >> 1), n0);
@@ -204,7 +213,7 @@ using namespace pcm;
 static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                          long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
                          long long st, int N, int H, int W, int ksz, pcm_stream_t s, int convt = 0) {
-  const int pad = ksz >> 1, ntaps = convt ? 4 : ksz * ksz;
+  const int pad = ksz >> 1, ntaps = convt == 1 ? 4 : convt == 2 ? 6 : ksz * ksz;
   PCM_REQUIRE(Co % 16 == 0 && (Co <= 64 ? (Co == 16 || Co == 32 || Co == 64) : Co % 128 == 0),
               "wgrad3x3_tc: Co must be 16, 32, 64 or a multiple of 128 (got %d)", Co);
   PCM_REQUIRE(Ci % 16 == 0 && (Ci <= 64 ? (Ci == 16 || Ci == 32 || Ci == 64) : (Ci % 64 == 0 && Ci <= 256)),
@@ -234,7 +243,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   // K tile: whole images (with their zero rows) when small, else a block of image rows; capped so that one
   // pipeline stage (A: m_extent channels, B: Ci channels, bf16) stays near 100 KB (two stages fit)
   const int rows_full = (H + 2 * pad) * p.Wp;
-  int rows_cap = (int)((100 * 1024) / ((size_t)(m_extent + (convt ? 4 : 1) * Ci) * 2)) - 2 * pad * p.Wp - 2 * pad;
+  int rows_cap = (int)((100 * 1024) / ((size_t)(m_extent + (convt ? ntaps : 1) * Ci) * 2)) - 2 * pad * p.Wp - 2 * pad;
   if (rows_cap > 240) rows_cap = 240;
   if (rows_cap < 16) rows_cap = 16;
   int a_box_h, b_box_h;
@@ -268,8 +277,8 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   p.b_chunk_bytes = ((uint32_t)b_alloc * rbb + 1023u) & ~1023u;
   p.a_stage_bytes = p.a_chunk_bytes * p.na_chunks;
   p.b_sub_bytes = p.b_chunk_bytes * p.nb_chunks;
-  p.b_stage_bytes = p.b_sub_bytes * (convt ? 4 : 1);
-  p.tx_bytes = (uint32_t)a_rows * rba * p.na_chunks + (uint32_t)b_rows * rbb * p.nb_chunks * (convt ? 4 : 1);
+  p.b_stage_bytes = p.b_sub_bytes * (convt ? ntaps : 1);
+  p.tx_bytes = (uint32_t)a_rows * rba * p.na_chunks + (uint32_t)b_rows * rbb * p.nb_chunks * (convt ? ntaps : 1);
   // M blocks beyond the real channels alias the tile shifted by 8 rows (results unused, reads stay in bounds)
   p.lbo_a = (p.na_chunks * p.Cca >= 128) ? p.a_chunk_bytes : 8 * rba;
   p.lbo_b = p.b_chunk_bytes;
@@ -309,7 +318,15 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
     int rc = make_tensor_map(&tmA, dy, 4, dims, strides, box, rba);
     if (rc != PCM_OK) return rc;
   }
-  if (convt) {
+  if (convt == 2) {
+    // B is the (2H, 2W) conv input with dense channels Ci/2: view {(pw, c), w, ph, h, n}
+    uint64_t dims[5] = {(uint64_t)Ci, (uint64_t)W, 2, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[4] = {(uint64_t)Ci * 2, (uint64_t)W * Ci * 2, (uint64_t)2 * W * Ci * 2, (uint64_t)x_ns * 2};
+    uint32_t box[5] = {(uint32_t)p.Ccb, (uint32_t)p.Wp, 1, (uint32_t)b_box_h, (uint32_t)p.Nb};
+    int rc = make_tensor_map(&tmB, x, 5, dims, strides, box, rbb);
+    if (rc != PCM_OK) return rc;
+    tmB2 = tmB;
+  } else if (convt) {
     // B is the (2H, 2W) image; view {C, kw, w, h, n}: pixel (2h + kh, 2w + kw), kh folded into the base pointer
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(x);
     uint64_t dims[5] = {(uint64_t)Ci, 2, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -361,4 +378,12 @@ extern "C" int pcm_convT2x2_wgrad_tc(const void* a, long long a_ns, int a_ps, in
                                      long long b_ns, int b_ps, int Cb, int Cb_real, float* dw, long long sa,
                                      long long sb, long long st, int N, int H, int W, pcm_stream_t s) {
   return wgrad_tc_impl(a, a_ns, a_ps, Ca, Ca_real, b, b_ns, b_ps, Cb, Cb_real, dw, sa, sb, st, N, H, W, 1, s, 1);
+}
+
+// Weight gradient of the 3x3 / stride-2 / pad-1 convolution in the pixel-pair form of pcm_conv3x3s2_tc:
+// dw[co*sa + pc*sb + q*st] += sum_{n,h,w} dy(n,h,w,co) * x(n, 2h+kh-1, 2(w+dw)+pw, c), q = kh*2 + (dw+1), pc = pw*Cs + c.
+// dy: (H, W) output gradient; x: the (2H, 2W) input with Cs dense channels.
+extern "C" int pcm_wgrad3x3s2_tc(const void* dy, long long dy_ns, int dy_ps, int Co, const void* x, long long x_ns, int Cs,
+                                 float* dw, long long sa, long long sb, long long st, int N, int H, int W, pcm_stream_t s) {
+  return wgrad_tc_impl(dy, dy_ns, dy_ps, Co, Co, x, x_ns, Cs, 2 * Cs, 2 * Cs, dw, sa, sb, st, N, H, W, 1, s, 2);
 }

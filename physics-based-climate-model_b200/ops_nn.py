@@ -87,6 +87,67 @@ def wgrad_same(dy, x, dw, N, H, W, Co, Ci, Ci_real, K):
         c0 += cs
 
 
+# ------------------------------------------------------------------------------------------------
+# 3x3 / stride-2 / pad-1 convolution in "pixel pair" form on the tensor cores (csrc/conv_tc.cu mode 2)
+# ------------------------------------------------------------------------------------------------
+_S2_IDX = {}
+
+
+def _s2_indices(Co, Ci, Cip, dev):
+    """Gather tables (built once per shape) from the flat (Co, Ci, 3, 3) weight [+ one trailing zero] into
+    fwd  [6][Co][2*Cip]   : tap kh*2 + dwp, channel pw*Cip + c  <- w[co][c][kh][2*dwp + pw - 1]
+    dgrad[4][4*Cip][Co]   : tap oh*2 + ow, row (ph*2+pw)*Cip + c <- w[co][c][kh(ph,oh)][kw(pw,ow)]
+    and from the flat packed weight gradient [6][Co][2*Cip] back to (Co, Ci, 3, 3)."""
+    key = (Co, Ci, Cip, str(dev))
+    if key in _S2_IDX:
+        return _S2_IDX[key]
+    zero = Co * Ci * 9
+    widx = lambda co, c, kh, kw: ((co * Ci + c) * 3 + kh) * 3 + kw
+    fwd = torch.full((6, Co, 2 * Cip), zero, dtype=torch.long)
+    fold = torch.zeros((Co, Ci, 3, 3), dtype=torch.long)
+    co = torch.arange(Co).reshape(Co, 1)
+    c = torch.arange(Ci).reshape(1, Ci)
+    for kh in range(3):
+        for dwp in range(2):
+            for pw in range(2):
+                kw = 2 * dwp + pw - 1
+                if kw < 0:
+                    continue
+                fwd[kh * 2 + dwp, :, pw * Cip: pw * Cip + Ci] = widx(co, c, kh, kw)
+                fold[:, :, kh, kw] = ((kh * 2 + dwp) * Co + co) * (2 * Cip) + pw * Cip + c
+    dgr = torch.full((4, 4 * Cip, Co), zero, dtype=torch.long)
+    tap_of = {(0, 0): 1, (1, 1): 0, (1, 0): 2}                  # (parity, offset) -> kernel index; (0, 1) unused
+    cc = torch.arange(Ci).reshape(Ci, 1)
+    oo = torch.arange(Co).reshape(1, Co)
+    for ph in range(2):
+        for oh in range(2):
+            if (ph, oh) not in tap_of:
+                continue
+            for pw in range(2):
+                for ow in range(2):
+                    if (pw, ow) not in tap_of:
+                        continue
+                    q = ph * 2 + pw
+                    dgr[oh * 2 + ow, q * Cip: q * Cip + Ci, :] = widx(oo, cc, tap_of[(ph, oh)], tap_of[(pw, ow)])
+    out = (fwd.reshape(-1).to(dev), dgr.reshape(-1).to(dev), fold.reshape(-1).to(dev))
+    _S2_IDX[key] = out
+    return out
+
+
+def _s2_supported(x, w, stride, pad):
+    N, H, W, Cip = x.shape
+    Co, Ci, K, _ = w.shape
+    return (x.dtype == torch.bfloat16 and K == 3 and stride == 2 and pad == 1 and H % 2 == 0 and W % 2 == 0 and
+            Cip in (16, 32, 64) and Co % 16 == 0 and Co <= 256 and (Co in (16, 32, 64) or Co % 128 == 0) and
+            (Co * Ci * 9) % 8 == 0 and W // 2 <= 256 and H // 2 <= 256 and os.environ.get("PCM_S2_TC", "1") != "0")
+
+
+def _gather_weight(w, idx, shape, dtype):
+    """Layout gather of a weight tensor (index plumbing: every output element is one input element or zero)."""
+    flat = torch.cat([w.detach().reshape(-1), w.new_zeros(1)])
+    return flat[idx].reshape(shape).to(dtype)
+
+
 class Conv2dFn(torch.autograd.Function):
     """nn.Conv2d(Ci, Co, K, stride, padding=K//2 (stride 1) or 1 (K=3, stride 2), bias) on NHWC, optional fused ReLU
     (src/models.py:47,50,57,90,108; src/cnn_transformer.py:10,12)."""
@@ -100,6 +161,15 @@ class Conv2dFn(torch.autograd.Function):
         assert Ci <= Cip and Co % 8 == 0
         dt = x.dtype
         Ho, Wo = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
+        if _s2_supported(x, w, stride, pad):
+            fwd_idx, _, _ = _s2_indices(Co, Ci, Cip, x.device)
+            wk = _gather_weight(w, fwd_idx, (6, Co, 2 * Cip), dt)
+            y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=dt)
+            _call("pcm_conv3x3s2_tc", x.data_ptr(), H * W * Cip, Cip, Ho, Wo, y.data_ptr(), Ho * Wo * Co, Co, Co, wk.data_ptr(),
+                  _p(b), N, int(relu), _s())
+            ctx.save_for_backward(x, w, b, y if relu else None)
+            ctx.cfg = (stride, pad, relu, Ho, Wo)
+            return y
         wk = pack_weight(w, Ci * K * K, K * K, 1, Co, Ci, K * K, dt, Ip=Cip)
         if stride == 1 and pad == K // 2:
             y = conv_same(x, wk, N, H, W, Cip, Co, K, bias=b, relu=relu)
@@ -123,7 +193,15 @@ class Conv2dFn(torch.autograd.Function):
             dy = dz
         gw, rw = _grad_buf(w)
         KK = K * K
-        if stride == 1 and pad == K // 2:
+        s2 = _s2_supported(x, w, stride, pad)
+        if s2:
+            _, dgr_idx, fold_idx = _s2_indices(Co, Ci, Cip, x.device)
+            tmp = torch.zeros((6, Co, 2 * Cip), device=x.device, dtype=torch.float32)
+            _call("pcm_wgrad3x3s2_tc", dy.data_ptr(), Ho * Wo * Co, Co, Co, x.data_ptr(), H * W * Cip, Cip, tmp.data_ptr(),
+                  2 * Cip, 1, Co * 2 * Cip, N, Ho, Wo, _s())
+            folded = tmp.reshape(-1)[fold_idx]                                  # layout gather back to (Co, Ci, 3, 3)
+            _call("pcm_add", gw.data_ptr(), folded.data_ptr(), gw.data_ptr(), gw.numel(), 0, _s())
+        elif stride == 1 and pad == K // 2:
             wgrad_same(dy, x, gw, N, H, W, Co, Cip, Ci, K)
         else:
             conv_wgrad(dy, x, gw, Ci * KK, KK, 1, N, Ho, Wo, Co, Co, H, W, Cip, Ci, K, K, stride, pad)
@@ -132,7 +210,12 @@ class Conv2dFn(torch.autograd.Function):
             gb, rb = _grad_buf(b)
             channel_sum(dy, gb, N, Ho * Wo, Co, Co)
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and s2:
+            wkd = _gather_weight(w, dgr_idx, (4, 4 * Cip, Co), dt)
+            dx = torch.empty_like(x)
+            _call("pcm_conv3x3s2_dgrad_tc", dy.data_ptr(), Ho * Wo * Co, Co, Ho, Wo, Co, dx.data_ptr(), H * W * Cip, Cip, Cip,
+                  wkd.data_ptr(), N, _s())
+        elif ctx.needs_input_grad[0]:
             if stride == 1 and pad == K // 2:
                 # data gradient == forward conv of dy with flipped taps and transposed channels
                 wkt = pack_weight(w, KK, Ci * KK, -1, Ci, Co, KK, dt, offset=KK - 1, Op=Cip)

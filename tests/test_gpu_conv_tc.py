@@ -337,3 +337,37 @@ def test_mha_bwd_tc_matches_reference(ops, cfg):
         o = (torch.softmax(q @ k.transpose(-1, -2) * sc, dim=-1) @ v).transpose(1, 2).reshape(B, L, E)
         o.backward(dout.double())
         assert float((a - x.grad).norm() / x.grad.norm()) < 1.5e-2
+
+
+@pytest.mark.parametrize("cfg", [(3, 48, 72, 5, 16, 64), (2, 24, 36, 64, 64, 128), (2, 12, 20, 32, 32, 32)])
+def test_conv3x3_stride2_tc_matches_reference(ops, cfg):
+    """3x3 / stride-2 / pad-1 conv (+bias +ReLU) forward, data gradient and weight gradient on the tensor cores (pixel-pair
+    form) against torch's CPU conv2d on the same bf16-rounded operands."""
+    from pcm_b200 import ops_nn
+    from pcm_b200._lib import lib
+    N, H, W, Ci, Cip, Co = cfg
+    g = torch.Generator().manual_seed(N + H + Ci + Co)
+    x = torch.zeros(N, H, W, Cip)
+    x[..., :Ci] = torch.randn(N, H, W, Ci, generator=g)
+    x = x.bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Ci ** 0.5)).bfloat16().float()
+    b = torch.randn(Co, generator=g)
+    xr = x[..., :Ci].double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True)
+    want = F.relu(F.conv2d(xr, wr, br, stride=2, padding=1))
+    xg = x.cuda().requires_grad_(True)
+    wg, bg = torch.nn.Parameter(w.cuda()), torch.nn.Parameter(b.cuda())
+    y = ops_nn.Conv2dFn.apply(xg, wg, bg, 2, 1, True)
+    assert lib().last_call == "pcm_conv3x3s2_tc"
+    got = y.float().cpu().permute(0, 3, 1, 2)
+    assert float((got - want.detach().float()).norm() / want.norm()) < 4e-3
+    dy = (torch.randn(y.shape, generator=g) / y.numel() ** 0.5).bfloat16()
+    y.backward(dy.cuda())
+    want.backward(dy.double().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    assert float((wg.grad.cpu().double() - wr.grad).norm() / wr.grad.norm()) < 2e-3      # dy is ReLU-masked in bf16
+    assert float((bg.grad.cpu().double() - br.grad).norm() / br.grad.norm()) < 2e-3
+    dx = xg.grad.float().cpu()[..., :Ci].permute(0, 3, 1, 2)
+    assert float((dx.double() - xr.grad).norm() / xr.grad.norm()) < 6e-3
