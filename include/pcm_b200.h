@@ -204,20 +204,24 @@ PCM_API int pcm_convblock_fused_supported(int H, int W, int C, int Cr, int dtype
 PCM_API int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const float* beta, float* stats, void* y, int N,
                                 int H, int W, int C, float eps, int dtype, pcm_stream_t s);
 /* tail 2: out = a*se*gate, a = silu(GroupNorm(x)), se = sigmoid(W2 relu(W1 mean_p a)),
- * gate = sigmoid(conv7x7([mean_c a*se, max_c a*se])).  Saves stats, pool[n][C] (= sum_p a), se[n][C], hid[n][Cr]. */
+ * gate = sigmoid(conv7x7([mean_c a*se, max_c a*se])).  Saves stats, pool[n][C] (= sum_p a), se[n][C], hid[n][Cr]
+ * and, when `maps` / `ties` are non-null (training; both or neither), maps[n] = mean[P] | max[P] | gate[P] (fp32)
+ * and ties[n][P] = number of channels attaining the maximum (x.amax splits its gradient between them). */
 PCM_API int pcm_convblock_tail_fwd(const void* x, const float* gamma, const float* beta, const float* w1,
                                    const float* w2, const float* wsp, float* stats, float* pool, float* se,
-                                   float* hid, void* out, int N, int H, int W, int C, int Cr, float eps, int dtype,
-                                   pcm_stream_t s);
+                                   float* hid, float* maps, unsigned char* ties, void* out, int N, int H, int W,
+                                   int C, int Cr, float eps, int dtype, pcm_stream_t s);
 /* backward of tail 1: da -> dx; dgamma, dbeta accumulate */
 PCM_API int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* stats, const float* gamma,
                                 const float* beta, void* dx, float* dgamma, float* dbeta, int N, int H, int W, int C,
                                 float eps, int dtype, pcm_stream_t s);
-/* backward of tail 2 (recomputes a, the channel maps and the gate from x): dout -> dx; dgamma, dbeta, dw1, dw2,
- * dwsp accumulate */
-PCM_API int pcm_convblock_tail_bwd(const void* dout, const void* x, const float* stats, const float* gamma,
-                                   const float* beta, const float* w1, const float* w2, const float* wsp,
-                                   const float* pool, const float* se, const float* hid, void* dx, float* dgamma,
+/* backward of tail 2: dout -> dx; dgamma, dbeta, dw1, dw2, dwsp accumulate.  `out`, `maps`, `ties` are what the
+ * forward tail produced for the same x (the gate's pre-activation gradient is (1 - gate) * sum_c dout*out; a is
+ * recomputed from x for the rest).  x must be 16-byte aligned. */
+PCM_API int pcm_convblock_tail_bwd(const void* dout, const void* x, const void* out, const float* stats,
+                                   const float* gamma, const float* beta, const float* w1, const float* w2,
+                                   const float* wsp, const float* pool, const float* se, const float* hid,
+                                   const float* maps, const unsigned char* ties, void* dx, float* dgamma,
                                    float* dbeta, float* dw1, float* dw2, float* dwsp, int N, int H, int W, int C,
                                    int Cr, float eps, int dtype, pcm_stream_t s);
 

@@ -46,11 +46,18 @@ def algo_cost(name: str, args):
     if name == "pcm_convT2x2_wgrad_tc":
         px = a["N"] * a["H"] * a["W"]
         return 2.0 * px * a["Ca"] * 4 * a["Cb"], px * (a["Ca"] + 4 * a["Cb"]) * 2 + 4 * a["Ca_real"] * a["Cb_real"] * 4, "tensor"
-    # per-image fused ConvBlock tails: every tensor once (x in, y out; backward: dout + x in, dx out)
-    if name in ("pcm_gn_silu_img_fwd", "pcm_convblock_tail_fwd"):
+    # per-image fused ConvBlock tails: every tensor once (x in, y out; backward: dout + x in, dx out); the second
+    # tail also writes / reads the saved gate maps (3 fp32 + 1 byte per pixel) and its backward reads `out`
+    if name == "pcm_gn_silu_img_fwd":
         return 0.0, 2 * a["N"] * a["H"] * a["W"] * a["C"] * es(), "hbm"
-    if name in ("pcm_gn_silu_img_bwd", "pcm_convblock_tail_bwd"):
+    if name == "pcm_convblock_tail_fwd":
+        px = a["N"] * a["H"] * a["W"]
+        return 0.0, 2 * px * a["C"] * es() + (13 * px if a["maps"] else 0), "hbm"
+    if name == "pcm_gn_silu_img_bwd":
         return 0.0, 3 * a["N"] * a["H"] * a["W"] * a["C"] * es(), "hbm"
+    if name == "pcm_convblock_tail_bwd":
+        px = a["N"] * a["H"] * a["W"]
+        return 0.0, 4 * px * a["C"] * es() + 13 * px, "hbm"
     if name in ("pcm_bn_stats",):
         return 0.0, a["R"] * a["C"] * es(), "hbm"
     if name in ("pcm_bn_apply_fwd",):

@@ -30,22 +30,32 @@ template <> __device__ __forceinline__ float sigmoid_t<__nv_bfloat16>(float z) {
   return fmaf(0.5f, t, 0.5f);
 }
 
-// add this thread's 8 per-channel partials (channel block cb = tid % cv) into dst[cb*8 + j]; lanes of a warp that
-// hold the same cb are combined with xor-shuffles first.  Must be called by every thread of the CTA.
-__device__ __forceinline__ void chan_add(float (&v)[8], float* dst, int cb, int cv) {
-  if (cv < 32) {
-    for (int off = cv; off < 32; off <<= 1) {
+// Per-channel sums over the image without shared-memory atomics (fp32 atomicAdd on shared memory is a CAS loop,
+// and every warp of the CTA would spin on the same C addresses).  chan_put: this thread's 8 per-channel partials
+// (channel block cb = tid % cv) go to part[slot][warp][C] after the lanes of the warp that hold the same cb are
+// combined with xor-shuffles; chan_finish: dst[slot][c] = sum over warps.  Both are called by every thread.
+__device__ __forceinline__ void chan_put(float (&v)[8], float* part, int slot, int cb, int cv, int C) {
+  for (int off = cv; off < 32; off <<= 1) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], off);
-    }
-    if ((int)(threadIdx.x & 31) < cv) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&dst[cb * 8 + j], v[j]);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&dst[cb * 8 + j], v[j]);
+    for (int j = 0; j < 8; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], off);
   }
+  if ((int)(threadIdx.x & 31) < cv) {
+    float4* d = reinterpret_cast<float4*>(part + ((size_t)slot * (NT >> 5) + (threadIdx.x >> 5)) * C + cb * 8);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+__device__ __forceinline__ void chan_finish(const float* part, int nslots, float* dst, int C) {
+  __syncthreads();
+  const int nw = NT >> 5;
+  for (int i = threadIdx.x; i < nslots * C; i += NT) {
+    const int slot = i / C, c = i - slot * C;
+    const float* src = part + (size_t)slot * nw * C + c;
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += src[w * C];
+    dst[i] = t;
+  }
+  __syncthreads();
 }
 
 // plain (generic-address) 8-element load: shared-memory reads and re-reads of this thread's own global writes
@@ -69,8 +79,14 @@ __device__ __forceinline__ void load8_rw(const T* p, float d[8]) {
 __host__ __device__ inline int plane_wp(int W) { return ((W + 7) / 8) * 8 + 8; }
 
 struct TailSmem {
-  size_t img, cm0, cm1, dq, gate, dm, cnt, fl, total;
+  size_t img, cm0, cm1, dq, gate, dm, bar, part, fl, total;
 };
+// threads per CTA: enough vectors per thread to amortise the phase barriers, few enough that small images get
+// several CTAs per SM (the kernels are register-limited to 512 threads per SM)
+__host__ __device__ inline int tail_threads(int H, int W, int C) {
+  const int nvec = H * W * (C / 8);
+  return nvec >= 4096 ? 512 : nvec >= 1536 ? 256 : 128;
+}
 // bwd: 0 = forward tails, 1 = backward tails (needs dq / dm / cnt as well)
 __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int elt, int full, int bwd) {
   TailSmem L;
@@ -83,7 +99,8 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
   L.dq = (full && bwd) ? PCM_TAKE(Pp * 4) : 0;
   L.gate = full ? PCM_TAKE(P * 4) : 0;
   L.dm = (full && bwd) ? PCM_TAKE(P * 8) : 0;
-  L.cnt = (full && bwd) ? PCM_TAKE(P) : 0;
+  L.bar = PCM_TAKE(16);                                  // mbarrier of the bulk copy that brings the image in
+  L.part = PCM_TAKE((size_t)4 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 4 slots x warps x C floats
   // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
   //         | wt[2][7][8] | wtf[2][7][8] | dw[100] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
   L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + (full ? C * C / 4 : 0)) * 4);
@@ -93,11 +110,13 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
 }
 
 struct TailPtrs {
+  float *part;
   float *ch0, *ch1, *ch2, *ch3, *ch4, *ca, *cb_, *se, *pool, *dpool, *dpre2, *hid, *dpre1, *mu, *rs, *m1, *m2, *wt, *wtf, *dw, *sw1, *sw2;
 };
 __device__ __forceinline__ TailPtrs tail_ptrs(uint8_t* smem, const TailSmem& L, int C) {
   float* f = reinterpret_cast<float*>(smem + L.fl);
   TailPtrs p;
+  p.part = reinterpret_cast<float*>(smem + L.part);
   p.ch0 = f; p.ch1 = f + C; p.ch2 = f + 2 * C; p.ch3 = f + 3 * C; p.ch4 = f + 4 * C;
   p.ca = f + 5 * C; p.cb_ = f + 6 * C;
   p.se = f + 7 * C; p.pool = f + 8 * C; p.dpool = f + 9 * C; p.dpre2 = f + 10 * C;
@@ -136,6 +155,50 @@ __device__ __forceinline__ void stencil_run8(const float* row0, int Wp, const fl
   }
 }
 
+// (mean, 1/std) of one group from its raw sums — ONE definition, so that the forward kernel and the backward
+// kernels (which start from the saved sums) derive bit-identical coefficients
+__device__ __forceinline__ void group_mu_rs(float S, float Q, float cnt, float eps, float& mu, float& rs) {
+  mu = S / cnt;
+  const float var = fmaxf(fmaf(-mu, mu, Q / cnt), 0.f);
+  rs = rsqrtf(var + eps);
+}
+// z = za*x + zb with za = gamma*rs, zb = beta - mu*za ; a = silu(z) rounded to the storage type.  The backward
+// tail compares u = a*se against the channel maximum the forward kernel saved, so both use this one definition.
+__device__ __forceinline__ void gn_coef(float gamma, float beta, float mu, float rs, float& za, float& zb) {
+  za = gamma * rs;
+  zb = fmaf(-mu, za, beta);
+}
+template <typename T>
+__device__ __forceinline__ float silu_act(float x, float za, float zb) {
+  const float z = fmaf(za, x, zb);
+  return round_to<T>(z * sigmoid_t<T>(z));
+}
+
+// ---- the image comes in through the bulk-copy engine (one thread issues, everybody waits on the mbarrier)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void image_copy_start(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
+  const uint32_t b = smem_addr(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = min(32768u, bytes - off);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst) + off), "l"(reinterpret_cast<const uint8_t*>(src) + off), "r"(n), "r"(b) : "memory");
+  }
+}
+__device__ __forceinline__ void image_copy_wait(uint64_t* bar) {
+  const uint32_t b = smem_addr(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(b) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();       // ~2 s: never hang the GPU
+  }
+}
+
 // GroupNorm statistics of the image in shared memory -> mu/rs per group (+ raw sums to `stats_out` when non-null)
 template <typename T>
 __device__ __forceinline__ void image_group_stats(const T* s_img, int nvec, int cv, int cg, int P, float eps,
@@ -151,18 +214,14 @@ __device__ __forceinline__ void image_group_stats(const T* s_img, int nvec, int 
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += x[j]; q[j] = fmaf(x[j], x[j], q[j]); }
   }
-  chan_add(s, sp.ch0, cb, cv);
-  chan_add(q, sp.ch1, cb, cv);
-  __syncthreads();
+  chan_put(s, sp.part, 0, cb, cv, cv * 8);
+  chan_put(q, sp.part, 1, cb, cv, cv * 8);
+  chan_finish(sp.part, 2, sp.ch0, cv * 8);
   if (threadIdx.x < kGroups) {
     const int g = threadIdx.x;
     float S = 0.f, Q = 0.f;
     for (int k = 0; k < cg; ++k) { S += sp.ch0[g * cg + k]; Q += sp.ch1[g * cg + k]; }
-    const float cnt = (float)cg * (float)P;
-    const float mu = S / cnt;
-    const float var = fmaxf(Q / cnt - mu * mu, 0.f);
-    sp.mu[g] = mu;
-    sp.rs[g] = rsqrtf(var + eps);
+    group_mu_rs(S, Q, (float)cg * (float)P, eps, sp.mu[g], sp.rs[g]);
     if (stats_out != nullptr) { stats_out[2 * g] = S; stats_out[2 * g + 1] = Q; }
   }
   __syncthreads();
@@ -171,11 +230,7 @@ __device__ __forceinline__ void image_group_stats(const T* s_img, int nvec, int 
 __device__ __forceinline__ void group_mu_rs_from_stats(const float* stats_n, int cg, int P, float eps, const TailPtrs& sp) {
   if (threadIdx.x < kGroups) {
     const int g = threadIdx.x;
-    const float cnt = (float)cg * (float)P;
-    const float mu = stats_n[2 * g] / cnt;
-    const float var = fmaxf(stats_n[2 * g + 1] / cnt - mu * mu, 0.f);
-    sp.mu[g] = mu;
-    sp.rs[g] = rsqrtf(var + eps);
+    group_mu_rs(stats_n[2 * g], stats_n[2 * g + 1], (float)cg * (float)P, eps, sp.mu[g], sp.rs[g]);
   }
 }
 
@@ -203,7 +258,8 @@ __global__ void __launch_bounds__(kFT, 1)
 convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ wsp,
                           float* __restrict__ stats, float* __restrict__ pool_g, float* __restrict__ se_g,
-                          float* __restrict__ hid_g, T* __restrict__ out, int H, int W, int C, int Cr, float eps) {
+                          float* __restrict__ hid_g, float* __restrict__ maps, uint8_t* __restrict__ ties,
+                          T* __restrict__ out, int H, int W, int C, int Cr, float eps) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
   const int cvs = __ffs(cv) - 1;
@@ -214,28 +270,23 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
   T* on = out + (size_t)n * P * C;
   const int cb = threadIdx.x & (cv - 1);
 
-#pragma unroll 4
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8];
-    load8(xn + (size_t)v * 8, t);
-    store8(s_img + (size_t)v * 8, t);
-  }
-  for (int i = threadIdx.x; i < 5 * C; i += NT) sp.ch0[i] = 0.f;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
   if (FULL) {
-    float* cm0 = reinterpret_cast<float*>(smem + L.cm0);       // cm0 and cm1 are contiguous
-    for (int i = threadIdx.x; i < 2 * (H + 6) * Wp; i += NT) cm0[i] = 0.f;
+    float4* z4 = reinterpret_cast<float4*>(smem + L.cm0);      // cm0 and cm1 are contiguous
+    for (int i = threadIdx.x; i < 2 * (H + 6) * Wp / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     load_gate_weights(wsp, sp);
     for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
   }
   __syncthreads();
+  image_copy_wait(bar);
   image_group_stats<T>(s_img, nvec, cv, cg, P, eps, sp, stats + (size_t)n * kGroups * 2);
 
   float ga[8], be[8], acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cb * 8 + j, g = c / cg;
-    ga[j] = __ldg(gamma + c) * sp.rs[g];
-    be[j] = fmaf(-sp.mu[g], ga[j], __ldg(beta + c));
+    gn_coef(__ldg(gamma + c), __ldg(beta + c), sp.mu[g], sp.rs[g], ga[j], be[j]);
     acc[j] = 0.f;
   }
 #pragma unroll 2
@@ -244,8 +295,7 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
     load8_rw(s_img + (size_t)v * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(ga[j], t[j], be[j]);
-      t[j] = round_to<T>(z * sigmoid_t<T>(z));
+      t[j] = silu_act<T>(t[j], ga[j], be[j]);
       acc[j] += t[j];
     }
     if (FULL) store8(s_img + (size_t)v * 8, t);
@@ -254,8 +304,8 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
   if (!FULL) return;
 
   // ---- squeeze / excite (SEBlock.forward, src/unet.py:16-17)
-  chan_add(acc, sp.ch2, cb, cv);
-  __syncthreads();
+  chan_put(acc, sp.part, 0, cb, cv, C);
+  chan_finish(sp.part, 1, sp.ch2, C);
   const float invP = 1.f / (float)P;
   for (int c = threadIdx.x; c < C; c += NT) pool_g[(size_t)n * C + c] = sp.ch2[c];
   // the two 1x1 "fc" matrices were staged in shared memory at kernel start; one warp per hidden unit
@@ -276,10 +326,14 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
   __syncthreads();
 
   // ---- channel mean / max of u = a*se (SpatialGate.forward, src/unet.py:26-27): each thread reduces its 8
-  // channels, the cv lanes of a pixel finish with a shuffle butterfly
+  // channels, the cv lanes of a pixel finish with a shuffle butterfly.  When `maps` is given (training) the maps,
+  // the gate and the number of channels that attain the maximum (amax splits its gradient between ties) are saved
+  // for the backward tail: maps[n] = mean[P] | max[P] | gate[P], ties[n][P].
   float* cm0 = reinterpret_cast<float*>(smem + L.cm0);
   float* cm1 = reinterpret_cast<float*>(smem + L.cm1);
   float* s_gate = reinterpret_cast<float*>(smem + L.gate);
+  float* mp = maps != nullptr ? maps + (size_t)n * 3 * P : nullptr;
+  uint8_t* tp = maps != nullptr ? ties + (size_t)n * P : nullptr;
   float sc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sc[j] = sp.se[cb * 8 + j];
@@ -287,27 +341,42 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
     const int nround = (nvec + NT - 1) / NT;
     const float invC = 1.f / (float)C;
     PixWalk pw(cvs, W);
+#pragma unroll 2
     for (int r = 0; r < nround; ++r, pw.next(W)) {
       const bool valid = pw.p < P;
       float sum = 0.f, mx = -INFINITY;
+      float u[8];
       if (valid) {
-        float t[8];
-        load8_rw(s_img + ((size_t)pw.p * cv + cb) * 8, t);
+        load8_rw(s_img + ((size_t)pw.p * cv + cb) * 8, u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float u = t[j] * sc[j];
-          sum += u;
-          mx = fmaxf(mx, u);
+          u[j] *= sc[j];
+          sum += u[j];
+          mx = fmaxf(mx, u[j]);
         }
       }
       for (int off = 1; off < cv; off <<= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, off);
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
       }
+      int cnt = 0;
+      if (mp != nullptr) {
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cnt += (u[j] == mx) ? 1 : 0;
+        }
+        for (int off = 1; off < cv; off <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+      }
       if (valid && cb == 0) {
         const int ip = (pw.h + 3) * Wp + pw.w + 4;
-        cm0[ip] = sum * invC;
+        const float mean = sum * invC;
+        cm0[ip] = mean;
         cm1[ip] = mx;
+        if (mp != nullptr) {
+          mp[pw.p] = mean;
+          mp[P + pw.p] = mx;
+          tp[pw.p] = (uint8_t)min(cnt, 255);
+        }
       }
     }
   }
@@ -323,8 +392,13 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
       stencil_run8(cm0 + h * Wp + w0, Wp, sp.wt, q);
       stencil_run8(cm1 + h * Wp + w0, Wp, sp.wt + 56, q);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (w0 + i < W) s_gate[h * W + w0 + i] = sigmoidf_(q[i]);
+      for (int i = 0; i < 8; ++i) {
+        if (w0 + i < W) {
+          const float gt = sigmoidf_(q[i]);
+          s_gate[h * W + w0 + i] = gt;
+          if (mp != nullptr) mp[2 * P + h * W + w0 + i] = gt;
+        }
+      }
     }
   }
   __syncthreads();
@@ -356,13 +430,8 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
   const T* dan = da + (size_t)n * P * C;
   T* dxn = dx + (size_t)n * P * C;
   const int cb = threadIdx.x & (cv - 1);
-#pragma unroll 4
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8];
-    load8(xn + (size_t)v * 8, t);
-    store8(s_img + (size_t)v * 8, t);
-  }
-  for (int i = threadIdx.x; i < 5 * C; i += NT) sp.ch0[i] = 0.f;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
   group_mu_rs_from_stats(stats + (size_t)n * kGroups * 2, cg, P, eps, sp);
   __syncthreads();
   // xhat = xa*x + xb ; z = za*x + zb
@@ -375,6 +444,7 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
     za[j] = gm[j] * xa[j]; zb[j] = fmaf(gm[j], xb[j], __ldg(beta + c));
     r0[j] = r1[j] = r2[j] = r3[j] = 0.f;
   }
+  image_copy_wait(bar);
   // pass 1: dxhat (stored to dx as scratch) and the reductions
 #pragma unroll 2
   for (int v = threadIdx.x; v < nvec; v += NT) {
@@ -396,11 +466,11 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
     }
     store8(dxn + (size_t)v * 8, d);
   }
-  chan_add(r0, sp.ch0, cb, cv);
-  chan_add(r1, sp.ch1, cb, cv);
-  chan_add(r2, sp.ch2, cb, cv);
-  chan_add(r3, sp.ch3, cb, cv);
-  __syncthreads();
+  chan_put(r0, sp.part, 0, cb, cv, C);
+  chan_put(r1, sp.part, 1, cb, cv, C);
+  chan_put(r2, sp.part, 2, cb, cv, C);
+  chan_put(r3, sp.part, 3, cb, cv, C);
+  chan_finish(sp.part, 4, sp.ch0, C);
   if (threadIdx.x < kGroups) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
@@ -436,17 +506,22 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward of tail 2: dout -> dx (gradient w.r.t. the conv2 output), all parameter gradients of GN2 / SE / gate
+// backward of tail 2: dout -> dx (gradient w.r.t. the conv2 output), all parameter gradients of GN2 / SE / gate.
+// The forward tail saved the channel maps, the gate and the tie counts, and the block output `out` = a*se*gate is
+// alive anyway (the next layer keeps it), so the gradient reaching the gate's pre-activation needs no activation:
+//     dq[p] = gate'(q) * sum_c dout*u = (1 - gate[p]) * sum_c dout[p,c]*out[p,c].
+// That first pass streams dout and out from global memory while the bulk-copy engine brings x into shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kFT, 1)
-convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, const float* __restrict__ stats,
-                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                          const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ wsp,
-                          const float* __restrict__ pool_g, const float* __restrict__ se_g,
-                          const float* __restrict__ hid_g, T* __restrict__ dx, float* __restrict__ dgamma,
-                          float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ dw2,
-                          float* __restrict__ dwsp, int H, int W, int C, int Cr, float eps) {
+convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, const T* __restrict__ out,
+                          const float* __restrict__ stats, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ w1, const float* __restrict__ w2,
+                          const float* __restrict__ wsp, const float* __restrict__ pool_g,
+                          const float* __restrict__ se_g, const float* __restrict__ hid_g,
+                          const float* __restrict__ maps, const uint8_t* __restrict__ ties, T* __restrict__ dx,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw1,
+                          float* __restrict__ dw2, float* __restrict__ dwsp, int H, int W, int C, int Cr, float eps) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
   const int cvs = __ffs(cv) - 1;
@@ -458,24 +533,23 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   float* s_dq = reinterpret_cast<float*>(smem + L.dq);
   float* s_gate = reinterpret_cast<float*>(smem + L.gate);
   float2* s_dm = reinterpret_cast<float2*>(smem + L.dm);
-  uint8_t* s_cnt = smem + L.cnt;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
   const TailPtrs sp = tail_ptrs(smem, L, C);
   const T* xn = x + (size_t)n * P * C;
   const T* don = dout + (size_t)n * P * C;
+  const T* outn = out + (size_t)n * P * C;
+  const float* mp = maps + (size_t)n * 3 * P;
+  const uint8_t* tp = ties + (size_t)n * P;
   T* dxn = dx + (size_t)n * P * C;
   const int cb = threadIdx.x & (cv - 1);
   const float invP = 1.f / (float)P;
 
-#pragma unroll 4
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8];
-    load8(xn + (size_t)v * 8, t);
-    store8(s_img + (size_t)v * 8, t);
+  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
+  {
+    float4* z4 = reinterpret_cast<float4*>(cm0);                                // cm0 | cm1 | dq are contiguous
+    for (int i = threadIdx.x; i < 3 * (H + 6) * Wp / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int i = threadIdx.x; i < 5 * C; i += NT) sp.ch0[i] = 0.f;
-  for (int i = threadIdx.x; i < 3 * (H + 6) * Wp; i += NT) cm0[i] = 0.f;     // cm0 | cm1 | dq are contiguous
   load_gate_weights(wsp, sp);
-  for (int i = threadIdx.x; i < 100; i += NT) sp.dw[i] = 0.f;
   for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
   for (int c = threadIdx.x; c < C; c += NT) {
     sp.se[c] = __ldg(se_g + (size_t)n * C + c);
@@ -484,90 +558,56 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   for (int j = threadIdx.x; j < Cr; j += NT) sp.hid[j] = __ldg(hid_g + (size_t)n * Cr + j);
   group_mu_rs_from_stats(stats + (size_t)n * kGroups * 2, cg, P, eps, sp);
   __syncthreads();
-  // per-thread channel coefficients (fixed channel block): xhat = xa*x + xb ; z = za*x + zb
-  float xa[8], xb[8], za[8], zb[8], gm[8], sc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cb * 8 + j, g = c / cg;
-    gm[j] = __ldg(gamma + c);
-    xa[j] = sp.rs[g]; xb[j] = -sp.mu[g] * sp.rs[g];
-    za[j] = gm[j] * xa[j]; zb[j] = fmaf(gm[j], xb[j], __ldg(beta + c));
-    sc[j] = sp.se[c];
-  }
 
-  // ---- pass A (sigmoid #1): u = a*se -> per-pixel (mean, max, #ties) and acc = sum_c dout*u.  The activation a is
-  // recomputed from x (not re-rounded to T: the difference is below the storage resolution and the same u is used
-  // for the max and for the tie test below)
+  // ---- pass A (global operands only): the saved maps go into the padded planes and dq = (1 - gate) * sum_c dout*out.
+  // Nothing here depends on shared memory, so the loads of kBatch rounds are issued back to back (the loop is
+  // bound by global-load latency otherwise: 16 warps per SM).
   {
-    const float invC = 1.f / (float)C;
+#pragma unroll 4
+    for (int p = threadIdx.x; p < P; p += NT) {
+      const int h = p / W, w = p - h * W, ip = (h + 3) * Wp + w + 4;
+      cm0[ip] = __ldg(mp + p);
+      cm1[ip] = __ldg(mp + P + p);
+      s_gate[p] = __ldg(mp + 2 * P + p);
+    }
+    constexpr int kBatch = 4;
     PixWalk pw(cvs, W);
-    for (int r = 0; r < nround; ++r, pw.next(W)) {
-      const bool valid = pw.p < P;
-      float sum = 0.f, mx = -INFINITY, acc = 0.f;
-      int cnt = 0;
-      if (valid) {
-        float t[8], d[8];
-        load8_rw(s_img + ((size_t)pw.p * cv + cb) * 8, t);
-        load8(don + ((size_t)pw.p * cv + cb) * 8, d);
+    for (int r0 = 0; r0 < nround; r0 += kBatch) {
+      float d[kBatch][8], o[kBatch][8], gt[kBatch];
+      int ip[kBatch];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(za[j], t[j], zb[j]);
-          const float u = z * sigmoid_t<T>(z) * sc[j];
-          sum += u;
-          if (u > mx) { mx = u; cnt = 1; } else if (u == mx) { ++cnt; }
-          acc = fmaf(d[j], u, acc);
-        }
+      for (int k = 0; k < kBatch; ++k) {
+        const bool valid = pw.p < P;
+        const size_t v = valid ? (size_t)pw.p * cv + cb : 0;
+        load8(don + v * 8, d[k]);
+        load8(outn + v * 8, o[k]);
+        gt[k] = (valid && cb == 0) ? __ldg(mp + 2 * P + pw.p) : 1.f;
+        ip[k] = (valid && cb == 0) ? (pw.h + 3) * Wp + pw.w + 4 : -1;
+        pw.next(W);
       }
-      for (int off = 1; off < cv; off <<= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        const float omx = __shfl_xor_sync(0xffffffffu, mx, off);
-        const int ocnt = __shfl_xor_sync(0xffffffffu, cnt, off);
-        if (omx > mx) { mx = omx; cnt = ocnt; } else if (omx == mx) { cnt += ocnt; }
-      }
-      if (valid && cb == 0) {
-        const int ip = (pw.h + 3) * Wp + pw.w + 4;
-        cm0[ip] = sum * invC;
-        cm1[ip] = mx;
-        s_dq[ip] = acc;
-        s_cnt[pw.p] = (uint8_t)min(cnt, 255);
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(d[k][j], o[k][j], acc);
+        for (int off = 1; off < cv; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (ip[k] >= 0) s_dq[ip[k]] = acc * (1.f - gt[k]);
       }
     }
   }
   __syncthreads();
-  // ---- gate = sigmoid(conv7x7) and dq = acc * gate * (1 - gate)
+  // ---- dwsp[k][dy][dx] = sum_p dq[p] * cmap_k[p + (dy-3, dx-3)]: one warp per (k, dy), lanes over the 8-pixel runs,
+  // 7 dx sums each, combined with shuffles (no atomics: every (k, dy, dx) has one owner)
   {
-    const int nrun = (W + 7) / 8;
-    for (int item = threadIdx.x; item < H * nrun; item += NT) {
-      const int h = item / nrun, w0 = (item - h * nrun) * 8;
-      float q[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nrun = (W + 7) / 8;
+    for (int combo = warp; combo < 14; combo += NT >> 5) {
+      const int k = combo / 7, dy = combo - k * 7;
+      const float* pl = k ? cm1 : cm0;
+      float a[7];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = 0.f;
-      stencil_run8(cm0 + h * Wp + w0, Wp, sp.wt, q);
-      stencil_run8(cm1 + h * Wp + w0, Wp, sp.wt + 56, q);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (w0 + i < W) {
-          const float gt = sigmoidf_(q[i]);
-          s_gate[h * W + w0 + i] = gt;
-          s_dq[(h + 3) * Wp + w0 + i + 4] *= gt * (1.f - gt);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- dwsp[k][dy][dx] += sum_p dq[p] * cmap_k[p + (dy-3, dx-3)]: thread = (k, dy, row partition), 7 dx sums
-  const int nparts = NT / 14;
-  if ((int)threadIdx.x < 14 * nparts) {
-    const int combo = threadIdx.x % 14, part = threadIdx.x / 14;
-    const int k = combo / 7, dy = combo % 7;
-    const float* pl = k ? cm1 : cm0;
-    float a[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) a[i] = 0.f;
-    const int Wr = (W + 7) / 8 * 8;
-    for (int h = part; h < H; h += nparts) {
-      for (int w0 = 0; w0 < Wr; w0 += 8) {
+      for (int i = 0; i < 7; ++i) a[i] = 0.f;
+      for (int item = lane; item < H * nrun; item += 32) {
+        const int h = item / nrun, w0 = (item - h * nrun) * 8;
         const float4* dr = reinterpret_cast<const float4*>(s_dq + (h + 3) * Wp + w0 + 4);
         const float4 d0 = dr[0], d1 = dr[1];
         const float dq8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -580,9 +620,12 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
           for (int i = 0; i < 8; ++i) a[dxx] = fmaf(dq8[i], m[i + dxx + 1], a[dxx]);
         }
       }
-    }
 #pragma unroll
-    for (int dxx = 0; dxx < 7; ++dxx) atomicAdd(&sp.dw[k * 49 + dy * 7 + dxx], a[dxx]);
+      for (int dxx = 0; dxx < 7; ++dxx) {
+        const float t = warp_sum(a[dxx]);
+        if (lane == 0) sp.dw[k * 49 + dy * 7 + dxx] = t;
+      }
+    }
   }
   // ---- gradient reaching (mean, max) through the transposed stencil (flipped weights)
   {
@@ -599,7 +642,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       for (int i = 0; i < 8; ++i) {
         if (w0 + i < W) {
           const int p = h * W + w0 + i;
-          s_dm[p] = make_float2(q0[i] * invC, q1[i] / (float)max((int)s_cnt[p], 1));
+          s_dm[p] = make_float2(q0[i] * invC, q1[i] / (float)max((int)__ldg(tp + p), 1));
         }
       }
     }
@@ -607,13 +650,27 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   __syncthreads();
   if (threadIdx.x < 98) atomicAdd(dwsp + threadIdx.x, sp.dw[threadIdx.x]);
 
-  // ---- pass B (sigmoid #2): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
-  // dse = sum_p du*a
+  // per-thread channel coefficients (fixed channel block): xhat = xa*x + xb ; z = za*x + zb
+  float xa[8], xb[8], za[8], zb[8], gm[8], sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb * 8 + j, g = c / cg;
+    gm[j] = __ldg(gamma + c);
+    xa[j] = sp.rs[g]; xb[j] = -sp.mu[g] * sp.rs[g];
+    gn_coef(gm[j], __ldg(beta + c), sp.mu[g], sp.rs[g], za[j], zb[j]);
+    sc[j] = sp.se[c];
+  }
+  image_copy_wait(bar);                                    // x is in shared memory from here on
+
+  // ---- pass B (sigmoid #1): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
+  // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu_act), so the
+  // comparison against the saved maximum selects the same channels.
   {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     PixWalk pw(cvs, W);
+#pragma unroll 2
     for (int r = 0; r < nround; ++r, pw.next(W)) {
       if (pw.p < P) {
         const size_t v = (size_t)pw.p * cv + cb;
@@ -625,8 +682,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
         const float mx = cm1[(pw.h + 3) * Wp + pw.w + 4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(za[j], t[j], zb[j]);
-          const float a = z * sigmoid_t<T>(z);
+          const float a = silu_act<T>(t[j], za[j], zb[j]);
           const float u = a * sc[j];
           const float du = fmaf(d[j], gt, dm.x) + ((u == mx) ? dm.y : 0.f);
           acc[j] = fmaf(du, a, acc[j]);
@@ -635,9 +691,9 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
         store8(dxn + v * 8, d);
       }
     }
-    chan_add(acc, sp.ch0, cb, cv);
+    chan_put(acc, sp.part, 0, cb, cv, C);
   }
-  __syncthreads();
+  chan_finish(sp.part, 1, sp.ch0, C);
   // ---- SE backward (tiny): dpool, dw1, dw2
   for (int c = threadIdx.x; c < C; c += NT) {
     const float s = sp.se[c];
@@ -693,11 +749,11 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     }
     store8(dxn + (size_t)v * 8, d);
   }
-  chan_add(r0, sp.ch1, cb, cv);
-  chan_add(r1, sp.ch2, cb, cv);
-  chan_add(r2, sp.ch3, cb, cv);
-  chan_add(r3, sp.ch4, cb, cv);
-  __syncthreads();
+  chan_put(r0, sp.part, 0, cb, cv, C);
+  chan_put(r1, sp.part, 1, cb, cv, C);
+  chan_put(r2, sp.part, 2, cb, cv, C);
+  chan_put(r3, sp.part, 3, cb, cv, C);
+  chan_finish(sp.part, 4, sp.ch1, C);
   if (threadIdx.x < kGroups) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
@@ -727,13 +783,6 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     for (int j = 0; j < 8; ++j) d[j] = fmaf(xa[j], d[j], fmaf(k2[j], t[j], k1[j]));
     store8(dxn + (size_t)v * 8, d);
   }
-}
-
-// threads per CTA: enough vectors per thread to amortise the phase barriers, few enough that small images get
-// several CTAs per SM (the kernels are register-limited to 512 threads per SM)
-static int tail_threads(int H, int W, int C) {
-  const int nvec = H * W * (C / 8);
-  return nvec >= 4096 ? 512 : nvec >= 1536 ? 256 : 128;
 }
 
 static bool fused_shape_ok(int H, int W, int C, int Cr) {
@@ -771,7 +820,8 @@ extern "C" int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const floa
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, false>, smem, "gn_silu_img_fwd");
     if (rc == PCM_OK)
       convblock_tail_fwd_kernel<T, false><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
-          (const T*)x, gamma, beta, nullptr, nullptr, nullptr, stats, nullptr, nullptr, nullptr, (T*)y, H, W, C, 1, eps);
+          (const T*)x, gamma, beta, nullptr, nullptr, nullptr, stats, nullptr, nullptr, nullptr, nullptr, nullptr,
+          (T*)y, H, W, C, 1, eps);
   });
   if (rc != PCM_OK) return rc;
   return check_launch("gn_silu_img_fwd");
@@ -779,18 +829,19 @@ extern "C" int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const floa
 
 extern "C" int pcm_convblock_tail_fwd(const void* x, const float* gamma, const float* beta, const float* w1,
                                       const float* w2, const float* wsp, float* stats, float* pool, float* se,
-                                      float* hid, void* out, int N, int H, int W, int C, int Cr, float eps, int dtype,
-                                      pcm_stream_t s) {
+                                      float* hid, float* maps, unsigned char* ties, void* out, int N, int H, int W,
+                                      int C, int Cr, float eps, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(fused_shape_ok(H, W, C, Cr), "convblock_tail_fwd: unsupported shape H=%d W=%d C=%d Cr=%d", H, W, C, Cr);
   if (N == 0) return PCM_OK;
   const size_t smem = tail_smem_layout(H, W, C, dtype == PCM_BF16 ? 2 : 4, 1, 0).total;
   PCM_REQUIRE(smem <= 227 * 1024, "convblock_tail_fwd: image does not fit shared memory (%zu B)", smem);
+  PCM_REQUIRE((maps == nullptr) == (ties == nullptr), "convblock_tail_fwd: maps and ties are saved together");
   int rc = PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, true>, smem, "convblock_tail_fwd");
     if (rc == PCM_OK)
       convblock_tail_fwd_kernel<T, true><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
-          (const T*)x, gamma, beta, w1, w2, wsp, stats, pool, se, hid, (T*)out, H, W, C, Cr, eps);
+          (const T*)x, gamma, beta, w1, w2, wsp, stats, pool, se, hid, maps, ties, (T*)out, H, W, C, Cr, eps);
   });
   if (rc != PCM_OK) return rc;
   return check_launch("convblock_tail_fwd");
@@ -814,22 +865,25 @@ extern "C" int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* s
   return check_launch("gn_silu_img_bwd");
 }
 
-extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const float* stats, const float* gamma,
-                                      const float* beta, const float* w1, const float* w2, const float* wsp,
-                                      const float* pool, const float* se, const float* hid, void* dx, float* dgamma,
+extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const void* out, const float* stats,
+                                      const float* gamma, const float* beta, const float* w1, const float* w2,
+                                      const float* wsp, const float* pool, const float* se, const float* hid,
+                                      const float* maps, const unsigned char* ties, void* dx, float* dgamma,
                                       float* dbeta, float* dw1, float* dw2, float* dwsp, int N, int H, int W, int C,
                                       int Cr, float eps, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(fused_shape_ok(H, W, C, Cr), "convblock_tail_bwd: unsupported shape H=%d W=%d C=%d Cr=%d", H, W, C, Cr);
   if (N == 0) return PCM_OK;
   const size_t smem = tail_smem_layout(H, W, C, dtype == PCM_BF16 ? 2 : 4, 1, 1).total;
   PCM_REQUIRE(smem <= 227 * 1024, "convblock_tail_bwd: image does not fit shared memory (%zu B)", smem);
+  PCM_REQUIRE(out != nullptr && maps != nullptr && ties != nullptr, "convblock_tail_bwd: the forward tail's saved out / maps / ties are required");
+  PCM_REQUIRE(((uintptr_t)x & 15) == 0, "convblock_tail_bwd: x must be 16-byte aligned (bulk copy)");
   int rc = PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_bwd_kernel<T>, smem, "convblock_tail_bwd");
     if (rc == PCM_OK)
       convblock_tail_bwd_kernel<T><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
-          (const T*)dout, (const T*)x, stats, gamma, beta, w1, w2, wsp, pool, se, hid, (T*)dx, dgamma, dbeta, dw1, dw2,
-          dwsp, H, W, C, Cr, eps);
+          (const T*)dout, (const T*)x, (const T*)out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties,
+          (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, H, W, C, Cr, eps);
   });
   if (rc != PCM_OK) return rc;
   return check_launch("convblock_tail_bwd");

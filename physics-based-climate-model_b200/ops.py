@@ -538,10 +538,13 @@ class ConvBlockFn(torch.autograd.Function):
                   N, H, W, Co, GN_EPS, d, st)
             y2 = conv_s1(a1, wk2, N, H, W, Co, Co)
             out = torch.empty_like(y2)
+            # saved for the backward tail: channel mean / max maps and the gate (fp32) + tie counts of the max
+            maps = torch.empty(N * P * 3, device=dev, dtype=torch.float32)
+            ties = torch.empty(N * P, device=dev, dtype=torch.uint8)
             _call("pcm_convblock_tail_fwd", y2.data_ptr(), g2.data_ptr(), b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(),
-                  wsp.data_ptr(), stats2.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), out.data_ptr(),
-                  N, H, W, Co, Cr, GN_EPS, d, st)
-            ctx.save_for_backward(x, y1, a1, y2, small, se, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp)
+                  wsp.data_ptr(), stats2.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), maps.data_ptr(),
+                  ties.data_ptr(), out.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
+            ctx.save_for_backward(x, y1, a1, y2, small, se, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp, maps, ties, out)
             return out
         # one zeroed scratch for every small accumulator of the forward
         small = torch.zeros(N * G * 2 * 2 + N * Co, device=dev, dtype=torch.float32)
@@ -625,7 +628,7 @@ class ConvBlockFn(torch.autograd.Function):
 
     @staticmethod
     def _backward_fused(ctx, dout):
-        x, y1, a1, y2, small, se, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp = ctx.saved_tensors
+        x, y1, a1, y2, small, se, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp, maps, ties, out = ctx.saved_tensors
         N, H, W, Cip, Ci, Co, Cr = ctx.dims
         G, dt = GN_GROUPS, x.dtype
         d, st = _DT[dt], _s()
@@ -636,10 +639,10 @@ class ConvBlockFn(torch.autograd.Function):
         gw2, rw2 = _grad_buf(w2); gg2, rg2 = _grad_buf(g2); gb2, rb2 = _grad_buf(b2)
         gs1, rs1 = _grad_buf(sw1); gs2, rs2 = _grad_buf(sw2); gsp, rsp = _grad_buf(wsp)
         dy2 = torch.empty_like(y2)
-        _call("pcm_convblock_tail_bwd", dout.data_ptr(), y2.data_ptr(), stats2.data_ptr(), g2.data_ptr(), b2.data_ptr(),
-              sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(),
-              dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(), gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(),
-              N, H, W, Co, Cr, GN_EPS, d, st)
+        _call("pcm_convblock_tail_bwd", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
+              b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(),
+              hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(),
+              gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
         with side_stream(dy2, a1):
             conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
         wk2t = conv_weight_dgrad(w2, dt)

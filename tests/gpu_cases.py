@@ -78,6 +78,27 @@ def case_convblock(dtype):
     return compare(ConvBlock(cfg["c_in"], cfg["c_out"]), lambda a, s: O.conv_block(a, s, ""), sd, x, y, dtype, z)
 
 
+def case_convblock_ties(dtype):
+    """ConvBlock whose output channels 0 and 1 are exact duplicates (same conv2 filters, GroupNorm affine and SE row)
+    and biased to be the channel maximum at most pixels: `x.amax(1)` (src/unet.py:27) then splits the gradient evenly
+    between the tied channels.  The backward tail relies on the forward tail's saved maximum and tie count and on a
+    bit-identical recomputation of a*se; a mismatch would drop the whole max-path gradient."""
+    from pcm_b200.src.unet import ConvBlock
+    c_in, c_out = 8, 16
+    sd = O.synth_state_dict(O._convblock_spec("", c_in, c_out), 41)
+    sd["body.3.weight"][1] = sd["body.3.weight"][0]
+    sd["body.4.weight"][:2] = 1.0
+    sd["body.4.bias"][:2] = 1.5
+    sd["se.fc.2.weight"][1] = sd["se.fc.2.weight"][0]
+    x, y = O.synth_frame_batch(3, c_in, 12, 20, 42, out_ch=c_out)
+    r = compare(ConvBlock(c_in, c_out), lambda a, s: O.conv_block(a, s, ""), sd, x, y, dtype)
+    # how often the duplicated pair is the maximum (fp64 oracle): the case is meaningful only if ties are common
+    with torch.no_grad():
+        a = O.conv_block(x.double(), {k: v.double() for k, v in sd.items()}, "")
+    r["tie_share"] = float(((a[:, 0] == a[:, 1]) & (a[:, 0] >= a.amax(1))).double().mean())
+    return r
+
+
 def case_convlstm(dtype):
     from pcm_b200.src.convlstm import ConvLSTM
     cfg, z = load_golden("convlstm_small")

@@ -69,6 +69,15 @@ def test_blocks(G, case, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_convblock_tied_channel_maximum(G, dtype):
+    """amax splits its gradient between tied channels; the fused backward tail takes maximum and tie count from the
+    forward tail and must select the same channels."""
+    r = G.case_convblock_ties(dtype)
+    assert r["tie_share"] > 0.3, r["tie_share"]
+    _check(r, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("tag", ["attunet_small", "attunet_cfg3_b2"])
 def test_attunet(G, tag, dtype):
     _check(G.case_attunet(tag, dtype), dtype)

@@ -133,11 +133,12 @@ def bench_tails(args):
         w1, w2, wsp = f32(Cr * C) / C ** 0.5, f32(C * Cr), f32(98) / 7
         stats, pool, se, hid = torch.zeros(N * 16, device="cuda"), torch.zeros(N * C, device="cuda"), torch.zeros(N * C, device="cuda"), torch.zeros(N * Cr, device="cuda")
         dg, db, dw1, dw2, dwsp = (torch.zeros(n, device="cuda") for n in (C, C, Cr * C, C * Cr, 98))
+        maps, ties = torch.zeros(N * P * 3, device="cuda"), torch.zeros(N * P, device="cuda", dtype=torch.uint8)
         cases = [
             ("gn_silu_img_fwd", 2, lambda: _call("pcm_gn_silu_img_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), y.data_ptr(), N, H, W, C, 1e-5, d, _s())),
-            ("convblock_tail_fwd", 2, lambda: _call("pcm_convblock_tail_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), stats.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), y.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())),
+            ("convblock_tail_fwd", 2, lambda: _call("pcm_convblock_tail_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), stats.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), y.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())),
             ("gn_silu_img_bwd", 3, lambda: _call("pcm_gn_silu_img_bwd", dout.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), N, H, W, C, 1e-5, d, _s())),
-            ("convblock_tail_bwd", 3, lambda: _call("pcm_convblock_tail_bwd", dout.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dw1.data_ptr(), dw2.data_ptr(), dwsp.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())),
+            ("convblock_tail_bwd", 4, lambda: _call("pcm_convblock_tail_bwd", dout.data_ptr(), x.data_ptr(), y.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dw1.data_ptr(), dw2.data_ptr(), dwsp.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())),
         ]
         cases[1][2]()                      # populate stats / pool / se / hid for the backward kernels
         for name, ntens, fn in cases:
