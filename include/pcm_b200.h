@@ -226,20 +226,21 @@ PCM_API int pcm_convblock_tail_bwd(const void* dout, const void* x, const void* 
                                    int Cr, float eps, int dtype, pcm_stream_t s);
 
 /* ---- BatchNorm2d, training mode (src/models.py:48,51,57,91,109; eps 1e-5, momentum 0.1) on NHWC rows
- * (R = N*H*W rows of C channels; C = 8 * a divisor of 256).  sums[c] = (sum x, sum x^2), zeroed by the caller. */
-PCM_API int pcm_bn_stats(const void* x, float* sums, long long R, int C, int dtype, pcm_stream_t s);
+ * (R = N*H*W rows of C channels; C = 8 * a divisor of 256).  sums[c] = (sum x, sum x^2) in DOUBLE (2*C doubles),
+ * zeroed by the caller: the cross-thread / cross-block accumulation order then cannot move mean or variance. */
+PCM_API int pcm_bn_stats(const void* x, double* sums, long long R, int C, int dtype, pcm_stream_t s);
 /* y = [relu]( gamma*(x-mean)*rstd + beta [+ res] )   (res nullable: the residual add of src/models.py:70-71) */
-PCM_API int pcm_bn_apply_fwd(const void* x, const float* sums, const float* gamma, const float* beta, const void* res,
+PCM_API int pcm_bn_apply_fwd(const void* x, const double* sums, const float* gamma, const float* beta, const void* res,
                              void* y, long long R, int C, float eps, int relu, int dtype, pcm_stream_t s);
 /* running_mean/var <- (1-m)*old + m*(batch mean / unbiased batch var); num_batches_tracked (int64, nullable) += 1 */
-PCM_API int pcm_bn_update_running(const float* sums, float* running_mean, float* running_var,
+PCM_API int pcm_bn_update_running(const double* sums, float* running_mean, float* running_var,
                                   long long* num_batches_tracked, long long R, int C, float momentum, pcm_stream_t s);
 /* backward pass 1: with dz = dy * (y > 0) when y != NULL (ReLU mask), else dz = dy:
  * dsum[c] += (sum dz, sum dz*xhat)   (caller zeroes dsum) */
-PCM_API int pcm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* sums, float* dsum, long long R,
+PCM_API int pcm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const double* sums, float* dsum, long long R,
                               int C, float eps, int dtype, pcm_stream_t s);
 /* pass 2: dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dres = dz (nullable); dgamma/dbeta += dsum */
-PCM_API int pcm_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* sums, const float* gamma,
+PCM_API int pcm_bn_bwd_apply(const void* dy, const void* y, const void* x, const double* sums, const float* gamma,
                              const float* dsum, void* dx, void* dres, float* dgamma, float* dbeta, long long R, int C,
                              float eps, int dtype, pcm_stream_t s);
 /* elementwise helpers (n multiple of 8): out = a + b ; y[i] = x[i] + b[i % period] (pos_embedding add,

@@ -44,7 +44,8 @@ PROTOS = parse_header()
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; PCM_B200_LIB points at another build of the same ABI (kernel experiments)."""
+    return os.environ.get("PCM_B200_LIB") or _build.LIB_PATH
 
 
 class _Lib:

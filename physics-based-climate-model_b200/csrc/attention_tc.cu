@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kAttThreads, 1)
 mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                   unsigned int* __restrict__ err, const AttParams p) {
+  pdl_launch_dependents();          // the next kernel may start launching; it waits for us in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                        // 2 x [128][64 B]
@@ -74,6 +75,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                       // predecessor complete: global memory may be touched from here on
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t colO = 2 * p.Lk;            // S_t at columns t*Lk, O_t at 2*Lk + 32*t   (2*Lk + 64 <= 512)
 
@@ -206,6 +208,7 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const __grid_constant__ CUtensorMap tmdO, const __nv_bfloat16* __restrict__ out,
                   const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
                   unsigned int* __restrict__ err, const AttParams p) {
+  pdl_launch_dependents();          // the next kernel may start launching; it waits for us in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                        // 2 x [128][64 B]
@@ -239,6 +242,7 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                       // predecessor complete: global memory may be touched from here on
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t cS = 0, cdP = 128, cdQ = 256, cdK = 320, cdV = 352;
 
@@ -438,7 +442,7 @@ extern "C" int pcm_mha_fwd_tc(const void* qkv, void* out, float* lse, int B, int
   }
   unsigned int* err = tc_error_counter();
   PCM_REQUIRE(err != nullptr, "mha_fwd_tc: could not allocate the error counter");
-  mha_fwd_tc_kernel<<<B * nh, kAttThreads, smem, (cudaStream_t)s>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(out), lse,
+  pcm::launch(mha_fwd_tc_kernel, B * nh, kAttThreads, smem, (cudaStream_t)s, tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(out), lse,
                                                                    err, p);
   return check_launch("mha_fwd_tc");
 }
@@ -467,7 +471,7 @@ extern "C" int pcm_mha_bwd_tc(const void* qkv, const void* out, const void* dout
   }
   unsigned int* err = tc_error_counter();
   PCM_REQUIRE(err != nullptr, "mha_bwd_tc: could not allocate the error counter");
-  mha_bwd_tc_kernel<<<B * nh, kAttThreads, smem, (cudaStream_t)s>>>(
+  pcm::launch(mha_bwd_tc_kernel, B * nh, kAttThreads, smem, (cudaStream_t)s, 
       tmQ, tmKV, tmdO, reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse,
       reinterpret_cast<__nv_bfloat16*>(dqkv), err, p);
   return check_launch("mha_bwd_tc");

@@ -18,13 +18,19 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
 }
 
 // sums[c][0] += sum_r x(r,c); sums[c][1] += sum_r x(r,c)^2          (caller zeroes sums)
+// The per-thread partials (a few rows each) are fp32; they are combined across threads and blocks in DOUBLE: the
+// order of those atomics varies from run to run, and in fp32 that moved mean / variance in the last bit — enough to
+// flip the ReLU that follows for pre-activations within ~1e-6 of zero and change every gradient upstream by ~1e-3
+// (seen as a 1-in-15 flake of the fp32 parity test).  In double the order-dependence is ~1e-16, and E[x^2] - mean^2
+// loses nothing to cancellation.
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
-bn_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long long R, int C) {
-  extern __shared__ float sh[];                 // [C][2]
+bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long R, int C) {
+  PCM_PDL_ENTRY();
+  extern __shared__ double shd[];                // [C][2]
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
-  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) shd[i] = 0.0;
   __syncthreads();
   float s[8], q[8];
 #pragma unroll
@@ -38,20 +44,27 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long long R, 
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[(cb * 8 + j) * 2], s[j]);
-      atomicAdd(&sh[(cb * 8 + j) * 2 + 1], q[j]);
+      atomicAdd(&shd[(cb * 8 + j) * 2], (double)s[j]);
+      atomicAdd(&shd[(cb * 8 + j) * 2 + 1], (double)q[j]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(sums + i, sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(sums + i, shd[i]);
 }
 
-__device__ __forceinline__ void bn_coeffs(const float* sums, const float* gamma, const float* beta, int c0, float invR,
+// (mean, biased variance) of channel c from the double sums
+__device__ __forceinline__ void bn_mean_var(const double* sums, int c, double invR, float& mean, float& var) {
+  const double m = sums[2 * c] * invR;
+  mean = (float)m;
+  var = (float)fmax(sums[2 * c + 1] * invR - m * m, 0.0);
+}
+
+__device__ __forceinline__ void bn_coeffs(const double* sums, const float* gamma, const float* beta, int c0, double invR,
                                           float eps, float mean[8], float rstd[8], float a[8], float b[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float m = sums[(c0 + j) * 2] * invR;
-    const float var = fmaxf(sums[(c0 + j) * 2 + 1] * invR - m * m, 0.f);
+    float m, var;
+    bn_mean_var(sums, c0 + j, invR, m, var);
     mean[j] = m;
     rstd[j] = rsqrtf(var + eps);
     a[j] = gamma[c0 + j] * rstd[j];
@@ -62,14 +75,15 @@ __device__ __forceinline__ void bn_coeffs(const float* sums, const float* gamma,
 // y = [relu]( (x-mean)*rstd*gamma + beta [+ res] )
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
-bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+bn_apply_fwd_kernel(const T* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ y, long long R, int C,
                     float eps, int relu) {
+  PCM_PDL_ENTRY();
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
   if (rl >= rpb) return;
   float mean[8], rstd[8], a[8], b[8];
-  bn_coeffs(sums, gamma, beta, cb * 8, 1.f / (float)R, eps, mean, rstd, a, b);
+  bn_coeffs(sums, gamma, beta, cb * 8, 1.0 / (double)R, eps, mean, rstd, a, b);
   for (long long r = (long long)blockIdx.x * rpb + rl; r < R; r += (long long)gridDim.x * rpb) {
     float v[8];
     load8(x + r * C + cb * 8, v);
@@ -93,7 +107,8 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ sums, con
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
-                     const float* __restrict__ sums, float* __restrict__ dsum, long long R, int C, float eps) {
+                     const double* __restrict__ sums, float* __restrict__ dsum, long long R, int C, float eps) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sh[];
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -104,8 +119,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T*
     const float invR = 1.f / (float)R;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float m = sums[(cb * 8 + j) * 2] * invR;
-      const float var = fmaxf(sums[(cb * 8 + j) * 2 + 1] * invR - m * m, 0.f);
+      float m, var;
+      bn_mean_var(sums, cb * 8 + j, 1.0 / (double)R, m, var);
       mean[j] = m; rstd[j] = rsqrtf(var + eps); s[j] = q[j] = 0.f;
     }
     for (long long r = (long long)blockIdx.x * rpb + rl; r < R; r += (long long)gridDim.x * rpb) {
@@ -135,9 +150,10 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T*
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
-                    const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ dsum,
+                    const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ dsum,
                     T* __restrict__ dx, T* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     long long R, int C, float eps) {
+  PCM_PDL_ENTRY();
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
   if (blockIdx.x == 0) {
@@ -152,8 +168,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cb * 8 + j;
-    const float m = sums[c * 2] * invR;
-    const float var = fmaxf(sums[c * 2 + 1] * invR - m * m, 0.f);
+    float m, var;
+    bn_mean_var(sums, c, 1.0 / (double)R, m, var);
     mean[j] = m; rstd[j] = rsqrtf(var + eps);
     a[j] = gamma[c] * rstd[j];
     m1[j] = dsum[2 * c] * invR; m2[j] = dsum[2 * c + 1] * invR;
@@ -175,14 +191,14 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
   }
 }
 
-__global__ void bn_update_running_kernel(const float* __restrict__ sums, float* __restrict__ rm, float* __restrict__ rv,
+__global__ void bn_update_running_kernel(const double* __restrict__ sums, float* __restrict__ rm, float* __restrict__ rv,
                                          long long* __restrict__ nbt, long long R, int C, float momentum) {
+  PCM_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt != nullptr) *nbt += 1;
   if (c >= C) return;
-  const float invR = 1.f / (float)R;
-  const float m = sums[2 * c] * invR;
-  const float var = fmaxf(sums[2 * c + 1] * invR - m * m, 0.f);
+  float m, var;
+  bn_mean_var(sums, c, 1.0 / (double)R, m, var);
   const float unb = R > 1 ? var * (float)R / (float)(R - 1) : var;
   rm[c] = (1.f - momentum) * rm[c] + momentum * m;
   rv[c] = (1.f - momentum) * rv[c] + momentum * unb;
@@ -192,6 +208,7 @@ __global__ void bn_update_running_kernel(const float* __restrict__ sums, float* 
 template <typename T>
 __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o,
                                                    long long n8) {
+  PCM_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float u[8], v[8];
     load8(a + i * 8, u); load8(b + i * 8, v);
@@ -205,6 +222,7 @@ __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const
 template <typename T>
 __global__ void __launch_bounds__(256) add_bcast_kernel(const T* __restrict__ x, const float* __restrict__ b,
                                                          T* __restrict__ y, long long n8, long long R8) {
+  PCM_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float u[8], v[8];
     load8(x + i * 8, u);
@@ -218,6 +236,7 @@ __global__ void __launch_bounds__(256) add_bcast_kernel(const T* __restrict__ x,
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
                                                         long long n8) {
+  PCM_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float g[8], o[8];
     load8(dy + i * 8, g); load8(y + i * 8, o);
@@ -231,6 +250,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dy,
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, float p,
                                                        unsigned long long seed) {
+  PCM_PDL_ENTRY();
   const float sc = 1.f / (1.f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float u[8];
@@ -242,6 +262,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
 }
 
 __global__ void dropout_mask_kernel(float* __restrict__ mask, long long n, float p, unsigned long long seed) {
+  PCM_PDL_ENTRY();
   const float sc = 1.f / (1.f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     mask[i] = hash_uniform(seed, (unsigned long long)i) >= p ? sc : 0.f;
@@ -251,6 +272,7 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, long long n, float
 template <typename T>
 __global__ void __launch_bounds__(128) batch_sum_kernel(const T* __restrict__ x, float* __restrict__ out, int B,
                                                          long long R8) {
+  PCM_PDL_ENTRY();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= R8) return;
   float acc[8];
@@ -288,47 +310,47 @@ using namespace pcm;
   PCM_REQUIRE((C) % 8 == 0 && (C) >= 8 && (C) <= 2048 && kBnThreads % ((C) / 8) == 0,                            \
               fn ": C must be 8 * (a divisor of 256) (got %d)", (int)(C))
 
-extern "C" int pcm_bn_stats(const void* x, float* sums, long long R, int C, int dtype, pcm_stream_t s) {
+extern "C" int pcm_bn_stats(const void* x, double* sums, long long R, int C, int dtype, pcm_stream_t s) {
   BN_CHECK_C("bn_stats", C);
   if (R == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (bn_stats_kernel<T><<<bn_grid(R, C), kBnThreads, 2 * C * sizeof(float), (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_stats_kernel<T>, bn_grid(R, C), kBnThreads, 2 * C * sizeof(double), (cudaStream_t)s,
                                    static_cast<const T*>(x), sums, R, C)));
   return check_launch("bn_stats");
 }
 
-extern "C" int pcm_bn_apply_fwd(const void* x, const float* sums, const float* gamma, const float* beta, const void* res,
+extern "C" int pcm_bn_apply_fwd(const void* x, const double* sums, const float* gamma, const float* beta, const void* res,
                                 void* y, long long R, int C, float eps, int relu, int dtype, pcm_stream_t s) {
   BN_CHECK_C("bn_apply_fwd", C);
   if (R == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (bn_apply_fwd_kernel<T><<<bn_grid(R, C), kBnThreads, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_apply_fwd_kernel<T>, bn_grid(R, C), kBnThreads, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(x), sums, gamma, beta, static_cast<const T*>(res),
                                    static_cast<T*>(y), R, C, eps, relu)));
   return check_launch("bn_apply_fwd");
 }
 
-extern "C" int pcm_bn_update_running(const float* sums, float* running_mean, float* running_var,
+extern "C" int pcm_bn_update_running(const double* sums, float* running_mean, float* running_var,
                                      long long* num_batches_tracked, long long R, int C, float momentum, pcm_stream_t s) {
-  bn_update_running_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)s>>>(sums, running_mean, running_var,
+  pcm::launch(bn_update_running_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)s, sums, running_mean, running_var,
                                                                           num_batches_tracked, R, C, momentum);
   return check_launch("bn_update_running");
 }
 
-extern "C" int pcm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* sums, float* dsum, long long R,
+extern "C" int pcm_bn_bwd_reduce(const void* dy, const void* y, const void* x, const double* sums, float* dsum, long long R,
                                  int C, float eps, int dtype, pcm_stream_t s) {
   BN_CHECK_C("bn_bwd_reduce", C);
   if (R == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (bn_bwd_reduce_kernel<T><<<bn_grid(R, C), kBnThreads, 2 * C * sizeof(float), (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_bwd_reduce_kernel<T>, bn_grid(R, C), kBnThreads, 2 * C * sizeof(float), (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<const T*>(x), sums, dsum,
                                    R, C, eps)));
   return check_launch("bn_bwd_reduce");
 }
 
-extern "C" int pcm_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* sums, const float* gamma,
+extern "C" int pcm_bn_bwd_apply(const void* dy, const void* y, const void* x, const double* sums, const float* gamma,
                                 const float* dsum, void* dx, void* dres, float* dgamma, float* dbeta, long long R, int C,
                                 float eps, int dtype, pcm_stream_t s) {
   BN_CHECK_C("bn_bwd_apply", C);
   if (R == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<bn_grid(R, C), kBnThreads, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_bwd_apply_kernel<T>, bn_grid(R, C), kBnThreads, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<const T*>(x), sums, gamma,
                                    dsum, static_cast<T*>(dx), static_cast<T*>(dres), dgamma, dbeta, R, C, eps)));
   return check_launch("bn_bwd_apply");
@@ -337,7 +359,7 @@ extern "C" int pcm_bn_bwd_apply(const void* dy, const void* y, const void* x, co
 extern "C" int pcm_add(const void* a, const void* b, void* out, long long n, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(n % 8 == 0, "add: n must be a multiple of 8");
   if (n == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (add_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(add_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(out), n / 8)));
   return check_launch("add");
 }
@@ -346,7 +368,7 @@ extern "C" int pcm_add_bcast(const void* x, const float* b, void* y, long long n
                              pcm_stream_t s) {
   PCM_REQUIRE(n % 8 == 0 && period % 8 == 0 && period > 0, "add_bcast: n and period must be multiples of 8");
   if (n == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (add_bcast_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(add_bcast_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(x), b, static_cast<T*>(y), n / 8, period / 8)));
   return check_launch("add_bcast");
 }
@@ -354,7 +376,7 @@ extern "C" int pcm_add_bcast(const void* x, const float* b, void* y, long long n
 extern "C" int pcm_relu_bwd(const void* dy, const void* y, void* dx, long long n, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(n % 8 == 0, "relu_bwd: n must be a multiple of 8");
   if (n == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (relu_bwd_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(relu_bwd_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<T*>(dx), n / 8)));
   return check_launch("relu_bwd");
 }
@@ -362,7 +384,7 @@ extern "C" int pcm_relu_bwd(const void* dy, const void* y, void* dx, long long n
 extern "C" int pcm_dropout(const void* x, void* y, long long n, float p, long long seed, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(n % 8 == 0 && p >= 0.f && p < 1.f, "dropout: n must be a multiple of 8 and 0 <= p < 1");
   if (n == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (dropout_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(dropout_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(x), static_cast<T*>(y), n / 8, p, (unsigned long long)seed)));
   return check_launch("dropout");
 }
@@ -370,14 +392,14 @@ extern "C" int pcm_dropout(const void* x, void* y, long long n, float p, long lo
 extern "C" int pcm_dropout_mask(float* mask, long long n, float p, long long seed, pcm_stream_t s) {
   PCM_REQUIRE(p >= 0.f && p < 1.f, "dropout_mask: 0 <= p < 1");
   if (n == 0) return PCM_OK;
-  dropout_mask_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)s>>>(mask, n, p, (unsigned long long)seed);
+  pcm::launch(dropout_mask_kernel, ew_grid(n), 256, 0, (cudaStream_t)s, mask, n, p, (unsigned long long)seed);
   return check_launch("dropout_mask");
 }
 
 extern "C" int pcm_batch_sum(const void* x, float* out, int B, long long R, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(R % 8 == 0, "batch_sum: row length must be a multiple of 8");
   if (B == 0 || R == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (batch_sum_kernel<T><<<ceil_div(R / 8, 128), 128, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(batch_sum_kernel<T>, ceil_div(R / 8, 128), 128, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(x), out, B, R / 8)));
   return check_launch("batch_sum");
 }

@@ -11,6 +11,7 @@ namespace pcm {
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, long long so, long long si, long long st, int O, int I,
                                    int taps, int Op, int Ip, T* __restrict__ out) {
+  PCM_PDL_ENTRY();
   const long long total = (long long)taps * Op * Ip;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -32,6 +33,7 @@ constexpr int kBatchBlockElems = 1024;
 
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs,
                                                                     const int* __restrict__ work) {
+  PCM_PDL_ENTRY();
   const int job = work[2 * blockIdx.x], blk = work[2 * blockIdx.x + 1];
   const long long* j = jobs + (long long)job * 8;
   const float* w = reinterpret_cast<const float*>(j[0]);
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
 // sb == taps, st == 1 — every conv / convT weight) are coalesced.
 __global__ void __launch_bounds__(256) unpack_grads_batched_kernel(const long long* __restrict__ jobs,
                                                                     const int* __restrict__ work) {
+  PCM_PDL_ENTRY();
   extern __shared__ float slab[];       // [taps][Cpad]
   const int job = work[2 * blockIdx.x], co = work[2 * blockIdx.x + 1];
   const long long* j = jobs + (long long)job * 8;
@@ -106,6 +109,7 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(128)
 conv_gather_kernel(const T* __restrict__ src, TO* __restrict__ dst, const T* __restrict__ wk,
                    const float* __restrict__ bias, GatherGeom g, int accumulate, int relu) {
+  PCM_PDL_ENTRY();
   const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long npix = (long long)g.N * g.Hd * g.Wd;
   if (pix >= npix) return;
@@ -188,6 +192,7 @@ struct WgradGeom {
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ dw, WgradGeom g) {
+  PCM_PDL_ENTRY();
   extern __shared__ float red[];   // [tiles_per_block][64] when lanes > 1
   const int tap = blockIdx.z;
   const int kh = tap / g.KW, kw = tap % g.KW;
@@ -253,6 +258,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const T* __restrict__ x, long long ns, int ps, int N, int P, int C, int C_real,
                    float* __restrict__ out, int per_image) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sacc[];   // [C]
   for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
@@ -314,7 +320,7 @@ extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long 
   PCM_REQUIRE(O <= Op && I <= Ip && taps > 0, "pack_weight: bad sizes");
   const long long total = (long long)taps * Op * Ip;
   const int blocks = (int)min((long long)1184, (total + 255) / 256);
-  PCM_DISPATCH_DTYPE(dtype, T, (pack_weight_kernel<T><<<blocks, 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(pack_weight_kernel<T>, blocks, 256, 0, (cudaStream_t)s, 
                                    w, so, si, st, O, I, taps, Op, Ip, (T*)out)));
   return check_launch("pack_weight");
 }
@@ -322,7 +328,7 @@ extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long 
 extern "C" int pcm_pack_weights_batched(const long long* jobs, const int* work, int nwork, pcm_stream_t s) {
   PCM_REQUIRE(jobs != nullptr && work != nullptr && nwork >= 0, "pack_weights_batched: bad arguments");
   if (nwork == 0) return PCM_OK;
-  pack_weights_batched_kernel<<<(unsigned)nwork, 256, 0, (cudaStream_t)s>>>(jobs, work);
+  pcm::launch(pack_weights_batched_kernel, (unsigned)nwork, 256, 0, (cudaStream_t)s, jobs, work);
   return check_launch("pack_weights_batched");
 }
 
@@ -330,7 +336,7 @@ extern "C" int pcm_unpack_grads_batched(const long long* jobs, const int* work, 
   PCM_REQUIRE(jobs != nullptr && work != nullptr && nwork >= 0, "unpack_grads_batched: bad arguments");
   if (nwork == 0) return PCM_OK;
   // dynamic shared memory: the largest [taps][Cpad] slab the library produces (9 x 512 floats)
-  unpack_grads_batched_kernel<<<(unsigned)nwork, 256, 9 * 512 * sizeof(float), (cudaStream_t)s>>>(jobs, work);
+  pcm::launch(unpack_grads_batched_kernel, (unsigned)nwork, 256, 9 * 512 * sizeof(float), (cudaStream_t)s, jobs, work);
   return check_launch("unpack_grads_batched");
 }
 
@@ -347,10 +353,10 @@ extern "C" int pcm_conv_gather(const void* src, long long src_ns, int src_ps, in
   dim3 grid(ceil_div(npix, 128), Dc / 8);
   cudaStream_t st = (cudaStream_t)s;
   if (dst_f32) {
-    PCM_DISPATCH_DTYPE(dtype, T, (conv_gather_kernel<T, float><<<grid, 128, 0, st>>>(
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(conv_gather_kernel<T, float>, grid, 128, 0, st, 
                                      (const T*)src, (float*)dst, (const T*)wk, bias, g, accumulate, relu)));
   } else {
-    PCM_DISPATCH_DTYPE(dtype, T, (conv_gather_kernel<T, T><<<grid, 128, 0, st>>>(
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(conv_gather_kernel<T, T>, grid, 128, 0, st, 
                                      (const T*)src, (T*)dst, (const T*)wk, bias, g, accumulate, relu)));
   }
   return check_launch("conv_gather");
@@ -384,7 +390,7 @@ extern "C" int pcm_conv_wgrad(const void* A, long long a_ns, int a_ps, int Ha, i
     PCM_DISPATCH_DTYPE(dtype, T, cudaFuncSetAttribute(conv_wgrad_kernel<T>,
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  PCM_DISPATCH_DTYPE(dtype, T, (conv_wgrad_kernel<T><<<grid, 256, smem, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(conv_wgrad_kernel<T>, grid, 256, smem, (cudaStream_t)s, 
                                    (const T*)A, (const T*)B, dw, g)));
   return check_launch("conv_wgrad");
 }
@@ -397,7 +403,7 @@ extern "C" int pcm_channel_sum(const void* x, long long ns, int ps, int N, int P
   int bx = (int)min((long long)592, (total + 255) / 256);
   if (per_image) bx = (int)min((long long)max(1, 592 / N), (total + 1023) / 1024);
   dim3 grid(bx, per_image ? N : 1);
-  PCM_DISPATCH_DTYPE(dtype, T, (channel_sum_kernel<T><<<grid, 256, C * sizeof(float), (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(channel_sum_kernel<T>, grid, 256, C * sizeof(float), (cudaStream_t)s, 
                                    (const T*)x, ns, ps, N, P, C, C_real, out, per_image)));
   return check_launch("channel_sum");
 }

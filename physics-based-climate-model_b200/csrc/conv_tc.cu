@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
                   const ConvTcParams p) {
+  pdl_launch_dependents();          // the next kernel may start launching; it waits for us in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -87,6 +88,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                       // predecessor complete: global memory may be touched from here on
   const uint32_t tmem_base = *tmem_slot;
 
   const int ntaps = p.mode == 1 ? 4 : p.mode == 2 ? 6 : p.ksz * p.ksz, kpad = p.pad;
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        void* __restrict__ dst, const float* __restrict__ bias, unsigned int* __restrict__ err,
                        const ConvHaloParams p) {
+  pdl_launch_dependents();          // the next kernel may start launching; it waits for us in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t b_region = (p.b_bytes + 1023u) & ~1023u;
@@ -350,6 +353,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                       // predecessor complete: global memory may be touched from here on
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t rb = KSTEPS * 32;     // bytes of one pixel row of one channel chunk
 
@@ -677,7 +681,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     int gx = g_num_sms / nslices;
     if (gx < 1) gx = 1;
     if (gx > h.num_tiles) gx = h.num_tiles;
-    kern<<<dim3(gx, nslices), kThreads, smem, (cudaStream_t)s>>>(tmA, tmB, dst, bias, err, h);
+    pcm::launch(kern, dim3(gx, nslices), kThreads, smem, (cudaStream_t)s, tmA, tmB, dst, bias, err, h);
     return check_launch("conv3x3_tc(halo)");
   }
   ConvTcParams p;
@@ -757,7 +761,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   }
   const int nitems = p.num_tiles * p.ngroups;
   const int grid = nitems < g_num_sms ? nitems : g_num_sms;
-  kern<<<grid, kThreads, smem, (cudaStream_t)s>>>(tmA, tmA2, tmB, dst, bias, err, p);
+  pcm::launch(kern, grid, kThreads, smem, (cudaStream_t)s, tmA, tmA2, tmB, dst, bias, err, p);
   return check_launch("conv3x3_tc");
 }
 

@@ -52,6 +52,7 @@ __device__ __forceinline__ void group_mean_rstd(const float* __restrict__ stats,
 template <typename T>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int P, int C, int G) {
+  PCM_PDL_ENTRY();
   __shared__ float sg[64 * 2];
   const int n = blockIdx.y, cv = C / 8, cg = C / G;
   for (int i = threadIdx.x; i < G * 2; i += blockDim.x) sg[i] = 0.f;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256)
 gn_silu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ pool, int P, int C, int G,
                    float eps) {
+  PCM_PDL_ENTRY();
   extern __shared__ float spool[];   // [C]
   const int n = blockIdx.y, cv = C / 8, cg = C / G;
   if (pool) {
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256)
 se_chanstat_fwd_kernel(const T* __restrict__ a, const float* __restrict__ pool, const float* __restrict__ w1,
                        const float* __restrict__ w2, float* __restrict__ se, float* __restrict__ hid,
                        float* __restrict__ cmap, int P, int C, int Cr) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];   // pm[C] | sh[Cr] | sse[C]
   float* pm = sm;
   float* sh = sm + C;
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(256)
 spatial_gate_fwd_kernel(const T* __restrict__ a, const float* __restrict__ se, const float* __restrict__ cmap,
                         const float* __restrict__ wsp, float* __restrict__ gate, T* __restrict__ out, int H, int W,
                         int C) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];   // wsp[98] | pad | sse[C] | sgate[TH*W] | tile float2 [(TH+6)*(W+6)]
   float* sw = sm;
   float* sse = sm + 100;
@@ -280,6 +284,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 spatial_gate_bwd_dq_kernel(const T* __restrict__ dout, const T* __restrict__ a, const float* __restrict__ se,
                            const float* __restrict__ gate, float* __restrict__ dq, int P, int C) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sse[];
   const int n = blockIdx.y;
   for (int i = threadIdx.x; i < C; i += blockDim.x) sse[i] = __ldg(se + (long long)n * C + i);
@@ -305,6 +310,7 @@ spatial_gate_bwd_dq_kernel(const T* __restrict__ dout, const T* __restrict__ a, 
 __global__ void __launch_bounds__(256)
 spatial_gate_bwd_dw_kernel(const float* __restrict__ dq, const float* __restrict__ cmap, float* __restrict__ dwsp,
                            int N, int H, int W) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];   // sdq[TH*W] | tile float2 [(TH+6)*(W+6)]
   float* sdq = sm;
   float2* tile = reinterpret_cast<float2*>(sdq + kGateTH * W + ((kGateTH * W) & 1));
@@ -352,6 +358,7 @@ spatial_gate_bwd_da_kernel(const T* __restrict__ dout, const T* __restrict__ a, 
                            const float* __restrict__ gate, const float* __restrict__ cmap,
                            const float* __restrict__ dq, const float* __restrict__ wsp, T* __restrict__ da,
                            float* __restrict__ dse, int H, int W, int C) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];
   // wsp[98] pad | sse[C] | sdse[C] | s_gate[THW] | s_mx[THW] | s_dmean[THW] | s_dmax[THW] | s_cnt[THW] | dq tile[(TH+6)*(W+6)]
   const int THW = kGateTH * W, Wt = W + 6;
@@ -444,6 +451,7 @@ __global__ void __launch_bounds__(128)
 se_bwd_kernel(const float* __restrict__ dse, const float* __restrict__ se, const float* __restrict__ hid,
               const float* __restrict__ pool, const float* __restrict__ w1, const float* __restrict__ w2,
               float* __restrict__ dpool, float* __restrict__ dw1, float* __restrict__ dw2, int P, int C, int Cr) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];   // dpre2[C] | dpre1[Cr] | sh[Cr] | pm[C]
   float* dpre2 = sm;
   float* dpre1 = sm + C;
@@ -489,6 +497,7 @@ gn_silu_bwd_kernel(const T* __restrict__ da, const float* __restrict__ dpool, co
                    const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ gsum, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    T* __restrict__ dx, int P, int C, int G, float eps) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];   // reduce: sgs[G*2] | sdg[C] | sdb[C]
   float* sgs = sm;
   float* sdg = sm + G * 2;
@@ -579,6 +588,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 scale_channels_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ add,
                       T* __restrict__ out, int N, int P, int C) {
+  PCM_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = (long long)N * P * cv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -615,7 +625,7 @@ extern "C" int pcm_gn_stats(const void* x, float* stats, int N, int P, int C, in
   PCM_REQUIRE(C % 8 == 0 && C % G == 0 && G <= 64 && C / 8 <= 256, "gn_stats: unsupported C=%d G=%d", C, G);
   if (N == 0) return PCM_OK;
   dim3 grid(splits_for(N, P, C / 8), N);
-  PCM_DISPATCH_DTYPE(dtype, T, (gn_stats_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, stats, P, C, G)));
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(gn_stats_kernel<T>, grid, 256, 0, (cudaStream_t)s, (const T*)x, stats, P, C, G)));
   return check_launch("gn_stats");
 }
 
@@ -624,7 +634,7 @@ extern "C" int pcm_gn_silu_fwd(const void* x, const float* stats, const float* g
   PCM_REQUIRE(C % 8 == 0 && C % G == 0 && G <= 64 && C / 8 <= 256, "gn_silu_fwd: unsupported C=%d G=%d", C, G);
   if (N == 0) return PCM_OK;
   dim3 grid(splits_for(N, P, C / 8), N);
-  PCM_DISPATCH_DTYPE(dtype, T, (gn_silu_fwd_kernel<T><<<grid, 256, C * sizeof(float), (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(gn_silu_fwd_kernel<T>, grid, 256, C * sizeof(float), (cudaStream_t)s, 
                                    (const T*)x, stats, gamma, beta, (T*)y, pool, P, C, G, eps)));
   return check_launch("gn_silu_fwd");
 }
@@ -638,7 +648,7 @@ extern "C" int pcm_se_chanstat_fwd(const void* a, const float* pool, const float
   if (splits > smax) splits = smax;
   dim3 grid(splits, N);
   const size_t smem = (2 * C + Cr) * sizeof(float);
-  PCM_DISPATCH_DTYPE(dtype, T, (se_chanstat_fwd_kernel<T><<<grid, 256, smem, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(se_chanstat_fwd_kernel<T>, grid, 256, smem, (cudaStream_t)s, 
                                    (const T*)a, pool, w1, w2, se, hid, cmap, P, C, Cr)));
   return check_launch("se_chanstat_fwd");
 }
@@ -650,7 +660,7 @@ extern "C" int pcm_scale_channels(const void* x, const float* scale, const float
   const long long total = (long long)N * P * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 1184) blocks = 1184;
-  PCM_DISPATCH_DTYPE(dtype, T, (scale_channels_kernel<T><<<(int)blocks, 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(scale_channels_kernel<T>, (int)blocks, 256, 0, (cudaStream_t)s, 
                                    (const T*)x, scale, add, (T*)out, N, P, C)));
   return check_launch("scale_channels");
 }
@@ -664,7 +674,7 @@ extern "C" int pcm_spatial_gate_fwd(const void* a, const float* se, const float*
   const size_t smem = (100 + C + kGateTH * W + 2 + 2 * (kGateTH + 6) * (W + 6)) * sizeof(float);
   if (smem > 48 * 1024)
     PCM_DISPATCH_DTYPE(dtype, T, cudaFuncSetAttribute(spatial_gate_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PCM_DISPATCH_DTYPE(dtype, T, (spatial_gate_fwd_kernel<T><<<grid, 256, smem, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(spatial_gate_fwd_kernel<T>, grid, 256, smem, (cudaStream_t)s, 
                                    (const T*)a, se, cmap, wsp, gate, (T*)out, H, W, C)));
   return check_launch("spatial_gate_fwd");
 }
@@ -674,7 +684,7 @@ extern "C" int pcm_spatial_gate_bwd_dq(const void* dout, const void* a, const fl
   PCM_REQUIRE(C % 8 == 0, "spatial_gate_bwd_dq: C must be a multiple of 8");
   if (N == 0) return PCM_OK;
   dim3 grid(ceil_div(P, 256), N);
-  PCM_DISPATCH_DTYPE(dtype, T, (spatial_gate_bwd_dq_kernel<T><<<grid, 256, C * sizeof(float), (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(spatial_gate_bwd_dq_kernel<T>, grid, 256, C * sizeof(float), (cudaStream_t)s, 
                                    (const T*)dout, (const T*)a, se, gate, dq, P, C)));
   return check_launch("spatial_gate_bwd_dq");
 }
@@ -687,7 +697,7 @@ extern "C" int pcm_spatial_gate_bwd_dw(const float* dq, const float* cmap, float
   const size_t smem = (kGateTH * W + 2 + 2 * (kGateTH + 6) * (W + 6)) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(spatial_gate_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  spatial_gate_bwd_dw_kernel<<<blocks, 256, smem, (cudaStream_t)s>>>(dq, cmap, dwsp, N, H, W);
+  pcm::launch(spatial_gate_bwd_dw_kernel, blocks, 256, smem, (cudaStream_t)s, dq, cmap, dwsp, N, H, W);
   return check_launch("spatial_gate_bwd_dw");
 }
 
@@ -701,7 +711,7 @@ extern "C" int pcm_spatial_gate_bwd_da(const void* dout, const void* a, const fl
   const size_t smem = (100 + 2 * C + 5 * kGateTH * W + (kGateTH + 6) * (W + 6)) * sizeof(float);
   if (smem > 48 * 1024)
     PCM_DISPATCH_DTYPE(dtype, T, cudaFuncSetAttribute(spatial_gate_bwd_da_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PCM_DISPATCH_DTYPE(dtype, T, (spatial_gate_bwd_da_kernel<T><<<grid, 256, smem, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(spatial_gate_bwd_da_kernel<T>, grid, 256, smem, (cudaStream_t)s, 
                                    (const T*)dout, (const T*)a, se, gate, cmap, dq, wsp, (T*)da, dse, H, W, C)));
   return check_launch("spatial_gate_bwd_da");
 }
@@ -711,7 +721,7 @@ extern "C" int pcm_se_bwd(const float* dse, const float* se, const float* hid, c
                           pcm_stream_t s) {
   if (N == 0) return PCM_OK;
   const size_t smem = (2 * C + 2 * Cr) * sizeof(float);
-  se_bwd_kernel<<<N, 128, smem, (cudaStream_t)s>>>(dse, se, hid, pool, w1, w2, dpool, dw1, dw2, P, C, Cr);
+  pcm::launch(se_bwd_kernel, N, 128, smem, (cudaStream_t)s, dse, se, hid, pool, w1, w2, dpool, dw1, dw2, P, C, Cr);
   return check_launch("se_bwd");
 }
 
@@ -723,7 +733,7 @@ extern "C" int pcm_gn_silu_bwd_reduce(const void* da, const float* dpool, const 
   if (N == 0) return PCM_OK;
   dim3 grid(splits_for(N, P, C / 8), N);
   const size_t smem = (G * 2 + 2 * C) * sizeof(float);
-  PCM_DISPATCH_DTYPE(dtype, T, (gn_silu_bwd_kernel<T, false><<<grid, 256, smem, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(gn_silu_bwd_kernel<T, false>, grid, 256, smem, (cudaStream_t)s, 
                                    (const T*)da, dpool, (const T*)x, stats, gamma, beta, gsum, dgamma, dbeta,
                                    (T*)nullptr, P, C, G, eps)));
   return check_launch("gn_silu_bwd_reduce");
@@ -735,7 +745,7 @@ extern "C" int pcm_gn_silu_bwd_apply(const void* da, const float* dpool, const v
   PCM_REQUIRE(C % 8 == 0 && C % G == 0 && G <= 64 && C / 8 <= 256, "gn_silu_bwd: unsupported C=%d G=%d", C, G);
   if (N == 0) return PCM_OK;
   dim3 grid(splits_for(N, P, C / 8), N);
-  PCM_DISPATCH_DTYPE(dtype, T, (gn_silu_bwd_kernel<T, true><<<grid, 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(gn_silu_bwd_kernel<T, true>, grid, 256, 0, (cudaStream_t)s, 
                                    (const T*)da, dpool, (const T*)x, stats, gamma, beta, (float*)gsum, nullptr,
                                    nullptr, (T*)dx, P, C, G, eps)));
   return check_launch("gn_silu_bwd_apply");

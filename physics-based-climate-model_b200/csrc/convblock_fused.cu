@@ -100,7 +100,7 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
   L.gate = full ? PCM_TAKE(P * 4) : 0;
   L.dm = (full && bwd) ? PCM_TAKE(P * 8) : 0;
   L.bar = PCM_TAKE(16);                                  // mbarrier of the bulk copy that brings the image in
-  L.part = PCM_TAKE((size_t)4 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 4 slots x warps x C floats
+  L.part = PCM_TAKE((size_t)2 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 2 slots x warps x C floats
   // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
   //         | wt[2][7][8] | wtf[2][7][8] | dw[100] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
   L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + (full ? C * C / 4 : 0)) * 4);
@@ -168,10 +168,35 @@ __device__ __forceinline__ void gn_coef(float gamma, float beta, float mu, float
   za = gamma * rs;
   zb = fmaf(-mu, za, beta);
 }
+// Rounding to the storage type goes through the PACKING conversion (two values per F2FP, ALU pipe) instead of one
+// F2F per value (SFU pipe, which the sigmoid already loads); same round-to-nearest-even result.
+template <typename T> __device__ __forceinline__ void round8_to(float (&a)[8]);
+template <> __device__ __forceinline__ void round8_to<float>(float (&)[8]) {}
+template <> __device__ __forceinline__ void round8_to<__nv_bfloat16>(float (&a)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(__floats2bfloat162_rn(a[2 * i], a[2 * i + 1]));
+    a[2 * i] = f.x; a[2 * i + 1] = f.y;
+  }
+}
+// store 8 values and leave them in `a` as the storage type holds them
+__device__ __forceinline__ void store8_rounded(float* p, float (&a)[8]) { store8(p, a); }
+__device__ __forceinline__ void store8_rounded(__nv_bfloat16* p, float (&a)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+    const float2 f = __bfloat1622float2(h[i]);
+    a[2 * i] = f.x; a[2 * i + 1] = f.y;
+  }
+  *reinterpret_cast<uint4*>(p) = u;
+}
+// a = silu(z), unrounded (callers round eight at a time)
 template <typename T>
-__device__ __forceinline__ float silu_act(float x, float za, float zb) {
+__device__ __forceinline__ float silu_raw(float x, float za, float zb) {
   const float z = fmaf(za, x, zb);
-  return round_to<T>(z * sigmoid_t<T>(z));
+  return z * sigmoid_t<T>(z);
 }
 
 // ---- the image comes in through the bulk-copy engine (one thread issues, everybody waits on the mbarrier)
@@ -260,6 +285,7 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
                           float* __restrict__ stats, float* __restrict__ pool_g, float* __restrict__ se_g,
                           float* __restrict__ hid_g, float* __restrict__ maps, uint8_t* __restrict__ ties,
                           T* __restrict__ out, int H, int W, int C, int Cr, float eps) {
+  pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
   const int cvs = __ffs(cv) - 1;
@@ -271,10 +297,13 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
   const int cb = threadIdx.x & (cv - 1);
 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
-  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
   if (FULL) {
     float4* z4 = reinterpret_cast<float4*>(smem + L.cm0);      // cm0 and cm1 are contiguous
     for (int i = threadIdx.x; i < 2 * (H + 6) * Wp / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_wait();                                                  // global memory from here on
+  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
+  if (FULL) {
     load_gate_weights(wsp, sp);
     for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
   }
@@ -294,12 +323,11 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
     float t[8];
     load8_rw(s_img + (size_t)v * 8, t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      t[j] = silu_act<T>(t[j], ga[j], be[j]);
-      acc[j] += t[j];
-    }
-    if (FULL) store8(s_img + (size_t)v * 8, t);
-    else store8(on + (size_t)v * 8, t);
+    for (int j = 0; j < 8; ++j) t[j] = silu_raw<T>(t[j], ga[j], be[j]);
+    if (FULL) store8_rounded(s_img + (size_t)v * 8, t);
+    else store8_rounded(on + (size_t)v * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += t[j];
   }
   if (!FULL) return;
 
@@ -421,6 +449,7 @@ __global__ void __launch_bounds__(kFT, 1)
 gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const float* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ dx,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, int H, int W, int C, float eps) {
+  pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv;
   const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), 0, 1);
@@ -431,18 +460,19 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
   T* dxn = dx + (size_t)n * P * C;
   const int cb = threadIdx.x & (cv - 1);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  pdl_wait();                                                  // global memory from here on
   if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
   group_mu_rs_from_stats(stats + (size_t)n * kGroups * 2, cg, P, eps, sp);
   __syncthreads();
   // xhat = xa*x + xb ; z = za*x + zb
-  float xa[8], xb[8], za[8], zb[8], gm[8], r0[8], r1[8], r2[8], r3[8];
+  float xa[8], xb[8], za[8], zb[8], gm[8], r0[8], r1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cb * 8 + j, g = c / cg;
     gm[j] = __ldg(gamma + c);
     xa[j] = sp.rs[g]; xb[j] = -sp.mu[g] * sp.rs[g];
     za[j] = gm[j] * xa[j]; zb[j] = fmaf(gm[j], xb[j], __ldg(beta + c));
-    r0[j] = r1[j] = r2[j] = r3[j] = 0.f;
+    r0[j] = r1[j] = 0.f;
   }
   image_copy_wait(bar);
   // pass 1: dxhat (stored to dx as scratch) and the reductions
@@ -457,24 +487,24 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
       const float z = fmaf(za[j], t[j], zb[j]);
       const float sg = sigmoid_t<T>(z);
       const float dz = d[j] * sg * fmaf(z, 1.f - sg, 1.f);
-      const float dxh = round_to<T>(dz * gm[j]);
       r0[j] = fmaf(dz, xh, r0[j]);
       r1[j] += dz;
-      r2[j] += dxh;
-      r3[j] = fmaf(dxh, xh, r3[j]);
-      d[j] = dxh;
+      d[j] = dz * gm[j];
     }
     store8(dxn + (size_t)v * 8, d);
   }
   chan_put(r0, sp.part, 0, cb, cv, C);
   chan_put(r1, sp.part, 1, cb, cv, C);
-  chan_put(r2, sp.part, 2, cb, cv, C);
-  chan_put(r3, sp.part, 3, cb, cv, C);
-  chan_finish(sp.part, 4, sp.ch0, C);
+  chan_finish(sp.part, 2, sp.ch0, C);
   if (threadIdx.x < kGroups) {
+    // group means of dxhat = gamma*dz and of dxhat*xhat, from the per-channel sums of dz and dz*xhat
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < cg; ++k) { a += sp.ch2[g * cg + k]; b += sp.ch3[g * cg + k]; }
+    for (int k = 0; k < cg; ++k) {
+      const float gmc = __ldg(gamma + g * cg + k);
+      a = fmaf(gmc, sp.ch1[g * cg + k], a);
+      b = fmaf(gmc, sp.ch0[g * cg + k], b);
+    }
     const float cnt = (float)cg * (float)P;
     sp.m1[g] = a / cnt;
     sp.m2[g] = b / cnt;
@@ -522,6 +552,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
                           const float* __restrict__ maps, const uint8_t* __restrict__ ties, T* __restrict__ dx,
                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw1,
                           float* __restrict__ dw2, float* __restrict__ dwsp, int H, int W, int C, int Cr, float eps) {
+  pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
   const int cvs = __ffs(cv) - 1;
@@ -544,11 +575,12 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   const int cb = threadIdx.x & (cv - 1);
   const float invP = 1.f / (float)P;
 
-  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
   {
     float4* z4 = reinterpret_cast<float4*>(cm0);                                // cm0 | cm1 | dq are contiguous
     for (int i = threadIdx.x; i < 3 * (H + 6) * Wp / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  pdl_wait();                                                                   // global memory from here on
+  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
   load_gate_weights(wsp, sp);
   for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
   for (int c = threadIdx.x; c < C; c += NT) {
@@ -663,7 +695,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   image_copy_wait(bar);                                    // x is in shared memory from here on
 
   // ---- pass B (sigmoid #1): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
-  // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu_act), so the
+  // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu_raw + rounding), so the
   // comparison against the saved maximum selects the same channels.
   {
     float acc[8];
@@ -681,8 +713,11 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
         const float2 dm = s_dm[pw.p];
         const float mx = cm1[(pw.h + 3) * Wp + pw.w + 4];
 #pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = silu_raw<T>(t[j], za[j], zb[j]);
+        round8_to<T>(t);
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float a = silu_act<T>(t[j], za[j], zb[j]);
+          const float a = t[j];
           const float u = a * sc[j];
           const float du = fmaf(d[j], gt, dm.x) + ((u == mx) ? dm.y : 0.f);
           acc[j] = fmaf(du, a, acc[j]);
@@ -726,9 +761,9 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   }
   __syncthreads();
   // ---- GroupNorm + SiLU backward, pass 1 (sigmoid #3): dxhat -> scratch, reductions
-  float dp[8], r0[8], r1[8], r2[8], r3[8];
+  float dp[8], r0[8], r1[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { dp[j] = sp.dpool[cb * 8 + j]; r0[j] = r1[j] = r2[j] = r3[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { dp[j] = sp.dpool[cb * 8 + j]; r0[j] = r1[j] = 0.f; }
 #pragma unroll 2
   for (int v = threadIdx.x; v < nvec; v += NT) {
     float t[8], d[8];
@@ -740,24 +775,23 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       const float z = fmaf(za[j], t[j], zb[j]);
       const float sg = sigmoid_t<T>(z);
       const float dz = (d[j] + dp[j]) * sg * fmaf(z, 1.f - sg, 1.f);
-      const float dxh = round_to<T>(dz * gm[j]);
       r0[j] = fmaf(dz, xh, r0[j]);
       r1[j] += dz;
-      r2[j] += dxh;
-      r3[j] = fmaf(dxh, xh, r3[j]);
-      d[j] = dxh;
+      d[j] = dz * gm[j];
     }
     store8(dxn + (size_t)v * 8, d);
   }
   chan_put(r0, sp.part, 0, cb, cv, C);
   chan_put(r1, sp.part, 1, cb, cv, C);
-  chan_put(r2, sp.part, 2, cb, cv, C);
-  chan_put(r3, sp.part, 3, cb, cv, C);
-  chan_finish(sp.part, 4, sp.ch1, C);
+  chan_finish(sp.part, 2, sp.ch1, C);
   if (threadIdx.x < kGroups) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < cg; ++k) { a += sp.ch3[g * cg + k]; b += sp.ch4[g * cg + k]; }
+    for (int k = 0; k < cg; ++k) {
+      const float gmc = __ldg(gamma + g * cg + k);
+      a = fmaf(gmc, sp.ch2[g * cg + k], a);
+      b = fmaf(gmc, sp.ch1[g * cg + k], b);
+    }
     const float cnt = (float)cg * (float)P;
     sp.m1[g] = a / cnt;
     sp.m2[g] = b / cnt;
@@ -819,7 +853,7 @@ extern "C" int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const floa
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, false>, smem, "gn_silu_img_fwd");
     if (rc == PCM_OK)
-      convblock_tail_fwd_kernel<T, false><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
+      pcm::launch(convblock_tail_fwd_kernel<T, false>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, 
           (const T*)x, gamma, beta, nullptr, nullptr, nullptr, stats, nullptr, nullptr, nullptr, nullptr, nullptr,
           (T*)y, H, W, C, 1, eps);
   });
@@ -840,7 +874,7 @@ extern "C" int pcm_convblock_tail_fwd(const void* x, const float* gamma, const f
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, true>, smem, "convblock_tail_fwd");
     if (rc == PCM_OK)
-      convblock_tail_fwd_kernel<T, true><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
+      pcm::launch(convblock_tail_fwd_kernel<T, true>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, 
           (const T*)x, gamma, beta, w1, w2, wsp, stats, pool, se, hid, maps, ties, (T*)out, H, W, C, Cr, eps);
   });
   if (rc != PCM_OK) return rc;
@@ -858,7 +892,7 @@ extern "C" int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* s
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(gn_silu_img_bwd_kernel<T>, smem, "gn_silu_img_bwd");
     if (rc == PCM_OK)
-      gn_silu_img_bwd_kernel<T><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>((const T*)da, (const T*)x, stats, gamma, beta, (T*)dx,
+      pcm::launch(gn_silu_img_bwd_kernel<T>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, (const T*)da, (const T*)x, stats, gamma, beta, (T*)dx,
                                                                    dgamma, dbeta, H, W, C, eps);
   });
   if (rc != PCM_OK) return rc;
@@ -881,7 +915,7 @@ extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const voi
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_bwd_kernel<T>, smem, "convblock_tail_bwd");
     if (rc == PCM_OK)
-      convblock_tail_bwd_kernel<T><<<N, tail_threads(H, W, C), smem, (cudaStream_t)s>>>(
+      pcm::launch(convblock_tail_bwd_kernel<T>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, 
           (const T*)dout, (const T*)x, (const T*)out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties,
           (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, H, W, C, Cr, eps);
   });

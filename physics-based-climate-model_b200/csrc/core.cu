@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pcm {
@@ -12,6 +14,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const int on = [] {
+    const char* e = getenv("PCM_PDL");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;          // opt-in: measured neutral on B200 (see common.cuh)
+  }();
+  return on != 0;
 }
 
 int check_launch(const char* what) {

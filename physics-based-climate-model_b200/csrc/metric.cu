@@ -11,6 +11,7 @@ namespace pcm {
 __global__ void __launch_bounds__(256)
 metric_partial_kernel(const float* __restrict__ pred, const float* __restrict__ truth, double* __restrict__ partial,
                       int T, int VYX) {
+  PCM_PDL_ENTRY();
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= VYX) return;
   const int per = (T + gridDim.y - 1) / gridDim.y;
@@ -41,6 +42,7 @@ __device__ __forceinline__ double denorm(double x, int kind, double a, double b,
 __global__ void __launch_bounds__(256)
 metric_partial_denorm_kernel(const float* __restrict__ pred, const float* __restrict__ truth,
                              const float* __restrict__ tr, double* __restrict__ partial, int T, int YX, int VYX) {
+  PCM_PDL_ENTRY();
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= VYX) return;
   const int v = pix / YX;
@@ -66,6 +68,7 @@ metric_partial_denorm_kernel(const float* __restrict__ pred, const float* __rest
 __global__ void __launch_bounds__(256)
 metric_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ w_lat, double* __restrict__ out,
                        double Tn, int Y, int X) {
+  PCM_PDL_ENTRY();
   __shared__ double red[32];
   const int v = blockIdx.x;
   double a0 = 0, a1 = 0, a2 = 0, wsum = 0;
@@ -107,7 +110,7 @@ extern "C" int pcm_metric_partial(const float* pred, const float* truth, double*
   if (chunks > (T + 15) / 16) chunks = (T + 15) / 16;
   if (chunks < 1) chunks = 1;
   dim3 grid(gx, chunks);
-  metric_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(pred, truth, partial, T, VYX);
+  pcm::launch(metric_partial_kernel, grid, 256, 0, (cudaStream_t)s, pred, truth, partial, T, VYX);
   return check_launch("metric_partial");
 }
 
@@ -124,13 +127,13 @@ extern "C" int pcm_metric_partial_denorm(const float* pred, const float* truth, 
   int chunks = (4 * 148 + gx - 1) / gx;
   if (chunks > (T + 15) / 16) chunks = (T + 15) / 16;
   if (chunks < 1) chunks = 1;
-  metric_partial_denorm_kernel<<<dim3(gx, chunks), 256, 0, (cudaStream_t)s>>>(pred, truth, tr, partial, T, Y * X, VYX);
+  pcm::launch(metric_partial_denorm_kernel, dim3(gx, chunks), 256, 0, (cudaStream_t)s, pred, truth, tr, partial, T, Y * X, VYX);
   return check_launch("metric_partial_denorm");
 }
 
 extern "C" int pcm_metric_finalize(const double* partial, const double* w_lat, double* out, long long T_total, int V,
                                    int Y, int X, pcm_stream_t s) {
   PCM_REQUIRE(T_total > 0, "metric_finalize: T_total must be positive");
-  metric_finalize_kernel<<<V, 256, 0, (cudaStream_t)s>>>(partial, w_lat, out, (double)T_total, Y, X);
+  pcm::launch(metric_finalize_kernel, V, 256, 0, (cudaStream_t)s, partial, w_lat, out, (double)T_total, Y, X);
   return check_launch("metric_finalize");
 }

@@ -13,6 +13,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int P, int Cp,
                     const int* __restrict__ month, int Tp) {
+  PCM_PDL_ENTRY();
   const int cv = Cp / 8;
   const int Bn = Tp > 1 ? N / Tp : N;
   const long long total = (long long)N * cv * P;
@@ -47,6 +48,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_x4_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int P, int Cp,
                        const int* __restrict__ month, int Tp) {
+  PCM_PDL_ENTRY();
   const int cv = Cp / 8, P4 = P / 4;
   const int Bn = Tp > 1 ? N / Tp : N;
   const long long total = (long long)N * cv * P4;
@@ -88,6 +90,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 window_stage_kernel(const float* __restrict__ series, const int* __restrict__ frames, T* __restrict__ y, int N, int C,
                     int P, int Cp) {
+  PCM_PDL_ENTRY();
   const int cv = Cp / 8, P4 = P / 4;
   const long long total = (long long)N * cv * P4;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -112,6 +115,7 @@ window_stage_kernel(const float* __restrict__ series, const int* __restrict__ fr
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int P, int Cp, int Tp) {
+  PCM_PDL_ENTRY();
   const int cv = Cp / 8;
   const int Bn = Tp > 1 ? N / Tp : N;
   const long long total = (long long)N * cv * P;
@@ -132,15 +136,15 @@ nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C
 }
 
 // ---- pooling / skips -------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename I>          // I: index type (int whenever the tensor allows it)
 __global__ void __launch_bounds__(256)
 maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
+  PCM_PDL_ENTRY();
   const int Ho = H / 2, Wo = W / 2, cv = C / 8;
-  const long long total = (long long)N * Ho * Wo * cv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const I total = (I)N * Ho * Wo * cv;
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
     const int cb = (int)(idx % cv);
-    long long r = idx / cv;
+    I r = idx / cv;
     const int wo = (int)(r % Wo); r /= Wo;
     const int ho = (int)(r % Ho);
     const int n = (int)(r / Ho);
@@ -149,36 +153,44 @@ maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, in
     load8(xp, a); load8(xp + C, b); load8(xp + (long long)W * C, c); load8(xp + (long long)W * C + C, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
-    store8(y + idx * 8, a);
+    store8(y + (size_t)idx * 8, a);
   }
 }
 
-// dx = [x is the FIRST max of its window (scan order)] * dy + dskip/T
-template <typename T>
+// dx = [x is the FIRST max of its window (scan order)] * dy + dskip/T.  One thread per 2x2 window and channel block:
+// the four x vectors are read once (not once per output pixel), nine independent 16-byte loads are in flight per
+// thread, and the index arithmetic is 32-bit whenever the tensor allows it (I = int).
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ dskip,
                          long long dskip_ns, int dskip_ps, T* __restrict__ dx, int N, int H, int W, int C, int Tn,
                          int t_major) {
-  const int Ho = H / 2, Wo = W / 2, cv = C / 8;
+  PCM_PDL_ENTRY();
+  const int Ho = H / 2, Wo = W / 2, Hc = (H + 1) / 2, Wc = (W + 1) / 2, cv = C / 8;
   const float invT = 1.f / (float)Tn;
-  const long long total = (long long)N * H * W * cv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const I total = (I)N * Hc * Wc * cv;
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
     const int cb = (int)(idx % cv);
-    long long r = idx / cv;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H);
-    const int n = (int)(r / H);
-    float out[8];
+    I r = idx / cv;
+    const int wc = (int)(r % Wc); r /= Wc;
+    const int hc = (int)(r % Hc);
+    const int n = (int)(r / Hc);
+    const int h0 = 2 * hc, w0 = 2 * wc;
+    const bool has_h1 = h0 + 1 < H, has_w1 = w0 + 1 < W, pooled = dy != nullptr && hc < Ho && wc < Wo;
+    const size_t base = (((size_t)n * H + h0) * W + w0) * C + (size_t)cb * 8;
+    const size_t offs[4] = {0, (size_t)C, (size_t)W * C, (size_t)W * C + C};
+    const bool live[4] = {true, has_w1, has_h1, has_h1 && has_w1};
+    float o[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = 0.f;
-    const int ho = h >> 1, wo = w >> 1;
-    if (dy != nullptr && ho < Ho && wo < Wo) {
-      const T* xp = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cb * 8;
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[k][j] = 0.f;
+    }
+    if (pooled) {
       float q[4][8], g[8];
-      load8(xp, q[0]); load8(xp + C, q[1]); load8(xp + (long long)W * C, q[2]); load8(xp + (long long)W * C + C, q[3]);
-      load8(dy + (((long long)n * Ho + ho) * Wo + wo) * C + cb * 8, g);
-      const int me = (h & 1) * 2 + (w & 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load8(x + base + offs[k], q[k]);
+      load8(dy + (((size_t)n * Ho + hc) * Wo + wc) * C + (size_t)cb * 8, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         int arg = 0;
@@ -186,35 +198,45 @@ maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
 #pragma unroll
         for (int k = 1; k < 4; ++k)
           if (q[k][j] > m) { m = q[k][j]; arg = k; }
-        out[j] = (arg == me) ? g[j] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k][j] = (arg == k) ? g[j] : 0.f;
       }
     }
     if (dskip != nullptr) {
-      float sk[8];
       const int bi = t_major ? n % (N / Tn) : n / Tn;
-      load8(dskip + (long long)bi * dskip_ns + ((long long)h * W + w) * dskip_ps + cb * 8, sk);
+      const T* sp = dskip + (size_t)bi * dskip_ns + (size_t)cb * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) out[j] = fmaf(sk[j], invT, out[j]);
+      for (int k = 0; k < 4; ++k) {
+        if (live[k]) {
+          float sk[8];
+          load8(sp + ((size_t)(h0 + (k >> 1)) * W + (w0 + (k & 1))) * dskip_ps, sk);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[k][j] = fmaf(sk[j], invT, o[k][j]);
+        }
+      }
     }
-    store8(dx + idx * 8, out);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (live[k]) store8(dx + base + offs[k], o[k]);
   }
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 time_mean_kernel(const T* __restrict__ src, T* __restrict__ dst, long long dst_ns, int dst_ps, int B, int Tn, int P,
                  int C, int t_major) {
+  PCM_PDL_ENTRY();
   const int cv = C / 8;
   const float invT = 1.f / (float)Tn;
-  const long long total = (long long)B * P * cv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const I total = (I)B * P * cv;
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
     const int cb = (int)(idx % cv);
     const int p = (int)((idx / cv) % P);
-    const int b = (int)(idx / ((long long)cv * P));
+    const int b = (int)(idx / ((I)cv * P));
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 6
     for (int t = 0; t < Tn; ++t) {
       float v[8];
       const long long img = t_major ? (long long)t * B + b : (long long)b * Tn + t;
@@ -233,6 +255,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 lstm_cell_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, T* __restrict__ acts,
                      float* __restrict__ c, T* __restrict__ h, int M, int Ch) {
+  PCM_PDL_ENTRY();
   const int cv = Ch / 8;
   const long long total = (long long)M * cv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -264,6 +287,7 @@ __global__ void __launch_bounds__(256)
 lstm_cell_bwd_kernel(const T* __restrict__ dh_a, const T* __restrict__ dh_b, const float* __restrict__ dc_in,
                      const T* __restrict__ acts, const float* __restrict__ c_prev, const float* __restrict__ c,
                      T* __restrict__ dgates, float* __restrict__ dc_prev, int M, int Ch) {
+  PCM_PDL_ENTRY();
   const int cv = Ch / 8;
   const long long total = (long long)M * cv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -307,6 +331,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ out, int N, int P, int C, int K) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sw[];   // w[K][C] | b[K]
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = __ldg(w + i);
   for (int i = threadIdx.x; i < K; i += blockDim.x) sw[K * C + i] = __ldg(b + i);
@@ -334,6 +359,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ x, const float* __restrict__ w,
                 T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int N, int P, int C, int K) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];   // w[K][C] | accw[K][C] | accb[K]
   float* sw = sm;
   float* accw = sm + K * C;
@@ -381,6 +407,7 @@ head_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ x, const f
 
 __global__ void __launch_bounds__(256)
 mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ loss, long long n) {
+  PCM_PDL_ENTRY();
   __shared__ float red[32];
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -394,6 +421,7 @@ mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* 
 __global__ void __launch_bounds__(256)
 mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gscale,
                float* __restrict__ da, long long n) {
+  PCM_PDL_ENTRY();
   const float k = 2.f / (float)n * (gscale ? __ldg(gscale) : 1.f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     da[i] = k * (__ldg(a + i) - __ldg(b + i));
@@ -401,6 +429,7 @@ mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const f
 
 // ---- Adam (torch.optim.Adam semantics, main_final.py:742-746) -----------------------------------------
 __global__ void adam_tick_kernel(float* state, float b1, float b2) {
+  PCM_PDL_ENTRY();
   // state: [0]=step, [1]=1-b1^step, [2]=1-b2^step
   const float step = state[0] + 1.f;
   state[0] = step;
@@ -412,6 +441,7 @@ __global__ void __launch_bounds__(256)
 adam_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   const float* __restrict__ state, long long n, float lr, float b1, float b2, float eps, float wd,
                   float grad_scale) {
+  PCM_PDL_ENTRY();
   const float bc1 = state[1], bc2s = sqrtf(state[2]);
   const float step_size = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -444,10 +474,10 @@ extern "C" int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, in
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
   if ((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_x4_kernel<T><<<grid_for(total / 4), 256, 0, (cudaStream_t)s>>>(
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(nchw_to_nhwc_x4_kernel<T>, grid_for(total / 4), 256, 0, (cudaStream_t)s, 
                                      x, (T*)y, N, C, H * W, Cp, nullptr, T_)));
   } else {
-    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(nchw_to_nhwc_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s, 
                                      x, (T*)y, N, C, H * W, Cp, nullptr, T_)));
   }
   return check_launch("nchw_to_nhwc");
@@ -459,7 +489,7 @@ extern "C" int pcm_window_stage(const float* series, const int* frames, void* y,
   PCM_REQUIRE((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(series) & 15) == 0, "window_stage: H*W must be a multiple of 4");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W / 4;
-  PCM_DISPATCH_DTYPE(dtype, T, (window_stage_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(window_stage_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s, 
                                    series, frames, (T*)y, N, C, H * W, Cp)));
   return check_launch("window_stage");
 }
@@ -471,10 +501,10 @@ extern "C" int pcm_season_embed_stage(const float* x5, const int* month, void* y
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
   if ((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(x5) & 15) == 0) {
-    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_x4_kernel<T><<<grid_for(total / 4), 256, 0, (cudaStream_t)s>>>(
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(nchw_to_nhwc_x4_kernel<T>, grid_for(total / 4), 256, 0, (cudaStream_t)s, 
                                      x5, (T*)y, N, 5, H * W, Cp, month, T_)));
   } else {
-    PCM_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(nchw_to_nhwc_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s, 
                                      x5, (T*)y, N, 5, H * W, Cp, month, T_)));
   }
   return check_launch("season_embed_stage");
@@ -486,7 +516,7 @@ extern "C" int pcm_nhwc_to_nchw(const void* x, float* y, int N, int C, int H, in
   PCM_REQUIRE(T_ >= 1 && N % T_ == 0, "nhwc_to_nchw: N must be a multiple of T");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W;
-  PCM_DISPATCH_DTYPE(dtype, T, (nhwc_to_nchw_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(nhwc_to_nchw_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s, 
                                    (const T*)x, y, N, C, H * W, Cp, T_)));
   return check_launch("nhwc_to_nchw");
 }
@@ -495,8 +525,13 @@ extern "C" int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int
   PCM_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "maxpool2_fwd: bad shape");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
-  PCM_DISPATCH_DTYPE(dtype, T, (maxpool2_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   (const T*)x, (T*)y, N, H, W, C)));
+  if (total + (long long)kGridCap * 256 < 0x7fffffffLL) {
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(maxpool2_fwd_kernel<T, int>, grid_for(total), 256, 0, (cudaStream_t)s,
+                                     (const T*)x, (T*)y, N, H, W, C)));
+  } else {
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(maxpool2_fwd_kernel<T, long long>, grid_for(total), 256, 0, (cudaStream_t)s,
+                                     (const T*)x, (T*)y, N, H, W, C)));
+  }
   return check_launch("maxpool2_fwd");
 }
 
@@ -505,10 +540,16 @@ extern "C" int pcm_maxpool2_bwd_skip(const void* x, const void* dy, const void* 
                                      int dtype, pcm_stream_t s) {
   PCM_REQUIRE(C % 8 == 0 && T_ >= 1 && N % T_ == 0, "maxpool2_bwd_skip: bad shape");
   if (N == 0) return PCM_OK;
-  const long long total = (long long)N * H * W * (C / 8);
-  PCM_DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_skip_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps, (T*)dx, N, H, W, C,
-                                   T_, t_major)));
+  const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  if (total + (long long)kGridCap * 256 < 0x7fffffffLL) {
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(maxpool2_bwd_skip_kernel<T, int>, grid_for(total), 256, 0, (cudaStream_t)s,
+                                     (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps, (T*)dx, N, H, W, C,
+                                     T_, t_major)));
+  } else {
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(maxpool2_bwd_skip_kernel<T, long long>, grid_for(total), 256, 0, (cudaStream_t)s,
+                                     (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps, (T*)dx, N, H, W, C,
+                                     T_, t_major)));
+  }
   return check_launch("maxpool2_bwd_skip");
 }
 
@@ -517,8 +558,13 @@ extern "C" int pcm_time_mean(const void* src, void* dst, long long dst_ns, int d
   PCM_REQUIRE(C % 8 == 0 && T_ >= 1, "time_mean: bad shape");
   if (B == 0) return PCM_OK;
   const long long total = (long long)B * P * (C / 8);
-  PCM_DISPATCH_DTYPE(dtype, T, (time_mean_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
-                                   (const T*)src, (T*)dst, dst_ns, dst_ps, B, T_, P, C, t_major)));
+  if (total + (long long)kGridCap * 256 < 0x7fffffffLL) {
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(time_mean_kernel<T, int>, grid_for(total), 256, 0, (cudaStream_t)s,
+                                     (const T*)src, (T*)dst, dst_ns, dst_ps, B, T_, P, C, t_major)));
+  } else {
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(time_mean_kernel<T, long long>, grid_for(total), 256, 0, (cudaStream_t)s,
+                                     (const T*)src, (T*)dst, dst_ns, dst_ps, B, T_, P, C, t_major)));
+  }
   return check_launch("time_mean");
 }
 
@@ -527,7 +573,7 @@ extern "C" int pcm_lstm_cell_fwd(const float* gates, const float* c_prev, void* 
   PCM_REQUIRE(Ch % 8 == 0, "lstm_cell_fwd: Ch must be a multiple of 8");
   if (M == 0) return PCM_OK;
   const long long total = (long long)M * (Ch / 8);
-  PCM_DISPATCH_DTYPE(dtype, T, (lstm_cell_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(lstm_cell_fwd_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s, 
                                    gates, c_prev, (T*)acts, c, (T*)h, M, Ch)));
   return check_launch("lstm_cell_fwd");
 }
@@ -538,7 +584,7 @@ extern "C" int pcm_lstm_cell_bwd(const void* dh_a, const void* dh_b, const float
   PCM_REQUIRE(Ch % 8 == 0, "lstm_cell_bwd: Ch must be a multiple of 8");
   if (M == 0) return PCM_OK;
   const long long total = (long long)M * (Ch / 8);
-  PCM_DISPATCH_DTYPE(dtype, T, (lstm_cell_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(lstm_cell_bwd_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s, 
                                    (const T*)dh_a, (const T*)dh_b, dc_in, (const T*)acts, c_prev, c, (T*)dgates,
                                    dc_prev, M, Ch)));
   return check_launch("lstm_cell_bwd");
@@ -549,7 +595,7 @@ extern "C" int pcm_head_fwd(const void* x, const float* w, const float* b, float
   PCM_REQUIRE(C % 8 == 0 && K >= 1, "head_fwd: bad shape");
   if (N == 0) return PCM_OK;
   const size_t smem = (size_t)(K * C + K) * sizeof(float);
-  PCM_DISPATCH_DTYPE(dtype, T, (head_fwd_kernel<T><<<grid_for((long long)N * P), 256, smem, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(head_fwd_kernel<T>, grid_for((long long)N * P), 256, smem, (cudaStream_t)s, 
                                    (const T*)x, w, b, out_nchw, N, P, C, K)));
   return check_launch("head_fwd");
 }
@@ -561,7 +607,7 @@ extern "C" int pcm_head_bwd(const float* dout_nchw, const void* x, const float* 
   const size_t smem = (size_t)(2 * K * C + K) * sizeof(float);
   long long blocks = ((long long)N * P + 255) / 256;
   if (blocks > 592) blocks = 592;
-  PCM_DISPATCH_DTYPE(dtype, T, (head_bwd_kernel<T><<<(int)blocks, 256, smem, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(head_bwd_kernel<T>, (int)blocks, 256, smem, (cudaStream_t)s, 
                                    dout_nchw, (const T*)x, w, (T*)dx, dw, db, N, P, C, K)));
   return check_launch("head_bwd");
 }
@@ -570,21 +616,21 @@ extern "C" int pcm_mse_fwd(const float* a, const float* b, float* loss, long lon
   if (n == 0) return PCM_OK;
   long long blocks = (n + 1023) / 1024;
   if (blocks > 296) blocks = 296;
-  mse_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(a, b, loss, n);
+  pcm::launch(mse_fwd_kernel, (int)blocks, 256, 0, (cudaStream_t)s, a, b, loss, n);
   return check_launch("mse_fwd");
 }
 
 extern "C" int pcm_mse_bwd(const float* a, const float* b, const float* gscale, float* da, long long n,
                            pcm_stream_t s) {
   if (n == 0) return PCM_OK;
-  mse_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(a, b, gscale, da, n);
+  pcm::launch(mse_bwd_kernel, grid_for(n), 256, 0, (cudaStream_t)s, a, b, gscale, da, n);
   return check_launch("mse_bwd");
 }
 
 extern "C" int pcm_adam_step(float* p, const float* g, float* m, float* v, float* state, long long n, float lr,
                              float b1, float b2, float eps, float wd, float grad_scale, pcm_stream_t s) {
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(state, b1, b2);
+  pcm::launch(adam_tick_kernel, 1, 1, 0, (cudaStream_t)s, state, b1, b2);
   if (n > 0)
-    adam_apply_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(p, g, m, v, state, n, lr, b1, b2, eps, wd, grad_scale);
+    pcm::launch(adam_apply_kernel, grid_for(n), 256, 0, (cudaStream_t)s, p, g, m, v, state, n, lr, b1, b2, eps, wd, grad_scale);
   return check_launch("adam_step");
 }

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
 add_layernorm_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ gamma,
                          const float* __restrict__ beta, T* __restrict__ sum_out, T* __restrict__ y,
                          float* __restrict__ stat, int M, int E, float eps) {
+  PCM_PDL_ENTRY();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int nv = E / 8;
   for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ sum_in, const float* __restrict__ stat,
                      const float* __restrict__ gamma, T* __restrict__ ds, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int M, int E) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sh[];     // [2][E]
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int nv = E / 8;
@@ -150,6 +152,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(256)
 mha_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int L, int nh, float scale,
                float drop_p, unsigned long long seed) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];
   float* sK = sm;                 // [L][D]
   float* sV = sm + (size_t)L * D; // [L][D]
@@ -242,6 +245,7 @@ __global__ void __launch_bounds__(256)
 mha_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
                const float* __restrict__ lse, T* __restrict__ dqkv, int L, int nh, float scale, float drop_p,
                unsigned long long seed) {
+  PCM_PDL_ENTRY();
   extern __shared__ float sm[];
   float* sQ = sm;                       // [L][D]  (pre-scaled by `scale`)
   float* sK = sQ + (size_t)L * D;
@@ -383,7 +387,7 @@ extern "C" int pcm_add_layernorm_fwd(const void* a, const void* b, const float* 
   if (M == 0) return PCM_OK;
   int grid = ceil_div(M, 8);
   if (grid > 148 * 8) grid = 148 * 8;
-  PCM_DISPATCH_DTYPE(dtype, T, (add_layernorm_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(add_layernorm_fwd_kernel<T>, grid, 256, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(a), static_cast<const T*>(b), gamma, beta, static_cast<T*>(sum_out),
                                    static_cast<T*>(y), stat, M, E, eps)));
   return check_launch("add_layernorm_fwd");
@@ -395,7 +399,7 @@ extern "C" int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float
   if (M == 0) return PCM_OK;
   int grid = ceil_div(M, 8 * 8);
   if (grid > 148 * 2) grid = 148 * 2;
-  PCM_DISPATCH_DTYPE(dtype, T, (layernorm_bwd_kernel<T><<<grid, 256, 2 * E * sizeof(float), (cudaStream_t)s>>>(
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(layernorm_bwd_kernel<T>, grid, 256, 2 * E * sizeof(float), (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(sum_in), stat, gamma, static_cast<T*>(ds),
                                    dgamma, dbeta, M, E)));
   return check_launch("layernorm_bwd");
@@ -407,7 +411,7 @@ static int mha_fwd_launch(const void* qkv, void* out, float* lse, int B, int L, 
   const size_t smem = (size_t)2 * L * D * sizeof(float);
   int rc = set_smem(mha_fwd_kernel<T, D>, smem, "mha_fwd");
   if (rc != PCM_OK) return rc;
-  mha_fwd_kernel<T, D><<<B * nh, 256, smem, (cudaStream_t)s>>>(static_cast<const T*>(qkv), static_cast<T*>(out), lse, L, nh,
+  pcm::launch(mha_fwd_kernel<T, D>, B * nh, 256, smem, (cudaStream_t)s, static_cast<const T*>(qkv), static_cast<T*>(out), lse, L, nh,
                                                                scale, p, (unsigned long long)seed);
   return check_launch("mha_fwd");
 }
@@ -418,7 +422,7 @@ static int mha_bwd_launch(const void* qkv, const void* out, const void* dout, co
   const size_t smem = ((size_t)4 * L * D + 2 * L) * sizeof(float);
   int rc = set_smem(mha_bwd_kernel<T, D>, smem, "mha_bwd");
   if (rc != PCM_OK) return rc;
-  mha_bwd_kernel<T, D><<<B * nh, 256, smem, (cudaStream_t)s>>>(static_cast<const T*>(qkv), static_cast<const T*>(out),
+  pcm::launch(mha_bwd_kernel<T, D>, B * nh, 256, smem, (cudaStream_t)s, static_cast<const T*>(qkv), static_cast<const T*>(out),
                                                                static_cast<const T*>(dout), lse, static_cast<T*>(dqkv), L,
                                                                nh, scale, p, (unsigned long long)seed);
   return check_launch("mha_bwd");

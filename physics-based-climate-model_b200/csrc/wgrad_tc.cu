@@ -40,6 +40,7 @@ constexpr int kWgThreads = 192;
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmB2, float* __restrict__ dw, unsigned int* __restrict__ err, const WgradTcParams p) {
+  pdl_launch_dependents();          // the next kernel may start launching; it waits for us in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -73,6 +74,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                       // predecessor complete: global memory may be touched from here on
   const uint32_t tmem_base = *tmem_slot;
   const int my_tiles = (p.num_ktiles - split + nsplit - 1) / nsplit;
 
@@ -356,7 +358,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   if (nsplit < 1) nsplit = 1;
   if (nsplit > p.num_ktiles) nsplit = p.num_ktiles;
   dim3 grid(nsplit, mtiles, p.ngroups);
-  wgrad3x3_tc_kernel<<<grid, kWgThreads, smem, (cudaStream_t)s>>>(tmA, tmB, tmB2, dw, err, p);
+  pcm::launch(wgrad3x3_tc_kernel, grid, kWgThreads, smem, (cudaStream_t)s, tmA, tmB, tmB2, dw, err, p);
   return check_launch("wgrad3x3_tc");
 }
 

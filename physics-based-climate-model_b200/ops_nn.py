@@ -279,7 +279,7 @@ class BatchNormFn(torch.autograd.Function):
         R = x.numel() // C
         d, st = _DT[x.dtype], _s()
         if training:
-            sums = torch.zeros(C * 2, device=x.device, dtype=torch.float32)
+            sums = torch.zeros(C * 2, device=x.device, dtype=torch.float64)     # (sum, sum of squares) in double
             _call("pcm_bn_stats", x.data_ptr(), sums.data_ptr(), R, C, d, st)
             if running_mean is not None:
                 _call("pcm_bn_update_running", sums.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(),
@@ -287,7 +287,7 @@ class BatchNormFn(torch.autograd.Function):
         else:
             # the kernels derive mean/var from (sum, sum of squares) / R: encode the running statistics that way
             # (a C-element host-side staging of buffers, not activation arithmetic)
-            rm, rv = running_mean.float(), running_var.float()
+            rm, rv = running_mean.double(), running_var.double()
             sums = (torch.stack([rm, rv + rm * rm], dim=1) * float(R)).reshape(-1).contiguous()
         y = torch.empty_like(x)
         if res is not None:

@@ -125,3 +125,51 @@ def test_parameter_surface_and_default_init_match_reference():
         assert list(a.keys()) == list(b.keys())
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_every_kernel_follows_the_dependent_launch_protocol():
+    """Kernels are launched with programmatic stream serialization (csrc/common.cuh): each __global__ function must
+    execute griddepcontrol.wait (PCM_PDL_ENTRY or pdl_wait) and no launch may bypass pcm::launch."""
+    import glob
+    import os
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "physics-based-climate-model_b200", "csrc")
+    n_kernels = 0
+    for path in sorted(glob.glob(os.path.join(csrc, "*.cu"))):
+        src = open(path).read()
+        assert "<<<" not in src, f"{path}: raw <<< >>> launch (use pcm::launch)"
+        for m in re.finditer(r"__global__", src):
+            start = src.index("{", _skip_signature(src, m.end()))
+            depth, i = 0, start
+            while True:
+                depth += src[i] == "{"
+                depth -= src[i] == "}"
+                if depth == 0:
+                    break
+                i += 1
+            body = src[start:i]
+            n_kernels += 1
+            assert "PCM_PDL_ENTRY()" in body or ("pdl_wait()" in body and "pdl_launch_dependents()" in body), \
+                f"{path}: kernel at offset {m.start()} has no griddepcontrol.wait"
+            first_ret = body.find("return")
+            first_wait = min(x for x in (body.find("PCM_PDL_ENTRY()"), body.find("pdl_wait()")) if x >= 0)
+            assert first_ret < 0 or first_wait < first_ret, f"{path}: kernel at offset {m.start()} can return before the wait"
+    assert n_kernels >= 50
+
+
+def _skip_signature(src, pos):
+    """index just past the parameter list of the kernel whose __global__ keyword ends at pos"""
+    i = src.index("(", pos)
+    while src[pos:i].rstrip().endswith("__launch_bounds__"):
+        i = src.index("(", _close(src, i))
+    return _close(src, i)
+
+
+def _close(src, i):
+    depth = 0
+    while True:
+        depth += src[i] == "("
+        depth -= src[i] == ")"
+        i += 1
+        if depth == 0:
+            return i
