@@ -73,6 +73,34 @@ __device__ __forceinline__ void load8_rw(const T* p, float d[8]) {
   }
 }
 
+// An 8-element vector as it sits in memory (16 bytes of bf16 / 32 bytes of fp32): the global-memory passes issue
+// the loads of several rounds back to back into these and convert afterwards — with 16 warps per SM a loop that
+// loads, waits and computes one round at a time is bound by memory latency, not bandwidth.
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+template <bool NC> __device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw(const __nv_bfloat16* p) {
+  Raw8<__nv_bfloat16> r;
+  r.u = NC ? __ldg(reinterpret_cast<const uint4*>(p)) : *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+template <bool NC> __device__ __forceinline__ Raw8<float> ld_raw(const float* p) {
+  Raw8<float> r;
+  const float4* q = reinterpret_cast<const float4*>(p);
+  r.a = NC ? __ldg(q) : q[0];
+  r.b = NC ? __ldg(q + 1) : q[1];
+  return r;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float d[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); d[2 * i] = f.x; d[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float d[8]) {
+  d[0] = r.a.x; d[1] = r.a.y; d[2] = r.a.z; d[3] = r.a.w; d[4] = r.b.x; d[5] = r.b.y; d[6] = r.b.z; d[7] = r.b.w;
+}
+template <typename T> constexpr int raw_batch() { return sizeof(T) == 2 ? 4 : 2; }   // vectors in flight per operand
+
 // Gate maps (channel mean / max, dq) live in zero-padded planes: pixel (h, w) at (h + 3) * Wp + (w + 4), with
 // Wp = roundup8(W) + 8, so that the 16 floats [w0, w0 + 16) a run of 8 pixels needs from one row are four aligned
 // 16-byte shared-memory loads.
@@ -99,7 +127,7 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
   L.dq = (full && bwd) ? PCM_TAKE(Pp * 4) : 0;
   L.gate = full ? PCM_TAKE(P * 4) : 0;
   L.dm = (full && bwd) ? PCM_TAKE(P * 8) : 0;
-  L.bar = PCM_TAKE(16);                                  // mbarrier of the bulk copy that brings the image in
+  L.bar = PCM_TAKE(64);                                  // mbarriers of the bulk copies that bring the image in (one per 32 KB piece)
   L.part = PCM_TAKE((size_t)2 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 2 slots x warps x C floats
   // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
   //         | wt[2][7][8] | wtf[2][7][8] | dw[100] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
@@ -199,21 +227,23 @@ __device__ __forceinline__ float silu_raw(float x, float za, float zb) {
   return z * sigmoid_t<T>(z);
 }
 
-// ---- the image comes in through the bulk-copy engine (one thread issues, everybody waits on the mbarrier)
+// ---- the image comes in through the bulk-copy engine in 32 KB pieces, one mbarrier per piece (one thread issues;
+// a pass that walks the image front to back waits piece by piece, so it starts while the rest is still in flight)
+constexpr uint32_t kPieceShift = 15, kPiece = 1u << kPieceShift;              // <= 8 pieces: 256 KB > any image
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void image_copy_start(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
-  const uint32_t b = smem_addr(bar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+__device__ __forceinline__ void image_copy_start(uint64_t* bars, void* dst, const void* src, uint32_t bytes) {
+  const uint32_t npiece = (bytes + kPiece - 1) >> kPieceShift;
+  for (uint32_t i = 0; i < npiece; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + i)));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-  for (uint32_t off = 0; off < bytes; off += 32768u) {
-    const uint32_t n = min(32768u, bytes - off);
+  for (uint32_t i = 0; i < npiece; ++i) {
+    const uint32_t off = i << kPieceShift, n = min(kPiece, bytes - off), b = smem_addr(bars + i);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(n) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst) + off), "l"(reinterpret_cast<const uint8_t*>(src) + off), "r"(n), "r"(b) : "memory");
   }
 }
-__device__ __forceinline__ void image_copy_wait(uint64_t* bar) {
-  const uint32_t b = smem_addr(bar);
+__device__ __forceinline__ void image_piece_wait(uint64_t* bars, uint32_t piece) {
+  const uint32_t b = smem_addr(bars + piece);
   const long long t0 = clock64();
   for (;;) {
     uint32_t ok;
@@ -223,22 +253,39 @@ __device__ __forceinline__ void image_copy_wait(uint64_t* bar) {
     if (clock64() - t0 > 4000000000LL) __trap();       // ~2 s: never hang the GPU
   }
 }
+__device__ __forceinline__ void image_copy_wait(uint64_t* bars, uint32_t bytes) {
+  const uint32_t npiece = (bytes + kPiece - 1) >> kPieceShift;
+  for (uint32_t i = 0; i < npiece; ++i) image_piece_wait(bars, i);
+}
+// front-to-back walkers: vector v (16 or 32 bytes) may be read once pieces [0, piece(v)] have landed
+struct PieceWalk {
+  uint64_t* bars;
+  int ready;                       // pieces [0, ready) are known to have landed
+  __device__ __forceinline__ PieceWalk(uint64_t* b) : bars(b), ready(0) {}
+  __device__ __forceinline__ void need(uint32_t byte_end) {          // data up to byte_end (exclusive) is about to be read
+    const int want = (int)((byte_end + kPiece - 1) >> kPieceShift);
+    while (ready < want) image_piece_wait(bars, (uint32_t)ready++);
+  }
+};
 
 // GroupNorm statistics of the image in shared memory -> mu/rs per group (+ raw sums to `stats_out` when non-null)
 template <typename T>
 __device__ __forceinline__ void image_group_stats(const T* s_img, int nvec, int cv, int cg, int P, float eps,
-                                                  const TailPtrs& sp, float* stats_out) {
+                                                  const TailPtrs& sp, float* stats_out, uint64_t* bars) {
   const int cb = threadIdx.x & (cv - 1);
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  PieceWalk land(bars);
 #pragma unroll 2
   for (int v = threadIdx.x; v < nvec; v += NT) {
     float x[8];
+    land.need((uint32_t)(v + 1) * 8u * (uint32_t)sizeof(T));
     load8_rw(s_img + (size_t)v * 8, x);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += x[j]; q[j] = fmaf(x[j], x[j], q[j]); }
   }
+  land.need((uint32_t)nvec * 8u * (uint32_t)sizeof(T));       // every thread has seen the whole image land
   chan_put(s, sp.part, 0, cb, cv, cv * 8);
   chan_put(q, sp.part, 1, cb, cv, cv * 8);
   chan_finish(sp.part, 2, sp.ch0, cv * 8);
@@ -308,8 +355,7 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
     for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
   }
   __syncthreads();
-  image_copy_wait(bar);
-  image_group_stats<T>(s_img, nvec, cv, cg, P, eps, sp, stats + (size_t)n * kGroups * 2);
+  image_group_stats<T>(s_img, nvec, cv, cg, P, eps, sp, stats + (size_t)n * kGroups * 2, bar);
 
   float ga[8], be[8], acc[8];
 #pragma unroll
@@ -474,24 +520,34 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
     za[j] = gm[j] * xa[j]; zb[j] = fmaf(gm[j], xb[j], __ldg(beta + c));
     r0[j] = r1[j] = 0.f;
   }
-  image_copy_wait(bar);
-  // pass 1: dxhat (stored to dx as scratch) and the reductions
-#pragma unroll 2
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8], d[8];
-    load8_rw(s_img + (size_t)v * 8, t);
-    load8(dan + (size_t)v * 8, d);
+  // pass 1: dxhat (stored to dx as scratch) and the reductions; x is consumed as its pieces land
+  constexpr int KB = raw_batch<T>();
+  PieceWalk land(bar);
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
+    Raw8<T> raw[KB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = fmaf(xa[j], t[j], xb[j]);
-      const float z = fmaf(za[j], t[j], zb[j]);
-      const float sg = sigmoid_t<T>(z);
-      const float dz = d[j] * sg * fmaf(z, 1.f - sg, 1.f);
-      r0[j] = fmaf(dz, xh, r0[j]);
-      r1[j] += dz;
-      d[j] = dz * gm[j];
+    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<true>(dan + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+    land.need((uint32_t)min(v0 + (KB - 1) * NT + 1, nvec) * 8u * (uint32_t)sizeof(T));
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      const int v = v0 + k * NT;
+      if (v < nvec) {
+        float t[8], d[8];
+        load8_rw(s_img + (size_t)v * 8, t);
+        unpack8(raw[k], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(xa[j], t[j], xb[j]);
+          const float z = fmaf(za[j], t[j], zb[j]);
+          const float sg = sigmoid_t<T>(z);
+          const float dz = d[j] * sg * fmaf(z, 1.f - sg, 1.f);
+          r0[j] = fmaf(dz, xh, r0[j]);
+          r1[j] += dz;
+          d[j] = dz * gm[j];
+        }
+        store8(dxn + (size_t)v * 8, d);
+      }
     }
-    store8(dxn + (size_t)v * 8, d);
   }
   chan_put(r0, sp.part, 0, cb, cv, C);
   chan_put(r1, sp.part, 1, cb, cv, C);
@@ -524,14 +580,22 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
     k2[j] = -xa[j] * sp.m2[g] * xa[j];
   }
   // pass 2: every thread re-reads exactly the vectors it wrote in pass 1
-#pragma unroll 2
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8], d[8];
-    load8_rw(s_img + (size_t)v * 8, t);
-    load8_rw(dxn + (size_t)v * 8, d);
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
+    Raw8<T> raw[KB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = fmaf(k0[j], d[j], fmaf(k2[j], t[j], k1[j]));
-    store8(dxn + (size_t)v * 8, d);
+    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<false>(dxn + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      const int v = v0 + k * NT;
+      if (v < nvec) {
+        float t[8], d[8];
+        load8_rw(s_img + (size_t)v * 8, t);
+        unpack8(raw[k], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(k0[j], d[j], fmaf(k2[j], t[j], k1[j]));
+        store8(dxn + (size_t)v * 8, d);
+      }
+    }
   }
 }
 
@@ -602,26 +666,29 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       cm1[ip] = __ldg(mp + P + p);
       s_gate[p] = __ldg(mp + 2 * P + p);
     }
-    constexpr int kBatch = 4;
+    constexpr int kBatch = 2 * raw_batch<T>();
     PixWalk pw(cvs, W);
     for (int r0 = 0; r0 < nround; r0 += kBatch) {
-      float d[kBatch][8], o[kBatch][8], gt[kBatch];
+      Raw8<T> dr[kBatch], orw[kBatch];
+      float gt[kBatch];
       int ip[kBatch];
 #pragma unroll
       for (int k = 0; k < kBatch; ++k) {
         const bool valid = pw.p < P;
         const size_t v = valid ? (size_t)pw.p * cv + cb : 0;
-        load8(don + v * 8, d[k]);
-        load8(outn + v * 8, o[k]);
+        dr[k] = ld_raw<true>(don + v * 8);
+        orw[k] = ld_raw<true>(outn + v * 8);
         gt[k] = (valid && cb == 0) ? __ldg(mp + 2 * P + pw.p) : 1.f;
         ip[k] = (valid && cb == 0) ? (pw.h + 3) * Wp + pw.w + 4 : -1;
         pw.next(W);
       }
 #pragma unroll
       for (int k = 0; k < kBatch; ++k) {
-        float acc = 0.f;
+        float acc = 0.f, d[8], o[8];
+        unpack8(dr[k], d);
+        unpack8(orw[k], o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(d[k][j], o[k][j], acc);
+        for (int j = 0; j < 8; ++j) acc = fmaf(d[j], o[j], acc);
         for (int off = 1; off < cv; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (ip[k] >= 0) s_dq[ip[k]] = acc * (1.f - gt[k]);
       }
@@ -692,7 +759,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     gn_coef(gm[j], __ldg(beta + c), sp.mu[g], sp.rs[g], za[j], zb[j]);
     sc[j] = sp.se[c];
   }
-  image_copy_wait(bar);                                    // x is in shared memory from here on
+  image_copy_wait(bar, (uint32_t)((size_t)P * C * sizeof(T)));      // x is in shared memory from here on
 
   // ---- pass B (sigmoid #1): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
   // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu_raw + rounding), so the
@@ -701,29 +768,41 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    constexpr int KB = raw_batch<T>();
     PixWalk pw(cvs, W);
-#pragma unroll 2
-    for (int r = 0; r < nround; ++r, pw.next(W)) {
-      if (pw.p < P) {
-        const size_t v = (size_t)pw.p * cv + cb;
-        float t[8], d[8];
-        load8_rw(s_img + v * 8, t);
-        load8(don + v * 8, d);
-        const float gt = s_gate[pw.p];
-        const float2 dm = s_dm[pw.p];
-        const float mx = cm1[(pw.h + 3) * Wp + pw.w + 4];
+    for (int r0 = 0; r0 < nround; r0 += KB) {
+      Raw8<T> dr[KB];
+      int pp[KB], ipk[KB];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = silu_raw<T>(t[j], za[j], zb[j]);
-        round8_to<T>(t);
+      for (int k = 0; k < KB; ++k) {
+        pp[k] = pw.p < P ? pw.p : -1;
+        ipk[k] = (pw.h + 3) * Wp + pw.w + 4;
+        dr[k] = ld_raw<true>(don + ((size_t)max(pp[k], 0) * cv + cb) * 8);
+        pw.next(W);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = t[j];
-          const float u = a * sc[j];
-          const float du = fmaf(d[j], gt, dm.x) + ((u == mx) ? dm.y : 0.f);
-          acc[j] = fmaf(du, a, acc[j]);
-          d[j] = du * sc[j];
+      for (int k = 0; k < KB; ++k) {
+        if (pp[k] >= 0) {
+          const size_t v = (size_t)pp[k] * cv + cb;
+          float t[8], d[8];
+          load8_rw(s_img + v * 8, t);
+          unpack8(dr[k], d);
+          const float gt = s_gate[pp[k]];
+          const float2 dm = s_dm[pp[k]];
+          const float mx = cm1[ipk[k]];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = silu_raw<T>(t[j], za[j], zb[j]);
+          round8_to<T>(t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float a = t[j];
+            const float u = a * sc[j];
+            const float du = fmaf(d[j], gt, dm.x) + ((u == mx) ? dm.y : 0.f);
+            acc[j] = fmaf(du, a, acc[j]);
+            d[j] = du * sc[j];
+          }
+          store8(dxn + v * 8, d);
         }
-        store8(dxn + v * 8, d);
       }
     }
     chan_put(acc, sp.part, 0, cb, cv, C);
@@ -764,22 +843,31 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   float dp[8], r0[8], r1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { dp[j] = sp.dpool[cb * 8 + j]; r0[j] = r1[j] = 0.f; }
-#pragma unroll 2
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8], d[8];
-    load8_rw(s_img + (size_t)v * 8, t);
-    load8_rw(dxn + (size_t)v * 8, d);
+  constexpr int KB = raw_batch<T>();
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
+    Raw8<T> raw[KB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = fmaf(xa[j], t[j], xb[j]);
-      const float z = fmaf(za[j], t[j], zb[j]);
-      const float sg = sigmoid_t<T>(z);
-      const float dz = (d[j] + dp[j]) * sg * fmaf(z, 1.f - sg, 1.f);
-      r0[j] = fmaf(dz, xh, r0[j]);
-      r1[j] += dz;
-      d[j] = dz * gm[j];
+    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<false>(dxn + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      const int v = v0 + k * NT;
+      if (v < nvec) {
+        float t[8], d[8];
+        load8_rw(s_img + (size_t)v * 8, t);
+        unpack8(raw[k], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(xa[j], t[j], xb[j]);
+          const float z = fmaf(za[j], t[j], zb[j]);
+          const float sg = sigmoid_t<T>(z);
+          const float dz = (d[j] + dp[j]) * sg * fmaf(z, 1.f - sg, 1.f);
+          r0[j] = fmaf(dz, xh, r0[j]);
+          r1[j] += dz;
+          d[j] = dz * gm[j];
+        }
+        store8(dxn + (size_t)v * 8, d);
+      }
     }
-    store8(dxn + (size_t)v * 8, d);
   }
   chan_put(r0, sp.part, 0, cb, cv, C);
   chan_put(r1, sp.part, 1, cb, cv, C);
@@ -808,14 +896,22 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     k1[j] = -xa[j] * (sp.m1[g] + sp.m2[g] * xb[j]);
     k2[j] = -xa[j] * sp.m2[g] * xa[j];
   }
-#pragma unroll 2
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8], d[8];
-    load8_rw(s_img + (size_t)v * 8, t);
-    load8_rw(dxn + (size_t)v * 8, d);
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
+    Raw8<T> raw[KB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = fmaf(xa[j], d[j], fmaf(k2[j], t[j], k1[j]));
-    store8(dxn + (size_t)v * 8, d);
+    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<false>(dxn + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      const int v = v0 + k * NT;
+      if (v < nvec) {
+        float t[8], d[8];
+        load8_rw(s_img + (size_t)v * 8, t);
+        unpack8(raw[k], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(xa[j], d[j], fmaf(k2[j], t[j], k1[j]));
+        store8(dxn + (size_t)v * 8, d);
+      }
+    }
   }
 }
 
