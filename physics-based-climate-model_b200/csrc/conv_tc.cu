@@ -24,6 +24,25 @@ namespace pcm {
 
 using namespace tc;
 
+// Work item -> (channel group, tile column, tile row, image block) for item = first + k*step WITHOUT per-item
+// divisions: a mixed-radix counter advanced by the (pre-decomposed) step.  The persistent loops of all three roles
+// used three integer divisions per tile; in the thin-layer kernels (epilogue-bound, ~250 instructions per tile and
+// warp) they were 30 % of the epilogue warps' stall samples.
+struct TileWalk {
+  int g, tw, th, tn, dg, dtw, dth, dtn, ng, nw, nh;
+  __device__ __forceinline__ TileWalk(int first, int step, int ngroups, int tiles_w, int tiles_h)
+      : ng(ngroups), nw(tiles_w), nh(tiles_h) {
+    g = first % ng; int r = first / ng; tw = r % nw; r /= nw; th = r % nh; tn = r / nh;
+    dg = step % ng; r = step / ng; dtw = r % nw; r /= nw; dth = r % nh; dtn = r / nh;
+  }
+  __device__ __forceinline__ void next() {
+    g += dg; int c = g >= ng ? 1 : 0; g -= c ? ng : 0;
+    tw += dtw + c; c = tw >= nw ? 1 : 0; tw -= c ? nw : 0;
+    th += dth + c; c = th >= nh ? 1 : 0; th -= c ? nh : 0;
+    tn += dtn + c;
+  }
+};
+
 struct ConvTcParams {
   int N, H, W, Cin, Cout;
   int Wb, Hb, Nb, tiles_w, tiles_h, num_tiles;
@@ -100,12 +119,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int item = blockIdx.x; item < p.num_tiles * p.ngroups && ok; item += gridDim.x) {
-        const int tile = item / p.ngroups, cgrp = item - tile * p.ngroups;
-        const int tw = tile % p.tiles_w;
-        const int th = (tile / p.tiles_w) % p.tiles_h;
-        const int tn = tile / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.Wb, h0 = th * p.Hb, n0 = tn * p.Nb;
+      TileWalk tk(blockIdx.x, gridDim.x, p.ngroups, p.tiles_w, p.tiles_h);
+      for (int item = blockIdx.x; item < p.num_tiles * p.ngroups && ok; item += gridDim.x, tk.next()) {
+        const int cgrp = tk.g;
+        const int w0 = tk.tw * p.Wb, h0 = tk.th * p.Hb, n0 = tk.tn * p.Nb;
         for (int tap = 0; tap < ntaps && ok; ++tap) {
           const int kh = tap / p.ksz, kw = tap % p.ksz;
           for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -183,15 +200,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int mvalid = p.Wb * p.Hb * p.Nb;
     int it = 0;
     bool ok = true;
-    for (int item = blockIdx.x; item < p.num_tiles * p.ngroups && ok; item += gridDim.x, ++it) {
-      const int tile = item / p.ngroups, cgrp = item - tile * p.ngroups;
+    const int wl = row % p.Wb, hl = (row / p.Wb) % p.Hb, nl = row / (p.Wb * p.Hb);
+    TileWalk tk(blockIdx.x, gridDim.x, p.ngroups, p.tiles_w, p.tiles_h);
+    for (int item = blockIdx.x; item < p.num_tiles * p.ngroups && ok; item += gridDim.x, ++it, tk.next()) {
+      const int cgrp = tk.g;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tw = tile % p.tiles_w;
-      const int th = (tile / p.tiles_w) % p.tiles_h;
-      const int tn = tile / (p.tiles_w * p.tiles_h);
-      const int wl = row % p.Wb, hl = (row / p.Wb) % p.Hb, nl = row / (p.Wb * p.Hb);
-      const int w = tw * p.Wb + wl, h = th * p.Hb + hl, n = tn * p.Nb + nl;
+      const int w = tk.tw * p.Wb + wl, h = tk.th * p.Hb + hl, n = tk.tn * p.Nb + nl;
       const bool valid = row < mvalid && w < p.W && h < p.H && n < p.N;
       const long long off = (long long)n * p.dst_ns + ((long long)h * p.W + w) * p.dst_ps;
       ok = mbar_wait(&tfull[acc], acc_phase, err);
@@ -364,10 +379,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tma_load_3d(sB + (size_t)kc * p.b_chunk_bytes, &tmB, bfull, kc * (int)(rb / 2), co0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tw = tile % p.tiles_w;
-        const int th = (tile / p.tiles_w) % p.tiles_h;
-        const int tn = tile / (p.tiles_w * p.tiles_h);
+      TileWalk tk(blockIdx.x, gridDim.x, 1, p.tiles_w, p.tiles_h);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tk.next()) {
+        const int tw = tk.tw, th = tk.th, tn = tk.tn;
         if (!mbar_wait(&empty[stage], phase ^ 1, err)) break;
         mbar_expect_tx(&full[stage], p.a_tx_bytes);
         for (int kc = 0; kc < p.kchunks; ++kc)
@@ -430,13 +444,11 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const bool row_ok = nl < p.Nb && hl < p.Hb && wl < p.Wb;
     int it = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+    TileWalk tk(blockIdx.x, gridDim.x, 1, p.tiles_w, p.tiles_h);
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it, tk.next()) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tw = tile % p.tiles_w;
-      const int th = (tile / p.tiles_w) % p.tiles_h;
-      const int tn = tile / (p.tiles_w * p.tiles_h);
-      const int w = tw * p.Wb + wl, h = th * p.Hb + hl, n = tn * p.Nb + nl;
+      const int w = tk.tw * p.Wb + wl, h = tk.th * p.Hb + hl, n = tk.tn * p.Nb + nl;
       const bool valid = row_ok && w < p.W && h < p.H && n < p.N;
       const long long off = (long long)n * p.dst_ns + ((long long)h * p.W + w) * p.dst_ps + co0;
       ok = mbar_wait(&tfull[acc], acc_phase, err);
