@@ -42,6 +42,17 @@ bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long R,
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
     }
+  }
+  // lanes of a warp that own the same channel block (cv < 32: lane stride cv) are combined by a fixed shuffle tree
+  // first, so that only cv lanes per warp touch the shared accumulators (shared-memory double atomics are CAS loops)
+  for (int off = cv; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+    }
+  }
+  if (rl < rpb && (cv >= 32 || (int)(threadIdx.x & 31) < cv)) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&shd[(cb * 8 + j) * 2], (double)s[j]);
@@ -76,14 +87,14 @@ __device__ __forceinline__ void bn_coeffs(const double* sums, const float* gamma
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_fwd_kernel(const T* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ y, long long R, int C,
+                    const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ y, long long R, double invRd, int C,
                     float eps, int relu) {
   PCM_PDL_ENTRY();
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
   if (rl >= rpb) return;
   float mean[8], rstd[8], a[8], b[8];
-  bn_coeffs(sums, gamma, beta, cb * 8, 1.0 / (double)R, eps, mean, rstd, a, b);
+  bn_coeffs(sums, gamma, beta, cb * 8, invRd, eps, mean, rstd, a, b);
   for (long long r = (long long)blockIdx.x * rpb + rl; r < R; r += (long long)gridDim.x * rpb) {
     float v[8];
     load8(x + r * C + cb * 8, v);
@@ -107,21 +118,24 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const double* __restrict__ sums, co
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
-                     const double* __restrict__ sums, float* __restrict__ dsum, long long R, int C, float eps) {
+                     const double* __restrict__ sums, float* __restrict__ dsum, long long R, double invRd, int C, float eps) {
   PCM_PDL_ENTRY();
   extern __shared__ float sh[];
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
   for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) sh[i] = 0.f;
   __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (rl < rpb) {
-    float mean[8], rstd[8], s[8], q[8];
+    float mean[8], rstd[8];
     const float invR = 1.f / (float)R;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float m, var;
-      bn_mean_var(sums, cb * 8 + j, 1.0 / (double)R, m, var);
-      mean[j] = m; rstd[j] = rsqrtf(var + eps); s[j] = q[j] = 0.f;
+      bn_mean_var(sums, cb * 8 + j, invRd, m, var);
+      mean[j] = m; rstd[j] = rsqrtf(var + eps);
     }
     for (long long r = (long long)blockIdx.x * rpb + rl; r < R; r += (long long)gridDim.x * rpb) {
       float g[8], v[8];
@@ -136,6 +150,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T*
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += g[j]; q[j] = fmaf(g[j], (v[j] - mean[j]) * rstd[j], q[j]); }
     }
+  }
+  for (int off = cv; off < 32; off <<= 1) {          // same-channel lanes of the warp first (see bn_stats_kernel)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+    }
+  }
+  if (rl < rpb && (cv >= 32 || (int)(threadIdx.x & 31) < cv)) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&sh[(cb * 8 + j) * 2], s[j]);
@@ -152,7 +175,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
                     const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ dsum,
                     T* __restrict__ dx, T* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                    long long R, int C, float eps) {
+                    long long R, double invRd, int C, float eps) {
   PCM_PDL_ENTRY();
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -169,7 +192,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
   for (int j = 0; j < 8; ++j) {
     const int c = cb * 8 + j;
     float m, var;
-    bn_mean_var(sums, c, 1.0 / (double)R, m, var);
+    bn_mean_var(sums, c, invRd, m, var);
     mean[j] = m; rstd[j] = rsqrtf(var + eps);
     a[j] = gamma[c] * rstd[j];
     m1[j] = dsum[2 * c] * invR; m2[j] = dsum[2 * c + 1] * invR;
@@ -192,13 +215,13 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
 }
 
 __global__ void bn_update_running_kernel(const double* __restrict__ sums, float* __restrict__ rm, float* __restrict__ rv,
-                                         long long* __restrict__ nbt, long long R, int C, float momentum) {
+                                         long long* __restrict__ nbt, long long R, double invRd, int C, float momentum) {
   PCM_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt != nullptr) *nbt += 1;
   if (c >= C) return;
   float m, var;
-  bn_mean_var(sums, c, 1.0 / (double)R, m, var);
+  bn_mean_var(sums, c, invRd, m, var);
   const float unb = R > 1 ? var * (float)R / (float)(R - 1) : var;
   rm[c] = (1.f - momentum) * rm[c] + momentum * m;
   rv[c] = (1.f - momentum) * rv[c] + momentum * unb;
@@ -324,14 +347,14 @@ extern "C" int pcm_bn_apply_fwd(const void* x, const double* sums, const float* 
   if (R == 0) return PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_apply_fwd_kernel<T>, bn_grid(R, C), kBnThreads, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(x), sums, gamma, beta, static_cast<const T*>(res),
-                                   static_cast<T*>(y), R, C, eps, relu)));
+                                   static_cast<T*>(y), R, 1.0 / (double)R, C, eps, relu)));
   return check_launch("bn_apply_fwd");
 }
 
 extern "C" int pcm_bn_update_running(const double* sums, float* running_mean, float* running_var,
                                      long long* num_batches_tracked, long long R, int C, float momentum, pcm_stream_t s) {
   pcm::launch(bn_update_running_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)s, sums, running_mean, running_var,
-                                                                          num_batches_tracked, R, C, momentum);
+                                                                          num_batches_tracked, R, 1.0 / (double)R, C, momentum);
   return check_launch("bn_update_running");
 }
 
@@ -341,7 +364,7 @@ extern "C" int pcm_bn_bwd_reduce(const void* dy, const void* y, const void* x, c
   if (R == 0) return PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_bwd_reduce_kernel<T>, bn_grid(R, C), kBnThreads, 2 * C * sizeof(float), (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<const T*>(x), sums, dsum,
-                                   R, C, eps)));
+                                   R, 1.0 / (double)R, C, eps)));
   return check_launch("bn_bwd_reduce");
 }
 
@@ -352,7 +375,7 @@ extern "C" int pcm_bn_bwd_apply(const void* dy, const void* y, const void* x, co
   if (R == 0) return PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_bwd_apply_kernel<T>, bn_grid(R, C), kBnThreads, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<const T*>(x), sums, gamma,
-                                   dsum, static_cast<T*>(dx), static_cast<T*>(dres), dgamma, dbeta, R, C, eps)));
+                                   dsum, static_cast<T*>(dx), static_cast<T*>(dres), dgamma, dbeta, R, 1.0 / (double)R, C, eps)));
   return check_launch("bn_bwd_apply");
 }
 
