@@ -268,6 +268,46 @@ def test_step_prefetch_matches_step(G):
         assert abs(a - b) / abs(a) < 1e-4, losses
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_side_stream_matches_single_stream(G, dtype, monkeypatch):
+    """The weight-gradient kernels run on a second stream inside the captured step (fork / join around every ConvBlock,
+    ConvTranspose and ConvLSTM backward): losses and final parameters must equal the single-stream step's (same
+    kernels, same inputs; only fp32 atomics may reorder)."""
+    import pcm_b200
+    from oracle import model_oracle as O
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    from pcm_b200.trainer import TrainStep
+    B, T, H, W, base = 4, 3, 48, 72, 16            # full-size grid: the per-image tails and the tensor-core kernels
+    sd = O.synth_state_dict(O.attunet_spec(7, 2, base), 91)
+    batches = [O.synth_attunet_batch(B, T, H, W, 92 + i)[:2] for i in range(3)]
+    pcm_b200.set_compute_dtype(dtype)
+    try:
+        runs = []
+        for side in ("0", "1"):
+            monkeypatch.setenv("PCM_SIDE_STREAM", side)
+            model = AttUNetConvLSTM(7, 2, base, seq_len=T)
+            model.load_state_dict(sd)
+            model = model.cuda()
+            step = TrainStep(model, (B, T, 7, H, W), (B, 2, H, W), lr=1e-3)
+            assert (step.side is not None) == (side == "1")
+            step.load_batch(*batches[0])
+            step.warmup_and_capture(warmup=2)
+            with torch.no_grad():                         # undo the warm-up updates
+                for k, p in model.named_parameters():
+                    p.copy_(sd[k].cuda())
+            step.reset_optimizer_state()
+            losses = [float(step.step(*batches[i % 3]).item()) for i in range(6)]
+            flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()]).cpu()
+            runs.append((losses, flat))
+    finally:
+        pcm_b200.set_compute_dtype(torch.bfloat16)
+    (l0, p0), (l1, p1) = runs
+    tol = 1e-4 if dtype == torch.float32 else 5e-3
+    for a, b in zip(l0, l1):
+        assert abs(a - b) / abs(a) < tol, (l0, l1)
+    assert float((p0 - p1).norm() / p0.norm()) < tol
+
+
 def test_forward_windows_matches_stacked_windows(G):
     """Device-resident window gather (SequenceDataset semantics, zero left-pad) == forward on the explicitly stacked
     windows; includes target indices smaller than seq_len - 1."""
