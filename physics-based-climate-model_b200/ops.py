@@ -667,16 +667,20 @@ class PoolSkipFn(torch.autograd.Function):
     each sample.  Backward is ONE kernel: max-pool routing (first max wins, like torch) + dskip/T."""
 
     @staticmethod
-    def forward(ctx, s, T):
-        """s: t-major frames (image t*B + b)."""
+    def forward(ctx, s, T, up_channels=0):
+        """s: t-major frames (image t*B + b).  up_channels > 0: the skip is written straight into the last C channels
+        of a (B, H, W, up_channels + C) buffer — the concat buffer of the decoder stage that will consume it (UpCatFn
+        recognises the view and fills the first up_channels channels in place: no copy of the skip)."""
         s = s.contiguous()
         N, H, W, C = s.shape
         B = N // T
         d = _DT[s.dtype]
         pooled = torch.empty((N, H // 2, W // 2, C), device=s.device, dtype=s.dtype)
         _call("pcm_maxpool2_fwd", s.data_ptr(), pooled.data_ptr(), N, H, W, C, d, _s())
-        skip = torch.empty((B, H, W, C), device=s.device, dtype=s.dtype)
-        _call("pcm_time_mean", s.data_ptr(), skip.data_ptr(), H * W * C, C, B, T, H * W, C, 1, d, _s())
+        Cc = up_channels + C
+        cat = torch.empty((B, H, W, Cc), device=s.device, dtype=s.dtype)
+        skip = cat[..., up_channels:] if up_channels > 0 else cat
+        _call("pcm_time_mean", s.data_ptr(), skip.data_ptr(), H * W * Cc, Cc, B, T, H * W, C, 1, d, _s())
         ctx.save_for_backward(s)
         ctx.T = T
         return pooled, skip
@@ -694,7 +698,7 @@ class PoolSkipFn(torch.autograd.Function):
             ns, ps = dskip.stride(0), dskip.stride(2)
         _call("pcm_maxpool2_bwd_skip", s.data_ptr(), _p(dp), _p(dskip), ns, ps, ds.data_ptr(), N, H, W, C, ctx.T, 1,
               _DT[s.dtype], _s())
-        return ds, None
+        return ds, None, None
 
 
 class MaxPoolFn(torch.autograd.Function):
@@ -733,10 +737,16 @@ class UpCatFn(torch.autograd.Function):
         Co, Cs = wt.shape[1], skip.shape[-1]
         assert wt.shape[0] == Ci and Co % 8 == 0 and Cs % 8 == 0
         H, W, Cc, dt = 2 * h, 2 * w, Co + Cs, x.dtype
-        cat = torch.empty((B, H, W, Cc), device=x.device, dtype=dt)
+        base = skip._base
+        in_place = (base is not None and tuple(base.shape) == (B, H, W, Cc) and base.is_contiguous() and base.dtype == dt
+                    and skip.data_ptr() == base.data_ptr() + Co * base.element_size()
+                    and tuple(skip.stride()) == (H * W * Cc, W * Cc, Cc, 1))
+        # PoolSkipFn(up_channels=Co) already put the skip into the last Cs channels of the concat buffer
+        cat = base if in_place else torch.empty((B, H, W, Cc), device=x.device, dtype=dt)
         # transposed conv = one GEMM [pixels x Ci] x [Ci x 4*Co] whose epilogue pixel-shuffles into the concat buffer
         convT2x2_fwd(x, wt, bt, B, h, w, Ci, Co, cat, H * W * Cc, Cc)
-        cat[..., Co:].copy_(skip)          # strided D2D copy (plumbing, no arithmetic)
+        if not in_place:
+            cat[..., Co:].copy_(skip)      # strided D2D copy (plumbing, no arithmetic)
         ctx.save_for_backward(x, wt, bt)
         ctx.dims = (B, h, w, Ci, Co, Cs)
         return cat

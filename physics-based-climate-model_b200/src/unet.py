@@ -128,11 +128,11 @@ class UNet(nn.Module):
     def forward(self, x):
         a = ops.StageIn.apply(x, compute_dtype())
         s1 = self.enc1.forward_nhwc(a)
-        p1, k1 = ops.PoolSkipFn.apply(s1, 1)
+        p1, k1 = ops.PoolSkipFn.apply(s1, 1, self.up1.up.out_channels)
         s2 = self.enc2.conv.forward_nhwc(p1)
-        p2, k2 = ops.PoolSkipFn.apply(s2, 1)
+        p2, k2 = ops.PoolSkipFn.apply(s2, 1, self.up2.up.out_channels)
         s3 = self.enc3.conv.forward_nhwc(p2)
-        p3, k3 = ops.PoolSkipFn.apply(s3, 1)
+        p3, k3 = ops.PoolSkipFn.apply(s3, 1, self.up3.up.out_channels)
         s4 = self.enc4.conv.forward_nhwc(p3)
         y = self.bott.forward_nhwc(s4)
         y = self.up3.forward_nhwc(y, k3)

@@ -69,11 +69,11 @@ class AttUNetConvLSTM(nn.Module):
         """x: NHWC frames (T*B, H, W, 16), t-major: image n = t*B + b (e.g. from
         ops.season_embed_stage(..., T=T), which synthesises the sin/cos month channels on the fly)."""
         s1 = self.enc1.forward_nhwc(x)
-        p1, k1 = ops.PoolSkipFn.apply(s1, T)
+        p1, k1 = ops.PoolSkipFn.apply(s1, T, self.up1.up.out_channels)
         s2 = self.enc2.conv.forward_nhwc(p1)
-        p2, k2 = ops.PoolSkipFn.apply(s2, T)
+        p2, k2 = ops.PoolSkipFn.apply(s2, T, self.up2.up.out_channels)
         s3 = self.enc3.conv.forward_nhwc(p2)
-        p3, k3 = ops.PoolSkipFn.apply(s3, T)
+        p3, k3 = ops.PoolSkipFn.apply(s3, T, self.up3.up.out_channels)
         s4 = self.enc4.conv.forward_nhwc(p3)
         s4 = ops.grad_ready_hook(s4, "encoder_boundary")     # data-parallel trainer: first gradient bucket is complete here
         bott = self.convlstm.forward_nhwc(s4, T, B, st_t=B, st_b=1, last_only=True)
