@@ -680,7 +680,8 @@ class PoolSkipFn(torch.autograd.Function):
         Cc = up_channels + C
         cat = torch.empty((B, H, W, Cc), device=s.device, dtype=s.dtype)
         skip = cat[..., up_channels:] if up_channels > 0 else cat
-        _call("pcm_time_mean", s.data_ptr(), skip.data_ptr(), H * W * Cc, Cc, B, T, H * W, C, 1, d, _s())
+        with side_stream(s, cat):          # nothing needs the skip before the decoder (UpCatFn joins)
+            _call("pcm_time_mean", s.data_ptr(), skip.data_ptr(), H * W * Cc, Cc, B, T, H * W, C, 1, d, _s())
         ctx.save_for_backward(s)
         ctx.T = T
         return pooled, skip
@@ -737,6 +738,7 @@ class UpCatFn(torch.autograd.Function):
         Co, Cs = wt.shape[1], skip.shape[-1]
         assert wt.shape[0] == Ci and Co % 8 == 0 and Cs % 8 == 0
         H, W, Cc, dt = 2 * h, 2 * w, Co + Cs, x.dtype
+        join_side()                        # the skip may have been produced on the side stream
         base = skip._base
         in_place = (base is not None and tuple(base.shape) == (B, H, W, Cc) and base.is_contiguous() and base.dtype == dt
                     and skip.data_ptr() == base.data_ptr() + Co * base.element_size()
