@@ -309,6 +309,7 @@ def run_ours(args):
                                    "same per-GPU batch on every rank = configs[3])",
                        "per_gpu_batch": B, "global_batch": world * B, "seq_len": T, "parallelism": f"dp{world}",
                        "cuda_graph": step.graph is not None,
+                       "streams": "2 (weight gradients / skips forked inside the graph)" if step.side is not None else "1",
                        "l2": f"inputs rotate over {N_ROTATE} resident batches ({N_ROTATE * B * T * C * H * W * 4 / 1e6:.0f} MB) "
                              "> 126 MB L2; per-step activation traffic is several hundred MB"},
             "clocks": clocks,
