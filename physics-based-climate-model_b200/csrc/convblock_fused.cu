@@ -7,8 +7,9 @@
 //   tail 1  (after conv1):  GroupNorm(8) statistics -> normalise -> SiLU                      1 read, 1 write
 //   tail 2  (after conv2):  GroupNorm(8) -> SiLU -> SE squeeze/excite -> channel mean/max map
 //                           -> 7x7 gate conv -> sigmoid -> out = a*se*gate                    1 read, 1 write
-//   and the two backward tails (dout -> dy2, da1 -> dy1), which recompute a2 / gate from the saved
-//   pre-normalisation tensor instead of reading saved activations.
+//                           (+ 13 bytes per pixel saved for the backward: mean / max maps, gate, tie count)
+//   and the two backward tails (dout -> dy2, da1 -> dy1): the gate's pre-activation gradient comes from dout*out
+//   and the saved maps, the activation a2 is recomputed once from the saved pre-normalisation tensor.
 //
 // The multi-kernel path in convblock.cu (grid-wide passes, 6 forward + 8 backward launches per block) remains for
 // images that do not fit (config 5, fp32 at full size) — see pcm_convblock_fused_supported.
@@ -761,7 +762,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   }
   image_copy_wait(bar, (uint32_t)((size_t)P * C * sizeof(T)));      // x is in shared memory from here on
 
-  // ---- pass B (sigmoid #1): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
+  // ---- pass B (first of the two activation evaluations): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
   // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu_raw + rounding), so the
   // comparison against the saved maximum selects the same channels.
   {
@@ -839,7 +840,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     }
   }
   __syncthreads();
-  // ---- GroupNorm + SiLU backward, pass 1 (sigmoid #3): dxhat -> scratch, reductions
+  // ---- GroupNorm + SiLU backward, pass 1 (second activation evaluation): dxhat -> scratch, reductions
   float dp[8], r0[8], r1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { dp[j] = sp.dpool[cb * 8 + j]; r0[j] = r1[j] = 0.f; }
