@@ -27,11 +27,14 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
 bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long R, int C) {
   PCM_PDL_ENTRY();
-  extern __shared__ double shd[];                // [C][2]
+  extern __shared__ double shd[];                // cv <= 32: [warps][C][2] per-warp slots; else [C][2] accumulators
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
-  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) shd[i] = 0.0;
-  __syncthreads();
+  constexpr int kWarps = kBnThreads / 32;
+  if (cv > 32) {
+    for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) shd[i] = 0.0;
+    __syncthreads();
+  }
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
@@ -52,15 +55,30 @@ bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long R,
       q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
     }
   }
-  if (rl < rpb && (cv >= 32 || (int)(threadIdx.x & 31) < cv)) {
+  if (cv <= 32) {
+    // every warp holds all cv channel blocks: lanes < cv park the warp's totals in the warp's own slot, then 2*C
+    // threads add the slots in a fixed order (no shared-memory atomics at all: they are CAS loops for double)
+    if ((int)(threadIdx.x & 31) < cv) {
+      double* slot = shd + (size_t)(threadIdx.x >> 5) * 2 * C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { slot[(cb * 8 + j) * 2] = (double)s[j]; slot[(cb * 8 + j) * 2 + 1] = (double)q[j]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += shd[(size_t)w * 2 * C + i];
+      atomicAdd(sums + i, t);
+    }
+  } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&shd[(cb * 8 + j) * 2], (double)s[j]);
       atomicAdd(&shd[(cb * 8 + j) * 2 + 1], (double)q[j]);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(sums + i, shd[i]);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(sums + i, shd[i]);
 }
 
 // (mean, biased variance) of channel c from the double sums
@@ -120,11 +138,14 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
                      const double* __restrict__ sums, float* __restrict__ dsum, long long R, double invRd, int C, float eps) {
   PCM_PDL_ENTRY();
-  extern __shared__ float sh[];
+  extern __shared__ float sh[];                  // cv <= 32: [warps][C][2] per-warp slots; else [C][2] accumulators
   const int cv = C / 8, rpb = kBnThreads / cv;
   const int cb = threadIdx.x % cv, rl = threadIdx.x / cv;
-  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) sh[i] = 0.f;
-  __syncthreads();
+  constexpr int kWarps = kBnThreads / 32;
+  if (cv > 32) {
+    for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) sh[i] = 0.f;
+    __syncthreads();
+  }
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
@@ -158,15 +179,28 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T*
       q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
     }
   }
-  if (rl < rpb && (cv >= 32 || (int)(threadIdx.x & 31) < cv)) {
+  if (cv <= 32) {
+    if ((int)(threadIdx.x & 31) < cv) {
+      float* slot = sh + (size_t)(threadIdx.x >> 5) * 2 * C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { slot[(cb * 8 + j) * 2] = s[j]; slot[(cb * 8 + j) * 2 + 1] = q[j]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += sh[(size_t)w * 2 * C + i];
+      atomicAdd(dsum + i, t);
+    }
+  } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&sh[(cb * 8 + j) * 2], s[j]);
       atomicAdd(&sh[(cb * 8 + j) * 2 + 1], q[j]);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(dsum + i, sh[i]);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) atomicAdd(dsum + i, sh[i]);
 }
 
 // dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dres = dz (nullable); block 0 adds dgamma/dbeta
@@ -336,7 +370,7 @@ using namespace pcm;
 extern "C" int pcm_bn_stats(const void* x, double* sums, long long R, int C, int dtype, pcm_stream_t s) {
   BN_CHECK_C("bn_stats", C);
   if (R == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_stats_kernel<T>, bn_grid(R, C), kBnThreads, 2 * C * sizeof(double), (cudaStream_t)s,
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_stats_kernel<T>, bn_grid(R, C), kBnThreads, (C <= 256 ? kBnThreads / 32 : 1) * 2 * C * sizeof(double), (cudaStream_t)s,
                                    static_cast<const T*>(x), sums, R, C)));
   return check_launch("bn_stats");
 }
@@ -362,7 +396,7 @@ extern "C" int pcm_bn_bwd_reduce(const void* dy, const void* y, const void* x, c
                                  int C, float eps, int dtype, pcm_stream_t s) {
   BN_CHECK_C("bn_bwd_reduce", C);
   if (R == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_bwd_reduce_kernel<T>, bn_grid(R, C), kBnThreads, 2 * C * sizeof(float), (cudaStream_t)s, 
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(bn_bwd_reduce_kernel<T>, bn_grid(R, C), kBnThreads, (C <= 256 ? kBnThreads / 32 : 1) * 2 * C * sizeof(float), (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<const T*>(x), sums, dsum,
                                    R, 1.0 / (double)R, C, eps)));
   return check_launch("bn_bwd_reduce");

@@ -157,6 +157,7 @@ class PackPlan:
 
 _PLAN: Optional[PackPlan] = None
 _SIDE: Optional[torch.cuda.Stream] = None      # trainer-provided stream for weight-gradient kernels
+_SIDE_FORKED = False                            # work has been issued on _SIDE since the last join
 
 
 class side_stream:
@@ -170,7 +171,9 @@ class side_stream:
         self.ctx = None
 
     def __enter__(self):
+        global _SIDE_FORKED
         if _SIDE is not None:
+            _SIDE_FORKED = True
             _SIDE.wait_stream(torch.cuda.current_stream())
             for t in self.tensors:
                 if t is not None:
@@ -215,9 +218,13 @@ def side_active() -> bool:
 
 
 def join_side():
-    """Make the current stream wait for everything issued on the side stream."""
-    if _SIDE is not None:
+    """Make the current stream wait for everything issued on the side stream.  Nothing to do when the side stream
+    has not been used since the last join — and under graph capture it MUST be skipped then: waiting on a stream that
+    is not part of the capture invalidates it (models without side-stream work, e.g. SimpleCNN)."""
+    global _SIDE_FORKED
+    if _SIDE is not None and _SIDE_FORKED:
         torch.cuda.current_stream().wait_stream(_SIDE)
+        _SIDE_FORKED = False
 
 
 class use_pack_plan:

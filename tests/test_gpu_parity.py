@@ -308,6 +308,34 @@ def test_side_stream_matches_single_stream(G, dtype, monkeypatch):
     assert float((p0 - p1).norm() / p0.norm()) < tol
 
 
+@pytest.mark.parametrize("kind", ["simplecnn", "cnn_transformer", "unet"])
+def test_trainstep_captures_every_model_family(G, kind):
+    """TrainStep (CUDA graph, second stream enabled by default) on the models that issue little or no side-stream work:
+    the capture must stay valid (joining a stream that was never forked would invalidate it) and the loss must fall."""
+    import pcm_b200
+    from pcm_b200.trainer import TrainStep
+    torch.manual_seed(0)
+    if kind == "simplecnn":
+        from pcm_b200.src.models import SimpleCNN
+        model, H, W = SimpleCNN(5, 2, kernel_size=3, init_dim=16, depth=2, dropout_rate=0.0), 16, 24
+    elif kind == "cnn_transformer":
+        from pcm_b200.src.cnn_transformer import CNNTransformer
+        model, H, W = CNNTransformer(5, 2, 32, 2, 4, 64, dropout=0.0), 48, 72
+    else:
+        from pcm_b200.src.unet import UNet
+        model, H, W = UNet(5, 2, 16), 16, 24
+    model = model.cuda()
+    B = 4
+    x, y = torch.randn(B, 5, H, W, device="cuda"), torch.randn(B, 2, H, W, device="cuda")
+    step = TrainStep(model, (B, 5, H, W), (B, 2, H, W), lr=2e-3)
+    assert step.side is not None
+    step.load_batch(x, y)
+    step.warmup_and_capture(warmup=2)
+    assert step.graph is not None
+    losses = [float(step.step(x, y).item()) for _ in range(8)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+
+
 def test_forward_windows_matches_stacked_windows(G):
     """Device-resident window gather (SequenceDataset semantics, zero left-pad) == forward on the explicitly stacked
     windows; includes target indices smaller than seq_len - 1."""
