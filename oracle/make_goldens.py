@@ -86,6 +86,29 @@ def main():
         d = run_module(mod, sd, x, y)
         np.savez(os.path.join(GOLD, tag + ".npz"), cfg=json.dumps(cfg), **d)
 
+    # ---- the BENCHMARK shape (B=64): output / gradient samples, (i) synthetic weights, (ii) the reference's own default
+    #      init under torch.manual_seed(42) on bench.py's first batch (seed 42) — bench.py checks its first loss against it
+    torch.set_num_threads(os.cpu_count() or 1)
+    for tag, cfg in [("attunet_cfg3_b64", dict(in_ch=7, out_ch=2, base=16, B=64, T=6, H=48, W=72, seed=42, init="synth")),
+                     ("attunet_cfg3_b64_default_init", dict(in_ch=7, out_ch=2, base=16, B=64, T=6, H=48, W=72, seed=42,
+                                                            init="default", batch_seed=42))]:
+        if cfg["init"] == "synth":
+            mod = R.unet_convlstm_attention.AttUNetConvLSTM(cfg["in_ch"], cfg["out_ch"], cfg["base"], seq_len=cfg["T"])
+            sd = O.synth_state_dict(O.attunet_spec(cfg["in_ch"], cfg["out_ch"], cfg["base"]), cfg["seed"])
+            x, y, _ = O.synth_attunet_batch(cfg["B"], cfg["T"], cfg["H"], cfg["W"], cfg["seed"] + 1, cfg["in_ch"], cfg["out_ch"])
+        else:
+            torch.manual_seed(cfg["seed"])                   # configs/main_config.yaml:11
+            mod = R.unet_convlstm_attention.AttUNetConvLSTM(cfg["in_ch"], cfg["out_ch"], cfg["base"], seq_len=cfg["T"])
+            sd = {k: v.clone() for k, v in mod.state_dict().items()}
+            x, y, _ = O.synth_attunet_batch(cfg["B"], cfg["T"], cfg["H"], cfg["W"], cfg["batch_seed"], cfg["in_ch"], cfg["out_ch"])
+        d = run_module(mod, sd, x, y)
+        out = d.pop("out")
+        flat = out.reshape(-1)
+        d["out_sample"] = flat[:: max(1, flat.size // (4 * SAMPLE))].copy()
+        d["out_norm"] = np.array([np.linalg.norm(flat.astype(np.float64)), flat.astype(np.float64).sum()], np.float64)
+        np.savez(os.path.join(GOLD, tag + ".npz"), cfg=json.dumps(cfg), **d)
+    torch.set_num_threads(1)
+
     # ---- UNet ------------------------------------------------------------------------------
     cfg = dict(in_ch=5, out_ch=2, base=8, B=2, H=16, W=24, seed=131)
     sd = O.synth_state_dict(O.unet_spec(cfg["in_ch"], cfg["out_ch"], cfg["base"]), cfg["seed"])
@@ -141,6 +164,20 @@ def main():
                                          "pr": [0.9742019753, 0.3126719193, 0.7152702066],
                                          "xarray_form_score": 1.1422441747, "kaggle_score": 1.1422444331},
                    "attunet_default_init_seed42": init}, f, indent=1)
+    # ---- Kaggle round trip: rows built by the reference's loop (restated in oracle/kaggle_oracle.py), scored by the
+    #      UNMODIFIED _climate_kaggle_metric.score ------------------------------------------------------------------
+    from oracle import kaggle_oracle as KO
+    pred, true, lat, lon, names = KO.synth_submission(T=4, seed=7)
+    ids, pv = KO.convert_predictions_to_kaggle_format(pred, np.arange(4), lat, lon, names)
+    _, tv = KO.convert_predictions_to_kaggle_format(true, np.arange(4), lat, lon, names)
+    sol = pd.DataFrame({"ID": ids, "Prediction": tv})
+    sub = pd.DataFrame({"ID": ids, "Prediction": pv})
+    rt = float(R.score(sol, sub, "ID"))
+    perm = np.random.RandomState(3).permutation(len(ids))                  # shuffled submission: merge must realign
+    rt_shuffled = float(R.score(sol, sub.iloc[perm].reset_index(drop=True), "ID"))
+    with open(os.path.join(GOLD, "kaggle_roundtrip.json"), "w") as f:
+        json.dump({"T": 4, "seed": 7, "reference_score": rt, "reference_score_shuffled_submission": rt_shuffled,
+                   "first_ids": ids[:3], "last_id": ids[-1], "n_rows": len(ids)}, f, indent=1)
     print("goldens written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(f"  {fn:32s} {os.path.getsize(os.path.join(GOLD, fn)) / 1024:.1f} KiB")

@@ -3,7 +3,8 @@
 numpy float64 restatement of the reference's metric arithmetic.  xarray is absent in this
 image, so ``calculate_weighted_metric`` (src/utils_final.py:282-302) is restated from the
 definition of ``DataArray.weighted(w).mean(dims)``: sum(w*x)/sum(w) with ``w`` broadcast over
-the reduced dims (no NaNs in synthetic data).
+the reduced dims; NaNs are skipped the way xarray skips them (``skipna=True`` for float reductions, and
+``weighted().mean()`` = sum(w*x over non-NaN x) / sum(w over non-NaN x)) — without NaNs this is the plain definition.
 
 Pinning: ``known_answer_fixture()`` regenerates the recipe of _test_kaggle_metric.py:33-78 and
 the values are pinned (a) against SURVEY.md Appendix G / tests/golden/metric_appendix_g.json and
@@ -32,20 +33,25 @@ def get_lat_weights(lat: np.ndarray) -> np.ndarray:
 
 
 def weighted_mean(x: np.ndarray, w_lat: np.ndarray) -> float:
-    """src/utils_final.py:296 — x (..., y, x) averaged over ALL its dims with weights w[y]."""
+    """src/utils_final.py:296 — x (..., y, x) averaged over ALL its dims with weights w[y]; NaN terms drop out of
+    numerator and denominator (xarray Weighted._weighted_mean: sum_of_weights uses da.notnull())."""
     x = np.asarray(x, dtype=np.float64)
     w = np.broadcast_to(np.asarray(w_lat, np.float64)[:, None], x.shape)
-    return float((w * x).sum() / w.sum())
+    ok = ~np.isnan(x)
+    return float(np.where(ok, w * np.where(ok, x, 0.0), 0.0).sum() / np.where(ok, w, 0.0).sum())
 
 
 def metric_triplet(pred: np.ndarray, true: np.ndarray, w_lat: np.ndarray):
     """main_final.py:616-631 for one variable; pred/true (T, Y, X).
-    Returns (monthly_rmse, time_mean_rmse, time_std_mae); std is ddof=0."""
+    Returns (monthly_rmse, time_mean_rmse, time_std_mae); std is ddof=0; .mean/.std over time skip NaNs."""
     pred = np.asarray(pred, np.float64)
     true = np.asarray(true, np.float64)
     monthly = np.sqrt(weighted_mean((pred - true) ** 2, w_lat))
-    tmean = np.sqrt(weighted_mean((pred.mean(0) - true.mean(0)) ** 2, w_lat))
-    tstd = weighted_mean(np.abs(pred.std(0) - true.std(0)), w_lat)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)        # all-NaN pixels -> NaN, skipped by weighted_mean
+        tmean = np.sqrt(weighted_mean((np.nanmean(pred, 0) - np.nanmean(true, 0)) ** 2, w_lat))
+        tstd = weighted_mean(np.abs(np.nanstd(pred, 0) - np.nanstd(true, 0)), w_lat)
     return monthly, tmean, tstd
 
 

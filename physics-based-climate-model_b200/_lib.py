@@ -88,6 +88,10 @@ class _Lib:
             raise RuntimeError(f"{name} failed (status {rc}): {self.last_error()}")
         self.launches += 1
 
+    def host_call(self, name: str, *args) -> int:
+        """Host-only entry points (Kaggle I/O): no kernel launch, not counted; returns the status code."""
+        return int(self._fn[name](*args))
+
 
 _LIB = None
 

@@ -2,94 +2,90 @@
 // monthly RMSE, time-mean RMSE and time-std MAE per variable, in one pass over pred/truth.
 // Pass 1 (HBM-bound, reads 2*T*V*Y*X*4 bytes once): per pixel time sums of p, p^2, t, t^2, (p-t)^2
 // accumulated in fp64 (tas ~ 273 K: fp32 sums of squares would cancel catastrophically in the
-// variance).  Pass 2: per-pixel terms -> latitude-weighted warp-shuffle reduction.
+// variance) plus the three counts of non-NaN terms.  Pass 2: per-pixel terms -> latitude-weighted warp-shuffle
+// reduction.
+// NaN handling = xarray's (skipna=True reductions and DataArray.weighted().mean(), src/utils_final.py:296): a NaN
+// prediction/target drops out of that pixel's time mean / std; (p-t)^2 drops out where either is NaN; the weighted
+// means divide by the weights of the terms that remain.  Without NaNs this is the plain definition.
 #include "common.cuh"
 
 namespace pcm {
 
-// grid: (ceil(V*Y*X / 256), time_chunks)
-__global__ void __launch_bounds__(256)
-metric_partial_kernel(const float* __restrict__ pred, const float* __restrict__ truth, double* __restrict__ partial,
-                      int T, int VYX) {
-  PCM_PDL_ENTRY();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= VYX) return;
-  const int per = (T + gridDim.y - 1) / gridDim.y;
-  const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
-  double sp = 0, spp = 0, st = 0, stt = 0, sd = 0;
-  for (int t = t0; t < t1; ++t) {
-    const double p = (double)__ldg(pred + (long long)t * VYX + pix);
-    const double q = (double)__ldg(truth + (long long)t * VYX + pix);
-    const double d = p - q;
-    sp += p; st += q;
-    spp = fma(p, p, spp);
-    stt = fma(q, q, stt);
-    sd = fma(d, d, sd);
-  }
-  double* o = partial + (long long)pix * 5;
-  atomicAdd(o + 0, sp); atomicAdd(o + 1, spp); atomicAdd(o + 2, st); atomicAdd(o + 3, stt); atomicAdd(o + 4, sd);
-}
+constexpr int kMS = 8;       // doubles per pixel: sum p, p^2, t, t^2, (p-t)^2, count p, count t, count (p-t)
 
-// Validation epilogue (main_final.py:563-574 + src/utils_final.py:130-206): predictions and targets arrive NORMALISED;
-// the inverse transform of Normalizer.inverse_transform_output is applied on the fly in fp64, so the de-normalised
-// tensors are never materialised.  tr[v] = (kind, a, b, c): x_phys = g(x*a + b) with
+// Validation epilogue (main_final.py:563-574 + src/utils_final.py:130-206): predictions and targets may arrive
+// NORMALISED; the inverse transform of Normalizer.inverse_transform_output is applied on the fly in fp64, so the
+// de-normalised tensors are never materialised.  tr[v] = (kind, a, b, c): x_phys = g(x*a + b) with
 //   kind 0 zscore / minimax: identity   1 log1p: expm1   2 sqrt: square   3 pow: (.)^(1/c)
 __device__ __forceinline__ double denorm(double x, int kind, double a, double b, double c) {
   const double u = fma(x, a, b);
   return kind == 0 ? u : kind == 1 ? expm1(u) : kind == 2 ? u * u : pow(u, 1.0 / c);
 }
 
+// grid: (ceil(V*Y*X / 256), time_chunks)
+template <typename TI, bool DENORM>
 __global__ void __launch_bounds__(256)
-metric_partial_denorm_kernel(const float* __restrict__ pred, const float* __restrict__ truth,
-                             const float* __restrict__ tr, double* __restrict__ partial, int T, int YX, int VYX) {
+metric_partial_kernel(const TI* __restrict__ pred, const TI* __restrict__ truth, const float* __restrict__ tr,
+                      double* __restrict__ partial, int T, int YX, int VYX) {
   PCM_PDL_ENTRY();
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= VYX) return;
-  const int v = pix / YX;
-  const int kind = (int)__ldg(tr + 4 * v);
-  const double a = (double)__ldg(tr + 4 * v + 1), b = (double)__ldg(tr + 4 * v + 2), c = (double)__ldg(tr + 4 * v + 3);
+  int kind = 0;
+  double a = 1.0, b = 0.0, c = 1.0;
+  if (DENORM) {
+    const int v = pix / YX;
+    kind = (int)__ldg(tr + 4 * v);
+    a = (double)__ldg(tr + 4 * v + 1); b = (double)__ldg(tr + 4 * v + 2); c = (double)__ldg(tr + 4 * v + 3);
+  }
   const int per = (T + gridDim.y - 1) / gridDim.y;
   const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
   double sp = 0, spp = 0, st = 0, stt = 0, sd = 0;
+  int np = 0, nt = 0, nd = 0;
   for (int t = t0; t < t1; ++t) {
-    const double p = denorm((double)__ldg(pred + (long long)t * VYX + pix), kind, a, b, c);
-    const double q = denorm((double)__ldg(truth + (long long)t * VYX + pix), kind, a, b, c);
-    const double d = p - q;
-    sp += p; st += q;
-    spp = fma(p, p, spp);
-    stt = fma(q, q, stt);
-    sd = fma(d, d, sd);
+    double p = (double)__ldg(pred + (long long)t * VYX + pix);
+    double q = (double)__ldg(truth + (long long)t * VYX + pix);
+    if (DENORM) { p = denorm(p, kind, a, b, c); q = denorm(q, kind, a, b, c); }
+    const bool okp = p == p, okq = q == q;
+    if (okp) { sp += p; spp = fma(p, p, spp); ++np; }
+    if (okq) { st += q; stt = fma(q, q, stt); ++nt; }
+    if (okp && okq) { const double d = p - q; sd = fma(d, d, sd); ++nd; }
   }
-  double* o = partial + (long long)pix * 5;
+  double* o = partial + (long long)pix * kMS;
   atomicAdd(o + 0, sp); atomicAdd(o + 1, spp); atomicAdd(o + 2, st); atomicAdd(o + 3, stt); atomicAdd(o + 4, sd);
+  atomicAdd(o + 5, (double)np); atomicAdd(o + 6, (double)nt); atomicAdd(o + 7, (double)nd);
 }
 
 // one block per variable; out[v][0..2]
 __global__ void __launch_bounds__(256)
 metric_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ w_lat, double* __restrict__ out,
-                       double Tn, int Y, int X) {
+                       int Y, int X) {
   PCM_PDL_ENTRY();
   __shared__ double red[32];
   const int v = blockIdx.x;
-  double a0 = 0, a1 = 0, a2 = 0, wsum = 0;
+  double a0 = 0, w0 = 0, a1 = 0, a2 = 0, w1 = 0;
   for (int i = threadIdx.x; i < Y * X; i += blockDim.x) {
     const double w = w_lat[i / X];
-    const double* q = partial + ((long long)v * Y * X + i) * 5;
-    const double mp = q[0] / Tn, mt = q[2] / Tn;
-    const double vp = fmax(q[1] / Tn - mp * mp, 0.0), vt = fmax(q[3] / Tn - mt * mt, 0.0);
-    a0 += w * q[4] / Tn;                       // time-mean of (p-t)^2 at this pixel
-    a1 += w * (mp - mt) * (mp - mt);
-    a2 += w * fabs(sqrt(vp) - sqrt(vt));
-    wsum += w;
+    const double* q = partial + ((long long)v * Y * X + i) * kMS;
+    const double np = q[5], nt = q[6], nd = q[7];
+    a0 += w * q[4];                            // sum over time of (p-t)^2 at this pixel, w * (terms that exist)
+    w0 += w * nd;
+    if (np > 0 && nt > 0) {                    // time mean / std exist for both fields at this pixel
+      const double mp = q[0] / np, mt = q[2] / nt;
+      const double vp = fmax(q[1] / np - mp * mp, 0.0), vt = fmax(q[3] / nt - mt * mt, 0.0);
+      a1 += w * (mp - mt) * (mp - mt);
+      a2 += w * fabs(sqrt(vp) - sqrt(vt));
+      w1 += w;
+    }
   }
   a0 = block_sum(a0, red);
+  w0 = block_sum(w0, red);
   a1 = block_sum(a1, red);
   a2 = block_sum(a2, red);
-  wsum = block_sum(wsum, red);
+  w1 = block_sum(w1, red);
   if (threadIdx.x == 0) {
-    out[v * 3 + 0] = sqrt(a0 / wsum);
-    out[v * 3 + 1] = sqrt(a1 / wsum);
-    out[v * 3 + 2] = a2 / wsum;
+    out[v * 3 + 0] = sqrt(a0 / w0);
+    out[v * 3 + 1] = sqrt(a1 / w1);
+    out[v * 3 + 2] = a2 / w1;
   }
 }
 
@@ -97,12 +93,13 @@ metric_finalize_kernel(const double* __restrict__ partial, const double* __restr
 
 using namespace pcm;
 
-extern "C" int pcm_metric_partial(const float* pred, const float* truth, double* partial, int T, int V, int Y, int X,
-                                  int zero_first, pcm_stream_t s) {
+template <typename TI, bool DENORM>
+static int metric_partial_launch(const TI* pred, const TI* truth, const float* tr, double* partial, int T, int V, int Y,
+                                 int X, int zero_first, pcm_stream_t s, const char* what) {
   const int VYX = V * Y * X;
   if (zero_first) {
-    cudaError_t e = cudaMemsetAsync(partial, 0, (size_t)VYX * 5 * sizeof(double), (cudaStream_t)s);
-    if (e != cudaSuccess) { set_error("metric_partial memset: %s", cudaGetErrorString(e)); return PCM_ERR_CUDA; }
+    cudaError_t e = cudaMemsetAsync(partial, 0, (size_t)VYX * kMS * sizeof(double), (cudaStream_t)s);
+    if (e != cudaSuccess) { set_error("%s memset: %s", what, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
   }
   if (T == 0) return PCM_OK;
   const int gx = ceil_div(VYX, 256);
@@ -110,30 +107,30 @@ extern "C" int pcm_metric_partial(const float* pred, const float* truth, double*
   if (chunks > (T + 15) / 16) chunks = (T + 15) / 16;
   if (chunks < 1) chunks = 1;
   dim3 grid(gx, chunks);
-  pcm::launch(metric_partial_kernel, grid, 256, 0, (cudaStream_t)s, pred, truth, partial, T, VYX);
-  return check_launch("metric_partial");
+  pcm::launch(metric_partial_kernel<TI, DENORM>, grid, 256, 0, (cudaStream_t)s, pred, truth, tr, partial, T, Y * X, VYX);
+  return check_launch(what);
+}
+
+extern "C" int pcm_metric_partial(const float* pred, const float* truth, double* partial, int T, int V, int Y, int X,
+                                  int zero_first, pcm_stream_t s) {
+  return metric_partial_launch<float, false>(pred, truth, nullptr, partial, T, V, Y, X, zero_first, s, "metric_partial");
+}
+
+extern "C" int pcm_metric_partial_f64(const double* pred, const double* truth, double* partial, int T, int V, int Y,
+                                      int X, int zero_first, pcm_stream_t s) {
+  return metric_partial_launch<double, false>(pred, truth, nullptr, partial, T, V, Y, X, zero_first, s,
+                                              "metric_partial_f64");
 }
 
 extern "C" int pcm_metric_partial_denorm(const float* pred, const float* truth, const float* tr, double* partial, int T,
                                          int V, int Y, int X, int zero_first, pcm_stream_t s) {
   PCM_REQUIRE(tr != nullptr, "metric_partial_denorm: transform table is null");
-  const int VYX = V * Y * X;
-  if (zero_first) {
-    cudaError_t e = cudaMemsetAsync(partial, 0, (size_t)VYX * 5 * sizeof(double), (cudaStream_t)s);
-    if (e != cudaSuccess) { set_error("metric_partial_denorm memset: %s", cudaGetErrorString(e)); return PCM_ERR_CUDA; }
-  }
-  if (T == 0) return PCM_OK;
-  const int gx = ceil_div(VYX, 256);
-  int chunks = (4 * 148 + gx - 1) / gx;
-  if (chunks > (T + 15) / 16) chunks = (T + 15) / 16;
-  if (chunks < 1) chunks = 1;
-  pcm::launch(metric_partial_denorm_kernel, dim3(gx, chunks), 256, 0, (cudaStream_t)s, pred, truth, tr, partial, T, Y * X, VYX);
-  return check_launch("metric_partial_denorm");
+  return metric_partial_launch<float, true>(pred, truth, tr, partial, T, V, Y, X, zero_first, s, "metric_partial_denorm");
 }
 
 extern "C" int pcm_metric_finalize(const double* partial, const double* w_lat, double* out, long long T_total, int V,
                                    int Y, int X, pcm_stream_t s) {
-  PCM_REQUIRE(T_total > 0, "metric_finalize: T_total must be positive");
-  pcm::launch(metric_finalize_kernel, V, 256, 0, (cudaStream_t)s, partial, w_lat, out, (double)T_total, Y, X);
+  (void)T_total;      // kept in the ABI: the per-pixel counts in `partial` carry the number of time steps
+  pcm::launch(metric_finalize_kernel, V, 256, 0, (cudaStream_t)s, partial, w_lat, out, Y, X);
   return check_launch("metric_finalize");
 }

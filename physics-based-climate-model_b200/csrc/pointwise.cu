@@ -86,10 +86,25 @@ nchw_to_nhwc_x4_kernel(const float* __restrict__ x, T* __restrict__ y, int N, in
 
 // Sliding-window staging from a device-resident series (main_final.py:97-154): NHWC image n <- NCHW frame frames[n]
 // of `series` (frames[n] < 0: the zero left-pad of windows that start before the record).  Four pixels per thread.
+// Optional, fused while staging:
+//   * norm != nullptr: Normalizer.normalize(data, "input") of src/utils_final.py:45-128 per channel, in fp64 like
+//     numpy on the reference's arrays: norm[c] = (kind, a, b, lambda), x_n = (g(x) - b) * a with g = identity
+//     (kind 0: zscore a = 1/(std+1e-8), b = mean; minimax a = 1/range, b = min), log1p (1), sqrt (2), x^lambda (3);
+//     kind < 0: pass through (no config for that channel).
+//   * month != nullptr: channels C, C+1 = sin / cos(2 pi month[frame] / 12), the seasonal channels of
+//     main_final.py:186-216 (not normalised: the reference has no statistics entry for them).
+// Left-pad frames stay all-zero (the reference pads with zeros of the already normalised tensor).
+__device__ __forceinline__ float norm_apply(float x, int kind, double a, double b, double lam) {
+  if (kind < 0) return x;
+  double u = (double)x;
+  u = kind == 0 ? u : kind == 1 ? log1p(u) : kind == 2 ? sqrt(u) : pow(u, lam);
+  return (float)((u - b) * a);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 window_stage_kernel(const float* __restrict__ series, const int* __restrict__ frames, T* __restrict__ y, int N, int C,
-                    int P, int Cp) {
+                    int P, int Cp, const double* __restrict__ norm, const int* __restrict__ month) {
   PCM_PDL_ENTRY();
   const int cv = Cp / 8, P4 = P / 4;
   const long long total = (long long)N * cv * P4;
@@ -104,8 +119,29 @@ window_stage_kernel(const float* __restrict__ series, const int* __restrict__ fr
     for (int j = 0; j < 8; ++j) {
       const int c = cb * 8 + j;
       float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < C && f >= 0) q = __ldg(reinterpret_cast<const float4*>(series + ((long long)f * C + c) * P) + p4);
+      if (c < C && f >= 0) {
+        q = __ldg(reinterpret_cast<const float4*>(series + ((long long)f * C + c) * P) + p4);
+        if (norm != nullptr) {
+          const int kind = (int)__ldg(norm + 4 * c);
+          const double a = __ldg(norm + 4 * c + 1), b = __ldg(norm + 4 * c + 2), lam = __ldg(norm + 4 * c + 3);
+          q.x = norm_apply(q.x, kind, a, b, lam); q.y = norm_apply(q.y, kind, a, b, lam);
+          q.z = norm_apply(q.z, kind, a, b, lam); q.w = norm_apply(q.w, kind, a, b, lam);
+        }
+      }
       v[0][j] = q.x; v[1][j] = q.y; v[2][j] = q.z; v[3][j] = q.w;
+    }
+    if (month != nullptr && f >= 0) {
+      const float ang = 6.283185307179586f * (float)__ldg(month + f) / 12.f;
+      const float sn = sinf(ang), cs = cosf(ang);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cb * 8 + j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (c == C) v[k][j] = sn;
+          if (c == C + 1) v[k][j] = cs;
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) store8(y + ((long long)n * P + 4 * p4 + k) * Cp + cb * 8, v[k]);
@@ -484,13 +520,13 @@ extern "C" int pcm_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, in
 }
 
 extern "C" int pcm_window_stage(const float* series, const int* frames, void* y, int N, int C, int H, int W, int Cp,
-                                int dtype, pcm_stream_t s) {
-  PCM_REQUIRE(Cp % 8 == 0 && Cp >= C, "window_stage: bad channel padding C=%d Cp=%d", C, Cp);
+                                const double* norm, const int* month, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(Cp % 8 == 0 && Cp >= C + (month ? 2 : 0), "window_stage: bad channel padding C=%d Cp=%d", C, Cp);
   PCM_REQUIRE((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(series) & 15) == 0, "window_stage: H*W must be a multiple of 4");
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * (Cp / 8) * H * W / 4;
-  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(window_stage_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s, 
-                                   series, frames, (T*)y, N, C, H * W, Cp)));
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(window_stage_kernel<T>, grid_for(total), 256, 0, (cudaStream_t)s,
+                                   series, frames, (T*)y, N, C, H * W, Cp, norm, month)));
   return check_launch("window_stage");
 }
 

@@ -29,18 +29,24 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+PARTIAL_WIDTH = 8      # per pixel: sums of p, p^2, t, t^2, (p-t)^2 and the counts of non-NaN p, t, (p-t)
+
+
 def metric_partial_sums(pred: torch.Tensor, truth: torch.Tensor, partial: torch.Tensor = None) -> torch.Tensor:
-    """pred/truth (T, V, Y, X) fp32 CUDA -> fp64 (V, Y, X, 5) per-pixel sums over time of
-    p, p^2, t, t^2, (p-t)^2.  Pass `partial` to accumulate further time shards into it."""
+    """pred/truth (T, V, Y, X) fp32 (or fp64) CUDA -> fp64 (V, Y, X, 8) per-pixel sums over time of
+    p, p^2, t, t^2, (p-t)^2 and the non-NaN counts (NaNs are skipped like xarray's reductions,
+    src/utils_final.py:296).  Pass `partial` to accumulate further time shards into it."""
     if not pred.is_cuda:
         raise RuntimeError("pcm_b200.metric: tensors must live on the GPU (no CPU fallback)")
-    pred = pred.contiguous().float()
-    truth = truth.contiguous().float()
+    f64 = pred.dtype == torch.float64
+    pred = pred.contiguous() if f64 else pred.contiguous().float()
+    truth = truth.contiguous().to(pred.dtype)
     T, V, Y, X = pred.shape
     zero = partial is None
     if zero:
-        partial = torch.empty((V, Y, X, 5), device=pred.device, dtype=torch.float64)
-    lib().call("pcm_metric_partial", pred.data_ptr(), truth.data_ptr(), partial.data_ptr(), T, V, Y, X, int(zero), _stream())
+        partial = torch.empty((V, Y, X, PARTIAL_WIDTH), device=pred.device, dtype=torch.float64)
+    lib().call("pcm_metric_partial_f64" if f64 else "pcm_metric_partial", pred.data_ptr(), truth.data_ptr(),
+               partial.data_ptr(), T, V, Y, X, int(zero), _stream())
     return partial
 
 
@@ -78,16 +84,19 @@ def metric_partial_sums_normalized(pred_norm: torch.Tensor, truth_norm: torch.Te
     T, V, Y, X = pred_norm.shape
     zero = partial is None
     if zero:
-        partial = torch.empty((V, Y, X, 5), device=pred_norm.device, dtype=torch.float64)
+        partial = torch.empty((V, Y, X, PARTIAL_WIDTH), device=pred_norm.device, dtype=torch.float64)
     lib().call("pcm_metric_partial_denorm", pred_norm.data_ptr(), truth_norm.data_ptr(), table.data_ptr(), partial.data_ptr(),
                T, V, Y, X, int(zero), _stream())
     return partial
 
 
-def metric_finalize(partial: torch.Tensor, lat, T_total: int) -> torch.Tensor:
-    """-> fp64 (V, 3): monthly_rmse, time_mean_rmse, time_std_mae per variable."""
+def metric_finalize(partial: torch.Tensor, lat, T_total: int, weights=None) -> torch.Tensor:
+    """-> fp64 (V, 3): monthly_rmse, time_mean_rmse, time_std_mae per variable.  `weights` (Y,) overrides the
+    cos(lat)/mean weights (the Kaggle scorer passes cos(lat_2dp)/sum; any positive scaling gives the same result)."""
     V, Y, X, _ = partial.shape
-    w = torch.as_tensor(get_lat_weights(lat), dtype=torch.float64, device=partial.device)
+    w = torch.as_tensor(get_lat_weights(lat) if weights is None else np.asarray(weights, np.float64),
+                        dtype=torch.float64, device=partial.device)
+    assert w.numel() == Y
     out = torch.empty((V, 3), device=partial.device, dtype=torch.float64)
     lib().call("pcm_metric_finalize", partial.data_ptr(), w.data_ptr(), out.data_ptr(), int(T_total), V, Y, X, _stream())
     return out

@@ -487,20 +487,28 @@ def season_embed_stage(x5: torch.Tensor, month: torch.Tensor, dtype, T: int = 1)
     return y
 
 
-def window_stage(series: torch.Tensor, idx: torch.Tensor, T: int, dtype) -> torch.Tensor:
+def window_stage(series: torch.Tensor, idx: torch.Tensor, T: int, dtype, norm: Optional[torch.Tensor] = None,
+                 month: Optional[torch.Tensor] = None) -> torch.Tensor:
     """SequenceDataset.__getitem__ (main_final.py:97-154) for a whole batch, on the device: `series` is the resident
     input record (Ttot, C, H, W) fp32, `idx` (B,) the target time indices; returns the t-major staged frames
     (T*B, H, W, 16): frame (t, b) = series[idx[b] - T + 1 + t], zeros where that index is negative (left pad).
+    norm (C, 4) fp64 [data.Normalizer.input_table]: the record is RAW and Normalizer.normalize is applied while staging;
+    month (Ttot,) int32: sin/cos month channels C, C+1 are synthesised (main_final.py:186-216).
     Inputs are data: no gradient."""
     _require_cuda(series, "series")
     Ttot, C, H, W = series.shape
     B = idx.numel()
+    Cout = C + (2 if month is not None else 0)
     # frame table: a (T, B) int tensor computed with torch integer ops (index plumbing, no activation arithmetic)
     frames = (idx.to(torch.int32).reshape(1, B) - (T - 1) + torch.arange(T, device=idx.device, dtype=torch.int32).reshape(T, 1))
     frames = torch.where(frames < Ttot, frames, torch.full_like(frames, -1)).contiguous()
-    y = torch.empty((T * B, H, W, padc(C)), device=series.device, dtype=dtype)
-    _call("pcm_window_stage", series.contiguous().float().data_ptr(), frames.data_ptr(), y.data_ptr(), T * B, C, H, W, padc(C),
-          _DT[dtype], _s())
+    y = torch.empty((T * B, H, W, padc(Cout)), device=series.device, dtype=dtype)
+    if norm is not None:
+        assert norm.dtype == torch.float64 and tuple(norm.shape) == (C, 4) and norm.is_cuda and norm.is_contiguous()
+    if month is not None:
+        assert month.dtype == torch.int32 and month.numel() == Ttot and month.is_cuda and month.is_contiguous()
+    _call("pcm_window_stage", series.contiguous().float().data_ptr(), frames.data_ptr(), y.data_ptr(), T * B, C, H, W,
+          padc(Cout), _p(norm), _p(month), _DT[dtype], _s())
     return y
 
 

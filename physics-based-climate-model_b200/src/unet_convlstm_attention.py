@@ -57,12 +57,15 @@ class AttUNetConvLSTM(nn.Module):
         x = ops.StageIn.apply(x_seq.reshape(B * T, C, H, W), compute_dtype(), 16, T)
         return self.forward_staged(x, B, T)
 
-    def forward_windows(self, series, idx, T=None):
-        """Device-resident data path: `series` (Ttot, C_in, H, W) is the whole normalised input record
-        kept in HBM, `idx` (B,) the target months; windows of T = seq_len frames ending at idx (zero left-padded,
-        main_final.py:97-154) are gathered and staged by one kernel.  Equals forward(x_seq) on the stacked windows."""
+    def forward_windows(self, series, idx, T=None, norm=None, month=None):
+        """Device-resident data path: `series` (Ttot, C, H, W) is the whole input record kept in HBM,
+        `idx` (B,) the target months; windows of T = seq_len frames ending at idx (zero left-padded,
+        main_final.py:97-154) are gathered and staged by one kernel.  Equals forward(x_seq) on the stacked windows.
+        norm: (C, 4) fp64 table of data.Normalizer.input_table — the record is then RAW (physical units) and
+        Normalizer.normalize (src/utils_final.py:45-128) is applied while staging; month: (Ttot,) int32 month index
+        0..11 — the sin/cos seasonal channels (main_final.py:186-216) are synthesised as channels C, C+1."""
         T = self.seq_len if T is None else T
-        x = ops.window_stage(series, idx, T, compute_dtype())
+        x = ops.window_stage(series, idx, T, compute_dtype(), norm=norm, month=month)
         return self.forward_staged(x, idx.numel(), T)
 
     def forward_staged(self, x, B, T):

@@ -394,3 +394,90 @@ def test_metric_with_fused_inverse_transform(G):
     for i in range(2):
         want = MO.metric_triplet(dp[:, i], dt[:, i], w)
         np.testing.assert_allclose(got[i], want, rtol=1e-5)
+
+
+def test_metric_skips_nans_like_xarray(G):
+    """NaN cells (e.g. the tas < 150 K placeholders the reference masks, main_final.py:222-224) drop out of the time
+    mean / std of their pixel and of the weighted means (src/utils_final.py:296) — against the numpy restatement."""
+    from oracle import metric_oracle as MO
+    from pcm_b200 import metric as M
+    pred, true, lat = MO.synth_metric_arrays(60)
+    rs = np.random.RandomState(0)
+    pred, true = pred.copy(), true.copy()
+    true[rs.rand(*true.shape) < 0.02] = np.nan            # scattered missing targets
+    pred[rs.rand(*pred.shape) < 0.01] = np.nan
+    true[:, 0, 5, 7] = np.nan                              # a pixel with no valid target at all
+    w = MO.get_lat_weights(lat)
+    got = M.weighted_metric_triplets(torch.from_numpy(pred).cuda(), torch.from_numpy(true).cuda(), lat)
+    for i in range(2):
+        np.testing.assert_allclose(got[i], MO.metric_triplet(pred[:, i], true[:, i], w), rtol=1e-9)
+
+
+def test_kaggle_score_matches_unmodified_reference(G, golden_dir):
+    """a18: the Kaggle form of the score (weights cos(lat_2dp)/sum, _climate_kaggle_metric.py:103-153) on the device,
+    against numbers the UNMODIFIED reference scorer produced (oracle/make_goldens.py): the Appendix G fixture through the
+    array route, and a DataFrame round trip (our writer -> our parser -> device reductions)."""
+    import json
+    import os
+    from oracle import kaggle_oracle as KO
+    from oracle import metric_oracle as MO
+    from pcm_b200 import kaggle as K
+    with open(os.path.join(golden_dir, "metric_appendix_g.json")) as f:
+        want = json.load(f)["reference_kaggle_score"]
+    fx = MO.known_answer_fixture()
+    got = K.score_arrays({v: fx[v + "_pred"] for v in ("tas", "pr")}, {v: fx[v + "_true"] for v in ("tas", "pr")}, fx["lats"])
+    assert abs(got - want) / want < 1e-9, (got, want)
+    with open(os.path.join(golden_dir, "kaggle_roundtrip.json")) as f:
+        g = json.load(f)
+    pred, true, lat, lon, names = KO.synth_submission(T=g["T"], seed=g["seed"])
+    sol = K.convert_predictions_to_kaggle_format(true, np.arange(g["T"]), lat, lon, names)
+    sub = K.convert_predictions_to_kaggle_format(pred, np.arange(g["T"]), lat, lon, names)
+    got = K.score(sol, sub, "ID")
+    assert abs(got - g["reference_score"]) / g["reference_score"] < 1e-9, (got, g["reference_score"])
+    perm = np.random.RandomState(3).permutation(len(sub))
+    got = K.score(sol, sub.iloc[perm].reset_index(drop=True), "ID")
+    assert abs(got - g["reference_score_shuffled_submission"]) / g["reference_score"] < 1e-9
+    with pytest.raises(ValueError, match="Submission must have columns"):
+        K.score(sol, sub.rename(columns={"Prediction": "p"}), "ID")
+    with pytest.raises(ValueError, match="missing predictions"):
+        K.score(sol, sub.iloc[:-5], "ID")
+
+
+def test_window_stage_fused_normalizer_and_season(G):
+    """(f)2: raw record in HBM -> Normalizer.normalize (zscore / minimax / log1p / sqrt / pow / pass-through) + seasonal
+    sin/cos channels + zero left-pad in the staging kernel == the reference's data pipeline order (normalise the record,
+    append the month channels, slice windows, pad with zeros)."""
+    import pcm_b200
+    from pcm_b200 import ops
+    from pcm_b200.data import Normalizer
+    Ttot, C, H, W, T = 14, 5, 8, 12, 4
+    g = torch.Generator().manual_seed(5)
+    raw = torch.rand(Ttot, C, H, W, generator=g) * 3 + 0.1
+    stats = {0: {"method": "zscore", "params": {"mean": 1.5, "std": 0.8}},
+             1: {"method": "minimax", "params": {"min_val": 0.1, "max_val": 3.1}},
+             2: {"method": "log1p", "params": {"mean": 0.9, "std": 0.4}},
+             3: {"method": "sqrt", "params": {"mean": 1.2, "std": 0.3}},
+             4: {"method": "pow", "params": {"lambda": 0.25, "mean": 1.1, "std": 0.2}}}
+    nz = Normalizer()
+    nz.set_input_statistics(stats)
+    month = torch.arange(Ttot, dtype=torch.int32) % 12
+    # reference order of operations, numpy fp64 (src/utils_final.py:76-128, main_final.py:188-216)
+    r = raw.double().numpy()
+    n = np.stack([(r[:, 0] - 1.5) / (0.8 + 1e-8), (r[:, 1] - 0.1) / 3.0, (np.log1p(r[:, 2]) - 0.9) / (0.4 + 1e-8),
+                  (np.sqrt(r[:, 3]) - 1.2) / (0.3 + 1e-8), (r[:, 4] ** 0.25 - 1.1) / (0.2 + 1e-8)], 1)
+    ang = 2 * np.pi * month.numpy() / 12
+    rec = np.concatenate([n, np.broadcast_to(np.sin(ang)[:, None, None, None], (Ttot, 1, H, W)),
+                          np.broadcast_to(np.cos(ang)[:, None, None, None], (Ttot, 1, H, W))], 1).astype(np.float32)
+    idx = torch.tensor([0, 2, 3, 9, 13])
+    want = np.zeros((T, len(idx), H, W, 16), np.float32)
+    for b, i in enumerate(idx.tolist()):
+        for t in range(T):
+            f = i - T + 1 + t
+            if f >= 0:
+                want[t, b, :, :, :7] = rec[f].transpose(1, 2, 0)
+    got = ops.window_stage(raw.cuda(), idx.cuda(), T, torch.float32, norm=nz.input_table(C, "cuda"),
+                           month=month.cuda()).cpu().numpy().reshape(T, len(idx), H, W, 16)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+    # stand-alone Normalizer.normalize on the device
+    out = nz.normalize(raw.cuda(), "input").cpu().numpy()
+    np.testing.assert_allclose(out, n.astype(np.float32), rtol=2e-6, atol=2e-6)
