@@ -258,6 +258,12 @@ PCM_API int pcm_batch_sum(const void* x, float* out, int B, long long R, int dty
 PCM_API int pcm_relu_bwd(const void* dy, const void* y, void* dx, long long n, int dtype, pcm_stream_t s);
 /* nn.Dropout: y = x * keep(seed, i)/(1-p) with a counter-based mask (the same call on dy is the backward);
  * nn.Dropout2d (src/models.py:103): mask[n*C + c] in {0, 1/(1-p)}, applied with pcm_scale_channels */
+/* Dropout epoch: every mask-drawing call (pcm_dropout, pcm_dropout_mask, pcm_mha_*) mixes ONE library-owned device
+ * counter into its seed.  pcm_dropout_epoch_advance increments it with a one-thread kernel on `s`; captured in a CUDA
+ * graph it makes every replay draw fresh masks (scalar seeds are frozen in the graph) while forward and backward of
+ * one step still agree.  pcm_dropout_epoch reads it back (synchronous; tests). */
+PCM_API int pcm_dropout_epoch_advance(pcm_stream_t s);
+PCM_API long long pcm_dropout_epoch(void);
 PCM_API int pcm_dropout(const void* x, void* y, long long n, float p, long long seed, int dtype, pcm_stream_t s);
 PCM_API int pcm_dropout_mask(float* mask, long long n, float p, long long seed, pcm_stream_t s);
 

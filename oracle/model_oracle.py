@@ -8,8 +8,9 @@ these functions.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'
 
 Pinning: the reference holds NO golden vectors for the models.  The
 restatement is pinned against the *imported reference modules themselves* in the build
-container (``oracle/make_goldens.py`` -> ``tests/golden/*.npz``; ``tests/test_oracle_vs_reference.py``
-re-checks live whenever ``/root/reference`` is present).
+container (``oracle/make_goldens.py`` -> ``tests/golden/*.npz``); ``tests/test_oracle_golden.py`` checks this
+restatement against those fixtures on every CPU run, and ``tests/test_cpu_boundary.py`` re-checks the parameter
+surface / default initialisation live against the reference modules whenever ``/root/reference`` is present.
 
 Every function cites the reference lines (relative to /root/reference) it restates.
 """

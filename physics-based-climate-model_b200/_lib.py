@@ -24,7 +24,7 @@ def parse_header(path: str = _HEADER):
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     txt = re.sub(r"//[^\n]*", "", txt)
     protos = {}
-    for m in re.finditer(r"\b(const char\*|int)\s+(pcm_\w+)\s*\(([^)]*)\)\s*;", txt):
+    for m in re.finditer(r"\b(const char\*|long long|int)\s+(pcm_\w+)\s*\(([^)]*)\)\s*;", txt):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         parsed = []
         if args and args != "void":
@@ -36,7 +36,7 @@ def parse_header(path: str = _HEADER):
                     toks = a.split(" ")
                     ty = " ".join(t for t in toks[:-1] if t != "const")
                     parsed.append((_CTYPES[ty], toks[-1]))
-        protos[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, parsed)
+        protos[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_longlong if "long" in ret else ctypes.c_int, parsed)
     return protos
 
 

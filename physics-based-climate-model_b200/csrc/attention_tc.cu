@@ -31,6 +31,7 @@ struct AttParams {
   int L, Lk, nh, E;
   float scale, drop_p;
   unsigned long long seed;
+  const unsigned long long* epoch;      // library-owned dropout epoch cell (common.cuh)
 };
 
 // 16-byte store of 8 bf16 into a K-major 128B-swizzled tile: row r, 16-byte unit u (0..7) of 64-element chunk
@@ -76,6 +77,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   pdl_wait();                       // predecessor complete: global memory may be touched from here on
+  const unsigned long long seed_eff = p.drop_p > 0.f ? mix_epoch(p.seed, p.epoch) : p.seed;
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t colO = 2 * p.Lk;            // S_t at columns t*Lk, O_t at 2*Lk + 32*t   (2*Lk + 64 <= 512)
 
@@ -152,7 +154,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               e = __expf((s[j] - mx) * p.scale);
               sum += e;
               if (p.drop_p > 0.f)
-                e = att_hash_uniform(p.seed, ((unsigned long long)bh * p.L + i) * p.L + j0 + j) >= p.drop_p ? e * keep_sc : 0.f;
+                e = att_hash_uniform(seed_eff, ((unsigned long long)bh * p.L + i) * p.L + j0 + j) >= p.drop_p ? e * keep_sc : 0.f;
             }
             pv[j] = row_ok ? e : 0.f;
           }
@@ -243,6 +245,7 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   pdl_wait();                       // predecessor complete: global memory may be touched from here on
+  const unsigned long long seed_eff = p.drop_p > 0.f ? mix_epoch(p.seed, p.epoch) : p.seed;
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t cS = 0, cdP = 128, cdQ = 256, cdK = 320, cdV = 352;
 
@@ -354,7 +357,7 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (row_ok && j < p.L) {
               pv = __expf(s[e] * p.scale - li);
               if (p.drop_p > 0.f)
-                ks = att_hash_uniform(p.seed, ((unsigned long long)bh * p.L + i) * p.L + j) >= p.drop_p ? keep_sc : 0.f;
+                ks = att_hash_uniform(seed_eff, ((unsigned long long)bh * p.L + i) * p.L + j) >= p.drop_p ? keep_sc : 0.f;
             }
             pt[e] = pv * ks;
             ds[e] = pv * (dp[e] * ks - Di) * p.scale;
@@ -429,7 +432,8 @@ extern "C" int pcm_mha_fwd_tc(const void* qkv, void* out, float* lse, int B, int
   if (B == 0) return PCM_OK;
   AttParams p;
   p.L = L; p.Lk = (L + 15) / 16 * 16; p.nh = nh; p.E = nh * kAttD;
-  p.scale = scale; p.drop_p = drop_p; p.seed = (unsigned long long)seed;
+  p.scale = scale; p.drop_p = drop_p; p.seed = (unsigned long long)seed; p.epoch = dropout_epoch_cell();
+  PCM_REQUIRE(p.epoch != nullptr, "mha_tc: could not allocate the dropout epoch cell");
   CUtensorMap tmQ, tmK, tmV;
   int rc = att_maps(qkv, B, L, 3 * p.E, &tmQ, &tmK, p.Lk, &tmV);
   if (rc != PCM_OK) return rc;
@@ -456,7 +460,8 @@ extern "C" int pcm_mha_bwd_tc(const void* qkv, const void* out, const void* dout
   if (B == 0) return PCM_OK;
   AttParams p;
   p.L = L; p.Lk = (L + 15) / 16 * 16; p.nh = nh; p.E = nh * kAttD;
-  p.scale = scale; p.drop_p = drop_p; p.seed = (unsigned long long)seed;
+  p.scale = scale; p.drop_p = drop_p; p.seed = (unsigned long long)seed; p.epoch = dropout_epoch_cell();
+  PCM_REQUIRE(p.epoch != nullptr, "mha_tc: could not allocate the dropout epoch cell");
   CUtensorMap tmQ, tmKV, tmdO;
   int rc = att_maps(qkv, B, L, 3 * p.E, &tmQ, nullptr, 0, &tmKV);
   if (rc != PCM_OK) return rc;

@@ -306,8 +306,10 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dy,
 // y = x * keep(seed, i) / (1 - p): counter-based mask, so applying the same call to dy is the backward
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, float p,
-                                                       unsigned long long seed) {
+                                                       unsigned long long seed,
+                                                       const unsigned long long* __restrict__ epoch) {
   PCM_PDL_ENTRY();
+  seed = mix_epoch(seed, epoch);
   const float sc = 1.f / (1.f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float u[8];
@@ -318,8 +320,10 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
   }
 }
 
-__global__ void dropout_mask_kernel(float* __restrict__ mask, long long n, float p, unsigned long long seed) {
+__global__ void dropout_mask_kernel(float* __restrict__ mask, long long n, float p, unsigned long long seed,
+                                    const unsigned long long* __restrict__ epoch) {
   PCM_PDL_ENTRY();
+  seed = mix_epoch(seed, epoch);
   const float sc = 1.f / (1.f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     mask[i] = hash_uniform(seed, (unsigned long long)i) >= p ? sc : 0.f;
@@ -441,15 +445,19 @@ extern "C" int pcm_relu_bwd(const void* dy, const void* y, void* dx, long long n
 extern "C" int pcm_dropout(const void* x, void* y, long long n, float p, long long seed, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(n % 8 == 0 && p >= 0.f && p < 1.f, "dropout: n must be a multiple of 8 and 0 <= p < 1");
   if (n == 0) return PCM_OK;
-  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(dropout_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s, 
-                                   static_cast<const T*>(x), static_cast<T*>(y), n / 8, p, (unsigned long long)seed)));
+  const unsigned long long* epoch = dropout_epoch_cell();
+  PCM_REQUIRE(epoch != nullptr, "dropout: could not allocate the epoch cell");
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(dropout_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s,
+                                   static_cast<const T*>(x), static_cast<T*>(y), n / 8, p, (unsigned long long)seed, epoch)));
   return check_launch("dropout");
 }
 
 extern "C" int pcm_dropout_mask(float* mask, long long n, float p, long long seed, pcm_stream_t s) {
   PCM_REQUIRE(p >= 0.f && p < 1.f, "dropout_mask: 0 <= p < 1");
   if (n == 0) return PCM_OK;
-  pcm::launch(dropout_mask_kernel, ew_grid(n), 256, 0, (cudaStream_t)s, mask, n, p, (unsigned long long)seed);
+  const unsigned long long* epoch = dropout_epoch_cell();
+  PCM_REQUIRE(epoch != nullptr, "dropout_mask: could not allocate the epoch cell");
+  pcm::launch(dropout_mask_kernel, ew_grid(n), 256, 0, (cudaStream_t)s, mask, n, p, (unsigned long long)seed, epoch);
   return check_launch("dropout_mask");
 }
 

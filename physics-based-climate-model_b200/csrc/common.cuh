@@ -49,6 +49,15 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
   } while (0)
 
 bool pdl_enabled();
+
+// Dropout epoch: ONE device cell owned by the library (allocated on first use, zero).  Every kernel that draws a
+// counter-based dropout mask mixes it into its seed, and pcm_dropout_epoch_advance bumps it with a one-thread kernel —
+// inside a captured CUDA graph the masks therefore change on every replay although the scalar seeds are frozen in the
+// graph, while forward and backward of one step (same epoch) still regenerate identical masks.
+unsigned long long* dropout_epoch_cell();
+__device__ __forceinline__ unsigned long long mix_epoch(unsigned long long seed, const unsigned long long* epoch) {
+  return seed + 0xD1342543DE82EF95ull * __ldg(epoch);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

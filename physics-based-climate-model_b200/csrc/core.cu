@@ -24,6 +24,20 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+unsigned long long* dropout_epoch_cell() {
+  static unsigned long long* ptr = nullptr;
+  if (ptr == nullptr) {
+    if (cudaMalloc(&ptr, sizeof(unsigned long long)) != cudaSuccess) { ptr = nullptr; return nullptr; }
+    cudaMemset(ptr, 0, sizeof(unsigned long long));
+  }
+  return ptr;
+}
+
+__global__ void dropout_epoch_advance_kernel(unsigned long long* cell) {
+  PCM_PDL_ENTRY();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cell += 1ull;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
@@ -36,4 +50,18 @@ int check_launch(const char* what) {
 }  // namespace pcm
 
 extern "C" const char* pcm_last_error(void) { return pcm::g_err; }
-extern "C" int pcm_version(void) { return 100; }
+extern "C" int pcm_version(void) { return 200; }
+
+extern "C" int pcm_dropout_epoch_advance(pcm_stream_t s) {
+  unsigned long long* cell = pcm::dropout_epoch_cell();
+  PCM_REQUIRE(cell != nullptr, "dropout_epoch_advance: could not allocate the epoch cell");
+  pcm::launch(pcm::dropout_epoch_advance_kernel, 1, 32, 0, (cudaStream_t)s, cell);
+  return pcm::check_launch("dropout_epoch_advance");
+}
+
+extern "C" long long pcm_dropout_epoch(void) {
+  unsigned long long v = 0;
+  unsigned long long* cell = pcm::dropout_epoch_cell();
+  if (cell == nullptr || cudaMemcpy(&v, cell, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (long long)v;
+}

@@ -151,8 +151,9 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ sum_in, con
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
 mha_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int L, int nh, float scale,
-               float drop_p, unsigned long long seed) {
+               float drop_p, unsigned long long seed, const unsigned long long* __restrict__ epoch) {
   PCM_PDL_ENTRY();
+  seed = mix_epoch(seed, epoch);
   extern __shared__ float sm[];
   float* sK = sm;                 // [L][D]
   float* sV = sm + (size_t)L * D; // [L][D]
@@ -244,8 +245,9 @@ template <typename T, int D>
 __global__ void __launch_bounds__(256)
 mha_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
                const float* __restrict__ lse, T* __restrict__ dqkv, int L, int nh, float scale, float drop_p,
-               unsigned long long seed) {
+               unsigned long long seed, const unsigned long long* __restrict__ epoch) {
   PCM_PDL_ENTRY();
+  seed = mix_epoch(seed, epoch);
   extern __shared__ float sm[];
   float* sQ = sm;                       // [L][D]  (pre-scaled by `scale`)
   float* sK = sQ + (size_t)L * D;
@@ -412,7 +414,7 @@ static int mha_fwd_launch(const void* qkv, void* out, float* lse, int B, int L, 
   int rc = set_smem(mha_fwd_kernel<T, D>, smem, "mha_fwd");
   if (rc != PCM_OK) return rc;
   pcm::launch(mha_fwd_kernel<T, D>, B * nh, 256, smem, (cudaStream_t)s, static_cast<const T*>(qkv), static_cast<T*>(out), lse, L, nh,
-                                                               scale, p, (unsigned long long)seed);
+                                                               scale, p, (unsigned long long)seed, dropout_epoch_cell());
   return check_launch("mha_fwd");
 }
 
@@ -424,7 +426,7 @@ static int mha_bwd_launch(const void* qkv, const void* out, const void* dout, co
   if (rc != PCM_OK) return rc;
   pcm::launch(mha_bwd_kernel<T, D>, B * nh, 256, smem, (cudaStream_t)s, static_cast<const T*>(qkv), static_cast<const T*>(out),
                                                                static_cast<const T*>(dout), lse, static_cast<T*>(dqkv), L,
-                                                               nh, scale, p, (unsigned long long)seed);
+                                                               nh, scale, p, (unsigned long long)seed, dropout_epoch_cell());
   return check_launch("mha_bwd");
 }
 

@@ -54,6 +54,12 @@ class TrainStep:
         self._copy_stream = None
         self.graph = None
         self.launches_per_step = 0
+        self.check_every = int(os.environ.get("PCM_CHECK_EVERY", "256"))    # poll the device error counter (0: never)
+        self._steps_run = 0
+        self._ragged_plans = {}
+        self._windows = None                # data.WindowLoader while the window-index step is being built / run
+        self.idx = None
+        self.graph_windows = None
 
     # -- one eager step on the static buffers ---------------------------------------------------
     def _early_bucket(self):
@@ -65,7 +71,20 @@ class TrainStep:
         self._early_work = dist.all_reduce(fg[self.split:self.opt.n_reduced], op=dist.ReduceOp.SUM, group=self.pg,
                                            async_op=True)
 
+    def _forward_loss(self):
+        if self._windows is not None:
+            # device-resident record: the batch is B window indices; gather + zero left-pad +
+            # normalisation + seasonal channels + NHWC staging are one kernel
+            from .config import compute_dtype
+            xs, y = self._windows.stage(self.idx, compute_dtype())
+            out = self.model.forward_staged(xs, self.idx.numel(), self._windows.seq_len)
+            return ops.mse_loss(out, y)
+        return ops.mse_loss(self.model(self.x), self.y)
+
     def _step_impl(self):
+        # fresh dropout masks on every step, also under graph replay (the scalar seeds are frozen in the graph; the
+        # kernels mix this device-side counter into them)
+        lib().call("pcm_dropout_epoch_advance", torch.cuda.current_stream().cuda_stream)
         self.opt.zero_grad()
         fg = self.opt.flat_grad
         overlap = self.split > 0
@@ -74,8 +93,7 @@ class TrainStep:
         try:
             with ops.use_pack_plan(self.plan, self.side):
                 self.plan.repack()
-                out = self.model(self.x)
-                loss = ops.mse_loss(out, self.y)
+                loss = self._forward_loss()
                 loss.backward()
                 ops.join_side()
                 if overlap:
@@ -94,10 +112,23 @@ class TrainStep:
         self.opt.step(grad_scale=scale)
         self.loss.copy_(loss.detach())
 
-    def warmup_and_capture(self, warmup: int = 3):
+    def _snapshot(self):
+        bufs = [b for b in self.model.buffers()]
+        return (self.opt.flat_param.clone(), self.opt.exp_avg.clone(), self.opt.exp_avg_sq.clone(),
+                self.opt.state.clone(), [b.clone() for b in bufs], bufs)
+
+    def _restore(self, snap):
+        fp, m, v, st, saved, bufs = snap
+        self.opt.flat_param.copy_(fp); self.opt.exp_avg.copy_(m); self.opt.exp_avg_sq.copy_(v); self.opt.state.copy_(st)
+        for b, sb in zip(bufs, saved):
+            b.copy_(sb)
+
+    def warmup_and_capture(self, warmup: int = 3, restore: bool = True):
         """Eager warm-up on a side stream (also sizes the allocator), then capture the graph.
-        NOTE: warm-up steps DO update the weights; callers that need exact step counts should
-        re-load parameters and call `reset_optimizer_state()` afterwards."""
+        Warm-up steps run real optimisation steps on whatever is in the static buffers; with `restore` (default) the
+        parameters, the Adam state and the module buffers (BatchNorm running statistics) are snapshotted before and put
+        back afterwards, so training starts from the weights the caller loaded, at step 0."""
+        snap = self._snapshot() if restore else None
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -112,6 +143,64 @@ class TrainStep:
             with torch.cuda.graph(self.graph):
                 self._step_impl()
             torch.cuda.synchronize(self.device)
+        if snap is not None:
+            self._restore(snap)
+        self.check_kernels()
+
+    def check_kernels(self):
+        """The tensor-core kernels report a pipeline time-out (a bounded mbarrier wait that expired) only through a
+        device counter and skip their epilogue; poll it (one 4-byte D2H, synchronising) and refuse to go on with
+        silently wrong activations.  Called after capture and every `check_every` steps from `run`."""
+        n = int(lib()._fn["pcm_tc_error_count"]())
+        if n != 0:
+            raise RuntimeError(f"pcm_b200: {n} tensor-core pipeline time-out(s) reported by the device "
+                               "(pcm_tc_error_count) — results of the affected launches are invalid")
+
+    def capture_windows(self, loader, warmup: int = 2, restore: bool = True):
+        """Second captured step whose input is `self.idx` — B window indices into `loader`'s HBM-resident record
+        (data.WindowLoader) — instead of a staged (B, T, C, H, W) batch: per step only the indices cross PCIe."""
+        B = self.x.shape[0]
+        self.idx = torch.zeros(B, dtype=torch.int64, device=self.device) if self.idx is None else self.idx
+        snap = self._snapshot() if restore else None
+        plan, self.plan = self.plan, ops.PackPlan()
+        self.plan.grad_range = plan.grad_range
+        self._windows = loader
+        try:
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self._step_impl()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            torch.cuda.synchronize(self.device)
+            if self.use_graph:
+                self.graph_windows = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_windows):
+                    self._step_impl()
+                torch.cuda.synchronize(self.device)
+            self._plan_windows = self.plan
+        finally:
+            self.plan = plan
+            self._windows = None
+        self._loader = loader
+        if snap is not None:
+            self._restore(snap)
+
+    def step_windows(self, idx: torch.Tensor) -> torch.Tensor:
+        """One optimisation step on the windows ending at `idx` (B,) int64 (host pinned or device)."""
+        if tuple(idx.shape) != tuple(self.idx.shape):
+            raise ValueError(f"step_windows: expected {tuple(self.idx.shape)} indices, got {tuple(idx.shape)}")
+        self.idx.copy_(idx, non_blocking=True)
+        if self.graph_windows is not None:
+            self.graph_windows.replay()
+        else:
+            plan, self.plan, self._windows = self.plan, self._plan_windows, self._loader
+            try:
+                self._step_impl()
+            finally:
+                self.plan, self._windows = plan, None
+        self._steps_run += 1
+        return self.loss
 
     def reset_optimizer_state(self):
         self.opt.exp_avg.zero_()
@@ -119,7 +208,13 @@ class TrainStep:
         self.opt.state.zero_()
 
     def load_batch(self, x: torch.Tensor, y: torch.Tensor):
-        """Copy a batch (host pinned or device) into the static input buffers (async)."""
+        """Copy a batch (host pinned or device) into the static input buffers (async).  The step is captured for ONE
+        batch shape: a different shape (e.g. the last, smaller batch of an epoch — the reference's DataLoader does not
+        drop it, main_final.py:486-492) must go through `step_ragged`, which pads it and masks the loss."""
+        if tuple(x.shape) != tuple(self.x.shape) or tuple(y.shape) != tuple(self.y.shape):
+            raise ValueError(f"TrainStep was built for x {tuple(self.x.shape)} / y {tuple(self.y.shape)}, got "
+                             f"{tuple(x.shape)} / {tuple(y.shape)}; use step_ragged() for a smaller final batch or "
+                             "drop_last=True")
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
 
@@ -129,6 +224,38 @@ class TrainStep:
             self.graph.replay()
         else:
             self._step_impl()
+        self._steps_run += 1
+        if self.check_every and self._steps_run % self.check_every == 0:
+            self.check_kernels()
+        return self.loss
+
+    def step_ragged(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """The final, smaller batch of an epoch (b < B rows): one EAGER step on exactly those rows (same kernels, no
+        graph: its shape differs from the captured one).  MSE is the mean over the b rows, as nn.MSELoss gives the
+        reference.  Single-process only (under data parallelism every rank must issue the same collectives; use
+        drop_last or pad the sampler like DistributedSampler does)."""
+        if self.world > 1:
+            raise RuntimeError("step_ragged: ragged batches are not supported under data parallelism (pad the sampler)")
+        b = x.shape[0]
+        if b == self.x.shape[0]:
+            return self.step(x, y)
+        if b == 0 or b > self.x.shape[0] or tuple(x.shape[1:]) != tuple(self.x.shape[1:]):
+            raise ValueError(f"step_ragged: bad batch shape {tuple(x.shape)} for a TrainStep of {tuple(self.x.shape)}")
+        xs, ys = self.x, self.y
+        try:
+            self.x = x.to(self.device, torch.float32, non_blocking=True)
+            self.y = y.to(self.device, torch.float32, non_blocking=True)
+            plan = self.plan
+            if b not in self._ragged_plans:                      # own resident buffers: the captured plan's tables
+                self._ragged_plans[b] = ops.PackPlan()           # must not change after capture
+                self._ragged_plans[b].grad_range = plan.grad_range
+            self.plan = self._ragged_plans[b]
+            try:
+                self._step_impl()
+            finally:
+                self.plan = plan
+        finally:
+            self.x, self.y = xs, ys
         return self.loss
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

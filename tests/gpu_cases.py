@@ -66,6 +66,7 @@ def compare(mod, fn, sd, x, y, dtype, golden=None, oracle_keys=None):
         res["golden_loss"] = abs(loss - float(z["loss"])) / abs(float(z["loss"]))
         ge = grad_errors(grads, z)
         res["golden_grads"] = {k: v[0] for k, v in ge.items()}
+        res["golden_gnorm"] = {k: v[2] for k, v in ge.items()}
     return res
 
 
@@ -383,3 +384,49 @@ def case_simplecnn_eval():
     t = F.relu(bn(conv(t, "final.0.", 1), "final.1."))
     want = conv(t, "final.3.", 0)
     return {"out": rel_l2(out.numpy(), want.numpy())}
+
+
+def case_attunet_b64(tag, dtype, through_trainer=True):
+    """The BENCHMARK shape (B=64, T=6, 48x72, base 16) against the fixture the real reference produced
+    (tests/golden/<tag>.npz: strided samples of the output and of every gradient, loss).  The step runs through
+    TrainStep under the captured CUDA graph with the second stream, i.e. exactly what bench.py times: the loss and the
+    gradients left in the flat buffer by the replayed step are compared; the output comes from an eager forward.
+    tag 'attunet_cfg3_b64': seed-derived weights; 'attunet_cfg3_b64_default_init': the reference's own default
+    initialisation under torch.manual_seed(42) on bench.py's first batch."""
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    from pcm_b200.trainer import TrainStep
+    cfg, z = load_golden(tag)
+    B, T, H, W = cfg["B"], cfg["T"], cfg["H"], cfg["W"]
+    if cfg["init"] == "synth":
+        mod = AttUNetConvLSTM(cfg["in_ch"], cfg["out_ch"], cfg["base"], seq_len=T)
+        mod.load_state_dict(O.synth_state_dict(O.attunet_spec(cfg["in_ch"], cfg["out_ch"], cfg["base"]), cfg["seed"]))
+        x, y, _ = O.synth_attunet_batch(B, T, H, W, cfg["seed"] + 1, cfg["in_ch"], cfg["out_ch"])
+    else:
+        torch.manual_seed(cfg["seed"])
+        mod = AttUNetConvLSTM(cfg["in_ch"], cfg["out_ch"], cfg["base"], seq_len=T)
+        x, y, _ = O.synth_attunet_batch(B, T, H, W, cfg["batch_seed"], cfg["in_ch"], cfg["out_ch"])
+    set_compute_dtype(dtype)
+    try:
+        mod = mod.to(DEV).train()
+        xd, yd = x.to(DEV), y.to(DEV)
+        with torch.no_grad():
+            out = mod(xd).float().cpu().numpy().reshape(-1)
+        step = TrainStep(mod, tuple(x.shape), tuple(y.shape), lr=5e-4, use_graph=through_trainer)
+        step.load_batch(xd, yd)
+        if through_trainer:
+            step.warmup_and_capture(warmup=2)            # restores the parameters afterwards
+            assert step.graph is not None and step.side is not None
+        loss = float(step.step(xd, yd).item())
+        torch.cuda.synchronize()
+        grads = {k: p.main_grad.detach().cpu().clone() for k, p in mod.named_parameters() if not k.startswith("post_conv")}
+        for k, p in mod.named_parameters():
+            if k.startswith("post_conv"):
+                grads[k] = None if float(p.main_grad.abs().max()) == 0.0 else p.main_grad.detach().cpu()
+    finally:
+        set_compute_dtype(torch.bfloat16)
+    stride = max(1, out.size // (4 * 1024))
+    ge = grad_errors(grads, z)
+    return {"out": rel_l2(out[::stride], z["out_sample"]),
+            "out_norm": abs(float(np.linalg.norm(out.astype(np.float64))) - float(z["out_norm"][0])) / float(z["out_norm"][0]),
+            "loss": abs(loss - float(z["loss"])) / abs(float(z["loss"])),
+            "grads": {k: v[0] for k, v in ge.items()}, "gnorm": {k: v[2] for k, v in ge.items()}}

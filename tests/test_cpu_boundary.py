@@ -173,3 +173,28 @@ def _close(src, i):
         i += 1
         if depth == 0:
             return i
+
+
+def test_product_synth_recipe_equals_the_oracle_recipe():
+    """bench.py's product arm synthesises its inputs with pcm_b200.synth (no oracle import on that path); the oracle keeps
+    its own statement of the same recipe for the checker side — both must produce identical bits."""
+    import torch
+    from oracle import model_oracle as O
+    from pcm_b200 import synth
+    a = synth.synth_attunet_batch(8, 3, 8, 12, seed=9)
+    b = O.synth_attunet_batch(8, 3, 8, 12, seed=9)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+    a = synth.synth_frame_batch(3, 5, 8, 12, seed=4)
+    b = O.synth_frame_batch(3, 5, 8, 12, seed=4)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_ours")
+    for node in ast.walk(fn):
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mod = getattr(node, "module", None) or ""
+            names = [a.name for a in node.names]
+            assert not mod.startswith("oracle") and not any(n.startswith("oracle") for n in names), \
+                "bench.py run_ours must not import oracle (only its baseline legs may)"

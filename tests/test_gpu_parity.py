@@ -33,7 +33,21 @@ def _check(res, dtype, median=None):
     assert res["out"] < tol["out"], res["out"]
     assert res["loss"] < tol["loss"], res["loss"]
     if "golden_out" in res:
+        # the same run against the fixtures the REAL reference modules produced (oracle/make_goldens.py)
         assert res["golden_out"] < tol["out"], res["golden_out"]
+        assert res["golden_loss"] < tol["loss"], res["golden_loss"]
+        gerrs = []
+        for k, e in res["golden_grads"].items():
+            if res["golden_gnorm"][k] <= 1e-7:
+                assert e < (1e-4 if dtype == torch.float32 else 1e-3), (k, e)
+                continue
+            gerrs.append(e)
+            if dtype != torch.float32 and ".se.fc." in k or k.startswith("fc."):
+                assert e < 4.0, (k, e)
+            else:
+                assert e < tol["grad"], ("golden", k, e)
+        if dtype != torch.float32 and len(gerrs) >= 8:
+            assert float(np.median(gerrs)) < tol["median"], float(np.median(gerrs))
     errs = []
     for k, e in res["grads"].items():
         gn = res["gnorm"].get(k, 1.0)
