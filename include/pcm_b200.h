@@ -326,6 +326,12 @@ PCM_API int pcm_mse_bwd(const float* a, const float* b, const float* gscale, flo
  * state[0] = step count (float), updated on device so a captured graph advances it. */
 PCM_API int pcm_adam_step(float* p, const float* g, float* m, float* v, float* state, long long n, float lr, float b1,
                   float b2, float eps, float wd, float grad_scale, pcm_stream_t s);
+/* pcm_adam_step = pcm_adam_tick (advance the device step counter / bias corrections once per step) + pcm_adam_apply
+ * (update one parameter range).  Separately they let the data-parallel step run the optimizer bucket by bucket, as
+ * each gradient bucket's all-reduce completes. */
+PCM_API int pcm_adam_tick(float* state, float b1, float b2, pcm_stream_t s);
+PCM_API int pcm_adam_apply(float* p, const float* g, float* m, float* v, const float* state, long long n, float lr,
+                   float b1, float b2, float eps, float wd, float grad_scale, pcm_stream_t s);
 
 /* ---- cos(lat)-weighted metric (src/utils_final.py:282-302, main_final.py:616-631) ----------------
  * pred/truth: fp32 [T][V][Y][X]; w_lat: fp64 [Y]; partial: fp64 workspace [V][Y][X][8] (zeroed by the call when

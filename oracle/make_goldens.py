@@ -170,13 +170,17 @@ def main():
     pred, true, lat, lon, names = KO.synth_submission(T=4, seed=7)
     ids, pv = KO.convert_predictions_to_kaggle_format(pred, np.arange(4), lat, lon, names)
     _, tv = KO.convert_predictions_to_kaggle_format(true, np.arange(4), lat, lon, names)
-    sol = pd.DataFrame({"ID": ids, "Prediction": tv})
-    sub = pd.DataFrame({"ID": ids, "Prediction": pv})
+    # float64 columns: what the scorer sees after the submission went through a CSV file (to_csv -> read_csv); with the
+    # in-memory float32 columns the reference's own numpy reductions run in float32 (second number, looser pin)
+    sol = pd.DataFrame({"ID": ids, "Prediction": tv.astype(np.float64)})
+    sub = pd.DataFrame({"ID": ids, "Prediction": pv.astype(np.float64)})
     rt = float(R.score(sol, sub, "ID"))
+    rt_f32 = float(R.score(pd.DataFrame({"ID": ids, "Prediction": tv}), pd.DataFrame({"ID": ids, "Prediction": pv}), "ID"))
     perm = np.random.RandomState(3).permutation(len(ids))                  # shuffled submission: merge must realign
     rt_shuffled = float(R.score(sol, sub.iloc[perm].reset_index(drop=True), "ID"))
     with open(os.path.join(GOLD, "kaggle_roundtrip.json"), "w") as f:
         json.dump({"T": 4, "seed": 7, "reference_score": rt, "reference_score_shuffled_submission": rt_shuffled,
+                   "reference_score_float32_columns": rt_f32,
                    "first_ids": ids[:3], "last_id": ids[-1], "n_rows": len(ids)}, f, indent=1)
     print("goldens written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):

@@ -670,3 +670,17 @@ extern "C" int pcm_adam_step(float* p, const float* g, float* m, float* v, float
     pcm::launch(adam_apply_kernel, grid_for(n), 256, 0, (cudaStream_t)s, p, g, m, v, state, n, lr, b1, b2, eps, wd, grad_scale);
   return check_launch("adam_step");
 }
+
+// The same two kernels separately: under data parallelism the optimizer runs bucket by bucket as each gradient bucket's
+// all-reduce completes (trainer.py) — ONE tick per step, then one apply per parameter range.
+extern "C" int pcm_adam_tick(float* state, float b1, float b2, pcm_stream_t s) {
+  pcm::launch(adam_tick_kernel, 1, 1, 0, (cudaStream_t)s, state, b1, b2);
+  return check_launch("adam_tick");
+}
+
+extern "C" int pcm_adam_apply(float* p, const float* g, float* m, float* v, const float* state, long long n, float lr,
+                              float b1, float b2, float eps, float wd, float grad_scale, pcm_stream_t s) {
+  if (n > 0)
+    pcm::launch(adam_apply_kernel, grid_for(n), 256, 0, (cudaStream_t)s, p, g, m, v, state, n, lr, b1, b2, eps, wd, grad_scale);
+  return check_launch("adam_apply");
+}

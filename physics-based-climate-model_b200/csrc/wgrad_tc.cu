@@ -31,6 +31,7 @@ struct WgradTcParams {
                                 //    sub-tile, gathered from pixels (2h+kh, 2w+kw) through the 5-D views tmB / tmB2
   uint32_t b_sub_bytes;         // convt: bytes of one tap's B sub-tile (all chunks)
   int stages;
+  int bx0;                      // first column of the x box in its tensor map (-pad; 0 for an interior column strip)
   long long sa, sb, st;
   uint32_t a_chunk_bytes, b_chunk_bytes, a_stage_bytes, b_stage_bytes, tx_bytes, tmem_cols, lbo_a, lbo_b;
 };
@@ -107,7 +108,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         } else {
           for (int c = 0; c < p.nb_chunks; ++c)
-            tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, -(p.ksz >> 1), h0 - (p.ksz >> 1), n0);
+            tma_load_4d(b + (size_t)c * p.b_chunk_bytes, &tmB, &full[stage], c * p.Ccb, p.bx0, h0 - (p.ksz >> 1), n0);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -214,8 +215,14 @@ using namespace pcm;
 
 static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                          long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
-                         long long st, int N, int H, int W, int ksz, pcm_stream_t s, int convt = 0) {
+                         long long st, int N, int H, int W, int ksz, pcm_stream_t s, int convt = 0, int Wfull = 0,
+                         int w0 = 0) {
+  // Wfull > 0: this call covers the column strip [w0, w0 + W) of images that are Wfull pixels wide (grids whose rows do
+  // not fit one TMA box, e.g. 360 columns): dy is viewed as a W-wide tensor starting at column w0 (everything outside
+  // the strip is out of bounds = zero, so it contributes nothing), x as the strip plus its real neighbour columns.
   const int pad = ksz >> 1, ntaps = convt == 1 ? 4 : convt == 2 ? 6 : ksz * ksz;
+  if (Wfull <= 0) { Wfull = W; w0 = 0; }
+  PCM_REQUIRE(Wfull == W || (convt == 0 && ksz == 3), "wgrad3x3_tc: column strips are implemented for the 3x3 stride-1 form");
   PCM_REQUIRE(Co % 16 == 0 && (Co <= 64 ? (Co == 16 || Co == 32 || Co == 64) : Co % 128 == 0),
               "wgrad3x3_tc: Co must be 16, 32, 64 or a multiple of 128 (got %d)", Co);
   PCM_REQUIRE(Ci % 16 == 0 && (Ci <= 64 ? (Ci == 16 || Ci == 32 || Ci == 64) : (Ci % 64 == 0 && Ci <= 256)),
@@ -233,6 +240,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   }
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.Wp = W + 2 * pad;
+  p.bx0 = -pad;
   p.ksz = ksz; p.ntaps = ntaps; p.convt = convt;
   p.Co_real = Co_real; p.Ci_real = Ci_real; p.Ci = Ci;
   p.Cca = Co < 64 ? Co : 64;
@@ -315,9 +323,9 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   CUtensorMap tmA, tmB, tmB2;
   {
     uint64_t dims[4] = {(uint64_t)Co, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t strides[3] = {(uint64_t)dy_ps * 2, (uint64_t)W * dy_ps * 2, (uint64_t)dy_ns * 2};
+    uint64_t strides[3] = {(uint64_t)dy_ps * 2, (uint64_t)Wfull * dy_ps * 2, (uint64_t)dy_ns * 2};
     uint32_t box[4] = {(uint32_t)p.Cca, (uint32_t)p.Wp, (uint32_t)a_box_h, (uint32_t)p.Nb};
-    int rc = make_tensor_map(&tmA, dy, 4, dims, strides, box, rba);
+    int rc = make_tensor_map(&tmA, reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)w0 * dy_ps, 4, dims, strides, box, rba);
     if (rc != PCM_OK) return rc;
   }
   if (convt == 2) {
@@ -339,10 +347,16 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
     rc = make_tensor_map(&tmB2, base + (size_t)2 * W * x_ps, 5, dims, strides, box, rbb);
     if (rc != PCM_OK) return rc;
   } else {
-    uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t strides[3] = {(uint64_t)x_ps * 2, (uint64_t)W * x_ps * 2, (uint64_t)x_ns * 2};
+    // x strip with its neighbour columns: an interior strip starts one REAL column to the left (box column 0), the
+    // first strip starts at the image edge (box column -1 = out of bounds = the zero padding)
+    const int xb = w0 > 0 ? w0 - 1 : 0;
+    int xw = (w0 > 0 ? W + 2 : W + 1);
+    if (xb + xw > Wfull) xw = Wfull - xb;
+    if (w0 > 0) p.bx0 = 0;
+    uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)(Wfull == W ? W : xw), (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)x_ps * 2, (uint64_t)Wfull * x_ps * 2, (uint64_t)x_ns * 2};
     uint32_t box[4] = {(uint32_t)p.Ccb, (uint32_t)p.Wp, (uint32_t)b_box_h, (uint32_t)p.Nb};
-    int rc = make_tensor_map(&tmB, x, 4, dims, strides, box, rbb);
+    int rc = make_tensor_map(&tmB, reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)xb * x_ps, 4, dims, strides, box, rbb);
     if (rc != PCM_OK) return rc;
     tmB2 = tmB;
   }
@@ -365,7 +379,16 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
 extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                                long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
                                long long st, int N, int H, int W, pcm_stream_t s) {
-  return wgrad_tc_impl(dy, dy_ns, dy_ps, Co, Co_real, x, x_ns, x_ps, Ci, Ci_real, dw, sa, sb, st, N, H, W, 3, s);
+  if (W + 2 <= 256) return wgrad_tc_impl(dy, dy_ns, dy_ps, Co, Co_real, x, x_ns, x_ps, Ci, Ci_real, dw, sa, sb, st, N, H, W, 3, s);
+  // rows wider than one TMA box (config 5: 360 columns): equal column strips, one launch each, all accumulating into dw
+  const int nstrips = (W + 253) / 254;
+  const int ws = (W + nstrips - 1) / nstrips;
+  for (int w0 = 0; w0 < W; w0 += ws) {
+    const int rc = wgrad_tc_impl(dy, dy_ns, dy_ps, Co, Co_real, x, x_ns, x_ps, Ci, Ci_real, dw, sa, sb, st, N, H,
+                                 (w0 + ws <= W ? ws : W - w0), 3, s, 0, W, w0);
+    if (rc != PCM_OK) return rc;
+  }
+  return PCM_OK;
 }
 
 extern "C" int pcm_wgrad1x1_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,

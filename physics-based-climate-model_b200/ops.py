@@ -267,11 +267,17 @@ def pack_weight(w: torch.Tensor, so: int, si: int, st: int, O: int, I: int, taps
     return out
 
 
-def conv_weight_fwd(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None, Ip: Optional[int] = None):
-    """nn.Conv2d weight (Co, Ci_tot, KH, KW) -> [taps][Co][Ci] (forward, gather mode 0)."""
+def conv_weight_fwd(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None, Ip: Optional[int] = None,
+                    co_split: int = 0):
+    """nn.Conv2d weight (Co, Ci_tot, KH, KW) -> [taps][Co][Ci] (forward, gather mode 0).  co_split > 0: a list of
+    packed slices of co_split output channels each (see conv_s1)."""
     Co, Ci_tot, KH, KW = w.shape
     ci = Ci_tot - ci_off if ci is None else ci
     K = KH * KW
+    if co_split and Co > co_split:
+        assert Co % co_split == 0
+        return [pack_weight(w, Ci_tot * K, K, 1, co_split, ci, K, dtype, offset=c0 * Ci_tot * K + ci_off * K, Ip=Ip)
+                for c0 in range(0, Co, co_split)]
     return pack_weight(w, Ci_tot * K, K, 1, Co, ci, K, dtype, offset=ci_off * K, Ip=Ip)
 
 
@@ -293,8 +299,22 @@ def tc_supported(dtype, Sc: int, Dc: int, K: int = 3) -> bool:
 
 def conv_s1(src, wk, N, H, W, Sc, Dc, K=3, dst=None, dst_f32=False, bias=None, accumulate=False,
             src_ns=None, src_ps=None, dst_ns=None, dst_ps=None, src_off=0, dst_off=0):
-    """Stride-1 'same' convolution dst = conv(src, wk) on NHWC views; wk = [K*K][Dc][Sc]."""
+    """Stride-1 'same' convolution dst = conv(src, wk) on NHWC views; wk = [K*K][Dc][Sc], or a list of such tensors
+    holding consecutive output-channel slices (outputs wider than one 256-column accumulator, e.g. the 512 gate
+    channels of the base-32 ConvLSTM: one launch per slice into its channel range of dst)."""
     dtype = src.dtype
+    if isinstance(wk, (list, tuple)):
+        if dst is None:
+            dst = torch.empty((N, H, W, Dc), device=src.device, dtype=torch.float32 if dst_f32 else dtype)
+        dps = Dc if dst_ps is None else dst_ps
+        c0 = 0
+        for part in wk:
+            dc = part.shape[1]
+            conv_s1(src, part, N, H, W, Sc, dc, K, dst=dst, dst_f32=dst_f32, bias=None if bias is None else bias[c0:c0 + dc],
+                    accumulate=accumulate, src_ns=src_ns, src_ps=src_ps, dst_ns=H * W * dps if dst_ns is None else dst_ns,
+                    dst_ps=dps, src_off=src_off, dst_off=dst_off + c0)
+            c0 += dc
+        return dst
     if not tc_supported(dtype, Sc, Dc, K):
         return conv_gather(src, wk, N, H, W, Sc, H, W, Dc, K, K, 1, K // 2, 0, dst=dst, dst_f32=dst_f32, bias=bias,
                            accumulate=accumulate, src_ns=src_ns, src_ps=src_ps, dst_ns=dst_ns, dst_ps=dst_ps,
@@ -339,8 +359,9 @@ def conv_wgrad(A, B, dw, sa, sb, st, N, Ha, Wa, Ca, Ca_real, Hb, Wb, Cb, Cb_real
 
 
 def wgrad_tc_supported(dtype, Co: int, Ci: int, H: int, W: int) -> bool:
+    # rows wider than one TMA box (W + 2 > 256, config 5) are covered in column strips inside pcm_wgrad3x3_tc
     return (dtype == torch.bfloat16 and (Co in (16, 32, 64) or (Co % 128 == 0 and Co > 0))
-            and Ci in (16, 32, 64, 128, 192, 256) and W + 2 <= 256 and H + 2 <= 256)
+            and Ci in (16, 32, 64, 128, 192, 256) and H + 2 <= 256)
 
 
 def conv3x3_wgrad(dy, x, dw, N, H, W, Co, Ci, Ci_real, Ci_tot=None, dy_ns=None, dy_ps=None, x_ns=None, x_ps=None,
@@ -379,6 +400,13 @@ def convT2x2_fwd(x, wt, bt, B, h, w, Ci, Co, dst, dst_ns, dst_ps, relu=False):
     """dst(b, 2h+kh, 2w+kw, co) = sum_ci x(b,h,w,ci) * wt[ci][co][kh][kw] + bt[co]; dst may be a channel slice of a
     wider buffer (dst_ns / dst_ps = its image / pixel strides)."""
     dt = x.dtype
+    if dt == torch.bfloat16 and _tc_k_ok(Ci) and Co > 64 and Co % 64 == 0:
+        # the GEMM's N extent is 4*Co <= 256: wider outputs go in slices of 64 channels of the destination
+        for c0 in range(0, Co, 64):
+            wk = pack_weight(wt, 4, Co * 4, 1, 64, Ci, 4, dt, offset=c0 * 4)
+            _call("pcm_convT2x2_tc", x.data_ptr(), h * w * Ci, Ci, h, w, Ci, dst.data_ptr() + c0 * dst.element_size(), dst_ns,
+                  dst_ps, 64, wk.data_ptr(), 0 if bt is None else bt.data_ptr() + 4 * c0, B, int(relu), _s())
+        return dst
     wk = pack_weight(wt, 4, Co * 4, 1, Co, Ci, 4, dt)                 # wk[tap][co][ci] = wt[ci][co][tap]
     if dt == torch.bfloat16 and _tc_k_ok(Ci) and Co % 16 == 0 and Co <= 64:
         _call("pcm_convT2x2_tc", x.data_ptr(), h * w * Ci, Ci, h, w, Ci, dst.data_ptr(), dst_ns, dst_ps, Co, wk.data_ptr(),
@@ -809,8 +837,9 @@ class ConvLSTMFn(torch.autograd.Function):
         P, dt, dev = H * W, x.dtype, x.device
         d, st = _DT[dt], _s()
         img = P * Cip
-        wx = conv_weight_fwd(w, dt, 0, Ci, Ip=Cip)
-        wh = conv_weight_fwd(w, dt, Ci, Ch)
+        split = 256 if (dt == torch.bfloat16 and K == 3 and 4 * Ch > 256 and (4 * Ch) % 256 == 0) else 0
+        wx = conv_weight_fwd(w, dt, 0, Ci, Ip=Cip, co_split=split)
+        wh = conv_weight_fwd(w, dt, Ci, Ch, co_split=split)
         gates = torch.empty((T, B, P, 4 * Ch), device=dev, dtype=torch.float32)
         acts = torch.empty((T, B, P, 4 * Ch), device=dev, dtype=dt)
         c_all = torch.empty((T, B, P, Ch), device=dev, dtype=torch.float32)

@@ -59,6 +59,19 @@ class FusedAdam:
                    self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.flat_param.numel(), self.lr, self.betas[0],
                    self.betas[1], self.eps, self.weight_decay, grad_scale, torch.cuda.current_stream().cuda_stream)
 
+    def tick(self):
+        """Advance the device step counter once (then `step_range` per bucket)."""
+        lib().call("pcm_adam_tick", self.state.data_ptr(), self.betas[0], self.betas[1], torch.cuda.current_stream().cuda_stream)
+
+    def step_range(self, lo: int, hi: int, grad_scale: float = 1.0):
+        """Adam update of flat elements [lo, hi) with the bias corrections of the last `tick()`."""
+        if hi <= lo:
+            return
+        o = 4 * lo
+        lib().call("pcm_adam_apply", self.flat_param.data_ptr() + o, self.flat_grad.data_ptr() + o, self.exp_avg.data_ptr() + o,
+                   self.exp_avg_sq.data_ptr() + o, self.state.data_ptr(), hi - lo, self.lr, self.betas[0], self.betas[1],
+                   self.eps, self.weight_decay, grad_scale, torch.cuda.current_stream().cuda_stream)
+
     # ---- checkpointing in torch.optim.Adam's layout (Lightning stores it under `optimizer_states`) -----------------
     def state_dict(self) -> dict:
         """{"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]} with parameters numbered in

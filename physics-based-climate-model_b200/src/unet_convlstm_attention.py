@@ -73,6 +73,7 @@ class AttUNetConvLSTM(nn.Module):
         ops.season_embed_stage(..., T=T), which synthesises the sin/cos month channels on the fly)."""
         s1 = self.enc1.forward_nhwc(x)
         p1, k1 = ops.PoolSkipFn.apply(s1, T, self.up1.up.out_channels)
+        p1 = ops.grad_ready_hook(p1, "enc1_boundary")        # trainer: enc2..enc4 gradients are complete when backward is here
         s2 = self.enc2.conv.forward_nhwc(p1)
         p2, k2 = ops.PoolSkipFn.apply(s2, T, self.up2.up.out_channels)
         s3 = self.enc3.conv.forward_nhwc(p2)

@@ -44,13 +44,31 @@ class TrainStep:
         # for their whole duration the branches do overlap (2.07 -> 1.99 ms per step on B200).  PCM_SIDE_STREAM=0
         # keeps everything on one stream.
         self.side = torch.cuda.Stream(device=self.device) if os.environ.get("PCM_SIDE_STREAM", "1") != "0" else None
-        # two all-reduce buckets (world > 1): [split, n_reduced) = ConvLSTM + decoder + head, complete when backward
-        # reaches the encoder boundary and reduced while the encoder's backward runs; [0, split) = encoder, at the end
+        # Gradient buckets (world > 1), in the order backward completes them.  A bucket is a range of the flat gradient
+        # buffer plus the name of the backward hook at which all of its gradients have been enqueued:
+        #   [convlstm .. head]  at "encoder_boundary" (backward reaches the ConvLSTM input)
+        #   [enc2 .. enc4]      at "enc1_boundary"    (backward reaches enc2's input)
+        #   [enc1]              at the end of backward (14 KB: the only all-reduce that stays exposed)
+        # At each hook the bucket's packed gradients are folded, and on a third stream its all-reduce is issued and
+        # followed by the Adam update of exactly that parameter range — both overlap the rest of backward.
+        # PCM_OVERLAP_ALLREDUCE=0: one all-reduce + one Adam launch after backward; PCM_GRAD_BUCKETS=2: the two-bucket
+        # scheme of round 1 (no hook at the enc1 boundary).
+        self.buckets = []            # [(hook name, lo, hi)]
+        self.tail_bucket = None      # (lo, hi) reduced after backward
         self.split = 0
         if self.world > 1 and hasattr(model, "convlstm") and os.environ.get("PCM_OVERLAP_ALLREDUCE", "1") != "0":
-            first = next(model.convlstm.parameters())
-            self.split = (first.main_grad.data_ptr() - fg.data_ptr()) // 4
-        self._early_work = None
+            off = lambda p: (p.main_grad.data_ptr() - fg.data_ptr()) // 4
+            s_lstm = off(next(model.convlstm.parameters()))
+            self.split = s_lstm
+            self.buckets.append(("encoder_boundary", s_lstm, self.opt.n_reduced))
+            lo = s_lstm
+            if hasattr(model, "enc2") and os.environ.get("PCM_GRAD_BUCKETS", "3") != "2":
+                s_enc2 = off(next(model.enc2.parameters()))
+                if 0 < s_enc2 < s_lstm:
+                    self.buckets.append(("enc1_boundary", s_enc2, s_lstm))
+                    lo = s_enc2
+            self.tail_bucket = (0, lo)
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.buckets else None
         self._copy_stream = None
         self.graph = None
         self.launches_per_step = 0
@@ -62,14 +80,16 @@ class TrainStep:
         self.graph_windows = None
 
     # -- one eager step on the static buffers ---------------------------------------------------
-    def _early_bucket(self):
-        """Backward has reached the encoder boundary: fold and all-reduce the ConvLSTM/decoder/head gradients now
-        (asynchronously — the NCCL kernel overlaps the encoder's backward)."""
+    def _bucket_ready(self, lo: int, hi: int):
+        """Backward has passed this bucket's hook: fold its packed gradients, then — on the communication stream, so that
+        the rest of backward keeps running — all-reduce the range and apply Adam to it."""
         fg = self.opt.flat_grad
         ops.join_side()
-        self.plan.unpack_grads(fg.data_ptr() + 4 * self.split, fg.data_ptr() + 4 * fg.numel())
-        self._early_work = dist.all_reduce(fg[self.split:self.opt.n_reduced], op=dist.ReduceOp.SUM, group=self.pg,
-                                           async_op=True)
+        self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
+        self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(fg[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            self.opt.step_range(lo, hi, grad_scale=1.0 / self.world)
 
     def _forward_loss(self):
         if self._windows is not None:
@@ -87,9 +107,11 @@ class TrainStep:
         lib().call("pcm_dropout_epoch_advance", torch.cuda.current_stream().cuda_stream)
         self.opt.zero_grad()
         fg = self.opt.flat_grad
-        overlap = self.split > 0
+        overlap = bool(self.buckets)
         if overlap:
-            ops._GRAD_HOOKS["encoder_boundary"] = self._early_bucket
+            self.opt.tick()                                   # one step-counter advance; Adam then runs per bucket
+            for name, lo, hi in self.buckets:
+                ops._GRAD_HOOKS[name] = (lambda lo=lo, hi=hi: self._bucket_ready(lo, hi))
         try:
             with ops.use_pack_plan(self.plan, self.side):
                 self.plan.repack()
@@ -97,19 +119,21 @@ class TrainStep:
                 loss.backward()
                 ops.join_side()
                 if overlap:
-                    self.plan.unpack_grads(fg.data_ptr(), fg.data_ptr() + 4 * self.split)
+                    lo, hi = self.tail_bucket
+                    self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
                 else:
                     self.plan.unpack_grads()
         finally:
-            ops._GRAD_HOOKS.pop("encoder_boundary", None)
+            for name, _, _ in self.buckets:
+                ops._GRAD_HOOKS.pop(name, None)
         if overlap:
-            dist.all_reduce(fg[:self.split], op=dist.ReduceOp.SUM, group=self.pg)
-            self._early_work.wait()
-            self._early_work = None
-            scale = 1.0 / self.world
+            lo, hi = self.tail_bucket
+            dist.all_reduce(fg[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            self.opt.step_range(lo, hi, grad_scale=1.0 / self.world)
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)     # the other buckets' updates are done
         else:
             scale = allreduce_flat_grads(fg, self.opt.n_reduced, self.pg)
-        self.opt.step(grad_scale=scale)
+            self.opt.step(grad_scale=scale)
         self.loss.copy_(loss.detach())
 
     def _snapshot(self):

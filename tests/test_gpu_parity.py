@@ -444,8 +444,13 @@ def test_kaggle_score_matches_unmodified_reference(G, golden_dir):
     with open(os.path.join(golden_dir, "kaggle_roundtrip.json")) as f:
         g = json.load(f)
     pred, true, lat, lon, names = KO.synth_submission(T=g["T"], seed=g["seed"])
-    sol = K.convert_predictions_to_kaggle_format(true, np.arange(g["T"]), lat, lon, names)
-    sub = K.convert_predictions_to_kaggle_format(pred, np.arange(g["T"]), lat, lon, names)
+    sol32 = K.convert_predictions_to_kaggle_format(true, np.arange(g["T"]), lat, lon, names)
+    sub32 = K.convert_predictions_to_kaggle_format(pred, np.arange(g["T"]), lat, lon, names)
+    # float32 columns (in memory): the reference's numpy reductions then run in float32 — agreement to float32 rounding
+    got = K.score(sol32, sub32, "ID")
+    assert abs(got - g["reference_score_float32_columns"]) / got < 2e-6, (got, g["reference_score_float32_columns"])
+    # float64 columns (what a scorer reads back from the submission CSV): agreement to fp64 rounding
+    sol, sub = sol32.astype({"Prediction": np.float64}), sub32.astype({"Prediction": np.float64})
     got = K.score(sol, sub, "ID")
     assert abs(got - g["reference_score"]) / g["reference_score"] < 1e-9, (got, g["reference_score"])
     perm = np.random.RandomState(3).permutation(len(sub))

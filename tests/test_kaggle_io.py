@@ -80,4 +80,5 @@ def test_unmodified_reference_score_on_our_rows():
     pred, true, lat, lon, names = KO.synth_submission(T=4, seed=7)
     sol = K.convert_predictions_to_kaggle_format(true, np.arange(4), lat, lon, names)
     sub = K.convert_predictions_to_kaggle_format(pred, np.arange(4), lat, lon, names)
+    sol, sub = sol.astype({"Prediction": np.float64}), sub.astype({"Prediction": np.float64})
     assert abs(float(R.score(sol, sub, "ID")) - _gold()["reference_score"]) < 1e-12
