@@ -106,6 +106,24 @@ PCM_API int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H,
  * gate pre-activations of the recurrent half never reach HBM.  wh: bf16 [9][4Ch][Ch]; Ch in {16,32,64}. */
 PCM_API int pcm_convlstm_step_tc(const void* h_prev, const void* wh, const float* gx, const float* c_prev,
                                  void* h_out, float* c_out, void* acts, int B, int H, int W, int Ch, pcm_stream_t s);
+/* Persistent ConvLSTM recurrence (src/convlstm.py:27-35): all T steps in ONE launch, forward, and the whole
+ * back-propagation through time in ONE launch.  A cluster of four CTAs owns two samples for all steps; CTA r keeps the
+ * Wh rows of hidden channels [16r, 16r+16) resident in shared memory, h_{t-1} lives in shared memory as a zero-ringed
+ * halo image (nine taps = nine row-shifted UMMA descriptors), the accumulator in TMEM, c / dc in registers; h_t (forward)
+ * and the K-split partial sums of dh_{t-1} (backward) are exchanged through distributed shared memory, one cluster
+ * barrier per step.  Ch = 64, bf16, (H-1)*(W+2) + W <= 64 (pcm_convlstm_seq_supported).
+ *   gx     fp32 [T][B][H*W][4*Ch]  Wx.x + bias for every step (one batched pcm_conv3x3_tc launch)
+ *   wh     bf16 [9][4*Ch][Ch]      recurrent half of the gate weight, forward packing
+ *   h_all  bf16 [T][B][H*W][Ch], c_all fp32 [T][B][H*W][Ch], acts bf16 [T][B][H*W][4*Ch]   (outputs; gate order i,f,o,g)
+ *   dh_ext bf16: gradient w.r.t. h of every step [T][B][H*W][Ch] (ext_all_steps = 1) or of the last step only [B][H*W][Ch]
+ *   wht    bf16 [9][Ch][4*Ch]      data-gradient packing of the recurrent half (taps flipped)
+ *   dgates bf16 [T][B][H*W][4*Ch]  (output) gradient w.r.t. the gate pre-activations of every step */
+PCM_API int pcm_convlstm_seq_supported(int H, int W, int Ch);
+PCM_API int pcm_convlstm_seq_fwd_tc(const float* gx, const void* wh, void* h_all, float* c_all, void* acts, int T, int B,
+                                    int H, int W, int Ch, pcm_stream_t s);
+PCM_API int pcm_convlstm_seq_bwd_tc(const void* dh_ext, int ext_all_steps, const void* acts, const float* c_all,
+                                    const void* wht, void* dgates, int T, int B, int H, int W, int Ch, pcm_stream_t s);
+
 /* Tensor-core weight gradient of the same convolution (GEMM over the pixel dimension, MN-major operands
  * straight from NHWC, all taps from ONE halo tile): dw[co*sa + ci*sb + tap*st] += sum_p dy(p,co)*x(p+tap,ci).
  * dy: Co in {16,32,64,128k}; x: Ci in {16,32,64,128,192,256}; only co < Co_real, ci < Ci_real are written.

