@@ -31,6 +31,17 @@ namespace pcm {
 
 using namespace tc;
 
+// -DPCM_SEQ_PROFILE: thread 0 of cluster 0 / CTA 0 accumulates clock64 deltas per phase and prints them at exit
+#ifdef PCM_SEQ_PROFILE
+#define SEQ_PROF_DECL long long prof_t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_c = clock64(); const bool prof_on = blockIdx.x == 0 && threadIdx.x == 0
+#define SEQ_PROF(i) do { if (prof_on) { const long long c_ = clock64(); prof_t[i] += c_ - prof_c; prof_c = c_; } } while (0)
+#define SEQ_PROF_PRINT(name) do { if (prof_on) printf("%s phases (cycles): %lld %lld %lld %lld %lld %lld %lld %lld\n", name, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6], prof_t[7]); if (prof_on) printf("   prologue: zero/init %lld weights %lld\n", prof_t[8], prof_t[9]); } while (0)
+#else
+#define SEQ_PROF_DECL
+#define SEQ_PROF(i)
+#define SEQ_PROF_PRINT(name)
+#endif
+
 constexpr int kSeqThreads = 192;      // warps 0,1: epilogue of sample 0 (TMEM lanes 0-63); 4,5: sample 1; 2: MMA issuer
 constexpr int kSeqCh = 64;
 constexpr int kSeqCluster = 4;
@@ -117,6 +128,7 @@ convlstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __res
   const uint32_t r = cluster_ctarank();
   const int pair = blockIdx.x / kSeqCluster;
   const int Ch = kSeqCh, G = 4 * kSeqCh;
+  SEQ_PROF_DECL;
 
   {  // zero both buffers of both halo images (the ring and the slack rows must read as zero)
     uint4* z = reinterpret_cast<uint4*>(sA);
@@ -129,13 +141,26 @@ convlstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __res
   }
   if (warp == 2) tmem_alloc(tmem_slot, 128);
   pdl_wait();                       // predecessor complete: global memory may be touched from here on
-  // resident weight slice: gate q, hidden channel 16r + j  ->  B row q*16 + j  (all 64 input channels, 9 taps)
-  for (int i = threadIdx.x; i < 9 * 64 * 8; i += blockDim.x) {
-    const int chunk = i & 7, n = (i >> 3) & 63, tap = i >> 9;
-    const int grow = (n >> 4) * Ch + (int)r * 16 + (n & 15);
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wh + ((size_t)tap * G + grow) * Ch) + chunk);
-    *reinterpret_cast<uint4*>(sB + tap * 8192 + sw128(n, chunk)) = v;
+  SEQ_PROF(8);
+  // resident weight slice: gate q, hidden channel 16r + j  ->  B row q*16 + j  (all 64 input channels, 9 taps);
+  // eight 16-byte loads in flight per thread (the loop is latency-bound otherwise: 24 dependent round trips)
+  for (int i0 = threadIdx.x; i0 < 9 * 64 * 8; i0 += 8 * kSeqThreads) {
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * kSeqThreads;
+      const int chunk = i & 7, n = (i >> 3) & 63, tap = i >> 9;
+      const int grow = (n >> 4) * Ch + (int)r * 16 + (n & 15);
+      if (i < 9 * 64 * 8) v[k] = __ldg(reinterpret_cast<const uint4*>(wh + ((size_t)tap * G + grow) * Ch) + chunk);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * kSeqThreads;
+      const int chunk = i & 7, n = (i >> 3) & 63, tap = i >> 9;
+      if (i < 9 * 64 * 8) *reinterpret_cast<uint4*>(sB + tap * 8192 + sw128(n, chunk)) = v[k];
+    }
   }
+  SEQ_PROF(9);
   fence_async_proxy();
   tc_fence_before();
   cluster_sync_all();               // every CTA of the cluster has zeroed its images before anyone writes into them
@@ -157,6 +182,7 @@ convlstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __res
   const long long BP = (long long)p.B * p.P;
 
   bool ok = true;
+  SEQ_PROF(0);                      // 0: first cluster barrier
   for (int t = 0; t < p.T; ++t) {      // every thread runs every step (cluster barriers); a timed-out wait only skips work
     if (warp == 2 && t > 0) {
       if (elect_one()) {
@@ -189,9 +215,11 @@ convlstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __res
 #pragma unroll
         for (int j = 0; j < 16; ++j) gi[j] = gf[j] = go[j] = gg[j] = 0.f;
       }
+      SEQ_PROF(1);                  // 1: gx loads issued
       if (t > 0) {
         ok = mbar_wait(&mma_done[s], (uint32_t)((t - 1) & 1), err) && ok;
         ok = __all_sync(0xffffffffu, ok);
+        SEQ_PROF(2);                // 2: waiting for the MMAs
         if (ok) {
           tc_fence_after();
           const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * 64u;
@@ -211,6 +239,7 @@ convlstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __res
           tc_fence_before();
         }
       }
+      SEQ_PROF(3);                  // 3: TMEM loads
       if (ok && valid) {
         // i,f,o = sigmoid, g = tanh ; c' = f*c + i*g ; h' = o*tanh(c')  (src/convlstm.py:14-18); same one-instruction
         // tanh.approx forms and bf16 rounding of the saved activations as the per-step kernel (conv_tc.cu, EPI == 1)
@@ -249,13 +278,16 @@ convlstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __res
         }
       }
     }
+    SEQ_PROF(4);                    // 4: cell math, global stores, DSMEM stores
     if (t + 1 < p.T) {
       fence_async_proxy();          // the halo-image writes (generic proxy) will be read by the tensor core's async proxy
       tc_fence_before();
       cluster_sync_all();
       tc_fence_after();
     }
+    SEQ_PROF(5);                    // 5: fence + cluster barrier
   }
+  SEQ_PROF_PRINT("convlstm_seq_fwd");
   tc_fence_before();
   cluster_sync_all();               // no CTA leaves while a peer could still write into its shared memory
   if (warp == 2) {
@@ -285,6 +317,7 @@ convlstm_seq_bwd_kernel(const __nv_bfloat16* __restrict__ dh_ext, const __nv_bfl
   const uint32_t r = cluster_ctarank();
   const int pair = blockIdx.x / kSeqCluster;
   const int Ch = kSeqCh, G = 4 * kSeqCh;
+  SEQ_PROF_DECL;
 
   {
     uint4* z = reinterpret_cast<uint4*>(sA);
@@ -297,14 +330,27 @@ convlstm_seq_bwd_kernel(const __nv_bfloat16* __restrict__ dh_ext, const __nv_bfl
   }
   if (warp == 2) tmem_alloc(tmem_slot, 128);
   pdl_wait();                       // predecessor complete: global memory may be touched from here on
+  SEQ_PROF(8);
   // resident weight slice of the data-gradient convolution: wht[tap][n = hidden channel][k = gate channel] (taps
   // flipped by the packer); this CTA's K = gate q, channel 16r + j  ->  k' = q*16 + j
-  for (int i = threadIdx.x; i < 9 * 64 * 8; i += blockDim.x) {
-    const int chunk = i & 7, nn = (i >> 3) & 63, tap = i >> 9;
-    const int q = chunk >> 1, half = chunk & 1;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wht + ((size_t)tap * Ch + nn) * G + q * Ch + (int)r * 16 + half * 8));
-    *reinterpret_cast<uint4*>(sB + tap * 8192 + sw128(nn, chunk)) = v;
+  for (int i0 = threadIdx.x; i0 < 9 * 64 * 8; i0 += 8 * kSeqThreads) {
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * kSeqThreads;
+      const int chunk = i & 7, nn = (i >> 3) & 63, tap = i >> 9;
+      const int q = chunk >> 1, half = chunk & 1;
+      if (i < 9 * 64 * 8)
+        v[k] = __ldg(reinterpret_cast<const uint4*>(wht + ((size_t)tap * Ch + nn) * G + q * Ch + (int)r * 16 + half * 8));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * kSeqThreads;
+      const int chunk = i & 7, nn = (i >> 3) & 63, tap = i >> 9;
+      if (i < 9 * 64 * 8) *reinterpret_cast<uint4*>(sB + tap * 8192 + sw128(nn, chunk)) = v[k];
+    }
   }
+  SEQ_PROF(9);
   fence_async_proxy();
   tc_fence_before();
   cluster_sync_all();
@@ -324,37 +370,62 @@ convlstm_seq_bwd_kernel(const __nv_bfloat16* __restrict__ dh_ext, const __nv_bfl
 #pragma unroll
   for (int j = 0; j < 16; ++j) dcs[j] = dhn[j] = 0.f;
 
+  // operands of the cell backward of one step, as loaded: 4 x 16 activations (bf16), c_t, c_{t-1}, external dh_t.  The
+  // loads of step t-1 are issued while the tensor core works on step t and the cluster exchanges partial sums.
+  uint4 ra[8], re[2];
+  float4 rc[4], rp[4];
+  auto load_step = [&](int t) {
+    if (!valid) return;
+    const long long row = (long long)t * BP + pix;
+    const __nv_bfloat16* ap = acts + row * G + r * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ra[2 * q] = __ldg(reinterpret_cast<const uint4*>(ap + q * Ch));
+      ra[2 * q + 1] = __ldg(reinterpret_cast<const uint4*>(ap + q * Ch) + 1);
+    }
+    const float4* cq = reinterpret_cast<const float4*>(c_all + row * Ch + r * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rc[j] = __ldg(cq + j);
+    if (t > 0) {
+      const float4* cr = reinterpret_cast<const float4*>(c_all + (row - BP) * Ch + r * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rp[j] = __ldg(cr + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (p.ext_all || t == p.T - 1) {
+      const uint4* ep = reinterpret_cast<const uint4*>(dh_ext + ((p.ext_all ? row : pix) * Ch + r * 16));
+      re[0] = __ldg(ep); re[1] = __ldg(ep + 1);
+    } else {
+      re[0] = re[1] = make_uint4(0, 0, 0, 0);
+    }
+  };
+  load_step(p.T - 1);
+
   bool ok = true;
   int par = 0;
+  SEQ_PROF(0);                      // 0: first cluster barrier, first operand loads issued
   for (int t = p.T - 1; t >= 0; --t) {
     if (valid) {
       // ---- cell backward at step t for this pixel's 16 channels (same arithmetic as lstm_cell_bwd_kernel)
       const long long row = (long long)t * BP + pix;
       float dh[16], cc[16], cp[16], gi[16], gf[16], go[16], gg[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { dh[j] = dhn[j]; cp[j] = 0.f; }
-      if (p.ext_all || t == p.T - 1) {
-        const uint4* ep = reinterpret_cast<const uint4*>(dh_ext + ((p.ext_all ? row : pix) * Ch + r * 16));
-        float e[16];
-        unpack8_bf16(__ldg(ep), e); unpack8_bf16(__ldg(ep + 1), e + 8);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dh[j] += e[j];
-      }
       {
-        const float4* cq = reinterpret_cast<const float4*>(c_all + row * Ch + r * 16);
+        float e[16];
+        unpack8_bf16(re[0], e); unpack8_bf16(re[1], e + 8);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float4 v = __ldg(cq + j); cc[4 * j] = v.x; cc[4 * j + 1] = v.y; cc[4 * j + 2] = v.z; cc[4 * j + 3] = v.w; }
-        if (t > 0) {
-          const float4* cr = reinterpret_cast<const float4*>(c_all + (row - BP) * Ch + r * 16);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { const float4 v = __ldg(cr + j); cp[4 * j] = v.x; cp[4 * j + 1] = v.y; cp[4 * j + 2] = v.z; cp[4 * j + 3] = v.w; }
-        }
-        const __nv_bfloat16* ap = acts + row * G + r * 16;
-        unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap)), gi); unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap) + 1), gi + 8);
-        unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap + Ch)), gf); unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap + Ch) + 1), gf + 8);
-        unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap + 2 * Ch)), go); unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap + 2 * Ch) + 1), go + 8);
-        unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap + 3 * Ch)), gg); unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ap + 3 * Ch) + 1), gg + 8);
+        for (int j = 0; j < 16; ++j) dh[j] = dhn[j] + e[j];
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cc[4 * j] = rc[j].x; cc[4 * j + 1] = rc[j].y; cc[4 * j + 2] = rc[j].z; cc[4 * j + 3] = rc[j].w;
+        cp[4 * j] = rp[j].x; cp[4 * j + 1] = rp[j].y; cp[4 * j + 2] = rp[j].z; cp[4 * j + 3] = rp[j].w;
+      }
+      unpack8_bf16(ra[0], gi); unpack8_bf16(ra[1], gi + 8);
+      unpack8_bf16(ra[2], gf); unpack8_bf16(ra[3], gf + 8);
+      unpack8_bf16(ra[4], go); unpack8_bf16(ra[5], go + 8);
+      unpack8_bf16(ra[6], gg); unpack8_bf16(ra[7], gg + 8);
       float di[16], df[16], dO[16], dg[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -381,11 +452,13 @@ convlstm_seq_bwd_kernel(const __nv_bfloat16* __restrict__ dh_ext, const __nv_bfl
         for (uint32_t c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(a + sw128(arow, c)) = u[c];
       }
     }
+    SEQ_PROF(1);                    // 1: cell backward, dgates stores
     if (t == 0) break;
     // ---- dh_{t-1} = conv(dgates_t, flipped Wh^T): this CTA's K slice -> partial sums for all 64 hidden channels
     fence_async_proxy();
     tc_fence_before();
     __syncthreads();
+    SEQ_PROF(2);                    // 2: fence + CTA barrier
     if (warp == 2) {
       if (elect_one()) {
         tc_fence_after();
@@ -396,9 +469,11 @@ convlstm_seq_bwd_kernel(const __nv_bfloat16* __restrict__ dh_ext, const __nv_bfl
       }
       __syncwarp();
     }
+    load_step(t - 1);               // next step's operands: in flight during the MMAs and the cluster exchange
     if (is_epi) {
       ok = mbar_wait(&mma_done[s], (uint32_t)((p.T - 1 - t) & 1), err) && ok;
       ok = __all_sync(0xffffffffu, ok);
+      SEQ_PROF(3);                  // 3: waiting for the MMAs
       if (ok) {
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * 64u;
@@ -417,7 +492,9 @@ convlstm_seq_bwd_kernel(const __nv_bfloat16* __restrict__ dh_ext, const __nv_bfl
         tc_fence_before();
       }
     }
+    SEQ_PROF(4);                    // 4: TMEM loads + DSMEM stores of the partial sums
     cluster_sync_all();             // all four partial sums of this step have landed in every CTA
+    SEQ_PROF(5);                    // 5: cluster barrier
     if (is_epi) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) dhn[j] = 0.f;
@@ -432,7 +509,9 @@ convlstm_seq_bwd_kernel(const __nv_bfloat16* __restrict__ dh_ext, const __nv_bfl
       }
     }
     par ^= 1;
+    SEQ_PROF(6);                    // 6: summing the four partials
   }
+  SEQ_PROF_PRINT("convlstm_seq_bwd");
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) {
