@@ -286,13 +286,18 @@ PCM_API int pcm_dropout(const void* x, void* y, long long n, float p, long long 
 PCM_API int pcm_dropout_mask(float* mask, long long n, float p, long long seed, pcm_stream_t s);
 
 /* ---- transformer encoder layer (src/cnn_transformer.py:25-31; post-norm, batch_first) ---------------------
- * y = LayerNorm(a + b)*gamma + beta over the last dim E (eps inside sqrt); sum_out = a + b (nullable) and
- * stat[m] = (mean, rstd) are saved for backward.  b nullable. */
+ * y = LayerNorm(a + dropout(b))*gamma + beta over the last dim E (eps inside sqrt); sum_out = a + dropout(b) (nullable)
+ * and stat[m] = (mean, rstd) are saved for backward.  b nullable.  drop_p > 0 applies nn.Dropout's counter-based mask
+ * (stream `seed`, element m*E + c — the mask pcm_dropout draws) to b on the fly: dropout -> residual add -> LayerNorm of
+ * the post-norm encoder layer in one pass. */
 PCM_API int pcm_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* sum_out,
-                                  void* y, float* stat, int M, int E, float eps, int dtype, pcm_stream_t s);
-/* ds (gradient of a + b); dgamma, dbeta accumulate */
+                                  void* y, float* stat, int M, int E, float eps, float drop_p, long long seed, int dtype,
+                                  pcm_stream_t s);
+/* ds (gradient of a + dropout(b), i.e. of a); with drop_p > 0 also db = dropout(ds) (gradient of b, same mask); dgamma,
+ * dbeta accumulate */
 PCM_API int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float* stat, const float* gamma, void* ds,
-                              float* dgamma, float* dbeta, int M, int E, int dtype, pcm_stream_t s);
+                              void* db, float* dgamma, float* dbeta, int M, int E, float drop_p, long long seed, int dtype,
+                              pcm_stream_t s);
 /* multi-head self-attention core of nn.MultiheadAttention: qkv [B][L][3*nh*D] (q | k | v; head h = columns
  * h*D..), out [B][L][nh*D] = softmax(scale * q k^T) v per head, lse [B][nh][L] fp32 saved for backward.
  * drop_p: dropout on the attention probabilities (counter-based mask from `seed`).  D in {8, 16, 32, 64}. */

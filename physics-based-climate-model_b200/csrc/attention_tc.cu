@@ -20,11 +20,7 @@ constexpr int kAttThreads = 320;     // warp 0: TMA, warp 1: MMA issuer, warps 2
 constexpr int kAttD = 32;
 
 __device__ __forceinline__ float att_hash_uniform(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  return dropout_uniform(seed, idx);      // common.cuh: one definition for every mask-drawing kernel
 }
 
 struct AttParams {

@@ -9,12 +9,7 @@ constexpr int kBnThreads = 256;
 constexpr int kBnGridCap = 148 * 8;
 
 __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
-  // splitmix64 finalizer over (seed, idx): counter-based, so backward regenerates the same mask
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  return dropout_uniform(seed, idx);      // common.cuh: one definition for every mask-drawing kernel
 }
 
 // sums[c][0] += sum_r x(r,c); sums[c][1] += sum_r x(r,c)^2          (caller zeroes sums)

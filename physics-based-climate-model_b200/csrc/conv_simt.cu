@@ -395,10 +395,75 @@ extern "C" int pcm_conv_wgrad(const void* A, long long a_ns, int a_ps, int Ha, i
   return check_launch("conv_wgrad");
 }
 
+namespace pcm {
+// Column sums of a [rows = N*P][C] view (bias gradients: out[c] += sum over all pixels).  A CTA owns a block of up to 64
+// channels (8 vectors of 8) and a chunk of rows: 32 row lanes x 8 channel vectors, every warp reads whole 128-byte row
+// segments; each thread accumulates its 8 channels in registers over its rows, the 32 row lanes are then combined
+// through shared memory and ONE global atomic per channel leaves the CTA.  (The general kernel above walks a flat
+// vector index: with C/8 not a power of two every iteration flushed through shared-memory atomics, and its 592 CTAs
+// each sent C global atomics — 25 us for 10 MB at C = 384.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_sum_rows_kernel(const T* __restrict__ x, long long ns, int ps, int P, long long rows, int C, int C_real,
+                        float* __restrict__ out, int rows_per_cta) {
+  PCM_PDL_ENTRY();
+  __shared__ float sm[32][65];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int cb = blockIdx.x * 8 + tx;                     // channel vector
+  const bool live = cb * 8 < C;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (live) {
+    long long r = r0 + ty;
+    // two rows in flight per thread
+    for (; r + 32 < r1; r += 64) {
+      float a[8], b[8];
+      const long long ra = r, rb = r + 32;
+      load8(x + (ra / P) * ns + (ra % P) * (long long)ps + cb * 8, a);
+      load8(x + (rb / P) * ns + (rb % P) * (long long)ps + cb * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j] + b[j];
+    }
+    for (; r < r1; r += 32) {
+      float a[8];
+      load8(x + (r / P) * ns + (r % P) * (long long)ps + cb * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    float t = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
+    if (c < C_real) atomicAdd(out + c, t);
+  }
+}
+}  // namespace pcm
+
 extern "C" int pcm_channel_sum(const void* x, long long ns, int ps, int N, int P, int C, int C_real, float* out,
                                int per_image, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(C % 8 == 0, "channel_sum: C must be a multiple of 8");
   if (N == 0) return PCM_OK;
+  if (!per_image) {
+    const long long rows = (long long)N * P;
+    const int cblocks = (C / 8 + 7) / 8;
+    // ~4 CTAs per SM in total, at least 64 rows per CTA
+    long long chunks = (148 * 4 + cblocks - 1) / cblocks;
+    if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
+    if (chunks < 1) chunks = 1;
+    const int rows_per_cta = (int)((rows + chunks - 1) / chunks);
+    dim3 grid(cblocks, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(pcm::channel_sum_rows_kernel<T>, grid, 256, 0, (cudaStream_t)s,
+                                     (const T*)x, ns, ps, P, rows, C, C_real, out, rows_per_cta)));
+    return check_launch("channel_sum");
+  }
   const long long total = per_image ? (long long)P * (C / 8) : (long long)N * P * (C / 8);
   int bx = (int)min((long long)592, (total + 255) / 256);
   if (per_image) bx = (int)min((long long)max(1, 592 / N), (total + 1023) / 1024);

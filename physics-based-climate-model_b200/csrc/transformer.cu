@@ -7,58 +7,76 @@
 namespace pcm {
 
 __device__ __forceinline__ float hash_uniform_t(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  return dropout_uniform(seed, idx);      // common.cuh: one definition for every mask-drawing kernel
 }
 
 constexpr int kLnMaxVec = 4;   // E <= 32 lanes * 4 vectors * 8 = 1024
 
 // y = LN(a + b) * gamma + beta ; sum_out = a + b (saved for backward) ; stat[m] = (mean, rstd).  One warp per row.
+// LayerNorm(a + dropout(b)) over the last dim.  A token's E/8 vectors are spread over `tl` = min(32, E/8) lanes, so a
+// warp processes 32/tl tokens at once (E = 128: two tokens per warp, every lane busy).  drop_p > 0: b goes through
+// nn.Dropout's counter-based mask (element index m*E + c of stream `seed`, the same mask pcm_dropout draws), so
+// the transformer layer's dropout -> residual add -> LayerNorm is ONE pass.
 template <typename T>
 __global__ void __launch_bounds__(256)
 add_layernorm_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ gamma,
                          const float* __restrict__ beta, T* __restrict__ sum_out, T* __restrict__ y,
-                         float* __restrict__ stat, int M, int E, float eps) {
+                         float* __restrict__ stat, int M, int E, float eps, float drop_p, unsigned long long seed,
+                         const unsigned long long* __restrict__ epoch) {
   PCM_PDL_ENTRY();
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int nv = E / 8;
-  for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
+  const int tl = nv < 32 ? nv : 32;                 // lanes per token (power of two)
+  const int tpw = 32 / tl;                          // tokens per warp
+  const int lane = threadIdx.x & 31, sub = lane / tl, l = lane - sub * tl;
+  const int wpb = blockDim.x >> 5;
+  const float keep_sc = 1.f / (1.f - drop_p);
+  if (drop_p > 0.f) seed = mix_epoch(seed, epoch);
+  for (int m0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * tpw; m0 < M; m0 += gridDim.x * wpb * tpw) {
+    const int m = m0 + sub;
+    const bool tok = m < M;
     float v[kLnMaxVec][8];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < kLnMaxVec; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < nv) {
+      const int vi = l + tl * k;
+      if (vi < nv && tok) {
         load8(a + (long long)m * E + vi * 8, v[k]);
         if (b != nullptr) {
           float t[8];
           load8(b + (long long)m * E + vi * 8, t);
+          if (drop_p > 0.f) {
+            const unsigned long long i0 = (unsigned long long)m * E + vi * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = dropout_uniform(seed, i0 + j) >= drop_p ? round_to<T>(t[j] * keep_sc) : 0.f;
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[k][j] = round_to<T>(v[k][j] + t[j]);
         }
         if (sum_out != nullptr) store8(sum_out + (long long)m * E + vi * 8, v[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[k][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
       }
     }
-    const float mean = warp_sum(s) / (float)E;
+    for (int o = tl >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)E;
     float q = 0.f;
 #pragma unroll
     for (int k = 0; k < kLnMaxVec; ++k) {
-      if (lane + 32 * k < nv) {
+      if (l + tl * k < nv) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q = fmaf(d, d, q); }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
-    if (lane == 0) { stat[2 * m] = mean; stat[2 * m + 1] = rstd; }
+    for (int o = tl >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)E + eps);
+    if (l == 0 && tok) { stat[2 * m] = mean; stat[2 * m + 1] = rstd; }
 #pragma unroll
     for (int k = 0; k < kLnMaxVec; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < nv) {
+      const int vi = l + tl * k;
+      if (vi < nv && tok) {
         float g[8], bt[8], o[8];
         load8(gamma + vi * 8, g);
         load8(beta + vi * 8, bt);
@@ -70,39 +88,51 @@ add_layernorm_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const
   }
 }
 
-// ds = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma ; dgamma += sum dy*xhat ; dbeta += sum dy
+// ds = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma ; dgamma += sum dy*xhat ; dbeta += sum dy.
+// drop_p > 0: additionally db = dropout(ds) with the forward's mask (the gradient of the dropped sub-layer output), so
+// the separate dropout launch of the backward disappears too.  Same token-per-sub-warp mapping as the forward; the
+// per-channel sums are reduced through per-warp shared-memory rows (no shared-memory atomics).
 template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ sum_in, const float* __restrict__ stat,
-                     const float* __restrict__ gamma, T* __restrict__ ds, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, int M, int E) {
+                     const float* __restrict__ gamma, T* __restrict__ ds, T* __restrict__ db, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int M, int E, float drop_p, unsigned long long seed,
+                     const unsigned long long* __restrict__ epoch) {
   PCM_PDL_ENTRY();
-  extern __shared__ float sh[];     // [2][E]
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  extern __shared__ float sh[];     // [warps][2][E]
   const int nv = E / 8;
-  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  float ag[kLnMaxVec][8], ab[kLnMaxVec][8];
+  const int tl = nv < 32 ? nv : 32, tpw = 32 / tl;
+  const int lane = threadIdx.x & 31, sub = lane / tl, l = lane - sub * tl;
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const float keep_sc = 1.f / (1.f - drop_p);
+  if (drop_p > 0.f) seed = mix_epoch(seed, epoch);
+  float ag[kLnMaxVec][8], ab[kLnMaxVec][8], gm[kLnMaxVec][8];
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k)
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int vi = l + tl * k;
+    if (vi < nv) load8(gamma + vi * 8, gm[k]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = 0.f;
-  for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
-    const float mean = stat[2 * m], rstd = stat[2 * m + 1];
+  }
+  for (int m0 = (blockIdx.x * wpb + warp) * tpw; m0 < M; m0 += gridDim.x * wpb * tpw) {
+    const int m = m0 + sub;
+    const bool tok = m < M;
+    const float mean = tok ? stat[2 * m] : 0.f, rstd = tok ? stat[2 * m + 1] : 0.f;
     float g[kLnMaxVec][8], xh[kLnMaxVec][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < kLnMaxVec; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < nv) {
-        float d[8], x[8], gm[8];
+      const int vi = l + tl * k;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[k][j] = xh[k][j] = 0.f;
+      if (vi < nv && tok) {
+        float d[8], x[8];
         load8(dy + (long long)m * E + vi * 8, d);
         load8(sum_in + (long long)m * E + vi * 8, x);
-        load8(gamma + vi * 8, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[k][j] = (x[j] - mean) * rstd;
-          g[k][j] = d[j] * gm[j];
+          g[k][j] = d[j] * gm[k][j];
           s1 += g[k][j];
           s2 = fmaf(g[k][j], xh[k][j], s2);
           ag[k][j] = fmaf(d[j], xh[k][j], ag[k][j]);
@@ -110,34 +140,59 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ sum_in, con
         }
       }
     }
-    s1 = warp_sum(s1) / (float)E;
-    s2 = warp_sum(s2) / (float)E;
+    for (int o = tl >> 1; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 /= (float)E;
+    s2 /= (float)E;
 #pragma unroll
     for (int k = 0; k < kLnMaxVec; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < nv) {
+      const int vi = l + tl * k;
+      if (vi < nv && tok) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2);
         store8(ds + (long long)m * E + vi * 8, o);
+        if (db != nullptr) {
+          const unsigned long long i0 = (unsigned long long)m * E + vi * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = dropout_uniform(seed, i0 + j) >= drop_p ? round_to<T>(o[j]) * keep_sc : 0.f;
+          store8(db + (long long)m * E + vi * 8, o);
+        }
       }
     }
   }
+  // per-channel sums: combine the sub-warp token groups with shuffles, one shared-memory row per warp, then one
+  // thread per channel adds the rows and issues a single global atomic
+  for (int o = tl; o < 32; o <<= 1) {
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < nv) {
+    for (int k = 0; k < kLnMaxVec; ++k)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sh[vi * 8 + j], ag[k][j]);
-        atomicAdd(&sh[E + vi * 8 + j], ab[k][j]);
+        ag[k][j] += __shfl_xor_sync(0xffffffffu, ag[k][j], o);
+        ab[k][j] += __shfl_xor_sync(0xffffffffu, ab[k][j], o);
+      }
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int vi = l + tl * k;
+      if (vi < nv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sh[(warp * 2 + 0) * E + vi * 8 + j] = ag[k][j];
+          sh[(warp * 2 + 1) * E + vi * 8 + j] = ab[k][j];
+        }
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    atomicAdd(dgamma + i, sh[i]);
-    atomicAdd(dbeta + i, sh[E + i]);
+  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) {
+    const int which = i / E, c = i - which * E;
+    float t = 0.f;
+    for (int w = 0; w < wpb; ++w) t += sh[(w * 2 + which) * E + c];
+    atomicAdd((which ? dbeta : dgamma) + c, t);
   }
 }
 
@@ -383,27 +438,45 @@ static int set_smem(K kern, size_t bytes, const char* what) {
 
 using namespace pcm;
 
+static bool ln_shape_ok(int E) {
+  const int nv = E / 8;
+  return E % 8 == 0 && E >= 8 && E <= 32 * kLnMaxVec * 8 && (nv >= 32 || (nv & (nv - 1)) == 0);
+}
+
 extern "C" int pcm_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* sum_out,
-                                     void* y, float* stat, int M, int E, float eps, int dtype, pcm_stream_t s) {
-  PCM_REQUIRE(E % 8 == 0 && E >= 8 && E <= 32 * kLnMaxVec * 8, "add_layernorm_fwd: E must be a multiple of 8, <= 1024 (got %d)", E);
+                                     void* y, float* stat, int M, int E, float eps, float drop_p, long long seed,
+                                     int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(ln_shape_ok(E), "add_layernorm_fwd: E must be 8..256 (power of two) or a multiple of 256 up to 1024 (got %d)", E);
+  PCM_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || b != nullptr), "add_layernorm_fwd: 0 <= drop_p < 1, dropout needs b");
   if (M == 0) return PCM_OK;
-  int grid = ceil_div(M, 8);
+  const int nv = E / 8, tpw = nv < 32 ? 32 / nv : 1;
+  int grid = ceil_div(M, 8 * tpw);
   if (grid > 148 * 8) grid = 148 * 8;
-  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(add_layernorm_fwd_kernel<T>, grid, 256, 0, (cudaStream_t)s, 
+  const unsigned long long* epoch = dropout_epoch_cell();
+  PCM_REQUIRE(epoch != nullptr, "add_layernorm_fwd: could not allocate the dropout epoch cell");
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(add_layernorm_fwd_kernel<T>, grid, 256, 0, (cudaStream_t)s,
                                    static_cast<const T*>(a), static_cast<const T*>(b), gamma, beta, static_cast<T*>(sum_out),
-                                   static_cast<T*>(y), stat, M, E, eps)));
+                                   static_cast<T*>(y), stat, M, E, eps, drop_p, (unsigned long long)seed, epoch)));
   return check_launch("add_layernorm_fwd");
 }
 
 extern "C" int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float* stat, const float* gamma, void* ds,
-                                 float* dgamma, float* dbeta, int M, int E, int dtype, pcm_stream_t s) {
-  PCM_REQUIRE(E % 8 == 0 && E >= 8 && E <= 32 * kLnMaxVec * 8, "layernorm_bwd: E must be a multiple of 8, <= 1024 (got %d)", E);
+                                 void* db, float* dgamma, float* dbeta, int M, int E, float drop_p, long long seed,
+                                 int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(ln_shape_ok(E), "layernorm_bwd: E must be 8..256 (power of two) or a multiple of 256 up to 1024 (got %d)", E);
+  PCM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: 0 <= drop_p < 1");
+  PCM_REQUIRE(E <= 768, "layernorm_bwd: E up to 768 (per-warp reduction rows in shared memory), got %d", E);
   if (M == 0) return PCM_OK;
-  int grid = ceil_div(M, 8 * 8);
-  if (grid > 148 * 2) grid = 148 * 2;
-  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(layernorm_bwd_kernel<T>, grid, 256, 2 * E * sizeof(float), (cudaStream_t)s, 
+  const int nv = E / 8, tpw = nv < 32 ? 32 / nv : 1;
+  // two token groups per warp on average: enough CTAs to fill the machine, few enough global atomics (2E per CTA)
+  int grid = ceil_div(M, 8 * tpw * 2);
+  if (grid > 148 * 4) grid = 148 * 4;
+  const unsigned long long* epoch = dropout_epoch_cell();
+  PCM_REQUIRE(epoch != nullptr, "layernorm_bwd: could not allocate the dropout epoch cell");
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(layernorm_bwd_kernel<T>, grid, 256, 8 * 2 * E * sizeof(float), (cudaStream_t)s,
                                    static_cast<const T*>(dy), static_cast<const T*>(sum_in), stat, gamma, static_cast<T*>(ds),
-                                   dgamma, dbeta, M, E)));
+                                   drop_p > 0.f ? static_cast<T*>(db) : nullptr, dgamma, dbeta, M, E, drop_p,
+                                   (unsigned long long)seed, epoch)));
   return check_launch("layernorm_bwd");
 }
 

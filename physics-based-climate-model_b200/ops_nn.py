@@ -481,10 +481,12 @@ class LinearFn(torch.autograd.Function):
 
 
 class AddLayerNormFn(torch.autograd.Function):
-    """LayerNorm(a + b) over the last dim (post-norm residual, eps 1e-5)."""
+    """LayerNorm(a + dropout_p(b)) over the last dim (post-norm residual, eps 1e-5).  The sub-layer dropout
+    (`dropout1` / `dropout2` of nn.TransformerEncoderLayer) is applied to b inside the kernel, and the backward kernel
+    emits both gradients (of a, and of b = the same mask applied to it)."""
 
     @staticmethod
-    def forward(ctx, a, b, gamma, beta):
+    def forward(ctx, a, b, gamma, beta, drop_p=0.0, seed=0):
         a, b = a.contiguous(), b.contiguous()
         E = a.shape[-1]
         M = a.numel() // E
@@ -492,22 +494,25 @@ class AddLayerNormFn(torch.autograd.Function):
         y = torch.empty_like(a)
         stat = torch.empty(M * 2, device=a.device, dtype=torch.float32)
         _call("pcm_add_layernorm_fwd", a.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(), s.data_ptr(),
-              y.data_ptr(), stat.data_ptr(), M, E, LN_EPS, _DT[a.dtype], _s())
+              y.data_ptr(), stat.data_ptr(), M, E, LN_EPS, float(drop_p), int(seed), _DT[a.dtype], _s())
         ctx.save_for_backward(s, stat, gamma, beta)
+        ctx.drop = (float(drop_p), int(seed))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         s, stat, gamma, beta = ctx.saved_tensors
+        drop_p, seed = ctx.drop
         E = s.shape[-1]
         M = s.numel() // E
         dy = dy.contiguous()
         gg, rg = _grad_buf(gamma)
         gb, rb = _grad_buf(beta)
         ds = torch.empty_like(s)
+        db = torch.empty_like(s) if drop_p > 0.0 else ds
         _call("pcm_layernorm_bwd", dy.data_ptr(), s.data_ptr(), stat.data_ptr(), gamma.data_ptr(), ds.data_ptr(),
-              gg.data_ptr(), gb.data_ptr(), M, E, _DT[s.dtype], _s())
-        return ds, ds, rg, rb
+              db.data_ptr(), gg.data_ptr(), gb.data_ptr(), M, E, drop_p, seed, _DT[s.dtype], _s())
+        return ds, db, rg, rb, None, None
 
 
 class MHAFn(torch.autograd.Function):

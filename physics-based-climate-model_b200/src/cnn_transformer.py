@@ -55,11 +55,12 @@ class CNNTransformer(nn.Module):
         qkv = ops_nn.LinearFn.apply(x, attn.in_proj_weight, attn.in_proj_bias, False)
         a = ops_nn.MHAFn.apply(qkv, self.n_heads, float(p) if tr else 0.0, ops_nn.next_seed())
         a = ops_nn.LinearFn.apply(a, attn.out_proj.weight, attn.out_proj.bias, False)
-        x = ops_nn.AddLayerNormFn.apply(xr, ops_nn.dropout(a, p, tr), lyr.norm1.weight, lyr.norm1.bias)
+        pd = float(p) if tr else 0.0            # sub-layer dropouts are fused into the residual-add + LayerNorm kernels
+        x = ops_nn.AddLayerNormFn.apply(xr, a, lyr.norm1.weight, lyr.norm1.bias, pd, ops_nn.next_seed() if pd > 0 else 0)
         x, xr = ops_nn.fork(x)
         f = ops_nn.LinearFn.apply(x, lyr.linear1.weight, lyr.linear1.bias, True)
         f = ops_nn.LinearFn.apply(ops_nn.dropout(f, p, tr), lyr.linear2.weight, lyr.linear2.bias, False)
-        return ops_nn.AddLayerNormFn.apply(xr, ops_nn.dropout(f, p, tr), lyr.norm2.weight, lyr.norm2.bias)
+        return ops_nn.AddLayerNormFn.apply(xr, f, lyr.norm2.weight, lyr.norm2.bias, pd, ops_nn.next_seed() if pd > 0 else 0)
 
     def forward(self, x):
         B = x.size(0)

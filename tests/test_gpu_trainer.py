@@ -199,3 +199,70 @@ def test_default_init_bf16_meets_the_planned_gates():
         assert errs[k] < (4.0 if ".se.fc." in k else 0.5), (k, errs[k])
     # at most a quarter of the tensors may sit above the tight per-tensor gate
     assert len(loose) <= len(errs) // 4, sorted(((errs[k], k) for k in loose), reverse=True)
+
+
+@pytest.mark.parametrize("E", [32, 128])
+def test_fused_dropout_layernorm_equals_the_unfused_composition(E):
+    """LayerNorm(a + dropout(b)) with the dropout drawn inside the LayerNorm kernels (forward and backward) is bit-identical
+    to DropoutFn followed by the plain residual LayerNorm with the same seed; and the column-sum / LayerNorm-backward
+    rewrites agree with torch on the parameter gradients."""
+    import pcm_b200  # noqa: F401
+    from pcm_b200 import ops_nn
+    torch.manual_seed(1)
+    M = 2 * 216 + 5
+    a = torch.randn(M, E, device="cuda").bfloat16().requires_grad_(True)
+    b = torch.randn(M, E, device="cuda").bfloat16().requires_grad_(True)
+    g = (1 + 0.1 * torch.randn(E, device="cuda")).requires_grad_(True)
+    bt = (0.1 * torch.randn(E, device="cuda")).requires_grad_(True)
+    dy = torch.randn(M, E, device="cuda").bfloat16()
+    outs = []
+    for fused in (True, False):
+        for t in (a, b, g, bt):
+            t.grad = None
+        if fused:
+            y = ops_nn.AddLayerNormFn.apply(a, b, g, bt, 0.25, 4242)
+        else:
+            y = ops_nn.AddLayerNormFn.apply(a, ops_nn.DropoutFn.apply(b, 0.25, 4242), g, bt)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        outs.append([y.detach().clone(), a.grad.clone(), b.grad.clone(), g.grad.clone(), bt.grad.clone()])
+    for u, v, name in zip(outs[0], outs[1], ["y", "da", "db", "dgamma", "dbeta"]):
+        if name in ("dgamma", "dbeta"):
+            assert torch.allclose(u, v, rtol=1e-5, atol=1e-5), name      # fp32 atomics: order only
+        else:
+            assert torch.equal(u, v), name
+    keep = float((outs[0][2] != 0).float().mean())
+    assert abs(keep - 0.75) < 0.02, keep
+    # p = 0 against torch's LayerNorm (fp32 reference on the same bf16 inputs)
+    for t in (a, b, g, bt):
+        t.grad = None
+    y = ops_nn.AddLayerNormFn.apply(a, b, g, bt)
+    y.backward(dy)
+    af, bf = a.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    gf, btf = g.detach().clone().requires_grad_(True), bt.detach().clone().requires_grad_(True)
+    s = (af + bf).bfloat16().float()
+    s.retain_grad()
+    yr = torch.nn.functional.layer_norm(s, (E,), gf, btf, 1e-5)
+    yr.backward(dy.float())
+    assert float((y.float() - yr).norm() / yr.norm()) < 5e-3
+    assert float((g.grad - gf.grad).norm() / gf.grad.norm()) < 5e-3
+    assert float((bt.grad - btf.grad).norm() / btf.grad.norm()) < 1e-4
+    assert float((a.grad.float() - s.grad).norm() / s.grad.norm()) < 5e-3
+
+
+@pytest.mark.parametrize("C,rows", [(16, 64 * 3456), (128, 13824), (384, 13824), (256, 20736), (48, 999)])
+def test_column_sum_kernel(C, rows):
+    from pcm_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(rows, C, device="cuda").bfloat16()
+    out = torch.zeros(C, device="cuda")
+    ops.channel_sum(x, out, 1, rows, C, C)
+    want = x.float().sum(0)
+    assert float((out - want).norm() / want.norm()) < 1e-5
+    # strided view: channels [8, 8 + C/2) of every second "image" handled as N images of P rows
+    if C >= 32:
+        N, P = 3, rows // 3
+        out2 = torch.zeros(C // 2, device="cuda")
+        ops.channel_sum(x, out2, N, P, C // 2, C // 2, ns=P * C, ps=C, off=8)
+        want2 = x[: N * P].float().reshape(N * P, C)[:, 8:8 + C // 2].sum(0)
+        assert float((out2 - want2).norm() / want2.norm()) < 1e-5
