@@ -223,6 +223,22 @@ PCM_API int pcm_gn_silu_bwd_apply(const void* da, const float* dpool, const void
  * memory.  GroupNorm has 8 groups (nn.GroupNorm(8, c), src/unet.py:37,39); stats[n][8][2] = (sum, sum of squares).
  * pcm_convblock_fused_supported: 1 when an H x W x C image of `dtype` (plus the gate maps) fits one SM. */
 PCM_API int pcm_convblock_fused_supported(int H, int W, int C, int Cr, int dtype);
+/* Whole ConvBlock forward (src/unet.py:35-49: conv3x3 -> GN(8) -> SiLU -> conv3x3 -> GN(8) -> SiLU -> SE -> spatial gate)
+ * as ONE kernel, one CTA per image, for the thin layers (C = 16 / 32 / 64 output channels, Cin = 16 / 32 / 64 padded input
+ * channels, bf16) whose halo image and weights fit one SM (pcm_convblock_fwd_tc_supported).  Both convolutions run on the
+ * tensor cores over the shared-memory-resident image (nine row-shifted UMMA descriptors per tile), each conv output stays
+ * in tensor memory as fp32 for the whole image, a1 = silu(GN(y1)) goes from TMEM straight into the next conv's operand
+ * image.  x [N][H][W][Cin]; wk1 [9][C][Cin], wk2 [9][C][C] packed bf16 (pcm_pack_weight); outputs (all saved for the
+ * backward pass, same contents as the 4-kernel path pcm_conv3x3_tc / pcm_gn_silu_img_fwd / pcm_conv3x3_tc /
+ * pcm_convblock_tail_fwd): y1, a1, y2, out [N][H][W][C] bf16; stats1 / stats2 [N][8][2]; pool, se [N][C]; hid [N][Cr];
+ * maps [N][3][H*W] fp32; ties [N][H*W]. */
+PCM_API int pcm_convblock_fwd_tc_supported(int H, int W, int Cin, int C, int Cr);
+PCM_API int pcm_convblock_fwd_tc(const void* x, const void* wk1, const void* wk2, const float* g1, const float* b1,
+                                 const float* g2, const float* b2, const float* sw1, const float* sw2, const float* wsp,
+                                 void* y1, void* a1, void* y2, float* stats1, float* stats2, float* pool, float* se,
+                                 float* hid, float* maps, unsigned char* ties, void* out, int N, int H, int W, int Cin,
+                                 int C, int Cr, float eps, pcm_stream_t s);
+
 /* tail 1: y = silu(GroupNorm(x))  [statistics + normalise in one pass over shared memory] */
 PCM_API int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const float* beta, float* stats, void* y, int N,
                                 int H, int W, int C, float eps, int dtype, pcm_stream_t s);

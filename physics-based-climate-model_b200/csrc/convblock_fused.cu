@@ -13,7 +13,7 @@
 //
 // The multi-kernel path in convblock.cu (grid-wide passes, 6 forward + 8 backward launches per block) remains for
 // images that do not fit (config 5, fp32 at full size) — see pcm_convblock_fused_supported.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pcm {
 
@@ -221,6 +221,18 @@ __device__ __forceinline__ void store8_rounded(__nv_bfloat16* p, float (&a)[8]) 
   }
   *reinterpret_cast<uint4*>(p) = u;
 }
+// pack 8 values to bf16 (16 bytes) and leave them in `a` as bf16 holds them
+__device__ __forceinline__ uint4 pack8_rounded(float* a) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+    const float2 f = __bfloat1622float2(h[i]);
+    a[2 * i] = f.x; a[2 * i + 1] = f.y;
+  }
+  return u;
+}
 // a = silu(z), unrounded (callers round eight at a time)
 template <typename T>
 __device__ __forceinline__ float silu_raw(float x, float za, float zb) {
@@ -323,64 +335,20 @@ struct PixWalk {
   }
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// forward tails.  FULL = false: y = silu(GN(x)).  FULL = true: out = a*se*gate with a = silu(GN(x)).
-// ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool FULL>
-__global__ void __launch_bounds__(kFT, 1)
-convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                          const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ wsp,
-                          float* __restrict__ stats, float* __restrict__ pool_g, float* __restrict__ se_g,
-                          float* __restrict__ hid_g, float* __restrict__ maps, uint8_t* __restrict__ ties,
-                          T* __restrict__ out, int H, int W, int C, int Cr, float eps) {
-  pdl_launch_dependents();
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
+// Second half of the full forward tail, shared by convblock_tail_fwd_kernel and the fused block kernel
+// (convblock_fwd_tc_kernel): on entry s_img holds a = silu(GN(x)) of image n (rounded to T, linear [pixel][C]) and
+// sp.ch2[c] the per-channel sums of a (published by a barrier).  Squeeze / excite, channel mean / max maps, the 7x7 gate
+// and out = a*se*gate; saves pool / hid / se and (training) maps / ties.  Every thread of the CTA calls it.
+template <typename T>
+__device__ __forceinline__ void tail_finish_from_pool(T* s_img, uint8_t* smem, const TailSmem& L, const TailPtrs& sp, int n,
+                                                      int H, int W, int C, int Cr, float* __restrict__ pool_g,
+                                                      float* __restrict__ se_g, float* __restrict__ hid_g,
+                                                      float* __restrict__ maps, uint8_t* __restrict__ ties,
+                                                      T* __restrict__ on) {
+  const int P = H * W, cv = C / 8, nvec = P * cv, Wp = plane_wp(W);
   const int cvs = __ffs(cv) - 1;
-  const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), FULL ? 1 : 0, 0);
-  T* s_img = reinterpret_cast<T*>(smem + L.img);
-  const TailPtrs sp = tail_ptrs(smem, L, C);
-  const T* xn = x + (size_t)n * P * C;
-  T* on = out + (size_t)n * P * C;
   const int cb = threadIdx.x & (cv - 1);
-
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
-  if (FULL) {
-    float4* z4 = reinterpret_cast<float4*>(smem + L.cm0);      // cm0 and cm1 are contiguous
-    for (int i = threadIdx.x; i < 2 * (H + 6) * Wp / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  pdl_wait();                                                  // global memory from here on
-  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
-  if (FULL) {
-    load_gate_weights(wsp, sp);
-    for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
-  }
-  __syncthreads();
-  image_group_stats<T>(s_img, nvec, cv, cg, P, eps, sp, stats + (size_t)n * kGroups * 2, bar);
-
-  float ga[8], be[8], acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cb * 8 + j, g = c / cg;
-    gn_coef(__ldg(gamma + c), __ldg(beta + c), sp.mu[g], sp.rs[g], ga[j], be[j]);
-    acc[j] = 0.f;
-  }
-#pragma unroll 2
-  for (int v = threadIdx.x; v < nvec; v += NT) {
-    float t[8];
-    load8_rw(s_img + (size_t)v * 8, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = silu_raw<T>(t[j], ga[j], be[j]);
-    if (FULL) store8_rounded(s_img + (size_t)v * 8, t);
-    else store8_rounded(on + (size_t)v * 8, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += t[j];
-  }
-  if (!FULL) return;
-
   // ---- squeeze / excite (SEBlock.forward, src/unet.py:16-17)
-  chan_put(acc, sp.part, 0, cb, cv, C);
-  chan_finish(sp.part, 1, sp.ch2, C);
   const float invP = 1.f / (float)P;
   for (int c = threadIdx.x; c < C; c += NT) pool_g[(size_t)n * C + c] = sp.ch2[c];
   // the two 1x1 "fc" matrices were staged in shared memory at kernel start; one warp per hidden unit
@@ -486,6 +454,392 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
     for (int j = 0; j < 8; ++j) t[j] = t[j] * sc[j] * gt;
     store8(on + (size_t)v * 8, t);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward tails.  FULL = false: y = silu(GN(x)).  FULL = true: out = a*se*gate with a = silu(GN(x)).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool FULL>
+__global__ void __launch_bounds__(kFT, 1)
+convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ wsp,
+                          float* __restrict__ stats, float* __restrict__ pool_g, float* __restrict__ se_g,
+                          float* __restrict__ hid_g, float* __restrict__ maps, uint8_t* __restrict__ ties,
+                          T* __restrict__ out, int H, int W, int C, int Cr, float eps) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
+  const int cvs = __ffs(cv) - 1;
+  const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), FULL ? 1 : 0, 0);
+  T* s_img = reinterpret_cast<T*>(smem + L.img);
+  const TailPtrs sp = tail_ptrs(smem, L, C);
+  const T* xn = x + (size_t)n * P * C;
+  T* on = out + (size_t)n * P * C;
+  const int cb = threadIdx.x & (cv - 1);
+
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  if (FULL) {
+    float4* z4 = reinterpret_cast<float4*>(smem + L.cm0);      // cm0 and cm1 are contiguous
+    for (int i = threadIdx.x; i < 2 * (H + 6) * Wp / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_wait();                                                  // global memory from here on
+  if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
+  if (FULL) {
+    load_gate_weights(wsp, sp);
+    for (int i = threadIdx.x; i < C * Cr; i += NT) { sp.sw1[i] = __ldg(w1 + i); sp.sw2[i] = __ldg(w2 + i); }
+  }
+  __syncthreads();
+  image_group_stats<T>(s_img, nvec, cv, cg, P, eps, sp, stats + (size_t)n * kGroups * 2, bar);
+
+  float ga[8], be[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb * 8 + j, g = c / cg;
+    gn_coef(__ldg(gamma + c), __ldg(beta + c), sp.mu[g], sp.rs[g], ga[j], be[j]);
+    acc[j] = 0.f;
+  }
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += NT) {
+    float t[8];
+    load8_rw(s_img + (size_t)v * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = silu_raw<T>(t[j], ga[j], be[j]);
+    if (FULL) store8_rounded(s_img + (size_t)v * 8, t);
+    else store8_rounded(on + (size_t)v * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += t[j];
+  }
+  if (!FULL) return;
+
+  // ---- squeeze / excite pool sums, then the shared second half
+  chan_put(acc, sp.part, 0, cb, cv, C);
+  chan_finish(sp.part, 1, sp.ch2, C);
+  tail_finish_from_pool<T>(s_img, smem, L, sp, n, H, W, C, Cr, pool_g, se_g, hid_g, maps, ties, on);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Whole ConvBlock forward in ONE kernel, one CTA per image (reference src/unet.py:35-49):
+//     x -> conv3x3 -> GN -> SiLU -> conv3x3 -> GN -> SiLU -> SE -> spatial gate -> out
+// for the thin layers (C = 16 / 32 / 64 output channels) whose image — and both weight tensors — fit one SM.
+//
+//   * the input image arrives by TMA as a zero-ringed halo image [(H+2) x (W+2) pixels][Cin] in the canonical K-major
+//     swizzled UMMA layout (out-of-bounds fill = the conv padding); both weight tensors sit next to it, resident;
+//   * each 3x3 convolution is an implicit GEMM on the 5th-gen tensor cores over the resident image: an M = 128 tile is
+//     128 consecutive halo rows, the nine taps are nine descriptors whose start address is advanced by kh*(W+2) + kw
+//     rows (conv3x3_tc_halo_kernel's trick), and the WHOLE output image stays in TENSOR MEMORY as fp32
+//     (tiles x C columns: 448 of 512 columns at 48 x 72 x 16) — it never goes through shared memory;
+//   * GroupNorm needs whole-image statistics before it can normalise, so each conv output is read from TMEM twice:
+//     once as its tiles complete (statistics of the bf16-rounded values + the copy of y the backward pass needs, to
+//     global), once to apply normalise + SiLU.  After conv1 that second read writes a1 as the NEXT conv's operand, i.e.
+//     straight into the halo image in shared memory (ring re-zeroed) — conv1 -> GN -> SiLU -> conv2 without the
+//     activation ever leaving the SM.  After conv2 it writes a2 as the linear image the SE / gate half of the
+//     tail (tail_finish_from_pool, shared with convblock_tail_fwd_kernel) works on.
+//   * replaces 4 launches (conv, gn_silu_img_fwd, conv, convblock_tail_fwd) and their 8 tensor passes over HBM by one
+//     launch and 5.4 (x in; y1, a1, y2, out + 13 B / pixel of gate maps out — all of which the backward needs).
+//
+// Thread roles: warps 0-15 read TMEM (warp w: lane quarter w & 3, tiles (w >> 2) + 4 i) and do all the tail work;
+// warp 16 issues the TMA loads and the MMAs (one elected thread).  Results are bit-compatible with the 4-kernel path: the
+// statistics are taken from the bf16-rounded conv outputs, the activations use the same silu_raw / rounding.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBlkThreads = 544;
+
+struct BlockFwdParams {
+  int N, H, W, Cin, C, Cr;           // Cin = padded input channels (16 / 32 / 64), C = output channels
+  int Wp, M, tiles, P;               // Wp = W + 2, M = H * Wp halo-row extent of the output, tiles = ceil(M / 128)
+  int rows_a;                        // halo rows addressable in the image region: tiles*128 + 2*Wp + 2
+  int box_h, nbox;                   // the input arrives in nbox TMA boxes of box_h halo rows each
+  uint32_t tmem_cols;
+  uint32_t off_w1, off_w2, off_cm0, off_cm1, off_gate, off_part, off_fl, off_bar;   // shared-memory layout (region 0 = image)
+  float eps;
+};
+
+// byte offset of 16-byte chunk `chunk` of halo row `row` in a 1024-byte aligned K-major tile with rows of rb bytes
+// (rb = 32 / 64 / 128 with the swizzle of the same width: chunk bits ^= row bits, a function of the address)
+__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk, uint32_t rb) {
+  const uint32_t off = row * rb + (chunk << 4);
+  return off ^ (((off >> 7) & ((rb >> 4) - 1u)) << 4);
+}
+
+__device__ __forceinline__ void issue_conv_tiles(uint32_t tmem_base, uint32_t a_base, uint32_t b_base, int tiles, int Wp,
+                                                 int Cin, int C, uint64_t* tile_done) {
+  using namespace tc;
+  const uint32_t rb = (uint32_t)Cin * 2u;
+  const uint32_t idesc = make_idesc_bf16(128, C, 0, 0);
+  const uint32_t ltype = layout_type_for_row_bytes((int)rb);
+  const uint64_t adesc0 = make_smem_desc(a_base, 16, 8 * rb, ltype);
+  const uint64_t bdesc0 = make_smem_desc(b_base, 16, 8 * rb, ltype);
+  const int ksteps = Cin / 16;
+  uint32_t a_off[9], b_off[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    a_off[tap] = ((uint32_t)((tap / 3) * Wp + (tap % 3)) * rb) >> 4;
+    b_off[tap] = ((uint32_t)tap * (uint32_t)C * rb) >> 4;
+  }
+  const uint32_t tile_step = (128u * rb) >> 4;
+  for (int t = 0; t < tiles; ++t) {
+    const uint32_t d = tmem_base + (uint32_t)(t * C);
+    const uint64_t ab = adesc0 + (uint64_t)(t * tile_step);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+      for (int k = 0; k < ksteps; ++k)
+        umma_bf16(d, ab + (uint64_t)(a_off[tap] + 2 * k), bdesc0 + (uint64_t)(b_off[tap] + 2 * k), idesc, (tap | k) != 0);
+    umma_commit(&tile_done[t]);
+  }
+}
+
+// packed weights [9][C][Cin] bf16 (global) -> swizzled K-major tiles in shared memory
+__device__ __forceinline__ void stage_weights(uint8_t* dst, const __nv_bfloat16* __restrict__ wk, int C, int Cin) {
+  const int cpr = Cin / 8;                                   // 16-byte chunks per row
+  const int total = 9 * C * cpr;
+  const uint32_t rb = (uint32_t)Cin * 2u;
+  for (int i = threadIdx.x; i < total; i += NT) {
+    const int chunk = i % cpr, row = i / cpr;                // row = tap*C + co
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wk) + i);
+    *reinterpret_cast<uint4*>(dst + swz((uint32_t)row, (uint32_t)chunk, rb)) = v;
+  }
+}
+
+template <int C>       // output channels (16 / 32 / 64): GroupNorm group of a channel and the TMEM column loops are compile-time
+__global__ void __launch_bounds__(kBlkThreads, 1)
+convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ wk1,
+                        const __nv_bfloat16* __restrict__ wk2, const float* __restrict__ g1, const float* __restrict__ b1,
+                        const float* __restrict__ g2, const float* __restrict__ b2, const float* __restrict__ sw1,
+                        const float* __restrict__ sw2, const float* __restrict__ wsp, __nv_bfloat16* __restrict__ y1,
+                        __nv_bfloat16* __restrict__ a1, __nv_bfloat16* __restrict__ y2, float* __restrict__ stats1,
+                        float* __restrict__ stats2, float* __restrict__ pool_g, float* __restrict__ se_g,
+                        float* __restrict__ hid_g, float* __restrict__ maps, uint8_t* __restrict__ ties,
+                        __nv_bfloat16* __restrict__ out, unsigned int* __restrict__ err, const BlockFwdParams p) {
+  using namespace tc;
+  typedef __nv_bfloat16 T;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sImg = smem;                                    // halo image of x, then of a1, then the linear image of a2
+  uint8_t* sW1 = smem + p.off_w1;
+  uint8_t* sW2 = smem + p.off_w2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* tile_done = bars;                              // [32]
+  uint64_t* xfull = bars + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
+  TailSmem L;
+  L.img = 0; L.cm0 = p.off_cm0; L.cm1 = p.off_cm1; L.dq = 0; L.gate = p.off_gate; L.dm = 0; L.bar = p.off_bar;
+  L.part = p.off_part; L.fl = p.off_fl; L.total = 0;
+  const TailPtrs sp = tail_ptrs(smem, L, p.C);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x, Cin = p.Cin, H = p.H, W = p.W, Wp = p.Wp, P = p.P;
+  constexpr int cg = C / kGroups;
+  const uint32_t rb1 = (uint32_t)Cin * 2u, rb2 = (uint32_t)C * 2u;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < p.tiles; ++i) mbar_init(&tile_done[i], 1);
+    mbar_init(xfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_slot, p.tmem_cols);
+  {  // zero the gate planes (their rings must read as zero) and the slack rows of the image region the last tile reads
+    float4* z4 = reinterpret_cast<float4*>(smem + p.off_cm0);              // cm0 and cm1 are contiguous
+    const int Wpl = plane_wp(W);
+    for (int i = threadIdx.x; i < 2 * (H + 6) * Wpl / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t lo = (uint32_t)(p.nbox * p.box_h * Wp) * rb1, hi = (uint32_t)p.rows_a * rb1;
+    for (uint32_t o = lo + threadIdx.x * 16u; o < hi; o += NT * 16u) *reinterpret_cast<uint4*>(sImg + o) = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();                                                  // global memory from here on
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    if (elect_one()) {
+      // the whole halo image of image n: nbox boxes {Cin, W+2, box_h, 1} at (0, -1, -1 + b*box_h, n)
+      mbar_expect_tx(xfull, (uint32_t)(p.nbox * p.box_h * Wp) * rb1);
+      for (int b = 0; b < p.nbox; ++b)
+        tma_load_4d(sImg + (size_t)b * p.box_h * Wp * rb1, &tmX, xfull, 0, -1, -1 + b * p.box_h, n);
+    }
+    __syncwarp();
+  }
+  stage_weights(sW1, wk1, C, Cin);
+  stage_weights(sW2, wk2, C, C);
+  load_gate_weights(wsp, sp);
+  for (int i = threadIdx.x; i < C * p.Cr; i += NT) { sp.sw1[i] = __ldg(sw1 + i); sp.sw2[i] = __ldg(sw2 + i); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  // ---------------- conv1 on the tensor cores ----------------
+  if (warp == 16) {
+    if (elect_one()) {
+      if (mbar_wait(xfull, 0, err)) {
+        tc_fence_after();
+        issue_conv_tiles(tmem_base, smem_u32(sImg), smem_u32(sW1), p.tiles, Wp, Cin, C, tile_done);
+      }
+    }
+    __syncwarp();
+  }
+  const int quarter = warp & 3, grp = warp >> 2;              // TMEM readers: warps 0..15
+
+  // Pass over this warp's tiles of a conv output in TMEM: statistics of the bf16-rounded values per GroupNorm group and
+  // the copy of y for the backward pass.  phase = mbarrier parity of this convolution.
+  auto stats_pass = [&](uint32_t phase, __nv_bfloat16* __restrict__ ydst, float* __restrict__ stats_out) {
+    float gs[kGroups], gq[kGroups];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) gs[g] = gq[g] = 0.f;
+    bool ok = true;
+    if (warp < 16) {
+      for (int t = grp; t < p.tiles; t += 4) {
+        const int m = t * 128 + quarter * 32 + lane;
+        const int h = m / Wp, w = m - h * Wp;
+        const bool valid = w < W && h < H;
+        ok = mbar_wait(&tile_done[t], phase, err) && ok;
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * C);
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 16) {
+          float v[16];
+          tmem_ld16(t_addr + c0, v);
+          if (valid) {
+            const uint4 u0 = pack8_rounded(v), u1 = pack8_rounded(v + 8);          // v now holds the rounded values
+            uint4* dp = reinterpret_cast<uint4*>(ydst + ((size_t)n * P + h * W + w) * C + c0);
+            dp[0] = u0; dp[1] = u1;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int g = (c0 + j) / cg;                     // compile-time: both loops are unrolled
+              gs[g] += v[j];
+              gq[g] = fmaf(v[j], v[j], gq[g]);
+            }
+          }
+        }
+      }
+    }
+    // CTA reduction of the 16 group sums: lanes, then warps through sp.part
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) { gs[g] = warp_sum(gs[g]); gq[g] = warp_sum(gq[g]); }
+    if (lane == 0) {
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) { sp.part[warp * 16 + 2 * g] = gs[g]; sp.part[warp * 16 + 2 * g + 1] = gq[g]; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x < kGroups) {
+      const int g = threadIdx.x;
+      float S = 0.f, Q = 0.f;
+      for (int wv = 0; wv < NT / 32; ++wv) { S += sp.part[wv * 16 + 2 * g]; Q += sp.part[wv * 16 + 2 * g + 1]; }
+      group_mu_rs(S, Q, (float)cg * (float)P, p.eps, sp.mu[g], sp.rs[g]);
+      stats_out[(size_t)n * kGroups * 2 + 2 * g] = S;
+      stats_out[(size_t)n * kGroups * 2 + 2 * g + 1] = Q;
+    }
+    __syncthreads();
+    return ok;
+  };
+  // per-channel GroupNorm + SiLU coefficients into shared memory (sp.ca = za, sp.cb_ = zb)
+  auto publish_coef = [&](const float* __restrict__ gamma, const float* __restrict__ beta) {
+    for (int c = threadIdx.x; c < C; c += NT) {
+      const int g = c / cg;
+      float za, zb;
+      gn_coef(__ldg(gamma + c), __ldg(beta + c), sp.mu[g], sp.rs[g], za, zb);
+      sp.ca[c] = za; sp.cb_[c] = zb;
+    }
+  };
+
+  bool ok = stats_pass(0u, y1, stats1);
+  publish_coef(g1, b1);
+  // conv1 is complete (every tile barrier was waited for): the image region becomes a1's halo image — all zero first
+  {
+    const uint32_t bytes = (uint32_t)p.rows_a * rb2;
+    for (uint32_t o = threadIdx.x * 16u; o < bytes; o += NT * 16u) *reinterpret_cast<uint4*>(sImg + o) = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  // ---------------- a1 = silu(GN1(y1)): TMEM -> halo image (the next conv's operand) + global (saved for backward) ----
+  if (warp < 16 && ok) {
+    for (int t = grp; t < p.tiles; t += 4) {
+      const int m = t * 128 + quarter * 32 + lane;
+      const int h = m / Wp, w = m - h * Wp;
+      const bool valid = w < W && h < H;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * C);
+      const uint32_t arow = (uint32_t)((h + 1) * Wp + w + 1);
+#pragma unroll
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_addr + c0, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_raw<T>(round_to<T>(v[j]), sp.ca[c0 + j], sp.cb_[c0 + j]);
+          const uint4 u0 = pack8_rounded(v), u1 = pack8_rounded(v + 8);
+          *reinterpret_cast<uint4*>(sImg + swz(arow, (uint32_t)(c0 >> 3), rb2)) = u0;
+          *reinterpret_cast<uint4*>(sImg + swz(arow, (uint32_t)(c0 >> 3) + 1u, rb2)) = u1;
+          uint4* dp = reinterpret_cast<uint4*>(a1 + ((size_t)n * P + h * W + w) * C + c0);
+          dp[0] = u0; dp[1] = u1;
+        }
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of a1 -> the tensor core's async proxy
+  tc_fence_before();
+  __syncthreads();
+  // ---------------- conv2 ----------------
+  if (warp == 16) {
+    if (elect_one()) {
+      tc_fence_after();
+      issue_conv_tiles(tmem_base, smem_u32(sImg), smem_u32(sW2), p.tiles, Wp, C, C, tile_done);
+    }
+    __syncwarp();
+  }
+  ok = stats_pass(1u, y2, stats2) && ok;
+  publish_coef(g2, b2);
+  __syncthreads();
+  // ---------------- a2 = silu(GN2(y2)): TMEM -> linear image [pixel][C] (conv2 is complete: the region is free) + SE pool sums
+  T* s_img = reinterpret_cast<T*>(sImg);
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    if (warp < 16 && ok) {
+      for (int t = grp; t < p.tiles; t += 4) {
+        const int m = t * 128 + quarter * 32 + lane;
+        const int h = m / Wp, w = m - h * Wp;
+        const bool valid = w < W && h < H;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * C);
+        float v[16];
+        tmem_ld16(t_addr + c0, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_raw<T>(round_to<T>(v[j]), sp.ca[c0 + j], sp.cb_[c0 + j]);
+          const uint4 u0 = pack8_rounded(v), u1 = pack8_rounded(v + 8);
+          uint4* dp = reinterpret_cast<uint4*>(s_img + (size_t)(h * W + w) * C + c0);
+          dp[0] = u0; dp[1] = u1;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += v[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sp.part[warp * 16 + j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      float t = 0.f;
+      for (int wv = 0; wv < NT / 32; ++wv) t += sp.part[wv * 16 + threadIdx.x];
+      sp.ch2[c0 + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+  // ---------------- SE, channel maps, 7x7 gate, out = a2*se*gate ----------------
+  tail_finish_from_pool<T>(s_img, smem, L, sp, n, H, W, C, p.Cr, pool_g, se_g, hid_g, maps, ties,
+                           out + (size_t)n * P * C);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -938,6 +1292,102 @@ extern "C" int pcm_convblock_fused_supported(int H, int W, int C, int Cr, int dt
   if (!fused_shape_ok(H, W, C, Cr)) return 0;
   const int elt = dtype == PCM_BF16 ? 2 : 4;
   return tail_smem_layout(H, W, C, elt, 1, 1).total <= 227 * 1024 ? 1 : 0;
+}
+
+// ---- fused block forward: shared-memory layout + support check -----------------------------------------------------
+static bool block_fwd_layout(int H, int W, int Cin, int C, int Cr, BlockFwdParams* p, size_t* smem_total) {
+  if (!(C == 16 || C == 32 || C == 64) || !(Cin == 16 || Cin == 32 || Cin == 64)) return false;
+  if (Cr < 1 || Cr > 64 || Cr * 8 > C || H < 1 || W < 1 || W + 2 > 256) return false;
+  p->H = H; p->W = W; p->Cin = Cin; p->C = C; p->Cr = Cr;
+  p->Wp = W + 2; p->P = H * W;
+  p->M = H * p->Wp;
+  p->tiles = (p->M + 127) / 128;
+  if (p->tiles > 32 || p->tiles * C > 512) return false;                    // tile barriers / TMEM columns
+  p->rows_a = p->tiles * 128 + 2 * p->Wp + 2;
+  // TMA boxes of the input: whole halo rows, <= 32 KB each, and every box must start on a swizzle-atom boundary of the
+  // image (8 rows x Cin*2 bytes; the swizzle is a function of the shared-memory address) — box_h*(W+2) a multiple of 8.
+  // Rows past H+2 are out of bounds (zero filled); pick the box height that overshoots least.
+  {
+    const int max_h = (32 * 1024) / (p->Wp * Cin * 2);
+    int best_h = 0, best_rows = 1 << 30;
+    for (int bh = 1; bh <= max_h && bh <= 256; ++bh) {
+      if ((bh * p->Wp) % 8 != 0) continue;
+      const int rows = ((H + 2 + bh - 1) / bh) * bh;
+      if (rows < best_rows || (rows == best_rows && bh > best_h)) { best_rows = rows; best_h = bh; }
+    }
+    if (best_h == 0) return false;
+    p->box_h = best_h;
+    p->nbox = best_rows / best_h;
+  }
+  const int box_h = p->box_h;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p->tiles * C)) cols <<= 1;
+  p->tmem_cols = cols;
+  const size_t rb1 = (size_t)Cin * 2, rb2 = (size_t)C * 2;
+  size_t rows = (size_t)p->rows_a;
+  if ((size_t)p->nbox * box_h * p->Wp > rows) rows = (size_t)p->nbox * box_h * p->Wp;
+  size_t img = rows * rb1;
+  if ((size_t)p->rows_a * rb2 > img) img = (size_t)p->rows_a * rb2;
+  if ((size_t)p->P * C * 2 > img) img = (size_t)p->P * C * 2;
+  size_t off = (img + 1023) & ~(size_t)1023;
+  auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) & ~(align - 1); const size_t o = off; off += bytes; return (uint32_t)o; };
+  p->off_w1 = take((size_t)9 * C * rb1, 1024);
+  p->off_w2 = take((size_t)9 * C * rb2, 1024);
+  const size_t Pp = (size_t)(H + 6) * plane_wp(W);
+  p->off_cm0 = take(Pp * 4, 16);
+  p->off_cm1 = take(Pp * 4, 16);
+  if (p->off_cm1 != p->off_cm0 + Pp * 4) return false;                      // the kernel zeroes them as one range
+  p->off_gate = take((size_t)p->P * 4, 16);
+  p->off_part = take((size_t)2 * (kBlkThreads / 32) * C * 4 + 64, 16);       // chan_put slots; >= 17 warps x 16 floats
+  p->off_fl = take((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + C * C / 4) * 4, 16);
+  p->off_bar = take(34 * 8 + 16, 16);
+  *smem_total = off + 1024;                                                  // + alignment slack of the dynamic base
+  return *smem_total <= 227 * 1024;
+}
+
+extern "C" int pcm_convblock_fwd_tc_supported(int H, int W, int Cin, int C, int Cr) {
+  BlockFwdParams p;
+  size_t smem = 0;
+  return block_fwd_layout(H, W, Cin, C, Cr, &p, &smem) ? 1 : 0;
+}
+
+extern "C" int pcm_convblock_fwd_tc(const void* x, const void* wk1, const void* wk2, const float* g1, const float* b1,
+                                    const float* g2, const float* b2, const float* sw1, const float* sw2, const float* wsp,
+                                    void* y1, void* a1, void* y2, float* stats1, float* stats2, float* pool, float* se,
+                                    float* hid, float* maps, unsigned char* ties, void* out, int N, int H, int W, int Cin,
+                                    int C, int Cr, float eps, pcm_stream_t s) {
+  BlockFwdParams p;
+  size_t smem = 0;
+  PCM_REQUIRE(block_fwd_layout(H, W, Cin, C, Cr, &p, &smem), "convblock_fwd_tc: unsupported shape H=%d W=%d Cin=%d C=%d Cr=%d",
+              H, W, Cin, C, Cr);
+  PCM_REQUIRE(maps != nullptr && ties != nullptr, "convblock_fwd_tc: maps and ties are required (training forward)");
+  PCM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wk1) | reinterpret_cast<uintptr_t>(wk2) |
+                reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(y2) |
+                reinterpret_cast<uintptr_t>(out)) & 15) == 0, "convblock_fwd_tc: pointers must be 16-byte aligned");
+  if (N == 0) return PCM_OK;
+  p.N = N; p.eps = eps;
+  CUtensorMap tmX;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)Cin, (uint32_t)p.Wp, (uint32_t)p.box_h, 1};
+    const int rc = make_tensor_map(&tmX, x, 4, dims, strides, box, Cin * 2);
+    if (rc != PCM_OK) return rc;
+  }
+  unsigned int* err = tc_error_counter();
+  PCM_REQUIRE(err != nullptr, "convblock_fwd_tc: could not allocate the error counter");
+  auto kern = C == 16 ? convblock_fwd_tc_kernel<16> : C == 32 ? convblock_fwd_tc_kernel<32> : convblock_fwd_tc_kernel<64>;
+  const int ki = C == 16 ? 0 : C == 32 ? 1 : 2;
+  static size_t smem_set[3] = {0, 0, 0};
+  if (smem > smem_set[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("convblock_fwd_tc: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return PCM_ERR_CUDA; }
+    smem_set[ki] = smem;
+  }
+  typedef __nv_bfloat16 B16;
+  pcm::launch(kern, N, kBlkThreads, smem, (cudaStream_t)s, tmX, (const B16*)wk1, (const B16*)wk2, g1, b1, g2, b2, sw1, sw2, wsp,
+              (B16*)y1, (B16*)a1, (B16*)y2, stats1, stats2, pool, se, hid, maps, ties, (B16*)out, err, p);
+  return check_launch("convblock_fwd_tc");
 }
 
 extern "C" int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const float* beta, float* stats, void* y, int N,

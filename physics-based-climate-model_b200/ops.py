@@ -552,6 +552,15 @@ def convblock_fused_ok(H: int, W: int, C: int, Cr: int, dtype) -> bool:
     return bool(lib()._fn["pcm_convblock_fused_supported"](H, W, C, Cr, _DT[dtype]))
 
 
+def convblock_fwd_tc_ok(H: int, W: int, Cin: int, C: int, Cr: int, dtype) -> bool:
+    """True when the whole-block forward kernel (csrc/convblock_fused.cu, convblock_fwd_tc_kernel) takes this shape.
+    PCM_BLOCK_FWD_TC=0 keeps the 4-kernel forward."""
+    import os
+    if dtype != torch.bfloat16 or os.environ.get("PCM_BLOCK_FWD_TC", "1") == "0":
+        return False
+    return bool(lib()._fn["pcm_convblock_fwd_tc_supported"](H, W, Cin, C, Cr))
+
+
 class ConvBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp):
@@ -569,6 +578,23 @@ class ConvBlockFn(torch.autograd.Function):
         ctx.dims = (N, H, W, Cip, Ci, Co, Cr)
         wk1 = conv_weight_fwd(w1, dt, Ip=Cip)
         wk2 = conv_weight_fwd(w2, dt)
+        if fused and convblock_fwd_tc_ok(H, W, Cip, Co, Cr, dt):
+            # the whole block forward in ONE launch: both convolutions on the tensor cores over the shared-memory
+            # resident image, conv outputs in tensor memory, a1 written straight into conv2's operand image
+            small = torch.empty(N * G * 2 * 2 + N * Co, device=dev, dtype=torch.float32)
+            stats1, stats2, pool = small[: N * G * 2], small[N * G * 2: N * G * 4], small[N * G * 4:]
+            se = torch.empty(N * Co + N * Cr, device=dev, dtype=torch.float32)
+            hid = se[N * Co:]
+            y1 = torch.empty((N, H, W, Co), device=dev, dtype=dt)
+            a1, y2, out = torch.empty_like(y1), torch.empty_like(y1), torch.empty_like(y1)
+            maps = torch.empty(N * P * 3, device=dev, dtype=torch.float32)
+            ties = torch.empty(N * P, device=dev, dtype=torch.uint8)
+            _call("pcm_convblock_fwd_tc", x.data_ptr(), wk1.data_ptr(), wk2.data_ptr(), g1.data_ptr(), b1.data_ptr(),
+                  g2.data_ptr(), b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), y1.data_ptr(), a1.data_ptr(),
+                  y2.data_ptr(), stats1.data_ptr(), stats2.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(),
+                  maps.data_ptr(), ties.data_ptr(), out.data_ptr(), N, H, W, Cip, Co, Cr, GN_EPS, st)
+            ctx.save_for_backward(x, y1, a1, y2, small, se, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp, maps, ties, out)
+            return out
         if fused:
             # per-image tails: conv -> [GN+SiLU] -> conv -> [GN+SiLU+SE+gate]; 4 launches, every tensor read once
             small = torch.empty(N * G * 2 * 2 + N * Co, device=dev, dtype=torch.float32)     # written fully

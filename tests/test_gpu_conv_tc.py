@@ -424,3 +424,65 @@ def test_persistent_convlstm_matches_per_step_path_and_oracle(B, last_only, monk
     for nm, u, v in zip(names[:3], a[:3], ref):
         e = float((u.double() - v).norm() / v.norm())
         assert e < (3e-2 if nm == "h" else 6e-2), (nm, e)
+
+
+@pytest.mark.parametrize("shape", [(5, 48, 72, 7, 16), (5, 24, 36, 16, 32), (5, 12, 18, 32, 64), (3, 24, 36, 64, 32),
+                                   (4, 12, 18, 8, 16)])
+def test_fused_block_forward_matches_four_kernel_path(shape, monkeypatch):
+    """convblock_fwd_tc_kernel (whole ConvBlock forward in one launch: convs on tcgen05 over the smem-resident image,
+    conv outputs in TMEM) against the 4-kernel forward it replaces — output, every saved tensor the backward consumes,
+    and the gradients that come out of the (shared) backward — and against the fp64 oracle of src/unet.py:35-49."""
+    import pcm_b200
+    from oracle import model_oracle as O
+    from pcm_b200 import ops
+    from pcm_b200._lib import lib
+    from pcm_b200.src.unet import ConvBlock
+    N, H, W, cin, cout = shape
+    sd = O.synth_state_dict(O._convblock_spec("", cin, cout), 501)
+    x, y = O.synth_frame_batch(N, cin, H, W, 502, out_ch=cout)
+
+    def run(fused):
+        monkeypatch.setenv("PCM_BLOCK_FWD_TC", "1" if fused else "0")
+        m = ConvBlock(cin, cout)
+        m.load_state_dict(sd)
+        m = m.cuda()
+        xs = ops.StageIn.apply(x.cuda(), torch.bfloat16)
+        xs.requires_grad_(True)
+        seen = []
+        orig = lib().call
+
+        def spy(name, *a):
+            seen.append(name)
+            return orig(name, *a)
+        monkeypatch.setattr(lib(), "call", spy)
+        out = m.forward_nhwc(xs)
+        saved = [t.detach().float().cpu() if torch.is_tensor(t) and t.dtype != torch.uint8 else (t.cpu() if torch.is_tensor(t) else t)
+                 for t in out.grad_fn.saved_tensors]
+        loss = ops.mse_loss(ops.StageOut.apply(out, cout), y.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        monkeypatch.setattr(lib(), "call", orig)
+        grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
+        return out.detach().float().cpu(), saved, grads, xs.grad.float().cpu(), seen
+
+    o1, s1, g1, dx1, seen1 = run(True)
+    o0, s0, g0, dx0, seen0 = run(False)
+    assert "pcm_convblock_fwd_tc" in seen1 and "pcm_convblock_fwd_tc" not in seen0
+    assert "pcm_convblock_tail_fwd" in seen0 and "pcm_convblock_tail_fwd" not in seen1
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    rel = lambda a, b: float((a.double() - b.double()).norm() / max(float(b.double().norm()), 1e-30))
+    assert rel(o1, o0) < 1e-2, rel(o1, o0)
+    names = ["x", "y1", "a1", "y2", "small", "se", "w1", "g1", "b1", "w2", "g2", "b2", "sw1", "sw2", "wsp", "maps", "ties", "out"]
+    for nm, a, b in zip(names, s1, s0):
+        if nm == "ties":
+            assert float((a != b).float().mean()) < 0.02, nm
+        else:
+            assert rel(a, b) < 1e-2, (nm, rel(a, b))
+    errs = {k: rel(g1[k], g0[k]) for k in g0 if float(g0[k].norm()) > 1e-7}
+    assert float(np.median(list(errs.values()))) < 3e-2 and max(errs.values()) < 0.3, errs
+    assert rel(dx1, dx0) < 3e-2
+    # oracle
+    sdd = {k: v.double() for k, v in sd.items()}
+    ref = O.conv_block(x.double(), sdd, "")
+    got = o1[..., :cout].permute(0, 3, 1, 2)
+    assert rel(got, ref) < 3e-2, rel(got, ref)
