@@ -543,6 +543,17 @@ convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gam
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBlkThreads = 544;
 
+// -DPCM_BLK_PROFILE: thread 0 of CTA 0 accumulates clock64 deltas per phase over its images and prints them at exit
+#ifdef PCM_BLK_PROFILE
+#define BLK_PROF_DECL long long prof_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_c = clock64(); const bool prof_on = blockIdx.x == 0 && threadIdx.x == 0
+#define BLK_PROF(i) do { if (prof_on) { const long long c_ = clock64(); prof_t[i] += c_ - prof_c; prof_c = c_; } } while (0)
+#define BLK_PROF_PRINT() do { if (prof_on) printf("convblock_fwd_tc[%d,%d,%d,%d] cycles: prologue %lld | xwait+conv1+stats %lld  coef+zero %lld  a1 %lld  conv2+stats %lld  coef %lld  a2+pool %lld  tail %lld\n", p.H, p.W, p.Cin, C, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6], prof_t[7]); } while (0)
+#else
+#define BLK_PROF_DECL
+#define BLK_PROF(i)
+#define BLK_PROF_PRINT()
+#endif
+
 struct BlockFwdParams {
   int N, H, W, Cin, C, Cr;           // Cin = padded input channels (16 / 32 / 64), C = output channels
   int Wp, M, tiles, P;               // Wp = W + 2, M = H * Wp halo-row extent of the output, tiles = ceil(M / 128)
@@ -627,9 +638,10 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
   const TailPtrs sp = tail_ptrs(smem, L, p.C);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x, Cin = p.Cin, H = p.H, W = p.W, Wp = p.Wp, P = p.P;
+  const int Cin = p.Cin, H = p.H, W = p.W, Wp = p.Wp, P = p.P;
   constexpr int cg = C / kGroups;
   const uint32_t rb1 = (uint32_t)Cin * 2u, rb2 = (uint32_t)C * 2u;
+  BLK_PROF_DECL;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -638,47 +650,53 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
     mbar_fence_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, p.tmem_cols);
-  {  // zero the gate planes (their rings must read as zero) and the slack rows of the image region the last tile reads
+  {  // zero the gate planes once: their rings must read as zero, the interiors are rewritten for every image
     float4* z4 = reinterpret_cast<float4*>(smem + p.off_cm0);              // cm0 and cm1 are contiguous
     const int Wpl = plane_wp(W);
     for (int i = threadIdx.x; i < 2 * (H + 6) * Wpl / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t lo = (uint32_t)(p.nbox * p.box_h * Wp) * rb1, hi = (uint32_t)p.rows_a * rb1;
-    for (uint32_t o = lo + threadIdx.x * 16u; o < hi; o += NT * 16u) *reinterpret_cast<uint4*>(sImg + o) = make_uint4(0, 0, 0, 0);
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_wait();                                                  // global memory from here on
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 16) {
-    if (elect_one()) {
-      // the whole halo image of image n: nbox boxes {Cin, W+2, box_h, 1} at (0, -1, -1 + b*box_h, n)
-      mbar_expect_tx(xfull, (uint32_t)(p.nbox * p.box_h * Wp) * rb1);
-      for (int b = 0; b < p.nbox; ++b)
-        tma_load_4d(sImg + (size_t)b * p.box_h * Wp * rb1, &tmX, xfull, 0, -1, -1 + b * p.box_h, n);
-    }
-    __syncwarp();
-  }
+  // the weights of both convolutions, the gate stencil and the squeeze-excite matrices: staged ONCE per CTA, resident for
+  // every image this (persistent) CTA processes
   stage_weights(sW1, wk1, C, Cin);
   stage_weights(sW2, wk2, C, C);
   load_gate_weights(wsp, sp);
   for (int i = threadIdx.x; i < C * p.Cr; i += NT) { sp.sw1[i] = __ldg(sw1 + i); sp.sw2[i] = __ldg(sw2 + i); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
+  const int quarter = warp & 3, grp = warp >> 2;              // TMEM readers: warps 0..15
+  BLK_PROF(0);
+
+  uint32_t xphase = 0;
+  for (int n = blockIdx.x; n < p.N; n += gridDim.x, xphase ^= 1u) {
+  if (warp == 16) {
+    if (elect_one()) {
+      // the whole halo image of image n: nbox boxes {Cin, W+2, box_h, 1} at (0, -1, -1 + b*box_h, n).  The image region
+      // is free: the previous image's tail (which read it as the linear a2 image) ended with a CTA barrier.  (Plain
+      // 16-byte loads by all threads were measured slower than these boxes: 43k vs 35k cycles per image for load + conv1.)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(xfull, (uint32_t)(p.nbox * p.box_h * Wp) * rb1);
+      for (int b = 0; b < p.nbox; ++b)
+        tma_load_4d(sImg + (size_t)b * p.box_h * Wp * rb1, &tmX, xfull, 0, -1, -1 + b * p.box_h, n);
+    }
+    __syncwarp();
+  }
 
   // ---------------- conv1 on the tensor cores ----------------
   if (warp == 16) {
     if (elect_one()) {
-      if (mbar_wait(xfull, 0, err)) {
+      if (mbar_wait(xfull, xphase, err)) {
         tc_fence_after();
         issue_conv_tiles(tmem_base, smem_u32(sImg), smem_u32(sW1), p.tiles, Wp, Cin, C, tile_done);
       }
     }
     __syncwarp();
   }
-  const int quarter = warp & 3, grp = warp >> 2;              // TMEM readers: warps 0..15
 
   // Pass over this warp's tiles of a conv output in TMEM: statistics of the bf16-rounded values per GroupNorm group and
   // the copy of y for the backward pass.  phase = mbarrier parity of this convolution.
@@ -747,6 +765,7 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
   };
 
   bool ok = stats_pass(0u, y1, stats1);
+  BLK_PROF(1);
   publish_coef(g1, b1);
   // conv1 is complete (every tile barrier was waited for): the image region becomes a1's halo image — all zero first
   {
@@ -754,6 +773,7 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
     for (uint32_t o = threadIdx.x * 16u; o < bytes; o += NT * 16u) *reinterpret_cast<uint4*>(sImg + o) = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
+  BLK_PROF(2);
   // ---------------- a1 = silu(GN1(y1)): TMEM -> halo image (the next conv's operand) + global (saved for backward) ----
   if (warp < 16 && ok) {
     for (int t = grp; t < p.tiles; t += 4) {
@@ -767,8 +787,9 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
         float v[16];
         tmem_ld16(t_addr + c0, v);
         if (valid) {
+          pack8_rounded(v); pack8_rounded(v + 8);                   // the bf16 values y1 holds in memory
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = silu_raw<T>(round_to<T>(v[j]), sp.ca[c0 + j], sp.cb_[c0 + j]);
+          for (int j = 0; j < 16; ++j) v[j] = silu_raw<T>(v[j], sp.ca[c0 + j], sp.cb_[c0 + j]);
           const uint4 u0 = pack8_rounded(v), u1 = pack8_rounded(v + 8);
           *reinterpret_cast<uint4*>(sImg + swz(arow, (uint32_t)(c0 >> 3), rb2)) = u0;
           *reinterpret_cast<uint4*>(sImg + swz(arow, (uint32_t)(c0 >> 3) + 1u, rb2)) = u1;
@@ -781,6 +802,7 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of a1 -> the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
+  BLK_PROF(3);
   // ---------------- conv2 ----------------
   if (warp == 16) {
     if (elect_one()) {
@@ -790,10 +812,13 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
     __syncwarp();
   }
   ok = stats_pass(1u, y2, stats2) && ok;
+  BLK_PROF(4);
   publish_coef(g2, b2);
   __syncthreads();
+  BLK_PROF(5);
   // ---------------- a2 = silu(GN2(y2)): TMEM -> linear image [pixel][C] (conv2 is complete: the region is free) + SE pool sums
   T* s_img = reinterpret_cast<T*>(sImg);
+#pragma unroll
   for (int c0 = 0; c0 < C; c0 += 16) {
     float acc[16];
 #pragma unroll
@@ -807,8 +832,9 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
         float v[16];
         tmem_ld16(t_addr + c0, v);
         if (valid) {
+          pack8_rounded(v); pack8_rounded(v + 8);                 // the bf16 values y2 holds in memory
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = silu_raw<T>(round_to<T>(v[j]), sp.ca[c0 + j], sp.cb_[c0 + j]);
+          for (int j = 0; j < 16; ++j) v[j] = silu_raw<T>(v[j], sp.ca[c0 + j], sp.cb_[c0 + j]);
           const uint4 u0 = pack8_rounded(v), u1 = pack8_rounded(v + 8);
           uint4* dp = reinterpret_cast<uint4*>(s_img + (size_t)(h * W + w) * C + c0);
           dp[0] = u0; dp[1] = u1;
@@ -821,25 +847,31 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
     for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
     if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) sp.part[warp * 16 + j] = acc[j];
+      for (int j = 0; j < 16; ++j) sp.part[warp * C + c0 + j] = acc[j];      // one row of C partial sums per warp
     }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-      float t = 0.f;
-      for (int wv = 0; wv < NT / 32; ++wv) t += sp.part[wv * 16 + threadIdx.x];
-      sp.ch2[c0 + threadIdx.x] = t;
-    }
-    __syncthreads();
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NT) {
+    float t = 0.f;
+    for (int wv = 0; wv < NT / 32; ++wv) t += sp.part[wv * C + c];
+    sp.ch2[c] = t;
+  }
+  tc_fence_before();
+  __syncthreads();
+  BLK_PROF(6);
+  // ---------------- SE, channel maps, 7x7 gate, out = a2*se*gate ----------------
+  tail_finish_from_pool<T>(s_img, smem, L, sp, n, H, W, C, p.Cr, pool_g, se_g, hid_g, maps, ties,
+                           out + (size_t)n * P * C);
+  __syncthreads();                  // the image region and the gate planes are free for the next image
+  BLK_PROF(7);
+  }   // images
+  BLK_PROF_PRINT();
   tc_fence_before();
   __syncthreads();
   if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
-  // ---------------- SE, channel maps, 7x7 gate, out = a2*se*gate ----------------
-  tail_finish_from_pool<T>(s_img, smem, L, sp, n, H, W, C, p.Cr, pool_g, se_g, hid_g, maps, ties,
-                           out + (size_t)n * P * C);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1385,7 +1417,16 @@ extern "C" int pcm_convblock_fwd_tc(const void* x, const void* wk1, const void* 
     smem_set[ki] = smem;
   }
   typedef __nv_bfloat16 B16;
-  pcm::launch(kern, N, kBlkThreads, smem, (cudaStream_t)s, tmX, (const B16*)wk1, (const B16*)wk2, g1, b1, g2, b2, sw1, sw2, wsp,
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  // persistent CTAs (one per SM): weights, gate stencil and SE matrices are staged once per CTA, not once per image
+  const int grid = N < num_sms ? N : num_sms;
+  pcm::launch(kern, grid, kBlkThreads, smem, (cudaStream_t)s, tmX, (const B16*)wk1, (const B16*)wk2, g1, b1, g2, b2, sw1, sw2, wsp,
               (B16*)y1, (B16*)a1, (B16*)y2, stats1, stats2, pool, se, hid, maps, ties, (B16*)out, err, p);
   return check_launch("convblock_fwd_tc");
 }

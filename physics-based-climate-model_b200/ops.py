@@ -553,10 +553,12 @@ def convblock_fused_ok(H: int, W: int, C: int, Cr: int, dtype) -> bool:
 
 
 def convblock_fwd_tc_ok(H: int, W: int, Cin: int, C: int, Cr: int, dtype) -> bool:
-    """True when the whole-block forward kernel (csrc/convblock_fused.cu, convblock_fwd_tc_kernel) takes this shape.
-    PCM_BLOCK_FWD_TC=0 keeps the 4-kernel forward."""
+    """True when the whole-block forward kernel (csrc/convblock_fused.cu, convblock_fwd_tc_kernel) is selected for this
+    shape.  It is OPT-IN (PCM_BLOCK_FWD_TC=1): parity-green, but measured on B200 it only ties the 4-kernel forward at
+    48x72x16 (178-188 us vs 188 us for 384 images) and loses at the smaller levels, where the 4-kernel path overlaps
+    several small CTAs per SM (profiles/r2_convblock_fwd_tc.md has the per-phase cycle counts)."""
     import os
-    if dtype != torch.bfloat16 or os.environ.get("PCM_BLOCK_FWD_TC", "1") == "0":
+    if dtype != torch.bfloat16 or os.environ.get("PCM_BLOCK_FWD_TC", "0") != "1":
         return False
     return bool(lib()._fn["pcm_convblock_fwd_tc_supported"](H, W, Cin, C, Cr))
 
