@@ -343,8 +343,9 @@ def run_ours(args):
     if world > 1:
         # stdout carries the ONE JSON line; whatever NCCL_DEBUG level the operator set is honoured and its log goes to
         # stderr (unless the operator chose a file), so the communicator's rank count stays checkable from outside
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # (NCCL may also get its debug level from /etc/nccl.conf — this image prints the version banner even with
+        # NCCL_DEBUG unset — so the redirection is set whenever the operator has not chosen a file)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         t = torch.tensor([float(rank + 1)], device=dev)
         dist.all_reduce(t)
