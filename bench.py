@@ -342,9 +342,11 @@ def run_ours(args):
     rank_checksum = None
     if world > 1:
         # stdout carries the ONE JSON line; whatever NCCL_DEBUG level the operator set is honoured and its log goes to
-        # stderr (unless the operator chose a file), so the communicator's rank count stays checkable from outside
-        # (NCCL may also get its debug level from /etc/nccl.conf — this image prints the version banner even with
-        # NCCL_DEBUG unset — so the redirection is set whenever the operator has not chosen a file)
+        # stderr (unless the operator chose a file), so the communicator's rank count stays checkable from outside.
+        # NCCL ignores NCCL_DEBUG_FILE at level VERSION (this image's default) and prints its banner on stdout: that
+        # level, or none, is raised to WARN so that the banner follows the file setting too.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         t = torch.tensor([float(rank + 1)], device=dev)
