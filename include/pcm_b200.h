@@ -70,8 +70,17 @@ PCM_API int pcm_window_stage(const float* series, const int* frames, void* y, in
 PCM_API int pcm_pack_weight(const float* w, long long so, long long si, long long st, int O, int I, int taps, int Op,
                     int Ip, void* out, int dtype, pcm_stream_t s);
 
+/* Pixel-group form of a 3x3 / stride-1 kernel, for pcm_conv3x3_tc_grouped: `group` = g adjacent pixels of an image row
+ * are treated as ONE pixel with g times the channels, so the packed kernel is [9][g*Op][g*Ip] with
+ * out[kh*3 + s][pa*Op + o][pb*Ip + i] = base[kh*3 + dx][o][i], dx = g*(s-1) + pb - pa + 1 (zero unless 0 <= dx <= 2),
+ * base[t][o][i] = (o<O && i<I) ? w[o*so + i*si + t*st] : 0 exactly as pcm_pack_weight (forward and flipped data-gradient
+ * packings alike). */
+PCM_API int pcm_pack_weight_grouped(const float* w, long long so, long long si, long long st, int O, int I, int Op,
+                                    int Ip, int group, void* out, int dtype, pcm_stream_t s);
+
 /* every re-pack of a training step in ONE launch.  jobs: device array of records of 8 x int64:
- * {w ptr, out ptr, so, si, st, O | I<<32, taps | Op<<32, Ip | dtype<<32} (same meaning as pcm_pack_weight);
+ * {w ptr, out ptr, so, si, st, O | I<<32, taps | Op<<32, Ip | dtype<<32 | group<<40} (same meaning as pcm_pack_weight /
+ * pcm_pack_weight_grouped; group 0 or 1 = plain; a grouped job has taps*Op*Ip*group^2 outputs);
  * work: device array of nwork (job, block) int32 pairs — block b of job j covers elements [1024 b, 1024 b + 1024)
  * of that job's taps*Op*Ip outputs, so that all jobs proceed in parallel. */
 PCM_API int pcm_pack_weights_batched(const long long* jobs, const int* work, int nwork, pcm_stream_t s);
@@ -100,6 +109,15 @@ PCM_API int pcm_conv_gather(const void* src, long long src_ns, int src_ps, int H
 PCM_API int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, pcm_stream_t s);
+/* The same convolution in PIXEL-GROUP form for the thin layers (Cin, Cout = 16 / 32): TMA moves a box one pixel row
+ * (Cin*2 bytes) at a time at a fixed cost per row, which — not the tensor pipe, not HBM — bounds a 16-channel layer
+ * (32-byte rows).  Here `group` = g adjacent pixels of a row (W % g == 0, dense pixels: src_ps == Cin, dst_ps == Cout)
+ * are one GEMM row of g*Cin channels and produce g*Cout outputs, through a kernel packed by pcm_pack_weight_grouped
+ * (bf16 [9][g*Cout][g*Cin], two thirds of it useful): g times fewer, g times longer TMA rows, the same number of UMMAs
+ * (each g times wider), identical results up to the fp32 summation order.  g*Cin, g*Cout <= 64. */
+PCM_API int pcm_conv3x3_tc_grouped(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                                   long long dst_ns, int dst_ps, int Cout, const void* wk, int N, int dst_f32,
+                                   int group, pcm_stream_t s);
 /* Fused ConvLSTM step (src/convlstm.py:11-19) for t >= 1: gates = conv3x3(h_prev, Wh) [tcgen05, fp32 in TMEM]
  * + gx (= Wx.x_t + bias, fp32 [B*P][4Ch], precomputed for all T by one pcm_conv3x3_tc launch); the epilogue
  * applies sigmoid/tanh, updates c (fp32) and h (bf16) and saves the activated gates for backward — the
@@ -131,6 +149,15 @@ PCM_API int pcm_convlstm_seq_bwd_tc(const void* dh_ext, int ext_all_steps, const
 PCM_API int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                             long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
                             long long st, int N, int H, int W, pcm_stream_t s);
+/* The same weight gradient in PIXEL-GROUP form for the thin layers (dense pixels, Co and Ci in {16, 32}, group*C <= 64,
+ * W % group == 0): both tensors are fetched as images of W/group pixels with group*C channels, i.e. `group` times fewer
+ * and longer TMA box rows (the per-row cost of TMA, not HBM or the tensor pipe, bounds these layers).  An output pixel pa
+ * of a group needs the input pixels p0-1 .. p0+group of its row — group+2 consecutive pixels of the pixel-linear tile — so
+ * one UMMA per kernel row with N = (group+2)*Ci covers all three taps for every pa; accumulator lane = (pa, co),
+ * column = (kh, input pixel, ci); the epilogue adds each block to tap dx = input - output + 1. */
+PCM_API int pcm_wgrad3x3_tc_grouped(const void* dy, long long dy_ns, int Co, const void* x, long long x_ns, int Ci,
+                                    int Ci_real, float* dw, long long sa, long long sb, long long st, int N, int H,
+                                    int W, int group, pcm_stream_t s);
 /* 1x1 convolution / linear layer on the same tcgen05 pipeline (one tap): dst(n,h,w,co) = sum_ci src(n,h,w,ci)*wk[co][ci]
  * (+bias) (relu) (+= dst, fp32 only).  Call sites: the ResidualBlock skip conv (src/models.py:56), and — with the token
  * matrix [M][E] presented as an image (N=1, H*W=M) — every nn.Linear of the transformer encoder layer

@@ -24,6 +24,11 @@ def algo_cost(name: str, args):
         osz = 4 if a["dst_f32"] else 2
         by = px * (a["Cin"] * 2 + a["Cout"] * osz * (2 if a["accumulate"] else 1)) + taps * a["Cin"] * a["Cout"] * 2
         return fl, by, "tensor"
+    if name == "pcm_conv3x3_tc_grouped":               # algorithmic cost of the layer, not of the zero-padded group GEMM
+        px = a["N"] * a["H"] * a["W"]
+        fl = 2.0 * px * a["Cin"] * a["Cout"] * 9
+        by = px * (a["Cin"] * 2 + a["Cout"] * (4 if a["dst_f32"] else 2)) + 9 * a["Cin"] * a["Cout"] * 2
+        return fl, by, "tensor"
     if name == "pcm_convlstm_step_tc":
         px = a["B"] * a["H"] * a["W"]
         Ch = a["Ch"]
@@ -51,6 +56,9 @@ def algo_cost(name: str, args):
         fl = 2.0 * px * a["Co"] * a["Ci"] * taps
         by = px * (a["Co"] + a["Ci"]) * 2 + taps * a["Co_real"] * a["Ci_real"] * 4
         return fl, by, "tensor"
+    if name == "pcm_wgrad3x3_tc_grouped":
+        px = a["N"] * a["H"] * a["W"]
+        return 2.0 * px * a["Co"] * a["Ci"] * 9, px * (a["Co"] + a["Ci"]) * 2 + 9 * a["Co"] * a["Ci_real"] * 4, "tensor"
     if name == "pcm_convT2x2_tc":          # H, W = input grid; output has 4x the pixels
         px = a["N"] * a["H"] * a["W"]
         return 2.0 * px * a["Cin"] * 4 * a["Cout"], px * (a["Cin"] + 4 * a["Cout"]) * 2 + 4 * a["Cin"] * a["Cout"] * 2, "tensor"

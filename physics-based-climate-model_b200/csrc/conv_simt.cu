@@ -8,25 +8,36 @@ namespace pcm {
 // ------------------------------------------------------------------------------------------------
 // weight packing: out[t][o][i] = w[o*so + i*si + t*st] (zero padded)
 // ------------------------------------------------------------------------------------------------
+// Pixel-group form of a 3x3 / stride-1 kernel (group = g adjacent pixels of a row act as ONE pixel with g times the
+// channels; see pcm_conv3x3_tc_grouped): out[kh*3 + s][pa*Op + o][pb*Ip + i] = base[kh*3 + dx][o][i] with
+// dx = g*(s-1) + pb - pa + 1 when 0 <= dx <= 2, else 0 — output pixel pa of a group sees input pixel pb of the group
+// s-1 groups to the right through tap dx.  base[t][o][i] = (o<O && i<I) ? w[o*so + i*si + t*st] : 0 as below.
+__device__ __forceinline__ float pack_weight_value(const float* __restrict__ w, long long so, long long si, long long st,
+                                                   int O, int I, int Op, int Ip, int g, unsigned idx) {
+  const unsigned Ig = (unsigned)Ip * g, Og = (unsigned)Op * g;
+  int i = (int)(idx % Ig), o = (int)((idx / Ig) % Og), t = (int)(idx / (Ig * Og));
+  if (g > 1) {
+    const int pb = i / Ip, pa = o / Op, kh = t / 3, s = t - kh * 3;
+    i -= pb * Ip; o -= pa * Op;
+    const int dx = g * (s - 1) + pb - pa + 1;
+    if (dx < 0 || dx > 2) return 0.f;
+    t = kh * 3 + dx;
+  }
+  return (o < O && i < I) ? __ldg(w + o * so + i * si + (long long)t * st) : 0.f;
+}
+
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, long long so, long long si, long long st, int O, int I,
-                                   int taps, int Op, int Ip, T* __restrict__ out) {
+                                   int taps, int Op, int Ip, int g, T* __restrict__ out) {
   PCM_PDL_ENTRY();
-  const long long total = (long long)taps * Op * Ip;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx % Ip);
-    const int o = (int)((idx / Ip) % Op);
-    const int t = (int)(idx / ((long long)Ip * Op));
-    float v = 0.f;
-    if (o < O && i < I) v = __ldg(w + o * so + i * si + t * st);
-    out[idx] = from_f<T>(v);
-  }
+  const unsigned total = (unsigned)taps * Op * Ip * g * g;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    out[idx] = from_f<T>(pack_weight_value(w, so, si, st, O, I, Op, Ip, g, idx));
 }
 
 // All weight re-packs of a training step in ONE launch: blockIdx.y = job, the x-grid strides over that job's
 // elements.  Job record (8 x int64, device memory): w ptr, out ptr, so, si, st, (O | I << 32), (taps | Op << 32),
-// (Ip | dtype << 32).
+// (Ip | dtype << 32 | group << 40).
 // Work item = (job, 1024-element block of that job): blockIdx.x indexes the flattened work list the host built, so
 // every job proceeds in parallel (a per-thread sweep over the jobs serialises ~2 us of memory latency per job).
 constexpr int kBatchBlockElems = 1024;
@@ -41,16 +52,15 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
   const long long so = j[2], si = j[3], st = j[4];
   const int O = (int)(j[5] & 0xffffffffll), I = (int)(j[5] >> 32);
   const int taps = (int)(j[6] & 0xffffffffll), Op = (int)(j[6] >> 32);
-  const int Ip = (int)(j[7] & 0xffffffffll), dtype = (int)(j[7] >> 32);
-  const unsigned total = (unsigned)taps * Op * Ip, plane = (unsigned)Op * Ip;
+  const int Ip = (int)(j[7] & 0xffffffffll), dtype = (int)((j[7] >> 32) & 0xff);
+  int g = (int)((j[7] >> 40) & 0xff);                       // pixel-group factor (0 / 1: plain)
+  if (g < 1) g = 1;
+  const unsigned total = (unsigned)taps * Op * Ip * g * g;
 #pragma unroll
   for (int r = 0; r < kBatchBlockElems / 256; ++r) {
     const unsigned idx = (unsigned)blk * kBatchBlockElems + r * 256 + threadIdx.x;
     if (idx >= total) break;
-    const unsigned t = idx / plane, rem = idx - t * plane;
-    const int o = (int)(rem / (unsigned)Ip), i = (int)(rem - (unsigned)o * Ip);
-    float v = 0.f;
-    if (o < O && i < I) v = __ldg(w + o * so + i * si + (long long)t * st);
+    const float v = pack_weight_value(w, so, si, st, O, I, Op, Ip, g, idx);
     if (dtype == PCM_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(out)[idx] = v;
   }
@@ -321,8 +331,19 @@ extern "C" int pcm_pack_weight(const float* w, long long so, long long si, long 
   const long long total = (long long)taps * Op * Ip;
   const int blocks = (int)min((long long)1184, (total + 255) / 256);
   PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(pack_weight_kernel<T>, blocks, 256, 0, (cudaStream_t)s, 
-                                   w, so, si, st, O, I, taps, Op, Ip, (T*)out)));
+                                   w, so, si, st, O, I, taps, Op, Ip, 1, (T*)out)));
   return check_launch("pack_weight");
+}
+
+extern "C" int pcm_pack_weight_grouped(const float* w, long long so, long long si, long long st, int O, int I, int Op,
+                                       int Ip, int group, void* out, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(O <= Op && I <= Ip && group >= 1 && group <= 8, "pack_weight_grouped: bad sizes");
+  const long long total = 9ll * Op * Ip * group * group;
+  PCM_REQUIRE(total < (1ll << 31), "pack_weight_grouped: too large");
+  const int blocks = (int)min((long long)1184, (total + 255) / 256);
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(pack_weight_kernel<T>, blocks, 256, 0, (cudaStream_t)s,
+                                   w, so, si, st, O, I, 9, Op, Ip, group, (T*)out)));
+  return check_launch("pack_weight_grouped");
 }
 
 extern "C" int pcm_pack_weights_batched(const long long* jobs, const int* work, int nwork, pcm_stream_t s) {

@@ -333,6 +333,8 @@ struct ConvHaloParams {
   long long dst_ns;
   int dst_ps, dst_f32, accumulate;
   uint32_t tmem_cols, acc_stride, a_chunk_bytes, a_stage_bytes, a_tx_bytes, b_chunk_bytes, b_bytes;
+  uint32_t kmask[3];    // per kernel column kw: the 16-channel K steps whose weights are not identically zero (all ones
+                        // for a plain layer; the pixel-group form skips the all-zero blocks of its shifted taps)
 };
 
 template <int KSTEPS>   // KC / 16
@@ -407,6 +409,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       const uint32_t a_step = p.a_stage_bytes >> 4, a_chunk = p.a_chunk_bytes >> 4, b_chunk = p.b_chunk_bytes >> 4;
       const int nstages = p.stages, ntiles = p.num_tiles, acc_stride = p.acc_stride, kchunks = p.kchunks;
+      const uint32_t km[3] = {p.kmask[0], p.kmask[1], p.kmask[2]};
       int stage = 0, it = 0;
       uint32_t phase = 0;
       bool ok = mbar_wait(bfull, 0, err);
@@ -420,14 +423,18 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         const uint64_t abase = adesc0 + (uint64_t)(stage * a_step);
+        uint32_t accum = 0;
         for (int kc = 0; kc < kchunks; ++kc) {
           const uint64_t ab = abase + (uint64_t)(kc * a_chunk), bb = bdesc0 + (uint64_t)(kc * b_chunk);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_bf16(d_tmem, ab + (uint64_t)(a_off[tap] + 2 * k), bb + (uint64_t)(b_off[tap] + 2 * k), idesc,
-                        (kc | tap | k) != 0);
+            for (int k = 0; k < KSTEPS; ++k) {
+              if ((km[tap % 3] >> k) & 1u) {
+                umma_bf16(d_tmem, ab + (uint64_t)(a_off[tap] + 2 * k), bb + (uint64_t)(b_off[tap] + 2 * k), idesc, accum);
+                accum = 1;
+              }
+            }
           }
         }
         umma_commit(&empty[stage]);
@@ -596,7 +603,8 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, const float* lstm_gx, const float* lstm_c_prev,
                            float* lstm_c_out, void* lstm_acts, pcm_stream_t s, int ksz = 3, int relu = 0, int mode = 0,
-                           int ps_co = 0, int pad = -1) {
+                           int ps_co = 0, int pad = -1, int group = 1) {
+  // group > 1: pcm_conv3x3_tc_grouped — H, W, Cin, Cout are already those of the grouped image (W/g pixels of g*C channels)
   PCM_REQUIRE(Cin % 16 == 0 && Cin >= 16, "conv3x3_tc: Cin must be a multiple of 16 (got %d)", Cin);
   PCM_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv3x3_tc: Cin above 64 must be a multiple of 64 (got %d)", Cin);
   PCM_REQUIRE(Cin == 16 || Cin == 32 || Cin >= 64, "conv3x3_tc: unsupported Cin %d", Cin);
@@ -647,6 +655,14 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     h.tiles_h = (H + h.Hb - 1) / h.Hb;
     h.num_tiles = h.tiles_w * h.tiles_h * ((N + h.Nb - 1) / h.Nb);
     h.dst_ns = dst_ns; h.dst_ps = dst_ps; h.dst_f32 = dst_f32; h.accumulate = accumulate;
+    h.kmask[0] = h.kmask[1] = h.kmask[2] = 0xffffffffu;
+    if (group > 1) {
+      // shifted taps of the pixel-group kernel: the group to the left contributes through its LAST pixel only, the group
+      // to the right through its FIRST (pcm_pack_weight_grouped: dx = g*(s-1) + pb - pa + 1 in [0, 2])
+      const int c16 = Cin / group / 16;                            // K steps per pixel of the group
+      h.kmask[0] = ((1u << c16) - 1u) << ((group - 1) * c16);
+      h.kmask[2] = (1u << c16) - 1u;
+    }
     h.acc_stride = cslice < 32 ? 32 : cslice;
     uint32_t cols = 32;
     while (cols < 2 * h.acc_stride) cols <<= 1;
@@ -664,6 +680,11 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
     const size_t b_region = ((size_t)h.b_bytes + 1023) & ~(size_t)1023;
     int stages = (int)(((Cin <= 32 ? 160 : 212) * 1024 - b_region) / h.a_stage_bytes);
     if (stages > 6) stages = 6;
+    {
+      static int cap = -1;                       // PCM_HALO_STAGES: cap the pipeline depth (A/B experiments)
+      if (cap < 0) { const char* e = getenv("PCM_HALO_STAGES"); cap = e ? atoi(e) : 0; }
+      if (cap > 0 && stages > cap) stages = cap;
+    }
     if (stages < 2) stages = 2;
     h.stages = stages;
     const size_t smem = 1024 + b_region + (size_t)stages * h.a_stage_bytes + (2 * stages + 5) * sizeof(uint64_t) + 16;
@@ -782,6 +803,17 @@ extern "C" int pcm_conv3x3_tc(const void* src, long long src_ns, int src_ps, int
                               int dst_f32, int accumulate, pcm_stream_t s) {
   return conv3x3_tc_impl(src, src_ns, src_ps, H, W, Cin, dst, dst_ns, dst_ps, Cout, wk, bias, N, dst_f32, accumulate,
                          nullptr, nullptr, nullptr, nullptr, s);
+}
+
+extern "C" int pcm_conv3x3_tc_grouped(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                                      long long dst_ns, int dst_ps, int Cout, const void* wk, int N, int dst_f32,
+                                      int group, pcm_stream_t s) {
+  PCM_REQUIRE(group >= 1 && W % group == 0, "conv3x3_tc_grouped: W (%d) must be a multiple of the group (%d)", W, group);
+  PCM_REQUIRE(src_ps == Cin && dst_ps == Cout, "conv3x3_tc_grouped: pixels must be dense (src_ps %d / Cin %d, dst_ps %d / Cout %d)",
+              src_ps, Cin, dst_ps, Cout);
+  PCM_REQUIRE(group * Cin <= 64 && group * Cout <= 64, "conv3x3_tc_grouped: group*Cin and group*Cout must be <= 64");
+  return conv3x3_tc_impl(src, src_ns, src_ps * group, H, W / group, Cin * group, dst, dst_ns, dst_ps * group, Cout * group,
+                         wk, nullptr, N, dst_f32, 0, nullptr, nullptr, nullptr, nullptr, s, 3, 0, 0, 0, -1, group);
 }
 
 extern "C" int pcm_convlstm_step_tc(const void* h_prev, const void* wh, const float* gx, const float* c_prev,

@@ -30,6 +30,10 @@ struct WgradTcParams {
   int convt;                    // 1: ConvTranspose2d(k2,s2) weight gradient — 4 taps (kh,kw); tap q's B tile is its own
                                 //    sub-tile, gathered from pixels (2h+kh, 2w+kw) through the 5-D views tmB / tmB2
   uint32_t b_sub_bytes;         // convt: bytes of one tap's B sub-tile (all chunks)
+  int group, Cog, Cig;          // pixel-group form (group > 1): `group` adjacent pixels of a row are one K row with group*C
+                                // channels; Cog / Cig = channels of ONE pixel (M index = pa*Cog + co, B row = pb*Cig + ci)
+  int ncol, sub16;              // wide / group: N extent of the MMA of one kernel row; group: B start offset inside a row (>>4)
+  int noatomic;                 // PCM_WGRAD_NOATOMIC=1 (measurement only): skip the global reductions of the epilogue
   int stages;
   int bx0;                      // first column of the x box in its tensor map (-pad; 0 for an interior column strip)
   long long sa, sb, st;
@@ -121,7 +125,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // operand (128 rows, re-read from shared memory by every MMA) is then read ksz times less often — for the
       // thin layers the kernel was bound by exactly that read (ncu: 68 cycles per N=16 MMA, tensor pipe 12 %).
       const int wide = p.wide;
-      const uint32_t idesc = make_idesc_bf16(128, wide ? p.ksz * p.Ci : p.Ci, 1, 1);
+      const uint32_t idesc = make_idesc_bf16(128, wide ? p.ncol : p.Ci, 1, 1);
       const uint64_t adesc0 = make_smem_desc(smem_u32(sA), p.lbo_a, 8 * rba, layout_type_for_row_bytes(rba));
       const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), wide ? rbb : p.lbo_b, 8 * rbb, layout_type_for_row_bytes(rbb));
       const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
@@ -131,7 +135,16 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // per-issue offsets of this group: B start-address offset and TMEM column offset (at most 9)
       uint32_t b_off[9], d_off[9];
       int nissue = 0;
-      if (wide) {
+      if (p.group > 1) {
+        // pixel-group form: output pixel pa of a group sees input pixels p0-1 .. p0+g of the row (p0 = first pixel of the
+        // group) — g+2 CONSECUTIVE pixels of the pixel-linear tile, starting g-1 pixels into the group to the left: one MMA
+        // per kernel row with N = (g+2)*Cig, its B start address advanced by that sub-row offset (the swizzle is a function
+        // of the absolute address, so a 16-byte-granular start inside a row is exact like the row shifts are)
+        for (int kh = 0; kh < 3; ++kh) {
+          b_off[nissue] = (uint32_t)kh * b_tap_row + (uint32_t)p.sub16;
+          d_off[nissue++] = (uint32_t)(kh * p.ncol);
+        }
+      } else if (wide) {
         for (int tl = 0; tl < ntap; tl += p.ksz) {
           b_off[nissue] = (uint32_t)((tap0 + tl) / p.ksz) * b_tap_row;
           d_off[nissue++] = (uint32_t)(tl * ci);
@@ -169,8 +182,57 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int q = warp & 3;
     const int co = mtile * 128 + q * 32 + lane;
     bool ok = my_tiles > 0 ? mbar_wait(done, 0, err) : false;
-    ok = __all_sync(0xffffffffu, ok);
-    if (ok) {
+    ok = __all_sync(0xffffffffu, ok) && !p.noatomic;
+    if (ok && p.group > 1) {
+      // pixel-group form: lane = (pa, co), column = (kh, j, ci) with input pixel p0 - 1 + j; tap dx = j - pa.  The g values
+      // of one (co, kh, dx, ci) sit in lanes of different pa: they are summed in shared memory (the pipeline stages are
+      // idle by now), one pass per pa — pass 0 stores, the others add, a 128-thread barrier in between — and the CTA then
+      // issues ONE vector reduction per 4 outputs, as the plain form does (g times fewer atomics on the same addresses).
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int m = q * 32 + lane, pa_l = m / p.Cog, cog = m - pa_l * p.Cog;
+      const int pa_first = (q * 32) / p.Cog, pa_last = (q * 32 + 31) / p.Cog;      // pa values held by this warp
+      float* acc = reinterpret_cast<float*>(smem);                                  // [9][Cog][Cig]
+      const int blocks = p.Cig >> 4;
+      for (int pa = 0; pa < p.group; ++pa) {
+        if (pa >= pa_first && pa <= pa_last) {
+          for (int t = 0; t < 9; ++t) {
+            const int kh = t / 3, dxx = t - kh * 3;
+            for (int b = 0; b < blocks; ++b) {
+              float v[16];
+              tmem_ld16(t_addr + kh * p.ncol + (dxx + pa) * p.Cig + b * 16, v);
+              if (pa_l == pa) {
+                float4* d = reinterpret_cast<float4*>(acc + ((size_t)t * p.Cog + cog) * p.Cig + b * 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float4 o = pa ? d[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                  o.x += v[4 * k]; o.y += v[4 * k + 1]; o.z += v[4 * k + 2]; o.w += v[4 * k + 3];
+                  d[k] = o;
+                }
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const int et = threadIdx.x - 64;                                              // 0..127 over the epilogue warps
+      const int nv4 = 9 * p.Cog * p.Cig / 4, per_row = p.Cig / 4;
+      for (int i = et; i < nv4; i += 128) {
+        const int row = i / per_row, c4 = i - row * per_row;                        // row = t*Cog + co
+        const int t = row / p.Cog, co = row - t * p.Cog;
+        const float4 v = reinterpret_cast<const float4*>(acc)[i];
+        float* base = dw + (long long)co * p.sa + (long long)t * p.st;
+        if (p.sb == 1) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + c4 * 4), "f"(v.x), "f"(v.y), "f"(v.z),
+                       "f"(v.w) : "memory");
+        } else {
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c4 * 4 + k < p.Ci_real) atomicAdd(base + (long long)(c4 * 4 + k) * p.sb, e[k]);
+        }
+      }
+    } else if (ok) {
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       const int ncols = ntap * p.Ci;
@@ -216,7 +278,16 @@ using namespace pcm;
 static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                          long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
                          long long st, int N, int H, int W, int ksz, pcm_stream_t s, int convt = 0, int Wfull = 0,
-                         int w0 = 0) {
+                         int w0 = 0, int group = 1) {
+  // group > 1 (pixel-group form, 3x3 only): the kernel sees images of W/group pixels with group*C channels; Ci_real keeps
+  // its per-pixel meaning
+  const int Cog = Co, Cig = Ci;
+  if (group > 1) {
+    PCM_REQUIRE(convt == 0 && ksz == 3 && Wfull <= 0 && W % group == 0, "wgrad3x3_tc: pixel groups need a 3x3 layer and W %% group == 0");
+    PCM_REQUIRE(dy_ps == Co && x_ps == Ci && Co == Co_real, "wgrad3x3_tc: pixel groups need dense pixels");
+    PCM_REQUIRE(group * Co <= 64 && group * Ci <= 64, "wgrad3x3_tc: group*C must be <= 64");
+    Co *= group; Co_real = Co; Ci *= group; W /= group; dy_ps *= group; x_ps *= group;
+  }
   // Wfull > 0: this call covers the column strip [w0, w0 + W) of images that are Wfull pixels wide (grids whose rows do
   // not fit one TMA box, e.g. 360 columns): dy is viewed as a W-wide tensor starting at column w0 (everything outside
   // the strip is out of bounds = zero, so it contributes nothing), x as the strip plus its real neighbour columns.
@@ -298,7 +369,19 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
     wide_env = e ? atoi(e) : 1;
   }
   p.wide = (wide_env && !convt && ksz == 3 && p.nb_chunks == 1 && 3 * Ci <= 256) ? 1 : 0;
-  if (p.wide) {
+  p.group = group; p.Cog = Cog; p.Cig = Cig;
+  {
+    static int na = -1;
+    if (na < 0) { const char* e = getenv("PCM_WGRAD_NOATOMIC"); na = e ? atoi(e) : 0; }
+    p.noatomic = na;
+  }
+  p.ncol = ksz * Ci; p.sub16 = 0;
+  if (group > 1) {
+    p.wide = 1;
+    p.ncol = (group + 2) * Cig; p.sub16 = (group - 1) * Cig * 2 / 16;
+    PCM_REQUIRE(3 * p.ncol <= 512 && p.ncol <= 256, "wgrad3x3_tc: pixel-group accumulator does not fit tensor memory");
+    p.tpg = 9; p.ngroups = 1;
+  } else if (p.wide) {
     int rows = 512 / (3 * Ci);                                  // whole kernel rows per group (TMEM: 512 columns)
     if (rows > 3) rows = 3;
     p.tpg = 3 * rows;
@@ -310,7 +393,7 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
     p.tpg = (ntaps + p.ngroups - 1) / p.ngroups;                // balance the groups
   }
   uint32_t cols = 32;
-  while (cols < (uint32_t)(p.tpg * Ci)) cols <<= 1;
+  while (cols < (uint32_t)(group > 1 ? 3 * p.ncol : p.tpg * Ci)) cols <<= 1;
   p.tmem_cols = cols;
   const size_t per_stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
   int stages = (int)((200 * 1024) / per_stage);
@@ -389,6 +472,12 @@ extern "C" int pcm_wgrad3x3_tc(const void* dy, long long dy_ns, int dy_ps, int C
     if (rc != PCM_OK) return rc;
   }
   return PCM_OK;
+}
+
+extern "C" int pcm_wgrad3x3_tc_grouped(const void* dy, long long dy_ns, int Co, const void* x, long long x_ns, int Ci,
+                                       int Ci_real, float* dw, long long sa, long long sb, long long st, int N, int H,
+                                       int W, int group, pcm_stream_t s) {
+  return wgrad_tc_impl(dy, dy_ns, Co, Co, Co, x, x_ns, Ci, Ci, Ci_real, dw, sa, sb, st, N, H, W, 3, s, 0, 0, 0, group);
 }
 
 extern "C" int pcm_wgrad1x1_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,

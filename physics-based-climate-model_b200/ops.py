@@ -249,28 +249,50 @@ class use_pack_plan:
 
 
 def pack_weight(w: torch.Tensor, so: int, si: int, st: int, O: int, I: int, taps: int, dtype, offset: int = 0,
-                Op: Optional[int] = None, Ip: Optional[int] = None):
-    """out[t][o][i] = w.flatten()[offset + o*so + i*si + t*st], zero padded to (taps, Op, Ip)."""
+                Op: Optional[int] = None, Ip: Optional[int] = None, group: int = 1):
+    """out[t][o][i] = w.flatten()[offset + o*so + i*si + t*st], zero padded to (taps, Op, Ip).
+    group > 1 (3x3 kernels only): the pixel-group form (9, group*Op, group*Ip) of pcm_pack_weight_grouped."""
     Op = pad8(O) if Op is None else Op
     Ip = pad8(I) if Ip is None else Ip
     src = w.data_ptr() + 4 * offset
     if _PLAN is not None:
-        key = (src, so, si, st, O, I, taps, Op, Ip, dtype)
+        key = (src, so, si, st, O, I, taps, Op, Ip, dtype, group)
         hit = _PLAN.lookup(key)
         if hit is not None:
             return hit
-    out = torch.empty((taps, Op, Ip), device=w.device, dtype=dtype)
-    _call("pcm_pack_weight", src, so, si, st, O, I, taps, Op, Ip, out.data_ptr(), _DT[dtype], _s())
+    out = torch.empty((taps, group * Op, group * Ip), device=w.device, dtype=dtype)
+    if group > 1:
+        assert taps == 9
+        _call("pcm_pack_weight_grouped", src, so, si, st, O, I, Op, Ip, group, out.data_ptr(), _DT[dtype], _s())
+    else:
+        _call("pcm_pack_weight", src, so, si, st, O, I, taps, Op, Ip, out.data_ptr(), _DT[dtype], _s())
     if _PLAN is not None:
         _PLAN.register(key, out, [src, out.data_ptr(), so, si, st, O | (I << 32), taps | (Op << 32),
-                                  Ip | (_DT[dtype] << 32)])
+                                  Ip | ((_DT[dtype] | ((group if group > 1 else 0) << 8)) << 32)])
     return out
 
 
+def conv_group(dtype, Sc: int, Dc: int, W: int, dense: bool = True) -> int:
+    """Pixel-group factor for a thin 3x3 layer on the tensor-core path (pcm_conv3x3_tc_grouped): g adjacent pixels
+    of a row become one GEMM row of g*Sc channels, which divides the number of TMA box rows — the measured bound of
+    the 16- and 32-channel layers — by g.  1 = plain form.  PCM_CONV_GROUP=0 disables, =2 caps the factor at 2;
+    PCM_CONV_GROUP_MAXC (default 16) is the widest layer (max of Sc, Dc) that is grouped."""
+    import os
+    cap = int(os.environ.get("PCM_CONV_GROUP", "4"))
+    maxc = int(os.environ.get("PCM_CONV_GROUP_MAXC", "16"))
+    if cap < 2 or not dense or dtype != torch.bfloat16 or Sc % 16 or Dc % 16 or max(Sc, Dc) > min(maxc, 32):
+        return 1
+    g = min(cap, 64 // max(Sc, Dc))
+    g = 4 if g >= 4 else 2 if g >= 2 else 1
+    while g > 1 and W % g:
+        g //= 2
+    return g
+
+
 def conv_weight_fwd(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None, Ip: Optional[int] = None,
-                    co_split: int = 0):
+                    co_split: int = 0, group: int = 1):
     """nn.Conv2d weight (Co, Ci_tot, KH, KW) -> [taps][Co][Ci] (forward, gather mode 0).  co_split > 0: a list of
-    packed slices of co_split output channels each (see conv_s1)."""
+    packed slices of co_split output channels each (see conv_s1).  group > 1: pixel-group form (conv_group)."""
     Co, Ci_tot, KH, KW = w.shape
     ci = Ci_tot - ci_off if ci is None else ci
     K = KH * KW
@@ -278,16 +300,17 @@ def conv_weight_fwd(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] =
         assert Co % co_split == 0
         return [pack_weight(w, Ci_tot * K, K, 1, co_split, ci, K, dtype, offset=c0 * Ci_tot * K + ci_off * K, Ip=Ip)
                 for c0 in range(0, Co, co_split)]
-    return pack_weight(w, Ci_tot * K, K, 1, Co, ci, K, dtype, offset=ci_off * K, Ip=Ip)
+    return pack_weight(w, Ci_tot * K, K, 1, Co, ci, K, dtype, offset=ci_off * K, Ip=Ip, group=group)
 
 
-def conv_weight_dgrad(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None, Op: Optional[int] = None):
+def conv_weight_dgrad(w: torch.Tensor, dtype, ci_off: int = 0, ci: Optional[int] = None, Op: Optional[int] = None,
+                      group: int = 1):
     """nn.Conv2d weight (stride 1, odd K) -> [taps][Ci][Co] with the taps FLIPPED, so the data gradient
-    is itself a forward (mode 0) convolution of dy: dx = conv(dy, flip(W)^T)."""
+    is itself a forward (mode 0) convolution of dy: dx = conv(dy, flip(W)^T).  group > 1: pixel-group form."""
     Co, Ci_tot, KH, KW = w.shape
     ci = Ci_tot - ci_off if ci is None else ci
     K = KH * KW
-    return pack_weight(w, K, Ci_tot * K, -1, ci, Co, K, dtype, offset=ci_off * K + K - 1, Op=Op)
+    return pack_weight(w, K, Ci_tot * K, -1, ci, Co, K, dtype, offset=ci_off * K + K - 1, Op=Op, group=group)
 
 
 def tc_supported(dtype, Sc: int, Dc: int, K: int = 3) -> bool:
@@ -298,11 +321,21 @@ def tc_supported(dtype, Sc: int, Dc: int, K: int = 3) -> bool:
 
 
 def conv_s1(src, wk, N, H, W, Sc, Dc, K=3, dst=None, dst_f32=False, bias=None, accumulate=False,
-            src_ns=None, src_ps=None, dst_ns=None, dst_ps=None, src_off=0, dst_off=0):
+            src_ns=None, src_ps=None, dst_ns=None, dst_ps=None, src_off=0, dst_off=0, group=1):
     """Stride-1 'same' convolution dst = conv(src, wk) on NHWC views; wk = [K*K][Dc][Sc], or a list of such tensors
     holding consecutive output-channel slices (outputs wider than one 256-column accumulator, e.g. the 512 gate
-    channels of the base-32 ConvLSTM: one launch per slice into its channel range of dst)."""
+    channels of the base-32 ConvLSTM: one launch per slice into its channel range of dst).
+    group > 1: wk is the pixel-group packing [9][group*Dc][group*Sc] (conv_group / conv_weight_*(group=...)); dense
+    pixels on both sides, no bias."""
     dtype = src.dtype
+    if group > 1:
+        assert K == 3 and bias is None and not accumulate and src_ps in (None, Sc) and dst_ps in (None, Dc)
+        if dst is None:
+            dst = torch.empty((N, H, W, Dc), device=src.device, dtype=torch.float32 if dst_f32 else dtype)
+        _call("pcm_conv3x3_tc_grouped", src.data_ptr() + src_off * src.element_size(),
+              H * W * Sc if src_ns is None else src_ns, Sc, H, W, Sc, dst.data_ptr() + dst_off * dst.element_size(),
+              H * W * Dc if dst_ns is None else dst_ns, Dc, Dc, wk.data_ptr(), N, int(dst_f32), group, _s())
+        return dst
     if isinstance(wk, (list, tuple)):
         if dst is None:
             dst = torch.empty((N, H, W, Dc), device=src.device, dtype=torch.float32 if dst_f32 else dtype)
@@ -364,6 +397,21 @@ def wgrad_tc_supported(dtype, Co: int, Ci: int, H: int, W: int) -> bool:
             and Ci in (16, 32, 64, 128, 192, 256) and H + 2 <= 256)
 
 
+def wgrad_group(dtype, Co: int, Ci: int, W: int, dense: bool = True) -> int:
+    """Pixel-group factor of the tensor-core weight gradient (pcm_wgrad3x3_tc_grouped) for the thin layers; 1 = plain.
+    PCM_WGRAD_GROUP=0 disables, =2 caps the factor; PCM_WGRAD_GROUP_MAXC (default 32) = widest layer that is grouped."""
+    import os
+    cap = int(os.environ.get("PCM_WGRAD_GROUP", "4"))
+    maxc = int(os.environ.get("PCM_WGRAD_GROUP_MAXC", "32"))
+    if cap < 2 or not dense or dtype != torch.bfloat16 or Co not in (16, 32) or Ci not in (16, 32) or max(Co, Ci) > maxc:
+        return 1
+    g = min(cap, 64 // max(Co, Ci))
+    g = 4 if g >= 4 else 2 if g >= 2 else 1
+    while g > 1 and (W % g or 3 * (g + 2) * Ci > 512):
+        g //= 2
+    return g
+
+
 def conv3x3_wgrad(dy, x, dw, N, H, W, Co, Ci, Ci_real, Ci_tot=None, dy_ns=None, dy_ps=None, x_ns=None, x_ps=None,
                   dy_off=0, x_off=0, dw_off=0):
     """dw[co][ci_off + ci][tap] += sum_p dy(p, co) * x(p + tap, ci) for the 3x3/s1/p1 convolution.
@@ -375,6 +423,15 @@ def conv3x3_wgrad(dy, x, dw, N, H, W, Co, Ci, Ci_real, Ci_tot=None, dy_ns=None, 
     x_ns = H * W * x_ps if x_ns is None else x_ns
     if wgrad_tc_supported(dy.dtype, Co, Ci, H, W):
         packed = _PLAN.grad_pack(dw, Co, Ci_tot, 9) if _PLAN is not None else None
+        grp = wgrad_group(dy.dtype, Co, Ci, W, dy_ps == Co and x_ps == Ci)
+        if grp > 1:
+            if packed is not None:
+                dst, sa, sb, st = packed.data_ptr() + 4 * (dw_off // 9), packed.shape[-1], 1, Co * packed.shape[-1]
+            else:
+                dst, sa, sb, st = dw.data_ptr() + 4 * dw_off, Ci_tot * 9, 9, 1
+            _call("pcm_wgrad3x3_tc_grouped", dy.data_ptr() + dy_off * dy.element_size(), dy_ns, Co,
+                  x.data_ptr() + x_off * x.element_size(), x_ns, Ci, Ci_real, dst, sa, sb, st, N, H, W, grp, _s())
+            return
         if packed is not None:
             # reduce into the packed [tap][Co][Cpad] buffer (16-byte vector atomics); PackPlan.unpack_grads folds
             # every layer's buffer into the parameter-layout gradient in one launch after backward
@@ -578,8 +635,11 @@ class ConvBlockFn(torch.autograd.Function):
         fused = convblock_fused_ok(H, W, Co, Cr, dt)
         ctx.fused = fused
         ctx.dims = (N, H, W, Cip, Ci, Co, Cr)
-        wk1 = conv_weight_fwd(w1, dt, Ip=Cip)
-        wk2 = conv_weight_fwd(w2, dt)
+        ga, gb = (conv_group(dt, Cip, Co, W), conv_group(dt, Co, Co, W)) if fused else (1, 1)
+        if fused and convblock_fwd_tc_ok(H, W, Cip, Co, Cr, dt):
+            ga = gb = 1
+        wk1 = conv_weight_fwd(w1, dt, Ip=Cip, group=ga)
+        wk2 = conv_weight_fwd(w2, dt, group=gb)
         if fused and convblock_fwd_tc_ok(H, W, Cip, Co, Cr, dt):
             # the whole block forward in ONE launch: both convolutions on the tensor cores over the shared-memory
             # resident image, conv outputs in tensor memory, a1 written straight into conv2's operand image
@@ -603,11 +663,11 @@ class ConvBlockFn(torch.autograd.Function):
             stats1, stats2, pool = small[: N * G * 2], small[N * G * 2: N * G * 4], small[N * G * 4:]
             se = torch.empty(N * Co + N * Cr, device=dev, dtype=torch.float32)
             hid = se[N * Co:]
-            y1 = conv_s1(x, wk1, N, H, W, Cip, Co)
+            y1 = conv_s1(x, wk1, N, H, W, Cip, Co, group=ga)
             a1 = torch.empty_like(y1)
             _call("pcm_gn_silu_img_fwd", y1.data_ptr(), g1.data_ptr(), b1.data_ptr(), stats1.data_ptr(), a1.data_ptr(),
                   N, H, W, Co, GN_EPS, d, st)
-            y2 = conv_s1(a1, wk2, N, H, W, Co, Co)
+            y2 = conv_s1(a1, wk2, N, H, W, Co, Co, group=gb)
             out = torch.empty_like(y2)
             # saved for the backward tail: channel mean / max maps and the gate (fp32) + tie counts of the max
             maps = torch.empty(N * P * 3, device=dev, dtype=torch.float32)
@@ -716,8 +776,9 @@ class ConvBlockFn(torch.autograd.Function):
               gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
         with side_stream(dy2, a1):
             conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
-        wk2t = conv_weight_dgrad(w2, dt)
-        da1 = conv_s1(dy2, wk2t, N, H, W, Co, Co)
+        gb = conv_group(dt, Co, Co, W)
+        wk2t = conv_weight_dgrad(w2, dt, group=gb)
+        da1 = conv_s1(dy2, wk2t, N, H, W, Co, Co, group=gb)
         dy1 = torch.empty_like(y1) if side_active() else dy2          # dy2 storage is reused unless a side kernel reads it
         _call("pcm_gn_silu_img_bwd", da1.data_ptr(), y1.data_ptr(), stats1.data_ptr(), g1.data_ptr(), b1.data_ptr(),
               dy1.data_ptr(), gg1.data_ptr(), gb1.data_ptr(), N, H, W, Co, GN_EPS, d, st)
@@ -725,8 +786,9 @@ class ConvBlockFn(torch.autograd.Function):
             conv3x3_wgrad(dy1, x, gw1, N, H, W, Co, Cip, Ci)
         dx = None
         if ctx.needs_input_grad[0]:
-            wk1t = conv_weight_dgrad(w1, dt, Op=Cip)
-            dx = conv_s1(dy1, wk1t, N, H, W, Co, Cip)
+            ga = conv_group(dt, Co, Cip, W)
+            wk1t = conv_weight_dgrad(w1, dt, Op=Cip, group=ga)
+            dx = conv_s1(dy1, wk1t, N, H, W, Co, Cip, group=ga)
         return dx, rw1, rg1, rb1, rw2, rg2, rb2, rs1, rs2, rsp
 
 

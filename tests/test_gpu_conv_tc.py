@@ -55,6 +55,53 @@ def test_conv3x3_tc_matches_reference(ops, shape):
     assert float((got16.float().cpu() - want).norm() / want.norm()) < 4e-3
 
 
+GROUPED = [  # (N, H, W, Cin, Cout, group): the thin layers of config 3 in pixel-group form (pcm_conv3x3_tc_grouped)
+    (5, 48, 72, 16, 16, 4), (5, 48, 72, 16, 16, 2), (3, 24, 36, 16, 32, 2), (3, 24, 36, 32, 32, 2), (2, 48, 72, 32, 16, 2),
+    (2, 5, 8, 16, 16, 4), (1, 7, 6, 16, 16, 2), (150, 48, 72, 16, 16, 4),
+]
+
+
+@pytest.mark.parametrize("shape", GROUPED)
+def test_conv3x3_tc_grouped_matches_reference(ops, shape):
+    """Pixel-group form: g adjacent pixels as one GEMM row (g x fewer, g x longer TMA rows).  Forward and the flipped
+    data-gradient packing, against fp64 convolution of the same bf16-rounded operands and against the plain form; the
+    batched re-pack (PackPlan) must reproduce the grouped packing bit for bit."""
+    from pcm_b200._lib import lib
+    N, H, W, Ci, Co, grp = shape
+    g = torch.Generator().manual_seed(N * 1000 + H * 10 + Ci + Co + grp)
+    x = torch.randn(N, H, W, Ci, generator=g).bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Ci ** 0.5)).bfloat16()
+    want = _ref(x, w, None)
+    xg, wg = x.cuda(), w.float().cuda()
+    wk = ops.conv_weight_fwd(wg, torch.bfloat16, group=grp)
+    assert tuple(wk.shape) == (9, grp * Co, grp * Ci)
+    got = ops.conv_s1(xg, wk, N, H, W, Ci, Co, dst_f32=True, group=grp)
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    assert float((got.cpu() - want).norm() / want.norm()) < 2e-6
+    plain = ops.conv_s1(xg, ops.conv_weight_fwd(wg, torch.bfloat16), N, H, W, Ci, Co)
+    got16 = ops.conv_s1(xg, wk, N, H, W, Ci, Co, group=grp)
+    assert float((got16.float() - plain.float()).norm() / plain.float().norm()) < 1e-3     # bf16 rounding of ~equal fp32 sums
+    assert float((got16.float().cpu() - want).norm() / want.norm()) < 4e-3
+    # data gradient of the same layer through the flipped grouped packing
+    dy = torch.randn(N, H, W, Co, generator=g).bfloat16()
+    xz = torch.zeros(N, Ci, H, W, requires_grad=True, dtype=torch.float64)
+    F.conv2d(xz, w.double(), padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    wkt = ops.conv_weight_dgrad(wg, torch.bfloat16, group=grp)
+    dx = ops.conv_s1(dy.cuda(), wkt, N, H, W, Co, Ci, dst_f32=True, group=grp)
+    wantdx = xz.grad.permute(0, 2, 3, 1).float()
+    assert float((dx.cpu() - wantdx).norm() / wantdx.norm()) < 2e-6
+    # the one-launch re-pack of the trainer writes the same grouped kernel
+    plan = ops.PackPlan()
+    with ops.use_pack_plan(plan):
+        a = ops.conv_weight_fwd(wg, torch.bfloat16, group=grp)
+        b = ops.conv_weight_dgrad(wg, torch.bfloat16, group=grp)
+        a.zero_(); b.zero_()
+        plan.repack()
+    torch.cuda.synchronize()
+    assert torch.equal(a, wk) and torch.equal(b, wkt)
+
+
 def test_conv3x3_tc_accumulate_and_views(ops):
     """fp32 accumulate (ConvLSTM Wx.x + Wh.h split), time-strided source images, channel-slice source view."""
     T, B, H, W, Ci, Co = 3, 4, 6, 9, 64, 256
@@ -130,6 +177,39 @@ def test_wgrad3x3_tc_matches_reference(ops, shape):
     # accumulates into what is already there; a second call doubles the result
     ops.conv3x3_wgrad(dy.cuda(), x.cuda(), dw, N, H, W, Co, Ci, Ci)
     assert float((dw.cpu() - 2 * want).norm() / want.norm()) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(5, 48, 72, 16, 16), (3, 24, 36, 16, 32), (3, 24, 36, 32, 32), (2, 48, 72, 32, 16),
+                                   (2, 6, 8, 16, 16), (150, 48, 72, 16, 16)])
+@pytest.mark.parametrize("grp", ["0", "2", "4"])
+def test_wgrad3x3_tc_grouped_forms_agree(ops, shape, grp, monkeypatch):
+    """Pixel-group form of the thin-layer weight gradient (pcm_wgrad3x3_tc_grouped) against fp64 autograd, for every
+    group factor, into the parameter layout (with padded input channels: Ci_real < Ci) and into the packed layout."""
+    from pcm_b200._lib import lib
+    monkeypatch.setenv("PCM_WGRAD_GROUP", grp)
+    N, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(N * 7 + H + Ci * 3 + Co)
+    Cr = Ci - 9 if Ci == 16 else Ci                      # the first layer has 7 real input channels of 16
+    x = torch.randn(N, H, W, Ci, generator=g).bfloat16()
+    x[..., Cr:] = 0
+    dy = (torch.randn(N, H, W, Co, generator=g) / (N * H * W) ** 0.5).bfloat16()
+    w = torch.zeros(Co, Cr, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x[..., :Cr].double().permute(0, 3, 1, 2), w, padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    want = w.grad.float()
+    dw = torch.zeros(Co, Cr, 3, 3, device="cuda")
+    ops.conv3x3_wgrad(dy.cuda(), x.cuda(), dw, N, H, W, Co, Ci, Cr)
+    torch.cuda.synchronize()
+    assert lib()._fn["pcm_tc_error_count"]() == 0
+    assert float((dw.cpu() - want).norm() / want.norm()) < 1e-5
+    if grp != "0":
+        assert ops.wgrad_group(torch.bfloat16, Co, Ci, W) > 1
+        packed = torch.zeros(9, Co, Ci, device="cuda")
+        dyg, xg = dy.cuda(), x.cuda()
+        ops._call("pcm_wgrad3x3_tc_grouped", dyg.data_ptr(), H * W * Co, Co, xg.data_ptr(), H * W * Ci, Ci, Cr,
+                  packed.data_ptr(), Ci, 1, Co * Ci, N, H, W, ops.wgrad_group(torch.bfloat16, Co, Ci, W), ops._s())
+        torch.cuda.synchronize()
+        got = packed.reshape(3, 3, Co, Ci).permute(2, 3, 0, 1)[:, :Cr]
+        assert float((got.cpu() - want).norm() / want.norm()) < 1e-5
 
 
 def test_wgrad3x3_tc_slices(ops):

@@ -63,9 +63,11 @@ def bench_conv(args):
             continue
         x = torch.randn(N, H, W, Ci, device="cuda").bfloat16()
         w = torch.randn(Co, Ci, 3, 3, device="cuda") / (3 * Ci ** 0.5)
-        wk = ops.conv_weight_fwd(w, torch.bfloat16)
+        grp = ops.conv_group(torch.bfloat16, Ci, Co, W)          # PCM_CONV_GROUP / PCM_CONV_GROUP_MAXC select the form
+        wk = ops.conv_weight_fwd(w, torch.bfloat16, group=grp)
         y = torch.empty(N, H, W, Co, device="cuda", dtype=torch.bfloat16)
-        ms = timeit(lambda: ops.conv_s1(x, wk, N, H, W, Ci, Co, dst=y), args.iters, args.flush)
+        name = f"{name} g{grp}"
+        ms = timeit(lambda: ops.conv_s1(x, wk, N, H, W, Ci, Co, dst=y, group=grp), args.iters, args.flush)
         flops = 2.0 * N * H * W * Ci * Co * 9
         byts = 2.0 * N * H * W * (Ci + Co)
         print(f"conv3x3 {name:16s} N={N:4d} {H:2d}x{W:2d} {Ci:3d}->{Co:3d}: {ms * 1e3:8.1f} us  "
