@@ -127,6 +127,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load without the wait: issue several, then tmem_wait_ld() once (the load latency is paid once per batch)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors --------------------------------------------------------------------------------------------
 // smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start[0:14) | LBO[16:30) | SBO[32:46) |
 // version=1 [46:48) | layout_type [61:64): 0 none, 2 = 128B, 4 = 64B, 6 = 32B swizzle.  Addresses >> 4.

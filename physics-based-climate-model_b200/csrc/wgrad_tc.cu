@@ -33,6 +33,7 @@ struct WgradTcParams {
   int group, Cog, Cig;          // pixel-group form (group > 1): `group` adjacent pixels of a row are one K row with group*C
                                 // channels; Cog / Cig = channels of ONE pixel (M index = pa*Cog + co, B row = pb*Cig + ci)
   int ncol, sub16;              // wide / group: N extent of the MMA of one kernel row; group: B start offset inside a row (>>4)
+  uint32_t bar_off;             // barriers sit behind the pipeline stages or the epilogue's staging array, whichever is larger
   int noatomic;                 // PCM_WGRAD_NOATOMIC=1 (measurement only): skip the global reductions of the epilogue
   int stages;
   int bx0;                      // first column of the x box in its tensor map (-pad; 0 for an interior column strip)
@@ -42,6 +43,69 @@ struct WgradTcParams {
 
 constexpr int kWgThreads = 192;
 
+// Epilogue of the pixel-group form: accumulator lane = (pa, co) (output pixel pa of the group), column = (kh, j, ci) with
+// input pixel p0 - 1 + j; tap dx = j - pa.  The g values of one (co, kh, dx, ci) sit in lanes of different pa, mostly in
+// different warps: every lane stores its three tap blocks per kernel row into its pa's copy of a [g][9][Cog][Cig] fp32
+// array in shared memory (the pipeline stages are idle by now), one barrier, and the 128 epilogue threads sum the g
+// copies and issue ONE coalesced vector reduction per 4 outputs — as many atomics as the plain form, on consecutive
+// addresses.  TMEM is read a whole kernel row at a time (one tcgen05.wait::ld per row, not per 16 columns).
+template <int COG, int CIG>
+__device__ __forceinline__ void wgrad_group_epilogue(uint8_t* smem, uint32_t tmem_base, float* __restrict__ dw,
+                                                     const WgradTcParams& p, int q, int lane) {
+  constexpr int PAW = 32 / COG;                   // group pixels held by one warp (2 for 16 channels, 1 for 32)
+  constexpr int NB = PAW + 2;                     // input-pixel blocks of CIG columns this warp needs per kernel row
+  const int g = p.group;
+  const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+  const int m = q * 32 + lane, pa_l = m / COG, cog = m - pa_l * COG, pa_first = (q * 32) / COG;
+  float* acc = reinterpret_cast<float*>(smem);    // [g][9][COG][CIG]
+  if (pa_first < g) {
+#pragma unroll 1
+    for (int kh = 0; kh < 3; ++kh) {
+      uint32_t r[NB * CIG];
+#pragma unroll
+      for (int c = 0; c < NB * CIG; c += 16) tc::tmem_ld16_nowait(t_addr + kh * p.ncol + pa_first * CIG + c, r + c);
+      tc::tmem_wait_ld();
+      const bool hi = PAW == 2 && pa_l != pa_first;          // this lane's blocks start one block further
+#pragma unroll
+      for (int dxx = 0; dxx < 3; ++dxx) {
+        float4* d = reinterpret_cast<float4*>(acc + (((size_t)pa_l * 9 + kh * 3 + dxx) * COG + cog) * CIG);
+#pragma unroll
+        for (int k = 0; k < CIG / 4; ++k) {
+          const int b0 = dxx * CIG + 4 * k, b1 = PAW == 2 ? b0 + CIG : b0;
+          float4 o;
+          o.x = __uint_as_float(hi ? r[b1] : r[b0]);
+          o.y = __uint_as_float(hi ? r[b1 + 1] : r[b0 + 1]);
+          o.z = __uint_as_float(hi ? r[b1 + 2] : r[b0 + 2]);
+          o.w = __uint_as_float(hi ? r[b1 + 3] : r[b0 + 3]);
+          d[k] = o;
+        }
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int et = threadIdx.x - 64;                // 0..127 over the epilogue warps
+  constexpr int nv4 = 9 * COG * CIG / 4, per_row = CIG / 4;
+  for (int i = et; i < nv4; i += 128) {
+    const int row = i / per_row, c4 = i - row * per_row;                        // row = t*COG + co
+    const int t = row / COG, co = row - t * COG;
+    float4 v = reinterpret_cast<const float4*>(acc)[i];
+    for (int pa = 1; pa < g; ++pa) {
+      const float4 u = reinterpret_cast<const float4*>(acc)[pa * nv4 + i];
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    float* base = dw + (long long)co * p.sa + (long long)t * p.st;
+    if (p.sb == 1) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + c4 * 4), "f"(v.x), "f"(v.y), "f"(v.z),
+                   "f"(v.w) : "memory");
+    } else {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c4 * 4 + k < p.Ci_real) atomicAdd(base + (long long)(c4 * 4 + k) * p.sb, e[k]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmB2, float* __restrict__ dw, unsigned int* __restrict__ err, const WgradTcParams p) {
@@ -50,7 +114,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* done = empty + p.stages;
@@ -184,78 +248,45 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     bool ok = my_tiles > 0 ? mbar_wait(done, 0, err) : false;
     ok = __all_sync(0xffffffffu, ok) && !p.noatomic;
     if (ok && p.group > 1) {
-      // pixel-group form: lane = (pa, co), column = (kh, j, ci) with input pixel p0 - 1 + j; tap dx = j - pa.  The g values
-      // of one (co, kh, dx, ci) sit in lanes of different pa: they are summed in shared memory (the pipeline stages are
-      // idle by now), one pass per pa — pass 0 stores, the others add, a 128-thread barrier in between — and the CTA then
-      // issues ONE vector reduction per 4 outputs, as the plain form does (g times fewer atomics on the same addresses).
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int m = q * 32 + lane, pa_l = m / p.Cog, cog = m - pa_l * p.Cog;
-      const int pa_first = (q * 32) / p.Cog, pa_last = (q * 32 + 31) / p.Cog;      // pa values held by this warp
-      float* acc = reinterpret_cast<float*>(smem);                                  // [9][Cog][Cig]
-      const int blocks = p.Cig >> 4;
-      for (int pa = 0; pa < p.group; ++pa) {
-        if (pa >= pa_first && pa <= pa_last) {
-          for (int t = 0; t < 9; ++t) {
-            const int kh = t / 3, dxx = t - kh * 3;
-            for (int b = 0; b < blocks; ++b) {
-              float v[16];
-              tmem_ld16(t_addr + kh * p.ncol + (dxx + pa) * p.Cig + b * 16, v);
-              if (pa_l == pa) {
-                float4* d = reinterpret_cast<float4*>(acc + ((size_t)t * p.Cog + cog) * p.Cig + b * 16);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  float4 o = pa ? d[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-                  o.x += v[4 * k]; o.y += v[4 * k + 1]; o.z += v[4 * k + 2]; o.w += v[4 * k + 3];
-                  d[k] = o;
-                }
-              }
-            }
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      const int et = threadIdx.x - 64;                                              // 0..127 over the epilogue warps
-      const int nv4 = 9 * p.Cog * p.Cig / 4, per_row = p.Cig / 4;
-      for (int i = et; i < nv4; i += 128) {
-        const int row = i / per_row, c4 = i - row * per_row;                        // row = t*Cog + co
-        const int t = row / p.Cog, co = row - t * p.Cog;
-        const float4 v = reinterpret_cast<const float4*>(acc)[i];
-        float* base = dw + (long long)co * p.sa + (long long)t * p.st;
-        if (p.sb == 1) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + c4 * 4), "f"(v.x), "f"(v.y), "f"(v.z),
-                       "f"(v.w) : "memory");
-        } else {
-          const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (c4 * 4 + k < p.Ci_real) atomicAdd(base + (long long)(c4 * 4 + k) * p.sb, e[k]);
-        }
-      }
+      if (p.Cog == 16 && p.Cig == 16) wgrad_group_epilogue<16, 16>(smem, tmem_base, dw, p, q, lane);
+      else if (p.Cog == 16) wgrad_group_epilogue<16, 32>(smem, tmem_base, dw, p, q, lane);
+      else if (p.Cig == 16) wgrad_group_epilogue<32, 16>(smem, tmem_base, dw, p, q, lane);
+      else wgrad_group_epilogue<32, 32>(smem, tmem_base, dw, p, q, lane);
     } else if (ok) {
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       const int ncols = ntap * p.Ci;
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_addr + c0, v);
-        if (co < p.Co_real) {
-          const int tap = tap0 + c0 / p.Ci;
-          const int ci0 = c0 % p.Ci;
-          float* base = dw + (long long)co * p.sa + (long long)tap * p.st;
-          if (p.sb == 1) {
-            // packed gradient layout [tap][co][ci] (ci contiguous, padded): 16-byte vector reductions — one L2
-            // sector operation per 4 values instead of one per value (the scattered scalar atomics of the
-            // reference layout were the whole cost of the wide layers: 49 splits x 147k values for enc4)
-            float* q = base + ci0;
+      // 64 accumulator columns per tcgen05.wait::ld (four loads in flight): the epilogue is a serial tail behind the K loop
+      // of every CTA, and one wait per 16 columns made it 5-10 us long on the wide layers
+      for (int c00 = 0; c00 < ncols; c00 += 64) {
+        uint32_t r[64];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + j), "f"(v[j]), "f"(v[j + 1]),
-                           "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-          } else {
+        for (int k = 0; k < 4; ++k)
+          if (c00 + 16 * k < ncols) tmem_ld16_nowait(t_addr + c00 + 16 * k, r + 16 * k);
+        tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (ci0 + j < p.Ci_real) atomicAdd(base + (long long)(ci0 + j) * p.sb, v[j]);
+        for (int k = 0; k < 4; ++k) {
+          const int c0 = c00 + 16 * k;
+          if (c0 < ncols && co < p.Co_real) {
+            const float* v = reinterpret_cast<const float*>(r + 16 * k);
+            const int tap = tap0 + c0 / p.Ci;
+            const int ci0 = c0 % p.Ci;
+            float* base = dw + (long long)co * p.sa + (long long)tap * p.st;
+            if (p.sb == 1) {
+              // packed gradient layout [tap][co][ci] (ci contiguous, padded): 16-byte vector reductions — one L2
+              // sector operation per 4 values instead of one per value (the scattered scalar atomics of the
+              // reference layout were the whole cost of the wide layers: 49 splits x 147k values for enc4)
+              float* qd = base + ci0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(qd + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (ci0 + j < p.Ci_real) atomicAdd(base + (long long)(ci0 + j) * p.sb, v[j]);
+            }
           }
         }
       }
@@ -401,7 +432,10 @@ static int wgrad_tc_impl(const void* dy, long long dy_ns, int dy_ps, int Co, int
   PCM_REQUIRE(stages >= 1, "wgrad3x3_tc: tile does not fit shared memory (%zu B per stage)", per_stage);
   if (stages > p.num_ktiles) stages = p.num_ktiles;
   p.stages = stages;
-  const size_t smem = 1024 + stages * per_stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  size_t pipe_bytes = stages * per_stage;
+  if (group > 1 && pipe_bytes < (size_t)group * 9 * Cog * Cig * 4) pipe_bytes = (size_t)group * 9 * Cog * Cig * 4;
+  p.bar_off = (uint32_t)((pipe_bytes + 15) & ~(size_t)15);
+  const size_t smem = 1024 + p.bar_off + (2 * stages + 1) * sizeof(uint64_t) + 16;
 
   CUtensorMap tmA, tmB, tmB2;
   {
