@@ -129,7 +129,7 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
   L.gate = full ? PCM_TAKE(P * 4) : 0;
   L.dm = (full && bwd) ? PCM_TAKE(P * 8) : 0;
   L.bar = PCM_TAKE(64);                                  // mbarriers of the bulk copies that bring the image in (one per 32 KB piece)
-  L.part = PCM_TAKE((size_t)2 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 2 slots x warps x C floats
+  L.part = PCM_TAKE((size_t)2 * (kFT / 32) * C * 4);                      // chan_put: 2 slots x warps (at most kFT / 32) x C floats
   // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
   //         | wt[2][7][8] | wtf[2][7][8] | dw[100] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
   L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + (full ? C * C / 4 : 0)) * 4);
@@ -1302,6 +1302,43 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   }
 }
 
+// Launch width of a per-image kernel.  tail_threads() sizes the CTA by the image; when that width needs more than one
+// wave of CTAs over the SMs and half the width fits everything in fewer, the narrower CTA wins: measured on 384 images of
+// 12x18x64, two waves of 256-thread CTAs (two per SM by registers) 56 us, one wave of 128-thread CTAs 42 us.  Cost model:
+// waves x (c0 + vector rounds per thread), c0 = the per-image fixed cost in units of one round (fitted: ~6.75 rounds for
+// the backward kernels, ~2.5 for the forward ones).  PCM_TAIL_WAVES=0 keeps tail_threads().
+template <typename K>
+static int tail_launch_threads(K kern, int N, int H, int W, int C, size_t smem, float c0) {
+  static int on = -1, sms = 0;
+  if (on < 0) {
+    const char* e = getenv("PCM_TAIL_WAVES");
+    on = e ? atoi(e) : 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int tmax = tail_threads(H, W, C);
+  if (!on || tmax <= 128) return tmax;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess || fa.numRegs <= 0) return tmax;
+  const int nvec = H * W * (C / 8);
+  int best = tmax;
+  float best_cost = 0.f;
+  for (int t = tmax; t >= tmax / 2 && t >= 128; t >>= 1) {
+    long long per = (228 * 1024) / (long long)(smem + 1024);                 // CTAs per SM: shared memory (+1 KB reserved each),
+    const long long by_regs = 65536 / ((long long)((fa.numRegs + 7) / 8 * 8) * t);   // registers, threads
+    if (by_regs < per) per = by_regs;
+    if (2048 / t < per) per = 2048 / t;
+    if (per > 32) per = 32;
+    if (per < 1) continue;
+    const long long waves = (N + sms * per - 1) / (sms * per);
+    const float cost = (float)waves * (c0 + (float)((nvec + t - 1) / t));
+    if (t == tmax || cost < best_cost - 0.5f) { best = t; best_cost = cost; }
+  }
+  return best;
+}
+
 static bool fused_shape_ok(int H, int W, int C, int Cr) {
   const int cv = C / 8;
   return C % 8 == 0 && C >= 8 && cv <= 32 && (cv & (cv - 1)) == 0 && Cr >= 1 && Cr <= 64 && Cr * 8 <= C && H >= 1 && W >= 1;
@@ -1441,7 +1478,7 @@ extern "C" int pcm_gn_silu_img_fwd(const void* x, const float* gamma, const floa
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, false>, smem, "gn_silu_img_fwd");
     if (rc == PCM_OK)
-      pcm::launch(convblock_tail_fwd_kernel<T, false>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, 
+      pcm::launch(convblock_tail_fwd_kernel<T, false>, N, tail_launch_threads(convblock_tail_fwd_kernel<T, false>, N, H, W, C, smem, 2.5f), smem, (cudaStream_t)s, 
           (const T*)x, gamma, beta, nullptr, nullptr, nullptr, stats, nullptr, nullptr, nullptr, nullptr, nullptr,
           (T*)y, H, W, C, 1, eps);
   });
@@ -1462,7 +1499,7 @@ extern "C" int pcm_convblock_tail_fwd(const void* x, const float* gamma, const f
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_fwd_kernel<T, true>, smem, "convblock_tail_fwd");
     if (rc == PCM_OK)
-      pcm::launch(convblock_tail_fwd_kernel<T, true>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, 
+      pcm::launch(convblock_tail_fwd_kernel<T, true>, N, tail_launch_threads(convblock_tail_fwd_kernel<T, true>, N, H, W, C, smem, 2.5f), smem, (cudaStream_t)s, 
           (const T*)x, gamma, beta, w1, w2, wsp, stats, pool, se, hid, maps, ties, (T*)out, H, W, C, Cr, eps);
   });
   if (rc != PCM_OK) return rc;
@@ -1480,7 +1517,7 @@ extern "C" int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* s
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(gn_silu_img_bwd_kernel<T>, smem, "gn_silu_img_bwd");
     if (rc == PCM_OK)
-      pcm::launch(gn_silu_img_bwd_kernel<T>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, (const T*)da, (const T*)x, stats, gamma, beta, (T*)dx,
+      pcm::launch(gn_silu_img_bwd_kernel<T>, N, tail_launch_threads(gn_silu_img_bwd_kernel<T>, N, H, W, C, smem, 6.75f), smem, (cudaStream_t)s, (const T*)da, (const T*)x, stats, gamma, beta, (T*)dx,
                                                                    dgamma, dbeta, H, W, C, eps);
   });
   if (rc != PCM_OK) return rc;
@@ -1503,7 +1540,7 @@ extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const voi
   PCM_DISPATCH_DTYPE(dtype, T, {
     rc = tail_set_smem(convblock_tail_bwd_kernel<T>, smem, "convblock_tail_bwd");
     if (rc == PCM_OK)
-      pcm::launch(convblock_tail_bwd_kernel<T>, N, tail_threads(H, W, C), smem, (cudaStream_t)s, 
+      pcm::launch(convblock_tail_bwd_kernel<T>, N, tail_launch_threads(convblock_tail_bwd_kernel<T>, N, H, W, C, smem, 6.75f), smem, (cudaStream_t)s, 
           (const T*)dout, (const T*)x, (const T*)out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties,
           (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, H, W, C, Cr, eps);
   });
