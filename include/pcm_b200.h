@@ -383,6 +383,15 @@ PCM_API int pcm_head_fwd(const void* x, const float* w, const float* b, float* o
                  int dtype, pcm_stream_t s);
 PCM_API int pcm_head_bwd(const float* dout_nchw, const void* x, const float* w, void* dx, float* dw, float* db, int N, int P,
                  int C, int K, int dtype, pcm_stream_t s);
+/* Head + loss fused for the training step (the prediction is needed only inside the loss): ONE pass forward —
+ * loss[0] += mean over (n,k,p) of (head(x) - target)^2, pred_nchw optional (NULL: not written) — and ONE pass backward that
+ * recomputes head(x) - target per pixel: dx = W^T dpred, dw += dpred x^T, db += dpred with dpred = 2 (pred - target) gscale[0] / n.
+ * x NHWC [N][P][C] (dtype), target / pred NCHW fp32 [N][K][P].  C in {16, 32}, K = 2 (pcm_head_mse_supported). */
+PCM_API int pcm_head_mse_supported(int C, int K);
+PCM_API int pcm_head_mse_fwd(const void* x, const float* w, const float* b, const float* target, float* pred_nchw,
+                             float* loss, int N, int P, int C, int K, int dtype, pcm_stream_t s);
+PCM_API int pcm_head_mse_bwd(const void* x, const float* w, const float* b, const float* target, const float* gscale,
+                             void* dx, float* dw, float* db, int N, int P, int C, int K, int dtype, pcm_stream_t s);
 /* loss[0] += mean((a-b)^2) (caller zeroes) */
 PCM_API int pcm_mse_fwd(const float* a, const float* b, float* loss, long long n, pcm_stream_t s);
 /* da = 2*(a-b)/n * gscale[0] */

@@ -154,6 +154,9 @@ def algo_cost(name: str, args):
     if name in ("pcm_head_fwd", "pcm_head_bwd"):
         k = 2 if name == "pcm_head_bwd" else 1
         return 2.0 * a["N"] * a["P"] * a["C"] * a["K"] * k, a["N"] * a["P"] * (a["C"] * es() * k + a["K"] * 4), "hbm"
+    if name in ("pcm_head_mse_fwd", "pcm_head_mse_bwd"):
+        k = 2 if name == "pcm_head_mse_bwd" else 1                              # x (and dx) + target; pred optional
+        return 2.0 * a["N"] * a["P"] * a["C"] * a["K"] * (k + (1 if k == 2 else 0)), a["N"] * a["P"] * (a["C"] * es() * k + a["K"] * 4), "hbm"
     if name in ("pcm_mse_fwd", "pcm_mse_bwd"):
         return 0.0, a["n"] * 4 * (2 if name == "pcm_mse_fwd" else 3), "hbm"
     if name == "pcm_adam_step":

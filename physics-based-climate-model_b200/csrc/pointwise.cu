@@ -441,6 +441,94 @@ head_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ x, const f
   for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(db + i, accb[i]);
 }
 
+// ---- head 1x1 + MSE loss fused (src/unet_convlstm_attention.py:104 + main_final.py:559): the training step needs the
+// prediction only inside the loss, so forward is ONE pass over the last activation (pred optional) and backward ONE pass
+// that recomputes pred_k - y_k per pixel (C*K FMAs) instead of reading a stored gradient: 4 launches -> 2.
+//   loss += sum_{n,k,p} (pred - y)^2 / (N*K*P);   dpred = 2*(pred - y)*g/(N*K*P);  dx = W^T dpred;  dw += dpred x^T;  db += dpred
+// Per-thread register accumulators for dw / db over the thread's pixels, ONE shuffle + shared reduction per block.
+template <typename T, int CV, int KK>
+__global__ void __launch_bounds__(256)
+head_mse_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                const float* __restrict__ target, const float* __restrict__ gscale, float* __restrict__ pred,
+                float* __restrict__ loss, T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int N, int P) {
+  PCM_PDL_ENTRY();
+  constexpr int C = CV * 8;
+  __shared__ float sw[KK * C + KK];
+  __shared__ float sacc[KK * C + KK + 1];
+  for (int i = threadIdx.x; i < KK * C; i += blockDim.x) sw[i] = __ldg(w + i);
+  for (int i = threadIdx.x; i < KK; i += blockDim.x) sw[KK * C + i] = __ldg(b + i);
+  for (int i = threadIdx.x; i < KK * C + KK + 1; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const bool bwd = dx != nullptr;
+  const long long total = (long long)N * P;
+  const float inv_n = 1.f / ((float)total * (float)KK);
+  const float gs = bwd ? 2.f * inv_n * __ldg(gscale) : 0.f;
+  float aw[KK][C], ab[KK], al = 0.f;
+#pragma unroll
+  for (int k = 0; k < KK; ++k) {
+    ab[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) aw[k][c] = 0.f;
+  }
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % P);
+    const long long n = idx / P;
+    float v[C], d[KK];
+#pragma unroll
+    for (int cb = 0; cb < CV; ++cb) load8(x + idx * C + cb * 8, v + cb * 8);
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      float acc = sw[KK * C + k];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc = fmaf(v[c], sw[k * C + c], acc);
+      const long long o = (n * KK + k) * P + p;
+      if (pred != nullptr) pred[o] = acc;
+      d[k] = acc - __ldg(target + o);
+      al = fmaf(d[k], d[k], al);
+    }
+    if (bwd) {
+      float r[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) r[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < KK; ++k) {
+        const float dk = d[k] * gs;
+        ab[k] += dk;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          r[c] = fmaf(sw[k * C + c], dk, r[c]);
+          aw[k][c] = fmaf(dk, v[c], aw[k][c]);
+        }
+      }
+#pragma unroll
+      for (int cb = 0; cb < CV; ++cb) store8(dx + idx * C + cb * 8, r + cb * 8);
+    }
+  }
+  const bool lead = (threadIdx.x & 31) == 0;
+  if (bwd) {
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float t = warp_sum(aw[k][c]);
+        if (lead) atomicAdd(&sacc[k * C + c], t);
+      }
+      const float t = warp_sum(ab[k]);
+      if (lead) atomicAdd(&sacc[KK * C + k], t);
+    }
+  } else {
+    const float t = warp_sum(al);
+    if (lead) atomicAdd(&sacc[KK * C + KK], t);
+  }
+  __syncthreads();
+  if (bwd) {
+    for (int i = threadIdx.x; i < KK * C; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) atomicAdd(db + i, sacc[KK * C + i]);
+  } else if (threadIdx.x == 0) {
+    atomicAdd(loss, sacc[KK * C + KK] * inv_n);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ loss, long long n) {
   PCM_PDL_ENTRY();
@@ -646,6 +734,39 @@ extern "C" int pcm_head_bwd(const float* dout_nchw, const void* x, const float* 
   PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(head_bwd_kernel<T>, (int)blocks, 256, smem, (cudaStream_t)s, 
                                    dout_nchw, (const T*)x, w, (T*)dx, dw, db, N, P, C, K)));
   return check_launch("head_bwd");
+}
+
+template <typename T, int CV, int KK>
+static void head_mse_launch(const void* x, const float* w, const float* b, const float* target, const float* gscale, float* pred,
+                            float* loss, void* dx, float* dw, float* db, int N, int P, pcm_stream_t s) {
+  long long blocks = ((long long)N * P + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  pcm::launch(head_mse_kernel<T, CV, KK>, (int)blocks, 256, 0, (cudaStream_t)s, (const T*)x, w, b, target, gscale, pred, loss,
+              (T*)dx, dw, db, N, P);
+}
+
+extern "C" int pcm_head_mse_supported(int C, int K) { return ((C == 16 || C == 32) && K == 2) ? 1 : 0; }
+
+static int head_mse_dispatch(const void* x, const float* w, const float* b, const float* target, const float* gscale, float* pred,
+                             float* loss, void* dx, float* dw, float* db, int N, int P, int C, int K, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(pcm_head_mse_supported(C, K), "head_mse: C must be 16 or 32 and K 2 (got C=%d K=%d)", C, K);
+  if (N == 0) return PCM_OK;
+  PCM_DISPATCH_DTYPE(dtype, T, {
+    if (C == 16) head_mse_launch<T, 2, 2>(x, w, b, target, gscale, pred, loss, dx, dw, db, N, P, s);
+    else head_mse_launch<T, 4, 2>(x, w, b, target, gscale, pred, loss, dx, dw, db, N, P, s);
+  });
+  return check_launch("head_mse");
+}
+
+extern "C" int pcm_head_mse_fwd(const void* x, const float* w, const float* b, const float* target, float* pred_nchw,
+                                float* loss, int N, int P, int C, int K, int dtype, pcm_stream_t s) {
+  return head_mse_dispatch(x, w, b, target, nullptr, pred_nchw, loss, nullptr, nullptr, nullptr, N, P, C, K, dtype, s);
+}
+
+extern "C" int pcm_head_mse_bwd(const void* x, const float* w, const float* b, const float* target, const float* gscale,
+                                void* dx, float* dw, float* db, int N, int P, int C, int K, int dtype, pcm_stream_t s) {
+  PCM_REQUIRE(dx != nullptr && dw != nullptr && db != nullptr && gscale != nullptr, "head_mse_bwd: null output");
+  return head_mse_dispatch(x, w, b, target, gscale, nullptr, nullptr, dx, dw, db, N, P, C, K, dtype, s);
 }
 
 extern "C" int pcm_mse_fwd(const float* a, const float* b, float* loss, long long n, pcm_stream_t s) {

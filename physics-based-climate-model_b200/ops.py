@@ -217,6 +217,11 @@ def side_active() -> bool:
     return _SIDE is not None
 
 
+def side_forked() -> bool:
+    """Work has been issued on the side stream since the last join (waiting on it is then legal under graph capture)."""
+    return _SIDE is not None and _SIDE_FORKED
+
+
 def join_side():
     """Make the current stream wait for everything issued on the side stream.  Nothing to do when the side stream
     has not been used since the last join — and under graph capture it MUST be skipped then: waiting on a stream that
@@ -276,10 +281,11 @@ def conv_group(dtype, Sc: int, Dc: int, W: int, dense: bool = True) -> int:
     """Pixel-group factor for a thin 3x3 layer on the tensor-core path (pcm_conv3x3_tc_grouped): g adjacent pixels
     of a row become one GEMM row of g*Sc channels, which divides the number of TMA box rows — the measured bound of
     the 16- and 32-channel layers — by g.  1 = plain form.  PCM_CONV_GROUP=0 disables, =2 caps the factor at 2;
-    PCM_CONV_GROUP_MAXC (default 16) is the widest layer (max of Sc, Dc) that is grouped."""
+    PCM_CONV_GROUP_MAXC (default 32) is the widest layer (max of Sc, Dc) that is grouped (32-channel layers in pairs:
+    -10 us per step)."""
     import os
     cap = int(os.environ.get("PCM_CONV_GROUP", "4"))
-    maxc = int(os.environ.get("PCM_CONV_GROUP_MAXC", "16"))
+    maxc = int(os.environ.get("PCM_CONV_GROUP_MAXC", "32"))
     if cap < 2 or not dense or dtype != torch.bfloat16 or Sc % 16 or Dc % 16 or max(Sc, Dc) > min(maxc, 32):
         return 1
     g = min(cap, 64 // max(Sc, Dc))
@@ -1064,6 +1070,41 @@ class HeadFn(torch.autograd.Function):
         _call("pcm_head_bwd", dout.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), gw.data_ptr(), gb.data_ptr(),
               N, H * W, C, K, _DT[x.dtype], _s())
         return dx, rw, rb
+
+
+class HeadMSEFn(torch.autograd.Function):
+    """loss = nn.MSELoss()(head(x), target) with the 1x1 head (src/unet_convlstm_attention.py:104, main_final.py:559) in
+    two launches instead of four: the prediction never goes to HBM in training (the step needs it only inside the loss)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, target):
+        x = x.contiguous()
+        target = target.contiguous().float()
+        N, H, W, C = x.shape
+        K = w.shape[0]
+        loss = torch.zeros(1, device=x.device, dtype=torch.float32)
+        _call("pcm_head_mse_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), target.data_ptr(), 0, loss.data_ptr(), N, H * W, C, K,
+              _DT[x.dtype], _s())
+        ctx.save_for_backward(x, w, b, target)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, b, target = ctx.saved_tensors
+        N, H, W, C = x.shape
+        K = w.shape[0]
+        g = g.contiguous().float()
+        gw, rw = _grad_buf(w)
+        gb, rb = _grad_buf(b)
+        dx = torch.empty_like(x)
+        _call("pcm_head_mse_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), target.data_ptr(), g.data_ptr(), dx.data_ptr(),
+              gw.data_ptr(), gb.data_ptr(), N, H * W, C, K, _DT[x.dtype], _s())
+        return dx, rw, rb, None
+
+
+def head_mse_ok(C: int, K: int) -> bool:
+    import os
+    return os.environ.get("PCM_HEAD_MSE", "1") != "0" and bool(lib()._fn["pcm_head_mse_supported"](C, K))
 
 
 class MSELossFn(torch.autograd.Function):

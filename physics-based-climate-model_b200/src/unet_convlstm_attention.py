@@ -68,7 +68,7 @@ class AttUNetConvLSTM(nn.Module):
         x = ops.window_stage(series, idx, T, compute_dtype(), norm=norm, month=month)
         return self.forward_staged(x, idx.numel(), T)
 
-    def forward_staged(self, x, B, T):
+    def forward_staged(self, x, B, T, target=None):
         """x: NHWC frames (T*B, H, W, 16), t-major: image n = t*B + b (e.g. from
         ops.season_embed_stage(..., T=T), which synthesises the sin/cos month channels on the fly)."""
         s1 = self.enc1.forward_nhwc(x)
@@ -84,4 +84,15 @@ class AttUNetConvLSTM(nn.Module):
         d3 = self.up3.forward_nhwc(bott, k3)
         d2 = self.up2.forward_nhwc(d3, k2)
         d1 = self.up1.forward_nhwc(d2, k1)
+        if target is not None:
+            # training step: loss = MSE(head(d1), target) in one fused pass each way (ops.HeadMSEFn)
+            if ops.head_mse_ok(d1.shape[-1], self.head.weight.shape[0]):
+                return ops.HeadMSEFn.apply(d1, self.head.weight, self.head.bias, target)
+            return ops.mse_loss(ops.HeadFn.apply(d1, self.head.weight, self.head.bias), target)
         return ops.HeadFn.apply(d1, self.head.weight, self.head.bias)
+
+    def forward_loss(self, x_seq, target):
+        """nn.MSELoss()(self(x_seq), target) (main_final.py:556-561) with the head and the loss fused."""
+        B, T, C, H, W = x_seq.shape
+        x = ops.StageIn.apply(x_seq.reshape(B * T, C, H, W), compute_dtype(), 16, T)
+        return self.forward_staged(x, B, T, target=target)

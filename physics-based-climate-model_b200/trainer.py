@@ -56,7 +56,12 @@ class TrainStep:
         self.buckets = []            # [(hook name, lo, hi)]
         self.tail_bucket = None      # (lo, hi) reduced after backward
         self.split = 0
-        if self.world > 1 and hasattr(model, "convlstm") and os.environ.get("PCM_OVERLAP_ALLREDUCE", "1") != "0":
+        # A single GPU uses the same buckets without the all-reduce (PCM_BUCKETS_SINGLE=0: one fold + one Adam launch at
+        # the end): the folds and Adam updates of the two big buckets then run on the communication stream while
+        # backward continues, and only enc1's fold and update stay behind the last weight gradient.
+        single = self.world == 1 and os.environ.get("PCM_BUCKETS_SINGLE", "1") != "0"
+        if ((self.world > 1 or single) and hasattr(model, "convlstm")
+                and os.environ.get("PCM_OVERLAP_ALLREDUCE", "1") != "0"):
             off = lambda p: (p.main_grad.data_ptr() - fg.data_ptr()) // 4
             s_lstm = off(next(model.convlstm.parameters()))
             self.split = s_lstm
@@ -69,6 +74,10 @@ class TrainStep:
                     lo = s_enc2
             self.tail_bucket = (0, lo)
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.buckets else None
+        # models without any dropout site (the UNet family) skip the per-step advance of the device-side mask epoch
+        self.has_dropout = (float(getattr(model, "p_drop", 0.0) or 0.0) > 0.0 or any(
+            isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d, torch.nn.Dropout3d)) and m.p > 0.0 or
+            isinstance(m, torch.nn.MultiheadAttention) and m.dropout > 0.0 for m in model.modules()))
         self._copy_stream = None
         self.graph = None
         self.launches_per_step = 0
@@ -84,6 +93,16 @@ class TrainStep:
         """Backward has passed this bucket's hook: fold its packed gradients, then — on the communication stream, so that
         the rest of backward keeps running — all-reduce the range and apply Adam to it."""
         fg = self.opt.flat_grad
+        if self.world == 1:
+            # nothing to exchange: the communication stream waits for the weight gradients (side stream) and for backward
+            # so far, folds and updates; the main stream does not wait for anybody
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+            if self.side is not None and ops.side_forked():
+                self.comm_stream.wait_stream(self.side)
+            with torch.cuda.stream(self.comm_stream):
+                self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
+                self.opt.step_range(lo, hi, grad_scale=1.0)
+            return
         ops.join_side()
         self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
         self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -97,14 +116,19 @@ class TrainStep:
             # normalisation + seasonal channels + NHWC staging are one kernel
             from .config import compute_dtype
             xs, y = self._windows.stage(self.idx, compute_dtype())
+            if hasattr(self.model, "forward_loss"):
+                return self.model.forward_staged(xs, self.idx.numel(), self._windows.seq_len, target=y)
             out = self.model.forward_staged(xs, self.idx.numel(), self._windows.seq_len)
             return ops.mse_loss(out, y)
+        if hasattr(self.model, "forward_loss"):
+            return self.model.forward_loss(self.x, self.y)          # head + loss fused (ops.HeadMSEFn)
         return ops.mse_loss(self.model(self.x), self.y)
 
     def _step_impl(self):
         # fresh dropout masks on every step, also under graph replay (the scalar seeds are frozen in the graph; the
         # kernels mix this device-side counter into them)
-        lib().call("pcm_dropout_epoch_advance", torch.cuda.current_stream().cuda_stream)
+        if self.has_dropout:
+            lib().call("pcm_dropout_epoch_advance", torch.cuda.current_stream().cuda_stream)
         self.opt.zero_grad()
         fg = self.opt.flat_grad
         overlap = bool(self.buckets)
@@ -128,7 +152,8 @@ class TrainStep:
                 ops._GRAD_HOOKS.pop(name, None)
         if overlap:
             lo, hi = self.tail_bucket
-            dist.all_reduce(fg[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            if self.world > 1:
+                dist.all_reduce(fg[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             self.opt.step_range(lo, hi, grad_scale=1.0 / self.world)
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)     # the other buckets' updates are done
         else:

@@ -92,6 +92,39 @@ def test_convblock_tied_channel_maximum(G, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [16, 32])
+def test_head_mse_fused_matches_head_then_mse(G, C, dtype):
+    """ops.HeadMSEFn (head 1x1 + nn.MSELoss in one pass each way) against ops.HeadFn followed by ops.mse_loss and against
+    torch fp64 on the same (rounded) operands: loss, dx, dw, db."""
+    from pcm_b200 import ops
+    g = torch.Generator().manual_seed(5 + C)
+    N, H, W, K = 5, 12, 18, 2
+    x = torch.randn(N, H, W, C, generator=g).to(dtype)
+    w = (torch.randn(K, C, 1, 1, generator=g) / C ** 0.5)
+    b = torch.randn(K, generator=g)
+    y = torch.randn(N, K, H, W, generator=g)
+    res = {}
+    for name in ("fused", "split", "torch"):
+        if name == "torch":
+            xr = x.double().requires_grad_(True); wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
+            pred = torch.einsum("nhwc,kc->nkhw", xr, wr[:, :, 0, 0]) + br[None, :, None, None]
+            loss = ((pred - y.double()) ** 2).mean()
+        else:
+            xr = x.cuda().requires_grad_(True); wr = w.cuda().requires_grad_(True); br = b.cuda().requires_grad_(True)
+            if name == "fused":
+                assert ops.head_mse_ok(C, K)
+                loss = ops.HeadMSEFn.apply(xr, wr, br, y.cuda())
+            else:
+                loss = ops.mse_loss(ops.HeadFn.apply(xr, wr, br), y.cuda())
+        (loss * 3.0).backward()
+        res[name] = [t.detach().double().cpu() for t in (loss, xr.grad, wr.grad, br.grad)]
+    tol = 1e-5 if dtype == torch.float32 else 1e-2        # bf16: dx is rounded to bf16
+    for a, f, t in zip(res["split"], res["fused"], res["torch"]):
+        assert float((f - t).norm() / t.norm()) < tol
+        assert float((f - a).norm() / t.norm()) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("tag", ["attunet_small", "attunet_cfg3_b2"])
 def test_attunet(G, tag, dtype):
     _check(G.case_attunet(tag, dtype), dtype)
