@@ -86,6 +86,7 @@ class PackPlan:
         self.gtables = {}
         self.gdirty = False
         self.gmax = 0
+        self.pending_join = False  # repack() was issued on the side stream and nothing has waited for it yet
 
     def lookup(self, key):
         e = self.entries.get(key)
@@ -264,6 +265,9 @@ def pack_weight(w: torch.Tensor, so: int, si: int, st: int, O: int, I: int, taps
         key = (src, so, si, st, O, I, taps, Op, Ip, dtype, group)
         hit = _PLAN.lookup(key)
         if hit is not None:
+            if _PLAN.pending_join:             # the step's re-pack was issued on the side stream: its first consumer waits
+                _PLAN.pending_join = False
+                join_side()
             return hit
     out = torch.empty((taps, group * Op, group * Ip), device=w.device, dtype=dtype)
     if group > 1:

@@ -138,8 +138,13 @@ class TrainStep:
                 ops._GRAD_HOOKS[name] = (lambda lo=lo, hi=hi: self._bucket_ready(lo, hi))
         try:
             with ops.use_pack_plan(self.plan, self.side):
-                self.plan.repack()
+                # the one-launch weight re-pack runs beside the input staging (second stream); the first layer that takes
+                # a packed weight joins it (ops.pack_weight joins on the first hit)
+                with ops.side_stream():
+                    self.plan.repack()
+                self.plan.pending_join = ops.side_forked()
                 loss = self._forward_loss()
+                self.plan.pending_join = False
                 loss.backward()
                 ops.join_side()
                 if overlap:
