@@ -93,21 +93,24 @@ class TrainStep:
         """Backward has passed this bucket's hook: fold its packed gradients, then — on the communication stream, so that
         the rest of backward keeps running — all-reduce the range and apply Adam to it."""
         fg = self.opt.flat_grad
-        if self.world == 1:
-            # nothing to exchange: the communication stream waits for the weight gradients (side stream) and for backward
-            # so far, folds and updates; the main stream does not wait for anybody
+        # the communication stream waits for backward so far and for the weight gradients (side stream), then folds,
+        # reduces and updates; the main stream does not wait for anybody (PCM_BUCKET_FOLD_MAIN=1: round-2 behaviour, the
+        # fold on the main stream after joining the side stream)
+        if os.environ.get("PCM_BUCKET_FOLD_MAIN", "0") == "1" and self.world > 1:
+            ops.join_side()
+            self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
             self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
-            if self.side is not None and ops.side_forked():
-                self.comm_stream.wait_stream(self.side)
             with torch.cuda.stream(self.comm_stream):
-                self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
-                self.opt.step_range(lo, hi, grad_scale=1.0)
+                dist.all_reduce(fg[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+                self.opt.step_range(lo, hi, grad_scale=1.0 / self.world)
             return
-        ops.join_side()
-        self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
         self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self.side is not None and ops.side_forked():
+            self.comm_stream.wait_stream(self.side)
         with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(fg[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            self.plan.unpack_grads(fg.data_ptr() + 4 * lo, fg.data_ptr() + 4 * hi)
+            if self.world > 1:
+                dist.all_reduce(fg[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             self.opt.step_range(lo, hi, grad_scale=1.0 / self.world)
 
     def _forward_loss(self):
