@@ -159,6 +159,8 @@ def algo_cost(name: str, args):
         return 2.0 * a["N"] * a["P"] * a["C"] * a["K"] * (k + (1 if k == 2 else 0)), a["N"] * a["P"] * (a["C"] * es() * k + a["K"] * 4), "hbm"
     if name in ("pcm_mse_fwd", "pcm_mse_bwd"):
         return 0.0, a["n"] * 4 * (2 if name == "pcm_mse_fwd" else 3), "hbm"
+    if name == "pcm_adam_apply":
+        return 0.0, a["n"] * 4 * 7, "hbm"
     if name == "pcm_adam_step":
         return 0.0, a["n"] * 4 * 7, "hbm"                                      # p,g,m,v in; p,m,v out
     if name == "pcm_pack_weight":
