@@ -740,7 +740,8 @@ class ConvBlockFn(torch.autograd.Function):
 
         _call("pcm_spatial_gate_bwd_dq", dout.data_ptr(), a2.data_ptr(), se.data_ptr(), gate.data_ptr(), dq.data_ptr(),
               N, P, Co, d, st)
-        _call("pcm_spatial_gate_bwd_dw", dq.data_ptr(), cmap.data_ptr(), gsp.data_ptr(), N, H, W, st)
+        with side_stream(e, maps):              # a parameter gradient: nothing in the backward chain waits for it
+            _call("pcm_spatial_gate_bwd_dw", dq.data_ptr(), cmap.data_ptr(), gsp.data_ptr(), N, H, W, _s())
         da2 = torch.empty_like(a2)
         _call("pcm_spatial_gate_bwd_da", dout.data_ptr(), a2.data_ptr(), se.data_ptr(), gate.data_ptr(),
               cmap.data_ptr(), dq.data_ptr(), wsp.data_ptr(), da2.data_ptr(), dse.data_ptr(), N, H, W, Co, d, st)
