@@ -129,7 +129,8 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
   L.gate = full ? PCM_TAKE(P * 4) : 0;
   L.dm = (full && bwd) ? PCM_TAKE(P * 8) : 0;
   L.bar = PCM_TAKE(64);                                  // mbarriers of the bulk copies that bring the image in (one per 32 KB piece)
-  L.part = PCM_TAKE((size_t)2 * (kFT / 32) * C * 4);                      // chan_put: 2 slots x warps (at most kFT / 32) x C floats
+  L.part = PCM_TAKE((size_t)2 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 2 slots x warps x C floats (launches never
+                                                                          // use more threads than tail_threads)
   // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
   //         | wt[2][7][8] | wtf[2][7][8] | dw[100] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
   L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + (full ? C * C / 4 : 0)) * 4);
@@ -459,8 +460,10 @@ __device__ __forceinline__ void tail_finish_from_pool(T* s_img, uint8_t* smem, c
 // ---------------------------------------------------------------------------------------------------------------
 // forward tails.  FULL = false: y = silu(GN(x)).  FULL = true: out = a*se*gate with a = silu(GN(x)).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool FULL>
-__global__ void __launch_bounds__(kFT, 1)
+// MAXT = 256: the instantiation for images that launch at most 256 threads — compiled for three CTAs per SM (<= 85
+// registers instead of 90), which lets 384 images of 24x36x32 run as ONE wave (444 slots) instead of two.
+template <typename T, bool FULL, int MAXT = kFT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 1)
 convblock_tail_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ wsp,
                           float* __restrict__ stats, float* __restrict__ pool_g, float* __restrict__ se_g,
@@ -1496,10 +1499,12 @@ extern "C" int pcm_convblock_tail_fwd(const void* x, const float* gamma, const f
   PCM_REQUIRE(smem <= 227 * 1024, "convblock_tail_fwd: image does not fit shared memory (%zu B)", smem);
   PCM_REQUIRE((maps == nullptr) == (ties == nullptr), "convblock_tail_fwd: maps and ties are saved together");
   int rc = PCM_OK;
+  const bool narrow = tail_threads(H, W, C) <= 256;
   PCM_DISPATCH_DTYPE(dtype, T, {
-    rc = tail_set_smem(convblock_tail_fwd_kernel<T, true>, smem, "convblock_tail_fwd");
+    auto kern = narrow ? convblock_tail_fwd_kernel<T, true, 256> : convblock_tail_fwd_kernel<T, true, kFT>;
+    rc = tail_set_smem(kern, smem, "convblock_tail_fwd");
     if (rc == PCM_OK)
-      pcm::launch(convblock_tail_fwd_kernel<T, true>, N, tail_launch_threads(convblock_tail_fwd_kernel<T, true>, N, H, W, C, smem, 2.5f), smem, (cudaStream_t)s, 
+      pcm::launch(kern, N, tail_launch_threads(kern, N, H, W, C, smem, 2.5f), smem, (cudaStream_t)s,
           (const T*)x, gamma, beta, w1, w2, wsp, stats, pool, se, hid, maps, ties, (T*)out, H, W, C, Cr, eps);
   });
   if (rc != PCM_OK) return rc;
