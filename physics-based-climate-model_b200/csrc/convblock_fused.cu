@@ -1312,10 +1312,10 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
 // the backward kernels, ~2.5 for the forward ones).  PCM_TAIL_WAVES=0 keeps tail_threads().
 template <typename K>
 static int tail_launch_threads(K kern, int N, int H, int W, int C, size_t smem, float c0) {
-  static int on = -1, sms = 0;
-  if (on < 0) {
-    const char* e = getenv("PCM_TAIL_WAVES");
-    on = e ? atoi(e) : 1;
+  static int sms = 0;
+  const char* e = getenv("PCM_TAIL_WAVES");          // read per launch (host side, cheap): tests flip it inside one process
+  const int on = e ? atoi(e) : 1;
+  if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -355,6 +355,43 @@ def test_side_stream_matches_single_stream(G, dtype, monkeypatch):
     assert float((p0 - p1).norm() / p0.norm()) < tol
 
 
+@pytest.mark.parametrize("switch", ["PCM_BUCKETS_SINGLE", "PCM_HEAD_MSE", "PCM_CONV_GROUP", "PCM_WGRAD_GROUP", "PCM_TAIL_WAVES"])
+def test_step_variants_agree(G, switch, monkeypatch):
+    """Every scheduling / kernel-form switch of the captured step — gradient buckets with per-bucket fold + Adam on the
+    communication stream at world size 1, the fused head + loss, the pixel-group forms of the thin convolutions and weight
+    gradients, the per-launch CTA width of the tails — must leave losses and parameters where the plain variant puts them
+    (same mathematics; only fp32 summation order and bf16 rounding of equal sums may differ)."""
+    import pcm_b200
+    from oracle import model_oracle as O
+    from pcm_b200.src.unet_convlstm_attention import AttUNetConvLSTM
+    from pcm_b200.trainer import TrainStep
+    B, T, H, W, base = 4, 3, 48, 72, 16
+    sd = O.synth_state_dict(O.attunet_spec(7, 2, base), 191)
+    batches = [O.synth_attunet_batch(B, T, H, W, 192 + i)[:2] for i in range(3)]
+    runs = []
+    for val in ("0", None):
+        if val is None:
+            monkeypatch.delenv(switch, raising=False)
+        else:
+            monkeypatch.setenv(switch, val)
+        model = AttUNetConvLSTM(7, 2, base, seq_len=T)
+        model.load_state_dict(sd)
+        model = model.cuda()
+        step = TrainStep(model, (B, T, 7, H, W), (B, 2, H, W), lr=1e-3)
+        if switch == "PCM_BUCKETS_SINGLE":
+            assert bool(step.buckets) == (val is None)
+        step.load_batch(*batches[0])
+        step.warmup_and_capture(warmup=2)                  # parameters / Adam state restored afterwards
+        losses = [float(step.step(*batches[i % 3]).item()) for i in range(6)]
+        step.check_kernels()
+        flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()]).cpu()
+        runs.append((losses, flat))
+    (l0, p0), (l1, p1) = runs
+    for a, b in zip(l0, l1):
+        assert abs(a - b) / abs(a) < 5e-3, (l0, l1)
+    assert float((p0 - p1).norm() / p0.norm()) < 5e-3
+
+
 @pytest.mark.parametrize("kind", ["simplecnn", "cnn_transformer", "unet"])
 def test_trainstep_captures_every_model_family(G, kind):
     """TrainStep (CUDA graph, second stream enabled by default) on the models that issue little or no side-stream work:
