@@ -1112,6 +1112,16 @@ def head_mse_ok(C: int, K: int) -> bool:
     return os.environ.get("PCM_HEAD_MSE", "1") != "0" and bool(lib()._fn["pcm_head_mse_supported"](C, K))
 
 
+def head_or_loss(x, w, b, target=None):
+    """The model's final 1x1 convolution; with `target` the training loss nn.MSELoss()(head(x), target) instead — fused
+    (HeadMSEFn) when the head shape allows, else head followed by the loss."""
+    if target is None:
+        return HeadFn.apply(x, w, b)
+    if head_mse_ok(x.shape[-1], w.shape[0]):
+        return HeadMSEFn.apply(x, w, b, target)
+    return mse_loss(HeadFn.apply(x, w, b), target)
+
+
 class MSELossFn(torch.autograd.Function):
     """nn.MSELoss() (main_final.py:544,559)."""
 

@@ -196,19 +196,21 @@ class Conv2dFn(torch.autograd.Function):
         s2 = _s2_supported(x, w, stride, pad)
         if s2:
             _, dgr_idx, fold_idx = _s2_indices(Co, Ci, Cip, x.device)
-            tmp = torch.zeros((6, Co, 2 * Cip), device=x.device, dtype=torch.float32)
-            _call("pcm_wgrad3x3s2_tc", dy.data_ptr(), Ho * Wo * Co, Co, Co, x.data_ptr(), H * W * Cip, Cip, tmp.data_ptr(),
-                  2 * Cip, 1, Co * 2 * Cip, N, Ho, Wo, _s())
-            folded = tmp.reshape(-1)[fold_idx]                                  # layout gather back to (Co, Ci, 3, 3)
-            _call("pcm_add", gw.data_ptr(), folded.data_ptr(), gw.data_ptr(), gw.numel(), 0, _s())
-        elif stride == 1 and pad == K // 2:
-            wgrad_same(dy, x, gw, N, H, W, Co, Cip, Ci, K)
-        else:
-            conv_wgrad(dy, x, gw, Ci * KK, KK, 1, N, Ho, Wo, Co, Co, H, W, Cip, Ci, K, K, stride, pad)
         rb = None
-        if b is not None:
-            gb, rb = _grad_buf(b)
-            channel_sum(dy, gb, N, Ho * Wo, Co, Co)
+        with ops.side_stream(dy, x):            # weight / bias gradients beside the data-gradient chain
+            if s2:
+                tmp = torch.zeros((6, Co, 2 * Cip), device=x.device, dtype=torch.float32)
+                _call("pcm_wgrad3x3s2_tc", dy.data_ptr(), Ho * Wo * Co, Co, Co, x.data_ptr(), H * W * Cip, Cip, tmp.data_ptr(),
+                      2 * Cip, 1, Co * 2 * Cip, N, Ho, Wo, _s())
+                folded = tmp.reshape(-1)[fold_idx]                              # layout gather back to (Co, Ci, 3, 3)
+                _call("pcm_add", gw.data_ptr(), folded.data_ptr(), gw.data_ptr(), gw.numel(), 0, _s())
+            elif stride == 1 and pad == K // 2:
+                wgrad_same(dy, x, gw, N, H, W, Co, Cip, Ci, K)
+            else:
+                conv_wgrad(dy, x, gw, Ci * KK, KK, 1, N, Ho, Wo, Co, Co, H, W, Cip, Ci, K, K, stride, pad)
+            if b is not None:
+                gb, rb = _grad_buf(b)
+                channel_sum(dy, gb, N, Ho * Wo, Co, Co)
         dx = None
         if ctx.needs_input_grad[0] and s2:
             wkd = _gather_weight(w, dgr_idx, (4, 4 * Cip, Co), dt)
@@ -258,8 +260,9 @@ class ConvT2x2Fn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.convT2x2_dgrad(dy, wt, B, h, w, Ci, Co, 4 * h * w * Co, Co)
-        ops.convT2x2_wgrad(x, dy, gwt, B, h, w, Ci, Co, 4 * h * w * Co, Co)
-        channel_sum(dy, gbt, B, 4 * h * w, Co, Co)
+        with ops.side_stream(dy, x):
+            ops.convT2x2_wgrad(x, dy, gwt, B, h, w, Ci, Co, 4 * h * w * Co, Co)
+            channel_sum(dy, gbt, B, 4 * h * w, Co, Co)
         return dx, rwt, rbt, None
 
 
@@ -438,7 +441,8 @@ class AddPosFn(torch.autograd.Function):
         B, LE = ctx.dims
         dy = dy.contiguous()
         gp, rp = _grad_buf(pos)
-        _call("pcm_batch_sum", dy.data_ptr(), gp.data_ptr(), B, LE, _DT[dy.dtype], _s())   # dpos = sum_b dy[b]
+        with ops.side_stream(dy):
+            _call("pcm_batch_sum", dy.data_ptr(), gp.data_ptr(), B, LE, _DT[dy.dtype], _s())   # dpos = sum_b dy[b]
         return dy, rp
 
 
@@ -471,8 +475,9 @@ class LinearFn(torch.autograd.Function):
             dy = dz
         gw, rw = _grad_buf(w)
         gb, rb = _grad_buf(b)
-        wgrad_same(dy, x, gw, B, 1, L, N, K, K, 1)
-        channel_sum(dy, gb, B, L, N, N)
+        with ops.side_stream(dy, x):            # parameter gradients: nothing in the backward chain waits for them
+            wgrad_same(dy, x, gw, B, 1, L, N, K, K, 1)
+            channel_sum(dy, gb, B, L, N, N)
         dx = None
         if ctx.needs_input_grad[0]:
             wkt = pack_weight(w, 1, K, 0, K, N, 1, dt)                          # [1][K][N] = W^T

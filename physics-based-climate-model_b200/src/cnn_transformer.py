@@ -62,7 +62,11 @@ class CNNTransformer(nn.Module):
         f = ops_nn.LinearFn.apply(ops_nn.dropout(f, p, tr), lyr.linear2.weight, lyr.linear2.bias, False)
         return ops_nn.AddLayerNormFn.apply(xr, f, lyr.norm2.weight, lyr.norm2.bias, pd, ops_nn.next_seed() if pd > 0 else 0)
 
-    def forward(self, x):
+    def forward_loss(self, x, target):
+        """nn.MSELoss()(self(x), target) with the final 1x1 convolution and the loss fused (the training step's form)."""
+        return self.forward(x, target)
+
+    def forward(self, x, target=None):
         B = x.size(0)
         e = self.encoder
         a = ops.StageIn.apply(x, compute_dtype())
@@ -79,4 +83,4 @@ class CNNTransformer(nn.Module):
         y = t.reshape(B, Hh, Ww, E)
         y = ops_nn.ConvT2x2Fn.apply(y, d[0].weight, d[0].bias, True)
         y = ops_nn.ConvT2x2Fn.apply(y, d[2].weight, d[2].bias, True)
-        return ops.HeadFn.apply(y, d[4].weight, d[4].bias)
+        return ops.head_or_loss(y, d[4].weight, d[4].bias, target)

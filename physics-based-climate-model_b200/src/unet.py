@@ -125,7 +125,11 @@ class UNet(nn.Module):
             setattr(self, name, Up(a, b, b))
         self.head = nn.Conv2d(w1, out_ch, kernel_size=1)
 
-    def forward(self, x):
+    def forward_loss(self, x, target):
+        """nn.MSELoss()(self(x), target) with the head and the loss fused (the training step's form)."""
+        return self.forward(x, target)
+
+    def forward(self, x, target=None):
         a = ops.StageIn.apply(x, compute_dtype())
         s1 = self.enc1.forward_nhwc(a)
         p1, k1 = ops.PoolSkipFn.apply(s1, 1, self.up1.up.out_channels)
@@ -138,4 +142,4 @@ class UNet(nn.Module):
         y = self.up3.forward_nhwc(y, k3)
         y = self.up2.forward_nhwc(y, k2)
         y = self.up1.forward_nhwc(y, k1)
-        return ops.HeadFn.apply(y, self.head.weight, self.head.bias)
+        return ops.head_or_loss(y, self.head.weight, self.head.bias, target)

@@ -84,12 +84,8 @@ class AttUNetConvLSTM(nn.Module):
         d3 = self.up3.forward_nhwc(bott, k3)
         d2 = self.up2.forward_nhwc(d3, k2)
         d1 = self.up1.forward_nhwc(d2, k1)
-        if target is not None:
-            # training step: loss = MSE(head(d1), target) in one fused pass each way (ops.HeadMSEFn)
-            if ops.head_mse_ok(d1.shape[-1], self.head.weight.shape[0]):
-                return ops.HeadMSEFn.apply(d1, self.head.weight, self.head.bias, target)
-            return ops.mse_loss(ops.HeadFn.apply(d1, self.head.weight, self.head.bias), target)
-        return ops.HeadFn.apply(d1, self.head.weight, self.head.bias)
+        # with a target (training step): loss = MSE(head(d1), target) in one fused pass each way (ops.HeadMSEFn)
+        return ops.head_or_loss(d1, self.head.weight, self.head.bias, target)
 
     def forward_loss(self, x_seq, target):
         """nn.MSELoss()(self(x_seq), target) (main_final.py:556-561) with the head and the loss fused."""
