@@ -165,6 +165,11 @@ PCM_API int pcm_wgrad3x3_tc_grouped(const void* dy, long long dy_ns, int Co, con
 PCM_API int pcm_conv1x1_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, int relu, pcm_stream_t s);
+/* nn.Linear -> ReLU -> nn.Dropout(p) (inner half of the transformer FFN, src/cnn_transformer.py:25-31) in one launch: the
+ * mask pcm_dropout(seed) would draw on the dense destination is applied in the store epilogue (0 < p < 1). */
+PCM_API int pcm_conv1x1_drop_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                                long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N, int relu,
+                                float drop_p, long long seed, pcm_stream_t s);
 /* weight gradient of the above: dw[co*sa + ci*sb] += sum_p dy(p,co)*x(p,ci)  (fp32, accumulates) */
 PCM_API int pcm_wgrad1x1_tc(const void* dy, long long dy_ns, int dy_ps, int Co, int Co_real, const void* x,
                             long long x_ns, int x_ps, int Ci, int Ci_real, float* dw, long long sa, long long sb,
@@ -325,6 +330,8 @@ PCM_API int pcm_relu_bwd(const void* dy, const void* y, void* dx, long long n, i
  * one step still agree.  pcm_dropout_epoch reads it back (synchronous; tests). */
 PCM_API int pcm_dropout_epoch_advance(pcm_stream_t s);
 PCM_API long long pcm_dropout_epoch(void);
+/* dx = y > 0 ? dy * scale : 0: backward of ReLU -> dropout from the saved output alone (scale = 1 / (1 - p)) */
+PCM_API int pcm_relu_bwd_scaled(const void* dy, const void* y, void* dx, long long n, float scale, int dtype, pcm_stream_t s);
 PCM_API int pcm_dropout(const void* x, void* y, long long n, float p, long long seed, int dtype, pcm_stream_t s);
 PCM_API int pcm_dropout_mask(float* mask, long long n, float p, long long seed, pcm_stream_t s);
 
@@ -341,6 +348,11 @@ PCM_API int pcm_add_layernorm_fwd(const void* a, const void* b, const float* gam
 PCM_API int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float* stat, const float* gamma, void* ds,
                               void* db, float* dgamma, float* dbeta, int M, int E, float drop_p, long long seed, int dtype,
                               pcm_stream_t s);
+/* the same with the incoming gradient given as TWO addends (dy2 nullable): the gradients of the two consumers of a residual
+ * fork are summed while loading instead of by a launch of their own */
+PCM_API int pcm_layernorm_bwd2(const void* dy, const void* dy2, const void* sum_in, const float* stat, const float* gamma,
+                               void* ds, void* db, float* dgamma, float* dbeta, int M, int E, float drop_p, long long seed,
+                               int dtype, pcm_stream_t s);
 /* multi-head self-attention core of nn.MultiheadAttention: qkv [B][L][3*nh*D] (q | k | v; head h = columns
  * h*D..), out [B][L][nh*D] = softmax(scale * q k^T) v per head, lse [B][nh][L] fp32 saved for backward.
  * drop_p: dropout on the attention probabilities (counter-based mask from `seed`).  D in {8, 16, 32, 64}. */

@@ -298,6 +298,21 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dy,
   }
 }
 
+// dx = y > 0 ? dy * scale : 0 — backward of ReLU followed by dropout from the saved OUTPUT alone: y > 0 exactly where the
+// pre-activation was positive and the element was kept, and the kept gradient is scaled by 1 / (1 - p)
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd_scaled_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                               T* __restrict__ dx, long long n8, float scale) {
+  PCM_PDL_ENTRY();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], o[8];
+    load8(dy + i * 8, g); load8(y + i * 8, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] * scale : 0.f;
+    store8(dx + i * 8, g);
+  }
+}
+
 // y = x * keep(seed, i) / (1 - p): counter-based mask, so applying the same call to dy is the backward
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, float p,
@@ -435,6 +450,15 @@ extern "C" int pcm_relu_bwd(const void* dy, const void* y, void* dx, long long n
   PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(relu_bwd_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s, 
                                    static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<T*>(dx), n / 8)));
   return check_launch("relu_bwd");
+}
+
+extern "C" int pcm_relu_bwd_scaled(const void* dy, const void* y, void* dx, long long n, float scale, int dtype,
+                                   pcm_stream_t s) {
+  PCM_REQUIRE(n % 8 == 0, "relu_bwd_scaled: n must be a multiple of 8");
+  if (n == 0) return PCM_OK;
+  PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(relu_bwd_scaled_kernel<T>, ew_grid(n / 8), 256, 0, (cudaStream_t)s,
+                                   static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<T*>(dx), n / 8, scale)));
+  return check_launch("relu_bwd_scaled");
 }
 
 extern "C" int pcm_dropout(const void* x, void* y, long long n, float p, long long seed, int dtype, pcm_stream_t s) {

@@ -48,6 +48,9 @@ struct ConvTcParams {
   int Wb, Hb, Nb, tiles_w, tiles_h, num_tiles;
   int KC, kchunks, stages;
   int ksz, relu;          // kernel size (1 or 3; pad = ksz/2), ReLU in the store epilogue
+  float drop_p;           // > 0: nn.Dropout(p) after the (ReLU) epilogue — the mask of pcm_dropout on the dense destination
+  unsigned long long drop_seed;          // (element index = offset from dst), so the fused and the two-kernel forms draw
+  const unsigned long long* drop_epoch;  // the same mask; the library's epoch cell is mixed in on the device
   int mode;               // 0: conv taps (shifted boxes) ; 1: ConvTranspose2d(k2,s2) data gradient — 4 taps (kh,kw), tap q
                           //    gathers dy(2h+kh, 2w+kw) through the 5-D views tmA (kh=0) / tmA2 (kh=1) {C, kw, w, h, n}
                           // 2: 3x3 / stride-2 / pad-1 conv — the input is viewed as {2C (pw, c), W/2, ph, H/2, n}; 6 taps
@@ -281,6 +284,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.drop_p > 0.f) {
+            const unsigned long long sd = mix_epoch(p.drop_seed, p.drop_epoch);
+            const float sc = 1.f / (1.f - p.drop_p);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              v[j] = dropout_uniform(sd, (unsigned long long)(offc + j)) >= p.drop_p ? v[j] * sc : 0.f;
           }
           if (p.dst_f32) {
             float* dp = reinterpret_cast<float*>(dst) + offc;
@@ -603,7 +613,7 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
                            long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N,
                            int dst_f32, int accumulate, const float* lstm_gx, const float* lstm_c_prev,
                            float* lstm_c_out, void* lstm_acts, pcm_stream_t s, int ksz = 3, int relu = 0, int mode = 0,
-                           int ps_co = 0, int pad = -1, int group = 1) {
+                           int ps_co = 0, int pad = -1, int group = 1, float drop_p = 0.f, long long drop_seed = 0) {
   // group > 1: pcm_conv3x3_tc_grouped — H, W, Cin, Cout are already those of the grouped image (W/g pixels of g*C channels)
   PCM_REQUIRE(Cin % 16 == 0 && Cin >= 16, "conv3x3_tc: Cin must be a multiple of 16 (got %d)", Cin);
   PCM_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv3x3_tc: Cin above 64 must be a multiple of 64 (got %d)", Cin);
@@ -630,6 +640,8 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   // halo kernel: one halo box per (tile, channel chunk), nine shifted descriptors, weights resident.  Wide layers
   // keep only a slice of the output channels per CTA (blockIdx.y) so that the resident weights stay <= ~100 KB.
   int cslice = 0;
+  PCM_REQUIRE(drop_p == 0.f || (drop_p > 0.f && drop_p < 1.f && ksz == 1 && ps_co == 0 && lstm_gx == nullptr),
+              "conv_tc: fused dropout is wired for the 1x1 / linear form with 0 < p < 1");
   if (halo_env && ksz == 3 && mode == 0 && ps_co == 0 && !relu && lstm_gx == nullptr && Cin <= 128) {
     const size_t budget = (size_t)(Cin <= 32 ? 64 : Cin <= 64 ? 148 : 100) * 1024;
     for (int cs = Cout; cs >= 16; cs >>= 1) {
@@ -727,6 +739,11 @@ static int conv3x3_tc_impl(const void* src, long long src_ns, int src_ps, int H,
   p.KC = Cin < 64 ? Cin : 64;
   p.kchunks = Cin / p.KC;
   p.ksz = ksz; p.relu = relu; p.mode = mode; p.ps_co = ps_co;
+  p.drop_p = drop_p; p.drop_seed = (unsigned long long)drop_seed; p.drop_epoch = nullptr;
+  if (drop_p > 0.f) {
+    p.drop_epoch = dropout_epoch_cell();
+    PCM_REQUIRE(p.drop_epoch != nullptr, "conv_tc: could not allocate the dropout epoch cell");
+  }
   p.pad = pad >= 0 ? pad : (ksz >> 1);
   const int ntaps = mode == 1 ? 4 : mode == 2 ? 6 : ksz * ksz;
   p.dst_ns = dst_ns; p.dst_ps = dst_ps; p.dst_f32 = dst_f32; p.accumulate = accumulate;
@@ -831,6 +848,16 @@ extern "C" int pcm_conv1x1_tc(const void* src, long long src_ns, int src_ps, int
                               int dst_f32, int accumulate, int relu, pcm_stream_t s) {
   return conv3x3_tc_impl(src, src_ns, src_ps, H, W, Cin, dst, dst_ns, dst_ps, Cout, wk, bias, N, dst_f32, accumulate,
                          nullptr, nullptr, nullptr, nullptr, s, 1, relu);
+}
+
+// nn.Linear -> ReLU -> nn.Dropout(p) (the inner half of the transformer FFN, src/cnn_transformer.py:25-31) in one launch:
+// the dropout mask of pcm_dropout on the dense destination is applied in the store epilogue.
+extern "C" int pcm_conv1x1_drop_tc(const void* src, long long src_ns, int src_ps, int H, int W, int Cin, void* dst,
+                                   long long dst_ns, int dst_ps, int Cout, const void* wk, const float* bias, int N, int relu,
+                                   float drop_p, long long seed, pcm_stream_t s) {
+  PCM_REQUIRE(dst_ps == Cout && dst_ns == (long long)H * W * Cout, "conv1x1_drop_tc: the destination must be dense");
+  return conv3x3_tc_impl(src, src_ns, src_ps, H, W, Cin, dst, dst_ns, dst_ps, Cout, wk, bias, N, 0, 0, nullptr, nullptr, nullptr,
+                         nullptr, s, 1, relu, 0, 0, -1, 1, drop_p, seed);
 }
 
 // ConvTranspose2d(kernel 2, stride 2) forward: one GEMM [pixels x Cin] x [Cin x 4*Cout] whose epilogue scatters

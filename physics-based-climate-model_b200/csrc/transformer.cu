@@ -94,7 +94,7 @@ add_layernorm_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const
 // per-channel sums are reduced through per-warp shared-memory rows (no shared-memory atomics).
 template <typename T>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ sum_in, const float* __restrict__ stat,
+layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ sum_in, const float* __restrict__ stat,
                      const float* __restrict__ gamma, T* __restrict__ ds, T* __restrict__ db, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int M, int E, float drop_p, unsigned long long seed,
                      const unsigned long long* __restrict__ epoch) {
@@ -128,6 +128,12 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ sum_in, con
       if (vi < nv && tok) {
         float d[8], x[8];
         load8(dy + (long long)m * E + vi * 8, d);
+        if (dy2 != nullptr) {                 // second addend of the incoming gradient (a residual fork's other branch),
+          float d2[8];                        // summed here instead of by a launch of its own; rounded like pcm_add's output
+          load8(dy2 + (long long)m * E + vi * 8, d2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = round_to<T>(d[j] + d2[j]);
+        }
         load8(sum_in + (long long)m * E + vi * 8, x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -460,9 +466,18 @@ extern "C" int pcm_add_layernorm_fwd(const void* a, const void* b, const float* 
   return check_launch("add_layernorm_fwd");
 }
 
+extern "C" int pcm_layernorm_bwd2(const void* dy, const void* dy2, const void* sum_in, const float* stat, const float* gamma,
+                                  void* ds, void* db, float* dgamma, float* dbeta, int M, int E, float drop_p, long long seed,
+                                  int dtype, pcm_stream_t s);
 extern "C" int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float* stat, const float* gamma, void* ds,
                                  void* db, float* dgamma, float* dbeta, int M, int E, float drop_p, long long seed,
                                  int dtype, pcm_stream_t s) {
+  return pcm_layernorm_bwd2(dy, nullptr, sum_in, stat, gamma, ds, db, dgamma, dbeta, M, E, drop_p, seed, dtype, s);
+}
+
+extern "C" int pcm_layernorm_bwd2(const void* dy, const void* dy2, const void* sum_in, const float* stat, const float* gamma,
+                                  void* ds, void* db, float* dgamma, float* dbeta, int M, int E, float drop_p, long long seed,
+                                  int dtype, pcm_stream_t s) {
   PCM_REQUIRE(ln_shape_ok(E), "layernorm_bwd: E must be 8..256 (power of two) or a multiple of 256 up to 1024 (got %d)", E);
   PCM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: 0 <= drop_p < 1");
   PCM_REQUIRE(E <= 768, "layernorm_bwd: E up to 768 (per-warp reduction rows in shared memory), got %d", E);
@@ -474,7 +489,8 @@ extern "C" int pcm_layernorm_bwd(const void* dy, const void* sum_in, const float
   const unsigned long long* epoch = dropout_epoch_cell();
   PCM_REQUIRE(epoch != nullptr, "layernorm_bwd: could not allocate the dropout epoch cell");
   PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(layernorm_bwd_kernel<T>, grid, 256, 8 * 2 * E * sizeof(float), (cudaStream_t)s,
-                                   static_cast<const T*>(dy), static_cast<const T*>(sum_in), stat, gamma, static_cast<T*>(ds),
+                                   static_cast<const T*>(dy), static_cast<const T*>(dy2), static_cast<const T*>(sum_in), stat, gamma,
+                                   static_cast<T*>(ds),
                                    drop_p > 0.f ? static_cast<T*>(db) : nullptr, dgamma, dbeta, M, E, drop_p,
                                    (unsigned long long)seed, epoch)));
   return check_launch("layernorm_bwd");

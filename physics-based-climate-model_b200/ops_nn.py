@@ -344,28 +344,39 @@ class AddFn(torch.autograd.Function):
         return g, g
 
 
+_PENDING_ADD = {}      # data_ptr of a gradient handed on by a lazy fork -> its second addend (consumed by AddLayerNormFn.backward)
+
+
 class ForkFn(torch.autograd.Function):
     """x -> (x, x) for a tensor consumed by two branches (residual connections): the two incoming gradients are
-    summed by pcm_add instead of autograd's own accumulation kernel."""
+    summed by pcm_add instead of autograd's own accumulation kernel.  lazy=True (ONLY when x is the output of
+    AddLayerNormFn, whose backward reads the pair): the sum is not materialised — g1 is handed on and g2 parked in
+    _PENDING_ADD under g1's address; pcm_layernorm_bwd adds the two while loading (one launch and one tensor pass fewer
+    per residual connection)."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, lazy=False):
+        ctx.lazy = bool(lazy)
         return x.view_as(x), x.view_as(x)
 
     @staticmethod
     def backward(ctx, g1, g2):
         if g1 is None:
-            return g2
+            return g2, None
         if g2 is None:
-            return g1
+            return g1, None
         g1, g2 = g1.contiguous(), g2.contiguous()
+        if ctx.lazy:
+            _PENDING_ADD[g1.data_ptr()] = g2
+            return g1, None
         out = torch.empty_like(g1)
         _call("pcm_add", g1.data_ptr(), g2.data_ptr(), out.data_ptr(), g1.numel(), _DT[g1.dtype], _s())
-        return out
+        return out, None
 
 
-def fork(x):
-    return ForkFn.apply(x) if x.requires_grad else (x, x)
+def fork(x, lazy=False):
+    """lazy=True only for the output of AddLayerNormFn (see ForkFn)."""
+    return ForkFn.apply(x, lazy) if x.requires_grad else (x, x)
 
 
 class Dropout2dFn(torch.autograd.Function):
@@ -451,15 +462,29 @@ class LinearFn(torch.autograd.Function):
     sample as a 1 x L image."""
 
     @staticmethod
-    def forward(ctx, x, w, b, relu):
+    def forward(ctx, x, w, b, relu, drop_p=0.0, seed=0):
+        """drop_p > 0: nn.Dropout(p) on the output as well (linear1 -> ReLU -> dropout of the transformer FFN) — in the
+        GEMM's store epilogue on the tensor-core path (pcm_conv1x1_drop_tc), by pcm_dropout otherwise; the same mask either
+        way.  The backward then needs only the saved output: dz = y > 0 ? dy / (1 - p) : 0."""
         x = x.contiguous()
         B, L, K = x.shape
         N = w.shape[0]
         dt = x.dtype
         wk = pack_weight(w, K, 1, 0, N, K, 1, dt)                               # [1][N][K]
-        y = conv_same(x, wk, B, 1, L, K, N, 1, bias=b, relu=relu).reshape(B, L, N)
-        ctx.save_for_backward(x, w, b, y if relu else None)
+        drop_p = float(drop_p)
+        if drop_p > 0.0 and relu and _tc_in_ok(dt, K) and N % 16 == 0 and N <= 256:
+            y = torch.empty((B, L, N), device=x.device, dtype=dt)
+            _call("pcm_conv1x1_drop_tc", x.data_ptr(), L * K, K, 1, L, K, y.data_ptr(), L * N, N, N, wk.data_ptr(), _p(b), B, 1,
+                  drop_p, int(seed), _s())
+        else:
+            y = conv_same(x, wk, B, 1, L, K, N, 1, bias=b, relu=relu).reshape(B, L, N)
+            if drop_p > 0.0:
+                yd = torch.empty_like(y)
+                _call("pcm_dropout", y.data_ptr(), yd.data_ptr(), y.numel(), drop_p, int(seed), _DT[dt], _s())
+                y = yd
+        ctx.save_for_backward(x, w, b, y if (relu or drop_p > 0.0) else None)
         ctx.relu = relu
+        ctx.drop = (drop_p, int(seed))
         return y
 
     @staticmethod
@@ -469,9 +494,19 @@ class LinearFn(torch.autograd.Function):
         N = w.shape[0]
         dt = x.dtype
         dy = dy.contiguous()
-        if ctx.relu:
+        drop_p, seed = ctx.drop
+        if ctx.relu and drop_p > 0.0:
+            dz = torch.empty_like(dy)
+            _call("pcm_relu_bwd_scaled", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), 1.0 / (1.0 - drop_p),
+                  _DT[dt], _s())
+            dy = dz
+        elif ctx.relu:
             dz = torch.empty_like(dy)
             _call("pcm_relu_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), _DT[dt], _s())
+            dy = dz
+        elif drop_p > 0.0:
+            dz = torch.empty_like(dy)
+            _call("pcm_dropout", dy.data_ptr(), dz.data_ptr(), dy.numel(), drop_p, seed, _DT[dt], _s())
             dy = dz
         gw, rw = _grad_buf(w)
         gb, rb = _grad_buf(b)
@@ -482,7 +517,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wkt = pack_weight(w, 1, K, 0, K, N, 1, dt)                          # [1][K][N] = W^T
             dx = conv_same(dy, wkt, B, 1, L, N, K, 1).reshape(B, L, K)
-        return dx, rw, rb, None
+        return dx, rw, rb, None, None, None
 
 
 class AddLayerNormFn(torch.autograd.Function):
@@ -515,7 +550,8 @@ class AddLayerNormFn(torch.autograd.Function):
         gb, rb = _grad_buf(beta)
         ds = torch.empty_like(s)
         db = torch.empty_like(s) if drop_p > 0.0 else ds
-        _call("pcm_layernorm_bwd", dy.data_ptr(), s.data_ptr(), stat.data_ptr(), gamma.data_ptr(), ds.data_ptr(),
+        dy2 = _PENDING_ADD.pop(dy.data_ptr(), None)         # second addend parked by a lazy ForkFn on this output
+        _call("pcm_layernorm_bwd2", dy.data_ptr(), _p(dy2), s.data_ptr(), stat.data_ptr(), gamma.data_ptr(), ds.data_ptr(),
               db.data_ptr(), gg.data_ptr(), gb.data_ptr(), M, E, drop_p, seed, _DT[s.dtype], _s())
         return ds, db, rg, rb, None, None
 

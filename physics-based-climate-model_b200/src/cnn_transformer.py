@@ -48,18 +48,21 @@ class CNNTransformer(nn.Module):
         if embed_dim % (8 * n_heads) != 0 or (embed_dim // 4) % 8 != 0:
             raise RuntimeError("pcm_b200 CNNTransformer needs embed_dim divisible by 8*n_heads and by 32")
 
-    def _layer(self, x, lyr):
+    def _layer(self, x, lyr, from_norm=False):
+        """from_norm: x is the output of the previous layer's norm2 — the residual fork then hands its two gradients to that
+        LayerNorm's backward kernel instead of adding them in a launch of its own (ops_nn.ForkFn lazy)."""
         tr, p = self.training, self.p_drop
         attn = lyr.self_attn
-        x, xr = ops_nn.fork(x)
+        x, xr = ops_nn.fork(x, lazy=from_norm)
         qkv = ops_nn.LinearFn.apply(x, attn.in_proj_weight, attn.in_proj_bias, False)
         a = ops_nn.MHAFn.apply(qkv, self.n_heads, float(p) if tr else 0.0, ops_nn.next_seed())
         a = ops_nn.LinearFn.apply(a, attn.out_proj.weight, attn.out_proj.bias, False)
         pd = float(p) if tr else 0.0            # sub-layer dropouts are fused into the residual-add + LayerNorm kernels
         x = ops_nn.AddLayerNormFn.apply(xr, a, lyr.norm1.weight, lyr.norm1.bias, pd, ops_nn.next_seed() if pd > 0 else 0)
-        x, xr = ops_nn.fork(x)
-        f = ops_nn.LinearFn.apply(x, lyr.linear1.weight, lyr.linear1.bias, True)
-        f = ops_nn.LinearFn.apply(ops_nn.dropout(f, p, tr), lyr.linear2.weight, lyr.linear2.bias, False)
+        x, xr = ops_nn.fork(x, lazy=True)                 # x = norm1's output
+        pf = float(p) if tr else 0.0            # linear1 -> ReLU -> dropout in one launch (GEMM store epilogue)
+        f = ops_nn.LinearFn.apply(x, lyr.linear1.weight, lyr.linear1.bias, True, pf, ops_nn.next_seed() if pf > 0 else 0)
+        f = ops_nn.LinearFn.apply(f, lyr.linear2.weight, lyr.linear2.bias, False)
         return ops_nn.AddLayerNormFn.apply(xr, f, lyr.norm2.weight, lyr.norm2.bias, pd, ops_nn.next_seed() if pd > 0 else 0)
 
     def forward_loss(self, x, target):
@@ -77,8 +80,8 @@ class CNNTransformer(nn.Module):
             raise RuntimeError(f"CNNTransformer: expected a {4 * self.height}x{4 * self.width} grid "
                                f"({self.num_tokens} tokens), got {Hh * Ww}")
         t = ops_nn.AddPosFn.apply(a.reshape(B, Hh * Ww, E), self.pos_embedding)
-        for lyr in self.transformer.layers:
-            t = self._layer(t, lyr)
+        for i, lyr in enumerate(self.transformer.layers):
+            t = self._layer(t, lyr, from_norm=i > 0)
         d = self.decoder
         y = t.reshape(B, Hh, Ww, E)
         y = ops_nn.ConvT2x2Fn.apply(y, d[0].weight, d[0].bias, True)

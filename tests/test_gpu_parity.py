@@ -173,6 +173,36 @@ def test_dropout_masks(G):
     assert r["whole_channels"] and abs(r["keep2d"] - 0.8) < 0.06, r
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_relu_dropout_fused_equals_three_steps(G, dtype):
+    """linear1 -> ReLU -> dropout of the transformer FFN in one Function (bf16: in the GEMM's store epilogue,
+    pcm_conv1x1_drop_tc): same mask as pcm_dropout with the same seed, same values up to one rounding, and a backward
+    that needs only the saved output (pcm_relu_bwd_scaled)."""
+    from pcm_b200 import ops_nn
+    g = torch.Generator().manual_seed(3)
+    B, L, K, N, p, seed = 3, 216, 128, 256, 0.3, 12345
+    x = torch.randn(B, L, K, generator=g).to(dtype).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    dy = torch.randn(B, L, N, generator=g).to(dtype).cuda()
+    outs = {}
+    for name in ("fused", "steps"):
+        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        if name == "fused":
+            y = ops_nn.LinearFn.apply(xr, wr, br, True, p, seed)
+        else:
+            y = ops_nn.DropoutFn.apply(ops_nn.LinearFn.apply(xr, wr, br, True), p, seed)
+        y.backward(dy)
+        outs[name] = [t.detach().float() for t in (y, xr.grad, wr.grad, br.grad)]
+    yf, ys = outs["fused"][0], outs["steps"][0]
+    assert torch.equal(yf == 0, ys == 0)                                   # same ReLU zeros and the same dropout mask
+    keep = float(((ys != 0).sum() / (torch.relu(x.float() @ w.t() + b) > 0).sum()).item())
+    assert abs(keep - (1 - p)) < 0.02, keep
+    tol = 1e-5 if dtype == torch.float32 else 8e-3                         # bf16: one rounding instead of two
+    for a, c in zip(outs["fused"], outs["steps"]):
+        assert float((a - c).norm() / c.norm()) < tol
+
+
 def test_metric_appendix_g(G):
     r = G.case_metric_appendix_g()            # fixture of _test_kaggle_metric.py:33-78, SURVEY Appendix G
     assert r["max_rel"] < 1e-5 and r["score_rel"] < 1e-5, r
