@@ -509,7 +509,14 @@ def run_ours(args):
 
     # ---- dominant kernel roofline: eager pass with per-call CUDA events on the launching stream -----------
     if rank == 0 and world == 1:
-        calls, agg = kernel_trace(step._step_impl, n_steps=2, dump=args.trace_file)
+        # one stream for this pass: a launch that shares the SMs with the side / communication stream's kernels is timed
+        # with their interference, and the roofline wants every kernel alone between its events
+        saved = (step.side, step.buckets, step.tail_bucket)
+        step.side, step.buckets, step.tail_bucket = None, [], None
+        try:
+            calls, agg = kernel_trace(step._step_impl, n_steps=2, dump=args.trace_file)
+        finally:
+            step.side, step.buckets, step.tail_bucket = saved
         tot = sum(v[0] for v in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1][0])
         line["kernel_breakdown_ms"] = {k: round(v[0], 4) for k, v in top[:12]}
@@ -528,8 +535,8 @@ def run_ours(args):
                             "algo_bytes_per_launch": g0["algo_bytes_per_launch"],
                             "algo_flops_per_launch": g0["algo_flops_per_launch"],
                             "peak_source": peak_src + ", burst figures (kernel timed alone between events)",
-                            "how": "dominant (kernel, shape) group of one eager step; CUDA events around each launch "
-                                   "on the launching stream with the host queued ahead of the device"}
+                            "how": "dominant (kernel, shape) group of one eager single-stream step; CUDA events around each "
+                                   "launch on the launching stream with the host queued ahead of the device"}
         line["roofline_top"] = [{k: r[k] for k in ("launch", "launches_per_step", "ms_per_step", "avg_us", "bound",
                                                    "achieved", "unit", "frac")} for r in groups[:10]]
         try:
