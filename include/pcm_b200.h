@@ -295,6 +295,17 @@ PCM_API int pcm_convblock_tail_bwd(const void* dout, const void* x, const void* 
                                    const float* maps, const unsigned char* ties, void* dx, float* dgamma,
                                    float* dbeta, float* dw1, float* dw2, float* dwsp, int N, int H, int W, int C,
                                    int Cr, float eps, int dtype, pcm_stream_t s);
+/* The same with the gate-weight gradient taken off the critical path: dq_out [N][H*W] fp32 (non-NULL) receives the gate's
+ * pre-activation gradient and dwsp is NOT touched; pcm_gate_wgrad(dq, maps, dwsp) then accumulates
+ * dwsp[k][dy][dx] += sum_n sum_p dq[n][p] * map_k[n][p + (dy-3, dx-3)] for all images (maps as saved by the forward tail:
+ * [N][3][H*W], mean | max | gate) — a parameter gradient, issued on a side stream by the caller. */
+PCM_API int pcm_convblock_tail_bwd_dq(const void* dout, const void* x, const void* out, const float* stats,
+                                      const float* gamma, const float* beta, const float* w1, const float* w2,
+                                      const float* wsp, const float* pool, const float* se, const float* hid,
+                                      const float* maps, const unsigned char* ties, void* dx, float* dgamma,
+                                      float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out, int N, int H,
+                                      int W, int C, int Cr, float eps, int dtype, pcm_stream_t s);
+PCM_API int pcm_gate_wgrad(const float* dq, const float* maps, float* dwsp, int N, int H, int W, pcm_stream_t s);
 
 /* ---- BatchNorm2d, training mode (src/models.py:48,51,57,91,109; eps 1e-5, momentum 0.1) on NHWC rows
  * (R = N*H*W rows of C channels; C = 8 * a divisor of 256).  sums[c] = (sum x, sum x^2) in DOUBLE (2*C doubles),

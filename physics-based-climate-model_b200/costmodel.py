@@ -77,6 +77,11 @@ def algo_cost(name: str, args):
         return 0.0, 2 * px * a["C"] * es() + (13 * px if a["maps"] else 0), "hbm"
     if name == "pcm_gn_silu_img_bwd":
         return 0.0, 3 * a["N"] * a["H"] * a["W"] * a["C"] * es(), "hbm"
+    if name == "pcm_gate_wgrad":
+        return 2.0 * 98 * a["N"] * a["H"] * a["W"], a["N"] * a["H"] * a["W"] * 12, "hbm"
+    if name == "pcm_convblock_tail_bwd_dq":
+        px = a["N"] * a["H"] * a["W"]
+        return 0.0, 4 * px * a["C"] * es() + 17 * px, "hbm"
     if name == "pcm_convblock_tail_bwd":
         px = a["N"] * a["H"] * a["W"]
         return 0.0, 4 * px * a["C"] * es() + 13 * px, "hbm"

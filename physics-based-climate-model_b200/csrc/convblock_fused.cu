@@ -1005,7 +1005,11 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
                           const float* __restrict__ se_g, const float* __restrict__ hid_g,
                           const float* __restrict__ maps, const uint8_t* __restrict__ ties, T* __restrict__ dx,
                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw1,
-                          float* __restrict__ dw2, float* __restrict__ dwsp, int H, int W, int C, int Cr, float eps) {
+                          float* __restrict__ dw2, float* __restrict__ dwsp, float* __restrict__ dq_out, int H, int W, int C,
+                          int Cr, float eps) {
+  // dq_out != NULL: the gate's pre-activation gradient dq [N][H*W] is also written to global memory and the gate-weight
+  // gradient (98 sums over the image: 11 % of this kernel's instructions on 14 of its 16 warps, 13 % of its samples) is
+  // left to pcm_gate_wgrad on the side stream — a parameter gradient nothing in the backward chain waits for.
   pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
@@ -1061,7 +1065,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     for (int r0 = 0; r0 < nround; r0 += kBatch) {
       Raw8<T> dr[kBatch], orw[kBatch];
       float gt[kBatch];
-      int ip[kBatch];
+      int ip[kBatch], pk[kBatch];
 #pragma unroll
       for (int k = 0; k < kBatch; ++k) {
         const bool valid = pw.p < P;
@@ -1070,6 +1074,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
         orw[k] = ld_raw<true>(outn + v * 8);
         gt[k] = (valid && cb == 0) ? __ldg(mp + 2 * P + pw.p) : 1.f;
         ip[k] = (valid && cb == 0) ? (pw.h + 3) * Wp + pw.w + 4 : -1;
+        pk[k] = pw.p;
         pw.next(W);
       }
 #pragma unroll
@@ -1080,14 +1085,18 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc = fmaf(d[j], o[j], acc);
         for (int off = 1; off < cv; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (ip[k] >= 0) s_dq[ip[k]] = acc * (1.f - gt[k]);
+        if (ip[k] >= 0) {
+          const float dqv = acc * (1.f - gt[k]);
+          s_dq[ip[k]] = dqv;
+          if (dq_out != nullptr) dq_out[(size_t)n * P + pk[k]] = dqv;
+        }
       }
     }
   }
   __syncthreads();
   // ---- dwsp[k][dy][dx] = sum_p dq[p] * cmap_k[p + (dy-3, dx-3)]: one warp per (k, dy), lanes over the 8-pixel runs,
   // 7 dx sums each, combined with shuffles (no atomics: every (k, dy, dx) has one owner)
-  {
+  if (dq_out == nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nrun = (W + 7) / 8;
     for (int combo = warp; combo < 14; combo += NT >> 5) {
       const int k = combo / 7, dy = combo - k * 7;
@@ -1137,7 +1146,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     }
   }
   __syncthreads();
-  if (threadIdx.x < 98) atomicAdd(dwsp + threadIdx.x, sp.dw[threadIdx.x]);
+  if (dq_out == nullptr && threadIdx.x < 98) atomicAdd(dwsp + threadIdx.x, sp.dw[threadIdx.x]);
 
   // per-thread channel coefficients (fixed channel block): xhat = xa*x + xb ; z = za*x + zb
   float xa[8], xb[8], za[8], zb[8], gm[8], sc[8];
@@ -1301,6 +1310,70 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
         for (int j = 0; j < 8; ++j) d[j] = fmaf(xa[j], d[j], fmaf(k2[j], t[j], k1[j]));
         store8(dxn + (size_t)v * 8, d);
       }
+    }
+  }
+}
+
+// Gate-weight gradient of SpatialGate's 7x7 conv (src/unet.py:24,28) for ALL images of a launch, off the critical path:
+//   dwsp[k][dy][dx] += sum_n sum_p dq[n][p] * map_k[n][p + (dy-3, dx-3)]      (k = channel mean / max map)
+// from the dq the backward tail wrote and the maps the forward tail saved.  One CTA walks images; the three planes of an
+// image sit zero-padded in shared memory; warp w owns kernel row dy = w for both maps (the 8-pixel run of dq a lane
+// loads serves 2 x 56 FMAs), accumulating in registers across its images; one shuffle reduction + 98 atomics per CTA.
+constexpr int kGwThreads = 224;        // 7 warps = 7 kernel rows
+
+__global__ void __launch_bounds__(kGwThreads)
+gate_wgrad_kernel(const float* __restrict__ dq, const float* __restrict__ maps, float* __restrict__ dwsp, int N, int H, int W) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int P = H * W, Wp = plane_wp(W), Pp = (H + 6) * Wp;
+  float* cm0 = reinterpret_cast<float*>(smem);
+  float* cm1 = cm0 + Pp;
+  float* s_dq = cm1 + Pp;
+  for (int i = threadIdx.x; i < 3 * Pp / 4; i += kGwThreads) reinterpret_cast<float4*>(cm0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();
+  const int dy = threadIdx.x >> 5, lane = threadIdx.x & 31, nrun = (W + 7) / 8;
+  float a0[7], a1[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) a0[i] = a1[i] = 0.f;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();                                           // zeros written / previous image consumed
+    const float* mp = maps + (size_t)n * 3 * P;
+    const float* dn = dq + (size_t)n * P;
+#pragma unroll 4
+    for (int p = threadIdx.x; p < P; p += kGwThreads) {
+      const int h = p / W, w = p - h * W, ip = (h + 3) * Wp + w + 4;
+      cm0[ip] = __ldg(mp + p);
+      cm1[ip] = __ldg(mp + P + p);
+      s_dq[ip] = __ldg(dn + p);
+    }
+    __syncthreads();
+    for (int item = lane; item < H * nrun; item += 32) {
+      const int h = item / nrun, w0 = (item - h * nrun) * 8;
+      const float4* dr = reinterpret_cast<const float4*>(s_dq + (h + 3) * Wp + w0 + 4);
+      const float4 d0 = dr[0], d1 = dr[1];
+      const float dq8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float4* cr = reinterpret_cast<const float4*>((k ? cm1 : cm0) + (h + dy) * Wp + w0);
+        const float4 c0 = cr[0], c1 = cr[1], c2 = cr[2], c3 = cr[3];
+        const float m[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+#pragma unroll
+        for (int dxx = 0; dxx < 7; ++dxx) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (k) a1[dxx] = fmaf(dq8[i], m[i + dxx + 1], a1[dxx]);
+            else a0[dxx] = fmaf(dq8[i], m[i + dxx + 1], a0[dxx]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int dxx = 0; dxx < 7; ++dxx) {
+    const float t0 = warp_sum(a0[dxx]), t1 = warp_sum(a1[dxx]);
+    if (lane == 0) {
+      atomicAdd(dwsp + dy * 7 + dxx, t0);
+      atomicAdd(dwsp + 49 + dy * 7 + dxx, t1);
     }
   }
 }
@@ -1529,12 +1602,40 @@ extern "C" int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* s
   return check_launch("gn_silu_img_bwd");
 }
 
+extern "C" int pcm_gate_wgrad(const float* dq, const float* maps, float* dwsp, int N, int H, int W, pcm_stream_t s) {
+  PCM_REQUIRE(dq != nullptr && maps != nullptr && dwsp != nullptr && H >= 1 && W >= 1, "gate_wgrad: bad arguments");
+  if (N == 0) return PCM_OK;
+  const size_t smem = (size_t)3 * (H + 6) * plane_wp(W) * sizeof(float);
+  PCM_REQUIRE(smem <= 227 * 1024, "gate_wgrad: planes do not fit shared memory (%zu B)", smem);
+  int rc = tail_set_smem(gate_wgrad_kernel, smem, "gate_wgrad");
+  if (rc != PCM_OK) return rc;
+  int grid = N < 148 * 4 ? N : 148 * 4;
+  pcm::launch(gate_wgrad_kernel, grid, kGwThreads, smem, (cudaStream_t)s, dq, maps, dwsp, N, H, W);
+  return check_launch("gate_wgrad");
+}
+
+extern "C" int pcm_convblock_tail_bwd_dq(const void* dout, const void* x, const void* out, const float* stats,
+                                         const float* gamma, const float* beta, const float* w1, const float* w2,
+                                         const float* wsp, const float* pool, const float* se, const float* hid,
+                                         const float* maps, const unsigned char* ties, void* dx, float* dgamma,
+                                         float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out, int N, int H,
+                                         int W, int C, int Cr, float eps, int dtype, pcm_stream_t s);
 extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const void* out, const float* stats,
                                       const float* gamma, const float* beta, const float* w1, const float* w2,
                                       const float* wsp, const float* pool, const float* se, const float* hid,
                                       const float* maps, const unsigned char* ties, void* dx, float* dgamma,
                                       float* dbeta, float* dw1, float* dw2, float* dwsp, int N, int H, int W, int C,
                                       int Cr, float eps, int dtype, pcm_stream_t s) {
+  return pcm_convblock_tail_bwd_dq(dout, x, out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties, dx, dgamma, dbeta,
+                                   dw1, dw2, dwsp, nullptr, N, H, W, C, Cr, eps, dtype, s);
+}
+
+extern "C" int pcm_convblock_tail_bwd_dq(const void* dout, const void* x, const void* out, const float* stats,
+                                         const float* gamma, const float* beta, const float* w1, const float* w2,
+                                         const float* wsp, const float* pool, const float* se, const float* hid,
+                                         const float* maps, const unsigned char* ties, void* dx, float* dgamma,
+                                         float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out, int N, int H,
+                                         int W, int C, int Cr, float eps, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(fused_shape_ok(H, W, C, Cr), "convblock_tail_bwd: unsupported shape H=%d W=%d C=%d Cr=%d", H, W, C, Cr);
   if (N == 0) return PCM_OK;
   const size_t smem = tail_smem_layout(H, W, C, dtype == PCM_BF16 ? 2 : 4, 1, 1).total;
@@ -1547,7 +1648,7 @@ extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const voi
     if (rc == PCM_OK)
       pcm::launch(convblock_tail_bwd_kernel<T>, N, tail_launch_threads(convblock_tail_bwd_kernel<T>, N, H, W, C, smem, 6.75f), smem, (cudaStream_t)s, 
           (const T*)dout, (const T*)x, (const T*)out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties,
-          (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, H, W, C, Cr, eps);
+          (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, dq_out, H, W, C, Cr, eps);
   });
   if (rc != PCM_OK) return rc;
   return check_launch("convblock_tail_bwd");

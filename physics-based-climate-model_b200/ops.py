@@ -407,6 +407,11 @@ def wgrad_tc_supported(dtype, Co: int, Ci: int, H: int, W: int) -> bool:
             and Ci in (16, 32, 64, 128, 192, 256) and H + 2 <= 256)
 
 
+import os as _os
+# opt-in (measured neutral: the stand-alone kernel costs the side stream more than the tail saves, profiles/r2_experiments.md)
+_GATE_WGRAD_SIDE = _os.environ.get("PCM_GATE_WGRAD_SIDE", "0") == "1"
+
+
 def wgrad_group(dtype, Co: int, Ci: int, W: int, dense: bool = True) -> int:
     """Pixel-group factor of the tensor-core weight gradient (pcm_wgrad3x3_tc_grouped) for the thin layers; 1 = plain.
     PCM_WGRAD_GROUP=0 disables, =2 caps the factor; PCM_WGRAD_GROUP_MAXC (default 32) = widest layer that is grouped."""
@@ -781,10 +786,21 @@ class ConvBlockFn(torch.autograd.Function):
         gw2, rw2 = _grad_buf(w2); gg2, rg2 = _grad_buf(g2); gb2, rb2 = _grad_buf(b2)
         gs1, rs1 = _grad_buf(sw1); gs2, rs2 = _grad_buf(sw2); gsp, rsp = _grad_buf(wsp)
         dy2 = torch.empty_like(y2)
-        _call("pcm_convblock_tail_bwd", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
-              b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(),
-              hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(),
-              gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
+        if _GATE_WGRAD_SIDE:
+            # the gate-weight gradient (98 sums per image, 11 % of the tail's instructions) leaves the critical path: the
+            # tail writes dq, pcm_gate_wgrad accumulates dwsp for all images on the side stream
+            dq = torch.empty(N * H * W, device=dout.device, dtype=torch.float32)
+            _call("pcm_convblock_tail_bwd_dq", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
+                  b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(),
+                  hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(),
+                  gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), dq.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
+            with side_stream(dq, maps):
+                _call("pcm_gate_wgrad", dq.data_ptr(), maps.data_ptr(), gsp.data_ptr(), N, H, W, _s())
+        else:
+            _call("pcm_convblock_tail_bwd", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
+                  b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(),
+                  hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(),
+                  gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
         with side_stream(dy2, a1):
             conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
         gb = conv_group(dt, Co, Co, W)
