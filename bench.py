@@ -387,7 +387,8 @@ def run_ours(args):
 
     # ---- device-resident throughput: `windows` timed regions of K steps each, median reported -----------------------
     sampler = ClockSampler(local)       # started before the warm-up steps (nvidia-smi needs ~100 ms to deliver its first
-    sampler.start()                     # sample); it keeps sampling through the timed regions
+    if rank == 0:                       # sample); it keeps sampling through the timed regions.  Rank 0 only: eight pollers
+        sampler.start()                 # taking the driver's lock every 100 ms showed up as slow windows at 8 GPUs
     # W untimed warm-up steps (at least 10 under NCCL: the first replays of a graph holding collectives are slow)
     for i in range(max(args.warmup, 10) if world > 1 else args.warmup):
         step.step(xs_d[i % n_rot], ys_d[i % n_rot])
