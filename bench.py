@@ -489,7 +489,9 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": e2e_ms_total / K,
                     "h2d_bytes_per_step": (xs_h[0].numel() + ys_h[0].numel()) * 4, "d2h_bytes_per_step": 4,
                     "how": "TrainStep.step_prefetch: H2D of the next batch (pinned host memory) on a copy stream overlaps the "
-                           "step; loss read back and stream synchronised every step; median of 3 windows",
+                           "step and lands in the alternate pair of static buffers (two captured graphs, one per pair: "
+                           "no device-to-device move); loss read back and stream synchronised every step; median of 3 "
+                           "windows",
                     "serial_value": world * B * K / (e2e_serial_ms_total / 1e3),
                     "serial_ms_per_step": e2e_serial_ms_total / K},
             "gpu_launches": step.launches_per_step * K * len(win_ms),

@@ -21,18 +21,20 @@ int check_launch(const char* what);
     }                                           \
   } while (0)
 
-// ---- programmatic dependent launch (opt-in: PCM_PDL=1) ------------------------------------------------------
+// ---- programmatic dependent launch (default on; PCM_PDL=0 off) ------------------------------------------------------
 // Every kernel of the library goes through pcm::launch and follows the dependent-launch protocol: it executes
 // `griddepcontrol.wait` (PCM_PDL_ENTRY / pdl_wait) before it touches global memory and before any thread exits, so that
-// "this grid completed" always implies "its predecessors completed".  With PCM_PDL=1 the launches carry the
+// "this grid completed" always implies "its predecessors completed".  Unless PCM_PDL=0 the launches carry the
 // programmatic-stream-serialization attribute (the edges of the captured CUDA graph become programmatic) and the next
 // kernel of the stream may begin launching before this one has drained.
-// Measured on B200 (flagship step, 120 dependent launches of 10-150 us, CUDA graph replay, 60 steps each):
-//   classic launches 2.11-2.16 ms | attribute, trigger at grid completion 2.11 ms | attribute + early trigger
-//   (`griddepcontrol.launch_dependents` at kernel entry, PCM_PDL_EARLY=1) 2.31 ms.
-// i.e. neutral at best and clearly worse with early triggers (dependents parked in griddepcontrol.wait are released
-// later than a fresh launch would start), so the default is the classic launch; the protocol stays in the kernels
-// (a no-op without the attribute) and tests/test_cpu_boundary.py checks every kernel follows it.
+// Measured on B200 (flagship step, CUDA graph replay):
+//   round 1 (120 dependent launches, one priority level): classic launches 2.11-2.16 ms | attribute, trigger at grid
+//   completion 2.11 ms | attribute + early trigger (`griddepcontrol.launch_dependents` at kernel entry, PCM_PDL_EARLY=1)
+//   2.31 ms — dependents parked in griddepcontrol.wait are released later than a fresh launch would start;
+//   round 2 (108 launches, critical chain on a high-priority stream): classic 1.666 ms | attribute 1.621 ms (-2.7 %: the
+//   ~85 kernels of the chain each start ~0.5 us earlier) — so the attribute is now the DEFAULT (PCM_PDL=0 turns it off),
+//   the early trigger stays off.  tests/test_cpu_boundary.py checks that every kernel follows the protocol (no global
+//   memory access before griddepcontrol.wait, no launch that bypasses pcm::launch).
 #ifndef PCM_PDL_EARLY
 #define PCM_PDL_EARLY 0          // 1: kernels also issue griddepcontrol.launch_dependents at entry
 #endif

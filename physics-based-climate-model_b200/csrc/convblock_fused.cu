@@ -14,6 +14,7 @@
 // The multi-kernel path in convblock.cu (grid-wide passes, 6 forward + 8 backward launches per block) remains for
 // images that do not fit (config 5, fp32 at full size) — see pcm_convblock_fused_supported.
 #include "tc_common.cuh"
+#include "f32x2.cuh"
 
 namespace pcm {
 
@@ -21,6 +22,7 @@ constexpr int kFT = 512;       // max threads per CTA (one CTA per image); small
                                // several CTAs share an SM and their latency-bound phases overlap
 #define NT ((int)blockDim.x)
 constexpr int kGroups = 8;     // nn.GroupNorm(8, c)
+constexpr int kDwFloats = 200; // gate-weight gradient staging: two halves of the image x 98 sums (+ pad)
 
 template <typename T> __device__ __forceinline__ float sigmoid_t(float z);
 template <> __device__ __forceinline__ float sigmoid_t<float>(float z) { return sigmoidf_(z); }
@@ -44,6 +46,21 @@ __device__ __forceinline__ void chan_put(float (&v)[8], float* part, int slot, i
     float4* d = reinterpret_cast<float4*>(part + ((size_t)slot * (NT >> 5) + (threadIdx.x >> 5)) * C + cb * 8);
     d[0] = make_float4(v[0], v[1], v[2], v[3]);
     d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+// the same for eight partials held as four fp32 pairs
+__device__ __forceinline__ void chan_put(float2 (&v)[4], float* part, int slot, int cb, int cv, int C) {
+  for (int off = cv; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j].x += __shfl_xor_sync(0xffffffffu, v[j].x, off);
+      v[j].y += __shfl_xor_sync(0xffffffffu, v[j].y, off);
+    }
+  }
+  if ((int)(threadIdx.x & 31) < cv) {
+    float4* d = reinterpret_cast<float4*>(part + ((size_t)slot * (NT >> 5) + (threadIdx.x >> 5)) * C + cb * 8);
+    d[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    d[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
   }
 }
 __device__ __forceinline__ void chan_finish(const float* part, int nslots, float* dst, int C) {
@@ -102,13 +119,39 @@ __device__ __forceinline__ void unpack8(const Raw8<float>& r, float d[8]) {
 }
 template <typename T> constexpr int raw_batch() { return sizeof(T) == 2 ? 4 : 2; }   // vectors in flight per operand
 
+// ---- the same vectors as four fp32 PAIRS (f32x2.cuh): the element-wise passes below run on pairs of channels
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float2 (&d)[4]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] = __bfloat1622float2(h[i]);
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float2 (&d)[4]) {
+  d[0] = make_float2(r.a.x, r.a.y); d[1] = make_float2(r.a.z, r.a.w);
+  d[2] = make_float2(r.b.x, r.b.y); d[3] = make_float2(r.b.z, r.b.w);
+}
+template <typename T>
+__device__ __forceinline__ void load8_rw(const T* p, float2 (&d)[4]) {      // generic-address load (shared / own global writes)
+  unpack8(ld_raw<false>(p), d);
+}
+__device__ __forceinline__ void store8(float* p, const float2 (&v)[4]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float2 (&v)[4]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[i].x, v[i].y);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
 // Gate maps (channel mean / max, dq) live in zero-padded planes: pixel (h, w) at (h + 3) * Wp + (w + 4), with
 // Wp = roundup8(W) + 8, so that the 16 floats [w0, w0 + 16) a run of 8 pixels needs from one row are four aligned
 // 16-byte shared-memory loads.
 __host__ __device__ inline int plane_wp(int W) { return ((W + 7) / 8) * 8 + 8; }
 
 struct TailSmem {
-  size_t img, cm0, cm1, dq, gate, dm, bar, part, fl, total;
+  size_t img, cm0, cm1, dq, gate, dm, scr, bar, part, fl, total;
 };
 // threads per CTA: enough vectors per thread to amortise the phase barriers, few enough that small images get
 // several CTAs per SM (the kernels are register-limited to 512 threads per SM)
@@ -117,7 +160,10 @@ __host__ __device__ inline int tail_threads(int H, int W, int C) {
   return nvec >= 4096 ? 512 : nvec >= 1536 ? 256 : 128;
 }
 // bwd: 0 = forward tails, 1 = backward tails (needs dq / dm / cnt as well)
-__host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int elt, int full, int bwd) {
+// scr (backward tails only): room for a second image-sized array — the scratch (dxhat) that GroupNorm pass 1 hands to
+// pass 2 then stays in shared memory instead of making a round trip through global memory.  It OVERLAYS the gate planes
+// (all dead once pass B is done) and only the excess over them is extra shared memory.
+__host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int elt, int full, int bwd, int scr = 0) {
   TailSmem L;
   const size_t P = (size_t)H * W, Pp = (size_t)(H + 6) * plane_wp(W);
   size_t off = 0;
@@ -128,12 +174,18 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
   L.dq = (full && bwd) ? PCM_TAKE(Pp * 4) : 0;
   L.gate = full ? PCM_TAKE(P * 4) : 0;
   L.dm = (full && bwd) ? PCM_TAKE(P * 8) : 0;
+  L.scr = 0;
+  if (scr && bwd) {
+    L.scr = full ? L.cm0 : off;
+    const size_t end = L.scr + ((P * C * elt + 15) & ~(size_t)15);
+    if (end > off) off = end;
+  }
   L.bar = PCM_TAKE(64);                                  // mbarriers of the bulk copies that bring the image in (one per 32 KB piece)
   L.part = PCM_TAKE((size_t)2 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 2 slots x warps x C floats (launches never
                                                                           // use more threads than tail_threads)
   // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
-  //         | wt[2][7][8] | wtf[2][7][8] | dw[100] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
-  L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + (full ? C * C / 4 : 0)) * 4);
+  //         | wt[2][7][8] | wtf[7][8][2] | dw[2][98 + 2] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
+  L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + kDwFloats + (full ? C * C / 4 : 0)) * 4);
 #undef PCM_TAKE
   L.total = off;
   return L;
@@ -154,16 +206,68 @@ __device__ __forceinline__ TailPtrs tail_ptrs(uint8_t* smem, const TailSmem& L, 
   p.hid = g; p.dpre1 = g + 64;
   p.mu = g + 128; p.rs = g + 136; p.m1 = g + 144; p.m2 = g + 152;
   p.wt = g + 160; p.wtf = g + 272; p.dw = g + 384;
-  p.sw1 = g + 484; p.sw2 = p.sw1 + C * C / 8;
+  p.sw1 = g + 384 + kDwFloats; p.sw2 = p.sw1 + C * C / 8;
   return p;
 }
 
-// 7x7 gate weights (2, 7, 7) -> wt[k][dy][8] (dx padded to 8) and the flipped copy wtf[k][dy][dx] = w[k][6-dy][6-dx]
+// 7x7 gate weights (2, 7, 7):
+//   wt[k][dy][8]      (dx padded to 8) for the forward gate conv over the two scalar planes (stencil_run8);
+//   wtf[dy][8][2]     the flipped kernel as PAIRS over the two maps, wtf[dy][dx] = (w[0][6-dy][6-dx], w[1][6-dy][6-dx]),
+//                     for the backward tail: the transposed stencil then produces (dmean, dmax) with one packed FMA
+//                     (f32x2.cuh) per tap from a broadcast dq, and the weight gradient accumulates (dw[0], dw[1]) the
+//                     same way from an interleaved (mean, max) plane — half the FMA instructions of the scalar form.
 __device__ __forceinline__ void load_gate_weights(const float* __restrict__ wsp, const TailPtrs& sp) {
   for (int i = threadIdx.x; i < 112; i += NT) {
-    const int k = i / 56, dy = (i % 56) / 8, dx = i % 8;
-    sp.wt[i] = dx < 7 ? __ldg(wsp + k * 49 + dy * 7 + dx) : 0.f;
-    sp.wtf[i] = dx < 7 ? __ldg(wsp + k * 49 + (6 - dy) * 7 + (6 - dx)) : 0.f;
+    {
+      const int k = i / 56, dy = (i % 56) / 8, dx = i % 8;
+      sp.wt[i] = dx < 7 ? __ldg(wsp + k * 49 + dy * 7 + dx) : 0.f;
+    }
+    {
+      const int k = i & 1, e = i >> 1, dy = e >> 3, dx = e & 7;
+      sp.wtf[i] = dx < 7 ? __ldg(wsp + k * 49 + (6 - dy) * 7 + (6 - dx)) : 0.f;
+    }
+  }
+}
+
+// one row of 16 consecutive pixels of the interleaved plane (8 aligned 16-byte loads) as 16 pairs
+__device__ __forceinline__ void load_pair_row16(const float2* row, float2 (&m)[16]) {
+  const float4* r = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 v = r[j];
+    m[2 * j] = make_float2(v.x, v.y);
+    m[2 * j + 1] = make_float2(v.z, v.w);
+  }
+}
+__device__ __forceinline__ void load_row16(const float* row, float (&m)[16]) {
+  const float4* r = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 v = r[j];
+    m[4 * j] = v.x; m[4 * j + 1] = v.y; m[4 * j + 2] = v.z; m[4 * j + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void load_weight_row(const float* wrow, float2 (&w)[7]) {   // wt / wtf + dy * 16
+  const float4* r = reinterpret_cast<const float4*>(wrow);
+  const float4 a = r[0], b = r[1], c = r[2], d = r[3];
+  w[0] = make_float2(a.x, a.y); w[1] = make_float2(a.z, a.w); w[2] = make_float2(b.x, b.y); w[3] = make_float2(b.z, b.w);
+  w[4] = make_float2(c.x, c.y); w[5] = make_float2(c.z, c.w); w[6] = make_float2(d.x, d.y);
+}
+
+// Transposed gate conv: q[i] += (sum_taps wf[0] * dq(..), sum_taps wf[1] * dq(..)) from the scalar dq plane
+// (row0 = plane + h * Wp + w0, 32-byte aligned): 4 + 4 vector loads feed 56 packed FMAs with a broadcast operand.
+__device__ __forceinline__ void stencil_dq_run8(const float* row0, int Wp, const float* wtf, float2 (&q)[8]) {
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy) {
+    float m[16];
+    float2 w[7];
+    load_row16(row0 + dy * Wp, m);
+    load_weight_row(wtf + dy * 16, w);
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fma2(w[dx], bc2(m[i + dx + 1]), q[i]);
+    }
   }
 }
 
@@ -239,6 +343,48 @@ template <typename T>
 __device__ __forceinline__ float silu_raw(float x, float za, float zb) {
   const float z = fmaf(za, x, zb);
   return z * sigmoid_t<T>(z);
+}
+
+// ---- the same on fp32 pairs: per lane exactly the operations of sigmoid_t / silu_raw / the rounding helpers above
+template <typename T> __device__ __forceinline__ float2 sigmoid2(float2 z);
+template <> __device__ __forceinline__ float2 sigmoid2<float>(float2 z) { return make_float2(sigmoidf_(z.x), sigmoidf_(z.y)); }
+template <> __device__ __forceinline__ float2 sigmoid2<__nv_bfloat16>(float2 z) {
+  const float2 h = mul2(z, bc2(0.5f));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+  return fma2(bc2(0.5f), t, bc2(0.5f));
+}
+// t <- silu(za*t + zb), unrounded
+template <typename T>
+__device__ __forceinline__ void silu8(float2 (&t)[4], const float2 (&za)[4], const float2 (&zb)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 z = fma2(za[i], t[i], zb[i]);
+    t[i] = mul2(z, sigmoid2<T>(z));
+  }
+}
+template <typename T> __device__ __forceinline__ void round8_to(float2 (&a)[4]);
+template <> __device__ __forceinline__ void round8_to<float>(float2 (&)[4]) {}
+template <> __device__ __forceinline__ void round8_to<__nv_bfloat16>(float2 (&a)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = __bfloat1622float2(__floats2bfloat162_rn(a[i].x, a[i].y));
+}
+__device__ __forceinline__ void store8_rounded(float* p, float2 (&a)[4]) { store8(p, a); }
+__device__ __forceinline__ void store8_rounded(__nv_bfloat16* p, float2 (&a)[4]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2bfloat162_rn(a[i].x, a[i].y);
+    a[i] = __bfloat1622float2(h[i]);
+  }
+  *reinterpret_cast<uint4*>(p) = u;
+}
+// the eight per-channel values of channel block cb of a shared-memory array as four pairs
+__device__ __forceinline__ void load_chan8(const float* a, int cb, float2 (&d)[4]) {
+  const float4 lo = reinterpret_cast<const float4*>(a + cb * 8)[0], hi = reinterpret_cast<const float4*>(a + cb * 8)[1];
+  d[0] = make_float2(lo.x, lo.y); d[1] = make_float2(lo.z, lo.w); d[2] = make_float2(hi.x, hi.y); d[3] = make_float2(hi.z, hi.w);
 }
 
 // ---- the image comes in through the bulk-copy engine in 32 KB pieces, one mbarrier per piece (one thread issues;
@@ -636,7 +782,7 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
   uint64_t* xfull = bars + 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
   TailSmem L;
-  L.img = 0; L.cm0 = p.off_cm0; L.cm1 = p.off_cm1; L.dq = 0; L.gate = p.off_gate; L.dm = 0; L.bar = p.off_bar;
+  L.img = 0; L.cm0 = p.off_cm0; L.cm1 = p.off_cm1; L.dq = 0; L.gate = p.off_gate; L.dm = 0; L.scr = 0; L.bar = p.off_bar;
   L.part = p.off_part; L.fl = p.off_fl; L.total = 0;
   const TailPtrs sp = tail_ptrs(smem, L, p.C);
 
@@ -877,6 +1023,52 @@ convblock_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bflo
   }
 }
 
+// Per-thread channel coefficients of a GroupNorm + SiLU backward (fixed channel block cb), as pairs:
+//   xhat = xa*x + xb ;  z = za*x + zb  (za, zb exactly as the forward kernel derives them: gn_coef)
+struct GnCoef {
+  float2 xa[4], xb[4], za[4], zb[4], gm[4];
+};
+__device__ __forceinline__ void gn_coef_load(GnCoef& k, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             const TailPtrs& sp, int cb, int cg) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb * 8 + j, g = c / cg;
+    const float gmj = __ldg(gamma + c), xaj = sp.rs[g], xbj = -sp.mu[g] * sp.rs[g];
+    float zaj, zbj;
+    gn_coef(gmj, __ldg(beta + c), sp.mu[g], sp.rs[g], zaj, zbj);
+    if (j & 1) { k.gm[j >> 1].y = gmj; k.xa[j >> 1].y = xaj; k.xb[j >> 1].y = xbj; k.za[j >> 1].y = zaj; k.zb[j >> 1].y = zbj; }
+    else { k.gm[j >> 1].x = gmj; k.xa[j >> 1].x = xaj; k.xb[j >> 1].x = xbj; k.za[j >> 1].x = zaj; k.zb[j >> 1].x = zbj; }
+  }
+}
+// pass 2: dx = rs*(dxh - m1 - xh*m2) = xa*dxh + k2*x + k1 with k1 = -(rs*m1 + rs*m2*xb), k2 = -rs*m2*xa
+__device__ __forceinline__ void gn_bwd_pass2_coef(const GnCoef& k, const TailPtrs& sp, int cb, int cg, float2 (&k1)[4],
+                                                  float2 (&k2)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int g0 = (cb * 8 + 2 * j) / cg, g1 = (cb * 8 + 2 * j + 1) / cg;
+    k1[j].x = -k.xa[j].x * (sp.m1[g0] + sp.m2[g0] * k.xb[j].x);
+    k1[j].y = -k.xa[j].y * (sp.m1[g1] + sp.m2[g1] * k.xb[j].y);
+    k2[j].x = -k.xa[j].x * sp.m2[g0] * k.xa[j].x;
+    k2[j].y = -k.xa[j].y * sp.m2[g1] * k.xa[j].y;
+  }
+}
+// one vector of pass 1: d (gradient reaching a) -> d = gamma * dz (dxhat), r0 += dz*xhat, r1 += dz
+template <typename T>
+__device__ __forceinline__ void gn_silu_bwd_vec(float2 (&d)[4], const float2 (&t)[4], const GnCoef& k, float2 (&r0)[4],
+                                                float2 (&r1)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 xh = fma2(k.xa[i], t[i], k.xb[i]);
+    const float2 z = fma2(k.za[i], t[i], k.zb[i]);
+    const float2 sg = sigmoid2<T>(z);
+    const float2 om = fma2(sg, bc2(-1.f), bc2(1.f));                       // 1 - sg
+    const float2 dz = mul2(mul2(d[i], sg), fma2(z, om, bc2(1.f)));         // d * sg * (1 + z*(1 - sg))
+    r0[i] = fma2(dz, xh, r0[i]);
+    r1[i] = add2(r1[i], dz);
+    d[i] = mul2(dz, k.gm[i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // backward of tail 1: da (gradient w.r.t. a = silu(GN(x))) -> dx ; dgamma, dbeta accumulate
 // ---------------------------------------------------------------------------------------------------------------
@@ -884,58 +1076,45 @@ template <typename T>
 __global__ void __launch_bounds__(kFT, 1)
 gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const float* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ dx,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta, int H, int W, int C, float eps) {
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, int H, int W, int C, float eps, int scr) {
   pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv;
-  const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), 0, 1);
+  const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), 0, 1, scr);
   T* s_img = reinterpret_cast<T*>(smem + L.img);
   const TailPtrs sp = tail_ptrs(smem, L, C);
   const T* xn = x + (size_t)n * P * C;
   const T* dan = da + (size_t)n * P * C;
   T* dxn = dx + (size_t)n * P * C;
+  T* sxn = scr ? reinterpret_cast<T*>(smem + L.scr) : dxn;     // pass 1 -> pass 2 scratch: shared memory when it fits
   const int cb = threadIdx.x & (cv - 1);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
   pdl_wait();                                                  // global memory from here on
   if (threadIdx.x == 0) image_copy_start(bar, s_img, xn, (uint32_t)((size_t)P * C * sizeof(T)));
   group_mu_rs_from_stats(stats + (size_t)n * kGroups * 2, cg, P, eps, sp);
   __syncthreads();
-  // xhat = xa*x + xb ; z = za*x + zb
-  float xa[8], xb[8], za[8], zb[8], gm[8], r0[8], r1[8];
+  GnCoef k;
+  gn_coef_load(k, gamma, beta, sp, cb, cg);
+  float2 r0[4], r1[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cb * 8 + j, g = c / cg;
-    gm[j] = __ldg(gamma + c);
-    xa[j] = sp.rs[g]; xb[j] = -sp.mu[g] * sp.rs[g];
-    za[j] = gm[j] * xa[j]; zb[j] = fmaf(gm[j], xb[j], __ldg(beta + c));
-    r0[j] = r1[j] = 0.f;
-  }
+  for (int j = 0; j < 4; ++j) r0[j] = r1[j] = make_float2(0.f, 0.f);
   // pass 1: dxhat (stored to dx as scratch) and the reductions; x is consumed as its pieces land
   constexpr int KB = raw_batch<T>();
   PieceWalk land(bar);
   for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
     Raw8<T> raw[KB];
 #pragma unroll
-    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<true>(dan + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+    for (int kk = 0; kk < KB; ++kk) raw[kk] = ld_raw<true>(dan + (size_t)min(v0 + kk * NT, nvec - 1) * 8);
     land.need((uint32_t)min(v0 + (KB - 1) * NT + 1, nvec) * 8u * (uint32_t)sizeof(T));
 #pragma unroll
-    for (int k = 0; k < KB; ++k) {
-      const int v = v0 + k * NT;
+    for (int kk = 0; kk < KB; ++kk) {
+      const int v = v0 + kk * NT;
       if (v < nvec) {
-        float t[8], d[8];
+        float2 t[4], d[4];
         load8_rw(s_img + (size_t)v * 8, t);
-        unpack8(raw[k], d);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = fmaf(xa[j], t[j], xb[j]);
-          const float z = fmaf(za[j], t[j], zb[j]);
-          const float sg = sigmoid_t<T>(z);
-          const float dz = d[j] * sg * fmaf(z, 1.f - sg, 1.f);
-          r0[j] = fmaf(dz, xh, r0[j]);
-          r1[j] += dz;
-          d[j] = dz * gm[j];
-        }
-        store8(dxn + (size_t)v * 8, d);
+        unpack8(raw[kk], d);
+        gn_silu_bwd_vec<T>(d, t, k, r0, r1);
+        store8(sxn + (size_t)v * 8, d);
       }
     }
   }
@@ -946,10 +1125,10 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
     // group means of dxhat = gamma*dz and of dxhat*xhat, from the per-channel sums of dz and dz*xhat
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < cg; ++k) {
-      const float gmc = __ldg(gamma + g * cg + k);
-      a = fmaf(gmc, sp.ch1[g * cg + k], a);
-      b = fmaf(gmc, sp.ch0[g * cg + k], b);
+    for (int kk = 0; kk < cg; ++kk) {
+      const float gmc = __ldg(gamma + g * cg + kk);
+      a = fmaf(gmc, sp.ch1[g * cg + kk], a);
+      b = fmaf(gmc, sp.ch0[g * cg + kk], b);
     }
     const float cnt = (float)cg * (float)P;
     sp.m1[g] = a / cnt;
@@ -961,28 +1140,22 @@ gn_silu_img_bwd_kernel(const T* __restrict__ da, const T* __restrict__ x, const 
   }
   __syncthreads();
   // dx = rs*(dxh - m1 - xh*m2) = rs*dxh - (rs*m1 + rs*m2*xb) - (rs*m2*xa)*x
-  float k0[8], k1[8], k2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (cb * 8 + j) / cg;
-    k0[j] = xa[j];
-    k1[j] = -xa[j] * (sp.m1[g] + sp.m2[g] * xb[j]);
-    k2[j] = -xa[j] * sp.m2[g] * xa[j];
-  }
+  float2 k1[4], k2[4];
+  gn_bwd_pass2_coef(k, sp, cb, cg, k1, k2);
   // pass 2: every thread re-reads exactly the vectors it wrote in pass 1
   for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
     Raw8<T> raw[KB];
 #pragma unroll
-    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<false>(dxn + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+    for (int kk = 0; kk < KB; ++kk) raw[kk] = ld_raw<false>(sxn + (size_t)min(v0 + kk * NT, nvec - 1) * 8);
 #pragma unroll
-    for (int k = 0; k < KB; ++k) {
-      const int v = v0 + k * NT;
+    for (int kk = 0; kk < KB; ++kk) {
+      const int v = v0 + kk * NT;
       if (v < nvec) {
-        float t[8], d[8];
+        float2 t[4], d[4];
         load8_rw(s_img + (size_t)v * 8, t);
-        unpack8(raw[k], d);
+        unpack8(raw[kk], d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = fmaf(k0[j], d[j], fmaf(k2[j], t[j], k1[j]));
+        for (int j = 0; j < 4; ++j) d[j] = fma2(k.xa[j], d[j], fma2(k2[j], t[j], k1[j]));
         store8(dxn + (size_t)v * 8, d);
       }
     }
@@ -1006,7 +1179,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
                           const float* __restrict__ maps, const uint8_t* __restrict__ ties, T* __restrict__ dx,
                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw1,
                           float* __restrict__ dw2, float* __restrict__ dwsp, float* __restrict__ dq_out, int H, int W, int C,
-                          int Cr, float eps) {
+                          int Cr, float eps, int scr) {
   // dq_out != NULL: the gate's pre-activation gradient dq [N][H*W] is also written to global memory and the gate-weight
   // gradient (98 sums over the image: 11 % of this kernel's instructions on 14 of its 16 warps, 13 % of its samples) is
   // left to pcm_gate_wgrad on the side stream — a parameter gradient nothing in the backward chain waits for.
@@ -1015,10 +1188,9 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   const int n = blockIdx.x, P = H * W, cv = C / 8, cg = C / kGroups, nvec = P * cv, Wp = plane_wp(W);
   const int cvs = __ffs(cv) - 1;
   const int nround = (nvec + NT - 1) / NT;
-  const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), 1, 1);
+  const TailSmem L = tail_smem_layout(H, W, C, (int)sizeof(T), 1, 1, scr);
   T* s_img = reinterpret_cast<T*>(smem + L.img);
-  float* cm0 = reinterpret_cast<float*>(smem + L.cm0);
-  float* cm1 = reinterpret_cast<float*>(smem + L.cm1);
+  float2* cm = reinterpret_cast<float2*>(smem + L.cm0);          // (mean, max) pairs: the cm0 | cm1 regions as one plane
   float* s_dq = reinterpret_cast<float*>(smem + L.dq);
   float* s_gate = reinterpret_cast<float*>(smem + L.gate);
   float2* s_dm = reinterpret_cast<float2*>(smem + L.dm);
@@ -1034,7 +1206,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   const float invP = 1.f / (float)P;
 
   {
-    float4* z4 = reinterpret_cast<float4*>(cm0);                                // cm0 | cm1 | dq are contiguous
+    float4* z4 = reinterpret_cast<float4*>(cm);                                 // cm0 | cm1 | dq are contiguous
     for (int i = threadIdx.x; i < 3 * (H + 6) * Wp / 4; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   pdl_wait();                                                                   // global memory from here on
@@ -1056,8 +1228,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
 #pragma unroll 4
     for (int p = threadIdx.x; p < P; p += NT) {
       const int h = p / W, w = p - h * W, ip = (h + 3) * Wp + w + 4;
-      cm0[ip] = __ldg(mp + p);
-      cm1[ip] = __ldg(mp + P + p);
+      cm[ip] = make_float2(__ldg(mp + p), __ldg(mp + P + p));
       s_gate[p] = __ldg(mp + 2 * P + p);
     }
     constexpr int kBatch = 2 * raw_batch<T>();
@@ -1079,11 +1250,13 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       }
 #pragma unroll
       for (int k = 0; k < kBatch; ++k) {
-        float acc = 0.f, d[8], o[8];
+        float2 d[4], o[4];
         unpack8(dr[k], d);
         unpack8(orw[k], o);
+        float2 a2 = mul2(d[0], o[0]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(d[j], o[j], acc);
+        for (int j = 1; j < 4; ++j) a2 = fma2(d[j], o[j], a2);
+        float acc = a2.x + a2.y;
         for (int off = 1; off < cv; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (ip[k] >= 0) {
           const float dqv = acc * (1.f - gt[k]);
@@ -1094,34 +1267,38 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     }
   }
   __syncthreads();
-  // ---- dwsp[k][dy][dx] = sum_p dq[p] * cmap_k[p + (dy-3, dx-3)]: one warp per (k, dy), lanes over the 8-pixel runs,
-  // 7 dx sums each, combined with shuffles (no atomics: every (k, dy, dx) has one owner)
+  // ---- dwsp[k][dy][dx] = sum_p dq[p] * cmap_k[p + (dy-3, dx-3)]: one warp per (kernel row dy, half of the 8-pixel
+  // runs), lanes over the runs; the 7 dx sums of BOTH maps accumulate as pairs (broadcast dq x (mean, max)), combined
+  // with shuffles (no atomics: every (half, k, dy, dx) has one owner; the two halves are added when dwsp is updated)
   if (dq_out == nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nrun = (W + 7) / 8;
+    const int nitem = H * nrun, ihalf = (nitem + 1) >> 1;
     for (int combo = warp; combo < 14; combo += NT >> 5) {
-      const int k = combo / 7, dy = combo - k * 7;
-      const float* pl = k ? cm1 : cm0;
-      float a[7];
+      const int half = combo / 7, dy = combo - half * 7;
+      const int i0 = half ? ihalf : 0, i1 = half ? nitem : ihalf;
+      float2 a[7];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) a[i] = 0.f;
-      for (int item = lane; item < H * nrun; item += 32) {
+      for (int i = 0; i < 7; ++i) a[i] = make_float2(0.f, 0.f);
+      for (int item = i0 + lane; item < i1; item += 32) {
         const int h = item / nrun, w0 = (item - h * nrun) * 8;
         const float4* dr = reinterpret_cast<const float4*>(s_dq + (h + 3) * Wp + w0 + 4);
         const float4 d0 = dr[0], d1 = dr[1];
         const float dq8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const float4* cr = reinterpret_cast<const float4*>(pl + (h + dy) * Wp + w0);
-        const float4 c0 = cr[0], c1 = cr[1], c2 = cr[2], c3 = cr[3];
-        const float m[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+        float2 m[16];
+        load_pair_row16(cm + (h + dy) * Wp + w0, m);
 #pragma unroll
         for (int dxx = 0; dxx < 7; ++dxx) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[dxx] = fmaf(dq8[i], m[i + dxx + 1], a[dxx]);
+          for (int i = 0; i < 8; ++i) a[dxx] = fma2(bc2(dq8[i]), m[i + dxx + 1], a[dxx]);
         }
       }
 #pragma unroll
       for (int dxx = 0; dxx < 7; ++dxx) {
-        const float t = warp_sum(a[dxx]);
-        if (lane == 0) sp.dw[k * 49 + dy * 7 + dxx] = t;
+        const float t0 = warp_sum(a[dxx].x), t1 = warp_sum(a[dxx].y);
+        if (lane == 0) {
+          sp.dw[half * 98 + dy * 7 + dxx] = t0;
+          sp.dw[half * 98 + 49 + dy * 7 + dxx] = t1;
+        }
       }
     }
   }
@@ -1131,74 +1308,68 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     const float invC = 1.f / (float)C;
     for (int item = threadIdx.x; item < H * nrun; item += NT) {
       const int h = item / nrun, w0 = (item - h * nrun) * 8;
-      float q0[8], q1[8];
+      float2 q[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q0[i] = q1[i] = 0.f;
-      stencil_run8(s_dq + h * Wp + w0, Wp, sp.wtf, q0);
-      stencil_run8(s_dq + h * Wp + w0, Wp, sp.wtf + 56, q1);
+      for (int i = 0; i < 8; ++i) q[i] = make_float2(0.f, 0.f);
+      stencil_dq_run8(s_dq + h * Wp + w0, Wp, sp.wtf, q);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (w0 + i < W) {
           const int p = h * W + w0 + i;
-          s_dm[p] = make_float2(q0[i] * invC, q1[i] / (float)max((int)__ldg(tp + p), 1));
+          s_dm[p] = make_float2(q[i].x * invC, q[i].y / (float)max((int)__ldg(tp + p), 1));
         }
       }
     }
   }
   __syncthreads();
-  if (dq_out == nullptr && threadIdx.x < 98) atomicAdd(dwsp + threadIdx.x, sp.dw[threadIdx.x]);
+  if (dq_out == nullptr && threadIdx.x < 98) atomicAdd(dwsp + threadIdx.x, sp.dw[threadIdx.x] + sp.dw[98 + threadIdx.x]);
 
-  // per-thread channel coefficients (fixed channel block): xhat = xa*x + xb ; z = za*x + zb
-  float xa[8], xb[8], za[8], zb[8], gm[8], sc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cb * 8 + j, g = c / cg;
-    gm[j] = __ldg(gamma + c);
-    xa[j] = sp.rs[g]; xb[j] = -sp.mu[g] * sp.rs[g];
-    gn_coef(gm[j], __ldg(beta + c), sp.mu[g], sp.rs[g], za[j], zb[j]);
-    sc[j] = sp.se[c];
-  }
+  // per-thread channel coefficients (fixed channel block), as pairs: xhat = xa*x + xb ; z = za*x + zb
+  GnCoef k;
+  gn_coef_load(k, gamma, beta, sp, cb, cg);
+  float2 sc[4];
+  load_chan8(sp.se, cb, sc);
   image_copy_wait(bar, (uint32_t)((size_t)P * C * sizeof(T)));      // x is in shared memory from here on
 
   // ---- pass B (first of the two activation evaluations): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
-  // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu_raw + rounding), so the
+  // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu8 + rounding), so the
   // comparison against the saved maximum selects the same channels.
   {
-    float acc[8];
+    float2 acc[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
     constexpr int KB = raw_batch<T>();
     PixWalk pw(cvs, W);
     for (int r0 = 0; r0 < nround; r0 += KB) {
       Raw8<T> dr[KB];
       int pp[KB], ipk[KB];
 #pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        pp[k] = pw.p < P ? pw.p : -1;
-        ipk[k] = (pw.h + 3) * Wp + pw.w + 4;
-        dr[k] = ld_raw<true>(don + ((size_t)max(pp[k], 0) * cv + cb) * 8);
+      for (int kk = 0; kk < KB; ++kk) {
+        pp[kk] = pw.p < P ? pw.p : -1;
+        ipk[kk] = (pw.h + 3) * Wp + pw.w + 4;
+        dr[kk] = ld_raw<true>(don + ((size_t)max(pp[kk], 0) * cv + cb) * 8);
         pw.next(W);
       }
 #pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        if (pp[k] >= 0) {
-          const size_t v = (size_t)pp[k] * cv + cb;
-          float t[8], d[8];
+      for (int kk = 0; kk < KB; ++kk) {
+        if (pp[kk] >= 0) {
+          const size_t v = (size_t)pp[kk] * cv + cb;
+          float2 t[4], d[4];
           load8_rw(s_img + v * 8, t);
-          unpack8(dr[k], d);
-          const float gt = s_gate[pp[k]];
-          const float2 dm = s_dm[pp[k]];
-          const float mx = cm1[ipk[k]];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = silu_raw<T>(t[j], za[j], zb[j]);
+          unpack8(dr[kk], d);
+          const float2 gt = bc2(s_gate[pp[kk]]);
+          const float2 dm = s_dm[pp[kk]];
+          const float mx = cm[ipk[kk]].y;
+          silu8<T>(t, k.za, k.zb);
           round8_to<T>(t);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float a = t[j];
-            const float u = a * sc[j];
-            const float du = fmaf(d[j], gt, dm.x) + ((u == mx) ? dm.y : 0.f);
-            acc[j] = fmaf(du, a, acc[j]);
-            d[j] = du * sc[j];
+          for (int j = 0; j < 4; ++j) {
+            const float2 u = mul2(t[j], sc[j]);
+            float2 du = fma2(d[j], gt, bc2(dm.x));
+            if (u.x == mx) du.x += dm.y;
+            if (u.y == mx) du.y += dm.y;
+            acc[j] = fma2(du, t[j], acc[j]);
+            d[j] = mul2(du, sc[j]);
           }
           store8(dxn + v * 8, d);
         }
@@ -1238,33 +1409,30 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     }
   }
   __syncthreads();
-  // ---- GroupNorm + SiLU backward, pass 1 (second activation evaluation): dxhat -> scratch, reductions
-  float dp[8], r0[8], r1[8];
+  // ---- GroupNorm + SiLU backward, pass 1 (second activation evaluation): dxhat -> scratch, reductions.  With `scr` the
+  // scratch is the shared-memory overlay of the gate planes (dead since pass B; the barriers of the SE backward separate
+  // their last reader from the first scratch write) and pass 2 has no global load left.
+  T* sxn = scr ? reinterpret_cast<T*>(smem + L.scr) : dxn;
+  float2 dp[4], r0[4], r1[4];
+  load_chan8(sp.dpool, cb, dp);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { dp[j] = sp.dpool[cb * 8 + j]; r0[j] = r1[j] = 0.f; }
+  for (int j = 0; j < 4; ++j) r0[j] = r1[j] = make_float2(0.f, 0.f);
   constexpr int KB = raw_batch<T>();
   for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
     Raw8<T> raw[KB];
 #pragma unroll
-    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<false>(dxn + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+    for (int kk = 0; kk < KB; ++kk) raw[kk] = ld_raw<false>(dxn + (size_t)min(v0 + kk * NT, nvec - 1) * 8);
 #pragma unroll
-    for (int k = 0; k < KB; ++k) {
-      const int v = v0 + k * NT;
+    for (int kk = 0; kk < KB; ++kk) {
+      const int v = v0 + kk * NT;
       if (v < nvec) {
-        float t[8], d[8];
+        float2 t[4], d[4];
         load8_rw(s_img + (size_t)v * 8, t);
-        unpack8(raw[k], d);
+        unpack8(raw[kk], d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = fmaf(xa[j], t[j], xb[j]);
-          const float z = fmaf(za[j], t[j], zb[j]);
-          const float sg = sigmoid_t<T>(z);
-          const float dz = (d[j] + dp[j]) * sg * fmaf(z, 1.f - sg, 1.f);
-          r0[j] = fmaf(dz, xh, r0[j]);
-          r1[j] += dz;
-          d[j] = dz * gm[j];
-        }
-        store8(dxn + (size_t)v * 8, d);
+        for (int j = 0; j < 4; ++j) d[j] = add2(d[j], dp[j]);
+        gn_silu_bwd_vec<T>(d, t, k, r0, r1);
+        store8(sxn + (size_t)v * 8, d);
       }
     }
   }
@@ -1274,10 +1442,10 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   if (threadIdx.x < kGroups) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < cg; ++k) {
-      const float gmc = __ldg(gamma + g * cg + k);
-      a = fmaf(gmc, sp.ch2[g * cg + k], a);
-      b = fmaf(gmc, sp.ch1[g * cg + k], b);
+    for (int kk = 0; kk < cg; ++kk) {
+      const float gmc = __ldg(gamma + g * cg + kk);
+      a = fmaf(gmc, sp.ch2[g * cg + kk], a);
+      b = fmaf(gmc, sp.ch1[g * cg + kk], b);
     }
     const float cnt = (float)cg * (float)P;
     sp.m1[g] = a / cnt;
@@ -1288,26 +1456,21 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     atomicAdd(dbeta + c, sp.ch2[c]);
   }
   __syncthreads();
-  float k1[8], k2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (cb * 8 + j) / cg;
-    k1[j] = -xa[j] * (sp.m1[g] + sp.m2[g] * xb[j]);
-    k2[j] = -xa[j] * sp.m2[g] * xa[j];
-  }
+  float2 k1[4], k2[4];
+  gn_bwd_pass2_coef(k, sp, cb, cg, k1, k2);
   for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
     Raw8<T> raw[KB];
 #pragma unroll
-    for (int k = 0; k < KB; ++k) raw[k] = ld_raw<false>(dxn + (size_t)min(v0 + k * NT, nvec - 1) * 8);
+    for (int kk = 0; kk < KB; ++kk) raw[kk] = ld_raw<false>(sxn + (size_t)min(v0 + kk * NT, nvec - 1) * 8);
 #pragma unroll
-    for (int k = 0; k < KB; ++k) {
-      const int v = v0 + k * NT;
+    for (int kk = 0; kk < KB; ++kk) {
+      const int v = v0 + kk * NT;
       if (v < nvec) {
-        float t[8], d[8];
+        float2 t[4], d[4];
         load8_rw(s_img + (size_t)v * 8, t);
-        unpack8(raw[k], d);
+        unpack8(raw[kk], d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = fmaf(xa[j], d[j], fmaf(k2[j], t[j], k1[j]));
+        for (int j = 0; j < 4; ++j) d[j] = fma2(k.xa[j], d[j], fma2(k2[j], t[j], k1[j]));
         store8(dxn + (size_t)v * 8, d);
       }
     }
@@ -1415,6 +1578,24 @@ static int tail_launch_threads(K kern, int N, int H, int W, int C, size_t smem, 
   return best;
 }
 
+// Whether a backward tail launched with `threads` per CTA may take the larger shared-memory layout (`smem_scr`: scratch
+// overlay, see tail_smem_layout) without losing resident CTAs per SM against `smem`: true when registers / threads, not
+// shared memory, bound the residency either way (the level-1 images: one 512-thread CTA per SM by registers alone).
+// PCM_TAIL_SCRATCH=0 keeps the scratch in global memory.
+template <typename K>
+static int tail_scratch_ok(K kern, int threads, size_t smem, size_t smem_scr) {
+  const char* e = getenv("PCM_TAIL_SCRATCH");
+  if (e != nullptr && atoi(e) == 0) return 0;
+  if (smem_scr > 227 * 1024) return 0;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess || fa.numRegs <= 0) return 0;
+  long long other = 65536 / ((long long)((fa.numRegs + 7) / 8 * 8) * threads);
+  if (2048 / threads < other) other = 2048 / threads;
+  if (other > 32) other = 32;
+  const long long a = (228 * 1024) / (long long)(smem + 1024), b = (228 * 1024) / (long long)(smem_scr + 1024);
+  return (b < other ? b : other) >= (a < other ? a : other) ? 1 : 0;
+}
+
 static bool fused_shape_ok(int H, int W, int C, int Cr) {
   const int cv = C / 8;
   return C % 8 == 0 && C >= 8 && cv <= 32 && (cv & (cv - 1)) == 0 && Cr >= 1 && Cr <= 64 && Cr * 8 <= C && H >= 1 && W >= 1;
@@ -1484,7 +1665,7 @@ static bool block_fwd_layout(int H, int W, int Cin, int C, int Cr, BlockFwdParam
   if (p->off_cm1 != p->off_cm0 + Pp * 4) return false;                      // the kernel zeroes them as one range
   p->off_gate = take((size_t)p->P * 4, 16);
   p->off_part = take((size_t)2 * (kBlkThreads / 32) * C * 4 + 64, 16);       // chan_put slots; >= 17 warps x 16 floats
-  p->off_fl = take((size_t)(11 * C + 128 + 32 + 112 + 112 + 100 + C * C / 4) * 4, 16);
+  p->off_fl = take((size_t)(11 * C + 128 + 32 + 112 + 112 + kDwFloats + C * C / 4) * 4, 16);
   p->off_bar = take(34 * 8 + 16, 16);
   *smem_total = off + 1024;                                                  // + alignment slack of the dynamic base
   return *smem_total <= 227 * 1024;
@@ -1593,10 +1774,14 @@ extern "C" int pcm_gn_silu_img_bwd(const void* da, const void* x, const float* s
   PCM_REQUIRE(smem <= 227 * 1024, "gn_silu_img_bwd: image does not fit shared memory (%zu B)", smem);
   int rc = PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, {
-    rc = tail_set_smem(gn_silu_img_bwd_kernel<T>, smem, "gn_silu_img_bwd");
+    const int threads = tail_launch_threads(gn_silu_img_bwd_kernel<T>, N, H, W, C, smem, 6.75f);
+    const size_t smem_scr = tail_smem_layout(H, W, C, (int)sizeof(T), 0, 1, 1).total;
+    const int scr = tail_scratch_ok(gn_silu_img_bwd_kernel<T>, threads, smem, smem_scr);
+    const size_t bytes = scr ? smem_scr : smem;
+    rc = tail_set_smem(gn_silu_img_bwd_kernel<T>, bytes, "gn_silu_img_bwd");
     if (rc == PCM_OK)
-      pcm::launch(gn_silu_img_bwd_kernel<T>, N, tail_launch_threads(gn_silu_img_bwd_kernel<T>, N, H, W, C, smem, 6.75f), smem, (cudaStream_t)s, (const T*)da, (const T*)x, stats, gamma, beta, (T*)dx,
-                                                                   dgamma, dbeta, H, W, C, eps);
+      pcm::launch(gn_silu_img_bwd_kernel<T>, N, threads, bytes, (cudaStream_t)s, (const T*)da, (const T*)x, stats, gamma, beta,
+                  (T*)dx, dgamma, dbeta, H, W, C, eps, scr);
   });
   if (rc != PCM_OK) return rc;
   return check_launch("gn_silu_img_bwd");
@@ -1644,11 +1829,15 @@ extern "C" int pcm_convblock_tail_bwd_dq(const void* dout, const void* x, const 
   PCM_REQUIRE(((uintptr_t)x & 15) == 0, "convblock_tail_bwd: x must be 16-byte aligned (bulk copy)");
   int rc = PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, {
-    rc = tail_set_smem(convblock_tail_bwd_kernel<T>, smem, "convblock_tail_bwd");
+    const int threads = tail_launch_threads(convblock_tail_bwd_kernel<T>, N, H, W, C, smem, 6.75f);
+    const size_t smem_scr = tail_smem_layout(H, W, C, (int)sizeof(T), 1, 1, 1).total;
+    const int scr = tail_scratch_ok(convblock_tail_bwd_kernel<T>, threads, smem, smem_scr);
+    const size_t bytes = scr ? smem_scr : smem;
+    rc = tail_set_smem(convblock_tail_bwd_kernel<T>, bytes, "convblock_tail_bwd");
     if (rc == PCM_OK)
-      pcm::launch(convblock_tail_bwd_kernel<T>, N, tail_launch_threads(convblock_tail_bwd_kernel<T>, N, H, W, C, smem, 6.75f), smem, (cudaStream_t)s, 
+      pcm::launch(convblock_tail_bwd_kernel<T>, N, threads, bytes, (cudaStream_t)s,
           (const T*)dout, (const T*)x, (const T*)out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties,
-          (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, dq_out, H, W, C, Cr, eps);
+          (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, dq_out, H, W, C, Cr, eps, scr);
   });
   if (rc != PCM_OK) return rc;
   return check_launch("convblock_tail_bwd");

@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 bool pdl_enabled() {
   static const int on = [] {
     const char* e = getenv("PCM_PDL");
-    return (e != nullptr && e[0] == '1') ? 1 : 0;          // opt-in: measured neutral on B200 (see common.cuh)
+    return (e != nullptr && e[0] == '0') ? 0 : 1;          // default on (PCM_PDL=0: classic launches; see common.cuh)
   }();
   return on != 0;
 }

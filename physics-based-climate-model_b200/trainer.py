@@ -330,28 +330,53 @@ class TrainStep:
         return self.run()
 
     # -- input prefetch: the host->device copy of the NEXT batch overlaps this step --------------------------
+    def _alt_buffers(self):
+        """Second pair of static input buffers and — under graph replay — a second captured step that reads them (same
+        memory pool: the two graphs never run concurrently).  step_prefetch alternates between the pairs, so the next
+        batch lands by H2D exactly where the next step reads it and no device-to-device move is left on the step's path."""
+        self._x_alt = torch.empty_like(self.x)
+        self._y_alt = torch.empty_like(self.y)
+        self._graph_alt = None
+        if self.graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.x, self._x_alt = self._x_alt, self.x
+            self.y, self._y_alt = self._y_alt, self.y
+            try:
+                g = torch.cuda.CUDAGraph()
+                # capture enqueues nothing: parameters / optimizer state are untouched
+                with torch.cuda.graph(g, pool=self.graph.pool(), stream=self._capture_stream()):
+                    self._step_impl()
+                self._graph_alt = g
+            finally:
+                self.x, self._x_alt = self._x_alt, self.x
+                self.y, self._y_alt = self._y_alt, self.y
+            torch.cuda.synchronize(self.device)
+        self._free_alt = torch.cuda.Event()       # the step that last read the (currently) alternate pair has finished
+        self._free_alt.record()
+        self._free_cur = torch.cuda.Event()
+
     def step_prefetch(self, x_next: torch.Tensor, y_next: torch.Tensor) -> torch.Tensor:
         """Run one step on the batch already resident in the static buffers while (x_next, y_next) — pinned host
-        tensors — are copied to a staging buffer on a second stream; afterwards the staged batch is moved into the
-        static buffers (device-to-device, ~25 us) so that the next call trains on it.  This is what a DataLoader with
-        pinned memory and non_blocking copies does for the reference's training loop (main_final.py:291), made
-        explicit: every call still moves one batch across PCIe, but off the critical path."""
+        tensors — are copied on a second stream into the ALTERNATE pair of static buffers, which the next call then
+        trains on (the pairs, and the two captured graphs that read them, swap roles after every call; `load_batch` /
+        `run` / `step` always address the current pair).  This is what a DataLoader with pinned memory and non_blocking
+        copies does for the reference's training loop (main_final.py:291), made explicit: every call still moves one
+        batch across PCIe, but off the critical path, and nothing is moved twice."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._xs = torch.empty_like(self.x)
-            self._ys = torch.empty_like(self.y)
             self._staged = torch.cuda.Event()
-            self._consumed = torch.cuda.Event()
-            self._consumed.record()
+            self._alt_buffers()
         main = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._consumed)        # the previous staged batch has been moved out
-            self._xs.copy_(x_next, non_blocking=True)
-            self._ys.copy_(y_next, non_blocking=True)
+            self._copy_stream.wait_event(self._free_alt)        # its previous contents have been consumed
+            self._x_alt.copy_(x_next, non_blocking=True)
+            self._y_alt.copy_(y_next, non_blocking=True)
             self._staged.record()
         loss = self.run()
-        main.wait_event(self._staged)
-        self.x.copy_(self._xs, non_blocking=True)
-        self.y.copy_(self._ys, non_blocking=True)
-        self._consumed.record()
+        self._free_cur.record(main)                             # the current pair may be overwritten from here on
+        main.wait_event(self._staged)                           # the next step (any stream order) sees the staged batch
+        self.x, self._x_alt = self._x_alt, self.x
+        self.y, self._y_alt = self._y_alt, self.y
+        self.graph, self._graph_alt = self._graph_alt, self.graph
+        self._free_cur, self._free_alt = self._free_alt, self._free_cur
         return loss
