@@ -229,21 +229,30 @@ __device__ __forceinline__ void load_gate_weights(const float* __restrict__ wsp,
   }
 }
 
-// one row of 16 consecutive pixels of the interleaved plane (8 aligned 16-byte loads) as 16 pairs
-__device__ __forceinline__ void load_pair_row16(const float2* row, float2 (&m)[16]) {
-  const float4* r = reinterpret_cast<const float4*>(row);
+// Bank swizzles of the gate planes.  A stencil work item reads 16 consecutive pixels of a plane row, and the lanes of a
+// warp own adjacent 8-pixel runs: their 16-byte loads start 32 bytes apart in a scalar plane (lanes l and l + 4 of a
+// quarter-warp hit the same banks: 2-way conflict) and 64 bytes apart in the interleaved pair plane (4-way) — the
+// gate-weight gradient phase of the backward tail was bound by exactly these replays (17 k of its 96 k cycles per
+// 48x72x16 image, against 5 k of issue).  Storing 16-byte granule g of a plane at g ^ ((g >> 3) & 1) (scalar) /
+// g ^ ((g >> 3) & 3) (pairs) makes the eight loads of a quarter-warp land in eight different bank groups.  Indices are
+// element indices relative to the plane (float / float2); the permutation stays inside aligned 8-element groups, so
+// zero-filling the plane linearly is still right.
+__device__ __forceinline__ int pswz(int i) { return i ^ ((i >> 3) & 4); }      // float index: byte-address bit 7 -> bit 4
+__device__ __forceinline__ int pswz2(int p) { return p ^ ((p >> 3) & 6); }     // float2 index: bits 7, 8 -> bits 4, 5
+// one row of 16 consecutive pixels of the interleaved plane (8 aligned 16-byte loads) as 16 pairs; i = element index of
+// the first pixel (a multiple of 8)
+__device__ __forceinline__ void load_pair_row16(const float2* plane, int i, float2 (&m)[16]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 v = r[j];
+    const float4 v = *reinterpret_cast<const float4*>(plane + pswz2(i + 2 * j));
     m[2 * j] = make_float2(v.x, v.y);
     m[2 * j + 1] = make_float2(v.z, v.w);
   }
 }
-__device__ __forceinline__ void load_row16(const float* row, float (&m)[16]) {
-  const float4* r = reinterpret_cast<const float4*>(row);
+__device__ __forceinline__ void load_row16(const float* plane, int i, float (&m)[16]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 v = r[j];
+    const float4 v = *reinterpret_cast<const float4*>(plane + pswz(i + 4 * j));
     m[4 * j] = v.x; m[4 * j + 1] = v.y; m[4 * j + 2] = v.z; m[4 * j + 3] = v.w;
   }
 }
@@ -255,13 +264,14 @@ __device__ __forceinline__ void load_weight_row(const float* wrow, float2 (&w)[7
 }
 
 // Transposed gate conv: q[i] += (sum_taps wf[0] * dq(..), sum_taps wf[1] * dq(..)) from the scalar dq plane
-// (row0 = plane + h * Wp + w0, 32-byte aligned): 4 + 4 vector loads feed 56 packed FMAs with a broadcast operand.
-__device__ __forceinline__ void stencil_dq_run8(const float* row0, int Wp, const float* wtf, float2 (&q)[8]) {
+// (i0 = h * Wp + w0, the element index of the window's first pixel): 4 + 4 vector loads feed 56 packed FMAs with a
+// broadcast operand.
+__device__ __forceinline__ void stencil_dq_run8(const float* plane, int i0, int Wp, const float* wtf, float2 (&q)[8]) {
 #pragma unroll
   for (int dy = 0; dy < 7; ++dy) {
     float m[16];
     float2 w[7];
-    load_row16(row0 + dy * Wp, m);
+    load_row16(plane, i0 + dy * Wp, m);
     load_weight_row(wtf + dy * 16, w);
 #pragma unroll
     for (int dx = 0; dx < 7; ++dx) {
@@ -272,13 +282,12 @@ __device__ __forceinline__ void stencil_dq_run8(const float* row0, int Wp, const
 }
 
 // q[i] += sum_{dy,dx} wt[dy][dx] * plane(h + dy - 3, w0 + i + dx - 3) for the 8 pixels (h, w0 .. w0 + 7);
-// row0 = plane + h * Wp + w0 (32-byte aligned).  Per kernel row: 4 + 2 vector loads feed 56 FMAs.
-__device__ __forceinline__ void stencil_run8(const float* row0, int Wp, const float* wt, float (&q)[8]) {
+// i0 = h * Wp + w0 (element index of the window's first pixel).  Per kernel row: 4 + 2 vector loads feed 56 FMAs.
+__device__ __forceinline__ void stencil_run8(const float* plane, int i0, int Wp, const float* wt, float (&q)[8]) {
 #pragma unroll
   for (int dy = 0; dy < 7; ++dy) {
-    const float4* r = reinterpret_cast<const float4*>(row0 + dy * Wp);
-    const float4 a = r[0], b = r[1], c = r[2], d = r[3];
-    const float m[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    float m[16];
+    load_row16(plane, i0 + dy * Wp, m);
     const float4 wa = reinterpret_cast<const float4*>(wt + dy * 8)[0], wb = reinterpret_cast<const float4*>(wt + dy * 8)[1];
     const float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
 #pragma unroll
@@ -560,8 +569,8 @@ __device__ __forceinline__ void tail_finish_from_pool(T* s_img, uint8_t* smem, c
       if (valid && cb == 0) {
         const int ip = (pw.h + 3) * Wp + pw.w + 4;
         const float mean = sum * invC;
-        cm0[ip] = mean;
-        cm1[ip] = mx;
+        cm0[pswz(ip)] = mean;
+        cm1[pswz(ip)] = mx;
         if (mp != nullptr) {
           mp[pw.p] = mean;
           mp[P + pw.p] = mx;
@@ -579,8 +588,8 @@ __device__ __forceinline__ void tail_finish_from_pool(T* s_img, uint8_t* smem, c
       float q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) q[i] = 0.f;
-      stencil_run8(cm0 + h * Wp + w0, Wp, sp.wt, q);
-      stencil_run8(cm1 + h * Wp + w0, Wp, sp.wt + 56, q);
+      stencil_run8(cm0, h * Wp + w0, Wp, sp.wt, q);
+      stencil_run8(cm1, h * Wp + w0, Wp, sp.wt + 56, q);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (w0 + i < W) {
@@ -701,6 +710,18 @@ constexpr int kBlkThreads = 544;
 #define BLK_PROF_DECL
 #define BLK_PROF(i)
 #define BLK_PROF_PRINT()
+#endif
+
+// -DPCM_TAIL_PROFILE: thread 0 of CTA 0 of convblock_tail_bwd records clock64 at every phase boundary (with a CTA
+// barrier, so a phase ends when its last warp does) and prints the cycles per phase (measurement builds only)
+#ifdef PCM_TAIL_PROFILE
+#define TPROF_DECL long long tp_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tp_c = clock64(); const bool tp_on = blockIdx.x == 0 && threadIdx.x == 0
+#define TPROF(i) do { __syncthreads(); if (tp_on) { const long long c_ = clock64(); tp_t[i] += c_ - tp_c; tp_c = c_; } } while (0)
+#define TPROF_PRINT() do { if (tp_on) printf("convblock_tail_bwd[%d,%d,%d] x%d thr, cycles: prologue %lld | passA %lld | gate wgrad %lld | gate dgrad %lld | coef+xwait %lld | passB %lld | SE %lld | pass1 %lld | stats %lld | pass2 %lld\n", H, W, C, NT, tp_t[0], tp_t[1], tp_t[2], tp_t[3], tp_t[4], tp_t[5], tp_t[6], tp_t[7], tp_t[8], tp_t[9]); } while (0)
+#else
+#define TPROF_DECL
+#define TPROF(i)
+#define TPROF_PRINT()
 #endif
 
 struct BlockFwdParams {
@@ -1204,6 +1225,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   T* dxn = dx + (size_t)n * P * C;
   const int cb = threadIdx.x & (cv - 1);
   const float invP = 1.f / (float)P;
+  TPROF_DECL;
 
   {
     float4* z4 = reinterpret_cast<float4*>(cm);                                 // cm0 | cm1 | dq are contiguous
@@ -1220,6 +1242,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   for (int j = threadIdx.x; j < Cr; j += NT) sp.hid[j] = __ldg(hid_g + (size_t)n * Cr + j);
   group_mu_rs_from_stats(stats + (size_t)n * kGroups * 2, cg, P, eps, sp);
   __syncthreads();
+  TPROF(0);
 
   // ---- pass A (global operands only): the saved maps go into the padded planes and dq = (1 - gate) * sum_c dout*out.
   // Nothing here depends on shared memory, so the loads of kBatch rounds are issued back to back (the loop is
@@ -1228,7 +1251,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
 #pragma unroll 4
     for (int p = threadIdx.x; p < P; p += NT) {
       const int h = p / W, w = p - h * W, ip = (h + 3) * Wp + w + 4;
-      cm[ip] = make_float2(__ldg(mp + p), __ldg(mp + P + p));
+      cm[pswz2(ip)] = make_float2(__ldg(mp + p), __ldg(mp + P + p));
       s_gate[p] = __ldg(mp + 2 * P + p);
     }
     constexpr int kBatch = 2 * raw_batch<T>();
@@ -1244,7 +1267,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
         dr[k] = ld_raw<true>(don + v * 8);
         orw[k] = ld_raw<true>(outn + v * 8);
         gt[k] = (valid && cb == 0) ? __ldg(mp + 2 * P + pw.p) : 1.f;
-        ip[k] = (valid && cb == 0) ? (pw.h + 3) * Wp + pw.w + 4 : -1;
+        ip[k] = (valid && cb == 0) ? pswz((pw.h + 3) * Wp + pw.w + 4) : -1;
         pk[k] = pw.p;
         pw.next(W);
       }
@@ -1267,6 +1290,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     }
   }
   __syncthreads();
+  TPROF(1);
   // ---- dwsp[k][dy][dx] = sum_p dq[p] * cmap_k[p + (dy-3, dx-3)]: one warp per (kernel row dy, half of the 8-pixel
   // runs), lanes over the runs; the 7 dx sums of BOTH maps accumulate as pairs (broadcast dq x (mean, max)), combined
   // with shuffles (no atomics: every (half, k, dy, dx) has one owner; the two halves are added when dwsp is updated)
@@ -1281,11 +1305,11 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       for (int i = 0; i < 7; ++i) a[i] = make_float2(0.f, 0.f);
       for (int item = i0 + lane; item < i1; item += 32) {
         const int h = item / nrun, w0 = (item - h * nrun) * 8;
-        const float4* dr = reinterpret_cast<const float4*>(s_dq + (h + 3) * Wp + w0 + 4);
-        const float4 d0 = dr[0], d1 = dr[1];
+        const int id = (h + 3) * Wp + w0 + 4;
+        const float4 d0 = *reinterpret_cast<const float4*>(s_dq + pswz(id)), d1 = *reinterpret_cast<const float4*>(s_dq + pswz(id + 4));
         const float dq8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         float2 m[16];
-        load_pair_row16(cm + (h + dy) * Wp + w0, m);
+        load_pair_row16(cm, (h + dy) * Wp + w0, m);
 #pragma unroll
         for (int dxx = 0; dxx < 7; ++dxx) {
 #pragma unroll
@@ -1302,6 +1326,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       }
     }
   }
+  TPROF(2);
   // ---- gradient reaching (mean, max) through the transposed stencil (flipped weights)
   {
     const int nrun = (W + 7) / 8;
@@ -1311,7 +1336,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       float2 q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) q[i] = make_float2(0.f, 0.f);
-      stencil_dq_run8(s_dq + h * Wp + w0, Wp, sp.wtf, q);
+      stencil_dq_run8(s_dq, h * Wp + w0, Wp, sp.wtf, q);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (w0 + i < W) {
@@ -1323,6 +1348,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   }
   __syncthreads();
   if (dq_out == nullptr && threadIdx.x < 98) atomicAdd(dwsp + threadIdx.x, sp.dw[threadIdx.x] + sp.dw[98 + threadIdx.x]);
+  TPROF(3);
 
   // per-thread channel coefficients (fixed channel block), as pairs: xhat = xa*x + xb ; z = za*x + zb
   GnCoef k;
@@ -1330,6 +1356,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   float2 sc[4];
   load_chan8(sp.se, cb, sc);
   image_copy_wait(bar, (uint32_t)((size_t)P * C * sizeof(T)));      // x is in shared memory from here on
+  TPROF(4);
 
   // ---- pass B (first of the two activation evaluations): du = dout*gate + dmean + [u == max]*dmax/ties ; r = du*se (scratch in dx) ;
   // dse = sum_p du*a.  a and u are recomputed exactly as the forward kernel computed them (silu8 + rounding), so the
@@ -1359,7 +1386,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
           unpack8(dr[kk], d);
           const float2 gt = bc2(s_gate[pp[kk]]);
           const float2 dm = s_dm[pp[kk]];
-          const float mx = cm[ipk[kk]].y;
+          const float mx = cm[pswz2(ipk[kk])].y;
           silu8<T>(t, k.za, k.zb);
           round8_to<T>(t);
 #pragma unroll
@@ -1378,6 +1405,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     chan_put(acc, sp.part, 0, cb, cv, C);
   }
   chan_finish(sp.part, 1, sp.ch0, C);
+  TPROF(5);
   // ---- SE backward (tiny): dpool, dw1, dw2
   for (int c = threadIdx.x; c < C; c += NT) {
     const float s = sp.se[c];
@@ -1409,6 +1437,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
     }
   }
   __syncthreads();
+  TPROF(6);
   // ---- GroupNorm + SiLU backward, pass 1 (second activation evaluation): dxhat -> scratch, reductions.  With `scr` the
   // scratch is the shared-memory overlay of the gate planes (dead since pass B; the barriers of the SE backward separate
   // their last reader from the first scratch write) and pass 2 has no global load left.
@@ -1439,6 +1468,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   chan_put(r0, sp.part, 0, cb, cv, C);
   chan_put(r1, sp.part, 1, cb, cv, C);
   chan_finish(sp.part, 2, sp.ch1, C);
+  TPROF(7);
   if (threadIdx.x < kGroups) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
@@ -1458,6 +1488,7 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   __syncthreads();
   float2 k1[4], k2[4];
   gn_bwd_pass2_coef(k, sp, cb, cg, k1, k2);
+  TPROF(8);
   for (int v0 = threadIdx.x; v0 < nvec; v0 += NT * KB) {
     Raw8<T> raw[KB];
 #pragma unroll
@@ -1475,6 +1506,8 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
       }
     }
   }
+  TPROF(9);
+  TPROF_PRINT();
 }
 
 // Gate-weight gradient of SpatialGate's 7x7 conv (src/unet.py:24,28) for ALL images of a launch, off the critical path:
