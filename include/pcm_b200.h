@@ -306,6 +306,17 @@ PCM_API int pcm_convblock_tail_bwd_dq(const void* dout, const void* x, const voi
                                       float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out, int N, int H,
                                       int W, int C, int Cr, float eps, int dtype, pcm_stream_t s);
 PCM_API int pcm_gate_wgrad(const float* dq, const float* maps, float* dwsp, int N, int H, int W, pcm_stream_t s);
+/* The same again with the per-pixel sum sdot[N][H*W] = sum_c dout*out supplied by the kernel that produced dout
+ * (pcm_maxpool2_bwd_skip_dot: the backward of MaxPool2d + time-mean skip that follows the block in the encoder,
+ * src/unet_convlstm_attention.py:21-24,91-93, holds dout and out in registers).  sdot non-NULL: dout / out are not streamed
+ * for the gate gradient (out may be NULL); sdot NULL: identical to pcm_convblock_tail_bwd_dq.  dq_out may be NULL. */
+PCM_API int pcm_convblock_tail_bwd_sdot(const void* dout, const void* x, const void* out, const float* stats,
+                                        const float* gamma, const float* beta, const float* w1, const float* w2,
+                                        const float* wsp, const float* pool, const float* se, const float* hid,
+                                        const float* maps, const unsigned char* ties, void* dx, float* dgamma,
+                                        float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out,
+                                        const float* sdot, int N, int H, int W, int C, int Cr, float eps, int dtype,
+                                        pcm_stream_t s);
 
 /* ---- BatchNorm2d, training mode (src/models.py:48,51,57,91,109; eps 1e-5, momentum 0.1) on NHWC rows
  * (R = N*H*W rows of C channels; C = 8 * a divisor of 256).  sums[c] = (sum x, sum x^2) in DOUBLE (2*C doubles),
@@ -388,6 +399,12 @@ PCM_API int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C,
  * (dy nullable; dskip nullable, an activation view with channel offset applied by the caller) */
 PCM_API int pcm_maxpool2_bwd_skip(const void* x, const void* dy, const void* dskip, long long dskip_ns, int dskip_ps,
                                   void* dx, int N, int H, int W, int C, int T, int t_major, int dtype, pcm_stream_t s);
+/* the same, also writing sdot[n][h][w] = sum_c dx(n,h,w,c) * x(n,h,w,c) (fp32, dx as the storage type rounds it; sdot
+ * nullable; C/8 a power of two <= 32) for pcm_convblock_tail_bwd_sdot: x is the output of the ConvBlock whose backward
+ * consumes dx next (src/unet.py:29,47-49: out = u * gate, so d gate = sum_c dout * u) */
+PCM_API int pcm_maxpool2_bwd_skip_dot(const void* x, const void* dy, const void* dskip, long long dskip_ns, int dskip_ps,
+                                      void* dx, float* sdot, int N, int H, int W, int C, int T, int t_major, int dtype,
+                                      pcm_stream_t s);
 /* dst(b,p,c) = mean_t src(img(b,t), p, c), img = t*B + b (t-major) or b*T + t */
 PCM_API int pcm_time_mean(const void* src, void* dst, long long dst_ns, int dst_ps, int B, int T, int P, int C,
                           int t_major, int dtype, pcm_stream_t s);

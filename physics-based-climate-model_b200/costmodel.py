@@ -85,6 +85,12 @@ def algo_cost(name: str, args):
     if name == "pcm_convblock_tail_bwd":
         px = a["N"] * a["H"] * a["W"]
         return 0.0, 4 * px * a["C"] * es() + 13 * px, "hbm"
+    if name == "pcm_convblock_tail_bwd_sdot":
+        # with sdot (4 bytes per pixel, formed by the pooling backward) neither `out` nor a second pass over dout is part
+        # of the algorithm: dout + x in, dx out; without it this is pcm_convblock_tail_bwd(_dq)
+        px = a["N"] * a["H"] * a["W"]
+        tensors = 3 if a["sdot"] else 4
+        return 0.0, tensors * px * a["C"] * es() + (13 + (4 if a["sdot"] else 0) + (4 if a["dq_out"] else 0)) * px, "hbm"
     if name in ("pcm_bn_stats",):
         return 0.0, a["R"] * a["C"] * es(), "hbm"
     if name in ("pcm_bn_apply_fwd",):
@@ -146,6 +152,9 @@ def algo_cost(name: str, args):
         return 0.0, a["N"] * a["H"] * a["W"] * a["C"] * es() * 1.25, "hbm"
     if name == "pcm_maxpool2_bwd_skip":
         return 0.0, a["N"] * a["H"] * a["W"] * a["C"] * es() * 2.25, "hbm"     # x in, dx out, dy (1/4) in
+    if name == "pcm_maxpool2_bwd_skip_dot":
+        px = a["N"] * a["H"] * a["W"]
+        return 0.0, px * a["C"] * es() * 2.25 + (4 * px if a["sdot"] else 0), "hbm"
     if name == "pcm_time_mean":
         return 0.0, a["B"] * (a["T"] + 1) * a["P"] * a["C"] * es(), "hbm"
     if name == "pcm_channel_sum":

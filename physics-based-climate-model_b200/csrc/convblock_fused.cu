@@ -184,8 +184,9 @@ __host__ __device__ inline TailSmem tail_smem_layout(int H, int W, int C, int el
   L.part = PCM_TAKE((size_t)2 * (tail_threads(H, W, C) / 32) * C * 4);    // chan_put: 2 slots x warps x C floats (launches never
                                                                           // use more threads than tail_threads)
   // floats: 5 channel arrays | a[C] b[C] | se[C] pool[C] dpool[C] dpre2[C] | hid[64] dpre1[64] | mu[8] rs[8] m1[8] m2[8]
-  //         | wt[2][7][8] | wtf[7][8][2] | dw[2][98 + 2] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats)
-  L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + kDwFloats + (full ? C * C / 4 : 0)) * 4);
+  //         | wt[2][7][8] | wtf[7][8][2] | sw1[Cr*C] sw2[C*Cr] (Cr = C/8 at most: C*C/4 floats) | dw[2][98 + 2] (backward
+  //         tail only, LAST: 384 forward images of 24x36x32 fit three CTAs per SM by 144 bytes)
+  L.fl = PCM_TAKE((size_t)(11 * C + 128 + 32 + 112 + 112 + (full ? C * C / 4 : 0) + ((full && bwd) ? kDwFloats : 0)) * 4);
 #undef PCM_TAKE
   L.total = off;
   return L;
@@ -205,8 +206,9 @@ __device__ __forceinline__ TailPtrs tail_ptrs(uint8_t* smem, const TailSmem& L, 
   float* g = f + 11 * C;
   p.hid = g; p.dpre1 = g + 64;
   p.mu = g + 128; p.rs = g + 136; p.m1 = g + 144; p.m2 = g + 152;
-  p.wt = g + 160; p.wtf = g + 272; p.dw = g + 384;
-  p.sw1 = g + 384 + kDwFloats; p.sw2 = p.sw1 + C * C / 8;
+  p.wt = g + 160; p.wtf = g + 272;
+  p.sw1 = g + 384; p.sw2 = p.sw1 + C * C / 8;
+  p.dw = p.sw1 + C * C / 4;
   return p;
 }
 
@@ -1199,8 +1201,11 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
                           const float* __restrict__ se_g, const float* __restrict__ hid_g,
                           const float* __restrict__ maps, const uint8_t* __restrict__ ties, T* __restrict__ dx,
                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw1,
-                          float* __restrict__ dw2, float* __restrict__ dwsp, float* __restrict__ dq_out, int H, int W, int C,
-                          int Cr, float eps, int scr) {
+                          float* __restrict__ dw2, float* __restrict__ dwsp, float* __restrict__ dq_out,
+                          const float* __restrict__ sdot, int H, int W, int C, int Cr, float eps, int scr) {
+  // sdot != NULL: sdot[n][p] = sum_c dout[p,c]*out[p,c] was already formed by the kernel that produced dout
+  // (pcm_maxpool2_bwd_skip_dot, which holds both operands in registers) — pass A then reads 4 bytes per pixel instead of
+  // streaming dout and out (2 x 2C bytes per pixel: a quarter of this kernel's cycles at 48x72x16).
   // dq_out != NULL: the gate's pre-activation gradient dq [N][H*W] is also written to global memory and the gate-weight
   // gradient (98 sums over the image: 11 % of this kernel's instructions on 14 of its 16 warps, 13 % of its samples) is
   // left to pcm_gate_wgrad on the side stream — a parameter gradient nothing in the backward chain waits for.
@@ -1248,15 +1253,22 @@ convblock_tail_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x, c
   // Nothing here depends on shared memory, so the loads of kBatch rounds are issued back to back (the loop is
   // bound by global-load latency otherwise: 16 warps per SM).
   {
+    const float* sdn = sdot != nullptr ? sdot + (size_t)n * P : nullptr;
 #pragma unroll 4
     for (int p = threadIdx.x; p < P; p += NT) {
       const int h = p / W, w = p - h * W, ip = (h + 3) * Wp + w + 4;
+      const float gtp = __ldg(mp + 2 * P + p);
       cm[pswz2(ip)] = make_float2(__ldg(mp + p), __ldg(mp + P + p));
-      s_gate[p] = __ldg(mp + 2 * P + p);
+      s_gate[p] = gtp;
+      if (sdn != nullptr) {
+        const float dqv = __ldg(sdn + p) * (1.f - gtp);
+        s_dq[pswz(ip)] = dqv;
+        if (dq_out != nullptr) dq_out[(size_t)n * P + p] = dqv;
+      }
     }
     constexpr int kBatch = 2 * raw_batch<T>();
     PixWalk pw(cvs, W);
-    for (int r0 = 0; r0 < nround; r0 += kBatch) {
+    for (int r0 = sdn != nullptr ? nround : 0; r0 < nround; r0 += kBatch) {
       Raw8<T> dr[kBatch], orw[kBatch];
       float gt[kBatch];
       int ip[kBatch], pk[kBatch];
@@ -1698,7 +1710,7 @@ static bool block_fwd_layout(int H, int W, int Cin, int C, int Cr, BlockFwdParam
   if (p->off_cm1 != p->off_cm0 + Pp * 4) return false;                      // the kernel zeroes them as one range
   p->off_gate = take((size_t)p->P * 4, 16);
   p->off_part = take((size_t)2 * (kBlkThreads / 32) * C * 4 + 64, 16);       // chan_put slots; >= 17 warps x 16 floats
-  p->off_fl = take((size_t)(11 * C + 128 + 32 + 112 + 112 + kDwFloats + C * C / 4) * 4, 16);
+  p->off_fl = take((size_t)(11 * C + 128 + 32 + 112 + 112 + C * C / 4) * 4, 16);
   p->off_bar = take(34 * 8 + 16, 16);
   *smem_total = off + 1024;                                                  // + alignment slack of the dynamic base
   return *smem_total <= 227 * 1024;
@@ -1848,17 +1860,36 @@ extern "C" int pcm_convblock_tail_bwd(const void* dout, const void* x, const voi
                                    dw1, dw2, dwsp, nullptr, N, H, W, C, Cr, eps, dtype, s);
 }
 
+extern "C" int pcm_convblock_tail_bwd_sdot(const void* dout, const void* x, const void* out, const float* stats,
+                                           const float* gamma, const float* beta, const float* w1, const float* w2,
+                                           const float* wsp, const float* pool, const float* se, const float* hid,
+                                           const float* maps, const unsigned char* ties, void* dx, float* dgamma,
+                                           float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out,
+                                           const float* sdot, int N, int H, int W, int C, int Cr, float eps, int dtype,
+                                           pcm_stream_t s);
 extern "C" int pcm_convblock_tail_bwd_dq(const void* dout, const void* x, const void* out, const float* stats,
                                          const float* gamma, const float* beta, const float* w1, const float* w2,
                                          const float* wsp, const float* pool, const float* se, const float* hid,
                                          const float* maps, const unsigned char* ties, void* dx, float* dgamma,
                                          float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out, int N, int H,
                                          int W, int C, int Cr, float eps, int dtype, pcm_stream_t s) {
+  return pcm_convblock_tail_bwd_sdot(dout, x, out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties, dx, dgamma, dbeta,
+                                     dw1, dw2, dwsp, dq_out, nullptr, N, H, W, C, Cr, eps, dtype, s);
+}
+
+extern "C" int pcm_convblock_tail_bwd_sdot(const void* dout, const void* x, const void* out, const float* stats,
+                                           const float* gamma, const float* beta, const float* w1, const float* w2,
+                                           const float* wsp, const float* pool, const float* se, const float* hid,
+                                           const float* maps, const unsigned char* ties, void* dx, float* dgamma,
+                                           float* dbeta, float* dw1, float* dw2, float* dwsp, float* dq_out,
+                                           const float* sdot, int N, int H, int W, int C, int Cr, float eps, int dtype,
+                                           pcm_stream_t s) {
   PCM_REQUIRE(fused_shape_ok(H, W, C, Cr), "convblock_tail_bwd: unsupported shape H=%d W=%d C=%d Cr=%d", H, W, C, Cr);
   if (N == 0) return PCM_OK;
   const size_t smem = tail_smem_layout(H, W, C, dtype == PCM_BF16 ? 2 : 4, 1, 1).total;
   PCM_REQUIRE(smem <= 227 * 1024, "convblock_tail_bwd: image does not fit shared memory (%zu B)", smem);
-  PCM_REQUIRE(out != nullptr && maps != nullptr && ties != nullptr, "convblock_tail_bwd: the forward tail's saved out / maps / ties are required");
+  PCM_REQUIRE((out != nullptr || sdot != nullptr) && maps != nullptr && ties != nullptr,
+              "convblock_tail_bwd: the forward tail's saved out (or sdot) / maps / ties are required");
   PCM_REQUIRE(((uintptr_t)x & 15) == 0, "convblock_tail_bwd: x must be 16-byte aligned (bulk copy)");
   int rc = PCM_OK;
   PCM_DISPATCH_DTYPE(dtype, T, {
@@ -1870,7 +1901,7 @@ extern "C" int pcm_convblock_tail_bwd_dq(const void* dout, const void* x, const 
     if (rc == PCM_OK)
       pcm::launch(convblock_tail_bwd_kernel<T>, N, threads, bytes, (cudaStream_t)s,
           (const T*)dout, (const T*)x, (const T*)out, stats, gamma, beta, w1, w2, wsp, pool, se, hid, maps, ties,
-          (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, dq_out, H, W, C, Cr, eps, scr);
+          (T*)dx, dgamma, dbeta, dw1, dw2, dwsp, dq_out, sdot, H, W, C, Cr, eps, scr);
   });
   if (rc != PCM_OK) return rc;
   return check_launch("convblock_tail_bwd");

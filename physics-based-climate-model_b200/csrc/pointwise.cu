@@ -196,11 +196,16 @@ maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, in
 // dx = [x is the FIRST max of its window (scan order)] * dy + dskip/T.  One thread per 2x2 window and channel block:
 // the four x vectors are read once (not once per output pixel), nine independent 16-byte loads are in flight per
 // thread, and the index arithmetic is 32-bit whenever the tensor allows it (I = int).
-template <typename T, typename I>
-__global__ void __launch_bounds__(256)
+template <typename T, typename I, bool DOT>
+__global__ void __launch_bounds__(256, 4)
 maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ dskip,
-                         long long dskip_ns, int dskip_ps, T* __restrict__ dx, int N, int H, int W, int C, int Tn,
-                         int t_major) {
+                         long long dskip_ns, int dskip_ps, T* __restrict__ dx, float* __restrict__ sdot, int N, int H, int W,
+                         int C, int Tn, int t_major) {
+  // DOT: also sdot[n][h][w] = sum_c dx(n,h,w,c) * x(n,h,w,c), with dx as the storage type rounds it — the sum the next
+  // kernel of the backward chain (the ConvBlock tail whose output x is) needs for its gate gradient; both operands pass
+  // through this thread, so that kernel does not have to stream dx and x a second time.  x is RE-LOADED per pixel for the
+  // product (an L1 hit: this thread read the same 16 bytes for the arg-max a moment ago): holding the 2x2 window of x in
+  // registers until the end doubled the register count and cost more than the re-load (37 vs 29 us at 48x72x16).
   PCM_PDL_ENTRY();
   const int Ho = H / 2, Wo = W / 2, Hc = (H + 1) / 2, Wc = (W + 1) / 2, cv = C / 8;
   const float invT = 1.f / (float)Tn;
@@ -251,9 +256,34 @@ maxpool2_bwd_skip_kernel(const T* __restrict__ x, const T* __restrict__ dy, cons
         }
       }
     }
+    float sd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (live[k]) store8(dx + base + offs[k], o[k]);
+    for (int k = 0; k < 4; ++k) {
+      if (live[k]) {
+        store8(dx + base + offs[k], o[k]);
+        if (DOT) {
+          float qk[8];
+          load8(x + base + offs[k], qk);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sd[k] = fmaf(round_to<T>(o[k][j]), qk[j], sd[k]);
+        }
+      }
+    }
+    if (DOT) {
+      // the cv threads of a 2x2 window are adjacent lanes (cb = idx % cv, cv a power of two <= 32 dividing the grid
+      // stride) and run the same iterations, so the shuffles are convergent within the group
+      const unsigned lane = threadIdx.x & 31u, grp = (lane / (unsigned)cv) * (unsigned)cv;
+      const unsigned mask = cv == 32 ? 0xffffffffu : ((1u << cv) - 1u) << grp;
+      for (int off = 1; off < cv; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sd[k] += __shfl_xor_sync(mask, sd[k], off);
+      }
+      if (cb == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (live[k]) sdot[((size_t)n * H + h0 + (k >> 1)) * W + w0 + (k & 1)] = sd[k];
+      }
+    }
   }
 }
 
@@ -659,20 +689,37 @@ extern "C" int pcm_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int
   return check_launch("maxpool2_fwd");
 }
 
+extern "C" int pcm_maxpool2_bwd_skip_dot(const void* x, const void* dy, const void* dskip, long long dskip_ns,
+                                         int dskip_ps, void* dx, float* sdot, int N, int H, int W, int C, int T_,
+                                         int t_major, int dtype, pcm_stream_t s);
 extern "C" int pcm_maxpool2_bwd_skip(const void* x, const void* dy, const void* dskip, long long dskip_ns,
                                      int dskip_ps, void* dx, int N, int H, int W, int C, int T_, int t_major,
                                      int dtype, pcm_stream_t s) {
+  return pcm_maxpool2_bwd_skip_dot(x, dy, dskip, dskip_ns, dskip_ps, dx, nullptr, N, H, W, C, T_, t_major, dtype, s);
+}
+
+extern "C" int pcm_maxpool2_bwd_skip_dot(const void* x, const void* dy, const void* dskip, long long dskip_ns,
+                                         int dskip_ps, void* dx, float* sdot, int N, int H, int W, int C, int T_,
+                                         int t_major, int dtype, pcm_stream_t s) {
   PCM_REQUIRE(C % 8 == 0 && T_ >= 1 && N % T_ == 0, "maxpool2_bwd_skip: bad shape");
+  if (sdot != nullptr) {
+    const int cv = C / 8;
+    PCM_REQUIRE(cv <= 32 && (cv & (cv - 1)) == 0, "maxpool2_bwd_skip_dot: C/8 must be a power of two <= 32 (C=%d)", C);
+  }
   if (N == 0) return PCM_OK;
   const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   if (total + (long long)kGridCap * 256 < 0x7fffffffLL) {
-    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(maxpool2_bwd_skip_kernel<T, int>, grid_for(total), 256, 0, (cudaStream_t)s,
-                                     (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps, (T*)dx, N, H, W, C,
-                                     T_, t_major)));
+    PCM_DISPATCH_DTYPE(dtype, T, {
+      auto kern = sdot != nullptr ? maxpool2_bwd_skip_kernel<T, int, true> : maxpool2_bwd_skip_kernel<T, int, false>;
+      pcm::launch(kern, grid_for(total), 256, 0, (cudaStream_t)s, (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps,
+                  (T*)dx, sdot, N, H, W, C, T_, t_major);
+    });
   } else {
-    PCM_DISPATCH_DTYPE(dtype, T, (pcm::launch(maxpool2_bwd_skip_kernel<T, long long>, grid_for(total), 256, 0, (cudaStream_t)s,
-                                     (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps, (T*)dx, N, H, W, C,
-                                     T_, t_major)));
+    PCM_DISPATCH_DTYPE(dtype, T, {
+      auto kern = sdot != nullptr ? maxpool2_bwd_skip_kernel<T, long long, true> : maxpool2_bwd_skip_kernel<T, long long, false>;
+      pcm::launch(kern, grid_for(total), 256, 0, (cudaStream_t)s, (const T*)x, (const T*)dy, (const T*)dskip, dskip_ns, dskip_ps,
+                  (T*)dx, sdot, N, H, W, C, T_, t_major);
+    });
   }
   return check_launch("maxpool2_bwd_skip");
 }

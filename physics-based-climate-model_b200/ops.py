@@ -411,6 +411,42 @@ import os as _os
 # opt-in (measured neutral: the stand-alone kernel costs the side stream more than the tail saves, profiles/r2_experiments.md)
 _GATE_WGRAD_SIDE = _os.environ.get("PCM_GATE_WGRAD_SIDE", "0") == "1"
 
+# The backward of MaxPool2d (+ time-mean skip) holds the gradient it produces and the block output it routes through in
+# registers, and the ConvBlock backward that runs NEXT needs exactly their per-pixel product sum (the gate gradient):
+# the pooling kernel writes it (pcm_maxpool2_bwd_skip_dot) and hands it over through this one-entry slot.  The slot
+# keeps the gradient tensor alive (its address cannot be reused for something else meanwhile) and is emptied by the
+# next ConvBlock backward whatever it finds.  PCM_POOL_SDOT=0: the tail streams dout and out itself.
+_SDOT_SLOT = None          # (gradient tensor, sdot tensor)
+
+
+def _pool_sdot_enabled() -> bool:
+    return _os.environ.get("PCM_POOL_SDOT", "1") != "0"
+
+
+def _offer_sdot(ds: torch.Tensor):
+    """Called by the pooling backward before its launch: the (N*H*W,) fp32 buffer to fill, or None."""
+    global _SDOT_SLOT
+    _SDOT_SLOT = None
+    N, H, W, C = ds.shape
+    cv = C // 8
+    if not _pool_sdot_enabled() or C % 8 or cv > 32 or cv & (cv - 1):
+        return None
+    sdot = torch.empty(N * H * W, device=ds.device, dtype=torch.float32)
+    _SDOT_SLOT = (ds, sdot)
+    return sdot
+
+
+def _take_sdot(dout: torch.Tensor):
+    """Called by every ConvBlock backward: the sum for exactly this gradient tensor, or None.  Empties the slot."""
+    global _SDOT_SLOT
+    slot, _SDOT_SLOT = _SDOT_SLOT, None
+    if slot is None:
+        return None
+    ds, sdot = slot
+    if ds.data_ptr() == dout.data_ptr() and ds.shape == dout.shape and ds.dtype == dout.dtype and dout.is_contiguous():
+        return sdot
+    return None
+
 
 def wgrad_group(dtype, Co: int, Ci: int, W: int, dense: bool = True) -> int:
     """Pixel-group factor of the tensor-core weight gradient (pcm_wgrad3x3_tc_grouped) for the thin layers; 1 = plain.
@@ -723,6 +759,7 @@ class ConvBlockFn(torch.autograd.Function):
     def backward(ctx, dout):
         if ctx.fused:
             return ConvBlockFn._backward_fused(ctx, dout)
+        _take_sdot(dout)                                # not used on this path; the slot must not outlive this backward
         x, y1, a1, y2, a2, small, se, maps, w1, g1, b1, w2, g2, b2, sw1, sw2, wsp = ctx.saved_tensors
         N, H, W, Cip, Ci, Co, Cr = ctx.dims
         P, G, dt, dev = H * W, GN_GROUPS, x.dtype, x.device
@@ -779,6 +816,7 @@ class ConvBlockFn(torch.autograd.Function):
         N, H, W, Cip, Ci, Co, Cr = ctx.dims
         G, dt = GN_GROUPS, x.dtype
         d, st = _DT[dt], _s()
+        sdot = _take_sdot(dout)        # per-pixel sum_c dout*out, when the pooling backward that produced dout formed it
         dout = dout.contiguous()
         stats1, stats2, pool = small[: N * G * 2], small[N * G * 2: N * G * 4], small[N * G * 4:]
         hid = se[N * Co:]
@@ -790,17 +828,17 @@ class ConvBlockFn(torch.autograd.Function):
             # the gate-weight gradient (98 sums per image, 11 % of the tail's instructions) leaves the critical path: the
             # tail writes dq, pcm_gate_wgrad accumulates dwsp for all images on the side stream
             dq = torch.empty(N * H * W, device=dout.device, dtype=torch.float32)
-            _call("pcm_convblock_tail_bwd_dq", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
+            _call("pcm_convblock_tail_bwd_sdot", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
                   b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(),
                   hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(),
-                  gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), dq.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
+                  gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), dq.data_ptr(), _p(sdot), N, H, W, Co, Cr, GN_EPS, d, st)
             with side_stream(dq, maps):
                 _call("pcm_gate_wgrad", dq.data_ptr(), maps.data_ptr(), gsp.data_ptr(), N, H, W, _s())
         else:
-            _call("pcm_convblock_tail_bwd", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
+            _call("pcm_convblock_tail_bwd_sdot", dout.data_ptr(), y2.data_ptr(), out.data_ptr(), stats2.data_ptr(), g2.data_ptr(),
                   b2.data_ptr(), sw1.data_ptr(), sw2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(),
                   hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dy2.data_ptr(), gg2.data_ptr(), gb2.data_ptr(),
-                  gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), N, H, W, Co, Cr, GN_EPS, d, st)
+                  gs1.data_ptr(), gs2.data_ptr(), gsp.data_ptr(), 0, _p(sdot), N, H, W, Co, Cr, GN_EPS, d, st)
         with side_stream(dy2, a1):
             conv3x3_wgrad(dy2, a1, gw2, N, H, W, Co, Co, Co)
         gb = conv_group(dt, Co, Co, W)
@@ -857,8 +895,9 @@ class PoolSkipFn(torch.autograd.Function):
             # dskip may be a channel-slice view of the decoder's concat gradient: pass its strides
             assert dskip.stride(3) == 1 and dskip.stride(1) == W * dskip.stride(2)
             ns, ps = dskip.stride(0), dskip.stride(2)
-        _call("pcm_maxpool2_bwd_skip", s.data_ptr(), _p(dp), _p(dskip), ns, ps, ds.data_ptr(), N, H, W, C, ctx.T, 1,
-              _DT[s.dtype], _s())
+        sdot = _offer_sdot(ds)
+        _call("pcm_maxpool2_bwd_skip_dot", s.data_ptr(), _p(dp), _p(dskip), ns, ps, ds.data_ptr(), _p(sdot), N, H, W, C,
+              ctx.T, 1, _DT[s.dtype], _s())
         return ds, None, None
 
 
@@ -879,8 +918,9 @@ class MaxPoolFn(torch.autograd.Function):
         (s,) = ctx.saved_tensors
         N, H, W, C = s.shape
         ds = torch.empty_like(s)
-        _call("pcm_maxpool2_bwd_skip", s.data_ptr(), dpooled.contiguous().data_ptr(), 0, 0, 0, ds.data_ptr(), N, H, W,
-              C, 1, 0, _DT[s.dtype], _s())
+        sdot = _offer_sdot(ds)
+        _call("pcm_maxpool2_bwd_skip_dot", s.data_ptr(), dpooled.contiguous().data_ptr(), 0, 0, 0, ds.data_ptr(), _p(sdot),
+              N, H, W, C, 1, 0, _DT[s.dtype], _s())
         return ds
 
 

@@ -385,11 +385,13 @@ def test_side_stream_matches_single_stream(G, dtype, monkeypatch):
     assert float((p0 - p1).norm() / p0.norm()) < tol
 
 
-@pytest.mark.parametrize("switch", ["PCM_BUCKETS_SINGLE", "PCM_HEAD_MSE", "PCM_CONV_GROUP", "PCM_WGRAD_GROUP", "PCM_TAIL_WAVES"])
+@pytest.mark.parametrize("switch", ["PCM_BUCKETS_SINGLE", "PCM_HEAD_MSE", "PCM_CONV_GROUP", "PCM_WGRAD_GROUP", "PCM_TAIL_WAVES",
+                                    "PCM_POOL_SDOT", "PCM_TAIL_SCRATCH"])
 def test_step_variants_agree(G, switch, monkeypatch):
     """Every scheduling / kernel-form switch of the captured step — gradient buckets with per-bucket fold + Adam on the
     communication stream at world size 1, the fused head + loss, the pixel-group forms of the thin convolutions and weight
-    gradients, the per-launch CTA width of the tails — must leave losses and parameters where the plain variant puts them
+    gradients, the per-launch CTA width of the tails, the gate-gradient sum handed from the pooling backward to the block
+    backward, the shared-memory scratch of the level-1 backward tails — must leave losses and parameters where the plain variant puts them
     (same mathematics; only fp32 summation order and bf16 rounding of equal sums may differ)."""
     import pcm_b200
     from oracle import model_oracle as O

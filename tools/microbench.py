@@ -142,6 +142,8 @@ def bench_tails(args):
             ("gn_silu_img_bwd", 3, lambda: _call("pcm_gn_silu_img_bwd", dout.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), N, H, W, C, 1e-5, d, _s())),
             ("convblock_tail_bwd", 4, lambda: _call("pcm_convblock_tail_bwd", dout.data_ptr(), x.data_ptr(), y.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dw1.data_ptr(), dw2.data_ptr(), dwsp.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())),
         ]
+        sdot = torch.randn(N * P, device="cuda")
+        cases.append(("convblock_tail_bwd_sdot", 3, lambda: _call("pcm_convblock_tail_bwd_sdot", dout.data_ptr(), x.data_ptr(), y.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w1.data_ptr(), w2.data_ptr(), wsp.data_ptr(), pool.data_ptr(), se.data_ptr(), hid.data_ptr(), maps.data_ptr(), ties.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dw1.data_ptr(), dw2.data_ptr(), dwsp.data_ptr(), 0, sdot.data_ptr(), N, H, W, C, Cr, 1e-5, d, _s())))
         cases[1][2]()                      # populate stats / pool / se / hid for the backward kernels
         for name, ntens, fn in cases:
             if args.only and args.only not in name:
