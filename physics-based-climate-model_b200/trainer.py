@@ -367,13 +367,13 @@ class TrainStep:
             self._staged = torch.cuda.Event()
             self._alt_buffers()
         main = torch.cuda.current_stream(self.device)
+        loss = self.run()                                       # the step is launched FIRST: the host-side set-up of the
+        self._free_cur.record(main)                             # copies below then overlaps it instead of delaying it
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._free_alt)        # its previous contents have been consumed
             self._x_alt.copy_(x_next, non_blocking=True)
             self._y_alt.copy_(y_next, non_blocking=True)
             self._staged.record()
-        loss = self.run()
-        self._free_cur.record(main)                             # the current pair may be overwritten from here on
         main.wait_event(self._staged)                           # the next step (any stream order) sees the staged batch
         self.x, self._x_alt = self._x_alt, self.x
         self.y, self._y_alt = self._y_alt, self.y

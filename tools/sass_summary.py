@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "physics-based-climate-model_b200", "libpcm_b200.so")
-KEYS = ["UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "UCGABAR", "MAPA", "SYNCS", "HMMA", "REDG", "MUFU.TANH"]
+KEYS = ["UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "UCGABAR", "MAPA", "SYNCS", "HMMA", "REDG", "MUFU.TANH", "FFMA2", "FMUL2", "FADD2"]
 
 
 def demangle(names):
@@ -28,7 +28,7 @@ def main():
             counts[fn]["_n"] = 0
             order.append(fn)
             continue
-        if fn and re.search(r"/\*[0-9a-f]{4}\*/", line):
+        if fn and re.search(r"/\*[0-9a-f]{4,}\*/", line):
             counts[fn]["_n"] += 1
             for k in KEYS:
                 if re.search(r"\b" + re.escape(k), line):
@@ -40,16 +40,17 @@ def main():
     print(f"{len(rows)} kernels in the library; {len(tc)} use tcgen05 / TMEM / TMA / bulk copies / clusters.  "
           f"Legacy `HMMA` (mma.sync) instructions in the whole library: {sum(c['HMMA'] for _, c in rows)}.\n")
     print("| kernel | SASS instr | UTCHMMA (tcgen05.mma) | LDTM (tcgen05.ld) | UTMALDG (TMA tensor) | UBLKCP (bulk copy) | "
-          "UCGABAR (cluster barrier) | MAPA (DSMEM) | MUFU.TANH |")
-    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+          "UCGABAR (cluster barrier) | MAPA (DSMEM) | MUFU.TANH | FFMA2 / FMUL2 / FADD2 (packed fp32) |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     for n, c in sorted(tc, key=lambda r: r[0]):
         print(f"| `{n[:88]}` | {c['_n']} | {c['UTCHMMA']} | {c['LDTM']} | {c['UTMALDG']} | {c['UBLKCP']} | {c['UCGABAR']} | "
-              f"{c['MAPA']} | {c['MUFU.TANH']} |")
+              f"{c['MAPA']} | {c['MUFU.TANH']} | {c['FFMA2'] + c['FMUL2'] + c['FADD2']} |")
     tot = {k: sum(c[k] for _, c in rows) for k in KEYS}
     print(f"\nTotals: " + ", ".join(f"{k} {v}" for k, v in tot.items()))
     print("\nNotes: `mapa.shared::cluster` + `st.shared::cluster` (distributed shared memory, convlstm_seq_*) compile to address "
           "arithmetic and generic `ST.E.128` stores into the shared::cluster window, so the MAPA column stays 0; the cluster "
-          "barrier is `UCGABAR_ARV` / `UCGABAR_WAIT`.  `MUFU.TANH` = the one-instruction tanh.approx used for sigmoid / tanh / SiLU.")
+          "barrier is `UCGABAR_ARV` / `UCGABAR_WAIT`.  `MUFU.TANH` = the one-instruction tanh.approx used for sigmoid / tanh / SiLU; "
+          "`FFMA2` / `FMUL2` / `FADD2` = packed fp32 pairs (fma / mul / add .rn.f32x2, sm_100+), used by the backward tails.")
 
 
 if __name__ == "__main__":
