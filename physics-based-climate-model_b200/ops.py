@@ -429,7 +429,11 @@ def _offer_sdot(ds: torch.Tensor):
     _SDOT_SLOT = None
     N, H, W, C = ds.shape
     cv = C // 8
-    if not _pool_sdot_enabled() or C % 8 or cv > 32 or cv & (cv - 1):
+    if not _pool_sdot_enabled() or C % 8 or cv > 32 or cv & (cv - 1) or ds.dtype not in _DT:
+        return None
+    # only the shared-memory resident tail takes the sum (SEBlock ratio 8: Cr = C // 8); images that do not fit one SM
+    # (config 5) go through the multi-kernel path, which forms dq itself
+    if ds.is_cuda and not lib()._fn["pcm_convblock_fused_supported"](H, W, C, max(C // 8, 1), _DT[ds.dtype]):
         return None
     sdot = torch.empty(N * H * W, device=ds.device, dtype=torch.float32)
     _SDOT_SLOT = (ds, sdot)

@@ -198,3 +198,32 @@ def test_product_synth_recipe_equals_the_oracle_recipe():
             names = [a.name for a in node.names]
             assert not mod.startswith("oracle") and not any(n.startswith("oracle") for n in names), \
                 "bench.py run_ours must not import oracle (only its baseline legs may)"
+
+
+def test_gate_sum_handover_slot(built, monkeypatch):
+    """ops._offer_sdot / ops._take_sdot (host logic of the pooling-backward -> block-backward hand-over): the sum is
+    delivered only to the backward that receives exactly the gradient tensor it was formed for, the slot never outlives
+    the next ConvBlock backward, and PCM_POOL_SDOT=0 / unsupported channel counts disable it."""
+    from pcm_b200 import ops
+    monkeypatch.delenv("PCM_POOL_SDOT", raising=False)
+    ds = torch.zeros(2, 4, 6, 16)
+    s = ops._offer_sdot(ds)
+    assert s is not None and s.shape == (2 * 4 * 6,) and s.dtype == torch.float32
+    assert ops._take_sdot(ds) is s                      # same tensor: delivered
+    assert ops._take_sdot(ds) is None                   # ... once
+    s = ops._offer_sdot(ds)
+    other = torch.zeros(2, 4, 6, 16)
+    assert ops._take_sdot(other) is None                # another gradient: not delivered, and the slot is emptied
+    assert ops._take_sdot(ds) is None
+    s = ops._offer_sdot(ds)
+    assert ops._take_sdot(ds.view(2, 4, 6, 16)) is s    # a view with the same address / shape is the same data
+    assert ops._offer_sdot(torch.zeros(1, 2, 2, 24)) is None          # C/8 = 3 is not a power of two
+    assert ops._offer_sdot(torch.zeros(1, 2, 2, 12)) is None          # C % 8 != 0
+    assert ops._take_sdot(ds) is None                   # a refused offer leaves the slot empty
+    monkeypatch.setenv("PCM_POOL_SDOT", "0")
+    assert ops._offer_sdot(ds) is None
+    # the support query the offer consults on the device is host-only arithmetic (no GPU needed): the level-1 image of
+    # config 3 fits one SM in bf16, the config-5 one does not
+    L = _lib.lib()
+    assert L._fn["pcm_convblock_fused_supported"](48, 72, 16, 2, 1) == 1
+    assert L._fn["pcm_convblock_fused_supported"](184, 360, 32, 4, 1) == 0
