@@ -227,3 +227,29 @@ def test_gate_sum_handover_slot(built, monkeypatch):
     L = _lib.lib()
     assert L._fn["pcm_convblock_fused_supported"](48, 72, 16, 2, 1) == 1
     assert L._fn["pcm_convblock_fused_supported"](184, 360, 32, 4, 1) == 0
+
+
+def test_cost_model_of_the_gate_sum_entry_points(built):
+    """costmodel.algo_cost (bench.py's roofline numerators) for the session-4 entry points: with the per-pixel gate sum
+    supplied the backward tail's algorithm is dout + x in, dx out (+ 13 bytes of maps / ties and 4 bytes of sum per pixel);
+    without it, it is pcm_convblock_tail_bwd's four tensors.  Argument order comes from the parsed header."""
+    from pcm_b200 import costmodel
+    names = [an for _, an in _lib.PROTOS["pcm_convblock_tail_bwd_sdot"][1]]
+    vals = {"N": 384, "H": 48, "W": 72, "C": 16, "Cr": 2, "dtype": 1}
+    px = 384 * 48 * 72
+
+    def args(**over):
+        return [over.get(n, vals.get(n, 1)) for n in names]                # non-zero stand-ins for pointers
+
+    fl, by, bound = costmodel.algo_cost("pcm_convblock_tail_bwd_sdot", args(dq_out=0))
+    assert (fl, bound) == (0.0, "hbm") and by == 3 * px * 16 * 2 + 17 * px
+    _, by0, _ = costmodel.algo_cost("pcm_convblock_tail_bwd_sdot", args(dq_out=0, sdot=0))
+    names_old = [an for _, an in _lib.PROTOS["pcm_convblock_tail_bwd"][1]]
+    _, by_old, _ = costmodel.algo_cost("pcm_convblock_tail_bwd", [vals.get(n, 1) for n in names_old])
+    assert by0 == by_old == 4 * px * 16 * 2 + 13 * px
+    assert costmodel.shape_key("pcm_convblock_tail_bwd_sdot", args()) == "convblock_tail_bwd_sdot[384,48,72,16,2]"
+    names_p = [an for _, an in _lib.PROTOS["pcm_maxpool2_bwd_skip_dot"][1]]
+    vp = {"N": 384, "H": 48, "W": 72, "C": 16, "T": 6, "t_major": 1, "dtype": 1}
+    _, byp, _ = costmodel.algo_cost("pcm_maxpool2_bwd_skip_dot", [vp.get(n, 1) for n in names_p])
+    _, byq, _ = costmodel.algo_cost("pcm_maxpool2_bwd_skip_dot", [0 if n == "sdot" else vp.get(n, 1) for n in names_p])
+    assert byp - byq == 4 * px
